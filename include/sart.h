@@ -1,0 +1,298 @@
+/* sart.h — C-ABI boundary of the B200-native solar-axion ray tracer.
+ *
+ * This header is the drop-in seam for ONE path of jovoy/SolarAxionRayTracing:
+ * the per-ray pipeline `traceAxion` (src/raytracer.nim:1736-2221) as driven by
+ * `traceAxionWrapper` (src/raytracer.nim:2223-2244) from
+ * `calculateFluxFractions` (src/raytracer.nim:2755-2776), plus the weighted
+ * detector histogram `prepareHeatmap` (src/raytracer.nim:818-842) that
+ * consumes its output and the CDF build in `initFullSetup`
+ * (src/raytracer.nim:2679-2705) that feeds it.
+ *
+ * The reference has no FFI for this path; each entry point below names the
+ * Nim proc (file:line) whose role it takes. INTEGRATION.md shows the Nim
+ * `{.importc, dynlib.}` stubs a maintainer would add.
+ *
+ * Conventions: plain C, no exceptions cross the boundary, every function
+ * returns 0 on success and a negative sart_status on failure; the message is
+ * available from sart_last_error() (thread-local). A handle owns one CUDA
+ * device and one stream and is not thread-safe. All host pointers are owned by
+ * the caller; tables and setup are copied at sart_create(). There is NO CPU
+ * fallback: without a CUDA device sart_create() fails with SART_ERR_CUDA.
+ */
+#ifndef SART_H
+#define SART_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SART_ABI_VERSION 1
+#define SART_MAX_SHELLS 64   /* XMM has 58 shells (raytracer.nim:1289-1313) */
+#define SART_MAX_COATINGS 8  /* LLNL has 4 coating recipes (raytracer.nim:1167) */
+#define SART_IMAGE_BINS 256  /* prepareHeatmap(256, 256, ...) raytracer.nim:2629 */
+#define SART_MAX_MASSES 64   /* axion masses traced per launch in a mass scan */
+
+typedef enum {
+  SART_OK = 0,
+  SART_ERR_ARG = -1,     /* bad argument */
+  SART_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+  SART_ERR_CONFIG = -3,  /* unsupported setup combination (reference: doAssert false) */
+  SART_ERR_NOMEM = -4
+} sart_status;
+
+/* ---- enums mirroring the reference's (raytracer.nim:16-46, 59-64, 164-167, 223-230) ---- */
+typedef enum { SART_ES_CAST = 0, SART_ES_BABYIAXO = 1 } sart_experiment_kind;
+typedef enum { SART_TK_LLNL = 0, SART_TK_XMM = 1, SART_TK_CUSTOM_BABYIAXO = 2,
+               SART_TK_ABRIXAS = 3, SART_TK_OTHER = 4 } sart_telescope_kind;
+typedef enum { SART_SK_VACUUM = 0, SART_SK_GAS = 1 } sart_stage_kind;
+typedef enum { SART_DK_INGRID2017 = 0, SART_DK_INGRID2018 = 1, SART_DK_INGRIDIAXO = 2 } sart_detector_kind;
+typedef enum { SART_WY_2017 = 0, SART_WY_2018 = 1, SART_WY_IAXO = 2 } sart_window_year;
+typedef enum { SART_HT_NONE = 0, SART_HT_CROSS = 1, SART_HT_STAR = 2, SART_HT_CIRCLE = 3,
+               SART_HT_SQUARE = 4, SART_HT_DIAMOND = 5 } sart_hole_type;
+typedef enum { SART_RK_EFFECTIVE_AREA = 0, SART_RK_SINGLE_COATING = 1,
+               SART_RK_MULTI_COATING = 2 } sart_reflectivity_kind;
+
+/* ConfigFlags (raytracer.nim:223-230) as a bit set: bit = ordinal of the Nim enum. */
+enum {
+  SART_CF_IGNORE_DET_WINDOW = 1u << 0,
+  SART_CF_IGNORE_GAS_ABS = 1u << 1,
+  SART_CF_IGNORE_REFLECTION = 1u << 2,
+  SART_CF_IGNORE_CONV_PROB = 1u << 3,
+  SART_CF_XRAY_TEST = 1u << 4,
+  SART_CF_READ_MAGNET_CONFIG = 1u << 5,
+  SART_CF_READ_DET_INSTALL_CONFIG = 1u << 6
+};
+
+/* Where a ray left traceAxion (one value per early `return` of raytracer.nim:1736-2221). */
+typedef enum {
+  SART_EXIT_PASSED = 0,         /* reached the end, weight != 0        rt:2220 */
+  SART_EXIT_MISSED_BORE = 1,    /* no entrance disc, no single wall hit rt:1825 */
+  SART_EXIT_CLIP_EXIT_CB = 2,   /* rt:1846-1848 */
+  SART_EXIT_CLIP_PIPE_VT3 = 3,  /* rt:1856-1858 */
+  SART_EXIT_CLIP_PIPE_XRT = 4,  /* rt:1866-1868 */
+  SART_EXIT_OPAQUE = 5,         /* spider / blocker                      rt:1910-1914 */
+  SART_EXIT_OUTSIDE_SHELLS = 6, /* rt:1934 */
+  SART_EXIT_GLASS_FRONT = 7,    /* rt:1942-1944 */
+  SART_EXIT_NICKEL = 8,         /* rt:2040-2046 */
+  SART_EXIT_NO_MIRROR_HIT = 9,  /* almostEqual test                      rt:2051-2057 */
+  SART_EXIT_WINDOW_APERTURE = 10, /* rt:2139-2147 */
+  SART_EXIT_ZERO_WEIGHT = 11,   /* reached the end with weight == 0      rt:2220 */
+  SART_EXIT_COLLIMATOR = 12,    /* X-ray test source only                rt:1800-1801 */
+  SART_N_EXIT_CODES = 13
+} sart_exit_code;
+/* `code` words carry the exit code in bits 0..7 and these flags above it. */
+#define SART_CODE_MASK 0xff
+#define SART_FLAG_PASSED_TILL_WINDOW 0x100 /* Axion.passedTillWindow rt:2135-2136 */
+#define SART_FLAG_INTERP_CLAMPED 0x200     /* an interpolation argument left its grid; the reference would raise */
+
+/* ---- setup: the read-only parameters of FullRaytraceSetup (raytracer.nim:232-242) as one POD ---- */
+typedef struct {
+  double lengthColdbore, B, lengthB, radiusCB, pGasRoom, tGas; /* Magnet rt:83-89 (mm, T, mm, mm, bar, K) */
+} sart_magnet_t;
+
+typedef struct {
+  double cb2vt3_length, cb2vt3_radius;   /* Pipes.coldBoreToVT3 rt:125-140 */
+  double vt3xrt_length, vt3xrt_radius;   /* Pipes.vt3ToXRT */
+  double distanceCBAxisXRTAxis;
+  double pipesTurned;                    /* degree */
+} sart_pipes_t;
+
+typedef struct {
+  int32_t kind;                 /* sart_telescope_kind */
+  int32_t nShells;
+  int32_t numberOfHoles;
+  int32_t holeType;             /* sart_hole_type */
+  int32_t reflKind;             /* sart_reflectivity_kind */
+  int32_t nCoatings;
+  int32_t layers[SART_MAX_COATINGS]; /* Reflectivity.layers rt:78 */
+  double optics_entrance[3], optics_exit[3];
+  double telescope_turned_x, telescope_turned_y; /* degree */
+  double lMirror, holeInOptics;
+  double allThickness[SART_MAX_SHELLS];
+  double allR1[SART_MAX_SHELLS];
+  double allXsep[SART_MAX_SHELLS];
+  double allAngles[SART_MAX_SHELLS];  /* degree */
+} sart_telescope_t;               /* Telescope rt:91-105 */
+
+typedef struct {
+  int32_t active, parallel;
+  double energy, distance, radius, offAxisUp, offAxisLeft, activity, lengthCol;
+} sart_test_source_t;             /* TestXraySource rt:108-122 */
+
+typedef struct {
+  double distanceDetectorXRT, distanceWindowFocalPlane, lateralShift, transversalShift;
+} sart_detector_install_t;        /* DetectorInstallation rt:146-153 */
+
+typedef struct {
+  int32_t windowYear;             /* sart_window_year */
+  int32_t numberOfStrips;
+  double stripDistWindow, stripWidthWindow, detectorWindowAperture;
+  double theta;                   /* rad */
+  double radiusWindow, openApertureRatio, windowThickness, alThickness, depthDet;
+} sart_detector_t;                /* DetectorSetup rt:170-184 (interpolators live in sart_tables_t) */
+
+typedef struct {
+  double radiusSun, distanceSunEarth; /* rt:249-250 */
+  double roomTemp, mAxion, g_agamma;  /* rt:254-256 (K, eV, GeV^-1) */
+  double chipXMax, chipYMax;          /* rt:260-266 */
+  double tesla_to_eV2;                /* unchained toNaturalUnit(T)      */
+  double m_to_inv_eV;                 /* unchained toNaturalUnit(m)      */
+  double exposureFactor;              /* rt:2207-2212 (1.0 with cfXrayTest) */
+} sart_consts_t;
+
+typedef struct {
+  uint32_t abi_version;           /* SART_ABI_VERSION */
+  uint32_t flags;                 /* SART_CF_* bit set */
+  int32_t experiment;             /* sart_experiment_kind */
+  int32_t stage;                  /* sart_stage_kind */
+  int32_t detectorKind;           /* sart_detector_kind */
+  int32_t reserved0;
+  sart_magnet_t magnet;
+  sart_pipes_t pipes;
+  sart_telescope_t telescope;
+  sart_test_source_t testSource;
+  sart_detector_install_t detectorInstall;
+  sart_detector_t detector;
+  sart_consts_t consts;
+} sart_setup_t;                   /* ExperimentSetup rt:155-162 + DetectorSetup + globals */
+
+/* 1-D linear interpolator on a sorted irregular grid (numericalnim newLinear1D; rt:1522-1527). */
+typedef struct { int32_t n; int32_t reserved; const double* x; const double* y; } sart_interp1d_t;
+
+/* ---- tables: everything the reference loads from resources/ for the path ---- */
+typedef struct {
+  /* solar model, after the CDF build of rt:2679-2705 */
+  int32_t nRadii, nEnergies;
+  const double* energies;        /* [nEnergies] keV, ascending                       rt:2657-2662 */
+  const double* fluxRadiusCDF;   /* [nRadii]                                         rt:2705 */
+  const double* diffFluxCDFs;    /* [nRadii][nEnergies] row-major                    rt:2704 */
+  /* reflectivity (angle-major: refl[c][iAngle][iEnergy])                            rt:1174-1208 */
+  int32_t nCoatings, nAngles, nReflEnergies, reserved;
+  double angleMin, angleMax;     /* degree */
+  double reflEnergyMin, reflEnergyMax; /* keV */
+  const double* reflectivity;    /* [nCoatings][nAngles][nReflEnergies] */
+  /* detector chain (keV grids)                                                      rt:1499-1527 */
+  sart_interp1d_t strongbackTransmission, windowTransmission, gasAbsorption;
+  sart_interp1d_t telescopeTransmission; /* only rkEffectiveArea (rt:1245-1249); n = 0 otherwise */
+} sart_tables_t;
+
+/* ---- per-ray outputs (structure of arrays; the Axion record rt:192-221 transposed) ---- */
+typedef struct {
+  /* required */
+  double* x;        /* pointdataX  (chip frame, mm)  rt:2214 */
+  double* y;        /* pointdataY                    rt:2215 */
+  double* w;        /* weights                       rt:2216 */
+  int32_t* code;    /* sart_exit_code | SART_FLAG_*  */
+  int32_t* shell;   /* shellNumber                   rt:2198 (-1 if never assigned) */
+  /* optional: NULL to skip */
+  double* energy;        /* energiesPre / energiesAx   rt:1819, 2197 */
+  double* reflect;       /* rt:2126 */
+  double* transMagnet;   /* transmissionMagnet rt:2120 */
+  double* yaw;           /* yawAngles rt:2123 */
+  double* alpha1;        /* grazing angle on mirror 1, degree */
+  double* alpha2;
+  double* pathCB;        /* rt:1843 */
+  double* r;             /* pointdataR rt:2202 */
+  double* deviationDet;  /* rt:2085 */
+  double* transProbArgon;/* rt:2193 */
+} sart_ray_out_t;
+
+/* Whole-run counters: the stdout counters of generateResultPlots (rt:2253-2257, 2276-2278, 886). */
+typedef struct {
+  uint64_t n_rays;
+  uint64_t n_exit[16];           /* histogram over sart_exit_code */
+  uint64_t n_passed;             /* Axion.passed */
+  uint64_t n_passed_till_window; /* Axion.passedTillWindow */
+  uint64_t n_hit_nickel;         /* Axion.hitNickel */
+  uint64_t n_interp_clamped;     /* rays where an interpolation argument was clamped */
+  double sum_w;                  /* Σ weights | passed  (performAngularScan rt:2800; "total flux" rt:885) */
+  double sum_w2;
+  double sum_x, sum_y, sum_r;    /* unweighted sums over passed rays (means of rt:2276-2278) */
+} sart_counters_t;
+
+typedef struct sart_handle sart_handle_t;
+
+/* ---- library ---- */
+const char* sart_last_error(void);
+int sart_abi_version(void);
+size_t sart_sizeof_setup(void);
+size_t sart_sizeof_tables(void);
+size_t sart_sizeof_counters(void);
+int sart_device_count(void);
+
+/* ---- host-side setup constructors (C++; replace newExperimentSetup rt:1411-1423, newDetectorSetup
+ * rt:1464-1528 minus file I/O, calcWindowVals rt:1431-1462 and the globals rt:248-272). Same defaults as
+ * the reference for every (experiment, detector, stage, telescope) it implements; SART_ERR_CONFIG where the
+ * reference does `doAssert false` (tkOther, tkCustomBabyIAXO). */
+int sart_init_setup(int experiment, int detectorKind, int stage, int telescope, uint32_t flags,
+                    sart_setup_t* out);
+int sart_calc_window_vals(double radiusWindow, int numberOfStrips, double openApertureRatio,
+                          double* width, double* dist);
+
+/* ---- handle ---- */
+/* Copies setup + tables to `device` (HBM), derives the per-shell constant blocks. */
+int sart_create(const sart_setup_t* setup, const sart_tables_t* tables, int device, sart_handle_t** out);
+void sart_destroy(sart_handle_t* h);
+/* Replace the setup of a live handle (tables stay resident): performAngularScan mutates
+ * telescope_turned_y between runs (rt:2794-2798). */
+int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup);
+/* Axion masses for the buffer-gas scan; default is the single value setup.consts.mAxion (rt:255). */
+int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV);
+/* 0 = "exact" FP64 pipeline (bit-faithful classification), 1 = "fast" mixed FP32 pipeline. */
+int sart_set_precision(sart_handle_t* h, int mode);
+void* sart_stream(sart_handle_t* h); /* cudaStream_t the handle launches on */
+
+/* ---- CDF build on the device (replaces rt:2679-2705). emRates is [nRadii][nEnergies] row-major,
+ * radii are fractions of the solar radius. Outputs are host arrays. Sequential per-row sums in the
+ * reference's order, so the result is bit-identical to a scalar loop. */
+int sart_build_cdfs(int device, int nRadii, int nEnergies, const double* radii, const double* energies,
+                    const double* emRates, double* fluxRadiusCDF, double* diffFluxCDFs);
+
+/* ---- tier (a): trace pre-sampled rays. Replaces the body of traceAxion after the sampling block
+ * (rt:1811-2221). origin_xyz = SoA [3][n] (rayOrigin), exit_xy = SoA [2][n] (pointExitCBMagneticField x,y;
+ * z = lengthB), energy_keV [n]. Host buffers; copies are inside the call. */
+int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin_xyz, const double* exit_xy,
+                          const double* energy_keV, const sart_ray_out_t* out);
+/* Same with DEVICE pointers (inputs resident in HBM, outputs left in HBM); asynchronous on sart_stream(). */
+int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin_xyz, const double* d_exit_xy,
+                              const double* d_energy_keV, const sart_ray_out_t* d_out);
+
+/* ---- the literal traceAxionWrapper drop-in (rt:2223-2244): Monte Carlo sampling (rt:1754-1764) from the
+ * counter-based generator Philox4x32-10 (key = seed, counter = global ray index) + trace; per-ray records
+ * out. Host buffers. Ray i of the call is global ray first_ray + i, so any split of a run over calls,
+ * streams or GPUs traces the same rays. */
+int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t seed, const sart_ray_out_t* out);
+
+/* ---- fused run: sample + trace + prepareHeatmap (rt:818-842, 256x256 over the 14x14 mm chip, norm = 1).
+ * Accumulates (+=) into the handle's device-resident image/counters; asynchronous. With M axion masses set
+ * (sart_set_axion_masses) the image is [M][256][256]. */
+int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed);
+int sart_reset_image(sart_handle_t* h);
+/* Device pointers for collectives (ncclAllReduce / torch.distributed on the caller's side). */
+double* sart_image_dev(sart_handle_t* h);       /* [M][256][256] Σw  */
+double* sart_image_w2_dev(sart_handle_t* h);    /* [M][256][256] Σw² */
+void* sart_counters_dev(sart_handle_t* h);      /* sart_counters_t[M] on the device */
+size_t sart_image_len(sart_handle_t* h);        /* M*256*256 */
+/* Synchronise and copy out. image/image_w2 may be NULL. counters is [M]. */
+int sart_read_image(sart_handle_t* h, double* image, double* image_w2, sart_counters_t* counters);
+int sart_synchronize(sart_handle_t* h);
+
+/* ---- prepareHeatmap (rt:818-842), general form, for per-ray records held by the host (e.g. the output of
+ * sart_trace_mc_rays filtered by `passed`): result[floor((y-start_y)/dy)][floor((x-start_x)/dx)] += w/norm on the
+ * GPU. result is a host array [numberOfRows*numberOfColumns], overwritten. Points outside the grid are counted in
+ * *n_out_of_range (may be NULL) instead of raising IndexDefect like the reference. */
+int sart_prepare_heatmap(sart_handle_t* h, int numberOfRows, int numberOfColumns, double start_x, double stop_x,
+                         double start_y, double stop_y, size_t n, const double* data_X, const double* data_Y,
+                         const double* weight1, double norm, double* result, uint64_t* n_out_of_range);
+
+/* ---- Philox helper exported for tests: the 6 uniforms of global ray `ray` in the order the reference
+ * draws them (rt:433-436, 418-419, 464): phi_sun, theta_sun, u_radius, u_disk_r, u_disk_phi, u_energy. */
+void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SART_H */

@@ -1,0 +1,66 @@
+"""Builds libsart.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+Run as ``python -m solaraxionraytracing_b200.build``. nvcc cross-compiles without a GPU. The built library
+stays next to the sources (git-ignored, but it travels to the GPU box with the gpurun snapshot).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libsart.so"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+HOST_CXX = "/usr/bin/g++"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+          "-ccbin", HOST_CXX, "-I", str(HERE.parent / "include")]
+
+# (source, extra flags). The exact pipeline must not contract a*b+c into FMA: its hit/miss decisions are
+# compared bit for bit with the CPU oracle.
+UNITS = [
+    ("kernels_exact.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
+    ("api.cu", []),
+    ("derive.cpp", []),
+    ("host_setup.cpp", []),
+]
+
+
+def _stale(out: Path, deps: list[Path]) -> bool:
+    if not out.exists():
+        return True
+    t = out.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    hdrs = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "sart.h",
+                                                                    Path(__file__)]
+    objdir = HERE / "build"
+    objdir.mkdir(exist_ok=True)
+    objs = []
+    for src, extra in UNITS:
+        s = CSRC / src
+        o = objdir / (src + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [NVCC, *ARCH, *COMMON, *extra, "-c", str(s), "-o", str(o)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), flush=True)
+            subprocess.run(cmd, check=True)
+    if force or _stale(LIB, objs):
+        cmd = [NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(LIB), *map(str, objs)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv)
+    print(LIB)

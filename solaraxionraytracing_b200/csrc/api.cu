@@ -1,0 +1,491 @@
+// api.cu — the C-ABI of libsart.so (include/sart.h): handle lifetime, table upload, launches, read-back.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels.h"
+#include "philox.cuh"
+#include "sart_internal.h"
+
+namespace sart {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(SART_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define SART_CUDA(call)                                  \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int validate(const sart_setup_t* s, const sart_tables_t* t) {
+  if (!s) return fail(SART_ERR_ARG, "setup is NULL");
+  if (s->abi_version != SART_ABI_VERSION) return fail(SART_ERR_ARG, "setup.abi_version %u != %u", s->abi_version, SART_ABI_VERSION);
+  const sart_telescope_t& tel = s->telescope;
+  if (tel.kind != SART_TK_LLNL && tel.kind != SART_TK_XMM && tel.kind != SART_TK_ABRIXAS)
+    return fail(SART_ERR_CONFIG, "The telescope kind %d does not have any opaque structures implemented yet.", tel.kind);
+  if (tel.nShells < 1 || tel.nShells > SART_MAX_SHELLS) return fail(SART_ERR_ARG, "telescope.nShells %d out of range", tel.nShells);
+  if (tel.nCoatings < 0 || tel.nCoatings > SART_MAX_COATINGS) return fail(SART_ERR_ARG, "telescope.nCoatings out of range");
+  if (!t) return SART_OK;
+  if (!s->testSource.active) {
+    if (t->nRadii < 1 || t->nEnergies < 1 || !t->energies || !t->fluxRadiusCDF || !t->diffFluxCDFs)
+      return fail(SART_ERR_ARG, "solar model tables missing");
+    if (t->nRadii > 65535 || t->nEnergies > 65535) return fail(SART_ERR_ARG, "solar model tables too large for the guide tables");
+  }
+  if (!(s->flags & SART_CF_IGNORE_REFLECTION)) {
+    if (tel.reflKind == SART_RK_EFFECTIVE_AREA) {
+      if (t->telescopeTransmission.n < 2) return fail(SART_ERR_ARG, "telescopeTransmission table missing");
+    } else {
+      if (!t->reflectivity || t->nAngles < 2 || t->nReflEnergies < 2) return fail(SART_ERR_ARG, "reflectivity table missing");
+      const int need = tel.reflKind == SART_RK_MULTI_COATING ? tel.nCoatings : 1;
+      if (t->nCoatings < need) return fail(SART_ERR_ARG, "reflectivity table has %d coatings, telescope needs %d", t->nCoatings, need);
+    }
+  }
+  if (t->strongbackTransmission.n < 2 || t->windowTransmission.n < 2 || t->gasAbsorption.n < 2)
+    return fail(SART_ERR_ARG, "detector transmission tables missing");
+  return SART_OK;
+}
+
+// Guide table of a CDF row: g[k] = lowerBound(cdf, k/K), k = 0..K. For k/K <= u < (k+1)/K the answer of
+// lowerBound(cdf, u) lies in [g[k], g[k+1]], so the device search starts from a window of a few entries.
+static void build_guide(const double* cdf, int n, uint16_t* g) {
+  int pos = 0;
+  for (int k = 0; k <= kGuide; ++k) {
+    const double key = double(k) / double(kGuide);
+    while (pos < n && cdf[pos] < key) ++pos;
+    g[k] = uint16_t(pos);
+  }
+}
+
+struct Blob {  // bump allocator over one device allocation
+  unsigned char* base = nullptr;
+  size_t off = 0;
+  std::vector<std::pair<size_t, std::vector<unsigned char>>> pending;
+  template <class T> size_t add(const T* src, size_t count) {
+    const size_t bytes = count * sizeof(T);
+    const size_t at = off;
+    std::vector<unsigned char> v(bytes);
+    if (bytes) std::memcpy(v.data(), src, bytes);
+    pending.emplace_back(at, std::move(v));
+    off = align256(off + bytes);
+    return at;
+  }
+};
+
+static int upload_tables(sart_handle* h, const sart_tables_t* t) {
+  Blob b;
+  size_t oEn = 0, oRC = 0, oDC = 0, oRG = 0, oEG = 0, oRefl = 0;
+  const bool solar = t->nRadii > 0 && t->energies;
+  if (solar) {
+    oEn = b.add(t->energies, t->nEnergies);
+    oRC = b.add(t->fluxRadiusCDF, t->nRadii);
+    oDC = b.add(t->diffFluxCDFs, size_t(t->nRadii) * t->nEnergies);
+    std::vector<uint16_t> rg(kGuide + 1), eg(size_t(t->nRadii) * (kGuide + 1));
+    build_guide(t->fluxRadiusCDF, t->nRadii, rg.data());
+    for (int r = 0; r < t->nRadii; ++r)
+      build_guide(t->diffFluxCDFs + size_t(r) * t->nEnergies, t->nEnergies, eg.data() + size_t(r) * (kGuide + 1));
+    oRG = b.add(rg.data(), rg.size());
+    oEG = b.add(eg.data(), eg.size());
+  }
+  const bool refl = t->reflectivity && t->nCoatings > 0;
+  if (refl) oRefl = b.add(t->reflectivity, size_t(t->nCoatings) * t->nAngles * t->nReflEnergies);
+  const sart_interp1d_t* I[4] = {&t->strongbackTransmission, &t->windowTransmission, &t->gasAbsorption, &t->telescopeTransmission};
+  size_t oX[4] = {0, 0, 0, 0}, oY[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k)
+    if (I[k]->n > 0 && I[k]->x && I[k]->y) { oX[k] = b.add(I[k]->x, I[k]->n); oY[k] = b.add(I[k]->y, I[k]->n); }
+  std::vector<sart::ShellF64> shells(SART_MAX_SHELLS);
+  derive_shells(h->setup, shells.data());
+  const size_t oSh = b.add(shells.data(), shells.size());
+
+  if (h->table_blob) { cudaFree(h->table_blob); h->table_blob = nullptr; }
+  SART_CUDA(cudaMalloc(&h->table_blob, b.off ? b.off : 256));
+  h->table_bytes = b.off;
+  unsigned char* base = static_cast<unsigned char*>(h->table_blob);
+  for (auto& pr : b.pending)
+    if (!pr.second.empty()) SART_CUDA(cudaMemcpyAsync(base + pr.first, pr.second.data(), pr.second.size(), cudaMemcpyHostToDevice, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+
+  Tables& T = h->tables;
+  std::memset(&T, 0, sizeof T);
+  if (solar) {
+    T.energies = reinterpret_cast<const double*>(base + oEn);
+    T.fluxRadiusCDF = reinterpret_cast<const double*>(base + oRC);
+    T.diffFluxCDFs = reinterpret_cast<const double*>(base + oDC);
+    T.radiusGuide = reinterpret_cast<const uint16_t*>(base + oRG);
+    T.energyGuide = reinterpret_cast<const uint16_t*>(base + oEG);
+  }
+  if (refl) T.reflectivity = reinterpret_cast<const double*>(base + oRefl);
+  const double** PX[4] = {&T.sbX, &T.wdX, &T.gaX, &T.ttX};
+  const double** PY[4] = {&T.sbY, &T.wdY, &T.gaY, &T.ttY};
+  int32_t* PN[4] = {&T.sbN, &T.wdN, &T.gaN, &T.ttN};
+  for (int k = 0; k < 4; ++k)
+    if (I[k]->n > 0 && I[k]->x && I[k]->y) {
+      *PX[k] = reinterpret_cast<const double*>(base + oX[k]);
+      *PY[k] = reinterpret_cast<const double*>(base + oY[k]);
+      *PN[k] = I[k]->n;
+    }
+  T.shells = reinterpret_cast<const ShellF64*>(base + oSh);
+  h->shell_offset = oSh;
+  return SART_OK;
+}
+
+static int ensure_image(sart_handle* h, int nMasses) {
+  const size_t len = size_t(nMasses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
+  if (h->d_image && h->image_masses == nMasses) return SART_OK;
+  if (h->d_image) { cudaFree(h->d_image); cudaFree(h->d_image_w2); cudaFree(h->d_counters); h->d_image = nullptr; }
+  SART_CUDA(cudaMalloc(&h->d_image, len * sizeof(double)));
+  SART_CUDA(cudaMalloc(&h->d_image_w2, len * sizeof(double)));
+  SART_CUDA(cudaMalloc(&h->d_counters, size_t(nMasses) * sizeof(sart_counters_t)));
+  h->image_masses = nMasses;
+  SART_CUDA(cudaMemsetAsync(h->d_image, 0, len * sizeof(double), h->stream));
+  SART_CUDA(cudaMemsetAsync(h->d_image_w2, 0, len * sizeof(double), h->stream));
+  SART_CUDA(cudaMemsetAsync(h->d_counters, 0, size_t(nMasses) * sizeof(sart_counters_t), h->stream));
+  return SART_OK;
+}
+
+static int ensure_stage(sart_handle* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return SART_OK;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr; h->stage_bytes = 0;
+  SART_CUDA(cudaMalloc(&h->d_stage, bytes));
+  h->stage_bytes = bytes;
+  return SART_OK;
+}
+
+}  // namespace sart
+
+using namespace sart;
+
+extern "C" {
+
+const char* sart_last_error(void) { return g_err; }
+int sart_abi_version(void) { return SART_ABI_VERSION; }
+size_t sart_sizeof_setup(void) { return sizeof(sart_setup_t); }
+size_t sart_sizeof_tables(void) { return sizeof(sart_tables_t); }
+size_t sart_sizeof_counters(void) { return sizeof(sart_counters_t); }
+int sart_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {
+  uint32_t w[6];
+  ray_words(seed, ray, w);
+  for (int i = 0; i < 6; ++i) u[i] = u01(w[i]);
+}
+
+int sart_create(const sart_setup_t* setup, const sart_tables_t* tables, int device, sart_handle_t** out) {
+  if (!out) return fail(SART_ERR_ARG, "sart_create: out is NULL");
+  *out = nullptr;
+  if (!tables) return fail(SART_ERR_ARG, "sart_create: tables is NULL");
+  int rc = validate(setup, tables);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SART_ERR_CUDA, "no CUDA device available (%s); libsart has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(SART_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+  SART_CUDA(cudaSetDevice(device));
+  sart_handle* h = new (std::nothrow) sart_handle();
+  if (!h) return fail(SART_ERR_NOMEM, "out of host memory");
+  h->device = device;
+  h->setup = *setup;
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDeviceProperties"); }
+  h->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  derive_params(h->setup, tables, &h->params);
+  if ((rc = upload_tables(h, tables))) { sart_destroy(h); return rc; }
+  if ((e = cudaMalloc(&h->d_masses, SART_MAX_MASSES * sizeof(double))) != cudaSuccess) { sart_destroy(h); return cuda_fail(e, "cudaMalloc"); }
+  h->n_masses = 1;
+  h->masses[0] = setup->consts.mAxion;
+  if ((e = cudaMemcpyAsync(h->d_masses, h->masses, sizeof(double), cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) { sart_destroy(h); return cuda_fail(e, "cudaMemcpyAsync"); }
+  if ((rc = ensure_image(h, 1))) { sart_destroy(h); return rc; }
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { sart_destroy(h); return cuda_fail(e, "cudaStreamSynchronize"); }
+  *out = h;
+  return SART_OK;
+}
+
+void sart_destroy(sart_handle_t* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->table_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
+  cudaFree(h->d_counters); cudaFree(h->d_stage);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  int rc = validate(setup, nullptr);
+  if (rc) return rc;
+  DeviceGuard dg(h->device);
+  // keep the table-derived fields
+  Params old = h->params;
+  h->setup = *setup;
+  derive_params(h->setup, nullptr, &h->params);
+  h->params.nAngles = old.nAngles; h->params.nReflEnergies = old.nReflEnergies;
+  h->params.angleMin = old.angleMin; h->params.angleMax = old.angleMax;
+  h->params.reflEMin = old.reflEMin; h->params.reflEMax = old.reflEMax;
+  h->params.reflDx = old.reflDx; h->params.reflDy = old.reflDy;
+  h->params.nRadii = old.nRadii; h->params.nEnergies = old.nEnergies;
+  std::vector<ShellF64> shells(SART_MAX_SHELLS);
+  derive_shells(h->setup, shells.data());
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  SART_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(h->table_blob) + h->shell_offset, shells.data(),
+                            shells.size() * sizeof(ShellF64), cudaMemcpyHostToDevice, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->n_masses == 1 && h->masses_default) {
+    h->masses[0] = setup->consts.mAxion;
+    SART_CUDA(cudaMemcpyAsync(h->d_masses, h->masses, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SART_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return SART_OK;
+}
+
+int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (n < 1 || n > SART_MAX_MASSES || !masses_eV) return fail(SART_ERR_ARG, "sart_set_axion_masses: need 1..%d masses", SART_MAX_MASSES);
+  DeviceGuard dg(h->device);
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(h->masses, masses_eV, n * sizeof(double));
+  h->n_masses = n;
+  h->masses_default = 0;
+  SART_CUDA(cudaMemcpyAsync(h->d_masses, h->masses, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = ensure_image(h, n);
+  if (rc) return rc;
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  return SART_OK;
+}
+
+int sart_set_precision(sart_handle_t* h, int mode) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (mode != 0) return fail(SART_ERR_ARG, "precision mode %d not available in this build", mode);
+  h->precision = mode;
+  return SART_OK;
+}
+
+void* sart_stream(sart_handle_t* h) { return h ? h->stream : nullptr; }
+
+int sart_build_cdfs(int device, int nR, int nE, const double* radii, const double* energies, const double* emRates,
+                    double* fluxRadiusCDF, double* diffFluxCDFs) {
+  if (nR < 1 || nE < 1 || !radii || !energies || !emRates || !fluxRadiusCDF || !diffFluxCDFs)
+    return fail(SART_ERR_ARG, "sart_build_cdfs: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SART_ERR_CUDA, "no CUDA device available; libsart has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(SART_ERR_ARG, "device %d out of range", device);
+  DeviceGuard dg(device);
+  const size_t cells = size_t(nR) * nE;
+  double *dR = nullptr, *dE = nullptr, *dEm = nullptr, *dTot = nullptr, *dC = nullptr, *dRC = nullptr;
+  int rc = SART_OK;
+  cudaError_t e;
+#define TRY(call) if (rc == SART_OK && (e = (call)) != cudaSuccess) rc = cuda_fail(e, #call)
+  TRY(cudaMalloc(&dR, nR * sizeof(double)));
+  TRY(cudaMalloc(&dE, nE * sizeof(double)));
+  TRY(cudaMalloc(&dEm, cells * sizeof(double)));
+  TRY(cudaMalloc(&dTot, nR * sizeof(double)));
+  TRY(cudaMalloc(&dC, cells * sizeof(double)));
+  TRY(cudaMalloc(&dRC, nR * sizeof(double)));
+  TRY(cudaMemcpy(dR, radii, nR * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(dE, energies, nE * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(dEm, emRates, cells * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(launch_build_cdfs(nR, nE, dR, dE, dEm, dTot, dC, dRC, nullptr));
+  TRY(cudaDeviceSynchronize());
+  TRY(cudaMemcpy(diffFluxCDFs, dC, cells * sizeof(double), cudaMemcpyDeviceToHost));
+  TRY(cudaMemcpy(fluxRadiusCDF, dRC, nR * sizeof(double), cudaMemcpyDeviceToHost));
+#undef TRY
+  cudaFree(dR); cudaFree(dE); cudaFree(dEm); cudaFree(dTot); cudaFree(dC); cudaFree(dRC);
+  return rc;
+}
+
+static int check_out(const sart_ray_out_t* out) {
+  if (!out || !out->x || !out->y || !out->w || !out->code || !out->shell)
+    return fail(SART_ERR_ARG, "sart_ray_out_t: x, y, w, code and shell are required");
+  return SART_OK;
+}
+
+int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin, const double* d_exit,
+                              const double* d_energy, const sart_ray_out_t* d_out) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  int rc = check_out(d_out);
+  if (rc) return rc;
+  if (n && (!d_origin || !d_exit || !d_energy)) return fail(SART_ERR_ARG, "sart_trace_presampled: NULL input");
+  DeviceGuard dg(h->device);
+  SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, d_origin, d_exit, d_energy, *d_out, h->stream));
+  return SART_OK;
+}
+
+// Lays a device-side sart_ray_out_t over the staging buffer; returns bytes used.
+static size_t carve_out(unsigned char* base, size_t n, const sart_ray_out_t& host, sart_ray_out_t* dev) {
+  size_t off = 0;
+  auto takeD = [&](double* hostp) -> double* {
+    if (!hostp) return nullptr;
+    double* p = reinterpret_cast<double*>(base + off);
+    off = align256(off + n * sizeof(double));
+    return p;
+  };
+  auto takeI = [&](int32_t* hostp) -> int32_t* {
+    if (!hostp) return nullptr;
+    int32_t* p = reinterpret_cast<int32_t*>(base + off);
+    off = align256(off + n * sizeof(int32_t));
+    return p;
+  };
+  dev->x = takeD(host.x); dev->y = takeD(host.y); dev->w = takeD(host.w);
+  dev->code = takeI(host.code); dev->shell = takeI(host.shell);
+  dev->energy = takeD(host.energy); dev->reflect = takeD(host.reflect); dev->transMagnet = takeD(host.transMagnet);
+  dev->yaw = takeD(host.yaw); dev->alpha1 = takeD(host.alpha1); dev->alpha2 = takeD(host.alpha2);
+  dev->pathCB = takeD(host.pathCB); dev->r = takeD(host.r); dev->deviationDet = takeD(host.deviationDet);
+  dev->transProbArgon = takeD(host.transProbArgon);
+  return off;
+}
+
+static int copy_out(sart_handle* h, size_t n, const sart_ray_out_t& host, const sart_ray_out_t& dev) {
+#define CPD(f) if (host.f) SART_CUDA(cudaMemcpyAsync(host.f, dev.f, n * sizeof(*host.f), cudaMemcpyDeviceToHost, h->stream))
+  CPD(x); CPD(y); CPD(w); CPD(code); CPD(shell); CPD(energy); CPD(reflect); CPD(transMagnet); CPD(yaw); CPD(alpha1);
+  CPD(alpha2); CPD(pathCB); CPD(r); CPD(deviationDet); CPD(transProbArgon);
+#undef CPD
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  return SART_OK;
+}
+
+int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin, const double* exitxy, const double* energy,
+                          const sart_ray_out_t* out) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  int rc = check_out(out);
+  if (rc) return rc;
+  if (n == 0) return SART_OK;
+  if (!origin || !exitxy || !energy) return fail(SART_ERR_ARG, "sart_trace_presampled: NULL input");
+  DeviceGuard dg(h->device);
+  const size_t inBytes = align256(3 * n * sizeof(double)) + align256(2 * n * sizeof(double)) + align256(n * sizeof(double));
+  sart_ray_out_t probe;
+  const size_t outBytes = carve_out(nullptr, n, *out, &probe);
+  if ((rc = ensure_stage(h, inBytes + outBytes))) return rc;
+  unsigned char* base = static_cast<unsigned char*>(h->d_stage);
+  double* dO = reinterpret_cast<double*>(base);
+  double* dX = reinterpret_cast<double*>(base + align256(3 * n * sizeof(double)));
+  double* dE = reinterpret_cast<double*>(base + align256(3 * n * sizeof(double)) + align256(2 * n * sizeof(double)));
+  sart_ray_out_t dev;
+  carve_out(base + inBytes, n, *out, &dev);
+  SART_CUDA(cudaMemcpyAsync(dO, origin, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SART_CUDA(cudaMemcpyAsync(dX, exitxy, 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SART_CUDA(cudaMemcpyAsync(dE, energy, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, dO, dX, dE, dev, h->stream));
+  return copy_out(h, n, *out, dev);
+}
+
+int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t seed, const sart_ray_out_t* out) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  int rc = check_out(out);
+  if (rc) return rc;
+  if (n == 0) return SART_OK;
+  DeviceGuard dg(h->device);
+  sart_ray_out_t probe;
+  const size_t outBytes = carve_out(nullptr, n, *out, &probe);
+  if ((rc = ensure_stage(h, outBytes))) return rc;
+  sart_ray_out_t dev;
+  carve_out(static_cast<unsigned char*>(h->d_stage), n, *out, &dev);
+  SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], first_ray, n, seed, dev, h->stream));
+  return copy_out(h, n, *out, dev);
+}
+
+int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  DeviceGuard dg(h->device);
+  SART_CUDA(launch_mc_image_exact(h->params, h->tables, h->n_masses, h->d_masses, first_ray, n_rays, seed, h->d_image,
+                                  h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+  return SART_OK;
+}
+
+int sart_reset_image(sart_handle_t* h) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  DeviceGuard dg(h->device);
+  const size_t len = size_t(h->n_masses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
+  SART_CUDA(cudaMemsetAsync(h->d_image, 0, len * sizeof(double), h->stream));
+  SART_CUDA(cudaMemsetAsync(h->d_image_w2, 0, len * sizeof(double), h->stream));
+  SART_CUDA(cudaMemsetAsync(h->d_counters, 0, size_t(h->n_masses) * sizeof(sart_counters_t), h->stream));
+  return SART_OK;
+}
+
+double* sart_image_dev(sart_handle_t* h) { return h ? h->d_image : nullptr; }
+double* sart_image_w2_dev(sart_handle_t* h) { return h ? h->d_image_w2 : nullptr; }
+void* sart_counters_dev(sart_handle_t* h) { return h ? h->d_counters : nullptr; }
+size_t sart_image_len(sart_handle_t* h) { return h ? size_t(h->n_masses) * SART_IMAGE_BINS * SART_IMAGE_BINS : 0; }
+
+int sart_read_image(sart_handle_t* h, double* image, double* image_w2, sart_counters_t* counters) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  DeviceGuard dg(h->device);
+  const size_t len = size_t(h->n_masses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
+  if (image) SART_CUDA(cudaMemcpyAsync(image, h->d_image, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (image_w2) SART_CUDA(cudaMemcpyAsync(image_w2, h->d_image_w2, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (counters) SART_CUDA(cudaMemcpyAsync(counters, h->d_counters, size_t(h->n_masses) * sizeof(sart_counters_t), cudaMemcpyDeviceToHost, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  return SART_OK;
+}
+
+int sart_prepare_heatmap(sart_handle_t* h, int rows, int cols, double start_x, double stop_x, double start_y,
+                         double stop_y, size_t n, const double* X, const double* Y, const double* W, double norm,
+                         double* result, uint64_t* n_out_of_range) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (rows < 1 || cols < 1 || !result || (n && (!X || !Y || !W))) return fail(SART_ERR_ARG, "sart_prepare_heatmap: bad argument");
+  DeviceGuard dg(h->device);
+  const size_t cells = size_t(rows) * cols;
+  const size_t bytes = align256(cells * sizeof(double)) + 256 + 3 * align256(n * sizeof(double));
+  int rc = ensure_stage(h, bytes);
+  if (rc) return rc;
+  unsigned char* base = static_cast<unsigned char*>(h->d_stage);
+  double* dRes = reinterpret_cast<double*>(base);
+  unsigned long long* dBad = reinterpret_cast<unsigned long long*>(base + align256(cells * sizeof(double)));
+  double* dX = reinterpret_cast<double*>(base + align256(cells * sizeof(double)) + 256);
+  double* dY = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dX) + align256(n * sizeof(double)));
+  double* dW = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dY) + align256(n * sizeof(double)));
+  SART_CUDA(cudaMemsetAsync(dRes, 0, align256(cells * sizeof(double)) + 256, h->stream));
+  if (n) {
+    SART_CUDA(cudaMemcpyAsync(dX, X, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SART_CUDA(cudaMemcpyAsync(dY, Y, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SART_CUDA(cudaMemcpyAsync(dW, W, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  // stepsize_X = (stop_x - start_x)/numberOfRows, stepsize_Y = (stop_y - start_y)/numberOfColumns (rt:828-830)
+  const double step_x = (stop_x - start_x) / double(rows), step_y = (stop_y - start_y) / double(cols);
+  SART_CUDA(launch_heatmap(rows, cols, start_x, step_x, start_y, step_y, n, dX, dY, dW, norm, dRes, dBad, h->stream));
+  unsigned long long bad = 0;
+  SART_CUDA(cudaMemcpyAsync(result, dRes, cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SART_CUDA(cudaMemcpyAsync(&bad, dBad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_out_of_range) *n_out_of_range = bad;
+  return SART_OK;
+}
+
+int sart_synchronize(sart_handle_t* h) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  DeviceGuard dg(h->device);
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  return SART_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// device_params.h — the POD blocks the kernels read: run-wide scalars (passed as a __grid_constant__ kernel
+// parameter) and one constant record per mirror shell (a small array in HBM, L1/L2 resident).
+//
+// Everything here is derived ONCE on the host from sart_setup_t (derive.cpp). The reference recomputes these
+// per ray inside traceAxion (tan/cos/sin of the shell angle, r2..r5, distanceMirrors, distDet, lengthTelescope,
+// rotation sines/cosines: src/raytracer.nim:1879-1884, 1951-1957, 1971-1973, 2070-2072, 639-644, 669-672,
+// 702-715); hoisting them does not change a single bit because each value is produced by the same expression.
+#pragma once
+#include <cstdint>
+
+#include "../../include/sart.h"
+
+namespace sart {
+
+// Per-shell constants, f64. Names follow the reference's variables.
+struct ShellF64 {
+  double R1;        // allR1[j]
+  double R1pT;      // allR1[j] + allThickness[j]   (glass front rt:1942-1943; nickel test of the shell above rt:1722)
+  double r1sq;      // R1*R1
+  double r4;        // rt:1954-1956
+  double r4sq;
+  double distanceMirrors;  // cos(beta)*(xSep + lMirror)  rt:1973
+  double distDet;   // rt:2070-2072
+  double ddWin;     // distDet / cos(pipesTurned)              rt:811
+  double ddEnd;     // (distDet + depthDet) / cos(pipesTurned) rt:2081, 811
+  // cone, mirror 1 (angle = beta, distMirr = 0): tan, tan^2, r1*tan, (2 r1)*tan, distMirr + lMirror*cos(angle)
+  double tan1, k1, r1tan1, two_r1_tan1, zmax1;
+  // cone, mirror 2 (angle = 3 beta, radius r4, distMirr = distanceMirrors)
+  double tan2, k2, r4tan2, two_r4_tan2, zmax2;
+  // paraboloid (mirror 1 of XMM/Abrixas, angle = beta)  rt:669-676, 743-746
+  double p_r3, p_e, p_r3sq, p_el, p_r3tan, p_r3_2tan;
+  // hyperboloid (mirror 2 of XMM/Abrixas, angle = 3 beta)  rt:702-715, 749-758
+  double h_r3, h_e, h_g, h_r3sq, h_el, h_gll, h_2g, h_nden, h_r3tan, h_r3_2tan;
+};
+
+struct Params {
+  // enums / counts
+  int32_t telKind, nShells, reflKind, nCoatings, stage, experiment, nStripHalf, testXray;
+  uint32_t flags;
+  int32_t layers[SART_MAX_COATINGS];
+  int32_t holeType, numberOfHoles, parallelSource, reserved;
+  // sun + sampling
+  double sunX, sunY, sunZ, radiusSun;
+  // magnet / pipes (z of the clip planes, radii)
+  double radiusCB, lengthB, zExitCB, zPipe1, zPipe2, rPipe1;
+  double B, g_agamma, tesla_to_eV2, m_to_inv_eV;
+  double pGas, tGas, roomTemp, radiusCB_m;  // pGas = pGasRoom/roomTemp*tGas rt:1601
+  // telescope frame
+  double cosTX, sinTX, cosTY, sinTY, halfLenTel, oeX, oeY;
+  double lMirror, fL;  // fL = distanceDetectorXRT
+  double holeInOptics;
+  // detector plane
+  double cosPipe, sinPipe, dShift, lateralShift, transversalShift;
+  double radiusWindow, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth;
+  double exposureFactor;
+  // X-ray test source rt:1765-1806
+  double srcX, srcY, srcZ, srcRadius, srcEnergy, colZ;
+  // reflectivity grid
+  int32_t nAngles, nReflEnergies;
+  double angleMin, angleMax, reflEMin, reflEMax, reflDx, reflDy;
+  // solar model
+  int32_t nRadii, nEnergies;
+};
+
+// Table pointers (device memory).
+struct Tables {
+  const double* energies;
+  const double* fluxRadiusCDF;
+  const double* diffFluxCDFs;
+  const uint16_t* radiusGuide;   // guide table for the radius CDF search
+  const uint16_t* energyGuide;   // [nRadii][kGuide+1] guide table for the per-radius energy CDF search
+  const double* reflectivity;
+  const double *sbX, *sbY, *wdX, *wdY, *gaX, *gaY, *ttX, *ttY;
+  int32_t sbN, wdN, gaN, ttN;
+  const ShellF64* shells;
+};
+
+constexpr int kGuide = 256;  // guide-table buckets per CDF row
+
+}  // namespace sart

@@ -1,0 +1,25 @@
+// kernels.h — launcher prototypes shared by the kernel TUs and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_params.h"
+
+namespace sart {
+
+// ---- FP64 "exact" pipeline (kernels_exact.cu)
+cudaError_t launch_presampled_exact(const Params& P, const Tables& T, double mAxion, size_t n, const double* origin,
+                                    const double* exitxy, const double* energy, const sart_ray_out_t& out,
+                                    cudaStream_t s);
+cudaError_t launch_mc_rays_exact(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n,
+                                 uint64_t seed, const sart_ray_out_t& out, cudaStream_t s);
+cudaError_t launch_mc_image_exact(const Params& P, const Tables& T, int nMasses, const double* masses, uint64_t first,
+                                  uint64_t nRays, uint64_t seed, double* image, double* imageW2,
+                                  sart_counters_t* counters, int smCount, cudaStream_t s);
+cudaError_t launch_build_cdfs(int nR, int nE, const double* radii, const double* energies, const double* emRates,
+                              double* rowTotals, double* cdfs, double* radiusCDF, cudaStream_t s);
+
+cudaError_t launch_heatmap(int rows, int cols, double start_x, double step_x, double start_y, double step_y, size_t n,
+                           const double* X, const double* Y, const double* W, double norm, double* result,
+                           unsigned long long* nBad, cudaStream_t s);
+
+}  // namespace sart

@@ -1,0 +1,291 @@
+// kernels_exact.cu — sm_100a kernels of the FP64 ("exact") pipeline and the CDF build.
+// Compiled with -fmad=false: see trace_exact.cuh for why.
+//
+//   k_trace_presampled  tier-(a) kernel: SoA rays in (origin xyz, exit-disc xy, energy: 6 f64 = 48 B... see
+//                       DESIGN.md for the byte count) -> SoA per-ray record out. One thread per ray.
+//   k_trace_mc_rays     traceAxionWrapper drop-in (rt:2223-2244): Philox sampling + trace, per-ray records out.
+//   k_trace_mc_image    fused run: Philox sampling + trace + prepareHeatmap (rt:818-842) + the counters of
+//                       generateResultPlots (rt:2252-2257). Grid-stride over global ray indices.
+//   k_build_cdf_rows / k_build_cdf_radius   initFullSetup's CDF build (rt:2679-2705).
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "trace_exact.cuh"
+
+namespace sart {
+
+struct RayOutDev {  // sart_ray_out_t with device pointers
+  double *x, *y, *w;
+  int32_t *code, *shell;
+  double *energy, *reflect, *transMagnet, *yaw, *alpha1, *alpha2, *pathCB, *r, *deviationDet, *transProbArgon;
+};
+
+__device__ __forceinline__ void store_ray(const RayOutDev& o, size_t i, const Geo& g, const Weights& w, const Final& f,
+                                          bool weighted) {
+  o.x[i] = f.x; o.y[i] = f.y; o.w[i] = f.w;
+  o.code[i] = f.code;
+  // shellNumber is assigned only at rt:2198, i.e. for rays that get past the window aperture
+  const bool tail = weighted && !g.windowMiss;
+  o.shell[i] = tail ? g.shell : -1;
+  if (o.energy) o.energy[i] = g.energy;
+  if (o.reflect) o.reflect[i] = weighted ? w.reflect : 0.0;
+  if (o.transMagnet) o.transMagnet[i] = weighted ? f.transMagnet : 0.0;
+  if (o.yaw) o.yaw[i] = g.ya;
+  if (o.alpha1) o.alpha1[i] = g.alpha1;
+  if (o.alpha2) o.alpha2[i] = g.alpha2;
+  if (o.pathCB) o.pathCB[i] = g.pathCB;
+  if (o.r) o.r[i] = f.r;
+  if (o.deviationDet) o.deviationDet[i] = g.deviationDet;
+  if (o.transProbArgon) o.transProbArgon[i] = tail ? w.absGas : 0.0;
+}
+
+__device__ __forceinline__ void trace_and_store(const Params& P, const Tables& T, double mAxion, V3 O, V3 E,
+                                                double energy, int preClamped, const RayOutDev& out, size_t i) {
+  Geo g;
+  trace_geometry<true>(P, T, O, E, energy, g);
+  g.clamped |= preClamped;
+  Weights w = {};
+  Final f = {};
+  if (g.code < 0) {
+    ray_weights(P, T, g, w);
+    ray_finish(P, g, w, mAxion, f);
+    store_ray(out, i, g, w, f, true);
+  } else {
+    f.code = g.code | (g.clamped ? SART_FLAG_INTERP_CLAMPED : 0);
+    store_ray(out, i, g, w, f, false);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_trace_presampled(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, size_t n,
+                   const double* __restrict__ origin, const double* __restrict__ exitxy,
+                   const double* __restrict__ energy, const __grid_constant__ RayOutDev out) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V3 O = {origin[i], origin[n + i], origin[2 * n + i]};
+  const V3 E = {exitxy[i], exitxy[n + i], P.lengthB};
+  trace_and_store(P, T, mAxion, O, E, energy[i], 0, out, i);
+}
+
+__global__ void __launch_bounds__(128)
+k_trace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, uint64_t first,
+                size_t n, uint64_t seed, const __grid_constant__ RayOutDev out) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V3 O, E;
+  double energy;
+  int clamped = 0;
+  if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped)) {
+    out.x[i] = 0.0; out.y[i] = 0.0; out.w[i] = 0.0; out.code[i] = SART_EXIT_COLLIMATOR; out.shell[i] = -1;
+    if (out.energy) out.energy[i] = energy;
+    if (out.reflect) out.reflect[i] = 0.0;
+    if (out.transMagnet) out.transMagnet[i] = 0.0;
+    if (out.yaw) out.yaw[i] = 0.0;
+    if (out.alpha1) out.alpha1[i] = 0.0;
+    if (out.alpha2) out.alpha2[i] = 0.0;
+    if (out.pathCB) out.pathCB[i] = 0.0;
+    if (out.r) out.r[i] = 0.0;
+    if (out.deviationDet) out.deviationDet[i] = 0.0;
+    if (out.transProbArgon) out.transProbArgon[i] = 0.0;
+    return;
+  }
+  trace_and_store(P, T, mAxion, O, E, energy, clamped, out, i);
+}
+
+// ---- fused Monte Carlo run -------------------------------------------------------------------------------
+// Block-level counters live in shared memory and are flushed once per block.
+struct BlockCounters {
+  unsigned long long n_rays;
+  unsigned long long n_exit[16];   // geometric exits (mass independent); PASSED / ZERO_WEIGHT are per mass
+  unsigned long long n_clamped;
+};
+struct MassCounters {
+  unsigned long long n_passed, n_zero, n_till_window, pad;
+  double sum_w, sum_w2, sum_x, sum_y, sum_r;
+};
+
+__global__ void __launch_bounds__(128)
+k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Tables T, int nMasses,
+                 const double* __restrict__ masses, uint64_t first, uint64_t nRays, uint64_t seed,
+                 double* __restrict__ image, double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+  extern __shared__ unsigned char smem_raw[];
+  BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem_raw);
+  MassCounters* mc = reinterpret_cast<MassCounters*>(smem_raw + sizeof(BlockCounters));
+  for (int k = threadIdx.x; k < int(sizeof(BlockCounters) / 8); k += blockDim.x)
+    reinterpret_cast<unsigned long long*>(bc)[k] = 0ull;
+  for (int k = threadIdx.x; k < int(nMasses * sizeof(MassCounters) / 8); k += blockDim.x)
+    reinterpret_cast<unsigned long long*>(mc)[k] = 0ull;
+  __syncthreads();
+
+  const double step = (P.chipCX * 2.0 - 0.0) / double(SART_IMAGE_BINS);  // (stop - start)/rows rt:828-830
+  const double stepY = (P.chipCY * 2.0 - 0.0) / double(SART_IMAGE_BINS);
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nRays; i += stride) {
+    V3 O, E;
+    double energy;
+    int clamped = 0;
+    atomicAdd(&bc->n_rays, 1ull);
+    if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped)) {
+      atomicAdd(&bc->n_exit[SART_EXIT_COLLIMATOR], 1ull);
+      continue;
+    }
+    Geo g;
+    trace_geometry<false>(P, T, O, E, energy, g);
+    g.clamped |= clamped;
+    if (g.code >= 0) {
+      atomicAdd(&bc->n_exit[g.code], 1ull);
+      if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
+      continue;
+    }
+    Weights w;
+    ray_weights(P, T, g, w);
+    if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
+    if (g.windowMiss) atomicAdd(&bc->n_exit[SART_EXIT_WINDOW_APERTURE], 1ull);
+    for (int m = 0; m < nMasses; ++m) {
+      Final f;
+      ray_finish(P, g, w, masses[m], f);
+      if (f.code & SART_FLAG_PASSED_TILL_WINDOW) atomicAdd(&mc[m].n_till_window, 1ull);
+      const int code = f.code & SART_CODE_MASK;
+      if (code == SART_EXIT_ZERO_WEIGHT) atomicAdd(&mc[m].n_zero, 1ull);
+      if (code != SART_EXIT_PASSED) continue;
+      atomicAdd(&mc[m].n_passed, 1ull);
+      atomicAdd(&mc[m].sum_w, f.w);
+      atomicAdd(&mc[m].sum_w2, f.w * f.w);
+      atomicAdd(&mc[m].sum_x, f.x);
+      atomicAdd(&mc[m].sum_y, f.y);
+      atomicAdd(&mc[m].sum_r, f.r);
+      // prepareHeatmap rt:839-842
+      const double cx = floor((f.x - 0.0) / step), cy = floor((f.y - 0.0) / stepY);
+      if (cx >= 0.0 && cx < double(SART_IMAGE_BINS) && cy >= 0.0 && cy < double(SART_IMAGE_BINS)) {
+        const size_t bin = size_t(m) * SART_IMAGE_BINS * SART_IMAGE_BINS + size_t(int(cy)) * SART_IMAGE_BINS + size_t(int(cx));
+        atomicAdd(image + bin, f.w);
+        atomicAdd(imageW2 + bin, f.w * f.w);
+      }
+    }
+  }
+  __syncthreads();
+  // flush
+  for (int m = threadIdx.x; m < nMasses; m += blockDim.x) {
+    sart_counters_t* c = counters + m;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_rays), bc->n_rays);
+    for (int e = 1; e < SART_N_EXIT_CODES; ++e)
+      if (e != SART_EXIT_ZERO_WEIGHT && bc->n_exit[e])
+        atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[e]), bc->n_exit[e]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[SART_EXIT_PASSED]), mc[m].n_passed);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[SART_EXIT_ZERO_WEIGHT]), mc[m].n_zero);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_passed), mc[m].n_passed);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_passed_till_window), mc[m].n_till_window);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_hit_nickel), bc->n_exit[SART_EXIT_NICKEL]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_interp_clamped), bc->n_clamped);
+    atomicAdd(&c->sum_w, mc[m].sum_w);
+    atomicAdd(&c->sum_w2, mc[m].sum_w2);
+    atomicAdd(&c->sum_x, mc[m].sum_x);
+    atomicAdd(&c->sum_y, mc[m].sum_y);
+    atomicAdd(&c->sum_r, mc[m].sum_r);
+  }
+}
+
+// ---- CDF build rt:2679-2705 -------------------------------------------------------------------------------
+// One thread walks one radius row sequentially (the reference's summation order => identical bits).
+__global__ void k_build_cdf_rows(int nR, int nE, const double* __restrict__ radii, const double* __restrict__ energies,
+                                 const double* __restrict__ emRates, double* __restrict__ rowTotals,
+                                 double* __restrict__ cdfs) {
+  const int iRad = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iRad >= nR) return;
+  const double radius = radii[iRad];
+  const double* em = emRates + size_t(iRad) * nE;
+  double* row = cdfs + size_t(iRad) * nE;
+  double diffSum = 0.0;
+  for (int iE = 0; iE < nE; ++iE) {
+    const double e = energies[iE];
+    const double diffFlux = em[iE] * (e * e) * radius * radius;
+    diffSum += diffFlux;
+    row[iE] = diffSum;
+  }
+  rowTotals[iRad] = diffSum;
+  const double integral = row[nE - 1];
+  for (int iE = 0; iE < nE; ++iE) row[iE] = row[iE] / integral;
+}
+__global__ void k_build_cdf_radius(int nR, const double* __restrict__ rowTotals, double* __restrict__ radiusCDF) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double acc = 0.0;
+  for (int i = 0; i < nR; ++i) { acc += rowTotals[i]; radiusCDF[i] = acc; }
+  const double integral = radiusCDF[nR - 1];
+  for (int i = 0; i < nR; ++i) radiusCDF[i] = radiusCDF[i] / integral;
+}
+
+// ---- prepareHeatmap rt:818-842 for host-provided points -------------------------------------------------------
+__global__ void k_heatmap(int rows, int cols, double start_x, double step_x, double start_y, double step_y, size_t n,
+                          const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ W,
+                          double norm, double* __restrict__ result, unsigned long long* __restrict__ nBad) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double cx = floor((X[i] - start_x) / step_x), cy = floor((Y[i] - start_y) / step_y);
+    if (cx >= 0.0 && cx < double(cols) && cy >= 0.0 && cy < double(rows))
+      atomicAdd(result + size_t(cy) * cols + size_t(cx), 1 * W[i] / norm);
+    else
+      atomicAdd(nBad, 1ull);
+  }
+}
+
+cudaError_t launch_heatmap(int rows, int cols, double start_x, double step_x, double start_y, double step_y, size_t n,
+                           const double* X, const double* Y, const double* W, double norm, double* result,
+                           unsigned long long* nBad, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int block = 256;
+  size_t want = (n + block - 1) / block;
+  const unsigned grid = unsigned(want < 148 * 8 ? want : 148 * 8);
+  k_heatmap<<<grid, block, 0, s>>>(rows, cols, start_x, step_x, start_y, step_y, n, X, Y, W, norm, result, nBad);
+  return cudaGetLastError();
+}
+
+// ---- launchers --------------------------------------------------------------------------------------------
+static RayOutDev to_dev(const sart_ray_out_t& o) {
+  return RayOutDev{o.x, o.y, o.w, o.code, o.shell, o.energy, o.reflect, o.transMagnet, o.yaw,
+                   o.alpha1, o.alpha2, o.pathCB, o.r, o.deviationDet, o.transProbArgon};
+}
+
+cudaError_t launch_presampled_exact(const Params& P, const Tables& T, double mAxion, size_t n, const double* origin,
+                                    const double* exitxy, const double* energy, const sart_ray_out_t& out,
+                                    cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int block = 128;
+  const unsigned grid = unsigned((n + block - 1) / block);
+  k_trace_presampled<<<grid, block, 0, s>>>(P, T, mAxion, n, origin, exitxy, energy, to_dev(out));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_rays_exact(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n,
+                                 uint64_t seed, const sart_ray_out_t& out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int block = 128;
+  const unsigned grid = unsigned((n + block - 1) / block);
+  k_trace_mc_rays<<<grid, block, 0, s>>>(P, T, mAxion, first, n, seed, to_dev(out));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_image_exact(const Params& P, const Tables& T, int nMasses, const double* masses, uint64_t first,
+                                  uint64_t nRays, uint64_t seed, double* image, double* imageW2,
+                                  sart_counters_t* counters, int smCount, cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const int block = 128;
+  const size_t smem = sizeof(BlockCounters) + size_t(nMasses) * sizeof(MassCounters);
+  int perSM = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace_mc_image, block, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  uint64_t want = (nRays + block - 1) / block;
+  uint64_t cap = uint64_t(smCount) * perSM;  // one resident wave; the grid-stride loop covers the rest
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  k_trace_mc_image<<<grid, block, smem, s>>>(P, T, nMasses, masses, first, nRays, seed, image, imageW2, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_cdfs(int nR, int nE, const double* radii, const double* energies, const double* emRates,
+                              double* rowTotals, double* cdfs, double* radiusCDF, cudaStream_t s) {
+  k_build_cdf_rows<<<(nR + 63) / 64, 64, 0, s>>>(nR, nE, radii, energies, emRates, rowTotals, cdfs);
+  k_build_cdf_radius<<<1, 32, 0, s>>>(nR, rowTotals, radiusCDF);
+  return cudaGetLastError();
+}
+
+}  // namespace sart

@@ -1,0 +1,55 @@
+// philox.cuh — Philox4x32-10 counter-based generator (Salmon et al., SC'11), host+device.
+//
+// Replaces std/random's global xoroshiro128+ state used by the reference's sampling procs
+// (src/raytracer.nim:276, 418-419, 433-436, 464), which is not reproducible under Weave. Key = run seed,
+// counter = (ray index lo, ray index hi, block, 0): a ray's random numbers depend only on (seed, global ray
+// index), so any partition of a run over launches, streams or GPUs traces the very same rays.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define SART_HD __host__ __device__ __forceinline__
+#else
+#define SART_HD inline
+#endif
+
+namespace sart {
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+SART_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return uint32_t((uint64_t(a) * uint64_t(b)) >> 32);
+#endif
+}
+
+SART_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// word -> uniform in (0,1): (w + 0.5) * 2^-32, exact in f64.
+SART_HD double u01(uint32_t w) { return (double(w) + 0.5) * (1.0 / 4294967296.0); }
+
+// The six uniforms of one ray in the reference's draw order:
+// phi_sun, theta_sun, u_radius (rt:433-436), u_disk_r, u_disk_phi (rt:418-419), u_energy (rt:464).
+SART_HD void ray_words(uint64_t seed, uint64_t ray, uint32_t w[6]) {
+  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+  const Philox4 a = philox4x32_10(uint32_t(ray), uint32_t(ray >> 32), 0u, 0u, k0, k1);
+  const Philox4 b = philox4x32_10(uint32_t(ray), uint32_t(ray >> 32), 1u, 0u, k0, k1);
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y;
+}
+
+}  // namespace sart

@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's driver for the per-ray path, on top of the C-ABI (include/sart.h).
+
+Names follow src/raytracer.nim: `initFullSetup` (rt:2637-2753) builds a `FullRaytraceSetup` (rt:232-242),
+`traceAxionWrapper` (rt:2223-2244) fills per-ray `Axion` records (here a structure of arrays),
+`calculateFluxFractions` (rt:2755-2776) runs the whole Monte Carlo and returns the 256x256 detector image that
+`prepareHeatmap` (rt:818-842) would build, plus the counters `generateResultPlots` prints (rt:2252-2257).
+Everything numeric happens in libsart.so on the GPU; this module only moves numpy arrays across the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi, tables as _tables
+from ._lib import SartError, check, lib  # noqa: F401  (re-exported)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(abi.c_double_p)
+
+
+def flags_from_cli(ignoreDetWindow=False, ignoreGasAbs=False, ignoreConvProb=False, ignoreReflection=False,
+                   xrayTest=False, magnet=False, detectorInstall=False) -> int:
+    """The flag set `main` builds from its CLI switches (rt:2842-2849)."""
+    f = 0
+    if ignoreDetWindow: f |= abi.CF_IGNORE_DET_WINDOW
+    if ignoreGasAbs: f |= abi.CF_IGNORE_GAS_ABS
+    if ignoreConvProb: f |= abi.CF_IGNORE_CONV_PROB
+    if ignoreReflection: f |= abi.CF_IGNORE_REFLECTION
+    if xrayTest: f |= abi.CF_XRAY_TEST
+    if magnet: f |= abi.CF_READ_MAGNET_CONFIG
+    if detectorInstall: f |= abi.CF_READ_DET_INSTALL_CONFIG
+    return f
+
+
+def newExperimentSetup(experiment, detector, stage, telescope, flags: int = 0) -> abi.Setup:
+    """newExperimentSetup (rt:1411-1423) + newDetectorSetup (rt:1464-1496): C++ constructors in libsart.
+    Accepts the reference's enum strings ("CAST", "InGrid2018", "vacuum", "LLNL") or the integer kinds."""
+    def kind(v, table):
+        if isinstance(v, str):
+            if v not in table:
+                raise ValueError(f"invalid enum value {v!r}; expected one of {sorted(table)}")  # parseEnum raises
+            return table[v]
+        return int(v)
+    s = abi.Setup()
+    check(lib.sart_init_setup(kind(experiment, abi.EXPERIMENT_KINDS), kind(detector, abi.DETECTOR_KINDS),
+                              kind(stage, abi.STAGE_KINDS), kind(telescope, abi.TELESCOPE_KINDS), flags, C.byref(s)))
+    return s
+
+
+def calcWindowVals(radiusWindow: float, numberOfStrips: int, openApertureRatio: float):
+    """calcWindowVals (rt:1431-1462) -> (width, dist) in mm."""
+    w, d = C.c_double(), C.c_double()
+    check(lib.sart_calc_window_vals(radiusWindow, numberOfStrips, openApertureRatio, C.byref(w), C.byref(d)))
+    return w.value, d.value
+
+
+def buildCdfs(emission: _tables.EmissionTable, device: int = 0):
+    """The CDF build of initFullSetup (rt:2679-2705) on the GPU -> (fluxRadiusCDF [nR], diffFluxCDFs [nR, nE])."""
+    radii = np.ascontiguousarray(emission.radii, dtype=np.float64)
+    en = np.ascontiguousarray(emission.energies, dtype=np.float64)
+    em = np.ascontiguousarray(emission.emRates, dtype=np.float64)
+    nR, nE = em.shape
+    rc = np.empty(nR)
+    dc = np.empty((nR, nE))
+    check(lib.sart_build_cdfs(device, nR, nE, _dp(radii), _dp(en), _dp(em), _dp(rc), _dp(dc)))
+    return rc, dc
+
+
+@dataclass
+class FullRaytraceSetup:
+    """FullRaytraceSetup (rt:232-242)."""
+    expSetup: abi.Setup
+    tables: _tables.TableSet
+    outpath: str = "out"
+
+    @property
+    def flags(self) -> int:
+        return self.expSetup.flags
+
+
+class AxionBatch:
+    """Per-ray results, the `Axion` record (rt:192-221) as a structure of numpy arrays."""
+
+    def __init__(self, n: int, optional: bool = True, pinned=None):
+        self.n = n
+        def alloc(dtype=np.float64):
+            return np.zeros(n, dtype=dtype)
+        self.x = alloc(); self.y = alloc(); self.w = alloc()
+        self.code = alloc(np.int32); self.shell = alloc(np.int32)
+        for name in abi.RAY_OUT_OPTIONAL:
+            setattr(self, name, alloc() if optional else None)
+
+    def c_struct(self) -> abi.RayOut:
+        o = abi.RayOut()
+        o.x, o.y, o.w = _dp(self.x), _dp(self.y), _dp(self.w)
+        o.code = self.code.ctypes.data_as(abi.c_int32_p)
+        o.shell = self.shell.ctypes.data_as(abi.c_int32_p)
+        for name in abi.RAY_OUT_OPTIONAL:
+            a = getattr(self, name)
+            if a is not None:
+                setattr(o, name, _dp(a))
+        return o
+
+    @property
+    def exit_code(self) -> np.ndarray:
+        return self.code & abi.CODE_MASK
+
+    @property
+    def passed(self) -> np.ndarray:          # Axion.passed
+        return self.exit_code == abi.EXIT_PASSED
+
+    @property
+    def passedTillWindow(self) -> np.ndarray:  # Axion.passedTillWindow
+        return (self.code & abi.FLAG_PASSED_TILL_WINDOW) != 0
+
+    @property
+    def hitNickel(self) -> np.ndarray:       # Axion.hitNickel
+        return self.exit_code == abi.EXIT_NICKEL
+
+
+@dataclass
+class RunResult:
+    image: np.ndarray        # [M, 256, 256] (M = number of axion masses), image[m, y, x] like heatmaptable2 rt:2629
+    image_w2: np.ndarray     # sum of squared weights per bin (Monte Carlo variance)
+    counters: list           # one dict per mass
+
+
+class RayTracer:
+    """One GPU's ray-tracing context: owns a sart_handle_t (tables resident in HBM, one stream)."""
+
+    def __init__(self, fullSetup: FullRaytraceSetup, device: int = 0):
+        self.fullSetup = fullSetup
+        self._h = abi.H()
+        self._tstruct = fullSetup.tables.c_struct()
+        check(lib.sart_create(C.byref(fullSetup.expSetup), C.byref(self._tstruct), device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib.sart_destroy(self._h)
+            self._h = abi.H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration
+    def update_setup(self, setup: abi.Setup):
+        check(lib.sart_update_setup(self._h, C.byref(setup)))
+        self.fullSetup.expSetup = setup
+
+    def set_axion_masses(self, masses):
+        m = np.ascontiguousarray(masses, dtype=np.float64)
+        check(lib.sart_set_axion_masses(self._h, m.size, _dp(m)))
+
+    def set_precision(self, mode: int):
+        check(lib.sart_set_precision(self._h, mode))
+
+    @property
+    def n_masses(self) -> int:
+        return lib.sart_image_len(self._h) // (abi.IMAGE_BINS * abi.IMAGE_BINS)
+
+    @property
+    def stream(self) -> int:
+        return lib.sart_stream(self._h) or 0
+
+    # -- tier (a): pre-sampled rays
+    def trace_presampled(self, origin_xyz, exit_xy, energy, optional: bool = True) -> AxionBatch:
+        origin_xyz = np.ascontiguousarray(origin_xyz, dtype=np.float64)
+        exit_xy = np.ascontiguousarray(exit_xy, dtype=np.float64)
+        energy = np.ascontiguousarray(energy, dtype=np.float64)
+        n = energy.size
+        if origin_xyz.shape != (3, n) or exit_xy.shape != (2, n):
+            raise ValueError("origin_xyz must be [3, n] and exit_xy [2, n] (structure of arrays)")
+        out = AxionBatch(n, optional)
+        o = out.c_struct()
+        check(lib.sart_trace_presampled(self._h, n, _dp(origin_xyz), _dp(exit_xy), _dp(energy), C.byref(o)))
+        return out
+
+    def trace_presampled_dev(self, n: int, d_origin: int, d_exit: int, d_energy: int, d_out: abi.RayOut):
+        """Device-pointer variant (asynchronous on `stream`)."""
+        check(lib.sart_trace_presampled_dev(self._h, n, d_origin, d_exit, d_energy, C.byref(d_out)))
+
+    # -- traceAxionWrapper: Monte Carlo rays, per-ray records
+    def traceAxionWrapper(self, bufLen: int, seed: int = 299792458, first_ray: int = 0,
+                          optional: bool = True) -> AxionBatch:
+        out = AxionBatch(bufLen, optional)
+        o = out.c_struct()
+        check(lib.sart_trace_mc_rays(self._h, first_ray, bufLen, seed, C.byref(o)))
+        return out
+
+    # -- fused run
+    def trace_mc(self, n_rays: int, seed: int = 299792458, first_ray: int = 0):
+        """Asynchronous: accumulates into the device image."""
+        check(lib.sart_trace_mc(self._h, first_ray, n_rays, seed))
+
+    def reset_image(self):
+        check(lib.sart_reset_image(self._h))
+
+    def synchronize(self):
+        check(lib.sart_synchronize(self._h))
+
+    def image_dev(self) -> tuple[int, int, int]:
+        """(device pointer of the image, of the w^2 image, number of doubles each) for collectives."""
+        return lib.sart_image_dev(self._h), lib.sart_image_w2_dev(self._h), lib.sart_image_len(self._h)
+
+    def counters_dev(self) -> int:
+        return lib.sart_counters_dev(self._h)
+
+    def read_image(self, want_w2: bool = True) -> RunResult:
+        m = self.n_masses
+        img = np.empty((m, abi.IMAGE_BINS, abi.IMAGE_BINS))
+        img2 = np.empty_like(img) if want_w2 else None
+        cnt = (abi.Counters * m)()
+        check(lib.sart_read_image(self._h, _dp(img), _dp(img2) if want_w2 else None, cnt))
+        return RunResult(img, img2, [c.as_dict() for c in cnt])
+
+
+def initFullSetup(setup, detectorSetup, stage, telescope, flags: int = 0, tables: _tables.TableSet | None = None,
+                  emission: _tables.EmissionTable | None = None, reflectivity=None, device: int = 0,
+                  outpath: str = "out") -> FullRaytraceSetup:
+    """initFullSetup (rt:2637-2753). `tables` wins if given; otherwise the CDFs are built on the GPU from
+    `emission` (default: the synthetic full-size table) and the packaged detector-chain tables are used."""
+    exp = newExperimentSetup(setup, detectorSetup, stage, telescope, flags)
+    if tables is None:
+        if emission is None:
+            emission = _tables.synthetic_emission()
+        rc, dc = buildCdfs(emission, device)
+        if reflectivity is None:
+            reflectivity = _tables.synthetic_reflectivity(max(1, exp.telescope.nCoatings))
+        tables = _tables.TableSet(energies=emission.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc,
+                                  reflectivity=reflectivity, **_tables.detector_tables_packaged())
+    return FullRaytraceSetup(expSetup=exp, tables=tables, outpath=outpath)
+
+
+def calculateFluxFractions(raytraceSetup: FullRaytraceSetup, nRays: int = 1_000_000, seed: int = 299792458,
+                           device: int = 0, tracer: RayTracer | None = None) -> RunResult:
+    """calculateFluxFractions (rt:2755-2776): trace `nRays` axions (NumberOfPointsSun = 1_000_000 in the
+    reference, rt:251) and return the detector image + counters."""
+    own = tracer is None
+    t = tracer or RayTracer(raytraceSetup, device)
+    try:
+        t.reset_image()
+        t.trace_mc(nRays, seed)
+        return t.read_image()
+    finally:
+        if own:
+            t.close()
+
+
+def prepareHeatmap(tracer: RayTracer, numberOfRows, numberOfColumns, start_x, stop_x, start_y, stop_y, data_X, data_Y,
+                   weight1, norm):
+    """prepareHeatmap (rt:818-842) for per-ray records held by the host; histogrammed on the GPU
+    (sart_prepare_heatmap). Returns (heatmap [rows, cols], number of points outside the grid)."""
+    X = np.ascontiguousarray(data_X, dtype=np.float64)
+    Y = np.ascontiguousarray(data_Y, dtype=np.float64)
+    W = np.ascontiguousarray(weight1, dtype=np.float64)
+    out = np.empty((numberOfRows, numberOfColumns))
+    bad = C.c_uint64(0)
+    check(lib.sart_prepare_heatmap(tracer._h, numberOfRows, numberOfColumns, start_x, stop_x, start_y, stop_y, X.size,
+                                   _dp(X), _dp(Y), _dp(W), norm, _dp(out), C.byref(bad)))
+    return out, bad.value

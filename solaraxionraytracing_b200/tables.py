@@ -1,0 +1,154 @@
+"""Input tables of the ray-tracing path as numpy arrays + the ctypes view libsart consumes.
+
+The reference reads these in initReflectivity (src/raytracer.nim:1160-1249), newDetectorSetup (rt:1498-1527) and
+initFullSetup (rt:2647-2668). Three of its files are not shipped, so besides loaders for the
+reference's file formats this module has deterministic synthetic generators of the same shapes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+
+DATA_DIR = Path(__file__).resolve().parent / "data"
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(abi.c_double_p)
+
+
+@dataclass
+class EmissionTable:
+    """`Radius, Energy [keV], emRates` of solar_model_dataframe.csv (rt:2647-2668) in dense form."""
+    radii: np.ndarray      # [nR] fraction of the solar radius, ascending
+    energies: np.ndarray   # [nE] keV, ascending
+    emRates: np.ndarray    # [nR, nE]
+
+
+@dataclass
+class TableSet:
+    energies: np.ndarray
+    fluxRadiusCDF: np.ndarray
+    diffFluxCDFs: np.ndarray          # [nR, nE]
+    reflectivity: np.ndarray | None   # [nCoat, nAng, nEn]
+    angleLim: tuple[float, float] = (0.0, 1.5)
+    reflEnergyLim: tuple[float, float] = (0.03, 15.0)
+    strongback: tuple[np.ndarray, np.ndarray] = None   # (E keV, T)
+    window: tuple[np.ndarray, np.ndarray] = None
+    gasAbsorption: tuple[np.ndarray, np.ndarray] = None
+    telescopeTransmission: tuple[np.ndarray, np.ndarray] | None = None
+    _keep: list = field(default_factory=list, repr=False)
+
+    def c_struct(self) -> abi.Tables:
+        """The sart_tables_t view. The returned struct borrows this object's arrays."""
+        t = abi.Tables()
+        self._keep.clear()
+
+        def hold(a):
+            a = _f64(a)
+            self._keep.append(a)
+            return a
+
+        if self.energies is not None:
+            en, rc, dc = hold(self.energies), hold(self.fluxRadiusCDF), hold(self.diffFluxCDFs)
+            assert dc.shape == (rc.size, en.size)
+            t.nRadii, t.nEnergies = rc.size, en.size
+            t.energies, t.fluxRadiusCDF, t.diffFluxCDFs = _ptr(en), _ptr(rc), _ptr(dc)
+        if self.reflectivity is not None:
+            r = hold(self.reflectivity)
+            assert r.ndim == 3
+            t.nCoatings, t.nAngles, t.nReflEnergies = r.shape
+            t.reflectivity = _ptr(r)
+        t.angleMin, t.angleMax = self.angleLim
+        t.reflEnergyMin, t.reflEnergyMax = self.reflEnergyLim
+        for name, pair in (("strongbackTransmission", self.strongback), ("windowTransmission", self.window),
+                           ("gasAbsorption", self.gasAbsorption), ("telescopeTransmission", self.telescopeTransmission)):
+            if pair is None:
+                continue
+            x, y = hold(pair[0]), hold(pair[1])
+            assert x.shape == y.shape and x.ndim == 1
+            it = getattr(t, name)
+            it.n, it.x, it.y = x.size, _ptr(x), _ptr(y)
+        return t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Detector chain (rt:1498-1527)
+
+def _read_tsv(path: Path) -> tuple[np.ndarray, np.ndarray]:
+    a = np.loadtxt(path, skiprows=1)
+    return a[:, 0].copy(), a[:, 1].copy()
+
+
+def detector_tables_from_resources(resources: str | Path, windowThickness=0.3, alThickness=0.02):
+    """Reads the reference's four Henke TSV files and combines them exactly as newDetectorSetup does:
+    strongback = Si(200 um) * Al, window = Si3N4 * Al, gas absorption = 1 - T_Ar; energies eV -> keV."""
+    res = Path(resources)
+    eSiN, tSiN = _read_tsv(res / f"Si3N4Density=3.44Thickness={windowThickness:.1f}microns.tsv")
+    eSi, tSi = _read_tsv(res / "SiDensity=2.33Thickness=200.microns.tsv")
+    eAr, tAr = _read_tsv(res / "transmission-argon-30mm-1050mbar-295K.tsv")
+    eAl, tAl = _read_tsv(res / f"AlDensity=2.7Thickness={alThickness:.2f}microns.tsv")
+    return {"strongback": (eSi / 1000.0, tSi * tAl), "window": (eSiN / 1000.0, tSiN * tAl),
+            "gasAbsorption": (eAr / 1000.0, 1.0 - tAr)}
+
+
+def detector_tables_packaged():
+    """The same three tables from the packaged fixture (made by tools/make_fixtures.py from the reference's
+    resources/*.tsv; the GPU box has no /root/reference)."""
+    z = np.load(DATA_DIR / "detector_tables.npz")
+    return {"strongback": (z["sb_E"], z["sb_T"]), "window": (z["wd_E"], z["wd_T"]),
+            "gasAbsorption": (z["ga_E"], z["ga_A"])}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Synthetic stand-ins for the un-shipped tables (shapes of SURVEY.md §8a)
+
+def synthetic_emission(nRadii: int = 1968, nEnergies: int = 1500, kind: str = "abc") -> EmissionTable:
+    """Deterministic analytic emission table with the real table's grid: radii 0.0015 + 0.0005 i
+    (resources/AGSS09_solar_model_stripped.dat), energies linspace(1e-3, 15, nE) keV
+    (src/readOpacityFile.nim:608-609). `abc`: axion-electron-like (bremsstrahlung continuum ~ exp(-E/T) plus a few
+    lines), `primakoff`: ~E^2/(exp(E/T)-1) screened. Temperature/density profiles are smooth fits to AGSS09."""
+    r = 0.0015 + 0.0005 * np.arange(nRadii, dtype=np.float64)
+    E = np.linspace(1e-3, 15.0, nEnergies)
+    T = 1.35 * np.exp(-(r / 0.29) ** 1.25) + 0.05           # keV
+    rho = np.exp(-r / 0.095)                                # relative density
+    Tm, Em = T[:, None], E[None, :]
+    if kind == "primakoff":
+        ks2 = (8.0 * rho[:, None] ** 0.5 + 0.2) ** 2        # Debye screening scale^2, keV^2
+        em = rho[:, None] * Tm * ks2 * Em / np.expm1(Em / Tm) * np.log1p(4.0 * Em * Em / ks2) / (Em * Em + 1e-3)
+    else:
+        cont = rho[:, None] ** 2 / np.sqrt(Tm) * np.exp(-Em / Tm) / (Em + 0.05)
+        lines = np.zeros_like(cont)
+        for e0, amp in ((0.653, 0.6), (0.779, 0.5), (0.986, 0.9), (1.865, 0.35), (2.45, 0.25), (6.5, 0.15)):
+            lines += amp * np.exp(-0.5 * ((Em - e0) / 0.012) ** 2) * np.exp(-e0 / Tm)
+        em = cont * (1.0 + 8.0 * lines)
+    em = em * 1e-12
+    return EmissionTable(radii=r, energies=E, emRates=np.ascontiguousarray(em))
+
+
+def synthetic_reflectivity(nCoatings: int = 4, nAngles: int = 1000, nEnergies: int = 1000,
+                           angleLim=(0.0, 1.5), energyLim=(0.03, 15.0)) -> np.ndarray:
+    """Analytic grazing-incidence reflectivity R(angle deg, E keV) on the reference's grid (1000 angles 0..1.5 deg x
+    1000 energies 0.03..15 keV per coating, tools/llnl_layer_reflectivity.nim:50-51): total external reflection below
+    a critical angle ~ 1/E, an absorption edge, and a Bragg bump per multilayer recipe."""
+    ang = np.linspace(angleLim[0], angleLim[1], nAngles)[:, None]
+    E = np.linspace(energyLim[0], energyLim[1], nEnergies)[None, :]
+    out = np.empty((nCoatings, nAngles, nEnergies), dtype=np.float64)
+    for c in range(nCoatings):
+        thc = (0.52 + 0.035 * c) * (8.0 / np.maximum(E, 0.05)) ** 0.95 * 0.1 + 0.02  # critical angle in deg
+        x = ang / thc
+        ter = 0.97 / (1.0 + x ** 6) ** 0.5 * np.exp(-0.08 * x)
+        edge = 1.0 - 0.35 * np.exp(-0.5 * ((E - (2.1 + 0.15 * c)) / 0.12) ** 2)
+        d = 3.2 + 0.6 * c                                                          # bilayer period, nm
+        bragg_ang = np.degrees(np.arcsin(np.clip(1.2398 / np.maximum(E, 0.05) / (2.0 * d), 0, 1)))
+        bump = 0.35 * np.exp(-0.5 * ((ang - bragg_ang) / 0.035) ** 2) * (E > 4.0)
+        out[c] = np.clip(ter * edge + bump * (1.0 - ter), 0.0, 1.0)
+    return out

@@ -1,0 +1,197 @@
+"""Tier (a)/(b) parity of the CUDA path (through the C-ABI, libsart.so) against the CPU oracle on a B200.
+
+Tolerances (north_star: "hit/miss classification bit-exact, (x, y, weight) within a stated tolerance"):
+  * exit code, passedTillWindow flag and shell number of every ray: IDENTICAL (integer compare);
+  * x, y (mm): |dx| <= 1e-9 mm absolute for pre-sampled inputs. The pipeline is the same IEEE-754 f64 operation
+    sequence on both sides except the libm calls asin/sincos/tan/acos/atan2/cos (glibc vs CUDA, <= 2 ulp each),
+    whose last-bit differences reach the detector plane amplified by the ~1.5 m lever arm: ~1e-13 mm expected;
+  * weight and the other f64 outputs: relative 1e-10.
+For Monte Carlo rays the emission point itself goes through sin/cos (rt:439-441) at |x| ~ 7e11 mm where one ulp is
+1.2e-4 mm; the reference's own geometry amplifies that (catastrophic cancellation at solar distances, DESIGN.md
+"Numerical floor"), so MC rays are compared at 5e-3 mm and a small exit-code mismatch budget.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_config
+from solaraxionraytracing_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+SEED = 299792458  # randomize(299792458) rt:276
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from solaraxionraytracing_b200 import raytracer
+    if raytracer.lib.sart_device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests need a B200")
+    return raytracer
+
+
+def _compare(gpu, ref, pos_tol, rel_tol, mismatch_budget=0):
+    same = gpu.code == ref.code
+    n_bad = int((~same).sum())
+    assert n_bad <= mismatch_budget, f"{n_bad} rays differ in exit code/flags: " \
+        f"{[(int(i), int(gpu.code[i]), int(ref.code[i])) for i in np.flatnonzero(~same)[:10]]}"
+    m = same
+    assert np.array_equal(gpu.shell[m], ref.shell[m])
+    # yaw = atan2(..)/deg + 90 is a difference of two numbers near 90 (rt:2107-2115): absolute tolerance, degrees
+    for name in ("x", "y", "r", "deviationDet", "yaw"):
+        a, b = getattr(gpu, name)[m], getattr(ref, name)[m]
+        assert np.max(np.abs(a - b), initial=0.0) <= pos_tol, (name, float(np.max(np.abs(a - b))))
+    for name in ("w", "energy", "reflect", "transMagnet", "alpha1", "alpha2", "pathCB", "transProbArgon"):
+        a, b = getattr(gpu, name)[m], getattr(ref, name)[m]
+        err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+        err[b == 0] = np.abs(a[b == 0])
+        assert np.max(err, initial=0.0) <= rel_tol, (name, float(np.max(err)))
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm", "babyiaxo_gas", "cast_abrixas", "cast_xmm"])
+def test_presampled_matches_oracle(rt, oracle, cfg):
+    setup, tb = make_config(cfg)
+    n = 200_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, SEED)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        gpu = tr.trace_presampled(origin, exit_xy, energy)
+    # sanity: the sample exercises the path
+    codes = set(np.unique(ref.exit_code).tolist())
+    if cfg != "cast_xmm":
+        assert abi.EXIT_PASSED in codes and len(codes) >= 5
+    _compare(gpu, ref, pos_tol=1e-9, rel_tol=1e-10)
+
+
+@pytest.mark.parametrize("flags", [abi.CF_IGNORE_DET_WINDOW, abi.CF_IGNORE_GAS_ABS, abi.CF_IGNORE_CONV_PROB,
+                                   abi.CF_IGNORE_REFLECTION,
+                                   abi.CF_IGNORE_DET_WINDOW | abi.CF_IGNORE_GAS_ABS | abi.CF_IGNORE_CONV_PROB |
+                                   abi.CF_IGNORE_REFLECTION])
+def test_presampled_flags(rt, oracle, flags):
+    setup, tb = make_config("cast_llnl", flags=flags)
+    n = 50_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, 7)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        gpu = tr.trace_presampled(origin, exit_xy, energy)
+    _compare(gpu, ref, pos_tol=1e-9, rel_tol=1e-10)
+
+
+def test_presampled_edge_inputs(rt, oracle):
+    """Empty batch, a single ray, rays that miss everything, NaN inputs."""
+    setup, tb = make_config("cast_llnl")
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        out = tr.trace_presampled(np.zeros((3, 0)), np.zeros((2, 0)), np.zeros(0))
+        assert out.n == 0
+        origin = np.array([[0.0, 1e13, np.nan, 3e11], [0.0, 0.0, 0.0, -2e11], [-1.5e14, -1.5e14, -1.5e14, -1.4999e14]])
+        exit_xy = np.array([[0.0, 0.0, 1.0, 21.49], [0.0, 0.0, 1.0, 0.0]])
+        energy = np.array([3.0, 3.0, 3.0, 20.0])   # 20 keV is outside every table: clamped + flagged
+        ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy)
+        gpu = tr.trace_presampled(origin, exit_xy, energy)
+        assert np.array_equal(gpu.code, ref.code), (gpu.code, ref.code)
+        assert (ref.exit_code[1] == abi.EXIT_MISSED_BORE) or (ref.exit_code[1] == abi.EXIT_CLIP_EXIT_CB)
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_mc_rays_match_oracle(rt, oracle, cfg):
+    setup, tb = make_config(cfg)
+    n = 200_000
+    ref = oracle.trace_mc_rays(setup, tb, 1000, n, SEED)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        gpu = tr.traceAxionWrapper(n, SEED, first_ray=1000)
+    # sampled energies are table values: identical unless the radius/energy index differs (never expected)
+    assert np.array_equal(gpu.energy, ref.energy)
+    _compare(gpu, ref, pos_tol=5e-3, rel_tol=1e-6, mismatch_budget=n // 5000)
+
+
+def test_mc_rays_split_invariance(rt):
+    """Ray i depends only on (seed, global index): two half launches == one launch."""
+    setup, tb = make_config("cast_llnl")
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        full = tr.traceAxionWrapper(20_000, 5, first_ray=0)
+        a = tr.traceAxionWrapper(7_000, 5, first_ray=0)
+        b = tr.traceAxionWrapper(13_000, 5, first_ray=7_000)
+    for name in ("x", "y", "w", "code", "shell"):
+        assert np.array_equal(getattr(full, name), np.concatenate([getattr(a, name), getattr(b, name)]))
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_mc_image_matches_oracle(rt, oracle, cfg):
+    setup, tb = make_config(cfg)
+    n = 300_000
+    img_ref, img2_ref, cnt_ref = oracle.trace_mc(setup, tb, 0, n, SEED)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.trace_mc(n // 3, SEED, first_ray=0)           # three launches accumulate into one image
+        tr.trace_mc(n // 3, SEED, first_ray=n // 3)
+        tr.trace_mc(n - 2 * (n // 3), SEED, first_ray=2 * (n // 3))
+        res = tr.read_image()
+    c, cr = res.counters[0], cnt_ref[0]
+    assert c["n_rays"] == n == cr["n_rays"]
+    budget = n // 5000
+    for k, v in cr["n_exit"].items():
+        assert abs(c["n_exit"][k] - v) <= budget, (k, c["n_exit"][k], v)
+    assert abs(c["n_passed"] - cr["n_passed"]) <= budget
+    assert abs(c["n_passed_till_window"] - cr["n_passed_till_window"]) <= budget
+    assert c["n_hit_nickel"] == c["n_exit"]["nickel"]
+    assert abs(c["sum_w"] / cr["sum_w"] - 1.0) < 1e-3
+    # image: same rays land in the same bins except those within ~1e-3 mm of a bin edge
+    tot = img_ref.sum()
+    assert abs(res.image.sum() / tot - 1.0) < 1e-3
+    assert np.abs(res.image[0] - img_ref[0]).sum() / tot < 0.05
+    # Σw in the image equals the counter
+    assert abs(res.image.sum() / c["sum_w"] - 1.0) < 1e-9
+    assert abs(res.image_w2.sum() / c["sum_w2"] - 1.0) < 1e-9
+
+
+def test_mass_scan_matches_oracle(rt, oracle):
+    setup, tb = make_config("babyiaxo_gas")
+    masses = np.linspace(0.01, 0.4, 8)
+    n = 60_000
+    img_ref, _, cnt_ref = oracle.trace_mc(setup, tb, 0, n, 3, masses=masses)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_axion_masses(masses)
+        assert tr.n_masses == 8
+        tr.trace_mc(n, 3)
+        res = tr.read_image()
+    for m in range(8):
+        assert abs(res.counters[m]["sum_w"] / cnt_ref[m]["sum_w"] - 1.0) < 2e-3, m
+        assert abs(res.counters[m]["n_passed"] - cnt_ref[m]["n_passed"]) <= 20
+    sw = np.array([c["sum_w"] for c in res.counters])
+    assert sw.max() / sw.min() > 1.5   # the scan really changes the conversion probability
+
+
+def test_build_cdfs_bit_identical(rt, oracle):
+    from solaraxionraytracing_b200 import tables
+    em = tables.synthetic_emission(246, 300, "abc")
+    rc_ref, dc_ref = oracle.build_cdfs(em.radii, em.energies, em.emRates)
+    rc, dc = rt.buildCdfs(em)
+    assert np.array_equal(rc, rc_ref)
+    assert np.array_equal(dc, dc_ref)
+    assert rc[-1] == 1.0 and np.all(dc[:, -1] == 1.0) and np.all(np.diff(rc) >= 0)
+
+
+def test_prepare_heatmap(rt, oracle):
+    setup, tb = make_config("cast_llnl")
+    rng = np.random.default_rng(0)
+    n = 100_000
+    x, y, w = rng.uniform(-1, 15, n), rng.uniform(-1, 15, n), rng.uniform(0, 1, n)
+    ref = np.zeros((256, 256))
+    import ctypes as C
+    bad_ref = oracle.lib().oracle_prepare_heatmap(256, 256, 0.0, 14.0, 0.0, 14.0, n, oracle._dp(x), oracle._dp(y),
+                                                  oracle._dp(w), 2.0, oracle._dp(ref))
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        hm, bad = rt.prepareHeatmap(tr, 256, 256, 0.0, 14.0, 0.0, 14.0, x, y, w, 2.0)
+    assert bad == bad_ref
+    assert np.allclose(hm, ref, rtol=1e-12, atol=0)
+
+
+def test_create_rejects_bad_input(rt):
+    setup, tb = make_config("cast_llnl")
+    import ctypes as C
+    bad = type(setup).from_buffer_copy(setup)
+    bad.abi_version = 99
+    with pytest.raises(rt.SartError):
+        rt.RayTracer(rt.FullRaytraceSetup(bad, tb))
+    bad = type(setup).from_buffer_copy(setup)
+    bad.telescope.kind = abi.TK_OTHER
+    with pytest.raises(rt.SartError):
+        rt.RayTracer(rt.FullRaytraceSetup(bad, tb))
