@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — traced rays/s of the per-ray pipeline on N B200s (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--rays-per-step R] [--precision exact|fast]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...     # the reference's CPU algorithm (restated oracle) on the host cores
+
+Workload (config.workload): BASELINE config "CAST magnet + LLNL telescope, detector chain active
+(Si3N4/Al window + Ar), 1e9 rays" — the largest single-GPU configuration of the setup the north-star target is
+quoted on. Tables have the reference's shapes (1968x1500 solar model, 4x1000x1000 reflectivity) with synthetic
+content (three of the reference's input files are not shipped), detector-chain tables are the reference's own.
+
+A "step" is one fused Monte Carlo pass (Philox sampling -> trace -> weighted 256x256 histogram) over
+--rays-per-step rays PER GPU (weak scaling); with N > 1 each step ends with one NCCL all-reduce of the image and the
+counters. `value` counts launched rays of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SEED = 299792458  # randomize(299792458), raytracer.nim:276
+# Algorithmic work per launched ray (SURVEY.md §8a tally x measured stage-reach probabilities):
+# 230 (sampling + bore/pipes + frame) + 70*0.997 (shell scan) + 370*0.936 (two mirror solves + reflections)
+# + 223*0.91 (detector plane, angles, weights, histogram) for CAST+LLNL.
+F_RAY_LLNL = 850.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rays-per-step", type=float, default=1e9)
+    ap.add_argument("--precision", choices=["exact", "fast"], default=None)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def workload_tables(rt, tables, device):
+    """Full-size tables of the CAST+LLNL workload; CDFs built on the GPU (sart_build_cdfs)."""
+    em = tables.synthetic_emission(1968, 1500, "abc")
+    rc, dc = rt.buildCdfs(em, device)
+    refl = tables.synthetic_reflectivity(4, 1000, 1000)
+    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl,
+                           **tables.detector_tables_packaged())
+
+
+def workload_tables_cpu(orc, tables):
+    em = tables.synthetic_emission(1968, 1500, "abc")
+    rc, dc = orc.build_cdfs(em.radii, em.energies, em.emRates)
+    refl = tables.synthetic_reflectivity(4, 1000, 1000)
+    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl,
+                           **tables.detector_tables_packaged())
+
+
+WORKLOAD = "CAST+LLNL vacuum, InGrid2018 window+Ar chain, solar table 1968x1500, reflectivity 4x1000x1000"
+
+
+def cpu_leg(seconds: float, threads: int | None = None):
+    """Times the restated CPU oracle (the reference's algorithm; the Nim binary cannot be built in this image) on
+    a bounded sample of the same workload. Returns (rays/s, cores, sample description)."""
+    from oracle import oracle as orc
+    from oracle import ref_setup
+    from solaraxionraytracing_b200 import abi, tables
+    orc.lib()
+    cores = threads or orc.lib().oracle_num_threads()
+    orc.lib().oracle_set_num_threads(cores)
+    setup = ref_setup.make_setup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
+    tb = workload_tables_cpu(orc, tables)
+    n0 = 200_000
+    t0 = time.perf_counter()
+    orc.trace_mc(setup, tb, 0, n0, SEED)
+    rate = n0 / (time.perf_counter() - t0)
+    n = int(max(n0, min(rate * seconds, 5e7)))
+    t0 = time.perf_counter()
+    _, _, cnt = orc.trace_mc(setup, tb, n0, n, SEED)
+    dt = time.perf_counter() - t0
+    return n / dt, cores, f"{n} rays of the same workload, OpenMP {cores} threads, {dt:.1f} s", cnt[0]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the line-faithful oracle port (kind
+    "port"), all host threads, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from oracle import ref_setup
+    from solaraxionraytracing_b200 import abi, tables
+    orc.lib()
+    cores = orc.lib().oracle_num_threads()
+    setup = ref_setup.make_setup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
+    tb = workload_tables_cpu(orc, tables)
+    t0 = time.perf_counter()
+    orc.trace_mc(setup, tb, 0, 100_000, SEED)
+    rate = 100_000 / (time.perf_counter() - t0)
+    total = args.steps + args.warmup
+    per_step = int(max(50_000, min(rate * (90.0 / max(1, total)), 2e7)))  # whole run within ~1.5 min
+    for w in range(args.warmup):
+        orc.trace_mc(setup, tb, w * per_step, per_step, SEED)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        orc.trace_mc(setup, tb, (args.warmup + k) * per_step, per_step, SEED)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} rays/step of the same workload on {cores} host threads (restated oracle, not the Nim executable)"
+    print(json.dumps({
+        "impl": "reference", "metric": "traced rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        # under load = the upper half of the samples (the sampler also sees the idle edges)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class DevArray:
+    """Zero-copy view of a libsart device buffer for torch (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    from solaraxionraytracing_b200 import abi, raytracer as rt, tables
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the ray-tracing path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    R = int(args.rays_per_step)
+    K, W = args.steps, args.warmup
+    precision = args.precision or ("fast" if rt.fast_available() else "exact")
+
+    t0 = time.perf_counter()
+    tb = workload_tables(rt, tables, local)
+    setup = rt.newExperimentSetup("CAST", "InGrid2018", "vacuum", "LLNL", 0)
+    fs = rt.FullRaytraceSetup(setup, tb)
+    tr = rt.RayTracer(fs, local)
+    tr.set_precision(1 if precision == "fast" else 0)
+    table_upload_s = time.perf_counter() - t0
+
+    stream = torch.cuda.ExternalStream(tr.stream, device=local)
+    img_ptr, img2_ptr, img_len = tr.image_dev()
+    t_img = torch.as_tensor(DevArray(img_ptr, img_len), device=f"cuda:{local}")
+    t_img2 = torch.as_tensor(DevArray(img2_ptr, img_len), device=f"cuda:{local}")
+    n_cnt_words = C.sizeof(abi.Counters) // 8
+    # counters: 22 u64 words then 5 f64; all-reduce them as two typed views
+    n_u64 = abi.Counters.sum_w.offset // 8
+    t_cnt_i = torch.as_tensor(DevArray(tr.counters_dev(), n_u64, "<i8"), device=f"cuda:{local}")
+    t_cnt_f = torch.as_tensor(DevArray(tr.counters_dev() + n_u64 * 8, n_cnt_words - n_u64), device=f"cuda:{local}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k: int, ev=None):
+        """One step: flush L2, trace R rays of this rank's shard, merge images across ranks."""
+        first = (k * n_gpus + rank) * R
+        flush.zero_()
+        if ev is not None:
+            ev[0].record(stream)
+        tr.trace_mc(R, SEED, first_ray=first)
+        if ev is not None:
+            ev[1].record(stream)
+        if dist is not None:
+            for t in (t_img, t_img2, t_cnt_i, t_cnt_f):
+                dist.all_reduce(t)
+            # every rank now holds the merged image; non-zero ranks drop theirs so the next step's sum stays right
+            if rank != 0:
+                tr.reset_image()
+
+    with torch.cuda.stream(stream):
+        tr.reset_image()
+        for w in range(W):
+            step(w)
+        barrier()
+        tr.reset_image()
+        barrier()
+        smi_index = local
+        try:
+            smi_index = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+        except (KeyError, ValueError, IndexError):
+            pass
+        sampler = ClockSampler(smi_index)
+        sampler.start()
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for k in range(K):
+            step(W + k, kev[k])
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms_total = e0.elapsed_time(e1)
+        kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    res = tr.read_image()
+
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    value = n_gpus * R * K / (ms_total * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers: reset + trace + read image/counters back to the host
+    def e2e_step(k):
+        first = ((W + K + k) * n_gpus + rank) * R
+        tr.reset_image()
+        tr.trace_mc(R, SEED, first_ray=first)
+        return tr.read_image()   # D2H of image, w2 image and counters, synchronises
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        e2e_step(1 + k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * R * K / float(t_e.item())
+    d2h = 2 * img_len * 8 + C.sizeof(abi.Counters) * tr.n_masses
+
+    if rank == 0:
+        c = res.counters[0]
+        fp64 = precision == "exact"
+        peak = C.c_double(0.0)
+        rt.check(rt.lib.sart_measure_fma_peak(local, 1 if fp64 else 0, C.byref(peak)))
+        k_ms = statistics.mean(kernel_ms)
+        achieved = F_RAY_LLNL * R / (k_ms * 1e-3) / 1e12
+        out = {
+            "metric": "traced rays/s", "value": value, "unit": "rays/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if fp64 else "f32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "precision": precision,
+                       "l2": "256 MiB buffer written between steps (L2 flush)", "seed": SEED,
+                       "table_upload_s": round(table_upload_s, 3),
+                       "passed_fraction": c["n_passed"] / max(1, c["n_rays"])},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
+                    "note": "sart_reset_image + sart_trace_mc + sart_read_image per step through the C-ABI; the path "
+                            "has no per-step host inputs (rays are generated in-kernel from Philox), tables are "
+                            "resident per run (config.table_upload_s)"},
+            "gpu_launches": K,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64" if fp64 else "fp32", "achieved": achieved, "peak": peak.value,
+                         "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                         "kernel": "k_trace_mc_image" if fp64 else "k_trace_mc_fast",
+                         "kernel_ms": k_ms, "flop_per_ray": F_RAY_LLNL,
+                         "peak_source": "sart_measure_fma_peak in this run (MEASURED_PEAKS.json has no CUDA-core "
+                                        "figure); the kernel moves ~0 HBM bytes per ray"},
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            v, cores, sample, _ = cpu_leg(args.cpu_seconds)
+            out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                                   "sample": sample + " (restated oracle, not the Nim executable)"}
+        print(json.dumps(out), flush=True)
+    tr.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

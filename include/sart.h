@@ -243,6 +243,7 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup);
 int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV);
 /* 0 = "exact" FP64 pipeline (bit-faithful classification), 1 = "fast" mixed FP32 pipeline. */
 int sart_set_precision(sart_handle_t* h, int mode);
+int sart_has_precision(int mode); /* 1 if this build has the pipeline for `mode` */
 void* sart_stream(sart_handle_t* h); /* cudaStream_t the handle launches on */
 
 /* ---- CDF build on the device (replaces rt:2679-2705). emRates is [nRadii][nEnergies] row-major,
@@ -287,6 +288,10 @@ int sart_synchronize(sart_handle_t* h);
 int sart_prepare_heatmap(sart_handle_t* h, int numberOfRows, int numberOfColumns, double start_x, double stop_x,
                          double start_y, double stop_y, size_t n, const double* data_X, const double* data_Y,
                          const double* weight1, double norm, double* result, uint64_t* n_out_of_range);
+
+/* ---- measurement helper: dense FMA issue rate of the CUDA cores (fp64 != 0: DFMA, else FFMA) in TFLOP/s, best of a
+ * few launches. bench.py uses it as the roofline denominator of the compute-bound trace kernels. */
+int sart_measure_fma_peak(int device, int fp64, double* tflops);
 
 /* ---- Philox helper exported for tests: the 6 uniforms of global ray `ray` in the order the reference
  * draws them (rt:433-436, 418-419, 464): phi_sun, theta_sun, u_radius, u_disk_r, u_disk_phi, u_energy. */

@@ -166,6 +166,7 @@ SIGNATURES = {
     "sart_update_setup": (C.c_int, [H, C.POINTER(Setup)]),
     "sart_set_axion_masses": (C.c_int, [H, C.c_int, c_double_p]),
     "sart_set_precision": (C.c_int, [H, C.c_int]),
+    "sart_has_precision": (C.c_int, [C.c_int]),
     "sart_stream": (C.c_void_p, [H]),
     "sart_build_cdfs": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_double_p]),
@@ -180,6 +181,7 @@ SIGNATURES = {
     "sart_image_len": (C.c_size_t, [H]),
     "sart_read_image": (C.c_int, [H, c_double_p, c_double_p, C.POINTER(Counters)]),
     "sart_synchronize": (C.c_int, [H]),
+    "sart_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
     "sart_prepare_heatmap": (C.c_int, [H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_size_t,
                                        c_double_p, c_double_p, c_double_p, C.c_double, c_double_p,
                                        C.POINTER(C.c_uint64)]),

@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # compared bit for bit with the CPU oracle.
 UNITS = [
     ("kernels_exact.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
+    ("kernels_util.cu", []),
     ("api.cu", []),
     ("derive.cpp", []),
     ("host_setup.cpp", []),

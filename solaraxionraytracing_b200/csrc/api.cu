@@ -291,6 +291,8 @@ int sart_set_precision(sart_handle_t* h, int mode) {
   return SART_OK;
 }
 
+int sart_has_precision(int mode) { return mode == 0; }
+
 void* sart_stream(sart_handle_t* h) { return h ? h->stream : nullptr; }
 
 int sart_build_cdfs(int device, int nR, int nE, const double* radii, const double* energies, const double* emRates,

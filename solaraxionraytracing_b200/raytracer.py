@@ -21,6 +21,11 @@ def _dp(a: np.ndarray):
     return a.ctypes.data_as(abi.c_double_p)
 
 
+def fast_available() -> bool:
+    """True if this build of libsart has the mixed-precision ("fast") pipeline."""
+    return bool(lib.sart_has_precision(1))
+
+
 def flags_from_cli(ignoreDetWindow=False, ignoreGasAbs=False, ignoreConvProb=False, ignoreReflection=False,
                    xrayTest=False, magnet=False, detectorInstall=False) -> int:
     """The flag set `main` builds from its CLI switches (rt:2842-2849)."""
