@@ -24,9 +24,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # compared bit for bit with the CPU oracle.
 UNITS = [
     ("kernels_exact.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
+    ("kernels_fast.cu", []),
     ("kernels_util.cu", []),
     ("api.cu", []),
     ("derive.cpp", []),
+    ("derive_fast.cpp", []),
     ("host_setup.cpp", []),
 ]
 

@@ -152,6 +152,58 @@ static int upload_tables(sart_handle* h, const sart_tables_t* t) {
   return SART_OK;
 }
 
+// Builds / refreshes the device data of the fast pipeline. `t` may be NULL on a setup update (tables unchanged).
+static int upload_fast(sart_handle* h, const sart_tables_t* t) {
+  const char* why = "";
+  h->fast_ok = fast::supported(h->setup, &why) ? 1 : 0;
+  h->fast_why = why;
+  if (!h->fast_ok) return SART_OK;
+  if (t) {
+    h->h_energies.assign(t->energies ? t->energies : nullptr, t->energies ? t->energies + t->nEnergies : nullptr);
+    const sart_interp1d_t* I[3] = {&t->strongbackTransmission, &t->windowTransmission, &t->gasAbsorption};
+    for (int k = 0; k < 3; ++k) {
+      h->h_tab[k][0].assign(I[k]->x, I[k]->x + I[k]->n);
+      h->h_tab[k][1].assign(I[k]->y, I[k]->y + I[k]->n);
+    }
+  }
+  sart_interp1d_t I[3];
+  for (int k = 0; k < 3; ++k) I[k] = sart_interp1d_t{int32_t(h->h_tab[k][0].size()), 0, h->h_tab[k][0].data(), h->h_tab[k][1].data()};
+  fast::derive_params(h->setup, h->params, &h->fparams);
+  std::vector<ShellF64> sh64(SART_MAX_SHELLS);
+  derive_shells(h->setup, sh64.data());
+  std::vector<fast::ShellFast> shf(SART_MAX_SHELLS);
+  fast::derive_shells(h->setup, sh64.data(), shf.data());
+  std::vector<fast::EnergyLUT> lut;
+  fast::build_energy_lut(h->params, int(h->h_energies.size()), h->h_energies.data(), I[0], I[1], I[2],
+                         h->setup.testSource.energy, &lut);
+  unsigned char* base = static_cast<unsigned char*>(h->fast_blob);
+  if (t) {
+    // layout: shells | lut | refl(f32)
+    const size_t nRefl = t->reflectivity ? size_t(t->nCoatings) * t->nAngles * t->nReflEnergies : 0;
+    h->fast_shell_off = 0;
+    h->fast_lut_off = align256(shf.size() * sizeof(fast::ShellFast));
+    const size_t reflOff = h->fast_lut_off + align256(lut.size() * sizeof(fast::EnergyLUT));
+    if (h->fast_blob) { cudaFree(h->fast_blob); h->fast_blob = nullptr; }
+    SART_CUDA(cudaMalloc(&h->fast_blob, reflOff + align256(nRefl * sizeof(float)) + 256));
+    base = static_cast<unsigned char*>(h->fast_blob);
+    if (nRefl) {
+      std::vector<float> rf(nRefl);
+      for (size_t i = 0; i < nRefl; ++i) rf[i] = float(t->reflectivity[i]);
+      SART_CUDA(cudaMemcpy(base + reflOff, rf.data(), nRefl * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    h->ftables.refl = reinterpret_cast<const float*>(base + reflOff);
+    h->ftables.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
+    h->ftables.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
+    h->ftables.radiusCDF = h->tables.fluxRadiusCDF;
+    h->ftables.radiusGuide = h->tables.radiusGuide;
+    h->ftables.energyCDF = h->tables.diffFluxCDFs;
+    h->ftables.energyGuide = h->tables.energyGuide;
+  }
+  SART_CUDA(cudaMemcpy(base + h->fast_shell_off, shf.data(), shf.size() * sizeof(fast::ShellFast), cudaMemcpyHostToDevice));
+  SART_CUDA(cudaMemcpy(base + h->fast_lut_off, lut.data(), lut.size() * sizeof(fast::EnergyLUT), cudaMemcpyHostToDevice));
+  return SART_OK;
+}
+
 static int ensure_image(sart_handle* h, int nMasses) {
   const size_t len = size_t(nMasses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
   if (h->d_image && h->image_masses == nMasses) return SART_OK;
@@ -221,6 +273,7 @@ int sart_create(const sart_setup_t* setup, const sart_tables_t* tables, int devi
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
   derive_params(h->setup, tables, &h->params);
   if ((rc = upload_tables(h, tables))) { sart_destroy(h); return rc; }
+  if ((rc = upload_fast(h, tables))) { sart_destroy(h); return rc; }
   if ((e = cudaMalloc(&h->d_masses, SART_MAX_MASSES * sizeof(double))) != cudaSuccess) { sart_destroy(h); return cuda_fail(e, "cudaMalloc"); }
   h->n_masses = 1;
   h->masses[0] = setup->consts.mAxion;
@@ -235,7 +288,7 @@ void sart_destroy(sart_handle_t* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->table_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
+  cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
   cudaFree(h->d_counters); cudaFree(h->d_stage);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -261,6 +314,8 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
   SART_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(h->table_blob) + h->shell_offset, shells.data(),
                             shells.size() * sizeof(ShellF64), cudaMemcpyHostToDevice, h->stream));
   SART_CUDA(cudaStreamSynchronize(h->stream));
+  if ((rc = upload_fast(h, nullptr))) return rc;
+  if (h->precision == 1 && !h->fast_ok) h->precision = 0;
   if (h->n_masses == 1 && h->masses_default) {
     h->masses[0] = setup->consts.mAxion;
     SART_CUDA(cudaMemcpyAsync(h->d_masses, h->masses, sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -286,12 +341,13 @@ int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV) {
 
 int sart_set_precision(sart_handle_t* h, int mode) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
-  if (mode != 0) return fail(SART_ERR_ARG, "precision mode %d not available in this build", mode);
+  if (mode != 0 && mode != 1) return fail(SART_ERR_ARG, "unknown precision mode %d", mode);
+  if (mode == 1 && !h->fast_ok) return fail(SART_ERR_CONFIG, "fast pipeline unavailable for this setup: %s", h->fast_why);
   h->precision = mode;
   return SART_OK;
 }
 
-int sart_has_precision(int mode) { return mode == 0; }
+int sart_has_precision(int mode) { return mode == 0 || mode == 1; }
 
 void* sart_stream(sart_handle_t* h) { return h ? h->stream : nullptr; }
 
@@ -412,13 +468,24 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
   if ((rc = ensure_stage(h, outBytes))) return rc;
   sart_ray_out_t dev;
   carve_out(static_cast<unsigned char*>(h->d_stage), n, *out, &dev);
-  SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], first_ray, n, seed, dev, h->stream));
+  if (h->precision == 1) {
+    // fast mode fills x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
+    SART_CUDA(cudaMemsetAsync(h->d_stage, 0, outBytes, h->stream));
+    SART_CUDA(launch_mc_rays_fast(h->fparams, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
+  } else {
+    SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], first_ray, n, seed, dev, h->stream));
+  }
   return copy_out(h, n, *out, dev);
 }
 
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   DeviceGuard dg(h->device);
+  if (h->precision == 1 && h->n_masses == 1) {
+    SART_CUDA(launch_mc_image_fast(h->fparams, h->ftables, h->masses[0], first_ray, n_rays, seed, h->d_image,
+                                   h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+    return SART_OK;
+  }
   SART_CUDA(launch_mc_image_exact(h->params, h->tables, h->n_masses, h->d_masses, first_ray, n_rays, seed, h->d_image,
                                   h->d_image_w2, h->d_counters, h->sm_count, h->stream));
   return SART_OK;

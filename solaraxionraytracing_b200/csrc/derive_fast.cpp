@@ -1,0 +1,163 @@
+// derive_fast.cpp — host derivation of the parameter blocks and look-up tables of the "fast" pipeline.
+//
+// What the reference evaluates per ray but depends only on the (tabulated, hence discrete — rt:470) axion energy
+// is tabulated once per energy index here: window / strongback / detector-gas transmissions (rt:2170-2190, linear
+// interpolation on the Henke grids), the energy cell and in-cell offset of the bilinear reflectivity lookup
+// (rt:1567-1578) and the He mass attenuation of the buffer-gas stage (axionMassforMagnet.nim:70-73).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "fast_params.h"
+#include "sart_internal.h"
+
+namespace sart {
+namespace fast {
+
+static constexpr double kPi = 3.141592653589793;
+
+static double lin1d(const sart_interp1d_t& t, double x) {  // numericalnim newLinear1D.eval, clamped
+  const int n = t.n;
+  if (n < 1 || !t.x || !t.y) return 0.0;
+  if (n == 1) return t.y[0];
+  x = std::min(std::max(x, t.x[0]), t.x[n - 1]);
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (t.x[mid] <= x) lo = mid; else hi = mid;
+  }
+  return t.y[lo] + (x - t.x[lo]) * ((t.y[lo + 1] - t.y[lo]) / (t.x[lo + 1] - t.x[lo]));
+}
+
+static double he_density(double p, double temp) {  // axionMassforMagnet.nim:4-15
+  return (p * 1e2) * 4.002602 / (8.314 * temp * 1000.0) / 1000.0;
+}
+
+bool supported(const sart_setup_t& s, const char** why) {
+  const sart_telescope_t& t = s.telescope;
+  if (t.reflKind == SART_RK_EFFECTIVE_AREA && !(s.flags & SART_CF_IGNORE_REFLECTION)) {
+    *why = "effective-area reflectivity (rkEffectiveArea) is only implemented in the exact pipeline";
+    return false;
+  }
+  if (t.kind == SART_TK_XMM && t.holeType != SART_HT_NONE) {
+    *why = "XMM with a hole in the optics is only implemented in the exact pipeline";
+    return false;
+  }
+  for (int j = 1; j < t.nShells; ++j)
+    if (!(t.allR1[j] > t.allR1[j - 1] + t.allThickness[j - 1])) {
+      *why = "shell radii must increase and shells must not overlap for the fast pipeline";
+      return false;
+    }
+  return true;
+}
+
+void derive_shells(const sart_setup_t& s, const ShellF64* a, ShellFast* out) {
+  const sart_telescope_t& t = s.telescope;
+  const double l = t.lMirror;
+  for (int j = 0; j < t.nShells; ++j) {
+    ShellFast& o = out[j];
+    std::memset(&o, 0, sizeof o);
+    const double beta = t.allAngles[j] * (kPi / 180.0), beta3 = 3.0 * beta;
+    o.R1 = a[j].R1; o.R1pT = a[j].R1pT; o.r1sq = a[j].r1sq;
+    o.tan1 = a[j].tan1; o.zmax1 = a[j].zmax1; o.cosb = std::cos(beta); o.sinb = std::sin(beta);
+    o.r4 = a[j].r4; o.tan2 = a[j].tan2; o.dm = a[j].distanceMirrors; o.zmax2 = a[j].zmax2;
+    o.cos3b = std::cos(beta3); o.sin3b = std::sin(beta3);
+    o.ddWin = a[j].ddWin; o.distDet = a[j].distDet;
+    o.p_e = a[j].p_e; o.p_c0 = a[j].p_r3sq + a[j].p_e * l; o.p_r3sq = a[j].p_r3sq; o.p_r3tan = a[j].p_r3tan;
+    o.h_e = a[j].h_e; o.h_g = a[j].h_g; o.h_r3sq = a[j].h_r3sq; o.h_r3tan = a[j].h_r3tan;
+    o.h_inv_nden = a[j].h_nden != 0.0 ? 1.0 / a[j].h_nden : 0.0;
+  }
+}
+
+void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
+  std::memset(f, 0, sizeof *f);
+  f->radiusCB2 = P.radiusCB * P.radiusCB;
+  f->radiusCB = P.radiusCB;
+  f->lengthB = P.lengthB;
+  f->dzExitCB = P.zExitCB - P.lengthB;
+  f->dzPipe1 = P.zPipe1 - P.lengthB;
+  f->dzPipe2 = P.zPipe2 - P.lengthB;
+  f->rPipe12 = P.rPipe1 * P.rPipe1;
+  f->cosTX = P.cosTX; f->sinTX = P.sinTX; f->cosTY = P.cosTY; f->sinTY = P.sinTY;
+  f->halfLenTel = P.halfLenTel; f->oeX = P.oeX; f->oeY = P.oeY;
+  f->zExitCBtel = P.zExitCB - P.zPipe2;
+  f->lMirror = P.lMirror;
+  f->cosPipe = P.cosPipe; f->sinPipe = P.sinPipe; f->dShift = P.dShift;
+  f->lateralShift = P.lateralShift; f->transversalShift = P.transversalShift;
+  f->radiusWindow2 = P.radiusWindow * P.radiusWindow;
+  f->chipCX = P.chipCX; f->chipCY = P.chipCY;
+  f->cosTheta = P.cosTheta; f->sinTheta = P.sinTheta;
+  f->stripDist = P.stripDist; f->stripWidth = P.stripWidth;
+  f->invBinX = double(SART_IMAGE_BINS) / (2.0 * P.chipCX);
+  f->invBinY = double(SART_IMAGE_BINS) / (2.0 * P.chipCY);
+  f->sunDist = s.consts.distanceSunEarth;
+  f->radiusSun = s.consts.radiusSun;
+  {
+    const double k = (P.g_agamma * 1e-9) * (P.B * P.tesla_to_eV2) * (1e-3 * P.m_to_inv_eV) / 2.0;
+    f->convK = float(k * k);
+  }
+  f->exposure = float(P.exposureFactor);
+  f->angleMin = float(P.angleMin); f->angleMax = float(P.angleMax);
+  f->invReflDx = float(1.0 / P.reflDx);
+  // buffer gas (axionMassforMagnet.nim:51-61, 75-113); note pGas is in bar but consumed as mbar (quirk Q4)
+  {
+    const double rhoMagnet = he_density(P.pGas, P.tGas), rhoPipe = he_density(P.pGas, P.roomTemp);
+    f->gasGamma0 = 1.97e-7 * 100.0 * rhoMagnet;
+    const double ne = 2.0 * 6.022e23 * ((P.pGas * 1e2) / (8.314 * P.tGas));  // amountMol / vol
+    const double mg = std::sqrt(std::pow(1.97e-7, 3.0) * 4.0 * kPi * (1.0 / 137.0) * ne / 511e3);
+    f->gasMgamma2 = mg * mg;
+    const double t1 = (P.g_agamma * 1e-9) * (P.B * 1e3 / 1.444) / 2.0;
+    f->gasTerm1 = t1 * t1;
+    f->gasRhoPipe100 = rhoPipe * 100.0;
+    f->gasRhoMagnet100 = rhoMagnet * 100.0;
+  }
+  f->srcX = P.srcX; f->srcY = P.srcY; f->srcZ = P.srcZ; f->srcRadius = P.srcRadius;
+  f->colDz = P.colZ - P.srcZ;
+  f->srcRadius2 = P.srcRadius * P.srcRadius;
+  f->srcEnergy = float(P.srcEnergy);
+  f->telKind = P.telKind; f->nShells = P.nShells; f->reflKind = P.reflKind; f->nCoatings = P.nCoatings;
+  f->stage = P.stage; f->nStripHalf = P.nStripHalf; f->testXray = P.testXray; f->parallelSource = P.parallelSource;
+  for (int i = 0; i < SART_MAX_COATINGS; ++i) f->layers[i] = P.layers[i];
+  f->flags = P.flags;
+  f->nRadii = P.nRadii; f->nEnergies = P.nEnergies; f->nAngles = P.nAngles; f->nReflEnergies = P.nReflEnergies;
+  f->shellsMonotonic = 1;
+  f->srcEIdx = P.nEnergies;  // the record after the tabulated energies holds the X-ray source energy
+}
+
+static EnergyLUT lut_entry(double E, const Params& P, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
+                           const sart_interp1d_t& ga) {
+  // A transmission that is non-zero in f64 must stay non-zero in the f32 table: `passed` means weight != 0
+  // (rt:2220), and e.g. 200 um of Si transmit 1e-60 at 0.3 keV.
+  auto f32nz = [](double v) { return (v != 0.0 && std::fabs(v) < 1.2e-38) ? float(std::copysign(1.2e-38, v)) : float(v); };
+  EnergyLUT e;
+  e.E = float(E);
+  e.Twindow = f32nz(lin1d(wd, E));
+  e.Tstrongback = f32nz(lin1d(sb, E));
+  e.Agas = f32nz(lin1d(ga, E));
+  if (P.nReflEnergies >= 2) {
+    const double y = std::min(std::max(E, P.reflEMin), P.reflEMax);
+    const double fy = (y - P.reflEMin) / P.reflDy;
+    int j = int(std::floor(fy));
+    if (j > P.nReflEnergies - 2) j = P.nReflEnergies - 2;
+    e.j = j;
+    e.yc = float(fy - double(j));
+  } else {
+    e.j = 0; e.yc = 0.f;
+  }
+  const double lma = -1.5832 + 5.9195 * std::exp(-0.353808 * E) + 4.03598 * std::exp(-0.970557 * E);
+  e.massAtt = float(std::exp(lma));
+  e.inv2E = float(1.0 / (2.0 * (E * 1000.0)));
+  return e;
+}
+
+// nEnergies records (E = max(0.03 keV, energies[i]), rt:470-471) + one for the X-ray test-source energy.
+void build_energy_lut(const Params& P, int nE, const double* energies, const sart_interp1d_t& sb,
+                      const sart_interp1d_t& wd, const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out) {
+  out->resize(size_t(nE) + 1);
+  for (int i = 0; i < nE; ++i) (*out)[i] = lut_entry(std::max(0.03, energies[i]), P, sb, wd, ga);
+  (*out)[nE] = lut_entry(srcEnergy, P, sb, wd, ga);
+}
+
+}  // namespace fast
+}  // namespace sart

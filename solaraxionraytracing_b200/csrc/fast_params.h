@@ -1,0 +1,63 @@
+// fast_params.h — POD blocks of the "fast" pipeline (kernels_fast.cu), filled on the host by derive_fast.cpp.
+#pragma once
+#include <cstdint>
+
+#include "device_params.h"
+
+namespace sart {
+namespace fast {
+
+// Shell record in shared memory (built from ShellF64 on the host, see derive_fast_shells).
+struct ShellFast {
+  double R1, R1pT, r1sq;
+  double tan1, zmax1, cosb, sinb;
+  double r4, tan2, dm, zmax2, cos3b, sin3b;
+  double ddWin, distDet;
+  // Wolter-I
+  double p_e, p_c0, p_r3sq, p_r3tan;                       // paraboloid: rho^2 = r3^2 + e (l - z); c0 = r3^2 + e l
+  double h_e, h_g, h_r3sq, h_r3tan, h_inv_nden;            // hyperboloid: rho^2 = r3^2 + e (l-z) + g (l-z)^2
+  double pad;
+};
+static_assert(sizeof(ShellFast) % 16 == 8, "odd number of doubles keeps shared-memory rows off the same banks");
+
+struct FastParams {
+  // geometry (FP64)
+  double radiusCB2, lengthB, dzExitCB, dzPipe1, dzPipe2, rPipe12;  // dz* = plane z - lengthB
+  double cosTX, sinTX, cosTY, sinTY, halfLenTel, oeX, oeY, zExitCBtel;  // zExitCBtel = zExitCB - zPipe2
+  double lMirror, cosPipe, sinPipe, dShift, lateralShift, transversalShift;
+  double radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invBinX, invBinY;
+  double sunDist, radiusSun, radiusCB;
+  // weights (FP32)
+  float convK;         // (g*1e-9 * B*T2eV2 * 1e-3*m2eV / 2)^2: conversionProb = convK * pathCB^2 (rt:363-365)
+  float exposure;
+  float angleMin, angleMax, invReflDx;
+  // gas stage (FP64 constants of axionMassforMagnet.nim)
+  double gasGamma0, gasMgamma2, gasTerm1, gasRhoPipe100, gasRhoMagnet100;
+  // X-ray source
+  double srcX, srcY, srcZ, srcRadius, colDz, srcRadius2;
+  float srcEnergy;
+  int32_t telKind, nShells, reflKind, nCoatings, stage, nStripHalf, testXray, parallelSource;
+  int32_t layers[SART_MAX_COATINGS];
+  uint32_t flags;
+  int32_t nRadii, nEnergies, nAngles, nReflEnergies, shellsMonotonic, srcEIdx;
+};
+
+struct EnergyLUT {  // one record per tabulated energy index (32 B)
+  float E, Twindow, Tstrongback, Agas;
+  float yc;        // offset inside the reflectivity energy cell, in units of the cell (0..1)
+  int32_t j;       // reflectivity energy cell
+  float massAtt;   // exp(logMassAttenuation(E)) am:70-73
+  float inv2E;     // 1 / (2 E[eV])
+};
+
+struct FastTables {
+  const double* radiusCDF; const uint16_t* radiusGuide;
+  const double* energyCDF; const uint16_t* energyGuide;
+  const EnergyLUT* elut;
+  const float* refl;          // [coat][nAngles][nReflEnergies]
+  const ShellFast* shells;    // [nShells]
+};
+
+
+}  // namespace fast
+}  // namespace sart

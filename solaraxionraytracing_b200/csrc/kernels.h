@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "device_params.h"
+#include "fast_params.h"
 
 namespace sart {
 
@@ -18,6 +19,13 @@ cudaError_t launch_mc_image_exact(const Params& P, const Tables& T, int nMasses,
 cudaError_t launch_build_cdfs(int nR, int nE, const double* radii, const double* energies, const double* emRates,
                               double* rowTotals, double* cdfs, double* radiusCDF, cudaStream_t s);
 
+// ---- "fast" pipeline (kernels_fast.cu)
+cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
+                                 uint64_t nRays, uint64_t seed, double* image, double* imageW2,
+                                 sart_counters_t* counters, int smCount, cudaStream_t s);
+
+cudaError_t launch_mc_rays_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
+                                uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount, cudaStream_t s);
 cudaError_t launch_heatmap(int rows, int cols, double start_x, double step_x, double start_y, double step_y, size_t n,
                            const double* X, const double* Y, const double* W, double norm, double* result,
                            unsigned long long* nBad, cudaStream_t s);

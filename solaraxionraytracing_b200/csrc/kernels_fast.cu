@@ -1,0 +1,576 @@
+// kernels_fast.cu — the "fast" fused Monte Carlo kernel (precision mode 1), sm_100a.
+//
+// Same physics as traceAxion (src/raytracer.nim:1736-2221) but formulated for throughput instead of for bitwise
+// agreement with the reference's operation order:
+//   * the ray is carried as (point on the exit disc of the magnetic field, slopes dx/dz, dy/dz) instead of two
+//     points 1.5e14 mm apart, which removes the catastrophic cancellation the reference suffers at solar
+//     distances (DESIGN.md "Numerical floor") — geometry is FP64 *algebra* only: no FP64 transcendental, and every
+//     FP64 divide / sqrt is an FP32 MUFU seed plus one Newton step in FP64 (relative error ~1e-14);
+//   * the reflection is written without trigonometry: with s = n.v (unit normal, unit ray) the reference's
+//     "rotate v by 2*alpha about n x v" (rt:762-780) is v' = v (1 - 2 s^2 + 2 |s| s) - 2 |s| n;
+//   * everything that only scales the weight (emission direction sines, grazing angles for the reflectivity
+//     lookup, cos(yaw), transmissions) is FP32 with MUFU intrinsics; transmissions, the energy and the reflectivity
+//     cell of each of the nE tabulated energies come from a per-energy-index LUT built once at sart_create;
+//   * CDF searches start from a 256-bucket guide table, so they touch 2-4 entries instead of 11;
+//   * run-wide tables (radius CDF, guide, shell constants) are staged once per block in shared memory;
+//   * counters live in registers / per-warp shared memory and are flushed once per block.
+// Exit codes follow the same decision sequence as the exact pipeline, so the counters of both are comparable.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+
+#include "fast_params.h"
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace sart {
+namespace fast {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+
+// ---- FP64 divide / sqrt from FP32 seeds ---------------------------------------------------------------------
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r = double(__frcp_rn(float(x)));
+  const double e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y = double(rsqrtf(float(x)));
+  const double h = 0.5 * x * y;
+  return fma(y, fma(-h, y, 0.5), y);  // y * (1.5 - 0.5 x y^2)
+}
+
+struct D3 { double x, y, z; };
+
+// ---- shared memory layout -----------------------------------------------------------------------------------
+struct WarpCounters { unsigned int n_exit[16]; unsigned int n_clamped; unsigned int pad[3]; };
+
+// lowerBound restricted to the guide window [lo, hi]
+__device__ __forceinline__ int lower_bound_window(const double* __restrict__ a, int lo, int hi, double key) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Picks the root the reference picks (rt:646-658): roots of A t^2 + 2 hb t + C = 0 in the reference's order
+// root1 = (-hb - sq)/A, root2 = (-hb + sq)/A, each accepted only if zmin < pz + t dz < zmax. Returns false if none.
+__device__ __forceinline__ bool pick_root(double A, double hb, double C, double pz, double dz, double zmin, double zmax,
+                                          double& t) {
+  const double disc = fma(hb, hb, -A * C);
+  if (!(disc >= 0.0)) return false;
+  const double sq = disc > 1e-30 ? disc * rsqrt_nr(disc) : 0.0;
+  // stable pair: q = -(hb + sign(hb) sq); roots q/A and C/q
+  const double q = -(hb + copysign(sq, hb));
+  const double ra = q * rcp_nr(A);   // = (-hb - sign(hb) sq)/A
+  const double rb = C * rcp_nr(q);   // the other root
+  // (-hb - sq)/A is `ra` when hb >= 0, `rb` otherwise
+  const double root1 = (hb >= 0.0) ? ra : rb;
+  const double root2 = (hb >= 0.0) ? rb : ra;
+  const double z1 = fma(root1, dz, pz), z2 = fma(root2, dz, pz);
+  if (z1 > zmin && z1 < zmax) { t = root1; return true; }
+  if (z2 > zmin && z2 < zmax) { t = root2; return true; }
+  return false;
+}
+
+// Reflection of unit vector v off unit normal n (rt:762-780 without trigonometry); returns |n.v| = sin(alpha).
+__device__ __forceinline__ double reflect(D3 n, D3& v) {
+  const double s = n.x * v.x + n.y * v.y + n.z * v.z;
+  const double as = fabs(s);
+  const double f = fma(2.0 * as, s, fma(-2.0 * s, s, 1.0));  // 1 - 2 s^2 + 2 |s| s
+  v.x = fma(v.x, f, -2.0 * as * n.x);
+  v.y = fma(v.y, f, -2.0 * as * n.y);
+  v.z = fma(v.z, f, -2.0 * as * n.z);
+  return as;
+}
+
+__device__ __forceinline__ float bilinear(const FastParams& P, const float* __restrict__ z, float alphaDeg, int j,
+                                          float yc, bool& clamped) {
+  float x = alphaDeg;
+  if (!(x >= P.angleMin)) { x = P.angleMin; clamped = true; }
+  if (!(x <= P.angleMax)) { x = P.angleMax; clamped = true; }
+  const float fx = (x - P.angleMin) * P.invReflDx;
+  int i = int(fx);
+  if (i > P.nAngles - 2) i = P.nAngles - 2;
+  const float xc = fx - float(i);
+  const float* r0 = z + size_t(i) * P.nReflEnergies + j;
+  const float z00 = __ldg(r0), z01 = __ldg(r0 + 1), z10 = __ldg(r0 + P.nReflEnergies), z11 = __ldg(r0 + P.nReflEnergies + 1);
+  const float a = fmaf(yc, z01 - z00, z00), b = fmaf(yc, z11 - z10, z10);
+  return fmaf(xc, b - a, a);
+}
+
+struct RayResult {
+  int code;       // exit code | flags
+  int bin;        // image bin or -1
+  int shell;
+  float energy;
+  double w, x, y, r;
+};
+
+template <bool kWolter>
+__device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const double* __restrict__ sRadCDF,
+                                          const uint16_t* __restrict__ sRadGuide, const ShellFast* __restrict__ sShell,
+                                          uint64_t seed, uint64_t ray, double mAxion2, RayResult& out) {
+  out.bin = -1; out.w = 0.0; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
+  uint32_t w[6];
+  ray_words(seed, ray, w);
+  constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
+  bool clamped = false;
+
+  // ================= sampling rt:1754-1764 (or the X-ray test source rt:1765-1801)
+  double ex, ey, sx, sy;   // point on the exit disc of the field (z = lengthB) and slopes
+  int eIdx;
+  if (!P.testXray) {
+    // emission shell (exact index: same f64 CDF, same key as the oracle)
+    const double ur = u01(w[2]);
+    const int kr = int(ur * double(kGuide));
+    const int rIdx = lower_bound_window(sRadCDF, sRadGuide[kr], sRadGuide[kr + 1], ur);
+    const float rs = (0.0015f + float(rIdx) * 0.0005f);  // fraction of the solar radius (weight-free: direction only)
+    float s1, c1, s2, c2;
+    sincospif(2.0f * (float(w[0]) * k2m32), &s1, &c1);    // phi = 360 u0
+    sincospif(float(w[1]) * k2m32, &s2, &c2);             // theta = 180 u1 (uniform in theta, quirk Q7)
+    const double rsun = double(rs) * P.radiusSun;
+    const double Ox = rsun * double(c1 * s2), Oy = rsun * double(s1 * s2), Ozr = rsun * double(c2);
+    // exit disc rt:412-422
+    float sd, cd;
+    sincospif(2.0f * (float(w[4]) * k2m32), &sd, &cd);
+    const float rd = sqrtf((float(w[3]) + 0.5f) * k2m32);
+    ex = P.radiusCB * double(rd * cd);
+    ey = P.radiusCB * double(rd * sd);
+    const double invD = rcp_nr(P.lengthB + P.sunDist - Ozr);  // lengthB - O.z
+    sx = (ex - Ox) * invD;
+    sy = (ey - Oy) * invD;
+    // energy: the reference recovers the radius index from the emission point (rt:454-460); it is rIdx again
+    const double ue = u01(w[5]);
+    const int ke = int(ue * double(kGuide));
+    const uint16_t* g = T.energyGuide + size_t(rIdx) * (kGuide + 1) + ke;
+    eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, g[0], g[1], ue);
+    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
+  } else {
+    float sd, cd;
+    sincospif(2.0f * (float(w[1]) * k2m32), &sd, &cd);
+    const float rd = sqrtf((float(w[0]) + 0.5f) * k2m32);
+    const double Ox = P.srcX + P.srcRadius * double(rd * cd), Oy = P.srcY + P.srcRadius * double(rd * sd);
+    if (P.parallelSource) {
+      ex = Ox + (0.5 * u01(w[2]) - 0.25);
+      ey = Oy + (0.5 * u01(w[3]) - 0.25);
+    } else {
+      sincospif(2.0f * (float(w[3]) * k2m32), &sd, &cd);
+      const float r2 = sqrtf((float(w[2]) + 0.5f) * k2m32);
+      ex = P.radiusCB * double(r2 * cd);
+      ey = P.radiusCB * double(r2 * sd);
+    }
+    const double invD = rcp_nr(P.lengthB - P.srcZ);
+    sx = (ex - Ox) * invD;
+    sy = (ey - Oy) * invD;
+    // collimator rt:1800: point at z = colZ relative to the source centre
+    const double qx = fma(sx, P.colDz, Ox) - P.srcX, qy = fma(sy, P.colDz, Oy) - P.srcY;
+    eIdx = P.srcEIdx;
+    if (!(qx * qx + qy * qy < P.srcRadius2)) { out.code = SART_EXIT_COLLIMATOR; return; }
+  }
+
+  // ================= bore and pipes rt:1813-1872: points of the line at the clip planes
+  const double s2sum = fma(sx, sx, sy * sy);
+  const double p0x = fma(-sx, P.lengthB, ex), p0y = fma(-sy, P.lengthB, ey);
+  const bool hitEntrance = fma(p0x, p0x, p0y * p0y) < P.radiusCB2;
+  const double pex = fma(sx, P.dzExitCB, ex), pey = fma(sy, P.dzExitCB, ey);
+  const bool insideExit = fma(pex, pex, pey * pey) < P.radiusCB2;
+  if (!insideExit) { out.code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE; return; }
+  // (a ray that misses the entrance disc but is inside at the exit entered through the wall exactly once)
+  double path2;  // pathCB^2 rt:1843
+  if (hitEntrance) {
+    path2 = P.lengthB * P.lengthB * (1.0 + s2sum);
+  } else {
+    // wall crossing |e + s t|^2 = R^2, t < 0
+    const double hb = fma(ex, sx, ey * sy), c = fma(ex, ex, ey * ey) - P.radiusCB2;
+    const double disc = fma(hb, hb, -s2sum * c);
+    const double sq = disc > 1e-30 ? disc * rsqrt_nr(disc) : 0.0;
+    const double t1 = (hb >= 0.0) ? -(hb + sq) * rcp_nr(s2sum) : c * rcp_nr(sq - hb);
+    path2 = t1 * t1 * (1.0 + s2sum);
+  }
+  {
+    const double qx = fma(sx, P.dzPipe1, ex), qy = fma(sy, P.dzPipe1, ey);
+    if (!(fma(qx, qx, qy * qy) < P.rPipe12)) { out.code = SART_EXIT_CLIP_PIPE_VT3; return; }
+  }
+  double x0 = fma(sx, P.dzPipe2, ex), y0 = fma(sy, P.dzPipe2, ey);
+  if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) { out.code = SART_EXIT_CLIP_PIPE_XRT; return; }  // quirk Q2
+
+  // ================= telescope frame rt:1888-1905 (rotation about (0, 0, halfLenTel); identity when not turned)
+  double dx = sx, dy = sy, dz = 1.0, z0 = 0.0;
+  if (P.sinTX != 0.0 || P.sinTY != 0.0) {
+    // rotateInX then rotateInY of point (x0, y0, 0) and of the direction
+    double zt = 0.0 - P.halfLenTel;
+    double xr = x0 * P.cosTX + zt * P.sinTX, zr = zt * P.cosTX - x0 * P.sinTX;
+    double yr = y0 * P.cosTY - zr * P.sinTY;
+    zr = zr * P.cosTY + y0 * P.sinTY;
+    x0 = xr; y0 = yr; z0 = zr + P.halfLenTel;
+    double ddx = dx * P.cosTX + dz * P.sinTX, ddz = dz * P.cosTX - dx * P.sinTX;
+    double ddy = dy * P.cosTY - ddz * P.sinTY;
+    ddz = ddz * P.cosTY + dy * P.sinTY;
+    dx = ddx; dy = ddy; dz = ddz;
+  }
+  x0 -= P.oeX; y0 -= P.oeY;
+  // renormalise to dz = 1 and move to the plane z = 0
+  const double invdz = (dz == 1.0) ? 1.0 : rcp_nr(dz);
+  const double tx = dx * invdz, ty = dy * invdz;  // slopes in the telescope frame
+  x0 = fma(-z0, tx, x0); y0 = fma(-z0, ty, y0);   // pointEntranceXRT
+  const double rho0sq = fma(x0, x0, y0 * y0);
+  const double invRho0 = rsqrt_nr(rho0sq);
+  const double radialDist = rho0sq * invRho0;
+  const double t2sum = fma(tx, tx, ty * ty);
+  const double invLen = rsqrt_nr(1.0 + t2sum);
+
+  // ================= opaque structures rt:1635-1704
+  if (kWolter) {
+    const bool xmm = P.telKind == SART_TK_XMM;
+    bool hit = false;
+    const float zs = xmm ? -85.0f : -35.0f;
+    const float phiF = acosf(float(x0 * invRho0)) * 57.29577951308232f;
+    const float xs = float(fma(double(zs), tx, x0)), ys = float(fma(double(zs), ty, y0));
+    const float phiS = acosf(xs * rsqrtf(xs * xs + ys * ys)) * 57.29577951308232f;
+    if (xmm) {
+      if (radialDist <= 64.7) hit = true;  // htNone hole: always opaque (rt:1674-1688)
+      else if (radialDist < 151.6 && radialDist > (151.6 - 20.9)) hit = true;
+      else {
+        // |phi - 22.5 k| <= 1.145 for some k in 0..16 (phi in [0, 180])
+        const float a = fabsf(phiF - 22.5f * rintf(phiF * (1.0f / 22.5f)));
+        const float b = fabsf(phiS - 22.5f * rintf(phiS * (1.0f / 22.5f)));
+        hit = (a <= 1.145f) || (b <= 1.145f);
+      }
+    } else {
+      if (radialDist < 37.5) hit = true;
+      else {
+        const float a = fabsf(phiF - 60.0f * rintf(phiF * (1.0f / 60.0f)));
+        const float b = fabsf(phiS - 60.0f * rintf(phiS * (1.0f / 60.0f)));
+        hit = (a <= 3.75f) || (b <= 3.75f);
+      }
+    }
+    if (hit) { out.code = SART_EXIT_OPAQUE; return; }
+  }
+
+  // ================= shell rt:1932-1957
+  const int nS = P.nShells;
+  if (radialDist > sShell[nS - 1].R1) { out.code = SART_EXIT_OUTSIDE_SHELLS; return; }
+  int hitLayer;
+  {
+    int lo = 0, hi = nS - 1;  // first j with R1[j] > radialDist
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sShell[mid].R1 > radialDist) hi = mid; else lo = mid + 1;
+    }
+    hitLayer = lo;
+    if (!(sShell[hitLayer].R1 > radialDist)) { out.code = SART_EXIT_NO_MIRROR_HIT; return; }  // == R1[last]
+    if (hitLayer > 0 && radialDist > sShell[hitLayer - 1].R1 && radialDist < sShell[hitLayer - 1].R1pT) {
+      out.code = SART_EXIT_GLASS_FRONT; return;
+    }
+  }
+  const ShellFast& sh = sShell[hitLayer];
+  const double lM = P.lMirror;
+  const double below = hitLayer > 0 ? sShell[hitLayer - 1].R1pT : 0.0;
+
+  // ================= mirror 1 rt:1983-2020. Ray: (x0 + tx z, y0 + ty z, z).
+  double z1;
+  bool hit1;
+  if (kWolter) {   // paraboloid rho^2 = r3^2 + e (l - z)  (findPosParabolic rt:660-690)
+    hit1 = pick_root(t2sum, fma(x0, tx, y0 * ty) + 0.5 * sh.p_e, rho0sq - sh.p_c0, 0.0, 1.0, 0.0, sh.zmax1, z1);
+  } else {         // cone rho = r1 - tan(beta) z  (findPosCone rt:628-658)
+    hit1 = pick_root(t2sum - sh.tan1 * sh.tan1, fma(x0, tx, y0 * ty) + sh.tan1 * sh.R1, rho0sq - sh.r1sq, 0.0, 1.0,
+                     0.0, sh.zmax1, z1);
+  }
+  if (!hit1) {
+    // The reference carries on with pointMirror1 = pointExitCB (start point returned, rt:655-658) and reaches the
+    // nickel test before the degenerate-hit test (rt:2040-2057): reproduce which of the two exits it takes.
+    int code = SART_EXIT_NO_MIRROR_HIT;
+    if (hitLayer > 0) {
+      const double zc = P.zExitCBtel;  // pointExitCB.z in the telescope frame (not turned: exact; turned: approx.)
+      const double xc = fma(zc, tx, x0), yc = fma(zc, ty, y0);
+      const double rc = sqrt(fma(xc, xc, yc * yc));
+      double nz;
+      if (kWolter) nz = rc * sh.p_r3tan * rsqrt_nr(fmax(fma(sh.p_e, lM - zc, sh.p_r3sq), 1e-300));
+      else nz = sh.tan1 * rc;
+      const double sg = (fma(xc, tx, yc * ty) + nz) * invLen * rsqrt_nr(fma(rc, rc, nz * nz));
+      const double a = fabs(sg);
+      const double lhs = a * (lM - zc), rhs = (sh.R1 - below) * sqrt(fmax(1.0 - a * a, 0.0));
+      if (lhs > rhs) code = SART_EXIT_NICKEL;
+    }
+    out.code = code;
+    return;
+  }
+  D3 pm = {fma(tx, z1, x0), fma(ty, z1, y0), z1};
+  D3 v = {tx * invLen, ty * invLen, invLen};
+  double sinA1;
+  {
+    const double rr = fma(pm.x, pm.x, pm.y * pm.y);
+    const double ir = rsqrt_nr(rr);
+    D3 n;
+    if (kWolter) {  // calcNormalVec msParabolic rt:740-746: n = (x, y, rho r3 tan / sqrt(r3^2 + e (l - z)))
+      const double nz = sh.p_r3tan * rsqrt_nr(fma(sh.p_e, lM - pm.z, sh.p_r3sq));
+      const double il = rsqrt_nr(1.0 + nz * nz);
+      n = {pm.x * ir * il, pm.y * ir * il, nz * il};
+    } else {        // msCone rt:737-739: n = (x, y, tan(beta) rho) / |.|
+      n = {pm.x * ir * sh.cosb, pm.y * ir * sh.cosb, sh.sinb};
+    }
+    sinA1 = reflect(n, v);
+  }
+  // ================= mirror 2 rt:1994-2029. Ray: pm + t v.
+  double t2;
+  bool hit2;
+  if (kWolter) {  // hyperboloid rho^2 = r3^2 + e (l - z) + g (l - z)^2  (findPosHyperbolic rt:692-729)
+    const double u = lM - pm.z;
+    const double A = fma(v.x, v.x, v.y * v.y) - sh.h_g * v.z * v.z;
+    const double hb = fma(pm.x, v.x, pm.y * v.y) + (sh.h_g * u + 0.5 * sh.h_e) * v.z;
+    const double C = fma(pm.x, pm.x, pm.y * pm.y) - sh.h_r3sq - (sh.h_e + sh.h_g * u) * u;
+    hit2 = pick_root(A, hb, C, pm.z, v.z, sh.dm, sh.zmax2, t2);
+  } else {        // cone rho = r4 - tan(3 beta) (z - distanceMirrors)
+    const double rc = sh.r4 - sh.tan2 * (pm.z - sh.dm);
+    const double A = fma(v.x, v.x, v.y * v.y) - sh.tan2 * sh.tan2 * v.z * v.z;
+    const double hb = fma(pm.x, v.x, pm.y * v.y) + sh.tan2 * rc * v.z;
+    const double C = fma(pm.x, pm.x, pm.y * pm.y) - rc * rc;
+    hit2 = pick_root(A, hb, C, pm.z, v.z, sh.dm, sh.zmax2, t2);
+  }
+  // ================= nickel of the shell below rt:1706-1734: tan(alpha1) > (r1 - below)/(l - z1)
+  if (hitLayer > 0) {
+    const double lhs = sinA1 * (lM - z1), rhs = (sh.R1 - below) * sqrt(fmax(1.0 - sinA1 * sinA1, 0.0));
+    if (lhs > rhs) { out.code = SART_EXIT_NICKEL; return; }
+  }
+  if (!hit2) { out.code = SART_EXIT_NO_MIRROR_HIT; return; }  // pointMirror2 == pointMirror1 (rt:2055)
+  pm.x = fma(t2, v.x, pm.x); pm.y = fma(t2, v.y, pm.y); pm.z = fma(t2, v.z, pm.z);
+  double sinA2;
+  {
+    const double rr = fma(pm.x, pm.x, pm.y * pm.y);
+    const double ir = rsqrt_nr(rr);
+    D3 n;
+    if (kWolter) {  // msHyperbolic rt:747-758: n = (x, y, rho / m)
+      const double u = lM - pm.z;
+      const double q1 = 1.0 + 2.0 * u * sh.h_inv_nden, q2 = 1.0 + u * sh.h_inv_nden;
+      const double nz = sh.h_r3tan * q1 * rsqrt_nr(fma(2.0 * sh.h_r3tan * u, q2, sh.h_r3sq));
+      const double il = rsqrt_nr(1.0 + nz * nz);
+      n = {pm.x * ir * il, pm.y * ir * il, nz * il};
+    } else {
+      n = {pm.x * ir * sh.cos3b, pm.y * ir * sh.cos3b, sh.sin3b};
+    }
+    sinA2 = reflect(n, v);
+  }
+  // ================= detector plane rt:797-814
+  double xw, yw, zw;
+  {
+    const double ax = pm.x * P.cosPipe + pm.z * P.sinPipe - P.dShift, az = pm.z * P.cosPipe - pm.x * P.sinPipe;
+    const double wx = v.x * P.cosPipe + v.z * P.sinPipe, wz = v.z * P.cosPipe - v.x * P.sinPipe;
+    const double n = (sh.ddWin - az) * rcp_nr(wz);
+    xw = fma(n, wx, ax); yw = fma(n, v.y, pm.y); zw = fma(n, wz, az);
+  }
+  xw -= P.lateralShift; yw -= P.transversalShift;
+  // ================= weights rt:2101-2128
+  const EnergyLUT el = T.elut[eIdx];
+  out.energy = el.E;
+  double weight;  // the factors are FP32, their product is formed in FP64 so that tiny weights do not flush to zero
+  {
+    const float ya = -atanf(float(ty)) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
+    float tm = __cosf(ya);
+    const float path2f = float(path2);
+    if (P.stage == SART_SK_VACUUM) {
+      if (!(P.flags & SART_CF_IGNORE_CONV_PROB)) tm *= P.convK * path2f;
+    } else {
+      const float pathm = sqrtf(path2f) * 1e-3f;
+      if (!(P.flags & SART_CF_IGNORE_CONV_PROB)) {   // axionConversionProb2 am:75-100
+        const double gamma = P.gasGamma0 * double(el.massAtt);
+        const double L = double(pathm) / 1.97e-7;
+        const double q = fabs(P.gasMgamma2 - mAxion2) * double(el.inv2E);
+        const float gl = float(gamma * L);
+        const float e1 = __expf(-gl), e2 = __expf(-0.5f * gl);
+        double ph = q * L;   // phase reduced in FP64 before the FP32 cosine
+        ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);
+        const float cq_ = __cosf(float(ph));
+        const double term2 = rcp_nr(fma(q, q, 0.25 * gamma * gamma));
+        tm *= float(P.gasTerm1 * term2) * (1.0f + e1 - 2.0f * e2 * cq_);
+      }
+      const float distPipe = float(zw - P.zExitCBtel) * 1e-3f;
+      tm *= __expf(-el.massAtt * float(P.gasRhoPipe100) * distPipe) * __expf(-el.massAtt * float(P.gasRhoMagnet100) * pathm);
+    }
+    float refl = 1.0f;
+    if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
+      int coat = 0;
+      if (P.reflKind == SART_RK_MULTI_COATING) {
+        while (coat < P.nCoatings - 1 && P.layers[coat] < hitLayer) ++coat;
+      }
+      const float* zt = T.refl + size_t(coat) * P.nAngles * P.nReflEnergies;
+      const float a1 = asinf(float(sinA1)) * 57.29577951308232f, a2 = asinf(float(sinA2)) * 57.29577951308232f;
+      refl = bilinear(P, zt, a1, el.j, el.yc, clamped) * bilinear(P, zt, a2, el.j, el.yc, clamped);
+    }
+    weight = double(refl) * double(tm);
+  }
+  int flags = (weight != 0.0) ? SART_FLAG_PASSED_TILL_WINDOW : 0;
+  if (clamped) flags |= SART_FLAG_INTERP_CLAMPED;
+  // ================= window aperture rt:2139-2147
+  const double rw2 = fma(xw, xw, yw * yw);
+  if ((!(P.flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > P.radiusWindow2) || fabs(xw) > P.chipCX || fabs(yw) > P.chipCY) {
+    out.code = SART_EXIT_WINDOW_APERTURE | flags; return;
+  }
+  // ================= strongback strips rt:2149-2185
+  {
+    const double yt = fabs(yw * P.cosTheta - xw * P.sinTheta);
+    int sb = 2;
+    for (int i = 0; i < P.nStripHalf; ++i) {
+      const double lo = (double(i) + 0.5) * P.stripDist + double(i) * P.stripWidth;
+      if (yt > lo && yt < lo + P.stripWidth) { sb = 1; break; }
+      sb = 0;
+    }
+    const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
+    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) weight *= double(tw);
+  }
+  if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) weight *= double(el.Agas);
+  if (!(P.flags & SART_CF_XRAY_TEST)) weight *= double(P.exposure);
+  out.shell = hitLayer;
+  out.r = sqrt(rw2);
+  out.x = -xw + P.chipCX;
+  out.y = yw + P.chipCY;
+  out.w = weight;
+  // prepareHeatmap rt:839-842
+  const int cx = int(floor(out.x * P.invBinX)), cy = int(floor(out.y * P.invBinY));
+  if (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) out.bin = cy * SART_IMAGE_BINS + cx;
+  out.code = ((weight != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
+}
+
+// ---- fused kernel ---------------------------------------------------------------------------------------------
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, 2)
+k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
+                uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
+                double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  // layout: radius CDF (f64) | shells | radius guide (u16) | per-warp counters
+  double* sRadCDF = reinterpret_cast<double*>(smem);
+  ShellFast* sShell = reinterpret_cast<ShellFast*>(sRadCDF + ((P.nRadii + 1) & ~1));
+  uint16_t* sRadGuide = reinterpret_cast<uint16_t*>(sShell + P.nShells);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(reinterpret_cast<unsigned char*>(sRadGuide) + ((2 * (kGuide + 1) + 15) & ~15));
+  for (int i = threadIdx.x; i < P.nRadii; i += kBlock) sRadCDF[i] = T.radiusCDF[i];
+  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
+    reinterpret_cast<double*>(sShell)[i] = reinterpret_cast<const double*>(T.shells)[i];
+  if (P.nRadii > 0) for (int i = threadIdx.x; i <= kGuide; i += kBlock) sRadGuide[i] = T.radiusGuide[i];
+  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int nPassed = 0, nTill = 0, nIter = 0;
+  double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
+
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
+    RayResult r;
+    trace_one<kWolter>(P, T, sRadCDF, sRadGuide, sShell, seed, first + i, mAxion2, r);
+    ++nIter;
+    const int code = r.code & SART_CODE_MASK;
+    if (r.code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
+    if (code == SART_EXIT_PASSED) {
+      ++nPassed;
+      const double wd = r.w;
+      sumW += wd; sumW2 += wd * wd; sumX += r.x; sumY += r.y; sumR += r.r;
+      if (r.bin >= 0) {
+        atomicAdd(image + r.bin, wd);
+        atomicAdd(imageW2 + r.bin, wd * wd);
+      }
+    } else {
+      atomicAdd(&wc[warp].n_exit[code], 1u);
+    }
+    if (r.code & SART_FLAG_INTERP_CLAMPED) atomicAdd(&wc[warp].n_clamped, 1u);
+  }
+  // ---- block reduction and flush
+  for (int o = 16; o > 0; o >>= 1) {
+    nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
+    nTill += __shfl_down_sync(0xffffffffu, nTill, o);
+    nIter += __shfl_down_sync(0xffffffffu, nIter, o);
+    sumW += __shfl_down_sync(0xffffffffu, sumW, o);
+    sumW2 += __shfl_down_sync(0xffffffffu, sumW2, o);
+    sumX += __shfl_down_sync(0xffffffffu, sumX, o);
+    sumY += __shfl_down_sync(0xffffffffu, sumY, o);
+    sumR += __shfl_down_sync(0xffffffffu, sumR, o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    sart_counters_t* c = counters;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_rays), (unsigned long long)nIter);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[SART_EXIT_PASSED]), (unsigned long long)nPassed);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_passed), (unsigned long long)nPassed);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_passed_till_window), (unsigned long long)nTill);
+    for (int e = 1; e < SART_N_EXIT_CODES; ++e)
+      if (wc[warp].n_exit[e]) atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[e]), (unsigned long long)wc[warp].n_exit[e]);
+    if (wc[warp].n_exit[SART_EXIT_NICKEL])
+      atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_hit_nickel), (unsigned long long)wc[warp].n_exit[SART_EXIT_NICKEL]);
+    if (wc[warp].n_clamped) atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_interp_clamped), (unsigned long long)wc[warp].n_clamped);
+    atomicAdd(&c->sum_w, sumW); atomicAdd(&c->sum_w2, sumW2);
+    atomicAdd(&c->sum_x, sumX); atomicAdd(&c->sum_y, sumY); atomicAdd(&c->sum_r, sumR);
+  }
+}
+
+// ---- per-ray records (traceAxionWrapper in fast mode) ----------------------------------------------------------
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, 2)
+k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
+                     uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ ox, double* __restrict__ oy,
+                     double* __restrict__ ow, int32_t* __restrict__ ocode, int32_t* __restrict__ oshell,
+                     double* __restrict__ oenergy, double* __restrict__ orad) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* sRadCDF = reinterpret_cast<double*>(smem);
+  ShellFast* sShell = reinterpret_cast<ShellFast*>(sRadCDF + ((P.nRadii + 1) & ~1));
+  uint16_t* sRadGuide = reinterpret_cast<uint16_t*>(sShell + P.nShells);
+  for (int i = threadIdx.x; i < P.nRadii; i += kBlock) sRadCDF[i] = T.radiusCDF[i];
+  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
+    reinterpret_cast<double*>(sShell)[i] = reinterpret_cast<const double*>(T.shells)[i];
+  if (P.nRadii > 0) for (int i = threadIdx.x; i <= kGuide; i += kBlock) sRadGuide[i] = T.radiusGuide[i];
+  __syncthreads();
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
+    RayResult r;
+    trace_one<kWolter>(P, T, sRadCDF, sRadGuide, sShell, seed, first + i, mAxion2, r);
+    ox[i] = r.x; oy[i] = r.y; ow[i] = r.w; ocode[i] = r.code; oshell[i] = r.shell;
+    if (oenergy) oenergy[i] = double(r.energy);
+    if (orad) orad[i] = r.r;
+  }
+}
+
+size_t smem_bytes(const FastParams& P) {
+  return size_t((P.nRadii + 1) & ~1) * 8 + size_t(P.nShells) * sizeof(ShellFast) + ((2 * (kGuide + 1) + 15) & ~15) +
+         kWarps * sizeof(WarpCounters);
+}
+
+}  // namespace fast
+
+cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
+                                 uint64_t nRays, uint64_t seed, double* image, double* imageW2,
+                                 sart_counters_t* counters, int smCount, cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes(P);
+  auto kern = wolter ? fast::k_trace_mc_fast<true> : fast::k_trace_mc_fast<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int perSM = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * perSM;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_rays_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
+                                uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount, cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes(P);
+  auto kern = wolter ? fast::k_trace_mc_rays_fast<true> : fast::k_trace_mc_rays_fast<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * 2;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, o.x, o.y, o.w, o.code, o.shell,
+                                        o.energy, o.r);
+  return cudaGetLastError();
+}
+
+}  // namespace sart

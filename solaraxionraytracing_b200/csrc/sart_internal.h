@@ -4,8 +4,11 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <vector>
+
 #include "../../include/sart.h"
 #include "device_params.h"
+#include "fast_params.h"
 
 typedef struct CUstream_st* cudaStream_t;
 
@@ -18,6 +21,15 @@ int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 void derive_params(const sart_setup_t& s, const sart_tables_t* tb, Params* p);
 void derive_shells(const sart_setup_t& s, ShellF64* shells /* [SART_MAX_SHELLS] */);
 
+namespace fast {
+bool supported(const sart_setup_t& s, const char** why);
+void derive_shells(const sart_setup_t& s, const ShellF64* exactShells, ShellFast* out);
+void derive_params(const sart_setup_t& s, const Params& P, FastParams* f);
+void build_energy_lut(const Params& P, int nE, const double* energies, const sart_interp1d_t& sb,
+                      const sart_interp1d_t& wd, const sart_interp1d_t& ga, double srcEnergy,
+                      std::vector<EnergyLUT>* out);
+}  // namespace fast
+
 }  // namespace sart
 
 struct sart_handle {
@@ -29,6 +41,14 @@ struct sart_handle {
   void* table_blob = nullptr;   // one allocation backing every table
   size_t table_bytes = 0;
   int precision = 0;            // 0 exact f64, 1 fast
+  // "fast" pipeline: parameter block, LUTs and f32 reflectivity in a second allocation
+  int fast_ok = 0;
+  const char* fast_why = "";
+  sart::fast::FastParams fparams;
+  sart::fast::FastTables ftables;
+  void* fast_blob = nullptr;
+  size_t fast_shell_off = 0, fast_lut_off = 0;
+  std::vector<double> h_energies, h_tab[3][2];  // host copies (energies; strongback/window/gas x,y) for LUT rebuilds
   int sm_count = 148;
   size_t shell_offset = 0;      // byte offset of the ShellF64 array inside table_blob
   int n_masses = 1;

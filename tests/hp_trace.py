@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""High-precision (mpmath, 60 digits) evaluation of traceAxion's GEOMETRY for single rays — development/validation aid.
+
+The reference's formulas (src/raytracer.nim:481-534, 628-814, 1813-2083) evaluated without rounding noise: tells which
+of two f64 results is closer to what the formulas mean. Only the happy path (entrance disc -> two mirrors -> window
+plane) is followed; returns None where the ray leaves it.
+"""
+from __future__ import annotations
+
+import mpmath as mp
+
+mp.mp.dps = 60
+
+
+def V(x, y, z):
+    return mp.matrix([x, y, z])
+
+
+def plane_point(p1, v, zc):
+    lam = (zc - p1[2]) / v[2]
+    return p1 + lam * v
+
+
+def rot_in_x(v, ang, off):
+    z = v[2] - off
+    return V(v[0] * mp.cos(ang) + z * mp.sin(ang), v[1], z * mp.cos(ang) - v[0] * mp.sin(ang) + off)
+
+
+def rot_in_y(v, ang, off):
+    z = v[2] - off
+    return V(v[0], v[1] * mp.cos(ang) - z * mp.sin(ang), z * mp.cos(ang) + v[1] * mp.sin(ang) + off)
+
+
+def pick_root(p, d, a, hb, c, zmin, zmax):
+    disc = hb * hb - a * c
+    if disc < 0:
+        return None
+    sq = mp.sqrt(disc)
+    for root in ((-hb - sq) / a, (-hb + sq) / a):
+        z = p[2] + root * d[2]
+        if zmin < z < zmax:
+            return p + root * d
+    return None
+
+
+def reflect(n, frm, to):
+    v = to - frm
+    v = v / mp.norm(v)
+    axis = V(n[1] * v[2] - n[2] * v[1], n[2] * v[0] - n[0] * v[2], n[0] * v[1] - n[1] * v[0])
+    axis = axis / mp.norm(axis)
+    alpha = mp.asin(abs((n.T * v)[0]) / mp.norm(n))
+    vba = V(v[1] * axis[2] - v[2] * axis[1], v[2] * axis[0] - v[0] * axis[2], v[0] * axis[1] - v[1] * axis[0])
+    return v * mp.cos(2 * alpha) - vba * mp.sin(2 * alpha), alpha
+
+
+def trace(setup, O, E_xy):
+    """setup: abi.Setup; O: (x, y, z) floats; E_xy: (x, y). Returns (x_chip, y_chip, shell, alpha1_deg, alpha2_deg)."""
+    m, tel, pipes = setup.magnet, setup.telescope, setup.pipes
+    mpf = mp.mpf
+    O = V(*[mpf(float(c)) for c in O])
+    E = V(mpf(float(E_xy[0])), mpf(float(E_xy[1])), mpf(m.lengthB))
+    v = E - O
+    # (rays that miss the entrance disc but enter through the bore wall follow the same line: rt:1820-1839 only
+    # changes pathCB, which is a weight, not geometry)
+    zE = mpf(m.lengthColdbore)
+    zP1 = zE + mpf(pipes.cb2vt3_length)
+    zP2 = zP1 + mpf(pipes.vt3xrt_length)
+    pE = plane_point(O, v, zE)
+    pP2 = plane_point(O, v, zP2)
+    for pt, R in ((pE, m.radiusCB), (plane_point(O, v, zP1), pipes.cb2vt3_radius), (pP2, pipes.cb2vt3_radius)):
+        if mp.sqrt(pt[0] ** 2 + pt[1] ** 2) >= R:
+            return None
+    rad = mp.pi / 180
+    tX, tY = mpf(tel.telescope_turned_x) * rad, mpf(tel.telescope_turned_y) * rad
+    b0 = mpf(tel.allAngles[0]) * rad
+    half = ((mpf(tel.lMirror) + mpf(tel.allXsep[0]) / 2) * (mp.cos(b0) + mp.cos(3 * b0))) / 2
+    oe = V(mpf(tel.optics_entrance[0]), mpf(tel.optics_entrance[1]), 0)
+    pE = rot_in_y(rot_in_x(V(pE[0], pE[1], pE[2] - zP2), tX, half), tY, half) - oe
+    pP2 = rot_in_y(rot_in_x(V(pP2[0], pP2[1], pP2[2] - zP2), tX, half), tY, half) - oe
+    vX = pP2 - pE
+    pEnt = pE + ((0 - pE[2]) / vX[2]) * vX
+    rd = mp.sqrt(pEnt[0] ** 2 + pEnt[1] ** 2)
+    hit = None
+    for j in range(tel.nShells):
+        if tel.allR1[j] < rd < tel.allR1[j] + tel.allThickness[j]:
+            return None
+        if hit is None and tel.allR1[j] > rd:
+            hit = j
+    if hit is None:
+        return None
+    r1 = mpf(tel.allR1[hit]); beta = mpf(tel.allAngles[hit]) * rad; xsep = mpf(tel.allXsep[hit]); l = mpf(tel.lMirror)
+    beta3 = 3 * beta
+    dm = mp.cos(beta) * (xsep + l)
+    f = mpf(setup.detectorInstall.distanceDetectorXRT)
+    wolter = tel.kind in (1, 3)
+    p, d = pE, pEnt - pE
+    if wolter:
+        t = mp.tan(beta)
+        r3 = -t * l + mp.sqrt(t * l * t * l + r1 * r1)
+        e = 2 * r3 * t
+        pm1 = pick_root(p, d, d[0] ** 2 + d[1] ** 2, p[0] * d[0] + p[1] * d[1] + e * d[2] / 2,
+                        p[0] ** 2 + p[1] ** 2 - r3 ** 2 - e * l + e * p[2], 0, l * mp.cos(beta))
+        if pm1 is None:
+            return None
+        mm = 1 / (r3 * t / mp.sqrt(r3 * r3 + r3 * 2 * t * (l - pm1[2])))
+        n = V(pm1[0], pm1[1], mp.sqrt(pm1[0] ** 2 + pm1[1] ** 2) / mm)
+    else:
+        t = mp.tan(beta)
+        k = t * t
+        pm1 = pick_root(p, d, d[0] ** 2 + d[1] ** 2 - k * d[2] ** 2, p[0] * d[0] + p[1] * d[1] + r1 * t * d[2] - k * p[2] * d[2],
+                        p[0] ** 2 + p[1] ** 2 - r1 ** 2 + 2 * r1 * t * p[2] - k * p[2] ** 2, 0, l * mp.cos(beta))
+        if pm1 is None:
+            return None
+        n = V(pm1[0], pm1[1], t * mp.sqrt(pm1[0] ** 2 + pm1[1] ** 2))
+    v1, a1 = reflect(n, pE, pEnt)
+    p, d = pm1, 200 * v1
+    if wolter:
+        t3 = mp.tan(beta3 / 3)
+        r3 = -t3 * l + mp.sqrt(t3 * l * t3 * l + r1 * r1)
+        T = mp.tan(beta3)
+        den = f + r3 / mp.tan(2 * beta3 / 3)
+        e = 2 * r3 * T
+        g = e / den
+        pm2 = pick_root(p, d, d[0] ** 2 + d[1] ** 2 - g * d[2] ** 2,
+                        p[0] * d[0] + p[1] * d[1] + g * d[2] * l - g * d[2] * p[2] + e * d[2] / 2,
+                        p[0] ** 2 + p[1] ** 2 - r3 ** 2 - e * l + e * p[2] - g * l * l + 2 * g * p[2] * l - g * p[2] ** 2,
+                        dm, dm + l * mp.cos(beta3))
+        if pm2 is None:
+            return None
+        u = l - pm2[2]
+        mm = 1 / (r3 * T * (1 + 2 * u / den) / mp.sqrt(r3 * r3 + r3 * 2 * T * u * (1 + u / den)))
+        n = V(pm2[0], pm2[1], mp.sqrt(pm2[0] ** 2 + pm2[1] ** 2) / mm)
+    else:
+        r2 = r1 - l * mp.sin(beta)
+        r3 = r2 - xsep / 2 * mp.tan(beta)
+        r4 = r3 - xsep / 2 * mp.tan(beta3)
+        t = mp.tan(beta3)
+        k = t * t
+        pz = p[2] - dm
+        pm2 = pick_root(p, d, d[0] ** 2 + d[1] ** 2 - k * d[2] ** 2, p[0] * d[0] + p[1] * d[1] + r4 * t * d[2] - k * pz * d[2],
+                        p[0] ** 2 + p[1] ** 2 - r4 ** 2 + 2 * r4 * t * pz - k * pz ** 2, dm, dm + l * mp.cos(beta3))
+        if pm2 is None:
+            return None
+        n = V(pm2[0], pm2[1], t * mp.sqrt(pm2[0] ** 2 + pm2[1] ** 2))
+    v2, a2 = reflect(n, pm1, pm1 + 200 * v1)
+    distDet = dm - mpf(tel.allXsep[8]) / 2 * mp.cos(beta) + f - mpf(setup.detectorInstall.distanceWindowFocalPlane)
+    pr = mpf(pipes.pipesTurned) * rad
+    dsh = -mpf(tel.optics_entrance[0])
+    a = rot_in_x(pm2, pr, 0) - V(dsh, 0, 0)
+    b = rot_in_x(pm2 + 200 * v2, pr, 0) - V(dsh, 0, 0)
+    w = b - a
+    nn = (distDet / mp.cos(pr) - a[2]) / w[2]
+    pdw = a + nn * w
+    x = pdw[0] - mpf(setup.detectorInstall.lateralShift)
+    y = pdw[1] - mpf(setup.detectorInstall.transversalShift)
+    cx, cy = mpf(setup.consts.chipXMax) / 2, mpf(setup.consts.chipYMax) / 2
+    return float(-x + cx), float(y + cy), hit, float(a1 / rad), float(a2 / rad)
