@@ -7,7 +7,10 @@ from pathlib import Path
 
 from . import abi
 
-LIB_PATH = Path(__file__).resolve().parent / "libsart.so"
+import os
+
+# SART_LIB selects an experimental build variant of the same library (development only).
+LIB_PATH = Path(os.environ.get("SART_LIB") or Path(__file__).resolve().parent / "libsart.so")
 
 
 class SartError(RuntimeError):

@@ -40,7 +40,10 @@ def _stale(out: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
+    """`defines`/`out` build an experimental variant (e.g. -DSART_FAST_MINBLOCKS=3) next to the default library."""
+    if defines or out:
+        return _build_variant(defines or [], out or LIB.with_name("libsart_variant.so"), verbose)
     hdrs = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "sart.h",
                                                                     Path(__file__)]
     objdir = HERE / "build"
@@ -64,6 +67,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def _build_variant(defines: list[str], out: Path, verbose: bool) -> Path:
+    objdir = HERE / "build" / out.stem
+    objdir.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for src, extra in UNITS:
+        o = objdir / (src + ".o")
+        objs.append(o)
+        cmd = [NVCC, *ARCH, *COMMON, *extra, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(o)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.run(cmd, check=True)
+    subprocess.run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(out), *map(str, objs)],
+                   check=True)
+    return out
+
+
 if __name__ == "__main__":
+    if any(a.startswith("-D") for a in sys.argv[1:]):
+        defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+        outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+        print(build(defines=defs, out=HERE / outs[0] if outs else None, verbose="-v" in sys.argv))
+        sys.exit(0)
     build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv)
     print(LIB)

@@ -26,7 +26,13 @@
 namespace sart {
 namespace fast {
 
-constexpr int kBlock = 256;
+#ifndef SART_FAST_BLOCK
+#define SART_FAST_BLOCK 256
+#endif
+#ifndef SART_FAST_MINBLOCKS
+#define SART_FAST_MINBLOCKS 4
+#endif
+constexpr int kBlock = SART_FAST_BLOCK;
 constexpr int kWarps = kBlock / 32;
 
 // ---- FP64 divide / sqrt from FP32 seeds ---------------------------------------------------------------------
@@ -435,7 +441,7 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
 template <bool kWolter>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, SART_FAST_MINBLOCKS)
 k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
                 uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
                 double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {

@@ -1,0 +1,115 @@
+"""The C-ABI library loads on a CPU-only machine, exports every symbol include/sart.h declares, its struct layouts
+match the ctypes mirror, its host-side setup constructors agree with an independent transcription of the reference,
+and it fails loudly (no CPU fallback) when asked to compute without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ref_setup
+from solaraxionraytracing_b200 import abi
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from solaraxionraytracing_b200 import raytracer
+    return raytracer
+
+
+def test_header_symbols_exported(rt):
+    hdr = (ROOT / "include" / "sart.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sart_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(rt.lib, name), f"{name} declared in include/sart.h but not exported by libsart.so"
+        assert name in abi.SIGNATURES, f"{name} missing from abi.SIGNATURES"
+
+
+def test_struct_layouts(rt):
+    assert rt.lib.sart_sizeof_setup() == C.sizeof(abi.Setup)
+    assert rt.lib.sart_sizeof_tables() == C.sizeof(abi.Tables)
+    assert rt.lib.sart_sizeof_counters() == C.sizeof(abi.Counters)
+    assert rt.lib.sart_abi_version() == abi.ABI_VERSION
+
+
+COMBOS = [(e, d, s, t) for e in (abi.ES_CAST, abi.ES_BABYIAXO)
+          for d in (abi.DK_INGRID2017, abi.DK_INGRID2018, abi.DK_INGRIDIAXO)
+          for s in (abi.SK_VACUUM, abi.SK_GAS) for t in (abi.TK_LLNL, abi.TK_XMM, abi.TK_ABRIXAS)]
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("flags", [0, abi.CF_XRAY_TEST | abi.CF_IGNORE_GAS_ABS])
+def test_host_setup_matches_independent_transcription(rt, combo, flags):
+    got = abi.struct_to_dict(rt.newExperimentSetup(*combo, flags))
+    want = abi.struct_to_dict(ref_setup.make_setup(*combo, flags))
+
+    def cmp(a, b, path=""):
+        assert type(a) is type(b), path
+        if isinstance(a, dict):
+            assert a.keys() == b.keys()
+            for k in a:
+                cmp(a[k], b[k], f"{path}.{k}")
+        elif isinstance(a, list):
+            assert len(a) == len(b)
+            for i, (x, y) in enumerate(zip(a, b)):
+                cmp(x, y, f"{path}[{i}]")
+        elif isinstance(a, float):
+            assert a == pytest.approx(b, rel=1e-15, abs=0), path
+        else:
+            assert a == b, path
+    cmp(got, want)
+
+
+def test_enum_strings_and_errors(rt):
+    s = rt.newExperimentSetup("BabyIAXO", "InGridIAXO", "vacuum", "XMM")   # config_default.toml:20-23
+    assert s.magnet.radiusCB == 500.0 and s.telescope.nShells == 58 and s.detectorInstall.distanceDetectorXRT == 7500.0
+    with pytest.raises(ValueError):
+        rt.newExperimentSetup("CAST", "InGrid2018", "vacuum", "Hubble")
+    for tk in ("CustomBabyIAXO", "Other"):       # doAssert false in the reference (rt:1232-1234, 1347-1348)
+        with pytest.raises(rt.SartError) as e:
+            rt.newExperimentSetup("CAST", "InGrid2018", "vacuum", tk)
+        assert e.value.code == -3
+
+
+def test_window_vals(rt):
+    w, d = rt.calcWindowVals(7.0, 4, 0.838)
+    assert w == pytest.approx(0.500418, abs=1e-6) and d == pytest.approx(2.299582, abs=1e-6)
+    assert w + d == pytest.approx(14.0 / 5.0)
+
+
+def test_uniforms_match_oracle(rt, oracle):
+    u = np.empty(6)
+    for seed, ray in ((299792458, 0), (1, 2**40 + 17), (2**63 + 5, 123456789)):
+        rt.lib.sart_ray_uniforms(seed, ray, u.ctypes.data_as(abi.c_double_p))
+        assert np.array_equal(u, oracle.ray_uniforms(seed, ray))
+
+
+def test_no_cpu_fallback(rt):
+    """Without a CUDA device every compute entry point must fail with SART_ERR_CUDA, not fall back."""
+    if rt.lib.sart_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    from helpers import make_config
+    setup, tb = make_config("cast_llnl")
+    with pytest.raises(rt.SartError) as e:
+        rt.RayTracer(rt.FullRaytraceSetup(setup, tb))
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    from solaraxionraytracing_b200 import tables
+    with pytest.raises(rt.SartError) as e:
+        rt.buildCdfs(tables.synthetic_emission(8, 8))
+    assert e.value.code == -2
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through oracle/ (tests, smoke() and bench.py's CPU legs only)."""
+    pkg = ROOT / "solaraxionraytracing_b200"
+    files = [f for ext in ("*.py", "*.cu", "*.cpp", "*.h", "*.cuh") for f in pkg.rglob(ext)]
+    assert len(files) > 10
+    for f in files:
+        txt = f.read_text()
+        for needle in ("import oracle", "from oracle", "liboracle", "oracle/"):
+            assert needle not in txt, (f, needle)
