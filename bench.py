@@ -177,16 +177,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-class DevArray:
-    """Zero-copy view of a libsart device buffer for torch (via __cuda_array_interface__)."""
-
-    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def run_ours(args):
     import torch
-    from solaraxionraytracing_b200 import abi, raytracer as rt, tables
+    from solaraxionraytracing_b200 import abi, multi_gpu, raytracer as rt, tables
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,14 +206,8 @@ def run_ours(args):
     table_upload_s = time.perf_counter() - t0
 
     stream = torch.cuda.ExternalStream(tr.stream, device=local)
-    img_ptr, img2_ptr, img_len = tr.image_dev()
-    t_img = torch.as_tensor(DevArray(img_ptr, img_len), device=f"cuda:{local}")
-    t_img2 = torch.as_tensor(DevArray(img2_ptr, img_len), device=f"cuda:{local}")
-    n_cnt_words = C.sizeof(abi.Counters) // 8
-    # counters: 22 u64 words then 5 f64; all-reduce them as two typed views
-    n_u64 = abi.Counters.sum_w.offset // 8
-    t_cnt_i = torch.as_tensor(DevArray(tr.counters_dev(), n_u64, "<i8"), device=f"cuda:{local}")
-    t_cnt_f = torch.as_tensor(DevArray(tr.counters_dev() + n_u64 * 8, n_cnt_words - n_u64), device=f"cuda:{local}")
+    _, _, img_len = tr.image_dev()
+    views = multi_gpu.device_views(tr, local)   # zero-copy torch views of the image, w^2 image and counters
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
 
     def barrier():
@@ -239,8 +226,7 @@ def run_ours(args):
         if ev is not None:
             ev[1].record(stream)
         if dist is not None:
-            for t in (t_img, t_img2, t_cnt_i, t_cnt_f):
-                dist.all_reduce(t)
+            multi_gpu.allreduce_device(tr, local, views=views)
             # every rank now holds the merged image; non-zero ranks drop theirs so the next step's sum stays right
             if rank != 0:
                 tr.reset_image()
