@@ -173,15 +173,18 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   derive_shells(h->setup, sh64.data());
   std::vector<fast::ShellFast> shf(SART_MAX_SHELLS);
   fast::derive_shells(h->setup, sh64.data(), shf.data());
+  std::vector<uint8_t> sguide;
+  fast::build_shell_guide(h->setup, &h->fparams, &sguide);
   std::vector<fast::EnergyLUT> lut;
   fast::build_energy_lut(h->params, int(h->h_energies.size()), h->h_energies.data(), I[0], I[1], I[2],
                          h->setup.testSource.energy, &lut);
   unsigned char* base = static_cast<unsigned char*>(h->fast_blob);
   if (t) {
-    // layout: shells | lut | refl(f32)
+    // layout: shells | shell guide (4 KiB reserved) | lut | refl(f32)
     const size_t nRefl = t->reflectivity ? size_t(t->nCoatings) * t->nAngles * t->nReflEnergies : 0;
     h->fast_shell_off = 0;
-    h->fast_lut_off = align256(shf.size() * sizeof(fast::ShellFast));
+    h->fast_sguide_off = align256(shf.size() * sizeof(fast::ShellFast));
+    h->fast_lut_off = h->fast_sguide_off + 4096;
     const size_t reflOff = h->fast_lut_off + align256(lut.size() * sizeof(fast::EnergyLUT));
     if (h->fast_blob) { cudaFree(h->fast_blob); h->fast_blob = nullptr; }
     SART_CUDA(cudaMalloc(&h->fast_blob, reflOff + align256(nRefl * sizeof(float)) + 256));
@@ -194,6 +197,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     h->ftables.refl = reinterpret_cast<const float*>(base + reflOff);
     h->ftables.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
     h->ftables.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
+    h->ftables.shellGuide = reinterpret_cast<const uint8_t*>(base + h->fast_sguide_off);
     h->ftables.radiusCDF = h->tables.fluxRadiusCDF;
     h->ftables.radiusGuide = h->tables.radiusGuide;
     h->ftables.energyCDF = h->tables.diffFluxCDFs;
@@ -201,6 +205,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   }
   SART_CUDA(cudaMemcpy(base + h->fast_shell_off, shf.data(), shf.size() * sizeof(fast::ShellFast), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_lut_off, lut.data(), lut.size() * sizeof(fast::EnergyLUT), cudaMemcpyHostToDevice));
+  if (sguide.size() > 4096) return fail(SART_ERR_CONFIG, "shell guide too large (%zu)", sguide.size());
+  SART_CUDA(cudaMemcpy(base + h->fast_sguide_off, sguide.data(), sguide.size(), cudaMemcpyHostToDevice));
   return SART_OK;
 }
 

@@ -67,7 +67,36 @@ void derive_shells(const sart_setup_t& s, const ShellF64* a, ShellFast* out) {
     o.p_e = a[j].p_e; o.p_c0 = a[j].p_r3sq + a[j].p_e * l; o.p_r3sq = a[j].p_r3sq; o.p_r3tan = a[j].p_r3tan;
     o.h_e = a[j].h_e; o.h_g = a[j].h_g; o.h_r3sq = a[j].h_r3sq; o.h_r3tan = a[j].h_r3tan;
     o.h_inv_nden = a[j].h_nden != 0.0 ? 1.0 / a[j].h_nden : 0.0;
+    int coat = 0;
+    if (t.reflKind == SART_RK_MULTI_COATING) {
+      while (coat < t.nCoatings - 1 && t.layers[coat] < j) ++coat;   // layers.lowerBound(hitLayer) rt:1573
+    }
+    o.coat = coat;
   }
+}
+
+// Uniform radial grid over [R1[0] - step, R1[last]]: guide[b] = smallest j with R1[j] > lower edge of bucket b, and the
+// step is at most half the smallest shell spacing, so the kernel's forward scan from guide[b] takes 0 or 1 steps.
+void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide) {
+  const sart_telescope_t& t = s.telescope;
+  double gap = t.allR1[0];
+  for (int j = 1; j < t.nShells; ++j) gap = std::min(gap, t.allR1[j] - t.allR1[j - 1]);
+  double step = 0.5 * gap;
+  const double span = t.allR1[t.nShells - 1] - t.allR1[0];
+  if (span / step > 2000.0) step = span / 2000.0;
+  if (!(step > 0.0)) step = 1.0;
+  const double rmin = t.allR1[0] - step;
+  const int n = int(std::ceil((t.allR1[t.nShells - 1] - rmin) / step)) + 2;
+  guide->assign(size_t(n), 0);
+  for (int b = 0; b < n; ++b) {
+    const double edge = rmin + double(b) * step;
+    int j = 0;
+    while (j < t.nShells - 1 && !(t.allR1[j] > edge)) ++j;
+    (*guide)[b] = uint8_t(j);
+  }
+  f->shellRhoMin = rmin;
+  f->shellInvStep = 1.0 / step;
+  f->nShellGuide = n;
 }
 
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
@@ -89,6 +118,7 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   f->chipCX = P.chipCX; f->chipCY = P.chipCY;
   f->cosTheta = P.cosTheta; f->sinTheta = P.sinTheta;
   f->stripDist = P.stripDist; f->stripWidth = P.stripWidth;
+  f->invStripPitch = 1.0 / (P.stripDist + P.stripWidth);
   f->invBinX = double(SART_IMAGE_BINS) / (2.0 * P.chipCX);
   f->invBinY = double(SART_IMAGE_BINS) / (2.0 * P.chipCY);
   f->sunDist = s.consts.distanceSunEarth;
@@ -122,6 +152,7 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   f->flags = P.flags;
   f->nRadii = P.nRadii; f->nEnergies = P.nEnergies; f->nAngles = P.nAngles; f->nReflEnergies = P.nReflEnergies;
   f->shellsMonotonic = 1;
+  f->rotated = (P.sinTX != 0.0 || P.sinTY != 0.0) ? 1 : 0;
   f->srcEIdx = P.nEnergies;  // the record after the tabulated energies holds the X-ray source energy
 }
 

@@ -75,6 +75,6 @@ struct Tables {
   const ShellF64* shells;
 };
 
-constexpr int kGuide = 256;  // guide-table buckets per CDF row
+constexpr int kGuide = 1024;  // guide-table buckets per CDF row
 
 }  // namespace sart

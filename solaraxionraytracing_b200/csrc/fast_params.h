@@ -16,7 +16,8 @@ struct ShellFast {
   // Wolter-I
   double p_e, p_c0, p_r3sq, p_r3tan;                       // paraboloid: rho^2 = r3^2 + e (l - z); c0 = r3^2 + e l
   double h_e, h_g, h_r3sq, h_r3tan, h_inv_nden;            // hyperboloid: rho^2 = r3^2 + e (l-z) + g (l-z)^2
-  double pad;
+  int32_t coat;   // reflectivity table of this shell: layers.lowerBound(hitLayer) (rt:1573)
+  int32_t pad_;
 };
 static_assert(sizeof(ShellFast) % 16 == 8, "odd number of doubles keeps shared-memory rows off the same banks");
 
@@ -25,8 +26,9 @@ struct FastParams {
   double radiusCB2, lengthB, dzExitCB, dzPipe1, dzPipe2, rPipe12;  // dz* = plane z - lengthB
   double cosTX, sinTX, cosTY, sinTY, halfLenTel, oeX, oeY, zExitCBtel;  // zExitCBtel = zExitCB - zPipe2
   double lMirror, cosPipe, sinPipe, dShift, lateralShift, transversalShift;
-  double radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invBinX, invBinY;
+  double radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invStripPitch, invBinX, invBinY;
   double sunDist, radiusSun, radiusCB;
+  double shellRhoMin, shellInvStep;   // uniform radial grid -> first candidate shell (shellGuide)
   // weights (FP32)
   float convK;         // (g*1e-9 * B*T2eV2 * 1e-3*m2eV / 2)^2: conversionProb = convK * pathCB^2 (rt:363-365)
   float exposure;
@@ -40,6 +42,7 @@ struct FastParams {
   int32_t layers[SART_MAX_COATINGS];
   uint32_t flags;
   int32_t nRadii, nEnergies, nAngles, nReflEnergies, shellsMonotonic, srcEIdx;
+  int32_t nShellGuide, rotated;
 };
 
 struct EnergyLUT {  // one record per tabulated energy index (32 B)
@@ -56,6 +59,7 @@ struct FastTables {
   const EnergyLUT* elut;
   const float* refl;          // [coat][nAngles][nReflEnergies]
   const ShellFast* shells;    // [nShells]
+  const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
 };
 
 

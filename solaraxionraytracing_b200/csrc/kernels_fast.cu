@@ -11,7 +11,8 @@
 //   * everything that only scales the weight (emission direction sines, grazing angles for the reflectivity
 //     lookup, cos(yaw), transmissions) is FP32 with MUFU intrinsics; transmissions, the energy and the reflectivity
 //     cell of each of the nE tabulated energies come from a per-energy-index LUT built once at sart_create;
-//   * CDF searches start from a 256-bucket guide table, so they touch 2-4 entries instead of 11;
+//   * CDF searches start from a 1024-bucket guide table (1-2 entries instead of 11 probes) and their dependent loads are
+//     issued ahead of the geometry that separates them from their use;
 //   * run-wide tables (radius CDF, guide, shell constants) are staged once per block in shared memory;
 //   * counters live in registers / per-warp shared memory and are flushed once per block.
 // Exit codes follow the same decision sequence as the exact pipeline, so the counters of both are comparable.
@@ -30,21 +31,43 @@ namespace fast {
 #define SART_FAST_BLOCK 256
 #endif
 #ifndef SART_FAST_MINBLOCKS
-#define SART_FAST_MINBLOCKS 4
+#define SART_FAST_MINBLOCKS 3
 #endif
 constexpr int kBlock = SART_FAST_BLOCK;
 constexpr int kWarps = kBlock / 32;
 
 // ---- FP64 divide / sqrt from FP32 seeds ---------------------------------------------------------------------
+// MUFU.RCP / MUFU.RSQ seeds (2^-23 relative); the *_rn intrinsics and rsqrtf() expand to range checks + slow paths.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ double rcp_nr(double x) {
-  double r = double(__frcp_rn(float(x)));
+  double r = double(rcp_approx(float(x)));
   const double e = fma(-x, r, 1.0);
   return fma(r, e, r);
 }
 __device__ __forceinline__ double rsqrt_nr(double x) {
-  double y = double(rsqrtf(float(x)));
+  double y = double(rsqrt_approx(float(x)));
   const double h = 0.5 * x * y;
   return fma(y, fma(-h, y, 0.5), y);  // y * (1.5 - 0.5 x y^2)
+}
+
+// sin/cos(2 pi u), u in [0, 1): MUFU.SIN/COS on the argument shifted into [-pi, pi) where their absolute error is
+// 2^-21.4; these only set the sampled emission direction / exit-disc point (a 5e-7 relative shift of a random point).
+__device__ __forceinline__ void sincos_2pi(float u, float& s, float& c) {
+  const float t = 6.283185307179586f * (u - 0.5f);
+  s = -__sinf(t);
+  c = -__cosf(t);
+}
+// asin / atan for small arguments (grazing angles <= 0.1 rad, slopes <= 0.1): odd series, relative error < 1e-7.
+__device__ __forceinline__ float asin_small(float x) {
+  if (fabsf(x) > 0.1f) return asinf(x);
+  const float x2 = x * x;
+  return x * fmaf(x2, fmaf(x2, 0.075f, 0.16666667f), 1.0f);
+}
+__device__ __forceinline__ float atan_small(float x) {
+  if (fabsf(x) > 0.1f) return atanf(x);
+  const float x2 = x * x;
+  return x * fmaf(x2, fmaf(x2, 0.2f, -0.33333334f), 1.0f);
 }
 
 struct D3 { double x, y, z; };
@@ -61,24 +84,37 @@ __device__ __forceinline__ int lower_bound_window(const double* __restrict__ a, 
   return lo;
 }
 
-// Picks the root the reference picks (rt:646-658): roots of A t^2 + 2 hb t + C = 0 in the reference's order
-// root1 = (-hb - sq)/A, root2 = (-hb + sq)/A, each accepted only if zmin < pz + t dz < zmax. Returns false if none.
+// Root choice of findPos* (rt:646-658): roots of A t^2 + 2 hb t + C = 0 in the reference's order root1 = (-hb - sq)/A,
+// root2 = (-hb + sq)/A, each accepted only if zmin < pz + t dz < zmax. With q = -(hb + sign(hb) sq) the roots are q/A
+// (the larger in magnitude) and C/q. The large root is never inside a mirror in practice (it is metres away), so it is
+// excluded with a division-free bound and only then does the small root need a reciprocal; the rare other case
+// reproduces the reference's order exactly.
+__device__ __noinline__ bool pick_root_slow(double A, double q, double C, bool first_is_qA, double dz, double lo,
+                                            double hi, double& t) {
+  auto in_range = [&](double num, double den) {
+    const double nd = num * dz;  // lo < (num/den) dz < hi without dividing
+    return den > 0.0 ? (nd > lo * den && nd < hi * den) : (nd < lo * den && nd > hi * den);
+  };
+  const bool okA = in_range(q, A), okC = in_range(C, q);
+  double num, den;
+  if (first_is_qA ? okA : okC) { num = first_is_qA ? q : C; den = first_is_qA ? A : q; }
+  else if (first_is_qA ? okC : okA) { num = first_is_qA ? C : q; den = first_is_qA ? q : A; }
+  else return false;
+  t = num / den;
+  return true;
+}
 __device__ __forceinline__ bool pick_root(double A, double hb, double C, double pz, double dz, double zmin, double zmax,
                                           double& t) {
   const double disc = fma(hb, hb, -A * C);
   if (!(disc >= 0.0)) return false;
   const double sq = disc > 1e-30 ? disc * rsqrt_nr(disc) : 0.0;
-  // stable pair: q = -(hb + sign(hb) sq); roots q/A and C/q
   const double q = -(hb + copysign(sq, hb));
-  const double ra = q * rcp_nr(A);   // = (-hb - sign(hb) sq)/A
-  const double rb = C * rcp_nr(q);   // the other root
-  // (-hb - sq)/A is `ra` when hb >= 0, `rb` otherwise
-  const double root1 = (hb >= 0.0) ? ra : rb;
-  const double root2 = (hb >= 0.0) ? rb : ra;
-  const double z1 = fma(root1, dz, pz), z2 = fma(root2, dz, pz);
-  if (z1 > zmin && z1 < zmax) { t = root1; return true; }
-  if (z2 > zmin && z2 < zmax) { t = root2; return true; }
-  return false;
+  const double lo = zmin - pz, hi = zmax - pz;
+  if (fabs(q * dz) < fmax(fabs(lo), fabs(hi)) * fabs(A)) return pick_root_slow(A, q, C, hb >= 0.0, dz, lo, hi, t);
+  const double ts = C * rcp_nr(q);
+  const double zs = ts * dz;
+  t = ts;
+  return zs > lo && zs < hi;
 }
 
 // Reflection of unit vector v off unit normal n (rt:762-780 without trigonometry); returns |n.v| = sin(alpha).
@@ -115,10 +151,34 @@ struct RayResult {
   double w, x, y, r;
 };
 
+// Shared-memory tables of one block (shells first so their addresses are compile-time offsets).
+struct Smem {
+  const ShellFast* shell;
+  const double* radCDF;
+  const uint16_t* radGuide;
+  const uint8_t* shellGuide;
+};
+__device__ __forceinline__ size_t smem_layout(const FastParams& P, unsigned char* base, Smem& s, unsigned char*& tail) {
+  size_t off = 0;
+  s.shell = reinterpret_cast<const ShellFast*>(base + off); off += size_t(P.nShells) * sizeof(ShellFast);
+  s.radCDF = reinterpret_cast<const double*>(base + off); off += size_t((P.nRadii + 1) & ~1) * 8;
+  s.radGuide = reinterpret_cast<const uint16_t*>(base + off); off += (2 * (kGuide + 1) + 15) & ~15;
+  s.shellGuide = base + off; off += (size_t(P.nShellGuide) + 15) & ~size_t(15);
+  tail = base + off;
+  return off;
+}
+__device__ __forceinline__ void smem_fill(const FastParams& P, const FastTables& T, const Smem& s) {
+  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
+    reinterpret_cast<double*>(const_cast<ShellFast*>(s.shell))[i] = reinterpret_cast<const double*>(T.shells)[i];
+  for (int i = threadIdx.x; i < P.nRadii; i += kBlock) const_cast<double*>(s.radCDF)[i] = T.radiusCDF[i];
+  if (P.nRadii > 0) for (int i = threadIdx.x; i <= kGuide; i += kBlock) const_cast<uint16_t*>(s.radGuide)[i] = T.radiusGuide[i];
+  for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
+}
+
 template <bool kWolter>
-__device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const double* __restrict__ sRadCDF,
-                                          const uint16_t* __restrict__ sRadGuide, const ShellFast* __restrict__ sShell,
+__device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const Smem& S,
                                           uint64_t seed, uint64_t ray, double mAxion2, RayResult& out) {
+  const ShellFast* __restrict__ sShell = S.shell;
   out.bin = -1; out.w = 0.0; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
   uint32_t w[6];
   ray_words(seed, ray, w);
@@ -128,42 +188,53 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   // ================= sampling rt:1754-1764 (or the X-ray test source rt:1765-1801)
   double ex, ey, sx, sy;   // point on the exit disc of the field (z = lengthB) and slopes
   int eIdx;
+  // energy search state: the guide entry is loaded here, the CDF window after the clip tests, the LUT record after
+  // mirror 1 — the dependent global loads overlap the geometry instead of stalling in a row
+  int eLo = 0, eHi = 0;
+  double ue = 0.0;
+  const double* eRow = nullptr;
   if (!P.testXray) {
     // emission shell (exact index: same f64 CDF, same key as the oracle)
     const double ur = u01(w[2]);
     const int kr = int(ur * double(kGuide));
-    const int rIdx = lower_bound_window(sRadCDF, sRadGuide[kr], sRadGuide[kr + 1], ur);
+    int rIdx = S.radGuide[kr];
+    {
+      const int rHi = S.radGuide[kr + 1];
+      while (rIdx < rHi && S.radCDF[rIdx] < ur) ++rIdx;   // lowerBound inside the guide window (1-2 entries)
+    }
+    ue = u01(w[5]);
+    {
+      const uint16_t* g = T.energyGuide + size_t(rIdx) * (kGuide + 1) + int(ue * double(kGuide));
+      eLo = __ldg(g); eHi = __ldg(g + 1);
+      eRow = T.energyCDF + size_t(rIdx) * P.nEnergies;
+    }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);  // fraction of the solar radius (weight-free: direction only)
     float s1, c1, s2, c2;
-    sincospif(2.0f * (float(w[0]) * k2m32), &s1, &c1);    // phi = 360 u0
-    sincospif(float(w[1]) * k2m32, &s2, &c2);             // theta = 180 u1 (uniform in theta, quirk Q7)
+    sincos_2pi(float(w[0]) * k2m32, s1, c1);              // phi = 360 u0
+    __sincosf(3.14159265358979f * (float(w[1]) * k2m32), &s2, &c2);  // theta = 180 u1 (uniform in theta, quirk Q7)
     const double rsun = double(rs) * P.radiusSun;
     const double Ox = rsun * double(c1 * s2), Oy = rsun * double(s1 * s2), Ozr = rsun * double(c2);
     // exit disc rt:412-422
     float sd, cd;
-    sincospif(2.0f * (float(w[4]) * k2m32), &sd, &cd);
+    sincos_2pi(float(w[4]) * k2m32, sd, cd);
     const float rd = sqrtf((float(w[3]) + 0.5f) * k2m32);
     ex = P.radiusCB * double(rd * cd);
     ey = P.radiusCB * double(rd * sd);
     const double invD = rcp_nr(P.lengthB + P.sunDist - Ozr);  // lengthB - O.z
     sx = (ex - Ox) * invD;
     sy = (ey - Oy) * invD;
-    // energy: the reference recovers the radius index from the emission point (rt:454-460); it is rIdx again
-    const double ue = u01(w[5]);
-    const int ke = int(ue * double(kGuide));
-    const uint16_t* g = T.energyGuide + size_t(rIdx) * (kGuide + 1) + ke;
-    eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, g[0], g[1], ue);
-    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
+    // (energy: the reference recovers the radius index from the emission point, rt:454-460; it is rIdx again)
+    eIdx = 0;
   } else {
     float sd, cd;
-    sincospif(2.0f * (float(w[1]) * k2m32), &sd, &cd);
+    sincos_2pi(float(w[1]) * k2m32, sd, cd);
     const float rd = sqrtf((float(w[0]) + 0.5f) * k2m32);
     const double Ox = P.srcX + P.srcRadius * double(rd * cd), Oy = P.srcY + P.srcRadius * double(rd * sd);
     if (P.parallelSource) {
       ex = Ox + (0.5 * u01(w[2]) - 0.25);
       ey = Oy + (0.5 * u01(w[3]) - 0.25);
     } else {
-      sincospif(2.0f * (float(w[3]) * k2m32), &sd, &cd);
+      sincos_2pi(float(w[3]) * k2m32, sd, cd);
       const float r2 = sqrtf((float(w[2]) + 0.5f) * k2m32);
       ex = P.radiusCB * double(r2 * cd);
       ey = P.radiusCB * double(r2 * sd);
@@ -202,10 +273,13 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   double x0 = fma(sx, P.dzPipe2, ex), y0 = fma(sy, P.dzPipe2, ey);
   if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) { out.code = SART_EXIT_CLIP_PIPE_XRT; return; }  // quirk Q2
+  // energy CDF window: four independent loads (the guide window is 1-2 entries wide on average)
+  double ec0 = 2.0, ec1 = 2.0, ec2 = 2.0, ec3 = 2.0;
+  if (eRow) { ec0 = __ldg(eRow + eLo); ec1 = __ldg(eRow + eLo + 1); ec2 = __ldg(eRow + eLo + 2); ec3 = __ldg(eRow + eLo + 3); }
 
   // ================= telescope frame rt:1888-1905 (rotation about (0, 0, halfLenTel); identity when not turned)
   double dx = sx, dy = sy, dz = 1.0, z0 = 0.0;
-  if (P.sinTX != 0.0 || P.sinTY != 0.0) {
+  if (P.rotated) {
     // rotateInX then rotateInY of point (x0, y0, 0) and of the direction
     double zt = 0.0 - P.halfLenTel;
     double xr = x0 * P.cosTX + zt * P.sinTX, zr = zt * P.cosTX - x0 * P.sinTX;
@@ -256,20 +330,18 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     if (hit) { out.code = SART_EXIT_OPAQUE; return; }
   }
 
-  // ================= shell rt:1932-1957
+  // ================= shell rt:1932-1957: uniform radial guide + at most one forward step
   const int nS = P.nShells;
   if (radialDist > sShell[nS - 1].R1) { out.code = SART_EXIT_OUTSIDE_SHELLS; return; }
   int hitLayer;
   {
-    int lo = 0, hi = nS - 1;  // first j with R1[j] > radialDist
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (sShell[mid].R1 > radialDist) hi = mid; else lo = mid + 1;
-    }
-    hitLayer = lo;
+    int b = int((radialDist - P.shellRhoMin) * P.shellInvStep);
+    b = b < 0 ? 0 : (b > P.nShellGuide - 1 ? P.nShellGuide - 1 : b);
+    hitLayer = S.shellGuide[b];
+    while (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;   // first j with R1[j] > radialDist
     if (!(sShell[hitLayer].R1 > radialDist)) { out.code = SART_EXIT_NO_MIRROR_HIT; return; }  // == R1[last]
-    if (hitLayer > 0 && radialDist > sShell[hitLayer - 1].R1 && radialDist < sShell[hitLayer - 1].R1pT) {
-      out.code = SART_EXIT_GLASS_FRONT; return;
+    if (hitLayer > 0 && radialDist < sShell[hitLayer - 1].R1pT) {   // R1[j-1] < radialDist holds by construction
+      if (radialDist > sShell[hitLayer - 1].R1) { out.code = SART_EXIT_GLASS_FRONT; return; }
     }
   }
   const ShellFast& sh = sShell[hitLayer];
@@ -292,18 +364,28 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     if (hitLayer > 0) {
       const double zc = P.zExitCBtel;  // pointExitCB.z in the telescope frame (not turned: exact; turned: approx.)
       const double xc = fma(zc, tx, x0), yc = fma(zc, ty, y0);
-      const double rc = sqrt(fma(xc, xc, yc * yc));
+      const double rc2 = fma(xc, xc, yc * yc);
+      const double rc = rc2 * rsqrt_nr(rc2);
       double nz;
       if (kWolter) nz = rc * sh.p_r3tan * rsqrt_nr(fmax(fma(sh.p_e, lM - zc, sh.p_r3sq), 1e-300));
       else nz = sh.tan1 * rc;
       const double sg = (fma(xc, tx, yc * ty) + nz) * invLen * rsqrt_nr(fma(rc, rc, nz * nz));
       const double a = fabs(sg);
-      const double lhs = a * (lM - zc), rhs = (sh.R1 - below) * sqrt(fmax(1.0 - a * a, 0.0));
-      if (lhs > rhs) code = SART_EXIT_NICKEL;
+      const double lhs = a * (lM - zc), rhs = sh.R1 - below;
+      if (lhs * lhs > rhs * rhs * (1.0 - a * a)) code = SART_EXIT_NICKEL;
     }
     out.code = code;
     return;
   }
+  // energy index from the CDF window loaded above; its LUT record is needed only at the weight stage
+  if (eRow) {
+    const int cnt = int(eLo < eHi && ec0 < ue) + int(eLo + 1 < eHi && ec1 < ue) + int(eLo + 2 < eHi && ec2 < ue) +
+                    int(eLo + 3 < eHi && ec3 < ue);
+    eIdx = eLo + cnt;
+    if (cnt == 4 && eLo + 4 < eHi) eIdx = lower_bound_window(eRow, eLo + 4, eHi, ue);
+    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
+  }
+  const EnergyLUT el = T.elut[eIdx];
   D3 pm = {fma(tx, z1, x0), fma(ty, z1, y0), z1};
   D3 v = {tx * invLen, ty * invLen, invLen};
   double sinA1;
@@ -338,8 +420,9 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   // ================= nickel of the shell below rt:1706-1734: tan(alpha1) > (r1 - below)/(l - z1)
   if (hitLayer > 0) {
-    const double lhs = sinA1 * (lM - z1), rhs = (sh.R1 - below) * sqrt(fmax(1.0 - sinA1 * sinA1, 0.0));
-    if (lhs > rhs) { out.code = SART_EXIT_NICKEL; return; }
+    // squared form of tan(alpha1) > (r1 - below)/(l - z1); both sides are positive
+    const double lhs = sinA1 * (lM - z1), rhs = sh.R1 - below;
+    if (lhs * lhs > rhs * rhs * (1.0 - sinA1 * sinA1)) { out.code = SART_EXIT_NICKEL; return; }
   }
   if (!hit2) { out.code = SART_EXIT_NO_MIRROR_HIT; return; }  // pointMirror2 == pointMirror1 (rt:2055)
   pm.x = fma(t2, v.x, pm.x); pm.y = fma(t2, v.y, pm.y); pm.z = fma(t2, v.z, pm.z);
@@ -369,11 +452,10 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   xw -= P.lateralShift; yw -= P.transversalShift;
   // ================= weights rt:2101-2128
-  const EnergyLUT el = T.elut[eIdx];
   out.energy = el.E;
   double weight;  // the factors are FP32, their product is formed in FP64 so that tiny weights do not flush to zero
   {
-    const float ya = -atanf(float(ty)) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
+    const float ya = -atan_small(float(ty)) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
     float tm = __cosf(ya);
     const float path2f = float(path2);
     if (P.stage == SART_SK_VACUUM) {
@@ -397,12 +479,8 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     }
     float refl = 1.0f;
     if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
-      int coat = 0;
-      if (P.reflKind == SART_RK_MULTI_COATING) {
-        while (coat < P.nCoatings - 1 && P.layers[coat] < hitLayer) ++coat;
-      }
-      const float* zt = T.refl + size_t(coat) * P.nAngles * P.nReflEnergies;
-      const float a1 = asinf(float(sinA1)) * 57.29577951308232f, a2 = asinf(float(sinA2)) * 57.29577951308232f;
+      const float* zt = T.refl + size_t(sh.coat) * P.nAngles * P.nReflEnergies;
+      const float a1 = asin_small(float(sinA1)) * 57.29577951308232f, a2 = asin_small(float(sinA2)) * 57.29577951308232f;
       refl = bilinear(P, zt, a1, el.j, el.yc, clamped) * bilinear(P, zt, a2, el.j, el.yc, clamped);
     }
     weight = double(refl) * double(tm);
@@ -416,12 +494,15 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   // ================= strongback strips rt:2149-2185
   {
+    // strips at (i + 0.5) d + i w < |y| < (i + 0.5) d + (i + 1) w, i = 0 .. nStripHalf-1  (closed form of the loop)
     const double yt = fabs(yw * P.cosTheta - xw * P.sinTheta);
     int sb = 2;
-    for (int i = 0; i < P.nStripHalf; ++i) {
-      const double lo = (double(i) + 0.5) * P.stripDist + double(i) * P.stripWidth;
-      if (yt > lo && yt < lo + P.stripWidth) { sb = 1; break; }
-      sb = 0;
+    if (P.nStripHalf > 0) {
+      const double pitch = P.stripDist + P.stripWidth;
+      const double u = yt - 0.5 * P.stripDist;
+      const double fi = floor(u * P.invStripPitch);
+      const double off = u - fi * pitch;
+      sb = (u > 0.0 && fi < double(P.nStripHalf) && off > 0.0 && off < P.stripWidth) ? 1 : 0;
     }
     const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
     if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) weight *= double(tw);
@@ -429,7 +510,7 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) weight *= double(el.Agas);
   if (!(P.flags & SART_CF_XRAY_TEST)) weight *= double(P.exposure);
   out.shell = hitLayer;
-  out.r = sqrt(rw2);
+  out.r = rw2 > 1e-30 ? rw2 * rsqrt_nr(rw2) : 0.0;
   out.x = -xw + P.chipCX;
   out.y = yw + P.chipCY;
   out.w = weight;
@@ -446,15 +527,11 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
                 uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
                 double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
-  // layout: radius CDF (f64) | shells | radius guide (u16) | per-warp counters
-  double* sRadCDF = reinterpret_cast<double*>(smem);
-  ShellFast* sShell = reinterpret_cast<ShellFast*>(sRadCDF + ((P.nRadii + 1) & ~1));
-  uint16_t* sRadGuide = reinterpret_cast<uint16_t*>(sShell + P.nShells);
-  WarpCounters* wc = reinterpret_cast<WarpCounters*>(reinterpret_cast<unsigned char*>(sRadGuide) + ((2 * (kGuide + 1) + 15) & ~15));
-  for (int i = threadIdx.x; i < P.nRadii; i += kBlock) sRadCDF[i] = T.radiusCDF[i];
-  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
-    reinterpret_cast<double*>(sShell)[i] = reinterpret_cast<const double*>(T.shells)[i];
-  if (P.nRadii > 0) for (int i = threadIdx.x; i <= kGuide; i += kBlock) sRadGuide[i] = T.radiusGuide[i];
+  Smem S;
+  unsigned char* tail;
+  smem_layout(P, smem, S, tail);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
+  smem_fill(P, T, S);
   for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
@@ -465,7 +542,7 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
     RayResult r;
-    trace_one<kWolter>(P, T, sRadCDF, sRadGuide, sShell, seed, first + i, mAxion2, r);
+    trace_one<kWolter>(P, T, S, seed, first + i, mAxion2, r);
     ++nIter;
     const int code = r.code & SART_CODE_MASK;
     if (r.code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
@@ -518,18 +595,15 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
                      double* __restrict__ ow, int32_t* __restrict__ ocode, int32_t* __restrict__ oshell,
                      double* __restrict__ oenergy, double* __restrict__ orad) {
   extern __shared__ __align__(16) unsigned char smem[];
-  double* sRadCDF = reinterpret_cast<double*>(smem);
-  ShellFast* sShell = reinterpret_cast<ShellFast*>(sRadCDF + ((P.nRadii + 1) & ~1));
-  uint16_t* sRadGuide = reinterpret_cast<uint16_t*>(sShell + P.nShells);
-  for (int i = threadIdx.x; i < P.nRadii; i += kBlock) sRadCDF[i] = T.radiusCDF[i];
-  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
-    reinterpret_cast<double*>(sShell)[i] = reinterpret_cast<const double*>(T.shells)[i];
-  if (P.nRadii > 0) for (int i = threadIdx.x; i <= kGuide; i += kBlock) sRadGuide[i] = T.radiusGuide[i];
+  Smem S;
+  unsigned char* tail;
+  smem_layout(P, smem, S, tail);
+  smem_fill(P, T, S);
   __syncthreads();
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
     RayResult r;
-    trace_one<kWolter>(P, T, sRadCDF, sRadGuide, sShell, seed, first + i, mAxion2, r);
+    trace_one<kWolter>(P, T, S, seed, first + i, mAxion2, r);
     ox[i] = r.x; oy[i] = r.y; ow[i] = r.w; ocode[i] = r.code; oshell[i] = r.shell;
     if (oenergy) oenergy[i] = double(r.energy);
     if (orad) orad[i] = r.r;
@@ -537,8 +611,8 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
 }
 
 size_t smem_bytes(const FastParams& P) {
-  return size_t((P.nRadii + 1) & ~1) * 8 + size_t(P.nShells) * sizeof(ShellFast) + ((2 * (kGuide + 1) + 15) & ~15) +
-         kWarps * sizeof(WarpCounters);
+  return size_t(P.nShells) * sizeof(ShellFast) + size_t((P.nRadii + 1) & ~1) * 8 + ((2 * (kGuide + 1) + 15) & ~15) +
+         ((size_t(P.nShellGuide) + 15) & ~size_t(15)) + kWarps * sizeof(WarpCounters);
 }
 
 }  // namespace fast
