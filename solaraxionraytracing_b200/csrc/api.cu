@@ -1,6 +1,7 @@
 // api.cu — the C-ABI of libsart.so (include/sart.h): handle lifetime, table upload, launches, read-back.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -70,13 +71,16 @@ static int validate(const sart_setup_t* s, const sart_tables_t* t) {
 }
 
 // Guide table of a CDF row: g[k] = lowerBound(cdf, k/K), k = 0..K. For k/K <= u < (k+1)/K the answer of
-// lowerBound(cdf, u) lies in [g[k], g[k+1]], so the device search starts from a window of a few entries.
-static void build_guide(const double* cdf, int n, uint16_t* g) {
+// lowerBound(cdf, u) lies in [g[k], g[k+1]], so the device search starts from a window of 1-2 entries. Stored packed,
+// out[k] = g[k] | g[k+1] << 16, so that a window is one 32-bit load.
+static void build_guide(const double* cdf, int n, uint32_t* out) {
   int pos = 0;
+  uint32_t prev = 0;
   for (int k = 0; k <= kGuide; ++k) {
     const double key = double(k) / double(kGuide);
     while (pos < n && cdf[pos] < key) ++pos;
-    g[k] = uint16_t(pos);
+    if (k > 0) out[k - 1] = prev | (uint32_t(pos) << 16);
+    prev = uint32_t(pos);
   }
 }
 
@@ -97,18 +101,12 @@ struct Blob {  // bump allocator over one device allocation
 
 static int upload_tables(sart_handle* h, const sart_tables_t* t) {
   Blob b;
-  size_t oEn = 0, oRC = 0, oDC = 0, oRG = 0, oEG = 0, oRefl = 0;
+  size_t oEn = 0, oRC = 0, oDC = 0, oRefl = 0;
   const bool solar = t->nRadii > 0 && t->energies;
   if (solar) {
     oEn = b.add(t->energies, t->nEnergies);
     oRC = b.add(t->fluxRadiusCDF, t->nRadii);
     oDC = b.add(t->diffFluxCDFs, size_t(t->nRadii) * t->nEnergies);
-    std::vector<uint16_t> rg(kGuide + 1), eg(size_t(t->nRadii) * (kGuide + 1));
-    build_guide(t->fluxRadiusCDF, t->nRadii, rg.data());
-    for (int r = 0; r < t->nRadii; ++r)
-      build_guide(t->diffFluxCDFs + size_t(r) * t->nEnergies, t->nEnergies, eg.data() + size_t(r) * (kGuide + 1));
-    oRG = b.add(rg.data(), rg.size());
-    oEG = b.add(eg.data(), eg.size());
   }
   const bool refl = t->reflectivity && t->nCoatings > 0;
   if (refl) oRefl = b.add(t->reflectivity, size_t(t->nCoatings) * t->nAngles * t->nReflEnergies);
@@ -134,8 +132,6 @@ static int upload_tables(sart_handle* h, const sart_tables_t* t) {
     T.energies = reinterpret_cast<const double*>(base + oEn);
     T.fluxRadiusCDF = reinterpret_cast<const double*>(base + oRC);
     T.diffFluxCDFs = reinterpret_cast<const double*>(base + oDC);
-    T.radiusGuide = reinterpret_cast<const uint16_t*>(base + oRG);
-    T.energyGuide = reinterpret_cast<const uint16_t*>(base + oEG);
   }
   if (refl) T.reflectivity = reinterpret_cast<const double*>(base + oRefl);
   const double** PX[4] = {&T.sbX, &T.wdX, &T.gaX, &T.ttX};
@@ -158,6 +154,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   h->fast_ok = fast::supported(h->setup, &why) ? 1 : 0;
   h->fast_why = why;
   if (!h->fast_ok) return SART_OK;
+  const Params& P = h->params;
   if (t) {
     h->h_energies.assign(t->energies ? t->energies : nullptr, t->energies ? t->energies + t->nEnergies : nullptr);
     const sart_interp1d_t* I[3] = {&t->strongbackTransmission, &t->windowTransmission, &t->gasAbsorption};
@@ -165,47 +162,81 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
       h->h_tab[k][0].assign(I[k]->x, I[k]->x + I[k]->n);
       h->h_tab[k][1].assign(I[k]->y, I[k]->y + I[k]->n);
     }
+    const size_t nRefl = t->reflectivity ? size_t(t->nCoatings) * t->nAngles * t->nReflEnergies : 0;
+    h->h_refl32.resize(nRefl);
+    for (size_t i = 0; i < nRefl; ++i) h->h_refl32[i] = float(t->reflectivity[i]);
   }
   sart_interp1d_t I[3];
   for (int k = 0; k < 3; ++k) I[k] = sart_interp1d_t{int32_t(h->h_tab[k][0].size()), 0, h->h_tab[k][0].data(), h->h_tab[k][1].data()};
-  fast::derive_params(h->setup, h->params, &h->fparams);
+  fast::derive_params(h->setup, P, &h->fparams);
   std::vector<ShellF64> sh64(SART_MAX_SHELLS);
   derive_shells(h->setup, sh64.data());
   std::vector<fast::ShellFast> shf(SART_MAX_SHELLS);
   fast::derive_shells(h->setup, sh64.data(), shf.data());
   std::vector<uint8_t> sguide;
   fast::build_shell_guide(h->setup, &h->fparams, &sguide);
+  if (sguide.size() > 4096) return fail(SART_ERR_CONFIG, "shell guide too large (%zu)", sguide.size());
+  const int nE = int(h->h_energies.size());
   std::vector<fast::EnergyLUT> lut;
-  fast::build_energy_lut(h->params, int(h->h_energies.size()), h->h_energies.data(), I[0], I[1], I[2],
-                         h->setup.testSource.energy, &lut);
+  std::vector<fast::GasLUT> glut;
+  fast::build_energy_lut(nE, h->h_energies.data(), I[0], I[1], I[2], h->setup.testSource.energy, &lut, &glut);
+  const int nCoat = P.nAngles > 0 && !h->h_refl32.empty() ? int(h->h_refl32.size() / (size_t(P.nAngles) * P.nReflEnergies)) : 0;
+  const size_t reflRow = size_t(P.nAngles), reflPlane = reflRow * (size_t(nE) + 1);
   unsigned char* base = static_cast<unsigned char*>(h->fast_blob);
   if (t) {
-    // layout: shells | shell guide (4 KiB reserved) | lut | refl(f32)
-    const size_t nRefl = t->reflectivity ? size_t(t->nCoatings) * t->nAngles * t->nReflEnergies : 0;
-    h->fast_shell_off = 0;
-    h->fast_sguide_off = align256(shf.size() * sizeof(fast::ShellFast));
-    h->fast_lut_off = h->fast_sguide_off + 4096;
-    const size_t reflOff = h->fast_lut_off + align256(lut.size() * sizeof(fast::EnergyLUT));
+    // layout: shells | shell guide (4 KiB) | lut | gas lut | radius guide | energy guide | reflE
+    size_t off = 0;
+    h->fast_shell_off = off; off += align256(shf.size() * sizeof(fast::ShellFast));
+    h->fast_sguide_off = off; off += 4096;
+    h->fast_lut_off = off; off += align256(lut.size() * sizeof(fast::EnergyLUT));
+    h->fast_glut_off = off; off += align256(glut.size() * sizeof(fast::GasLUT));
+    const size_t rgOff = off; off += align256(size_t(kGuide) * 4);
+    const size_t egOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * kGuide * 4);
+    h->fast_refl_off = off; off += align256(size_t(std::max(nCoat, 1)) * reflPlane * sizeof(float));
     if (h->fast_blob) { cudaFree(h->fast_blob); h->fast_blob = nullptr; }
-    SART_CUDA(cudaMalloc(&h->fast_blob, reflOff + align256(nRefl * sizeof(float)) + 256));
+    SART_CUDA(cudaMalloc(&h->fast_blob, off + 256));
     base = static_cast<unsigned char*>(h->fast_blob);
-    if (nRefl) {
-      std::vector<float> rf(nRefl);
-      for (size_t i = 0; i < nRefl; ++i) rf[i] = float(t->reflectivity[i]);
-      SART_CUDA(cudaMemcpy(base + reflOff, rf.data(), nRefl * sizeof(float), cudaMemcpyHostToDevice));
+    if (P.nRadii > 0 && t->fluxRadiusCDF) {
+      std::vector<uint32_t> rg(kGuide), eg(size_t(P.nRadii) * kGuide);
+      build_guide(t->fluxRadiusCDF, P.nRadii, rg.data());
+      for (int r = 0; r < P.nRadii; ++r)
+        build_guide(t->diffFluxCDFs + size_t(r) * P.nEnergies, P.nEnergies, eg.data() + size_t(r) * kGuide);
+      SART_CUDA(cudaMemcpy(base + rgOff, rg.data(), rg.size() * 4, cudaMemcpyHostToDevice));
+      SART_CUDA(cudaMemcpy(base + egOff, eg.data(), eg.size() * 4, cudaMemcpyHostToDevice));
     }
-    h->ftables.refl = reinterpret_cast<const float*>(base + reflOff);
-    h->ftables.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
-    h->ftables.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
-    h->ftables.shellGuide = reinterpret_cast<const uint8_t*>(base + h->fast_sguide_off);
-    h->ftables.radiusCDF = h->tables.fluxRadiusCDF;
-    h->ftables.radiusGuide = h->tables.radiusGuide;
-    h->ftables.energyCDF = h->tables.diffFluxCDFs;
-    h->ftables.energyGuide = h->tables.energyGuide;
+    // reflectivity interpolated along energy at each tabulated energy
+    if (nCoat > 0) {
+      std::vector<float> re(size_t(nCoat) * reflPlane);
+      for (int c = 0; c < nCoat; ++c) {
+        const float* z = h->h_refl32.data() + size_t(c) * P.nAngles * P.nReflEnergies;
+        for (int i = 0; i <= nE; ++i)
+          fast::refl_at_energy(P, z, i < nE ? std::max(0.03, h->h_energies[i]) : h->setup.testSource.energy,
+                               re.data() + size_t(c) * reflPlane + size_t(i) * reflRow);
+      }
+      SART_CUDA(cudaMemcpy(base + h->fast_refl_off, re.data(), re.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    fast::FastTables& F = h->ftables;
+    F.radiusCDF = h->tables.fluxRadiusCDF;
+    F.energyCDF = h->tables.diffFluxCDFs;
+    F.radiusGuide = reinterpret_cast<const uint32_t*>(base + rgOff);
+    F.energyGuide = reinterpret_cast<const uint32_t*>(base + egOff);
+    F.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
+    F.glut = reinterpret_cast<const fast::GasLUT*>(base + h->fast_glut_off);
+    F.reflE = reinterpret_cast<const float*>(base + h->fast_refl_off);
+    F.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
+    F.shellGuide = reinterpret_cast<const uint8_t*>(base + h->fast_sguide_off);
+  } else if (nCoat > 0) {
+    // setup update: only the X-ray-source row (index nE) of each coating can have changed
+    std::vector<float> row(reflRow);
+    for (int c = 0; c < nCoat; ++c) {
+      fast::refl_at_energy(P, h->h_refl32.data() + size_t(c) * P.nAngles * P.nReflEnergies, h->setup.testSource.energy, row.data());
+      SART_CUDA(cudaMemcpy(base + h->fast_refl_off + (size_t(c) * reflPlane + size_t(nE) * reflRow) * sizeof(float),
+                           row.data(), reflRow * sizeof(float), cudaMemcpyHostToDevice));
+    }
   }
   SART_CUDA(cudaMemcpy(base + h->fast_shell_off, shf.data(), shf.size() * sizeof(fast::ShellFast), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_lut_off, lut.data(), lut.size() * sizeof(fast::EnergyLUT), cudaMemcpyHostToDevice));
-  if (sguide.size() > 4096) return fail(SART_ERR_CONFIG, "shell guide too large (%zu)", sguide.size());
+  SART_CUDA(cudaMemcpy(base + h->fast_glut_off, glut.data(), glut.size() * sizeof(fast::GasLUT), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_sguide_off, sguide.data(), sguide.size(), cudaMemcpyHostToDevice));
   return SART_OK;
 }

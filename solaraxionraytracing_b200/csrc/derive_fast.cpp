@@ -156,38 +156,43 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   f->srcEIdx = P.nEnergies;  // the record after the tabulated energies holds the X-ray source energy
 }
 
-static EnergyLUT lut_entry(double E, const Params& P, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
-                           const sart_interp1d_t& ga) {
+static void lut_entry(double E, const sart_interp1d_t& sb, const sart_interp1d_t& wd, const sart_interp1d_t& ga,
+                      EnergyLUT* e, GasLUT* g) {
   // A transmission that is non-zero in f64 must stay non-zero in the f32 table: `passed` means weight != 0
   // (rt:2220), and e.g. 200 um of Si transmit 1e-60 at 0.3 keV.
   auto f32nz = [](double v) { return (v != 0.0 && std::fabs(v) < 1.2e-38) ? float(std::copysign(1.2e-38, v)) : float(v); };
-  EnergyLUT e;
-  e.E = float(E);
-  e.Twindow = f32nz(lin1d(wd, E));
-  e.Tstrongback = f32nz(lin1d(sb, E));
-  e.Agas = f32nz(lin1d(ga, E));
-  if (P.nReflEnergies >= 2) {
-    const double y = std::min(std::max(E, P.reflEMin), P.reflEMax);
-    const double fy = (y - P.reflEMin) / P.reflDy;
-    int j = int(std::floor(fy));
-    if (j > P.nReflEnergies - 2) j = P.nReflEnergies - 2;
-    e.j = j;
-    e.yc = float(fy - double(j));
-  } else {
-    e.j = 0; e.yc = 0.f;
-  }
+  e->E = float(E);
+  e->Twindow = f32nz(lin1d(wd, E));
+  e->Tstrongback = f32nz(lin1d(sb, E));
+  e->Agas = f32nz(lin1d(ga, E));
   const double lma = -1.5832 + 5.9195 * std::exp(-0.353808 * E) + 4.03598 * std::exp(-0.970557 * E);
-  e.massAtt = float(std::exp(lma));
-  e.inv2E = float(1.0 / (2.0 * (E * 1000.0)));
-  return e;
+  g->massAtt = float(std::exp(lma));
+  g->inv2E = float(1.0 / (2.0 * (E * 1000.0)));
 }
 
 // nEnergies records (E = max(0.03 keV, energies[i]), rt:470-471) + one for the X-ray test-source energy.
-void build_energy_lut(const Params& P, int nE, const double* energies, const sart_interp1d_t& sb,
-                      const sart_interp1d_t& wd, const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out) {
+void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
+                      const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out, std::vector<GasLUT>* gout) {
   out->resize(size_t(nE) + 1);
-  for (int i = 0; i < nE; ++i) (*out)[i] = lut_entry(std::max(0.03, energies[i]), P, sb, wd, ga);
-  (*out)[nE] = lut_entry(srcEnergy, P, sb, wd, ga);
+  gout->resize(size_t(nE) + 1);
+  for (int i = 0; i <= nE; ++i)
+    lut_entry(i < nE ? std::max(0.03, energies[i]) : srcEnergy, sb, wd, ga, &(*out)[i], &(*gout)[i]);
+}
+
+// Reflectivity of one coating interpolated along the energy axis at energy E, for every angle node:
+// out[i] = z[i][j] + yc (z[i][j+1] - z[i][j]) with (j, yc) the energy cell of the bilinear spline (rt:1567-1578).
+void refl_at_energy(const Params& P, const float* z, double E, float* out) {
+  const int nA = P.nAngles, nEn = P.nReflEnergies;
+  const double y = std::min(std::max(E, P.reflEMin), P.reflEMax);
+  const double fy = (y - P.reflEMin) / P.reflDy;
+  int j = int(std::floor(fy));
+  if (j > nEn - 2) j = nEn - 2;
+  if (j < 0) j = 0;
+  const float yc = float(fy - double(j));
+  for (int i = 0; i < nA; ++i) {
+    const float z0 = z[size_t(i) * nEn + j], z1 = z[size_t(i) * nEn + j + 1];
+    out[i] = z0 + yc * (z1 - z0);
+  }
 }
 
 }  // namespace fast

@@ -67,8 +67,6 @@ struct Tables {
   const double* energies;
   const double* fluxRadiusCDF;
   const double* diffFluxCDFs;
-  const uint16_t* radiusGuide;   // guide table for the radius CDF search
-  const uint16_t* energyGuide;   // [nRadii][kGuide+1] guide table for the per-radius energy CDF search
   const double* reflectivity;
   const double *sbX, *sbY, *wdX, *wdY, *gaX, *gaY, *ttX, *ttY;
   int32_t sbN, wdN, gaN, ttN;

@@ -45,23 +45,27 @@ struct FastParams {
   int32_t nShellGuide, rotated;
 };
 
-struct EnergyLUT {  // one record per tabulated energy index (32 B)
+struct EnergyLUT {  // one record per tabulated energy index (16 B, one LDG.128)
   float E, Twindow, Tstrongback, Agas;
-  float yc;        // offset inside the reflectivity energy cell, in units of the cell (0..1)
-  int32_t j;       // reflectivity energy cell
+};
+struct GasLUT {     // buffer-gas stage only
   float massAtt;   // exp(logMassAttenuation(E)) am:70-73
   float inv2E;     // 1 / (2 E[eV])
 };
 
 struct FastTables {
-  const double* radiusCDF; const uint16_t* radiusGuide;
-  const double* energyCDF; const uint16_t* energyGuide;
-  const EnergyLUT* elut;
-  const float* refl;          // [coat][nAngles][nReflEnergies]
+  const double* radiusCDF;
+  const uint32_t* radiusGuide;   // [kGuide] packed (g[k] | g[k+1] << 16), g[k] = lowerBound(cdf, k/kGuide)
+  const double* energyCDF;
+  const uint32_t* energyGuide;   // [nRadii][kGuide] packed likewise
+  const EnergyLUT* elut;         // [nEnergies + 1]
+  const GasLUT* glut;            // [nEnergies + 1]
+  // reflectivity pre-interpolated along the energy axis at every tabulated energy: [coat][nEnergies + 1][nAngles];
+  // the per-ray lookup is then linear in the grazing angle only (same value as the bilinear form of rt:1567-1578)
+  const float* reflE;
   const ShellFast* shells;    // [nShells]
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
 };
-
 
 }  // namespace fast
 }  // namespace sart

@@ -128,19 +128,16 @@ __device__ __forceinline__ double reflect(D3 n, D3& v) {
   return as;
 }
 
-__device__ __forceinline__ float bilinear(const FastParams& P, const float* __restrict__ z, float alphaDeg, int j,
-                                          float yc, bool& clamped) {
+// Reflectivity at grazing angle alphaDeg from the row pre-interpolated at the ray's energy: linear in the angle.
+__device__ __forceinline__ float refl_lookup(const FastParams& P, const float* __restrict__ row, float alphaDeg, bool& clamped) {
   float x = alphaDeg;
   if (!(x >= P.angleMin)) { x = P.angleMin; clamped = true; }
   if (!(x <= P.angleMax)) { x = P.angleMax; clamped = true; }
   const float fx = (x - P.angleMin) * P.invReflDx;
   int i = int(fx);
   if (i > P.nAngles - 2) i = P.nAngles - 2;
-  const float xc = fx - float(i);
-  const float* r0 = z + size_t(i) * P.nReflEnergies + j;
-  const float z00 = __ldg(r0), z01 = __ldg(r0 + 1), z10 = __ldg(r0 + P.nReflEnergies), z11 = __ldg(r0 + P.nReflEnergies + 1);
-  const float a = fmaf(yc, z01 - z00, z00), b = fmaf(yc, z11 - z10, z10);
-  return fmaf(xc, b - a, a);
+  const float z0 = __ldg(row + i), z1 = __ldg(row + i + 1);
+  return fmaf(fx - float(i), z1 - z0, z0);
 }
 
 struct RayResult {
@@ -155,14 +152,14 @@ struct RayResult {
 struct Smem {
   const ShellFast* shell;
   const double* radCDF;
-  const uint16_t* radGuide;
+  const uint32_t* radGuide;
   const uint8_t* shellGuide;
 };
 __device__ __forceinline__ size_t smem_layout(const FastParams& P, unsigned char* base, Smem& s, unsigned char*& tail) {
   size_t off = 0;
   s.shell = reinterpret_cast<const ShellFast*>(base + off); off += size_t(P.nShells) * sizeof(ShellFast);
   s.radCDF = reinterpret_cast<const double*>(base + off); off += size_t((P.nRadii + 1) & ~1) * 8;
-  s.radGuide = reinterpret_cast<const uint16_t*>(base + off); off += (2 * (kGuide + 1) + 15) & ~15;
+  s.radGuide = reinterpret_cast<const uint32_t*>(base + off); off += size_t(kGuide) * 4;
   s.shellGuide = base + off; off += (size_t(P.nShellGuide) + 15) & ~size_t(15);
   tail = base + off;
   return off;
@@ -171,7 +168,7 @@ __device__ __forceinline__ void smem_fill(const FastParams& P, const FastTables&
   for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
     reinterpret_cast<double*>(const_cast<ShellFast*>(s.shell))[i] = reinterpret_cast<const double*>(T.shells)[i];
   for (int i = threadIdx.x; i < P.nRadii; i += kBlock) const_cast<double*>(s.radCDF)[i] = T.radiusCDF[i];
-  if (P.nRadii > 0) for (int i = threadIdx.x; i <= kGuide; i += kBlock) const_cast<uint16_t*>(s.radGuide)[i] = T.radiusGuide[i];
+  if (P.nRadii > 0) for (int i = threadIdx.x; i < kGuide; i += kBlock) const_cast<uint32_t*>(s.radGuide)[i] = T.radiusGuide[i];
   for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
 }
 
@@ -197,15 +194,12 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     // emission shell (exact index: same f64 CDF, same key as the oracle)
     const double ur = u01(w[2]);
     const int kr = int(ur * double(kGuide));
-    int rIdx = S.radGuide[kr];
-    {
-      const int rHi = S.radGuide[kr + 1];
-      while (rIdx < rHi && S.radCDF[rIdx] < ur) ++rIdx;   // lowerBound inside the guide window (1-2 entries)
-    }
+    const uint32_t gr = S.radGuide[kr];
+    const int rIdx = lower_bound_window(S.radCDF, int(gr & 0xffffu), int(gr >> 16), ur);
     ue = u01(w[5]);
     {
-      const uint16_t* g = T.energyGuide + size_t(rIdx) * (kGuide + 1) + int(ue * double(kGuide));
-      eLo = __ldg(g); eHi = __ldg(g + 1);
+      const uint32_t ge = __ldg(T.energyGuide + size_t(rIdx) * kGuide + int(ue * double(kGuide)));
+      eLo = int(ge & 0xffffu); eHi = int(ge >> 16);
       eRow = T.energyCDF + size_t(rIdx) * P.nEnergies;
     }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);  // fraction of the solar radius (weight-free: direction only)
@@ -273,9 +267,15 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   double x0 = fma(sx, P.dzPipe2, ex), y0 = fma(sy, P.dzPipe2, ey);
   if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) { out.code = SART_EXIT_CLIP_PIPE_XRT; return; }  // quirk Q2
-  // energy CDF window: four independent loads (the guide window is 1-2 entries wide on average)
-  double ec0 = 2.0, ec1 = 2.0, ec2 = 2.0, ec3 = 2.0;
-  if (eRow) { ec0 = __ldg(eRow + eLo); ec1 = __ldg(eRow + eLo + 1); ec2 = __ldg(eRow + eLo + 2); ec3 = __ldg(eRow + eLo + 3); }
+  // energy CDF window: two 16-byte loads starting at the aligned entry at or below eLo (windows are 1-2 entries wide)
+  double2 ecA = make_double2(2.0, 2.0), ecB = make_double2(2.0, 2.0);
+  int e0 = 0;
+  if (eRow) {
+    const double* p = eRow + eLo;
+    e0 = eLo - int((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
+    ecA = __ldg(reinterpret_cast<const double2*>(eRow + e0));
+    ecB = __ldg(reinterpret_cast<const double2*>(eRow + e0 + 2));
+  }
 
   // ================= telescope frame rt:1888-1905 (rotation about (0, 0, halfLenTel); identity when not turned)
   double dx = sx, dy = sy, dz = 1.0, z0 = 0.0;
@@ -379,13 +379,14 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   // energy index from the CDF window loaded above; its LUT record is needed only at the weight stage
   if (eRow) {
-    const int cnt = int(eLo < eHi && ec0 < ue) + int(eLo + 1 < eHi && ec1 < ue) + int(eLo + 2 < eHi && ec2 < ue) +
-                    int(eLo + 3 < eHi && ec3 < ue);
+    const int cnt = int(e0 >= eLo && e0 < eHi && ecA.x < ue) + int(e0 + 1 < eHi && ecA.y < ue) +
+                    int(e0 + 2 < eHi && ecB.x < ue) + int(e0 + 3 < eHi && ecB.y < ue);
     eIdx = eLo + cnt;
-    if (cnt == 4 && eLo + 4 < eHi) eIdx = lower_bound_window(eRow, eLo + 4, eHi, ue);
+    if (eIdx == e0 + 4 && e0 + 4 < eHi) eIdx = lower_bound_window(eRow, e0 + 4, eHi, ue);
     if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
   }
-  const EnergyLUT el = T.elut[eIdx];
+  const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);
+  const EnergyLUT el = {elv.x, elv.y, elv.z, elv.w};
   D3 pm = {fma(tx, z1, x0), fma(ty, z1, y0), z1};
   D3 v = {tx * invLen, ty * invLen, invLen};
   double sinA1;
@@ -461,11 +462,13 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     if (P.stage == SART_SK_VACUUM) {
       if (!(P.flags & SART_CF_IGNORE_CONV_PROB)) tm *= P.convK * path2f;
     } else {
+      const float2 gv = __ldg(reinterpret_cast<const float2*>(T.glut) + eIdx);
+      const GasLUT gl_ = {gv.x, gv.y};
       const float pathm = sqrtf(path2f) * 1e-3f;
       if (!(P.flags & SART_CF_IGNORE_CONV_PROB)) {   // axionConversionProb2 am:75-100
-        const double gamma = P.gasGamma0 * double(el.massAtt);
+        const double gamma = P.gasGamma0 * double(gl_.massAtt);
         const double L = double(pathm) / 1.97e-7;
-        const double q = fabs(P.gasMgamma2 - mAxion2) * double(el.inv2E);
+        const double q = fabs(P.gasMgamma2 - mAxion2) * double(gl_.inv2E);
         const float gl = float(gamma * L);
         const float e1 = __expf(-gl), e2 = __expf(-0.5f * gl);
         double ph = q * L;   // phase reduced in FP64 before the FP32 cosine
@@ -475,13 +478,13 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
         tm *= float(P.gasTerm1 * term2) * (1.0f + e1 - 2.0f * e2 * cq_);
       }
       const float distPipe = float(zw - P.zExitCBtel) * 1e-3f;
-      tm *= __expf(-el.massAtt * float(P.gasRhoPipe100) * distPipe) * __expf(-el.massAtt * float(P.gasRhoMagnet100) * pathm);
+      tm *= __expf(-gl_.massAtt * float(P.gasRhoPipe100) * distPipe) * __expf(-gl_.massAtt * float(P.gasRhoMagnet100) * pathm);
     }
     float refl = 1.0f;
     if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
-      const float* zt = T.refl + size_t(sh.coat) * P.nAngles * P.nReflEnergies;
+      const float* zt = T.reflE + (size_t(sh.coat) * (P.nEnergies + 1) + eIdx) * P.nAngles;
       const float a1 = asin_small(float(sinA1)) * 57.29577951308232f, a2 = asin_small(float(sinA2)) * 57.29577951308232f;
-      refl = bilinear(P, zt, a1, el.j, el.yc, clamped) * bilinear(P, zt, a2, el.j, el.yc, clamped);
+      refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
     }
     weight = double(refl) * double(tm);
   }
@@ -611,7 +614,7 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
 }
 
 size_t smem_bytes(const FastParams& P) {
-  return size_t(P.nShells) * sizeof(ShellFast) + size_t((P.nRadii + 1) & ~1) * 8 + ((2 * (kGuide + 1) + 15) & ~15) +
+  return size_t(P.nShells) * sizeof(ShellFast) + size_t((P.nRadii + 1) & ~1) * 8 + size_t(kGuide) * 4 +
          ((size_t(P.nShellGuide) + 15) & ~size_t(15)) + kWarps * sizeof(WarpCounters);
 }
 

@@ -26,9 +26,10 @@ bool supported(const sart_setup_t& s, const char** why);
 void derive_shells(const sart_setup_t& s, const ShellF64* exactShells, ShellFast* out);
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f);
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide);
-void build_energy_lut(const Params& P, int nE, const double* energies, const sart_interp1d_t& sb,
-                      const sart_interp1d_t& wd, const sart_interp1d_t& ga, double srcEnergy,
-                      std::vector<EnergyLUT>* out);
+void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
+                      const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out,
+                      std::vector<GasLUT>* gout);
+void refl_at_energy(const Params& P, const float* z, double E, float* out);
 }  // namespace fast
 
 }  // namespace sart
@@ -48,7 +49,8 @@ struct sart_handle {
   sart::fast::FastParams fparams;
   sart::fast::FastTables ftables;
   void* fast_blob = nullptr;
-  size_t fast_shell_off = 0, fast_lut_off = 0, fast_sguide_off = 0;
+  size_t fast_shell_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_sguide_off = 0, fast_refl_off = 0;
+  std::vector<float> h_refl32;  // host copy of the reflectivity (f32) for rebuilding the X-ray-source row
   std::vector<double> h_energies, h_tab[3][2];  // host copies (energies; strongback/window/gas x,y) for LUT rebuilds
   int sm_count = 148;
   size_t shell_offset = 0;      // byte offset of the ShellF64 array inside table_blob
