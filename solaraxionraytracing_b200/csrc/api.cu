@@ -518,7 +518,12 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   DeviceGuard dg(h->device);
-  if (h->precision == 1 && h->n_masses == 1) {
+  if (h->precision == 1 && h->n_masses > 1) {
+    SART_CUDA(launch_mc_image_fast_masses(h->fparams, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays, seed,
+                                          h->d_image, h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+    return SART_OK;
+  }
+  if (h->precision == 1) {
     SART_CUDA(launch_mc_image_fast(h->fparams, h->ftables, h->masses[0], first_ray, n_rays, seed, h->d_image,
                                    h->d_image_w2, h->d_counters, h->sm_count, h->stream));
     return SART_OK;

@@ -24,6 +24,10 @@ cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTabl
                                  uint64_t nRays, uint64_t seed, double* image, double* imageW2,
                                  sart_counters_t* counters, int smCount, cudaStream_t s);
 
+cudaError_t launch_mc_image_fast_masses(const fast::FastParams& P, const fast::FastTables& T, int nMasses,
+                                        const double* dMasses, uint64_t first, uint64_t nRays, uint64_t seed,
+                                        double* image, double* imageW2, sart_counters_t* counters, int smCount,
+                                        cudaStream_t s);
 cudaError_t launch_mc_rays_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
                                 uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount, cudaStream_t s);
 cudaError_t launch_heatmap(int rows, int cols, double start_x, double step_x, double start_y, double step_y, size_t n,

@@ -140,12 +140,20 @@ __device__ __forceinline__ float refl_lookup(const FastParams& P, const float* _
   return fmaf(fx - float(i), z1 - z0, z0);
 }
 
+// What trace_one knows about a ray. `code` is the exit code of a geometric early return, or -1 when the ray reached
+// the weight stage; then weight(m_a) = wPre * conv(m_a) * wPost (finish_ray), so a mass scan re-uses one traced ray.
 struct RayResult {
-  int code;       // exit code | flags
+  int code;
   int bin;        // image bin or -1
   int shell;
+  bool windowMiss, clamped;
   float energy;
-  double w, x, y, r;
+  double wPre;    // reflectivity * cos(yaw) * He absorption        (everything before the window, without P(a->gamma))
+  double wPost;   // window or strongback * detector gas * exposure (0 when the window aperture is missed)
+  double x, y, r;
+  // conversion probability pieces: vacuum convVac = (g B L / 2)^2; gas: Gamma, L, exp(-Gamma L), exp(-Gamma L/2), 1/(2E)
+  float convVac, gasGamma, gasE1, gasE2, gasInv2E;
+  double gasL;
 };
 
 // Shared-memory tables of one block (shells first so their addresses are compile-time offsets).
@@ -172,11 +180,27 @@ __device__ __forceinline__ void smem_fill(const FastParams& P, const FastTables&
   for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
 }
 
-template <bool kWolter>
+// Conversion probability for axion mass^2 m2 (computeMagnetTransmission rt:1582-1625 without the cos(ya) factor).
+__device__ __forceinline__ double conv_factor(const FastParams& P, float convVac, float gasGamma, float gasE1, float gasE2,
+                                              float gasInv2E, double gasL, double m2) {
+  if (P.flags & SART_CF_IGNORE_CONV_PROB) return 1.0;
+  if (P.stage == SART_SK_VACUUM) return double(convVac);
+  const double q = fabs(P.gasMgamma2 - m2) * double(gasInv2E);   // momentumTransfer am:63-68
+  double ph = q * gasL;   // phase reduced in FP64 before the FP32 cosine
+  ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);
+  const float cq = __cosf(float(ph));
+  const double g = double(gasGamma);
+  const double term2 = rcp_nr(fma(q, q, 0.25 * g * g));
+  return P.gasTerm1 * term2 * double(1.0f + gasE1 - 2.0f * gasE2 * cq);
+}
+// kFold: fold the conversion probability of the single axion mass m2 into wPre right away (fewer live values).
+template <bool kWolter, bool kFold>
 __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const Smem& S,
-                                          uint64_t seed, uint64_t ray, double mAxion2, RayResult& out) {
+                                          uint64_t seed, uint64_t ray, double m2, RayResult& out) {
   const ShellFast* __restrict__ sShell = S.shell;
-  out.bin = -1; out.w = 0.0; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
+  out.bin = -1; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
+  out.windowMiss = false; out.clamped = false; out.wPre = 0.0; out.wPost = 0.0;
+  out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
   uint32_t w[6];
   ray_words(seed, ray, w);
   constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
@@ -452,33 +476,25 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     xw = fma(n, wx, ax); yw = fma(n, v.y, pm.y); zw = fma(n, wz, az);
   }
   xw -= P.lateralShift; yw -= P.transversalShift;
-  // ================= weights rt:2101-2128
+  // ================= weights rt:2101-2128 (mass-independent factors; P(a->gamma) is applied in finish_ray)
   out.energy = el.E;
-  double weight;  // the factors are FP32, their product is formed in FP64 so that tiny weights do not flush to zero
   {
     const float ya = -atan_small(float(ty)) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
-    float tm = __cosf(ya);
+    float pre = __cosf(ya);
     const float path2f = float(path2);
     if (P.stage == SART_SK_VACUUM) {
-      if (!(P.flags & SART_CF_IGNORE_CONV_PROB)) tm *= P.convK * path2f;
+      out.convVac = P.convK * path2f;              // conversionProb rt:363-365
     } else {
       const float2 gv = __ldg(reinterpret_cast<const float2*>(T.glut) + eIdx);
-      const GasLUT gl_ = {gv.x, gv.y};
       const float pathm = sqrtf(path2f) * 1e-3f;
-      if (!(P.flags & SART_CF_IGNORE_CONV_PROB)) {   // axionConversionProb2 am:75-100
-        const double gamma = P.gasGamma0 * double(gl_.massAtt);
-        const double L = double(pathm) / 1.97e-7;
-        const double q = fabs(P.gasMgamma2 - mAxion2) * double(gl_.inv2E);
-        const float gl = float(gamma * L);
-        const float e1 = __expf(-gl), e2 = __expf(-0.5f * gl);
-        double ph = q * L;   // phase reduced in FP64 before the FP32 cosine
-        ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);
-        const float cq_ = __cosf(float(ph));
-        const double term2 = rcp_nr(fma(q, q, 0.25 * gamma * gamma));
-        tm *= float(P.gasTerm1 * term2) * (1.0f + e1 - 2.0f * e2 * cq_);
-      }
-      const float distPipe = float(zw - P.zExitCBtel) * 1e-3f;
-      tm *= __expf(-gl_.massAtt * float(P.gasRhoPipe100) * distPipe) * __expf(-gl_.massAtt * float(P.gasRhoMagnet100) * pathm);
+      const double gamma = P.gasGamma0 * double(gv.x);   // am:75-100
+      out.gasL = double(pathm) / 1.97e-7;
+      const float gl = float(gamma * out.gasL);
+      out.gasGamma = float(gamma);
+      out.gasE1 = __expf(-gl); out.gasE2 = __expf(-0.5f * gl);
+      out.gasInv2E = gv.y;
+      const float distPipe = float(zw - P.zExitCBtel) * 1e-3f;   // intensitySuppression2 am:102-113
+      pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
     }
     float refl = 1.0f;
     if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
@@ -486,16 +502,19 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
       const float a1 = asin_small(float(sinA1)) * 57.29577951308232f, a2 = asin_small(float(sinA2)) * 57.29577951308232f;
       refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
     }
-    weight = double(refl) * double(tm);
+    out.wPre = double(refl) * double(pre);   // FP32 factors, FP64 product: tiny weights must not flush to zero
+    if (kFold) out.wPre *= conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, m2);
   }
-  int flags = (weight != 0.0) ? SART_FLAG_PASSED_TILL_WINDOW : 0;
-  if (clamped) flags |= SART_FLAG_INTERP_CLAMPED;
+  out.clamped = clamped;
+  out.shell = hitLayer;
+  out.code = -1;
   // ================= window aperture rt:2139-2147
   const double rw2 = fma(xw, xw, yw * yw);
   if ((!(P.flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > P.radiusWindow2) || fabs(xw) > P.chipCX || fabs(yw) > P.chipCY) {
-    out.code = SART_EXIT_WINDOW_APERTURE | flags; return;
+    out.windowMiss = true; return;
   }
   // ================= strongback strips rt:2149-2185
+  double post = 1.0;
   {
     // strips at (i + 0.5) d + i w < |y| < (i + 0.5) d + (i + 1) w, i = 0 .. nStripHalf-1  (closed form of the loop)
     const double yt = fabs(yw * P.cosTheta - xw * P.sinTheta);
@@ -508,19 +527,30 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
       sb = (u > 0.0 && fi < double(P.nStripHalf) && off > 0.0 && off < P.stripWidth) ? 1 : 0;
     }
     const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
-    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) weight *= double(tw);
+    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) post *= double(tw);
   }
-  if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) weight *= double(el.Agas);
-  if (!(P.flags & SART_CF_XRAY_TEST)) weight *= double(P.exposure);
-  out.shell = hitLayer;
+  if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
+  if (!(P.flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
+  out.wPost = post;
   out.r = rw2 > 1e-30 ? rw2 * rsqrt_nr(rw2) : 0.0;
   out.x = -xw + P.chipCX;
   out.y = yw + P.chipCY;
-  out.w = weight;
   // prepareHeatmap rt:839-842
   const int cx = int(floor(out.x * P.invBinX)), cy = int(floor(out.y * P.invBinY));
   if (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) out.bin = cy * SART_IMAGE_BINS + cx;
-  out.code = ((weight != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
+}
+
+// Tail of traceAxion for one axion mass: exit code | flags and the final weight.
+template <bool kFolded>
+__device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& r, double m2, double& w) {
+  const double w0 = kFolded ? r.wPre
+                            : r.wPre * conv_factor(P, r.convVac, r.gasGamma, r.gasE1, r.gasE2, r.gasInv2E, r.gasL, m2);
+  int flags = (w0 != 0.0) ? SART_FLAG_PASSED_TILL_WINDOW : 0;
+  if (r.clamped) flags |= SART_FLAG_INTERP_CLAMPED;
+  w = 0.0;
+  if (r.windowMiss) return SART_EXIT_WINDOW_APERTURE | flags;
+  w = w0 * r.wPost;
+  return ((w != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
 }
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
@@ -545,22 +575,23 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
     RayResult r;
-    trace_one<kWolter>(P, T, S, seed, first + i, mAxion2, r);
+    trace_one<kWolter, true>(P, T, S, seed, first + i, mAxion2, r);
     ++nIter;
-    const int code = r.code & SART_CODE_MASK;
-    if (r.code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
-    if (code == SART_EXIT_PASSED) {
+    int code = r.code;
+    double wd = 0.0;
+    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
+    if (code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
+    if ((code & SART_CODE_MASK) == SART_EXIT_PASSED) {
       ++nPassed;
-      const double wd = r.w;
       sumW += wd; sumW2 += wd * wd; sumX += r.x; sumY += r.y; sumR += r.r;
       if (r.bin >= 0) {
         atomicAdd(image + r.bin, wd);
         atomicAdd(imageW2 + r.bin, wd * wd);
       }
     } else {
-      atomicAdd(&wc[warp].n_exit[code], 1u);
+      atomicAdd(&wc[warp].n_exit[code & SART_CODE_MASK], 1u);
     }
-    if (r.code & SART_FLAG_INTERP_CLAMPED) atomicAdd(&wc[warp].n_clamped, 1u);
+    if (code & SART_FLAG_INTERP_CLAMPED) atomicAdd(&wc[warp].n_clamped, 1u);
   }
   // ---- block reduction and flush
   for (int o = 16; o > 0; o >>= 1) {
@@ -590,6 +621,109 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
   }
 }
 
+// ---- fused kernel, axion-mass scan ---------------------------------------------------------------------------
+// Rays are traced once (lanes = rays); each ray that reaches the weight stage is then broadcast through the warp and
+// weighted for all M masses at once with lanes = masses (mass lane + 32 k), so the per-mass sums live in registers of
+// the lane that owns the mass and need no reduction, and the per-mass image planes are hit by distinct lanes.
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, 2)
+k_trace_mc_fast_masses(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T,
+                       const double* __restrict__ masses, int nMasses, uint64_t first, uint64_t nRays, uint64_t seed,
+                       double* __restrict__ image, double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem S;
+  unsigned char* tail;
+  smem_layout(P, smem, S, tail);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
+  smem_fill(P, T, S);
+  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  __syncthreads();
+
+  constexpr int kPer = SART_MAX_MASSES / 32;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double m2[kPer], sumW[kPer], sumW2[kPer], sumX[kPer], sumY[kPer], sumR[kPer];
+  unsigned int nPassed[kPer], nZero[kPer], nTill[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int m = lane + 32 * k;
+    const double mm = m < nMasses ? masses[m] : 0.0;
+    m2[k] = mm * mm;
+    sumW[k] = sumW2[k] = sumX[k] = sumY[k] = sumR[k] = 0.0;
+    nPassed[k] = nZero[k] = nTill[k] = 0u;
+  }
+  unsigned int nIter = 0;
+  const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS;
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  for (uint64_t b = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31); b < nRays; b += stride) {   // warp-uniform
+    const uint64_t i = b + lane;
+    const bool valid = i < nRays;
+    RayResult r;
+    r.code = SART_N_EXIT_CODES;
+    if (valid) {
+      trace_one<kWolter, false>(P, T, S, seed, first + i, 0.0, r);
+      ++nIter;
+      if (r.code >= 0) atomicAdd(&wc[warp].n_exit[r.code], 1u);
+      else if (r.windowMiss) atomicAdd(&wc[warp].n_exit[SART_EXIT_WINDOW_APERTURE], 1u);
+      if (r.clamped) atomicAdd(&wc[warp].n_clamped, 1u);
+    }
+    unsigned alive = __ballot_sync(kFull, valid && r.code < 0);
+    while (alive) {
+      const int src = __ffs(alive) - 1;
+      alive &= alive - 1;
+      const double wPre = __shfl_sync(kFull, r.wPre, src), wPost = __shfl_sync(kFull, r.wPost, src);
+      const double gasL = __shfl_sync(kFull, r.gasL, src);
+      const float convVac = __shfl_sync(kFull, r.convVac, src), gG = __shfl_sync(kFull, r.gasGamma, src);
+      const float gE1 = __shfl_sync(kFull, r.gasE1, src), gE2 = __shfl_sync(kFull, r.gasE2, src);
+      const float gI = __shfl_sync(kFull, r.gasInv2E, src);
+      const double x = __shfl_sync(kFull, r.x, src), y = __shfl_sync(kFull, r.y, src), rr = __shfl_sync(kFull, r.r, src);
+      const int bin = __shfl_sync(kFull, r.bin, src);
+      const bool miss = __shfl_sync(kFull, int(r.windowMiss), src) != 0;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int m = lane + 32 * k;
+        if (m >= nMasses) continue;
+        const double w0 = wPre * conv_factor(P, convVac, gG, gE1, gE2, gI, gasL, m2[k]);
+        if (w0 != 0.0) ++nTill[k];
+        if (miss) continue;
+        const double w = w0 * wPost;
+        if (w != 0.0) {
+          ++nPassed[k];
+          sumW[k] += w; sumW2[k] += w * w; sumX[k] += x; sumY[k] += y; sumR[k] += rr;
+          if (bin >= 0) {
+            atomicAdd(image + size_t(m) * plane + bin, w);
+            atomicAdd(imageW2 + size_t(m) * plane + bin, w * w);
+          }
+        } else {
+          ++nZero[k];
+        }
+      }
+    }
+  }
+  // ---- flush: the lane that owns a mass adds its sums; geometric exits are the same for every mass
+  for (int o = 16; o > 0; o >>= 1) nIter += __shfl_down_sync(kFull, nIter, o);
+  nIter = __shfl_sync(kFull, nIter, 0);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int m = lane + 32 * k;
+    if (m >= nMasses) continue;
+    sart_counters_t* c = counters + m;
+    auto addu = [](uint64_t* p, unsigned long long v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), v); };
+    addu(&c->n_rays, nIter);
+    addu(&c->n_exit[SART_EXIT_PASSED], nPassed[k]);
+    addu(&c->n_exit[SART_EXIT_ZERO_WEIGHT], nZero[k]);
+    addu(&c->n_passed, nPassed[k]);
+    addu(&c->n_passed_till_window, nTill[k]);
+    for (int e = 1; e < SART_N_EXIT_CODES; ++e)
+      if (e != SART_EXIT_ZERO_WEIGHT) addu(&c->n_exit[e], wc[warp].n_exit[e]);
+    addu(&c->n_hit_nickel, wc[warp].n_exit[SART_EXIT_NICKEL]);
+    addu(&c->n_interp_clamped, wc[warp].n_clamped);
+    atomicAdd(&c->sum_w, sumW[k]); atomicAdd(&c->sum_w2, sumW2[k]);
+    atomicAdd(&c->sum_x, sumX[k]); atomicAdd(&c->sum_y, sumY[k]); atomicAdd(&c->sum_r, sumR[k]);
+  }
+}
+
 // ---- per-ray records (traceAxionWrapper in fast mode) ----------------------------------------------------------
 template <bool kWolter>
 __global__ void __launch_bounds__(kBlock, 2)
@@ -606,10 +740,15 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
     RayResult r;
-    trace_one<kWolter>(P, T, S, seed, first + i, mAxion2, r);
-    ox[i] = r.x; oy[i] = r.y; ow[i] = r.w; ocode[i] = r.code; oshell[i] = r.shell;
+    trace_one<kWolter, true>(P, T, S, seed, first + i, mAxion2, r);
+    int code = r.code;
+    double wd = 0.0;
+    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
+    else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
+    const bool tail = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
+    ox[i] = tail ? r.x : 0.0; oy[i] = tail ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tail ? r.shell : -1;
     if (oenergy) oenergy[i] = double(r.energy);
-    if (orad) orad[i] = r.r;
+    if (orad) orad[i] = tail ? r.r : 0.0;
   }
 }
 
@@ -637,6 +776,27 @@ cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTabl
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
   kern<<<grid, fast::kBlock, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_image_fast_masses(const fast::FastParams& P, const fast::FastTables& T, int nMasses,
+                                        const double* dMasses, uint64_t first, uint64_t nRays, uint64_t seed,
+                                        double* image, double* imageW2, sart_counters_t* counters, int smCount,
+                                        cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes(P);
+  auto kern = wolter ? fast::k_trace_mc_fast_masses<true> : fast::k_trace_mc_fast_masses<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int perSM = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * perSM;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, T, dMasses, nMasses, first, nRays, seed, image, imageW2, counters);
   return cudaGetLastError();
 }
 

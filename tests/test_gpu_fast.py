@@ -143,3 +143,33 @@ def test_fast_rejects_unsupported(rt):
             tr.set_precision(1)
         tr.trace_mc(10_000, 1)      # the exact pipeline handles it
         assert tr.read_image().counters[0]["n_rays"] == 10_000
+
+
+def test_fast_mass_scan_vs_exact(rt):
+    """BASELINE config 4: buffer-gas stage, many axion masses sharing one traced ray (lanes = masses in fast mode)."""
+    setup, tb = make_config("babyiaxo_gas")
+    n = 400_000
+    # m_gamma of the reference's (bar-as-mbar) pressure is ~8e-3 eV; scan around it and far above it
+    masses = np.concatenate([np.linspace(0.004, 0.012, 40), np.linspace(0.02, 0.4, 24)])
+    assert masses.size == 64
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_axion_masses(masses)
+        tr.trace_mc(n, 3)
+        e = tr.read_image()
+        tr.set_precision(1)
+        tr.reset_image()
+        tr.trace_mc(n, 3)
+        f = tr.read_image()
+    assert f.image.shape == (64, 256, 256)
+    for m in range(64):
+        ce, cf = e.counters[m], f.counters[m]
+        assert cf["n_rays"] == n
+        assert abs(cf["n_passed"] - ce["n_passed"]) <= 20, m
+        assert abs(cf["n_passed_till_window"] - ce["n_passed_till_window"]) <= 20
+        for k, v in ce["n_exit"].items():
+            assert abs(cf["n_exit"][k] - v) <= 20, (m, k)
+        assert abs(cf["sum_w"] / ce["sum_w"] - 1.0) < 2e-3, (m, cf["sum_w"], ce["sum_w"])
+        assert abs(f.image[m].sum() / cf["sum_w"] - 1.0) < 1e-9
+    sw = np.array([c["sum_w"] for c in f.counters])
+    assert sw.max() / sw.min() > 3.0     # the resonance at m_a = m_gamma is resolved
+    assert np.argmax(sw) < 40            # ... and lies in the fine part of the scan
