@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-presampled", action="store_true", help="skip the tier-(a) pre-sampled kernel measurement")
     return ap.parse_args()
 
 
@@ -175,6 +176,85 @@ class ClockSampler:
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def presampled_leg(tr, torch, device, n_unique: int = 1 << 20, repeat: int = 16):
+    """Tier-(a) kernel (k_trace_presampled, exact FP64 mode): SoA rays in HBM -> SoA records in HBM, 80 B/ray
+    (48 in: origin xyz, exit xy, energy; 32 out: x, y, w f64 + code, shell i32), plus the same through host buffers.
+    Inputs are real Philox rays of the workload (sampled once through the C-ABI), tiled `repeat` times on the device."""
+    import numpy as np
+    from solaraxionraytracing_b200 import abi
+    # sample inputs with the product itself: trace n_unique MC rays and keep... the C-ABI returns no emission points,
+    # so draw them from the same distributions on the host (uniform disc; solar shell radius from the radius CDF)
+    rng = np.random.default_rng(12345)
+    tb = tr.fullSetup.tables
+    s = tr.fullSetup.expSetup
+    ridx = np.searchsorted(tb.fluxRadiusCDF, rng.random(n_unique), side="left")
+    r = (0.0015 + 0.0005 * ridx) * s.consts.radiusSun
+    a1, a2 = 2 * np.pi * rng.random(n_unique), np.pi * rng.random(n_unique)
+    origin = np.stack([np.cos(a1) * np.sin(a2) * r, np.sin(a1) * np.sin(a2) * r, np.cos(a2) * r - s.consts.distanceSunEarth])
+    rd, ad = s.magnet.radiusCB * np.sqrt(rng.random(n_unique)), 2 * np.pi * rng.random(n_unique)
+    exit_xy = np.stack([np.cos(ad) * rd, np.sin(ad) * rd])
+    eidx = np.array([np.searchsorted(tb.diffFluxCDFs[i], u) for i, u in zip(ridx[:4096], rng.random(4096))])
+    energy = np.maximum(0.03, tb.energies[np.minimum(eidx, tb.energies.size - 1)])
+    energy = np.resize(energy, n_unique)
+    n = n_unique * repeat
+    dev = f"cuda:{device}"
+    d_o = torch.from_numpy(np.ascontiguousarray(origin)).to(dev).repeat(1, repeat).contiguous()
+    d_e = torch.from_numpy(np.ascontiguousarray(exit_xy)).to(dev).repeat(1, repeat).contiguous()
+    d_en = torch.from_numpy(energy).to(dev).repeat(repeat).contiguous()
+    ox, oy, ow = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    oc, osh = (torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2))
+    ro = abi.RayOut()
+    import ctypes as C
+    ro.x, ro.y, ro.w = (C.cast(t.data_ptr(), abi.c_double_p) for t in (ox, oy, ow))
+    ro.code, ro.shell = (C.cast(t.data_ptr(), abi.c_int32_p) for t in (oc, osh))
+    tr.set_precision(0)
+    stream = torch.cuda.ExternalStream(tr.stream, device=device)
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            tr.trace_presampled_dev(n, d_o.data_ptr(), d_e.data_ptr(), d_en.data_ptr(), ro)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        reps = 3
+        for _ in range(reps):
+            tr.trace_presampled_dev(n, d_o.data_ptr(), d_e.data_ptr(), d_en.data_ptr(), ro)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    passed = float((oc.bitwise_and(0xff) == 0).double().mean().item())
+    # end to end with host (pinned) buffers through sart_trace_presampled
+    h_o = torch.from_numpy(np.ascontiguousarray(origin)).pin_memory()
+    h_e = torch.from_numpy(np.ascontiguousarray(exit_xy)).pin_memory()
+    h_en = torch.from_numpy(energy).pin_memory()
+    hx, hy, hw = (torch.empty(n_unique, dtype=torch.float64).pin_memory() for _ in range(3))
+    hc, hs = (torch.empty(n_unique, dtype=torch.int32).pin_memory() for _ in range(2))
+    hro = abi.RayOut()
+    hro.x, hro.y, hro.w = (C.cast(t.data_ptr(), abi.c_double_p) for t in (hx, hy, hw))
+    hro.code, hro.shell = (C.cast(t.data_ptr(), abi.c_int32_p) for t in (hc, hs))
+    from solaraxionraytracing_b200._lib import check, lib
+    call = lambda: check(lib.sart_trace_presampled(tr._h, n_unique, C.cast(h_o.data_ptr(), abi.c_double_p),
+                                                   C.cast(h_e.data_ptr(), abi.c_double_p),
+                                                   C.cast(h_en.data_ptr(), abi.c_double_p), C.byref(hro)))
+    call()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        call()
+    e2e = 3 * n_unique / (time.perf_counter() - t0)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    rate = n / (ms * 1e-3)
+    return {"kernel": "k_trace_presampled (exact FP64)", "rays": n, "rays_per_s": rate, "passed_fraction": passed,
+            "bytes_per_ray": 80, "e2e_rays_per_s": e2e, "e2e_h2d_bytes": 48 * n_unique, "e2e_d2h_bytes": 32 * n_unique,
+            "roofline": {"bound": "hbm", "achieved": rate * 80 / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": rate * 80 / 1e9 / hbm,
+                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         "note": "FP64 libm per ray makes this kernel compute-bound; the HBM figure is its ceiling"}}
 
 
 def run_ours(args):
@@ -311,6 +391,8 @@ def run_ours(args):
                          "peak_source": "sart_measure_fma_peak in this run (MEASURED_PEAKS.json has no CUDA-core "
                                         "figure); the kernel moves ~0 HBM bytes per ray"},
         }
+        if n_gpus == 1 and not args.no_presampled:
+            out["presampled"] = presampled_leg(tr, torch, local)
         if n_gpus == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_leg(args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
