@@ -1,0 +1,112 @@
+"""BASELINE-size runs checked through size-independent properties (the oracle cannot follow at 1e9 rays):
+ray conservation over exit codes, image mass == counter sums, split/merge invariance (Philox is keyed on the global
+ray index), linearity of the weight in the exposure factor, flag monotonicity."""
+import numpy as np
+import pytest
+
+from solaraxionraytracing_b200 import abi
+
+pytestmark = pytest.mark.gpu
+SEED = 299792458
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from solaraxionraytracing_b200 import raytracer
+    if raytracer.lib.sart_device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests need a B200")
+    return raytracer
+
+
+@pytest.fixture(scope="module")
+def full_llnl(rt):
+    """BASELINE config 1/3 at full table sizes (1968x1500 solar model, 4x1000x1000 reflectivity)."""
+    return rt.initFullSetup("CAST", "InGrid2018", "vacuum", "LLNL")
+
+
+def _check_conservation(res, n):
+    c = res.counters[0]
+    assert c["n_rays"] == n
+    assert sum(c["n_exit"].values()) == n                      # every ray leaves through exactly one exit
+    assert c["n_passed"] == c["n_exit"]["passed"] and c["n_hit_nickel"] == c["n_exit"]["nickel"]
+    assert c["n_passed_till_window"] >= c["n_passed"]
+    assert c["n_passed_till_window"] <= c["n_passed"] + c["n_exit"]["window_aperture"] + c["n_exit"]["zero_weight"]
+    assert res.image.sum() == pytest.approx(c["sum_w"], rel=1e-9)      # checksum of checksums
+    assert res.image_w2.sum() == pytest.approx(c["sum_w2"], rel=1e-9)
+    assert np.all(res.image >= 0) and np.all(res.image_w2 >= 0)
+    assert c["n_interp_clamped"] == 0
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_config3_1e9_rays(rt, full_llnl, precision):
+    n = 1_000_000_000 if precision == 1 else 200_000_000
+    with rt.RayTracer(full_llnl) as tr:
+        tr.set_precision(precision)
+        tr.trace_mc(n, SEED)
+        one = tr.read_image()
+        _check_conservation(one, n)
+        # split into 3 uneven launches with ray offsets: identical counters, image equal up to f64 summation order
+        tr.reset_image()
+        cuts = [0, n // 7, n // 2 + 12345, n]
+        for a, b in zip(cuts, cuts[1:]):
+            tr.trace_mc(b - a, SEED, first_ray=a)
+        three = tr.read_image()
+    c1, c3 = one.counters[0], three.counters[0]
+    assert c1["n_exit"] == c3["n_exit"] and c1["n_passed_till_window"] == c3["n_passed_till_window"]
+    assert np.allclose(one.image, three.image, rtol=1e-9, atol=0)
+    assert c1["sum_w"] == pytest.approx(c3["sum_w"], rel=1e-12)
+    # physics sanity at scale: the focal spot is inside the 7 mm window and most rays pass
+    assert 0.80 < c1["n_passed"] / n < 0.90
+    assert c1["sum_r"] / c1["n_passed"] < 3.0
+
+
+def test_config5_babyiaxo_xmm_4e9_rays(rt):
+    """config_default.toml as shipped (BabyIAXO / InGridIAXO / vacuum / XMM) at the per-GPU share of 1e11/8 rays is
+    1.25e10; 4e9 here keeps the test short. Ray indices beyond 2^32 exercise the 64-bit Philox counter."""
+    fs = rt.initFullSetup("BabyIAXO", "InGridIAXO", "vacuum", "XMM")
+    n = 4_000_000_000
+    with rt.RayTracer(fs) as tr:
+        tr.set_precision(1)
+        tr.trace_mc(n, 4, first_ray=3_000_000_000)     # crosses 2^32
+        res = tr.read_image()
+        _check_conservation(res, n)
+        c = res.counters[0]
+        assert 0.20 < c["n_passed"] / n < 0.27
+        assert c["n_exit"]["clip_pipe_vt3"] / n == pytest.approx(0.4526, abs=2e-3)   # bore 500 mm vs pipe 370 mm
+        # rays [2^32 - 1000, 2^32 + 1000) traced alone equal the same index range of the exact pipeline's counters
+        tr.reset_image()
+        tr.trace_mc(2000, 4, first_ray=2**32 - 1000)
+        f = tr.read_image().counters[0]
+        tr.set_precision(0); tr.reset_image()
+        tr.trace_mc(2000, 4, first_ray=2**32 - 1000)
+        e = tr.read_image().counters[0]
+    assert f["n_exit"] == e["n_exit"]
+
+
+def test_weight_linear_in_exposure_and_flags(rt, full_llnl):
+    n = 5_000_000
+    import ctypes as C
+
+    def run(setup):
+        with rt.RayTracer(rt.FullRaytraceSetup(setup, full_llnl.tables)) as tr:
+            tr.set_precision(1)
+            tr.trace_mc(n, 11)
+            return tr.read_image()
+
+    base = run(full_llnl.expSetup)
+    s2 = type(full_llnl.expSetup).from_buffer_copy(full_llnl.expSetup)
+    s2.consts.exposureFactor *= 4.0
+    scaled = run(s2)
+    assert scaled.counters[0]["n_exit"] == base.counters[0]["n_exit"]
+    assert np.allclose(scaled.image, 4.0 * base.image, rtol=1e-12)
+    # dropping a transmission factor can only increase every weight (all factors are in [0, 1])
+    s3 = type(full_llnl.expSetup).from_buffer_copy(full_llnl.expSetup)
+    s3.flags |= abi.CF_IGNORE_GAS_ABS
+    nogas = run(s3)
+    assert np.all(nogas.image >= base.image * (1 - 1e-12))
+    assert nogas.counters[0]["n_passed"] >= base.counters[0]["n_passed"]
+    s4 = type(full_llnl.expSetup).from_buffer_copy(full_llnl.expSetup)
+    s4.flags |= abi.CF_IGNORE_DET_WINDOW
+    nowin = run(s4)
+    assert nowin.counters[0]["n_passed"] >= base.counters[0]["n_passed"]
+    assert nowin.counters[0]["sum_w"] > base.counters[0]["sum_w"]
