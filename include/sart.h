@@ -243,6 +243,10 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup);
 int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV);
 /* 0 = "exact" FP64 pipeline (bit-faithful classification), 1 = "fast" mixed FP32 pipeline. */
 int sart_set_precision(sart_handle_t* h, int mode);
+/* Fast mode only: 1 = compact the rays that survive bore, pipes, vetoes and glass fronts into full warps before the
+ * mirror stage (pays off when most rays are clipped, e.g. BabyIAXO + XMM); 0 = one ray per lane throughout. Results are
+ * identical ray by ray. Default: chosen at sart_create from the setup (on for XMM/Abrixas, off for LLNL). */
+int sart_set_compaction(sart_handle_t* h, int mode);
 int sart_has_precision(int mode); /* 1 if this build has the pipeline for `mode` */
 void* sart_stream(sart_handle_t* h); /* cudaStream_t the handle launches on */
 

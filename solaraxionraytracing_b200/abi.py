@@ -167,6 +167,7 @@ SIGNATURES = {
     "sart_set_axion_masses": (C.c_int, [H, C.c_int, c_double_p]),
     "sart_set_precision": (C.c_int, [H, C.c_int]),
     "sart_has_precision": (C.c_int, [C.c_int]),
+    "sart_set_compaction": (C.c_int, [H, C.c_int]),
     "sart_stream": (C.c_void_p, [H]),
     "sart_build_cdfs": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_double_p]),

@@ -22,7 +22,7 @@ cudaError_t launch_build_cdfs(int nR, int nE, const double* radii, const double*
 // ---- "fast" pipeline (kernels_fast.cu)
 cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
                                  uint64_t nRays, uint64_t seed, double* image, double* imageW2,
-                                 sart_counters_t* counters, int smCount, cudaStream_t s);
+                                 sart_counters_t* counters, int smCount, bool compact, cudaStream_t s);
 
 cudaError_t launch_mc_image_fast_masses(const fast::FastParams& P, const fast::FastTables& T, int nMasses,
                                         const double* dMasses, uint64_t first, uint64_t nRays, uint64_t seed,

@@ -193,14 +193,21 @@ __device__ __forceinline__ double conv_factor(const FastParams& P, float convVac
   const double term2 = rcp_nr(fma(q, q, 0.25 * g * g));
   return P.gasTerm1 * term2 * double(1.0f + gasE1 - 2.0f * gasE2 * cq);
 }
-// kFold: fold the conversion probability of the single axion mass m2 into wPre right away (fewer live values).
-template <bool kWolter, bool kFold>
-__device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const Smem& S,
-                                          uint64_t seed, uint64_t ray, double m2, RayResult& out) {
+// A ray that survived everything before the mirrors (stage A): what stage B needs to finish it. 48 bytes; this is
+// the record the compacting kernel queues in shared memory.
+struct Rec {
+  double x0, y0, tx, ty;   // pointEntranceXRT (telescope frame, z = 0) and slopes dx/dz, dy/dz
+  double path2;            // pathCB^2
+  int hitLayer, eIdx;
+  bool clamped;
+};
+
+// Stage A of traceAxion: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
+// Returns the exit code of an early return, or -1 with `rec` filled.
+template <bool kWolter>
+__device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T, const Smem& S, uint64_t seed,
+                                       uint64_t ray, Rec& rec) {
   const ShellFast* __restrict__ sShell = S.shell;
-  out.bin = -1; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
-  out.windowMiss = false; out.clamped = false; out.wPre = 0.0; out.wPost = 0.0;
-  out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
   uint32_t w[6];
   ray_words(seed, ray, w);
   constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
@@ -209,8 +216,8 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   // ================= sampling rt:1754-1764 (or the X-ray test source rt:1765-1801)
   double ex, ey, sx, sy;   // point on the exit disc of the field (z = lengthB) and slopes
   int eIdx;
-  // energy search state: the guide entry is loaded here, the CDF window after the clip tests, the LUT record after
-  // mirror 1 — the dependent global loads overlap the geometry instead of stalling in a row
+  // energy search state: the guide entry is loaded here, the CDF window after the clip tests and the index is resolved
+  // at the end of the stage — the dependent global loads overlap the geometry instead of stalling in a row
   int eLo = 0, eHi = 0;
   double ue = 0.0;
   const double* eRow = nullptr;
@@ -263,7 +270,7 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     // collimator rt:1800: point at z = colZ relative to the source centre
     const double qx = fma(sx, P.colDz, Ox) - P.srcX, qy = fma(sy, P.colDz, Oy) - P.srcY;
     eIdx = P.srcEIdx;
-    if (!(qx * qx + qy * qy < P.srcRadius2)) { out.code = SART_EXIT_COLLIMATOR; return; }
+    if (!(qx * qx + qy * qy < P.srcRadius2)) return SART_EXIT_COLLIMATOR;
   }
 
   // ================= bore and pipes rt:1813-1872: points of the line at the clip planes
@@ -272,7 +279,7 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   const bool hitEntrance = fma(p0x, p0x, p0y * p0y) < P.radiusCB2;
   const double pex = fma(sx, P.dzExitCB, ex), pey = fma(sy, P.dzExitCB, ey);
   const bool insideExit = fma(pex, pex, pey * pey) < P.radiusCB2;
-  if (!insideExit) { out.code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE; return; }
+  if (!insideExit) return hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
   // (a ray that misses the entrance disc but is inside at the exit entered through the wall exactly once)
   double path2;  // pathCB^2 rt:1843
   if (hitEntrance) {
@@ -287,10 +294,10 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   }
   {
     const double qx = fma(sx, P.dzPipe1, ex), qy = fma(sy, P.dzPipe1, ey);
-    if (!(fma(qx, qx, qy * qy) < P.rPipe12)) { out.code = SART_EXIT_CLIP_PIPE_VT3; return; }
+    if (!(fma(qx, qx, qy * qy) < P.rPipe12)) return SART_EXIT_CLIP_PIPE_VT3;
   }
   double x0 = fma(sx, P.dzPipe2, ex), y0 = fma(sy, P.dzPipe2, ey);
-  if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) { out.code = SART_EXIT_CLIP_PIPE_XRT; return; }  // quirk Q2
+  if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) return SART_EXIT_CLIP_PIPE_XRT;  // quirk Q2
   // energy CDF window: two 16-byte loads starting at the aligned entry at or below eLo (windows are 1-2 entries wide)
   double2 ecA = make_double2(2.0, 2.0), ecB = make_double2(2.0, 2.0);
   int e0 = 0;
@@ -323,8 +330,6 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   const double rho0sq = fma(x0, x0, y0 * y0);
   const double invRho0 = rsqrt_nr(rho0sq);
   const double radialDist = rho0sq * invRho0;
-  const double t2sum = fma(tx, tx, ty * ty);
-  const double invLen = rsqrt_nr(1.0 + t2sum);
 
   // ================= opaque structures rt:1635-1704
   if (kWolter) {
@@ -351,23 +356,53 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
         hit = (a <= 3.75f) || (b <= 3.75f);
       }
     }
-    if (hit) { out.code = SART_EXIT_OPAQUE; return; }
+    if (hit) return SART_EXIT_OPAQUE;
   }
 
   // ================= shell rt:1932-1957: uniform radial guide + at most one forward step
   const int nS = P.nShells;
-  if (radialDist > sShell[nS - 1].R1) { out.code = SART_EXIT_OUTSIDE_SHELLS; return; }
+  if (radialDist > sShell[nS - 1].R1) return SART_EXIT_OUTSIDE_SHELLS;
   int hitLayer;
   {
     int b = int((radialDist - P.shellRhoMin) * P.shellInvStep);
     b = b < 0 ? 0 : (b > P.nShellGuide - 1 ? P.nShellGuide - 1 : b);
     hitLayer = S.shellGuide[b];
     while (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;   // first j with R1[j] > radialDist
-    if (!(sShell[hitLayer].R1 > radialDist)) { out.code = SART_EXIT_NO_MIRROR_HIT; return; }  // == R1[last]
+    if (!(sShell[hitLayer].R1 > radialDist)) return SART_EXIT_NO_MIRROR_HIT;  // == R1[last]
     if (hitLayer > 0 && radialDist < sShell[hitLayer - 1].R1pT) {   // R1[j-1] < radialDist holds by construction
-      if (radialDist > sShell[hitLayer - 1].R1) { out.code = SART_EXIT_GLASS_FRONT; return; }
+      if (radialDist > sShell[hitLayer - 1].R1) return SART_EXIT_GLASS_FRONT;
     }
   }
+  // energy index from the CDF window loaded above
+  if (eRow) {
+    const int cnt = int(e0 >= eLo && e0 < eHi && ecA.x < ue) + int(e0 + 1 < eHi && ecA.y < ue) +
+                    int(e0 + 2 < eHi && ecB.x < ue) + int(e0 + 3 < eHi && ecB.y < ue);
+    eIdx = eLo + cnt;
+    if (eIdx == e0 + 4 && e0 + 4 < eHi) eIdx = lower_bound_window(eRow, e0 + 4, eHi, ue);
+    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
+  }
+  rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.path2 = path2;
+  rec.hitLayer = hitLayer; rec.eIdx = eIdx; rec.clamped = clamped;
+  return -1;
+}
+
+// Stage B: the two reflections, nickel / degenerate exits, detector plane, weights, window (rt:1971-2221).
+// kFold: fold the conversion probability of the single axion mass m2 into wPre right away (fewer live values).
+template <bool kWolter, bool kFold>
+__device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T, const Smem& S, const Rec& rec,
+                                        double m2, RayResult& out) {
+  const ShellFast* __restrict__ sShell = S.shell;
+  out.bin = -1; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
+  out.windowMiss = false; out.clamped = false; out.wPre = 0.0; out.wPost = 0.0;
+  out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
+  const double x0 = rec.x0, y0 = rec.y0, tx = rec.tx, ty = rec.ty, path2 = rec.path2;
+  const int hitLayer = rec.hitLayer, eIdx = rec.eIdx;
+  bool clamped = rec.clamped;
+  const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);   // needed at the weight stage
+  const EnergyLUT el = {elv.x, elv.y, elv.z, elv.w};
+  const double rho0sq = fma(x0, x0, y0 * y0);
+  const double t2sum = fma(tx, tx, ty * ty);
+  const double invLen = rsqrt_nr(1.0 + t2sum);
   const ShellFast& sh = sShell[hitLayer];
   const double lM = P.lMirror;
   const double below = hitLayer > 0 ? sShell[hitLayer - 1].R1pT : 0.0;
@@ -401,16 +436,6 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
     out.code = code;
     return;
   }
-  // energy index from the CDF window loaded above; its LUT record is needed only at the weight stage
-  if (eRow) {
-    const int cnt = int(e0 >= eLo && e0 < eHi && ecA.x < ue) + int(e0 + 1 < eHi && ecA.y < ue) +
-                    int(e0 + 2 < eHi && ecB.x < ue) + int(e0 + 3 < eHi && ecB.y < ue);
-    eIdx = eLo + cnt;
-    if (eIdx == e0 + 4 && e0 + 4 < eHi) eIdx = lower_bound_window(eRow, e0 + 4, eHi, ue);
-    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
-  }
-  const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);
-  const EnergyLUT el = {elv.x, elv.y, elv.z, elv.w};
   D3 pm = {fma(tx, z1, x0), fma(ty, z1, y0), z1};
   D3 v = {tx * invLen, ty * invLen, invLen};
   double sinA1;
@@ -540,6 +565,19 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   if (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) out.bin = cy * SART_IMAGE_BINS + cx;
 }
 
+template <bool kWolter, bool kFold>
+__device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const Smem& S, uint64_t seed,
+                                          uint64_t ray, double m2, RayResult& out) {
+  Rec rec;
+  const int code = stage_a<kWolter>(P, T, S, seed, ray, rec);
+  if (code >= 0) {
+    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1; out.energy = 0.f;
+    out.x = out.y = out.r = 0.0;
+    return;
+  }
+  stage_b<kWolter, kFold>(P, T, S, rec, m2, out);
+}
+
 // Tail of traceAxion for one axion mass: exit code | flags and the final weight.
 template <bool kFolded>
 __device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& r, double m2, double& w) {
@@ -616,6 +654,115 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
     if (wc[warp].n_exit[SART_EXIT_NICKEL])
       atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_hit_nickel), (unsigned long long)wc[warp].n_exit[SART_EXIT_NICKEL]);
     if (wc[warp].n_clamped) atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_interp_clamped), (unsigned long long)wc[warp].n_clamped);
+    atomicAdd(&c->sum_w, sumW); atomicAdd(&c->sum_w2, sumW2);
+    atomicAdd(&c->sum_x, sumX); atomicAdd(&c->sum_y, sumY); atomicAdd(&c->sum_r, sumR);
+  }
+}
+
+// ---- fused kernel with warp-level compaction ------------------------------------------------------------------
+// Stage A (sample, clip, frame, vetoes, shell) runs on 32 fresh rays per warp; the survivors are ballot-compacted into
+// a per-warp shared-memory queue, and stage B (mirrors .. histogram) runs only on full batches of 32 queued rays, so
+// its lanes stay busy whatever fraction of the rays the bore, pipes, spider and glass fronts remove (BabyIAXO + XMM:
+// 2/3 of the launched rays never reach a mirror). Same arithmetic per ray as k_trace_mc_fast.
+constexpr int kQueue = 64;
+struct WarpQueue {
+  double x0[kQueue], y0[kQueue], tx[kQueue], ty[kQueue], path2[kQueue];
+  int meta[kQueue];   // hitLayer | eIdx << 8 | clamped << 30
+};
+
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, SART_FAST_MINBLOCKS)
+k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
+                        uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
+                        double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem S;
+  unsigned char* tail;
+  smem_layout(P, smem, S, tail);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
+  WarpQueue* queues = reinterpret_cast<WarpQueue*>(tail + kWarps * sizeof(WarpCounters));
+  smem_fill(P, T, S);
+  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  __syncthreads();
+
+  constexpr unsigned kFull = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpQueue& Q = queues[warp];
+  unsigned int nPassed = 0, nTill = 0, nIter = 0;
+  double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  uint64_t base = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31);   // warp-uniform
+  int qn = 0;                                                              // warp-uniform queue fill
+  for (;;) {
+    while (qn <= kQueue - 32 && base < nRays) {
+      const uint64_t i = base + lane;
+      base += stride;
+      Rec rec;
+      int code = SART_N_EXIT_CODES;
+      if (i < nRays) {
+        code = stage_a<kWolter>(P, T, S, seed, first + i, rec);
+        ++nIter;
+        if (code >= 0) atomicAdd(&wc[warp].n_exit[code], 1u);
+      }
+      const unsigned m = __ballot_sync(kFull, code < 0);
+      if (code < 0) {
+        const int pos = qn + __popc(m & ((1u << lane) - 1u));
+        Q.x0[pos] = rec.x0; Q.y0[pos] = rec.y0; Q.tx[pos] = rec.tx; Q.ty[pos] = rec.ty; Q.path2[pos] = rec.path2;
+        Q.meta[pos] = rec.hitLayer | (rec.eIdx << 8) | (rec.clamped ? (1 << 30) : 0);
+      }
+      qn += __popc(m);
+    }
+    if (qn == 0) break;
+    __syncwarp();
+    const int take = qn < 32 ? qn : 32;
+    if (lane < take) {
+      const int pos = qn - take + lane;
+      Rec rec;
+      rec.x0 = Q.x0[pos]; rec.y0 = Q.y0[pos]; rec.tx = Q.tx[pos]; rec.ty = Q.ty[pos]; rec.path2 = Q.path2[pos];
+      const int meta = Q.meta[pos];
+      rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
+      RayResult r;
+      stage_b<kWolter, true>(P, T, S, rec, mAxion2, r);
+      int code = r.code;
+      double wd = 0.0;
+      if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
+      if (code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
+      if ((code & SART_CODE_MASK) == SART_EXIT_PASSED) {
+        ++nPassed;
+        sumW += wd; sumW2 += wd * wd; sumX += r.x; sumY += r.y; sumR += r.r;
+        if (r.bin >= 0) {
+          atomicAdd(image + r.bin, wd);
+          atomicAdd(imageW2 + r.bin, wd * wd);
+        }
+      } else {
+        atomicAdd(&wc[warp].n_exit[code & SART_CODE_MASK], 1u);
+      }
+      if (code & SART_FLAG_INTERP_CLAMPED) atomicAdd(&wc[warp].n_clamped, 1u);
+    }
+    qn -= take;
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nPassed += __shfl_down_sync(kFull, nPassed, o);
+    nTill += __shfl_down_sync(kFull, nTill, o);
+    nIter += __shfl_down_sync(kFull, nIter, o);
+    sumW += __shfl_down_sync(kFull, sumW, o);
+    sumW2 += __shfl_down_sync(kFull, sumW2, o);
+    sumX += __shfl_down_sync(kFull, sumX, o);
+    sumY += __shfl_down_sync(kFull, sumY, o);
+    sumR += __shfl_down_sync(kFull, sumR, o);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    sart_counters_t* c = counters;
+    auto addu = [](uint64_t* p, unsigned long long v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), v); };
+    addu(&c->n_rays, nIter);
+    addu(&c->n_exit[SART_EXIT_PASSED], nPassed);
+    addu(&c->n_passed, nPassed);
+    addu(&c->n_passed_till_window, nTill);
+    for (int e = 1; e < SART_N_EXIT_CODES; ++e) addu(&c->n_exit[e], wc[warp].n_exit[e]);
+    addu(&c->n_hit_nickel, wc[warp].n_exit[SART_EXIT_NICKEL]);
+    addu(&c->n_interp_clamped, wc[warp].n_clamped);
     atomicAdd(&c->sum_w, sumW); atomicAdd(&c->sum_w2, sumW2);
     atomicAdd(&c->sum_x, sumX); atomicAdd(&c->sum_y, sumY); atomicAdd(&c->sum_r, sumR);
   }
@@ -761,11 +908,12 @@ size_t smem_bytes(const FastParams& P) {
 
 cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTables& T, double mAxion, uint64_t first,
                                  uint64_t nRays, uint64_t seed, double* image, double* imageW2,
-                                 sart_counters_t* counters, int smCount, cudaStream_t s) {
+                                 sart_counters_t* counters, int smCount, bool compact, cudaStream_t s) {
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
-  const size_t smem = fast::smem_bytes(P);
-  auto kern = wolter ? fast::k_trace_mc_fast<true> : fast::k_trace_mc_fast<false>;
+  const size_t smem = fast::smem_bytes(P) + (compact ? fast::kWarps * sizeof(fast::WarpQueue) : 0);
+  auto kern = compact ? (wolter ? fast::k_trace_mc_fast_compact<true> : fast::k_trace_mc_fast_compact<false>)
+                      : (wolter ? fast::k_trace_mc_fast<true> : fast::k_trace_mc_fast<false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int perSM = 0;

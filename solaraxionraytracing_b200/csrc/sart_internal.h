@@ -43,6 +43,8 @@ struct sart_handle {
   void* table_blob = nullptr;   // one allocation backing every table
   size_t table_bytes = 0;
   int precision = 0;            // 0 exact f64, 1 fast
+  int compact = 0;              // fast mode: warp-level compaction between the clip stages and the mirrors
+  double pilot_survival = 1.0;  // fraction of launched rays that reach the mirrors (pilot run at create)
   // "fast" pipeline: parameter block, LUTs and f32 reflectivity in a second allocation
   int fast_ok = 0;
   const char* fast_why = "";

@@ -172,6 +172,9 @@ class RayTracer:
     def set_precision(self, mode: int):
         check(lib.sart_set_precision(self._h, mode))
 
+    def set_compaction(self, mode: int):
+        check(lib.sart_set_compaction(self._h, mode))
+
     @property
     def n_masses(self) -> int:
         return lib.sart_image_len(self._h) // (abi.IMAGE_BINS * abi.IMAGE_BINS)

@@ -173,3 +173,24 @@ def test_fast_mass_scan_vs_exact(rt):
     sw = np.array([c["sum_w"] for c in f.counters])
     assert sw.max() / sw.min() > 3.0     # the resonance at m_a = m_gamma is resolved
     assert np.argmax(sw) < 40            # ... and lies in the fine part of the scan
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_compaction_is_result_neutral(rt, cfg):
+    """Warp compaction only re-packs surviving rays into full warps: counters identical, image equal up to f64
+    summation order."""
+    setup, tb = make_config(cfg)
+    n = 3_000_001   # not a multiple of the warp / block size: exercises the partial last batch
+    out = {}
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(1)
+        for mode in (0, 1):
+            tr.set_compaction(mode)
+            tr.reset_image()
+            tr.trace_mc(n, 99, first_ray=17)
+            out[mode] = tr.read_image()
+    a, b = out[0].counters[0], out[1].counters[0]
+    assert a["n_exit"] == b["n_exit"] and a["n_rays"] == b["n_rays"] == n
+    assert a["n_passed_till_window"] == b["n_passed_till_window"]
+    assert np.allclose(out[0].image, out[1].image, rtol=1e-10, atol=0)
+    assert a["sum_w"] == pytest.approx(b["sum_w"], rel=1e-12)
