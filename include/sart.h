@@ -256,6 +256,24 @@ void* sart_stream(sart_handle_t* h); /* cudaStream_t the handle launches on */
 int sart_build_cdfs(int device, int nRadii, int nEnergies, const double* radii, const double* energies,
                     const double* emRates, double* fluxRadiusCDF, double* diffFluxCDFs);
 
+/* ---- emission-rate table of the solar model (src/readOpacityFile.nim `calculateOpacities` :598-860, the
+ * opacity-free processes): emRates[nRadii][nEnergies] row-major, ready for sart_build_cdfs. temp_K, rho_gcm3 [nRadii]
+ * and massFractions [nRadii][29] are the AGSS09 columns Temp, Rho and H1..Ni in file order (readSolarModel.nim:3-7);
+ * radius i is 0.0015 + 0.0005 i solar radii (:793). `processes` is a SART_EM_* bit set; couplings as in the reference
+ * (g_ae = 1e-13, gagamma = 1e-12, ganuclei = 1e-15 at :641-645). FB/BB (term1 :369-371) and the transverse plasmon
+ * (:439-452) need the un-shipped OPCD opacities and are not produced. */
+enum {
+  SART_EM_PRIMAKOFF = 1u << 0,    /* primakoff      readOpacityFile.nim:384-413 */
+  SART_EM_COMPTON = 1u << 1,      /* comptonEmrate  :360-362 */
+  SART_EM_EE_BREMS = 1u << 2,     /* bremsEmrate    :364-367 (fNew :312-326) */
+  SART_EM_FREE_FREE = 1u << 3,    /* freefreeEmrate :378-381 */
+  SART_EM_IRON57 = 1u << 4,       /* iron           :454-466 */
+  SART_EM_LONG_PLASMON = 1u << 5  /* longPlasmon    :421-437 in the limit of zero opacity */
+};
+int sart_emission_rates(int device, int nRadii, const double* temp_K, const double* rho_gcm3,
+                        const double* massFractions, int nEnergies, const double* energies_keV, uint32_t processes,
+                        double g_ae, double gagamma, double ganuclei, double* emRates);
+
 /* ---- tier (a): trace pre-sampled rays. Replaces the body of traceAxion after the sampling block
  * (rt:1811-2221). origin_xyz = SoA [3][n] (rayOrigin), exit_xy = SoA [2][n] (pointExitCBMagneticField x,y;
  * z = lengthB), energy_keV [n]. Host buffers; copies are inside the call. */
@@ -284,6 +302,16 @@ size_t sart_image_len(sart_handle_t* h);        /* M*256*256 */
 /* Synchronise and copy out. image/image_w2 may be NULL. counters is [M]. */
 int sart_read_image(sart_handle_t* h, double* image, double* image_w2, sart_counters_t* counters);
 int sart_synchronize(sart_handle_t* h);
+
+/* ---- performAngularScan (rt:2778-2815): n_angles runs of n_rays_per_angle rays each, run i with
+ * telescope_turned_y = angles_deg[i] (rt:2794-2798) and everything else as in the handle's setup. All runs are
+ * queued on the handle's stream without host synchronisation (only the by-value parameter block changes between scan
+ * points); scan point i traces the global rays first_ray + [i*n, (i+1)*n), so a scan split over GPUs by blocks of scan
+ * points (first_ray = first point * n) traces the same rays as an unsplit one. fluxes[i] = sum of the weights of the passed rays
+ * (rt:2800, un-normalised; the reference then divides by the maximum, rt:2801-2802). counters [n_angles] and images
+ * [n_angles][256][256] are optional host arrays (NULL to skip). Leaves the handle's own setup and image untouched. */
+int sart_angular_scan(sart_handle_t* h, int n_angles, const double* angles_deg, uint64_t first_ray,
+                      uint64_t n_rays_per_angle, uint64_t seed, double* fluxes, sart_counters_t* counters, double* images);
 
 /* ---- prepareHeatmap (rt:818-842), general form, for per-ray records held by the host (e.g. the output of
  * sart_trace_mc_rays filtered by `passed`): result[floor((y-start_y)/dy)][floor((x-start_x)/dx)] += w/norm on the

@@ -18,9 +18,8 @@ LIB_PATH = HERE / "liboracle.so"
 
 
 def build(force: bool = False) -> Path:
-    src = HERE / "oracle.c"
-    hdr = HERE.parent / "include" / "sart.h"
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+    deps = [HERE / "oracle.c", HERE / "oracle_emission.c", HERE / "Makefile", HERE.parent / "include" / "sart.h"]
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(d.stat().st_mtime for d in deps):
         subprocess.run(["make", "-C", str(HERE), "-B", "liboracle.so"], check=True, capture_output=True)
     return LIB_PATH
 
@@ -55,6 +54,11 @@ def lib() -> C.CDLL:
             "oracle_axionConversionProb2": (C.c_double, [C.c_double] * 8),
             "oracle_intensitySuppression2": (C.c_double, [C.c_double] * 6),
             "oracle_conversionProb": (C.c_double, [S, C.c_double, C.c_double, C.c_double]),
+            "oracle_emission_rates": (C.c_int, [C.c_int, dp, dp, dp, C.c_int, dp, C.c_uint32, C.c_double, C.c_double,
+                                                C.c_double, dp]),
+            "oracle_fNew": (C.c_double, [C.c_double, C.c_double]),
+            "oracle_bfield": (C.c_double, [C.c_double]),
+            "oracle_primakoff": (C.c_double, [C.c_double] * 9),
             "oracle_num_threads": (C.c_int, []),
             "oracle_set_num_threads": (None, [C.c_int]),
         }
@@ -147,3 +151,14 @@ def ray_uniforms(seed: int, ray: int) -> np.ndarray:
     u = np.empty(6)
     lib().oracle_ray_uniforms(seed, ray, _dp(u))
     return u
+
+
+def emission_rates(temp, rho, frac, energies, processes: int, g_ae=1e-13, gagamma=1e-12, ganuclei=1e-15) -> np.ndarray:
+    """oracle_emission_rates (readOpacityFile.nim:598-860, opacity-free processes) -> emRates [nR, nE]."""
+    temp = np.ascontiguousarray(temp, dtype=np.float64); rho = np.ascontiguousarray(rho, dtype=np.float64)
+    frac = np.ascontiguousarray(frac, dtype=np.float64); energies = np.ascontiguousarray(energies, dtype=np.float64)
+    assert frac.shape == (temp.size, 29)
+    out = np.empty((temp.size, energies.size))
+    lib().oracle_emission_rates(temp.size, _dp(temp), _dp(rho), _dp(frac), energies.size, _dp(energies), processes,
+                                g_ae, gagamma, ganuclei, _dp(out))
+    return out

@@ -150,6 +150,10 @@ def struct_to_dict(s) -> dict:
     return out
 
 
+EM_PRIMAKOFF, EM_COMPTON, EM_EE_BREMS, EM_FREE_FREE, EM_IRON57, EM_LONG_PLASMON = (1 << i for i in range(6))
+EM_PROCESSES = {"primakoff": EM_PRIMAKOFF, "compton": EM_COMPTON, "ee_brems": EM_EE_BREMS, "free_free": EM_FREE_FREE,
+                "iron57": EM_IRON57, "long_plasmon": EM_LONG_PLASMON}
+
 # The exported symbols of libsart.so (every function include/sart.h declares) with their signatures.
 H = C.c_void_p
 SIGNATURES = {
@@ -171,6 +175,8 @@ SIGNATURES = {
     "sart_stream": (C.c_void_p, [H]),
     "sart_build_cdfs": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_double_p]),
+    "sart_emission_rates": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p,
+                                      C.c_uint32, C.c_double, C.c_double, C.c_double, c_double_p]),
     "sart_trace_presampled": (C.c_int, [H, C.c_size_t, c_double_p, c_double_p, c_double_p, C.POINTER(RayOut)]),
     "sart_trace_presampled_dev": (C.c_int, [H, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RayOut)]),
     "sart_trace_mc_rays": (C.c_int, [H, C.c_uint64, C.c_size_t, C.c_uint64, C.POINTER(RayOut)]),
@@ -182,6 +188,8 @@ SIGNATURES = {
     "sart_image_len": (C.c_size_t, [H]),
     "sart_read_image": (C.c_int, [H, c_double_p, c_double_p, C.POINTER(Counters)]),
     "sart_synchronize": (C.c_int, [H]),
+    "sart_angular_scan": (C.c_int, [H, C.c_int, c_double_p, C.c_uint64, C.c_uint64, C.c_uint64, c_double_p, C.POINTER(Counters),
+                                    c_double_p]),
     "sart_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
     "sart_prepare_heatmap": (C.c_int, [H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_size_t,
                                        c_double_p, c_double_p, c_double_p, C.c_double, c_double_p,

@@ -293,6 +293,17 @@ static int ensure_stage(sart_handle* h, size_t bytes) {
   return SART_OK;
 }
 
+// Parameter block of `s` for a live handle: setup-derived fields recomputed, table-derived fields kept.
+static void rederive_params(const sart_handle* h, const sart_setup_t& s, Params* p) {
+  const Params old = h->params;
+  derive_params(s, nullptr, p);
+  p->nAngles = old.nAngles; p->nReflEnergies = old.nReflEnergies;
+  p->angleMin = old.angleMin; p->angleMax = old.angleMax;
+  p->reflEMin = old.reflEMin; p->reflEMax = old.reflEMax;
+  p->reflDx = old.reflDx; p->reflDy = old.reflDy;
+  p->nRadii = old.nRadii; p->nEnergies = old.nEnergies;
+}
+
 }  // namespace sart
 
 using namespace sart;
@@ -366,15 +377,8 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
   int rc = validate(setup, nullptr);
   if (rc) return rc;
   DeviceGuard dg(h->device);
-  // keep the table-derived fields
-  Params old = h->params;
   h->setup = *setup;
-  derive_params(h->setup, nullptr, &h->params);
-  h->params.nAngles = old.nAngles; h->params.nReflEnergies = old.nReflEnergies;
-  h->params.angleMin = old.angleMin; h->params.angleMax = old.angleMax;
-  h->params.reflEMin = old.reflEMin; h->params.reflEMax = old.reflEMax;
-  h->params.reflDx = old.reflDx; h->params.reflDy = old.reflDy;
-  h->params.nRadii = old.nRadii; h->params.nEnergies = old.nEnergies;
+  rederive_params(h, h->setup, &h->params);
   std::vector<ShellF64> shells(SART_MAX_SHELLS);
   derive_shells(h->setup, shells.data());
   SART_CUDA(cudaStreamSynchronize(h->stream));
@@ -454,6 +458,39 @@ int sart_build_cdfs(int device, int nR, int nE, const double* radii, const doubl
   TRY(cudaMemcpy(fluxRadiusCDF, dRC, nR * sizeof(double), cudaMemcpyDeviceToHost));
 #undef TRY
   cudaFree(dR); cudaFree(dE); cudaFree(dEm); cudaFree(dTot); cudaFree(dC); cudaFree(dRC);
+  return rc;
+}
+
+int sart_emission_rates(int device, int nR, const double* temp, const double* rho, const double* frac, int nE,
+                        const double* energies, uint32_t processes, double g_ae, double gagamma, double ganuclei,
+                        double* emRates) {
+  if (nR < 1 || nE < 1 || !temp || !rho || !frac || !energies || !emRates) return fail(SART_ERR_ARG, "sart_emission_rates: bad argument");
+  if (processes == 0 || (processes >> 6)) return fail(SART_ERR_ARG, "sart_emission_rates: unknown process bits 0x%x", processes);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SART_ERR_CUDA, "no CUDA device available; libsart has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(SART_ERR_ARG, "device %d out of range", device);
+  DeviceGuard dg(device);
+  const size_t cells = size_t(nR) * nE;
+  double *dT = nullptr, *dRho = nullptr, *dF = nullptr, *dE = nullptr, *dEm = nullptr;
+  void* dSt = nullptr;
+  int rc = SART_OK;
+  cudaError_t e;
+#define TRY(call) if (rc == SART_OK && (e = (call)) != cudaSuccess) rc = cuda_fail(e, #call)
+  TRY(cudaMalloc(&dT, nR * sizeof(double)));
+  TRY(cudaMalloc(&dRho, nR * sizeof(double)));
+  TRY(cudaMalloc(&dF, size_t(nR) * 29 * sizeof(double)));
+  TRY(cudaMalloc(&dE, nE * sizeof(double)));
+  TRY(cudaMalloc(&dEm, cells * sizeof(double)));
+  TRY(cudaMalloc(&dSt, size_t(nR) * 80));
+  TRY(cudaMemcpy(dT, temp, nR * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(dRho, rho, nR * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(dF, frac, size_t(nR) * 29 * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(dE, energies, nE * sizeof(double), cudaMemcpyHostToDevice));
+  TRY(launch_emission_rates(nR, nE, dT, dRho, dF, dE, processes, g_ae, gagamma, ganuclei, dSt, dEm, nullptr));
+  TRY(cudaDeviceSynchronize());
+  TRY(cudaMemcpy(emRates, dEm, cells * sizeof(double), cudaMemcpyDeviceToHost));
+#undef TRY
+  cudaFree(dT); cudaFree(dRho); cudaFree(dF); cudaFree(dE); cudaFree(dEm); cudaFree(dSt);
   return rc;
 }
 
@@ -627,6 +664,51 @@ int sart_prepare_heatmap(sart_handle_t* h, int rows, int cols, double start_x, d
   SART_CUDA(cudaMemcpyAsync(&bad, dBad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
   SART_CUDA(cudaStreamSynchronize(h->stream));
   if (n_out_of_range) *n_out_of_range = bad;
+  return SART_OK;
+}
+
+int sart_angular_scan(sart_handle_t* h, int n_angles, const double* angles_deg, uint64_t first_ray,
+                      uint64_t n_rays_per_angle, uint64_t seed, double* fluxes, sart_counters_t* counters, double* images) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (n_angles < 1 || !angles_deg || !fluxes) return fail(SART_ERR_ARG, "sart_angular_scan: bad argument");
+  if (h->n_masses != 1) return fail(SART_ERR_ARG, "sart_angular_scan: set a single axion mass");
+  DeviceGuard dg(h->device);
+  const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS;
+  const size_t imgBytes = align256(size_t(n_angles) * plane * sizeof(double));
+  const size_t bytes = 2 * imgBytes + align256(size_t(n_angles) * sizeof(sart_counters_t));
+  int rc = ensure_stage(h, bytes);
+  if (rc) return rc;
+  unsigned char* base = static_cast<unsigned char*>(h->d_stage);
+  double* dImg = reinterpret_cast<double*>(base);
+  double* dImg2 = reinterpret_cast<double*>(base + imgBytes);
+  sart_counters_t* dCnt = reinterpret_cast<sart_counters_t*>(base + 2 * imgBytes);
+  SART_CUDA(cudaMemsetAsync(base, 0, bytes, h->stream));
+  // One launch per scan point, queued back to back on the handle's stream: only the by-value parameter block differs
+  // (the rotation of the telescope frame), the tables and shell records in HBM are shared, nothing synchronises.
+  for (int i = 0; i < n_angles; ++i) {
+    sart_setup_t s = h->setup;
+    s.telescope.telescope_turned_y = angles_deg[i];   // rt:2796
+    Params P;
+    rederive_params(h, s, &P);
+    const uint64_t first = first_ray + uint64_t(i) * n_rays_per_angle;   // every scan point traces its own rays, like the reference
+    if (h->precision == 1) {
+      fast::FastParams F;
+      fast::derive_params(s, P, &F);
+      F.shellRhoMin = h->fparams.shellRhoMin; F.shellInvStep = h->fparams.shellInvStep; F.nShellGuide = h->fparams.nShellGuide;
+      SART_CUDA(launch_mc_image_fast(F, h->ftables, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
+                                     dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->compact != 0, h->stream));
+    } else {
+      SART_CUDA(launch_mc_image_exact(P, h->tables, 1, h->d_masses, first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
+                                      dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->stream));
+    }
+  }
+  std::vector<sart_counters_t> cnt;
+  cnt.resize(size_t(n_angles));
+  SART_CUDA(cudaMemcpyAsync(cnt.data(), dCnt, cnt.size() * sizeof(sart_counters_t), cudaMemcpyDeviceToHost, h->stream));
+  if (images) SART_CUDA(cudaMemcpyAsync(images, dImg, size_t(n_angles) * plane * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_angles; ++i) fluxes[i] = cnt[size_t(i)].sum_w;   // axions.filterIt(it.passed).mapIt(it.weights).sum() rt:2800
+  if (counters) std::memcpy(counters, cnt.data(), cnt.size() * sizeof(sart_counters_t));
   return SART_OK;
 }
 

@@ -74,6 +74,29 @@ def buildCdfs(emission: _tables.EmissionTable, device: int = 0):
     return rc, dc
 
 
+def calculateEmissionRates(solarModel: _tables.SolarModel | None = None, processes=("primakoff",), nElems: int = 1500,
+                           g_ae: float = 1e-13, gagamma: float = 1e-12, ganuclei: float = 1e-15,
+                           device: int = 0) -> _tables.EmissionTable:
+    """The opacity-free part of calculateOpacities (src/readOpacityFile.nim:598-860) on the GPU: emission rates on
+    energies = linspace(1e-3, 15, nElems) keV (:608-609) for every radius of the solar model. `processes` names
+    SART_EM_* terms ("primakoff", "compton", "ee_brems", "free_free", "iron57", "long_plasmon")."""
+    sm = solarModel or _tables.solar_model_packaged()
+    bits = 0
+    for p in processes:
+        if p not in abi.EM_PROCESSES:
+            raise ValueError(f"unknown emission process {p!r}; expected one of {sorted(abi.EM_PROCESSES)}")
+        bits |= abi.EM_PROCESSES[p]
+    energies = np.linspace(1e-3, 15.0, nElems)
+    T = np.ascontiguousarray(sm.temp_K, dtype=np.float64)
+    rho = np.ascontiguousarray(sm.rho_gcm3, dtype=np.float64)
+    fr = np.ascontiguousarray(sm.mass_fractions, dtype=np.float64)
+    em = np.empty((T.size, nElems))
+    check(lib.sart_emission_rates(device, T.size, _dp(T), _dp(rho), _dp(fr), nElems, _dp(energies), bits, g_ae, gagamma,
+                                  ganuclei, _dp(em)))
+    radii = 0.0015 + 0.0005 * np.arange(T.size)   # readOpacityFile.nim:793
+    return _tables.EmissionTable(radii=radii, energies=energies, emRates=em)
+
+
 @dataclass
 class FullRaytraceSetup:
     """FullRaytraceSetup (rt:232-242)."""
@@ -226,6 +249,17 @@ class RayTracer:
     def counters_dev(self) -> int:
         return lib.sart_counters_dev(self._h)
 
+    def angular_scan(self, angles_deg, n_rays_per_angle: int, seed: int = 299792458, want_images: bool = False,
+                     first_ray: int = 0):
+        """sart_angular_scan: (fluxes [n], counters [n dicts], images [n, 256, 256] or None)."""
+        a = np.ascontiguousarray(angles_deg, dtype=np.float64)
+        fl = np.empty(a.size)
+        cnt = (abi.Counters * a.size)()
+        img = np.empty((a.size, abi.IMAGE_BINS, abi.IMAGE_BINS)) if want_images else None
+        check(lib.sart_angular_scan(self._h, a.size, _dp(a), first_ray, n_rays_per_angle, seed, _dp(fl), cnt,
+                                    _dp(img) if want_images else None))
+        return fl, [c.as_dict() for c in cnt], img
+
     def read_image(self, want_w2: bool = True) -> RunResult:
         m = self.n_masses
         img = np.empty((m, abi.IMAGE_BINS, abi.IMAGE_BINS))
@@ -279,3 +313,31 @@ def prepareHeatmap(tracer: RayTracer, numberOfRows, numberOfColumns, start_x, st
     check(lib.sart_prepare_heatmap(tracer._h, numberOfRows, numberOfColumns, start_x, stop_x, start_y, stop_y, X.size,
                                    _dp(X), _dp(Y), _dp(W), norm, _dp(out), C.byref(bad)))
     return out, bad.value
+
+
+def performAngularScan(fullSetup: FullRaytraceSetup, angularScanMin: float, angularScanMax: float,
+                       numAngularScanPoints: int = 50, nRays: int = 1_000_000, seed: int = 299792458, device: int = 0,
+                       tracer: RayTracer | None = None, rank: int = 0, world: int = 1, group=None):
+    """performAngularScan (rt:2778-2815): relative flux versus telescope_turned_y. Returns (angles [deg],
+    relative flux = flux / max flux, absolute fluxes). With world > 1 the scan points are dealt to the
+    ranks in contiguous blocks (no exchange while tracing) and the per-point fluxes are summed over `group` at the end."""
+    from .multi_gpu import shard
+    angles = np.linspace(angularScanMin, angularScanMax, numAngularScanPoints)
+    lo, cnt = shard(numAngularScanPoints, rank, world)   # a contiguous block of scan points per rank
+    fluxes = np.zeros(numAngularScanPoints)
+    if cnt:
+        own = tracer is None
+        t = tracer or RayTracer(fullSetup, device)
+        try:
+            # scan point i always traces the global rays [i*nRays, (i+1)*nRays), whichever rank owns it
+            fluxes[lo:lo + cnt], _, _ = t.angular_scan(angles[lo:lo + cnt], nRays, seed, first_ray=lo * nRays)
+        finally:
+            if own:
+                t.close()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        tf = torch.from_numpy(fluxes)
+        dist.all_reduce(tf, op=dist.ReduceOp.SUM, group=group)
+        fluxes = tf.numpy()
+    return angles, fluxes / fluxes.max(), fluxes

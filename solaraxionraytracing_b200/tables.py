@@ -152,3 +152,48 @@ def synthetic_reflectivity(nCoatings: int = 4, nAngles: int = 1000, nEnergies: i
         bump = 0.35 * np.exp(-0.5 * ((ang - bragg_ang) / 0.035) ** 2) * (E > 4.0)
         out[c] = np.clip(ter * edge + bump * (1.0 - ter), 0.0, 1.0)
     return out
+
+
+def gold_reflectivity_packaged(nAngles: int = 1000, nEnergies: int = 1000, angleLim=(0.0, 1.5),
+                               energyLim=(0.03, 15.0)) -> np.ndarray:
+    """Gold (0.25 um) grazing-incidence reflectivity on the reference's grid, [1, nAngles, nEnergies].
+
+    The HDF5 the reference reads (rt:1196-1208, gold_0.25microns_reflectivities.h5) is not shipped; what the tree has
+    is the Henke download it was made from (resources/reflectivity.zip: 71 angles 0.13..0.83 deg x 500 energies
+    30..10000 eV), packed by tools/make_fixtures.py. It is resampled bilinearly (linear in angle and in energy) onto
+    the (0..1.5 deg) x (0.03..15 keV) grid of tools/download_henke_files.nim:258-262. Outside the tabulated range:
+    below 0.13 deg the reflectivity is continued linearly to R = 1 at grazing angle 0 (total external reflection),
+    above 0.83 deg and above 10 keV the edge value is kept."""
+    z = np.load(DATA_DIR / "gold_reflectivity_henke.npz")
+    a0, e0, R = z["angles_deg"].astype(np.float64), z["energies_eV"].astype(np.float64) / 1000.0, z["R"].astype(np.float64)
+    a0 = np.concatenate([[0.0], a0])
+    R = np.concatenate([np.ones((1, R.shape[1])), R], axis=0)
+    ang = np.linspace(angleLim[0], angleLim[1], nAngles)
+    en = np.linspace(energyLim[0], energyLim[1], nEnergies)
+    # energy axis first (np.interp clamps at the edges), then the angle axis
+    Re = np.stack([np.interp(en, e0, row) for row in R])                       # [72, nEnergies]
+    out = np.stack([np.interp(ang, a0, Re[:, j]) for j in range(nEnergies)], axis=1)   # [nAngles, nEnergies]
+    return np.ascontiguousarray(out[None, :, :])
+
+
+@dataclass
+class SolarModel:
+    """The AGSS09 columns the emission-rate generator reads (readSolarModel.nim:3-7; readOpacityFile.nim:659-700)."""
+    radius: np.ndarray          # [nR] fraction of the solar radius (0.0015 + 0.0005 i)
+    temp_K: np.ndarray          # [nR]
+    rho_gcm3: np.ndarray        # [nR]
+    mass_fractions: np.ndarray  # [nR, 29] H1, He4, He3, C12 ... Ni (file order)
+
+
+def read_solar_model(path: str | Path) -> SolarModel:
+    """readSolarModel (src/readSolarModel.nim:3-7) for AGSS09_solar_model_stripped.dat (35 columns, '#' header)."""
+    sm = np.loadtxt(path, comments="#")
+    if sm.ndim != 2 or sm.shape[1] != 35:
+        raise ValueError(f"{path}: expected 35 columns (Mass Radius Temp Rho Pres Lumi + 29 elements)")
+    return SolarModel(sm[:, 1].copy(), sm[:, 2].copy(), sm[:, 3].copy(), np.ascontiguousarray(sm[:, 6:35]))
+
+
+def solar_model_packaged() -> SolarModel:
+    """The same columns from the packaged copy (tools/make_fixtures.py; the GPU box has no /root/reference)."""
+    z = np.load(DATA_DIR / "agss09_solar_model.npz")
+    return SolarModel(z["radius"], z["temp_K"], z["rho_gcm3"], np.ascontiguousarray(z["mass_fractions"]))

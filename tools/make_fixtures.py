@@ -27,6 +27,14 @@ def main(ref: str = "/root/reference") -> None:
                         ga_E=t["gasAbsorption"][0], ga_A=t["gasAbsorption"][1])
     print("wrote", out / "detector_tables.npz")
 
+    # AGSS09 solar model (resources/AGSS09_solar_model_stripped.dat, read by readSolarModel.nim:3-7): the columns the
+    # emission-rate generator needs — Radius, Temp, Rho and the 29 mass fractions H1..Ni in file order.
+    sm = np.loadtxt(res / "AGSS09_solar_model_stripped.dat", comments="#")
+    assert sm.shape == (1968, 35)
+    np.savez_compressed(out / "agss09_solar_model.npz", radius=sm[:, 1], temp_K=sm[:, 2], rho_gcm3=sm[:, 3],
+                        mass_fractions=sm[:, 6:35])
+    print("wrote", out / "agss09_solar_model.npz")
+
     # Gold reflectivity (Henke, 0.25 um Au): 71 angle files x 500 energies inside resources/reflectivity.zip
     # (the HDF5 the reference reads, rt:1196-1208, is a missing blob). Packed as float32 [71, 500].
     zf = zipfile.ZipFile(res / "reflectivity.zip")
