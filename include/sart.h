@@ -294,6 +294,12 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
  * (sart_set_axion_masses) the image is [M][256][256]. */
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed);
 int sart_reset_image(sart_handle_t* h);
+/* Optional weighted radial histogram of the passed rays, for the 68 % / 95.5 % containment radii of
+ * generateResultPlots (rt:2459-2527, which sorts pointdataR of every passed ray): bin = floor(pointdataR * nbins / r_max),
+ * the last bin also collects r >= r_max. Filled by sart_trace_mc for a single axion mass, cleared by sart_reset_image.
+ * nbins = 0 switches it off (default). sum_w / counts are host arrays [nbins] (either may be NULL). */
+int sart_enable_radial_hist(sart_handle_t* h, int nbins, double r_max);
+int sart_read_radial_hist(sart_handle_t* h, double* sum_w, uint64_t* counts);
 /* Device pointers for collectives (ncclAllReduce / torch.distributed on the caller's side). */
 double* sart_image_dev(sart_handle_t* h);       /* [M][256][256] Σw  */
 double* sart_image_w2_dev(sart_handle_t* h);    /* [M][256][256] Σw² */

@@ -1,0 +1,99 @@
+"""Command line of the ray tracer: the switches of the reference's `main` (src/raytracer.nim:2817-2865, cligen
+`dispatch main`) driving the GPU path.
+
+  python -m solaraxionraytracing_b200 [--ignoreDetWindow] [--ignoreGasAbs] [--ignoreConvProb] [--ignoreReflection]
+      [--xrayTest] [--detectorInstall] [--magnet] [--angularScanMin A --angularScanMax B --numAngularScanPoints N]
+      [--noPlots] [--config FILE | --configPath DIR] [--nRays N] [--precision fast|exact] [--device D]
+
+Inputs the reference reads from `resources/` and that are not shipped with it (solar_model_dataframe.csv, the two
+reflectivity HDF5 files) are taken from [Resources] when present, else generated: Primakoff emission rates from AGSS09
+on the GPU and the packaged Henke gold reflectivity (XMM) / the synthetic multilayer tables (LLNL).
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+
+
+def build_parser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog="raytracer", description=__doc__.split("\n\n")[0])
+    for flag in ("ignoreDetWindow", "ignoreGasAbs", "ignoreConvProb", "ignoreReflection", "xrayTest", "detectorInstall",
+                 "magnet", "noPlots"):
+        ap.add_argument(f"--{flag}", action="store_true")
+    ap.add_argument("--angularScanMin", type=float, default=0.0)
+    ap.add_argument("--angularScanMax", type=float, default=0.0)
+    ap.add_argument("--numAngularScanPoints", type=int, default=50)
+    ap.add_argument("--config", default="", help="path to a config.toml")
+    ap.add_argument("--configPath", default="", help="directory holding config.toml")
+    ap.add_argument("--nRays", type=float, default=1e6, help="NumberOfPointsSun (rt:251)")
+    ap.add_argument("--seed", type=int, default=299792458)
+    ap.add_argument("--precision", choices=["fast", "exact"], default="fast")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--outputPath", default="", help="overrides [Resources].outputPath")
+    return ap
+
+
+def load_tables(rt, tables, res, setup, device: int):
+    """initFullSetup's inputs (rt:2645-2705, 1160-1249, 1498-1527): files under [Resources] when they exist."""
+    base = Path(res.resourcePath)
+    csv = base / res.solarModelFile
+    if res.solarModelFile and csv.is_file():
+        em = tables.read_solar_model_dataframe(csv)
+    else:
+        raw = base / res.rawSolarModel
+        sm = tables.read_solar_model(raw) if res.rawSolarModel and raw.is_file() else None
+        em = rt.calculateEmissionRates(sm, ("primakoff",), device=device)
+    rc, dc = rt.buildCdfs(em, device)
+    from . import abi
+    if setup.telescope.kind == abi.TK_LLNL:
+        refl = tables.synthetic_reflectivity(max(1, setup.telescope.nCoatings))
+    else:
+        refl = tables.gold_reflectivity_packaged()
+    try:
+        det = tables.detector_tables_from_resources(base, setup.detector.windowThickness, setup.detector.alThickness)
+    except OSError:
+        det = tables.detector_tables_packaged()
+    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl, **det)
+
+
+def main(argv=None) -> int:
+    a = build_parser().parse_args(argv)
+    from . import config as cfgmod, output, raytracer as rt, tables
+    cfg_file = a.config or (str(Path(a.configPath) / "config.toml") if a.configPath else None)
+    flags = rt.flags_from_cli(a.ignoreDetWindow, a.ignoreGasAbs, a.ignoreConvProb, a.ignoreReflection, a.xrayTest,
+                              a.magnet, a.detectorInstall)
+    print("Flags:", {n for n, on in vars(a).items() if on is True and n != "noPlots"})
+    setup, res = cfgmod.setup_from_config(cfg_file, flags)
+    outpath = a.outputPath or res.outputPath
+    tb = load_tables(rt, tables, res, setup, a.device)
+    fs = rt.FullRaytraceSetup(setup, tb, outpath)
+    n = int(a.nRays)
+    with rt.RayTracer(fs, a.device) as tr:
+        tr.set_precision(1 if a.precision == "fast" else 0)
+        if a.angularScanMin == a.angularScanMax:
+            print("start")
+            tr.enable_radial_hist()
+            tr.reset_image()
+            tr.trace_mc(n, a.seed)
+            result = tr.read_image()
+            radii = output.containment_radii_from_hist(*tr.read_radial_hist())
+            path = output.generateResultPlots(result, setup.detector.windowYear, outpath, radii=radii,
+                                              chipXMax=setup.consts.chipXMax, chipYMax=setup.consts.chipYMax)
+            print("wrote", path)
+        else:
+            angles, rel, _ = rt.performAngularScan(fs, a.angularScanMin, a.angularScanMax, a.numAngularScanPoints, n,
+                                                   a.seed, tracer=tr)
+            print("Angle [deg], relative flux")
+            for ang, r in zip(angles, rel):
+                print(f"{ang:.4f}, {r:.6f}")
+            Path(outpath).mkdir(parents=True, exist_ok=True)
+            np.savetxt(Path(outpath) / "angular_scan_telescope_y.csv", np.column_stack([angles, rel]), delimiter=",",
+                       header="Angle [deg],relative flux", comments="")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -182,6 +182,8 @@ SIGNATURES = {
     "sart_trace_mc_rays": (C.c_int, [H, C.c_uint64, C.c_size_t, C.c_uint64, C.POINTER(RayOut)]),
     "sart_trace_mc": (C.c_int, [H, C.c_uint64, C.c_uint64, C.c_uint64]),
     "sart_reset_image": (C.c_int, [H]),
+    "sart_enable_radial_hist": (C.c_int, [H, C.c_int, C.c_double]),
+    "sart_read_radial_hist": (C.c_int, [H, c_double_p, C.POINTER(C.c_uint64)]),
     "sart_image_dev": (C.c_void_p, [H]),
     "sart_image_w2_dev": (C.c_void_p, [H]),
     "sart_counters_dev": (C.c_void_p, [H]),

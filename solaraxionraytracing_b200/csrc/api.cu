@@ -271,7 +271,9 @@ static int autotune(sart_handle* h) {
   SART_CUDA(cudaMemsetAsync(base, 0, bytes, h->stream));
   const uint64_t n = 1u << 17;
   sart_counters_t* dc = reinterpret_cast<sart_counters_t*>(base + 2 * plane * sizeof(double));
-  SART_CUDA(launch_mc_image_fast(h->fparams, h->ftables, h->setup.consts.mAxion, 0, n, 0x5eedull,
+  fast::FastTables pilotTables = h->ftables;
+  pilotTables.rad = RadialHist{};   // the pilot rays must not reach the user's radial histogram
+  SART_CUDA(launch_mc_image_fast(h->fparams, pilotTables, h->setup.consts.mAxion, 0, n, 0x5eedull,
                                  reinterpret_cast<double*>(base), reinterpret_cast<double*>(base) + plane, dc,
                                  h->sm_count, false, h->stream));
   sart_counters_t c;
@@ -367,7 +369,7 @@ void sart_destroy(sart_handle_t* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
-  cudaFree(h->d_counters); cudaFree(h->d_stage);
+  cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -615,6 +617,41 @@ int sart_reset_image(sart_handle_t* h) {
   SART_CUDA(cudaMemsetAsync(h->d_image, 0, len * sizeof(double), h->stream));
   SART_CUDA(cudaMemsetAsync(h->d_image_w2, 0, len * sizeof(double), h->stream));
   SART_CUDA(cudaMemsetAsync(h->d_counters, 0, size_t(h->n_masses) * sizeof(sart_counters_t), h->stream));
+  if (h->rad_bins > 0) {
+    SART_CUDA(cudaMemsetAsync(h->d_rad_w, 0, size_t(h->rad_bins) * sizeof(double), h->stream));
+    SART_CUDA(cudaMemsetAsync(h->d_rad_n, 0, size_t(h->rad_bins) * sizeof(unsigned long long), h->stream));
+  }
+  return SART_OK;
+}
+
+int sart_enable_radial_hist(sart_handle_t* h, int nbins, double r_max) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (nbins < 0 || nbins > (1 << 24) || (nbins > 0 && !(r_max > 0.0))) return fail(SART_ERR_ARG, "sart_enable_radial_hist: bad argument");
+  DeviceGuard dg(h->device);
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_rad_w); cudaFree(h->d_rad_n);
+  h->d_rad_w = nullptr; h->d_rad_n = nullptr; h->rad_bins = 0; h->rad_rmax = 0.0;
+  RadialHist r{};
+  if (nbins > 0) {
+    SART_CUDA(cudaMalloc(&h->d_rad_w, size_t(nbins) * sizeof(double)));
+    SART_CUDA(cudaMalloc(&h->d_rad_n, size_t(nbins) * sizeof(unsigned long long)));
+    SART_CUDA(cudaMemsetAsync(h->d_rad_w, 0, size_t(nbins) * sizeof(double), h->stream));
+    SART_CUDA(cudaMemsetAsync(h->d_rad_n, 0, size_t(nbins) * sizeof(unsigned long long), h->stream));
+    h->rad_bins = nbins; h->rad_rmax = r_max;
+    r.w = h->d_rad_w; r.n = h->d_rad_n; r.invStep = double(nbins) / r_max; r.nbins = nbins;
+  }
+  h->tables.rad = r;
+  h->ftables.rad = r;
+  return SART_OK;
+}
+
+int sart_read_radial_hist(sart_handle_t* h, double* sum_w, uint64_t* counts) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (h->rad_bins < 1) return fail(SART_ERR_ARG, "sart_read_radial_hist: no radial histogram enabled");
+  DeviceGuard dg(h->device);
+  if (sum_w) SART_CUDA(cudaMemcpyAsync(sum_w, h->d_rad_w, size_t(h->rad_bins) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (counts) SART_CUDA(cudaMemcpyAsync(counts, h->d_rad_n, size_t(h->rad_bins) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
   return SART_OK;
 }
 
@@ -685,6 +722,9 @@ int sart_angular_scan(sart_handle_t* h, int n_angles, const double* angles_deg, 
   SART_CUDA(cudaMemsetAsync(base, 0, bytes, h->stream));
   // One launch per scan point, queued back to back on the handle's stream: only the by-value parameter block differs
   // (the rotation of the telescope frame), the tables and shell records in HBM are shared, nothing synchronises.
+  fast::FastTables ft = h->ftables;
+  Tables et = h->tables;
+  ft.rad = RadialHist{}; et.rad = RadialHist{};
   for (int i = 0; i < n_angles; ++i) {
     sart_setup_t s = h->setup;
     s.telescope.telescope_turned_y = angles_deg[i];   // rt:2796
@@ -695,10 +735,10 @@ int sart_angular_scan(sart_handle_t* h, int n_angles, const double* angles_deg, 
       fast::FastParams F;
       fast::derive_params(s, P, &F);
       F.shellRhoMin = h->fparams.shellRhoMin; F.shellInvStep = h->fparams.shellInvStep; F.nShellGuide = h->fparams.nShellGuide;
-      SART_CUDA(launch_mc_image_fast(F, h->ftables, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
+      SART_CUDA(launch_mc_image_fast(F, ft, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
                                      dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->compact != 0, h->stream));
     } else {
-      SART_CUDA(launch_mc_image_exact(P, h->tables, 1, h->d_masses, first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
+      SART_CUDA(launch_mc_image_exact(P, et, 1, h->d_masses, first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
                                       dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->stream));
     }
   }

@@ -62,6 +62,15 @@ struct Params {
   int32_t nRadii, nEnergies;
 };
 
+// Optional weighted radial histogram of the passed rays (pointdataR rt:2202) for the containment radii of
+// generateResultPlots (rt:2459-2527): bin = floor(r * invStep), the last bin collects everything beyond. w == nullptr: off.
+struct RadialHist {
+  double* w;                 // [nbins] sum of weights
+  unsigned long long* n;     // [nbins] number of rays
+  double invStep;
+  int32_t nbins, pad;
+};
+
 // Table pointers (device memory).
 struct Tables {
   const double* energies;
@@ -71,6 +80,7 @@ struct Tables {
   const double *sbX, *sbY, *wdX, *wdY, *gaX, *gaY, *ttX, *ttY;
   int32_t sbN, wdN, gaN, ttN;
   const ShellF64* shells;
+  RadialHist rad;
 };
 
 constexpr int kGuide = 1024;  // guide-table buckets per CDF row

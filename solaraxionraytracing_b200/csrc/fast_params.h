@@ -65,6 +65,7 @@ struct FastTables {
   const float* reflE;
   const ShellFast* shells;    // [nShells]
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
+  RadialHist rad;             // optional (w == nullptr: off)
 };
 
 }  // namespace fast

@@ -161,6 +161,12 @@ k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Table
         atomicAdd(image + bin, f.w);
         atomicAdd(imageW2 + bin, f.w * f.w);
       }
+      if (T.rad.w && m == 0) {
+        int b = int(f.r * T.rad.invStep);
+        b = b < 0 ? 0 : (b > T.rad.nbins - 1 ? T.rad.nbins - 1 : b);
+        atomicAdd(T.rad.w + b, f.w);
+        atomicAdd(T.rad.n + b, 1ull);
+      }
     }
   }
   __syncthreads();

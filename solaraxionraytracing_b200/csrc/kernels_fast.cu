@@ -72,6 +72,13 @@ __device__ __forceinline__ float atan_small(float x) {
 
 struct D3 { double x, y, z; };
 
+__device__ __forceinline__ void rad_add(const RadialHist& h, double r, double w) {
+  int b = int(r * h.invStep);
+  b = b < 0 ? 0 : (b > h.nbins - 1 ? h.nbins - 1 : b);
+  atomicAdd(h.w + b, w);
+  atomicAdd(h.n + b, 1ull);
+}
+
 // ---- shared memory layout -----------------------------------------------------------------------------------
 struct WarpCounters { unsigned int n_exit[16]; unsigned int n_clamped; unsigned int pad[3]; };
 
@@ -626,6 +633,7 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
         atomicAdd(image + r.bin, wd);
         atomicAdd(imageW2 + r.bin, wd * wd);
       }
+      if (T.rad.w) rad_add(T.rad, r.r, wd);
     } else {
       atomicAdd(&wc[warp].n_exit[code & SART_CODE_MASK], 1u);
     }
@@ -734,6 +742,7 @@ k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_const
           atomicAdd(image + r.bin, wd);
           atomicAdd(imageW2 + r.bin, wd * wd);
         }
+        if (T.rad.w) rad_add(T.rad, r.r, wd);
       } else {
         atomicAdd(&wc[warp].n_exit[code & SART_CODE_MASK], 1u);
       }

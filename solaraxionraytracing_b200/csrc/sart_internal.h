@@ -64,6 +64,11 @@ struct sart_handle {
   double* d_image = nullptr;    // [n_masses][256][256]
   double* d_image_w2 = nullptr;
   sart_counters_t* d_counters = nullptr;  // [n_masses]
+  // optional radial histogram of the passed rays (sart_enable_radial_hist)
+  double* d_rad_w = nullptr;
+  unsigned long long* d_rad_n = nullptr;
+  int rad_bins = 0;
+  double rad_rmax = 0.0;
   // staging for the host-pointer entry points
   void* d_stage = nullptr;
   size_t stage_bytes = 0;

@@ -239,6 +239,22 @@ class RayTracer:
     def reset_image(self):
         check(lib.sart_reset_image(self._h))
 
+    def enable_radial_hist(self, nbins: int = 16384, r_max: float | None = None):
+        """Radial histogram of the passed rays (for the containment radii); r_max defaults to the chip diagonal / 2."""
+        if r_max is None:
+            c = self.fullSetup.expSetup.consts
+            r_max = 0.5 * float(np.hypot(c.chipXMax, c.chipYMax)) * 1.0001
+        check(lib.sart_enable_radial_hist(self._h, nbins, r_max))
+        self._rad = (nbins, r_max)
+
+    def read_radial_hist(self):
+        """(bin edges [nbins + 1], sum of weights [nbins], ray counts [nbins])."""
+        nbins, r_max = self._rad
+        w = np.empty(nbins)
+        n = np.empty(nbins, dtype=np.uint64)
+        check(lib.sart_read_radial_hist(self._h, _dp(w), n.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return np.linspace(0.0, r_max, nbins + 1), w, n
+
     def synchronize(self):
         check(lib.sart_synchronize(self._h))
 

@@ -197,3 +197,37 @@ def solar_model_packaged() -> SolarModel:
     """The same columns from the packaged copy (tools/make_fixtures.py; the GPU box has no /root/reference)."""
     z = np.load(DATA_DIR / "agss09_solar_model.npz")
     return SolarModel(z["radius"], z["temp_K"], z["rho_gcm3"], np.ascontiguousarray(z["mass_fractions"]))
+
+
+def read_solar_model_dataframe(path: str | Path) -> EmissionTable:
+    """The emission table the reference reads in initFullSetup (rt:2647-2668): a CSV with the columns `Radius`,
+    `Energy [keV]` and `emRates` written by readOpacityFile (one row per (radius, energy), any order). Radii and energies
+    are the sorted unique values; every radius must carry the same energies (the reference's doAssert, rt:2667)."""
+    with open(path) as f:
+        header = [h.strip() for h in f.readline().rstrip("\n").split(",")]
+    need = ("Radius", "Energy [keV]", "emRates")
+    for n in need:
+        if n not in header:
+            raise ValueError(f"{path}: column {n!r} missing (found {header})")
+    data = np.loadtxt(path, delimiter=",", skiprows=1, usecols=[header.index(n) for n in need], ndmin=2)
+    radii, ri = np.unique(data[:, 0], return_inverse=True)
+    energies, ei = np.unique(data[:, 1], return_inverse=True)
+    if data.shape[0] != radii.size * energies.size:
+        raise ValueError(f"{path}: {data.shape[0]} rows is not {radii.size} radii x {energies.size} energies")
+    em = np.full((radii.size, energies.size), np.nan)
+    em[ri, ei] = data[:, 2]
+    if np.isnan(em).any():
+        raise ValueError(f"{path}: not every radius has every energy")
+    return EmissionTable(radii=radii, energies=energies, emRates=em)
+
+
+def write_solar_model_dataframe(path: str | Path, table: EmissionTable) -> Path:
+    """Writes an EmissionTable in the format readOpacityFile produces (readOpacityFile.nim:848-849 `result.add toDf(...)`)."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    R = np.repeat(table.radii, table.energies.size)
+    E = np.tile(table.energies, table.radii.size)
+    with open(path, "w") as f:
+        f.write("Radius,Energy [keV],emRates\n")
+        np.savetxt(f, np.column_stack([R, E, table.emRates.reshape(-1)]), delimiter=",", fmt="%.17g")
+    return path
