@@ -40,7 +40,7 @@ F_RAY_LLNL = 850.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays-per-step", type=float, default=1e9)
     ap.add_argument("--precision", choices=["exact", "fast"], default=None)
@@ -132,7 +132,7 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -148,6 +148,10 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def mark(self, name: str):
+        """Wall-clock marks ("t0"/"t1") of the timed region, to pick the samples taken inside it."""
+        setattr(self, name, time.time())
+
     def stop(self) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -158,24 +162,33 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for line in self.f.read().splitlines():
             p = [x.strip() for x in line.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[1]), float(p[2]), p[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+        os.unlink(self.f.name)
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        inside = [r for r in rows if t0 is not None and t1 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        where = "timed region"
+        if not inside:
+            # region shorter than the sampling period: fall back to the samples under load (upper half by SM clock)
+            inside = sorted(rows, key=lambda r: r[1])[len(rows) // 2:]
+            where = "whole run, upper half by SM clock (timed region shorter than the 100 ms sampling period)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
-        # under load = the upper half of the samples (the sampler also sees the idle edges)
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "samples": len(inside), "window": where, "reasons": sorted(reasons)}
 
 
 def presampled_leg(tr, torch, device, n_unique: int = 1 << 20, repeat: int = 16):
@@ -257,6 +270,29 @@ def presampled_leg(tr, torch, device, n_unique: int = 1 << 20, repeat: int = 16)
                          "note": "FP64 libm per ray makes this kernel compute-bound; the HBM figure is its ceiling"}}
 
 
+def records_leg(tr, torch, n: int = 1 << 24, reps: int = 3):
+    """The literal traceAxionWrapper drop-in (sart_trace_mc_rays): Philox sampling + trace on the GPU, one record per
+    ray (x, y, w f64 + code, shell i32 = 32 B) copied into the caller's pinned host arrays inside the call."""
+    import ctypes as C
+    from solaraxionraytracing_b200 import abi
+    from solaraxionraytracing_b200._lib import check, lib
+    hx, hy, hw = (torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3))
+    hc, hs = (torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2))
+    ro = abi.RayOut()
+    ro.x, ro.y, ro.w = (C.cast(t.data_ptr(), abi.c_double_p) for t in (hx, hy, hw))
+    ro.code, ro.shell = (C.cast(t.data_ptr(), abi.c_int32_p) for t in (hc, hs))
+    tr.set_precision(1)
+    call = lambda k: check(lib.sart_trace_mc_rays(tr._h, k * n, n, SEED, C.byref(ro)))
+    call(0)
+    t0 = time.perf_counter()
+    for k in range(reps):
+        call(1 + k)
+    dt = (time.perf_counter() - t0) / reps
+    return {"api": "sart_trace_mc_rays (traceAxionWrapper, per-ray records to host)", "rays_per_call": n,
+            "value": n / dt, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32 * n,
+            "d2h_GBps": 32 * n / dt / 1e9, "passed_fraction": float((hc.bitwise_and(0xff) == 0).double().mean())}
+
+
 def run_ours(args):
     import torch
     from solaraxionraytracing_b200 import abi, multi_gpu, raytracer as rt, tables
@@ -311,6 +347,14 @@ def run_ours(args):
             if rank != 0:
                 tr.reset_image()
 
+    smi_index = local
+    try:
+        smi_index = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+    except (KeyError, ValueError, IndexError):
+        pass
+    sampler = ClockSampler(smi_index)
+    if rank == 0:
+        sampler.start()   # started before the warm-up: nvidia-smi needs up to a second to deliver its first sample
     with torch.cuda.stream(stream):
         tr.reset_image()
         for w in range(W):
@@ -318,22 +362,17 @@ def run_ours(args):
         barrier()
         tr.reset_image()
         barrier()
-        smi_index = local
-        try:
-            smi_index = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
-        except (KeyError, ValueError, IndexError):
-            pass
-        sampler = ClockSampler(smi_index)
-        sampler.start()
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        sampler.mark("t0")
         e0.record(stream)
         for k in range(K):
             step(W + k, kev[k])
         e1.record(stream)
         barrier()
-        clocks = sampler.stop()
+        sampler.mark("t1")
+        clocks = sampler.stop() if rank == 0 else None
         ms_total = e0.elapsed_time(e1)
         kernel_ms = [a.elapsed_time(b) for a, b in kev]
     res = tr.read_image()
@@ -393,6 +432,7 @@ def run_ours(args):
         }
         if n_gpus == 1 and not args.no_presampled:
             out["presampled"] = presampled_leg(tr, torch, local)
+            out["e2e_records"] = records_leg(tr, torch)
         if n_gpus == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_leg(args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
