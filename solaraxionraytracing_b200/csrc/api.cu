@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -70,18 +71,31 @@ static int validate(const sart_setup_t* s, const sart_tables_t* t) {
   return SART_OK;
 }
 
-// Guide table of a CDF row: g[k] = lowerBound(cdf, k/K), k = 0..K. For k/K <= u < (k+1)/K the answer of
-// lowerBound(cdf, u) lies in [g[k], g[k+1]], so the device search starts from a window of 1-2 entries. Stored packed,
-// out[k] = g[k] | g[k+1] << 16, so that a window is one 32-bit load.
-static void build_guide(const double* cdf, int n, uint32_t* out) {
+// Guide table of a CDF row: g[k] = lowerBound(cdf, k/K). For a uniform u in bucket k (k/K <= u < (k+1)/K) the answer of
+// lowerBound(cdf, u) is >= g[k], and usually g[k] or g[k] + 1: the device counts thresholds from there.
+static void build_guide(const double* cdf, int n, int nBuckets, uint16_t* out) {
   int pos = 0;
-  uint32_t prev = 0;
-  for (int k = 0; k <= kGuide; ++k) {
-    const double key = double(k) / double(kGuide);
+  for (int k = 0; k < nBuckets; ++k) {
+    const double key = double(k) / double(nBuckets);
     while (pos < n && cdf[pos] < key) ++pos;
-    if (k > 0) out[k - 1] = prev | (uint32_t(pos) << 16);
-    prev = uint32_t(pos);
+    out[k] = uint16_t(pos);
   }
+}
+
+// Smallest 32-bit word w with c < (w + 0.5) 2^-32, i.e. "cdf entry < uniform of word w" <=> w >= threshold. Exact:
+// c 2^32 is a power-of-two scaling and its fractional part is compared with 0.5. Saturates at 0xffffffff (c within
+// 1.5 2^-32 of 1, or NaN rows of shells that emit nothing); the kernel sends that one word to the f64 table.
+static uint32_t cdf_threshold(double c) {
+  if (c != c) return 0xffffffffu;
+  if (!(c > 0.0)) return 0u;
+  const double x = c * 4294967296.0, k = std::floor(x);
+  const double t = k + ((x - k) >= 0.5 ? 1.0 : 0.0);
+  return t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
+}
+static void build_thresholds(const double* cdf, int n, uint32_t* out /* [thr_pitch(n)] */) {
+  const int pitch = thr_pitch(n);
+  for (int i = 0; i < n; ++i) out[i] = cdf_threshold(cdf[i]);
+  for (int i = n; i < pitch; ++i) out[i] = 0xffffffffu;
 }
 
 struct Blob {  // bump allocator over one device allocation
@@ -190,19 +204,28 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     h->fast_sguide_off = off; off += 4096;
     h->fast_lut_off = off; off += align256(lut.size() * sizeof(fast::EnergyLUT));
     h->fast_glut_off = off; off += align256(glut.size() * sizeof(fast::GasLUT));
-    const size_t rgOff = off; off += align256(size_t(kGuide) * 4);
-    const size_t egOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * kGuide * 4);
+    const size_t rgOff = off; off += align256(size_t(kRadGuide) * 2);
+    const size_t egOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * kEnGuide * 2);
+    const size_t rtOff = off; off += align256(size_t(thr_pitch(std::max(P.nRadii, 1))) * 4);
+    const size_t etOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * thr_pitch(std::max(P.nEnergies, 1)) * 4);
     h->fast_refl_off = off; off += align256(size_t(std::max(nCoat, 1)) * reflPlane * sizeof(float));
     if (h->fast_blob) { cudaFree(h->fast_blob); h->fast_blob = nullptr; }
     SART_CUDA(cudaMalloc(&h->fast_blob, off + 256));
     base = static_cast<unsigned char*>(h->fast_blob);
     if (P.nRadii > 0 && t->fluxRadiusCDF) {
-      std::vector<uint32_t> rg(kGuide), eg(size_t(P.nRadii) * kGuide);
-      build_guide(t->fluxRadiusCDF, P.nRadii, rg.data());
-      for (int r = 0; r < P.nRadii; ++r)
-        build_guide(t->diffFluxCDFs + size_t(r) * P.nEnergies, P.nEnergies, eg.data() + size_t(r) * kGuide);
-      SART_CUDA(cudaMemcpy(base + rgOff, rg.data(), rg.size() * 4, cudaMemcpyHostToDevice));
-      SART_CUDA(cudaMemcpy(base + egOff, eg.data(), eg.size() * 4, cudaMemcpyHostToDevice));
+      const int ep = thr_pitch(P.nEnergies);
+      std::vector<uint16_t> rg(kRadGuide), eg(size_t(P.nRadii) * kEnGuide);
+      std::vector<uint32_t> rth(size_t(thr_pitch(P.nRadii))), eth(size_t(P.nRadii) * ep);
+      build_guide(t->fluxRadiusCDF, P.nRadii, kRadGuide, rg.data());
+      build_thresholds(t->fluxRadiusCDF, P.nRadii, rth.data());
+      for (int r = 0; r < P.nRadii; ++r) {
+        build_guide(t->diffFluxCDFs + size_t(r) * P.nEnergies, P.nEnergies, kEnGuide, eg.data() + size_t(r) * kEnGuide);
+        build_thresholds(t->diffFluxCDFs + size_t(r) * P.nEnergies, P.nEnergies, eth.data() + size_t(r) * ep);
+      }
+      SART_CUDA(cudaMemcpy(base + rgOff, rg.data(), rg.size() * 2, cudaMemcpyHostToDevice));
+      SART_CUDA(cudaMemcpy(base + egOff, eg.data(), eg.size() * 2, cudaMemcpyHostToDevice));
+      SART_CUDA(cudaMemcpy(base + rtOff, rth.data(), rth.size() * 4, cudaMemcpyHostToDevice));
+      SART_CUDA(cudaMemcpy(base + etOff, eth.data(), eth.size() * 4, cudaMemcpyHostToDevice));
     }
     // reflectivity interpolated along energy at each tabulated energy
     if (nCoat > 0) {
@@ -218,8 +241,10 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     fast::FastTables& F = h->ftables;
     F.radiusCDF = h->tables.fluxRadiusCDF;
     F.energyCDF = h->tables.diffFluxCDFs;
-    F.radiusGuide = reinterpret_cast<const uint32_t*>(base + rgOff);
-    F.energyGuide = reinterpret_cast<const uint32_t*>(base + egOff);
+    F.radiusGuide = reinterpret_cast<const uint16_t*>(base + rgOff);
+    F.energyGuide = reinterpret_cast<const uint16_t*>(base + egOff);
+    F.radiusThr = reinterpret_cast<const uint32_t*>(base + rtOff);
+    F.energyThr = reinterpret_cast<const uint32_t*>(base + etOff);
     F.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
     F.glut = reinterpret_cast<const fast::GasLUT*>(base + h->fast_glut_off);
     F.reflE = reinterpret_cast<const float*>(base + h->fast_refl_off);

@@ -83,6 +83,22 @@ struct Tables {
   RadialHist rad;
 };
 
-constexpr int kGuide = 1024;  // guide-table buckets per CDF row
+// Guide-table buckets per CDF row; the bucket of the uniform (w + 0.5) 2^-32 is w >> (32 - bits). Sized so that the
+// flat tails of the CDFs (hundreds of entries sharing 1e-3 of the probability) still resolve within the 8 thresholds
+// the kernel prefetches for all but ~1e-3 of the rays: radius guide 16 KiB of shared memory, energy guide 4 KiB per row (larger guides cost more in L1/L2 capacity than they save: measured).
+#ifndef SART_RAD_GUIDE_BITS
+#define SART_RAD_GUIDE_BITS 13
+#endif
+#ifndef SART_EN_GUIDE_BITS
+#define SART_EN_GUIDE_BITS 11
+#endif
+constexpr int kRadGuideBits = SART_RAD_GUIDE_BITS, kRadGuide = 1 << kRadGuideBits;
+constexpr int kEnGuideBits = SART_EN_GUIDE_BITS, kEnGuide = 1 << kEnGuideBits;
+// Entries per row of a u32 threshold table: the row rounded up to 4 entries plus 8 saturated pad entries, so that two
+// 16-byte loads from any 4-aligned start inside the row stay inside the row's storage.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int thr_pitch(int n) { return ((n + 3) & ~3) + 8; }
 
 }  // namespace sart

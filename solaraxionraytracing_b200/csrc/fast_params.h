@@ -54,10 +54,14 @@ struct GasLUT {     // buffer-gas stage only
 };
 
 struct FastTables {
-  const double* radiusCDF;
-  const uint32_t* radiusGuide;   // [kGuide] packed (g[k] | g[k+1] << 16), g[k] = lowerBound(cdf, k/kGuide)
-  const double* energyCDF;
-  const uint32_t* energyGuide;   // [nRadii][kGuide] packed likewise
+  // Inverse-CDF sampling (rt:437, 464) in integers: with u = (w + 0.5) 2^-32, cdf[i] < u  <=>  w >= thr[i], where
+  // thr[i] is the smallest such 32-bit word (saturated at 0xffffffff; that word falls back to the f64 tables).
+  const double* radiusCDF;       // [nRadii] f64, fallback only
+  const uint32_t* radiusThr;     // [thr_pitch(nRadii)]
+  const uint16_t* radiusGuide;   // [kRadGuide] g[k] = lowerBound(cdf, k/kRadGuide): the search for a word of bucket k starts there
+  const double* energyCDF;       // [nRadii][nEnergies] f64, fallback only
+  const uint32_t* energyThr;     // [nRadii][thr_pitch(nEnergies)]
+  const uint16_t* energyGuide;   // [nRadii][kEnGuide]
   const EnergyLUT* elut;         // [nEnergies + 1]
   const GasLUT* glut;            // [nEnergies + 1]
   // reflectivity pre-interpolated along the energy axis at every tabulated energy: [coat][nEnergies + 1][nAngles];

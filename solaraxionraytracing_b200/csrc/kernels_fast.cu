@@ -11,8 +11,11 @@
 //   * everything that only scales the weight (emission direction sines, grazing angles for the reflectivity
 //     lookup, cos(yaw), transmissions) is FP32 with MUFU intrinsics; transmissions, the energy and the reflectivity
 //     cell of each of the nE tabulated energies come from a per-energy-index LUT built once at sart_create;
-//   * CDF searches start from a 1024-bucket guide table (1-2 entries instead of 11 probes) and their dependent loads are
-//     issued ahead of the geometry that separates them from their use;
+//   * the two inverse-CDF searches (rt:437, 464) are exact integer work: cdf[i] < u with u = (w + 0.5) 2^-32 is
+//     w >= T[i] for the 32-bit threshold T[i] = smallest such w, so the f64 tables become u32 tables of half the size,
+//     a guide table (bucket = top bits of w) gives the start, one or two 16-byte loads give 8 thresholds and the index
+//     is start + the number of thresholds <= w — no loop, no f64 compare, same index as lowerBound on the f64 CDF;
+//     the dependent loads are issued ahead of the geometry that separates them from their use;
 //   * run-wide tables (radius CDF, guide, shell constants) are staged once per block in shared memory;
 //   * counters live in registers / per-warp shared memory and are flushed once per block.
 // Exit codes follow the same decision sequence as the exact pipeline, so the counters of both are comparable.
@@ -87,6 +90,20 @@ __device__ __forceinline__ int lower_bound_window(const double* __restrict__ a, 
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Number of the 4 ascending thresholds that are <= w.
+__device__ __forceinline__ int count_le(const uint4& t, uint32_t w) {
+  return int(w >= t.x) + int(w >= t.y) + int(w >= t.z) + int(w >= t.w);
+}
+// lowerBound over u32 thresholds beyond the 8 prefetched ones (windows wider than 8 entries: flat CDF tails)
+__device__ __noinline__ int thr_search_tail(const uint32_t* __restrict__ thr, int from, int n, uint32_t w) {
+  int lo = from, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (w >= thr[mid]) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -166,24 +183,28 @@ struct RayResult {
 // Shared-memory tables of one block (shells first so their addresses are compile-time offsets).
 struct Smem {
   const ShellFast* shell;
-  const double* radCDF;
-  const uint32_t* radGuide;
+  const uint32_t* radThr;     // [thrPitch(nRadii)] thresholds of the radius CDF, 16-byte aligned
+  const uint16_t* radGuide;   // [kRadGuide]
   const uint8_t* shellGuide;
 };
+__host__ __device__ __forceinline__ size_t align16(size_t n) { return (n + 15) & ~size_t(15); }
 __device__ __forceinline__ size_t smem_layout(const FastParams& P, unsigned char* base, Smem& s, unsigned char*& tail) {
   size_t off = 0;
-  s.shell = reinterpret_cast<const ShellFast*>(base + off); off += size_t(P.nShells) * sizeof(ShellFast);
-  s.radCDF = reinterpret_cast<const double*>(base + off); off += size_t((P.nRadii + 1) & ~1) * 8;
-  s.radGuide = reinterpret_cast<const uint32_t*>(base + off); off += size_t(kGuide) * 4;
-  s.shellGuide = base + off; off += (size_t(P.nShellGuide) + 15) & ~size_t(15);
+  s.shell = reinterpret_cast<const ShellFast*>(base + off); off += align16(size_t(P.nShells) * sizeof(ShellFast));
+  s.radThr = reinterpret_cast<const uint32_t*>(base + off); off += size_t(thr_pitch(P.nRadii)) * 4;
+  s.radGuide = reinterpret_cast<const uint16_t*>(base + off); off += size_t(kRadGuide) * 2;
+  s.shellGuide = base + off; off += align16(size_t(P.nShellGuide));
   tail = base + off;
   return off;
 }
 __device__ __forceinline__ void smem_fill(const FastParams& P, const FastTables& T, const Smem& s) {
   for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
     reinterpret_cast<double*>(const_cast<ShellFast*>(s.shell))[i] = reinterpret_cast<const double*>(T.shells)[i];
-  for (int i = threadIdx.x; i < P.nRadii; i += kBlock) const_cast<double*>(s.radCDF)[i] = T.radiusCDF[i];
-  if (P.nRadii > 0) for (int i = threadIdx.x; i < kGuide; i += kBlock) const_cast<uint32_t*>(s.radGuide)[i] = T.radiusGuide[i];
+  if (P.nRadii > 0) {
+    for (int i = threadIdx.x; i < thr_pitch(P.nRadii); i += kBlock) const_cast<uint32_t*>(s.radThr)[i] = T.radiusThr[i];
+    for (int i = threadIdx.x; i < kRadGuide / 8; i += kBlock)   // 16 bytes per thread and step
+      reinterpret_cast<uint4*>(const_cast<uint16_t*>(s.radGuide))[i] = __ldg(reinterpret_cast<const uint4*>(T.radiusGuide) + i);
+  }
   for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
 }
 
@@ -223,22 +244,28 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
   // ================= sampling rt:1754-1764 (or the X-ray test source rt:1765-1801)
   double ex, ey, sx, sy;   // point on the exit disc of the field (z = lengthB) and slopes
   int eIdx;
-  // energy search state: the guide entry is loaded here, the CDF window after the clip tests and the index is resolved
+  // energy search state: the guide entry is loaded here, the thresholds after the clip tests and the index is resolved
   // at the end of the stage — the dependent global loads overlap the geometry instead of stalling in a row
-  int eLo = 0, eHi = 0;
-  double ue = 0.0;
-  const double* eRow = nullptr;
+  int e0 = 0;
+  const uint32_t* eRow = nullptr;
   if (!P.testXray) {
-    // emission shell (exact index: same f64 CDF, same key as the oracle)
-    const double ur = u01(w[2]);
-    const int kr = int(ur * double(kGuide));
-    const uint32_t gr = S.radGuide[kr];
-    const int rIdx = lower_bound_window(S.radCDF, int(gr & 0xffffu), int(gr >> 16), ur);
-    ue = u01(w[5]);
+    // emission shell rt:437: rIdx = lowerBound(fluxRadiusCDF, u), exact (integer thresholds in shared memory)
+    int rIdx;
     {
-      const uint32_t ge = __ldg(T.energyGuide + size_t(rIdx) * kGuide + int(ue * double(kGuide)));
-      eLo = int(ge & 0xffffu); eHi = int(ge >> 16);
-      eRow = T.energyCDF + size_t(rIdx) * P.nEnergies;
+      const uint32_t wr = w[2];
+      const int r0 = int(S.radGuide[wr >> (32 - kRadGuideBits)]) & ~3;
+      rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
+      if (rIdx == r0 + 4) {
+        rIdx += count_le(*reinterpret_cast<const uint4*>(S.radThr + r0 + 4), wr);
+        if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, P.nRadii, wr);
+      }
+      if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));   // saturated thresholds
+      if (rIdx > P.nRadii - 1) rIdx = P.nRadii - 1;
+    }
+    {
+      const uint32_t we = w[5];
+      e0 = int(__ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (we >> (32 - kEnGuideBits)))) & ~3;
+      eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
     }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);  // fraction of the solar radius (weight-free: direction only)
     float s1, c1, s2, c2;
@@ -305,14 +332,11 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
   }
   double x0 = fma(sx, P.dzPipe2, ex), y0 = fma(sy, P.dzPipe2, ey);
   if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) return SART_EXIT_CLIP_PIPE_XRT;  // quirk Q2
-  // energy CDF window: two 16-byte loads starting at the aligned entry at or below eLo (windows are 1-2 entries wide)
-  double2 ecA = make_double2(2.0, 2.0), ecB = make_double2(2.0, 2.0);
-  int e0 = 0;
+  // energy thresholds: 8 entries from the 16-byte aligned entry at or below the guide's start (windows are 1-2 wide)
+  uint4 etA = make_uint4(0, 0, 0, 0), etB = etA;
   if (eRow) {
-    const double* p = eRow + eLo;
-    e0 = eLo - int((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
-    ecA = __ldg(reinterpret_cast<const double2*>(eRow + e0));
-    ecB = __ldg(reinterpret_cast<const double2*>(eRow + e0 + 2));
+    etA = __ldg(reinterpret_cast<const uint4*>(eRow + e0));
+    etB = __ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4));
   }
 
   // ================= telescope frame rt:1888-1905 (rotation about (0, 0, halfLenTel); identity when not turned)
@@ -380,12 +404,16 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
       if (radialDist > sShell[hitLayer - 1].R1) return SART_EXIT_GLASS_FRONT;
     }
   }
-  // energy index from the CDF window loaded above
+  // energy index rt:464 from the thresholds loaded above: idx = lowerBound(diffFluxCDFs[iRad], u), exact
   if (eRow) {
-    const int cnt = int(e0 >= eLo && e0 < eHi && ecA.x < ue) + int(e0 + 1 < eHi && ecA.y < ue) +
-                    int(e0 + 2 < eHi && ecB.x < ue) + int(e0 + 3 < eHi && ecB.y < ue);
-    eIdx = eLo + cnt;
-    if (eIdx == e0 + 4 && e0 + 4 < eHi) eIdx = lower_bound_window(eRow, e0 + 4, eHi, ue);
+    const uint32_t we = w[5];
+    eIdx = e0 + count_le(etA, we);
+    if (eIdx == e0 + 4) {
+      eIdx += count_le(etB, we);
+      if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, P.nEnergies, we);
+    }
+    if (we == 0xffffffffu)   // saturated thresholds: the f64 row decides
+      eIdx = lower_bound_window(T.energyCDF + size_t(eRow - T.energyThr) / thr_pitch(P.nEnergies) * P.nEnergies, 0, P.nEnergies, u01(we));
     if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
   }
   rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.path2 = path2;
@@ -394,13 +422,15 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
 }
 
 // Stage B: the two reflections, nickel / degenerate exits, detector plane, weights, window (rt:1971-2221).
-// kFold: fold the conversion probability of the single axion mass m2 into wPre right away (fewer live values).
-template <bool kWolter, bool kFold>
+// The outcome goes to `sink` at the point where it is known — sink.fail(code) for a geometric exit, sink.hit(record)
+// for a ray that reached the weight stage — instead of through a result struct merged over all return paths (that
+// merge cost ~10 % of the kernel's instructions in register moves and zero fills).
+// Sink::kFold: fold the conversion probability of the single axion mass sink.m2 into wPre right away.
+template <bool kWolter, class Sink>
 __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T, const Smem& S, const Rec& rec,
-                                        double m2, RayResult& out) {
+                                        Sink& sink) {
   const ShellFast* __restrict__ sShell = S.shell;
-  out.bin = -1; out.x = 0.0; out.y = 0.0; out.r = 0.0; out.shell = -1; out.energy = 0.f;
-  out.windowMiss = false; out.clamped = false; out.wPre = 0.0; out.wPost = 0.0;
+  RayResult out;
   out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
   const double x0 = rec.x0, y0 = rec.y0, tx = rec.tx, ty = rec.ty, path2 = rec.path2;
   const int hitLayer = rec.hitLayer, eIdx = rec.eIdx;
@@ -440,7 +470,7 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
       const double lhs = a * (lM - zc), rhs = sh.R1 - below;
       if (lhs * lhs > rhs * rhs * (1.0 - a * a)) code = SART_EXIT_NICKEL;
     }
-    out.code = code;
+    sink.fail(code);
     return;
   }
   D3 pm = {fma(tx, z1, x0), fma(ty, z1, y0), z1};
@@ -479,9 +509,9 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
   if (hitLayer > 0) {
     // squared form of tan(alpha1) > (r1 - below)/(l - z1); both sides are positive
     const double lhs = sinA1 * (lM - z1), rhs = sh.R1 - below;
-    if (lhs * lhs > rhs * rhs * (1.0 - sinA1 * sinA1)) { out.code = SART_EXIT_NICKEL; return; }
+    if (lhs * lhs > rhs * rhs * (1.0 - sinA1 * sinA1)) { sink.fail(SART_EXIT_NICKEL); return; }
   }
-  if (!hit2) { out.code = SART_EXIT_NO_MIRROR_HIT; return; }  // pointMirror2 == pointMirror1 (rt:2055)
+  if (!hit2) { sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }  // pointMirror2 == pointMirror1 (rt:2055)
   pm.x = fma(t2, v.x, pm.x); pm.y = fma(t2, v.y, pm.y); pm.z = fma(t2, v.z, pm.z);
   double sinA2;
   {
@@ -535,7 +565,7 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
       refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
     }
     out.wPre = double(refl) * double(pre);   // FP32 factors, FP64 product: tiny weights must not flush to zero
-    if (kFold) out.wPre *= conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, m2);
+    if (Sink::kFold) out.wPre *= conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
   }
   out.clamped = clamped;
   out.shell = hitLayer;
@@ -543,8 +573,11 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
   // ================= window aperture rt:2139-2147
   const double rw2 = fma(xw, xw, yw * yw);
   if ((!(P.flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > P.radiusWindow2) || fabs(xw) > P.chipCX || fabs(yw) > P.chipCY) {
-    out.windowMiss = true; return;
+    out.windowMiss = true; out.wPost = 0.0; out.x = out.y = out.r = 0.0; out.bin = -1;
+    sink.hit(out);
+    return;
   }
+  out.windowMiss = false;
   // ================= strongback strips rt:2149-2185
   double post = 1.0;
   {
@@ -569,20 +602,31 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
   out.y = yw + P.chipCY;
   // prepareHeatmap rt:839-842
   const int cx = int(floor(out.x * P.invBinX)), cy = int(floor(out.y * P.invBinY));
-  if (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) out.bin = cy * SART_IMAGE_BINS + cx;
+  out.bin = (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) ? cy * SART_IMAGE_BINS + cx : -1;
+  sink.hit(out);
 }
+
+// Sink that keeps the outcome as a RayResult (per-ray records, mass scan).
+template <bool kFoldT>
+struct RecordSink {
+  static constexpr bool kFold = kFoldT;
+  RayResult& out;
+  double m2;
+  __device__ __forceinline__ void fail(int code) {
+    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1; out.energy = 0.f;
+    out.x = out.y = out.r = 0.0; out.wPre = out.wPost = 0.0;
+  }
+  __device__ __forceinline__ void hit(const RayResult& h) { out = h; out.code = -1; }
+};
 
 template <bool kWolter, bool kFold>
 __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const Smem& S, uint64_t seed,
                                           uint64_t ray, double m2, RayResult& out) {
   Rec rec;
   const int code = stage_a<kWolter>(P, T, S, seed, ray, rec);
-  if (code >= 0) {
-    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1; out.energy = 0.f;
-    out.x = out.y = out.r = 0.0;
-    return;
-  }
-  stage_b<kWolter, kFold>(P, T, S, rec, m2, out);
+  RecordSink<kFold> sink{out, m2};
+  if (code >= 0) { sink.fail(code); return; }
+  stage_b<kWolter>(P, T, S, rec, sink);
 }
 
 // Tail of traceAxion for one axion mass: exit code | flags and the final weight.
@@ -597,6 +641,39 @@ __device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& 
   w = w0 * r.wPost;
   return ((w != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
 }
+
+// Sink of the fused kernels: the tail of traceAxion (rt:2135-2221) + prepareHeatmap (rt:839-842) for one axion mass,
+// applied where the ray's outcome becomes known. Sums live in the caller's registers, exit counts in the warp's
+// shared-memory counters.
+struct ImageSink {
+  static constexpr bool kFold = true;
+  const FastTables& T;
+  double m2;
+  double* __restrict__ image;
+  double* __restrict__ imageW2;
+  WarpCounters& wc;
+  unsigned int &nPassed, &nTill;
+  double &sumW, &sumW2, &sumX, &sumY, &sumR;
+  __device__ __forceinline__ void fail(int code) { atomicAdd(&wc.n_exit[code], 1u); }
+  __device__ __forceinline__ void hit(const RayResult& h) {
+    const double w0 = h.wPre;   // conversion probability already folded in
+    if (w0 != 0.0) ++nTill;                                   // passedTillWindow rt:2135-2136
+    if (h.clamped) atomicAdd(&wc.n_clamped, 1u);
+    if (h.windowMiss) { atomicAdd(&wc.n_exit[SART_EXIT_WINDOW_APERTURE], 1u); return; }
+    const double wd = w0 * h.wPost;
+    if (wd != 0.0) {                                          // passed rt:2220
+      ++nPassed;
+      sumW += wd; sumW2 += wd * wd; sumX += h.x; sumY += h.y; sumR += h.r;
+      if (h.bin >= 0) {
+        atomicAdd(image + h.bin, wd);
+        atomicAdd(imageW2 + h.bin, wd * wd);
+      }
+      if (T.rad.w) rad_add(T.rad, h.r, wd);
+    } else {
+      atomicAdd(&wc.n_exit[SART_EXIT_ZERO_WEIGHT], 1u);
+    }
+  }
+};
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
 template <bool kWolter>
@@ -617,27 +694,14 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
 
+  ImageSink sink{T, mAxion2, image, imageW2, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
-    RayResult r;
-    trace_one<kWolter, true>(P, T, S, seed, first + i, mAxion2, r);
     ++nIter;
-    int code = r.code;
-    double wd = 0.0;
-    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
-    if (code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
-    if ((code & SART_CODE_MASK) == SART_EXIT_PASSED) {
-      ++nPassed;
-      sumW += wd; sumW2 += wd * wd; sumX += r.x; sumY += r.y; sumR += r.r;
-      if (r.bin >= 0) {
-        atomicAdd(image + r.bin, wd);
-        atomicAdd(imageW2 + r.bin, wd * wd);
-      }
-      if (T.rad.w) rad_add(T.rad, r.r, wd);
-    } else {
-      atomicAdd(&wc[warp].n_exit[code & SART_CODE_MASK], 1u);
-    }
-    if (code & SART_FLAG_INTERP_CLAMPED) atomicAdd(&wc[warp].n_clamped, 1u);
+    Rec rec;
+    const int code = stage_a<kWolter>(P, T, S, seed, first + i, rec);
+    if (code >= 0) { sink.fail(code); continue; }
+    stage_b<kWolter>(P, T, S, rec, sink);
   }
   // ---- block reduction and flush
   for (int o = 16; o > 0; o >>= 1) {
@@ -699,6 +763,7 @@ k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_const
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  ImageSink sink{T, mAxion2, image, imageW2, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   uint64_t base = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31);   // warp-uniform
   int qn = 0;                                                              // warp-uniform queue fill
   for (;;) {
@@ -729,24 +794,7 @@ k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_const
       rec.x0 = Q.x0[pos]; rec.y0 = Q.y0[pos]; rec.tx = Q.tx[pos]; rec.ty = Q.ty[pos]; rec.path2 = Q.path2[pos];
       const int meta = Q.meta[pos];
       rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
-      RayResult r;
-      stage_b<kWolter, true>(P, T, S, rec, mAxion2, r);
-      int code = r.code;
-      double wd = 0.0;
-      if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
-      if (code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
-      if ((code & SART_CODE_MASK) == SART_EXIT_PASSED) {
-        ++nPassed;
-        sumW += wd; sumW2 += wd * wd; sumX += r.x; sumY += r.y; sumR += r.r;
-        if (r.bin >= 0) {
-          atomicAdd(image + r.bin, wd);
-          atomicAdd(imageW2 + r.bin, wd * wd);
-        }
-        if (T.rad.w) rad_add(T.rad, r.r, wd);
-      } else {
-        atomicAdd(&wc[warp].n_exit[code & SART_CODE_MASK], 1u);
-      }
-      if (code & SART_FLAG_INTERP_CLAMPED) atomicAdd(&wc[warp].n_clamped, 1u);
+      stage_b<kWolter>(P, T, S, rec, sink);
     }
     qn -= take;
     __syncwarp();
@@ -909,8 +957,8 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
 }
 
 size_t smem_bytes(const FastParams& P) {
-  return size_t(P.nShells) * sizeof(ShellFast) + size_t((P.nRadii + 1) & ~1) * 8 + size_t(kGuide) * 4 +
-         ((size_t(P.nShellGuide) + 15) & ~size_t(15)) + kWarps * sizeof(WarpCounters);
+  return align16(size_t(P.nShells) * sizeof(ShellFast)) + size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2 +
+         align16(size_t(P.nShellGuide)) + kWarps * sizeof(WarpCounters);
 }
 
 }  // namespace fast
