@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays-per-step", type=float, default=1e9)
-    ap.add_argument("--precision", choices=["exact", "fast"], default=None)
+    ap.add_argument("--precision", choices=["exact", "fast", "f32"], default=None)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -318,7 +318,7 @@ def run_ours(args):
     setup = rt.newExperimentSetup("CAST", "InGrid2018", "vacuum", "LLNL", 0)
     fs = rt.FullRaytraceSetup(setup, tb)
     tr = rt.RayTracer(fs, local)
-    tr.set_precision(1 if precision == "fast" else 0)
+    tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[precision])
     table_upload_s = time.perf_counter() - t0
 
     stream = torch.cuda.ExternalStream(tr.stream, device=local)

@@ -241,7 +241,9 @@ void sart_destroy(sart_handle_t* h);
 int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup);
 /* Axion masses for the buffer-gas scan; default is the single value setup.consts.mAxion (rt:255). */
 int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV);
-/* 0 = "exact" FP64 pipeline (bit-faithful classification), 1 = "fast" mixed FP32 pipeline. */
+/* 0 = "exact": FP64, the reference's operation order (bit-faithful hit/miss classification);
+ * 1 = "fast": FP64 algebra on (point, slopes) + FP32 weights (closer to exact arithmetic than the reference itself);
+ * 2 = "f32": the same formulation with FP32 geometry (positions to ~1e-4 mm, the reference's own rounding level). */
 int sart_set_precision(sart_handle_t* h, int mode);
 /* Fast mode only: 1 = compact the rays that survive bore, pipes, vetoes and glass fronts into full warps before the
  * mirror stage (pays off when most rays are clipped, e.g. BabyIAXO + XMM); 0 = one ray per lane throughout. Results are

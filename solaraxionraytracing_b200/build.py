@@ -25,6 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 UNITS = [
     ("kernels_exact.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
     ("kernels_fast.cu", []),
+    ("kernels_f32.cu", []),
     ("kernels_util.cu", []),
     ("kernels_emission.cu", []),
     ("api.cu", []),

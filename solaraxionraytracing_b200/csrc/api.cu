@@ -201,6 +201,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     // layout: shells | shell guide (4 KiB) | lut | gas lut | radius guide | energy guide | reflE
     size_t off = 0;
     h->fast_shell_off = off; off += align256(shf.size() * sizeof(fast::ShellFast));
+    h->fast_shell32_off = off; off += align256(size_t(SART_MAX_SHELLS) * sizeof(fast::ShellF32));
     h->fast_sguide_off = off; off += 4096;
     h->fast_lut_off = off; off += align256(lut.size() * sizeof(fast::EnergyLUT));
     h->fast_glut_off = off; off += align256(glut.size() * sizeof(fast::GasLUT));
@@ -229,12 +230,13 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     }
     // reflectivity interpolated along energy at each tabulated energy
     if (nCoat > 0) {
-      std::vector<float> re(size_t(nCoat) * reflPlane);
+      std::vector<float> re(size_t(nCoat) * reflPlane), line(size_t(P.nAngles));
       for (int c = 0; c < nCoat; ++c) {
         const float* z = h->h_refl32.data() + size_t(c) * P.nAngles * P.nReflEnergies;
-        for (int i = 0; i <= nE; ++i)
-          fast::refl_at_energy(P, z, i < nE ? std::max(0.03, h->h_energies[i]) : h->setup.testSource.energy,
-                               re.data() + size_t(c) * reflPlane + size_t(i) * reflRow);
+        for (int i = 0; i <= nE; ++i) {
+          fast::refl_at_energy(P, z, i < nE ? std::max(0.03, h->h_energies[i]) : h->setup.testSource.energy, line.data());
+          std::copy(line.begin(), line.end(), re.begin() + size_t(c) * reflPlane + size_t(i) * reflRow);
+        }
       }
       SART_CUDA(cudaMemcpy(base + h->fast_refl_off, re.data(), re.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -249,17 +251,22 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     F.glut = reinterpret_cast<const fast::GasLUT*>(base + h->fast_glut_off);
     F.reflE = reinterpret_cast<const float*>(base + h->fast_refl_off);
     F.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
+    F.shells32 = reinterpret_cast<const fast::ShellF32*>(base + h->fast_shell32_off);
     F.shellGuide = reinterpret_cast<const uint8_t*>(base + h->fast_sguide_off);
   } else if (nCoat > 0) {
     // setup update: only the X-ray-source row (index nE) of each coating can have changed
-    std::vector<float> row(reflRow);
+    std::vector<float> row(reflRow), line(size_t(P.nAngles));
     for (int c = 0; c < nCoat; ++c) {
-      fast::refl_at_energy(P, h->h_refl32.data() + size_t(c) * P.nAngles * P.nReflEnergies, h->setup.testSource.energy, row.data());
+      fast::refl_at_energy(P, h->h_refl32.data() + size_t(c) * P.nAngles * P.nReflEnergies, h->setup.testSource.energy, line.data());
+      std::copy(line.begin(), line.end(), row.begin());
       SART_CUDA(cudaMemcpy(base + h->fast_refl_off + (size_t(c) * reflPlane + size_t(nE) * reflRow) * sizeof(float),
                            row.data(), reflRow * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
+  std::vector<fast::ShellF32> sh32(SART_MAX_SHELLS);
+  fast::derive_f32(h->fparams, shf.data(), h->setup.telescope.nShells, &h->geo32, sh32.data());
   SART_CUDA(cudaMemcpy(base + h->fast_shell_off, shf.data(), shf.size() * sizeof(fast::ShellFast), cudaMemcpyHostToDevice));
+  SART_CUDA(cudaMemcpy(base + h->fast_shell32_off, sh32.data(), sh32.size() * sizeof(fast::ShellF32), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_lut_off, lut.data(), lut.size() * sizeof(fast::EnergyLUT), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_glut_off, glut.data(), glut.size() * sizeof(fast::GasLUT), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_sguide_off, sguide.data(), sguide.size(), cudaMemcpyHostToDevice));
@@ -413,7 +420,7 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
                             shells.size() * sizeof(ShellF64), cudaMemcpyHostToDevice, h->stream));
   SART_CUDA(cudaStreamSynchronize(h->stream));
   if ((rc = upload_fast(h, nullptr))) return rc;
-  if (h->precision == 1 && !h->fast_ok) h->precision = 0;
+  if (h->precision >= 1 && !h->fast_ok) h->precision = 0;
   if ((rc = autotune(h))) return rc;
   if (h->n_masses == 1 && h->masses_default) {
     h->masses[0] = setup->consts.mAxion;
@@ -440,13 +447,13 @@ int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV) {
 
 int sart_set_precision(sart_handle_t* h, int mode) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
-  if (mode != 0 && mode != 1) return fail(SART_ERR_ARG, "unknown precision mode %d", mode);
-  if (mode == 1 && !h->fast_ok) return fail(SART_ERR_CONFIG, "fast pipeline unavailable for this setup: %s", h->fast_why);
+  if (mode < 0 || mode > 2) return fail(SART_ERR_ARG, "unknown precision mode %d", mode);
+  if (mode >= 1 && !h->fast_ok) return fail(SART_ERR_CONFIG, "fast pipeline unavailable for this setup: %s", h->fast_why);
   h->precision = mode;
   return SART_OK;
 }
 
-int sart_has_precision(int mode) { return mode == 0 || mode == 1; }
+int sart_has_precision(int mode) { return mode >= 0 && mode <= 2; }
 
 int sart_set_compaction(sart_handle_t* h, int mode) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
@@ -607,10 +614,13 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
   if ((rc = ensure_stage(h, outBytes))) return rc;
   sart_ray_out_t dev;
   carve_out(static_cast<unsigned char*>(h->d_stage), n, *out, &dev);
-  if (h->precision == 1) {
-    // fast mode fills x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
+  if (h->precision >= 1) {
+    // the throughput modes fill x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
     SART_CUDA(cudaMemsetAsync(h->d_stage, 0, outBytes, h->stream));
-    SART_CUDA(launch_mc_rays_fast(h->fparams, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
+    if (h->precision == 2)
+      SART_CUDA(launch_mc_rays_f32(h->fparams, h->geo32, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
+    else
+      SART_CUDA(launch_mc_rays_fast(h->fparams, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
   } else {
     SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], first_ray, n, seed, dev, h->stream));
   }
@@ -620,9 +630,14 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   DeviceGuard dg(h->device);
-  if (h->precision == 1 && h->n_masses > 1) {
+  if (h->precision >= 1 && h->n_masses > 1) {   // the mass scan has one implementation (FP64 algebra) for modes 1 and 2
     SART_CUDA(launch_mc_image_fast_masses(h->fparams, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays, seed,
                                           h->d_image, h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+    return SART_OK;
+  }
+  if (h->precision == 2) {
+    SART_CUDA(launch_mc_image_f32(h->fparams, h->geo32, h->ftables, h->masses[0], first_ray, n_rays, seed, h->d_image,
+                                  h->d_image_w2, h->d_counters, h->sm_count, h->compact != 0, h->stream));
     return SART_OK;
   }
   if (h->precision == 1) {
@@ -756,10 +771,18 @@ int sart_angular_scan(sart_handle_t* h, int n_angles, const double* angles_deg, 
     Params P;
     rederive_params(h, s, &P);
     const uint64_t first = first_ray + uint64_t(i) * n_rays_per_angle;   // every scan point traces its own rays, like the reference
-    if (h->precision == 1) {
+    if (h->precision >= 1) {
       fast::FastParams F;
       fast::derive_params(s, P, &F);
       F.shellRhoMin = h->fparams.shellRhoMin; F.shellInvStep = h->fparams.shellInvStep; F.nShellGuide = h->fparams.nShellGuide;
+      if (h->precision == 2) {
+        fast::Geo32 G;
+        std::vector<fast::ShellF32> unused(SART_MAX_SHELLS);
+        fast::derive_f32(F, nullptr, 0, &G, unused.data());
+        SART_CUDA(launch_mc_image_f32(F, G, ft, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
+                                      dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->compact != 0, h->stream));
+        continue;
+      }
       SART_CUDA(launch_mc_image_fast(F, ft, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
                                      dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->compact != 0, h->stream));
     } else {

@@ -75,6 +75,35 @@ void derive_shells(const sart_setup_t& s, const ShellF64* a, ShellFast* out) {
   }
 }
 
+// Single-precision blocks of precision mode 2, rounded from the FP64 ones.
+void derive_f32(const FastParams& f, const ShellFast* a, int nShells, Geo32* g, ShellF32* out) {
+  std::memset(g, 0, sizeof *g);
+  g->radiusCB = float(f.radiusCB); g->radiusCB2 = float(f.radiusCB2); g->lengthB = float(f.lengthB);
+  g->lengthB2 = float(f.lengthB * f.lengthB); g->lengthBplusSun = float(f.lengthB + f.sunDist); g->radiusSun = float(f.radiusSun);
+  g->dzExitCB = float(f.dzExitCB); g->dzPipe1 = float(f.dzPipe1); g->dzPipe2 = float(f.dzPipe2); g->rPipe12 = float(f.rPipe12);
+  g->cosTX = float(f.cosTX); g->sinTX = float(f.sinTX); g->cosTY = float(f.cosTY); g->sinTY = float(f.sinTY);
+  g->halfLenTel = float(f.halfLenTel); g->oeX = float(f.oeX); g->oeY = float(f.oeY); g->zExitCBtel = float(f.zExitCBtel);
+  g->lMirror = float(f.lMirror); g->cosPipe = float(f.cosPipe); g->sinPipe = float(f.sinPipe); g->dShift = float(f.dShift);
+  g->lateralShift = float(f.lateralShift); g->transversalShift = float(f.transversalShift);
+  g->radiusWindow2 = float(f.radiusWindow2); g->chipCX = float(f.chipCX); g->chipCY = float(f.chipCY);
+  g->cosTheta = float(f.cosTheta); g->sinTheta = float(f.sinTheta); g->stripDist = float(f.stripDist);
+  g->stripWidth = float(f.stripWidth); g->invStripPitch = float(f.invStripPitch); g->invBinX = float(f.invBinX);
+  g->invBinY = float(f.invBinY); g->shellRhoMin = float(f.shellRhoMin); g->shellInvStep = float(f.shellInvStep);
+  g->srcX = float(f.srcX); g->srcY = float(f.srcY); g->srcRadius = float(f.srcRadius); g->srcRadius2 = float(f.srcRadius2);
+  g->invSrcDz = float(1.0 / (f.lengthB - f.srcZ)); g->colDz = float(f.colDz);
+  for (int j = 0; j < nShells; ++j) {
+    const ShellFast& s = a[j];
+    ShellF32& o = out[j];
+    std::memset(&o, 0, sizeof o);
+    o.R1 = float(s.R1); o.R1pT = float(s.R1pT); o.tan1 = float(s.tan1); o.zmax1 = float(s.zmax1);
+    o.cosb = float(s.cosb); o.sinb = float(s.sinb); o.r4 = float(s.r4); o.tan2 = float(s.tan2); o.dm = float(s.dm);
+    o.zmax2 = float(s.zmax2); o.cos3b = float(s.cos3b); o.sin3b = float(s.sin3b); o.ddWin = float(s.ddWin);
+    o.p_e = float(s.p_e); o.p_R0 = float(std::sqrt(std::max(s.p_c0, 0.0))); o.p_r3sq = float(s.p_r3sq); o.p_r3tan = float(s.p_r3tan);
+    o.h_e = float(s.h_e); o.h_g = float(s.h_g); o.h_r3sq = float(s.h_r3sq); o.h_r3tan = float(s.h_r3tan);
+    o.h_inv_nden = float(s.h_inv_nden); o.coat = s.coat;
+  }
+}
+
 // Uniform radial grid over [R1[0] - step, R1[last]]: guide[b] = smallest j with R1[j] > lower edge of bucket b, and the
 // step is at most half the smallest shell spacing, so the kernel's forward scan from guide[b] takes 0 or 1 steps.
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide) {

@@ -1,0 +1,202 @@
+// fast_common.cuh — pieces shared by the throughput pipelines (kernels_fast.cu: FP64 algebra, kernels_f32.cu: FP32
+// geometry): MUFU-seeded arithmetic, the integer inverse-CDF search, the reflectivity lookup, the conversion probability,
+// the per-ray outcome record and the sinks that turn an outcome into counters / image contributions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cfloat>
+
+#include "fast_params.h"
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace sart {
+namespace fast {
+
+#ifndef SART_FAST_BLOCK
+#define SART_FAST_BLOCK 256
+#endif
+#ifndef SART_FAST_MINBLOCKS
+#define SART_FAST_MINBLOCKS 3
+#endif
+#ifndef SART_LAZY_THR
+#define SART_LAZY_THR 0   // 1: second group of four energy thresholds loaded only by the lanes that need it (measured: neutral)
+#endif
+constexpr int kBlock = SART_FAST_BLOCK;
+constexpr int kWarps = kBlock / 32;
+
+// ---- FP64 divide / sqrt from FP32 seeds ---------------------------------------------------------------------
+// MUFU.RCP / MUFU.RSQ seeds (2^-23 relative); the *_rn intrinsics and rsqrtf() expand to range checks + slow paths.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r = double(rcp_approx(float(x)));
+  const double e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y = double(rsqrt_approx(float(x)));
+  const double h = 0.5 * x * y;
+  return fma(y, fma(-h, y, 0.5), y);  // y * (1.5 - 0.5 x y^2)
+}
+
+// sin/cos(2 pi u), u in [0, 1): MUFU.SIN/COS on the argument shifted into [-pi, pi) where their absolute error is
+// 2^-21.4; these only set the sampled emission direction / exit-disc point (a 5e-7 relative shift of a random point).
+__device__ __forceinline__ void sincos_2pi(float u, float& s, float& c) {
+  const float t = 6.283185307179586f * (u - 0.5f);
+  s = -__sinf(t);
+  c = -__cosf(t);
+}
+// asin / atan for small arguments (grazing angles <= 0.1 rad, slopes <= 0.1): odd series, relative error < 1e-7.
+__device__ __forceinline__ float asin_small(float x) {
+  if (fabsf(x) > 0.1f) return asinf(x);
+  const float x2 = x * x;
+  return x * fmaf(x2, fmaf(x2, 0.075f, 0.16666667f), 1.0f);
+}
+__device__ __forceinline__ float atan_small(float x) {
+  if (fabsf(x) > 0.1f) return atanf(x);
+  const float x2 = x * x;
+  return x * fmaf(x2, fmaf(x2, 0.2f, -0.33333334f), 1.0f);
+}
+
+struct D3 { double x, y, z; };
+
+__device__ __forceinline__ void rad_add(const RadialHist& h, double r, double w) {
+  int b = int(r * h.invStep);
+  b = b < 0 ? 0 : (b > h.nbins - 1 ? h.nbins - 1 : b);
+  atomicAdd(h.w + b, w);
+  atomicAdd(h.n + b, 1ull);
+}
+
+// ---- shared memory layout -----------------------------------------------------------------------------------
+struct WarpCounters { unsigned int n_exit[16]; unsigned int n_clamped; unsigned int pad[3]; };
+
+// lowerBound restricted to the guide window [lo, hi]
+__device__ __forceinline__ int lower_bound_window(const double* __restrict__ a, int lo, int hi, double key) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Number of the 4 ascending thresholds that are <= w.
+__device__ __forceinline__ int count_le(const uint4& t, uint32_t w) {
+  return int(w >= t.x) + int(w >= t.y) + int(w >= t.z) + int(w >= t.w);
+}
+// lowerBound over u32 thresholds beyond the 8 prefetched ones (windows wider than 8 entries: flat CDF tails)
+static __device__ __noinline__ int thr_search_tail(const uint32_t* __restrict__ thr, int from, int n, uint32_t w) {
+  int lo = from, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (w >= thr[mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Reflectivity at grazing angle alphaDeg from the row pre-interpolated at the ray's energy: linear in the angle.
+// (Variants measured on B200 and rejected: rows of overlapping 16-byte quads — one load per lookup, but the table grows by
+// a third and CAST+LLNL, whose tables already fill most of one L2 partition, loses 25 %; one aligned 16-byte load plus a
+// conditional second one — no gain over two 4-byte loads.)
+__device__ __forceinline__ float refl_lookup(const FastParams& P, const float* __restrict__ row, float alphaDeg, bool& clamped) {
+  float x = alphaDeg;
+  if (!(x >= P.angleMin)) { x = P.angleMin; clamped = true; }
+  if (!(x <= P.angleMax)) { x = P.angleMax; clamped = true; }
+  const float fx = (x - P.angleMin) * P.invReflDx;
+  int i = int(fx);
+  if (i > P.nAngles - 2) i = P.nAngles - 2;
+  const float z0 = __ldg(row + i), z1 = __ldg(row + i + 1);
+  return fmaf(fx - float(i), z1 - z0, z0);
+}
+
+// What trace_one knows about a ray. `code` is the exit code of a geometric early return, or -1 when the ray reached
+// the weight stage; then weight(m_a) = wPre * conv(m_a) * wPost (finish_ray), so a mass scan re-uses one traced ray.
+struct RayResult {
+  int code;
+  int bin;        // image bin or -1
+  int shell;
+  bool windowMiss, clamped;
+  float energy;
+  double wPre;    // reflectivity * cos(yaw) * He absorption        (everything before the window, without P(a->gamma))
+  double wPost;   // window or strongback * detector gas * exposure (0 when the window aperture is missed)
+  double x, y, r;
+  // conversion probability pieces: vacuum convVac = (g B L / 2)^2; gas: Gamma, L, exp(-Gamma L), exp(-Gamma L/2), 1/(2E)
+  float convVac, gasGamma, gasE1, gasE2, gasInv2E;
+  double gasL;
+};
+
+// Conversion probability for axion mass^2 m2 (computeMagnetTransmission rt:1582-1625 without the cos(ya) factor).
+__device__ __forceinline__ double conv_factor(const FastParams& P, float convVac, float gasGamma, float gasE1, float gasE2,
+                                              float gasInv2E, double gasL, double m2) {
+  if (P.flags & SART_CF_IGNORE_CONV_PROB) return 1.0;
+  if (P.stage == SART_SK_VACUUM) return double(convVac);
+  const double q = fabs(P.gasMgamma2 - m2) * double(gasInv2E);   // momentumTransfer am:63-68
+  double ph = q * gasL;   // phase reduced in FP64 before the FP32 cosine
+  ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);
+  const float cq = __cosf(float(ph));
+  const double g = double(gasGamma);
+  const double term2 = rcp_nr(fma(q, q, 0.25 * g * g));
+  return P.gasTerm1 * term2 * double(1.0f + gasE1 - 2.0f * gasE2 * cq);
+}
+// Tail of traceAxion for one axion mass: exit code | flags and the final weight.
+template <bool kFolded>
+__device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& r, double m2, double& w) {
+  const double w0 = kFolded ? r.wPre
+                            : r.wPre * conv_factor(P, r.convVac, r.gasGamma, r.gasE1, r.gasE2, r.gasInv2E, r.gasL, m2);
+  int flags = (w0 != 0.0) ? SART_FLAG_PASSED_TILL_WINDOW : 0;
+  if (r.clamped) flags |= SART_FLAG_INTERP_CLAMPED;
+  w = 0.0;
+  if (r.windowMiss) return SART_EXIT_WINDOW_APERTURE | flags;
+  w = w0 * r.wPost;
+  return ((w != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
+}
+
+// Sink that keeps the outcome as a RayResult (per-ray records, mass scan).
+template <bool kFoldT>
+struct RecordSink {
+  static constexpr bool kFold = kFoldT;
+  RayResult& out;
+  double m2;
+  __device__ __forceinline__ void fail(int code) {
+    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1; out.energy = 0.f;
+    out.x = out.y = out.r = 0.0; out.wPre = out.wPost = 0.0;
+  }
+  __device__ __forceinline__ void hit(const RayResult& h) { out = h; out.code = -1; }
+};
+
+// Sink of the fused kernels: the tail of traceAxion (rt:2135-2221) + prepareHeatmap (rt:839-842) for one axion mass,
+// applied where the ray's outcome becomes known. Sums live in the caller's registers, exit counts in the warp's
+// shared-memory counters.
+struct ImageSink {
+  static constexpr bool kFold = true;
+  const FastTables& T;
+  double m2;
+  double* __restrict__ image;
+  double* __restrict__ imageW2;
+  WarpCounters& wc;
+  unsigned int &nPassed, &nTill;
+  double &sumW, &sumW2, &sumX, &sumY, &sumR;
+  __device__ __forceinline__ void fail(int code) { atomicAdd(&wc.n_exit[code], 1u); }
+  __device__ __forceinline__ void hit(const RayResult& h) {
+    const double w0 = h.wPre;   // conversion probability already folded in
+    if (w0 != 0.0) ++nTill;                                   // passedTillWindow rt:2135-2136
+    if (h.clamped) atomicAdd(&wc.n_clamped, 1u);
+    if (h.windowMiss) { atomicAdd(&wc.n_exit[SART_EXIT_WINDOW_APERTURE], 1u); return; }
+    const double wd = w0 * h.wPost;
+    if (wd != 0.0) {                                          // passed rt:2220
+      ++nPassed;
+      sumW += wd; sumW2 += wd * wd; sumX += h.x; sumY += h.y; sumR += h.r;
+      if (h.bin >= 0) {
+        atomicAdd(image + h.bin, wd);
+        atomicAdd(imageW2 + h.bin, wd * wd);
+      }
+      if (T.rad.w) rad_add(T.rad, h.r, wd);
+    } else {
+      atomicAdd(&wc.n_exit[SART_EXIT_ZERO_WEIGHT], 1u);
+    }
+  }
+};
+
+
+}  // namespace fast
+}  // namespace sart

@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include <vector_types.h>
+
 #include "device_params.h"
 
 namespace sart {
@@ -45,6 +47,28 @@ struct FastParams {
   int32_t nShellGuide, rotated;
 };
 
+// ---- single-precision pipeline (kernels_f32.cu): the same blocks rounded to FP32, plus a few derived values that
+// keep its arithmetic free of cancellation (radii instead of squared radii: C = (rho - R)(rho + R))
+struct ShellF32 {
+  float R1, R1pT, tan1, zmax1, cosb, sinb;
+  float r4, tan2, dm, zmax2, cos3b, sin3b;
+  float ddWin;
+  float p_e, p_R0, p_r3sq, p_r3tan;                        // p_R0 = sqrt(r3^2 + e l): paraboloid radius at z = 0
+  float h_e, h_g, h_r3sq, h_r3tan, h_inv_nden;
+  int32_t coat;
+};
+static_assert(sizeof(ShellF32) == 92, "23 words: an odd stride keeps shared-memory rows off the same banks");
+
+struct Geo32 {
+  float radiusCB, radiusCB2, lengthB, lengthB2, lengthBplusSun, radiusSun;
+  float dzExitCB, dzPipe1, dzPipe2, rPipe12;
+  float cosTX, sinTX, cosTY, sinTY, halfLenTel, oeX, oeY, zExitCBtel;
+  float lMirror, cosPipe, sinPipe, dShift, lateralShift, transversalShift;
+  float radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invStripPitch, invBinX, invBinY;
+  float shellRhoMin, shellInvStep;
+  float srcX, srcY, srcRadius, srcRadius2, invSrcDz, colDz;
+};
+
 struct EnergyLUT {  // one record per tabulated energy index (16 B, one LDG.128)
   float E, Twindow, Tstrongback, Agas;
 };
@@ -68,6 +92,7 @@ struct FastTables {
   // the per-ray lookup is then linear in the grazing angle only (same value as the bilinear form of rt:1567-1578)
   const float* reflE;
   const ShellFast* shells;    // [nShells]
+  const ShellF32* shells32;   // [nShells] the same records in single precision (kernels_f32.cu)
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
   RadialHist rad;             // optional (w == nullptr: off)
 };

@@ -34,6 +34,13 @@ cudaError_t launch_mc_rays_fast(const fast::FastParams& P, const fast::FastTable
 cudaError_t launch_emission_rates(int nR, int nE, const double* dTemp, const double* dRho, const double* dFrac,
                                   const double* dEnergies, unsigned processes, double gae, double gagamma, double ganuclei,
                                   void* dState /* 80 B per radius */, double* dEmRates, cudaStream_t s);
+// ---- single-precision pipeline (kernels_f32.cu)
+cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
+                                uint64_t first, uint64_t nRays, uint64_t seed, double* image, double* imageW2,
+                                sart_counters_t* counters, int smCount, bool compact, cudaStream_t s);
+cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
+                               uint64_t first, uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount,
+                               cudaStream_t s);
 cudaError_t launch_heatmap(int rows, int cols, double start_x, double step_x, double start_y, double step_y, size_t n,
                            const double* X, const double* Y, const double* W, double norm, double* result,
                            unsigned long long* nBad, cudaStream_t s);

@@ -1,0 +1,680 @@
+// kernels_f32.cu — the single-precision fused Monte Carlo kernel (precision mode 2), sm_100a.
+//
+// Same decision sequence and weights as kernels_fast.cu (mode 1), with the geometry in FP32 instead of FP64. Mode 1's
+// profile on B200 has the FP64 pipe and the XU pipe (MUFU seeds + FP64<->FP32 conversions around them) as its two
+// busiest pipes and 76-80 registers per thread; FP32 runs on the 4x wider FMA pipe, needs no conversions and half
+// the registers for the ray state. What makes FP32 sufficient here:
+//   * the ray is (point, slopes) with |slope| < 0.1 and coordinates < 400 mm, so FP32 rounding is ~1e-5 mm in position
+//     and ~1e-9 in direction (a few 1e-5 mm over the 1.5-7.5 m to the detector) — at or below the 1e-4 mm rounding
+//     noise the reference itself carries from intersecting lines between points 1.5e14 mm apart;
+//   * every difference of squares that decides a root or a hit is taken in factored form, (rho - R)(rho + R) with rho
+//     from one rsqrt, instead of rho^2 - R^2, so no quadratic coefficient loses digits to cancellation;
+//   * reciprocals / square roots are MUFU seeds plus one Newton step in FP32 (2-3 FFMA).
+// Sampling (integer inverse-CDF search, Philox) and weights (FP32 factors, FP64 product and accumulation) are the very
+// same code as mode 1 (fast_common.cuh), so a ray has the same emission shell, energy and exit-disc point in all modes.
+#include "fast_common.cuh"
+
+namespace sart {
+namespace fast {
+
+__device__ __forceinline__ float rcpf_nr(float x) {
+  const float r = rcp_approx(x);
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ float rsqrtf_nr(float x) {
+  const float y = rsqrt_approx(x);
+  const float h = 0.5f * x * y;
+  return fmaf(y, fmaf(-h, y, 0.5f), y);
+}
+
+struct F3 { float x, y, z; };
+
+struct Smem32 {
+  const ShellF32* shell;
+  const uint32_t* radThr;
+  const uint16_t* radGuide;
+  const uint8_t* shellGuide;
+};
+__device__ __forceinline__ void smem_layout32(const FastParams& P, unsigned char* base, Smem32& s, unsigned char*& tail) {
+  size_t off = 0;
+  s.shell = reinterpret_cast<const ShellF32*>(base + off); off += (size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15);
+  s.radThr = reinterpret_cast<const uint32_t*>(base + off); off += size_t(thr_pitch(P.nRadii)) * 4;
+  s.radGuide = reinterpret_cast<const uint16_t*>(base + off); off += size_t(kRadGuide) * 2;
+  s.shellGuide = base + off; off += (size_t(P.nShellGuide) + 15) & ~size_t(15);
+  tail = base + off;
+}
+__device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTables& T, const Smem32& s) {
+  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellF32) / 4); i += kBlock)
+    reinterpret_cast<float*>(const_cast<ShellF32*>(s.shell))[i] = reinterpret_cast<const float*>(T.shells32)[i];
+  if (P.nRadii > 0) {
+    for (int i = threadIdx.x; i < thr_pitch(P.nRadii); i += kBlock) const_cast<uint32_t*>(s.radThr)[i] = T.radiusThr[i];
+    for (int i = threadIdx.x; i < kRadGuide / 8; i += kBlock)
+      reinterpret_cast<uint4*>(const_cast<uint16_t*>(s.radGuide))[i] = __ldg(reinterpret_cast<const uint4*>(T.radiusGuide) + i);
+  }
+  for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
+}
+
+// Root choice of findPos* (rt:646-658) for A t^2 + 2 hb t + C = 0, as in kernels_fast.cu: q = -(hb + sign(hb) sq), the
+// roots are q/A (large, metres away) and C/q. Returns t with lo < t dz < hi.
+static __device__ __noinline__ bool pick_root_slow32(float A, float q, float C, bool first_is_qA, float dz, float lo,
+                                                     float hi, float& t) {
+  auto in_range = [&](float num, float den) {
+    const float nd = num * dz;
+    return den > 0.0f ? (nd > lo * den && nd < hi * den) : (nd < lo * den && nd > hi * den);
+  };
+  const bool okA = in_range(q, A), okC = in_range(C, q);
+  float num, den;
+  if (first_is_qA ? okA : okC) { num = first_is_qA ? q : C; den = first_is_qA ? A : q; }
+  else if (first_is_qA ? okC : okA) { num = first_is_qA ? C : q; den = first_is_qA ? q : A; }
+  else return false;
+  t = num / den;
+  return true;
+}
+__device__ __forceinline__ bool pick_root32(float A, float hb, float C, float dz, float lo, float hi, float& t) {
+  const float disc = fmaf(hb, hb, -A * C);
+  if (!(disc >= 0.0f)) return false;
+  const float sq = disc > 1e-30f ? disc * rsqrtf_nr(disc) : 0.0f;
+  const float q = -(hb + copysignf(sq, hb));
+  if (fabsf(q * dz) < fmaxf(fabsf(lo), fabsf(hi)) * fabsf(A)) return pick_root_slow32(A, q, C, hb >= 0.0f, dz, lo, hi, t);
+  const float ts = C * rcpf_nr(q);
+  const float zs = ts * dz;
+  t = ts;
+  return zs > lo && zs < hi;
+}
+
+// Reflection of unit vector v off unit normal n (rt:762-780 without trigonometry); returns |n.v| = sin(alpha).
+__device__ __forceinline__ float reflect32(F3 n, F3& v) {
+  const float s = fmaf(n.x, v.x, fmaf(n.y, v.y, n.z * v.z));
+  const float as = fabsf(s);
+  const float f = fmaf(2.0f * as, s, fmaf(-2.0f * s, s, 1.0f));
+  v.x = fmaf(v.x, f, -2.0f * as * n.x);
+  v.y = fmaf(v.y, f, -2.0f * as * n.y);
+  v.z = fmaf(v.z, f, -2.0f * as * n.z);
+  return as;
+}
+
+struct Rec32 {
+  float x0, y0, tx, ty;   // pointEntranceXRT (telescope frame, z = 0) and slopes dx/dz, dy/dz
+  float rho0;             // radialDist
+  float path2;            // pathCB^2
+  int hitLayer, eIdx;
+  bool clamped;
+};
+
+// Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
+template <bool kWolter>
+__device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
+                                         uint64_t seed, uint64_t ray, Rec32& rec) {
+  const ShellF32* __restrict__ sShell = S.shell;
+  uint32_t w[6];
+  ray_words(seed, ray, w);
+  constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
+  bool clamped = false;
+
+  float ex, ey, sx, sy;
+  int eIdx;
+  int e0 = 0;
+  const uint32_t* eRow = nullptr;
+  if (!P.testXray) {
+    int rIdx;
+    {
+      const uint32_t wr = w[2];
+      const int r0 = int(S.radGuide[wr >> (32 - kRadGuideBits)]) & ~3;
+      rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
+      if (rIdx == r0 + 4) {
+        rIdx += count_le(*reinterpret_cast<const uint4*>(S.radThr + r0 + 4), wr);
+        if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, P.nRadii, wr);
+      }
+      if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
+      if (rIdx > P.nRadii - 1) rIdx = P.nRadii - 1;
+    }
+    {
+      const uint32_t we = w[5];
+      e0 = int(__ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (we >> (32 - kEnGuideBits)))) & ~3;
+      eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
+    }
+    const float rs = (0.0015f + float(rIdx) * 0.0005f);
+    float s1, c1, s2, c2;
+    sincos_2pi(float(w[0]) * k2m32, s1, c1);
+    __sincosf(3.14159265358979f * (float(w[1]) * k2m32), &s2, &c2);
+    const float rsun = rs * G.radiusSun;
+    const float Ox = rsun * (c1 * s2), Oy = rsun * (s1 * s2), Ozr = rsun * c2;
+    float sd, cd;
+    sincos_2pi(float(w[4]) * k2m32, sd, cd);
+    const float rd = sqrtf((float(w[3]) + 0.5f) * k2m32);
+    ex = G.radiusCB * (rd * cd);
+    ey = G.radiusCB * (rd * sd);
+    const float invD = rcpf_nr(G.lengthBplusSun - Ozr);   // lengthB - O.z
+    sx = fmaf(ex, invD, -Ox * invD);
+    sy = fmaf(ey, invD, -Oy * invD);
+    eIdx = 0;
+  } else {
+    float sd, cd;
+    sincos_2pi(float(w[1]) * k2m32, sd, cd);
+    const float rd = sqrtf((float(w[0]) + 0.5f) * k2m32);
+    const float Ox = fmaf(G.srcRadius, rd * cd, G.srcX), Oy = fmaf(G.srcRadius, rd * sd, G.srcY);
+    if (P.parallelSource) {
+      ex = Ox + (0.5f * ((float(w[2]) + 0.5f) * k2m32) - 0.25f);
+      ey = Oy + (0.5f * ((float(w[3]) + 0.5f) * k2m32) - 0.25f);
+    } else {
+      sincos_2pi(float(w[3]) * k2m32, sd, cd);
+      const float r2 = sqrtf((float(w[2]) + 0.5f) * k2m32);
+      ex = G.radiusCB * (r2 * cd);
+      ey = G.radiusCB * (r2 * sd);
+    }
+    sx = (ex - Ox) * G.invSrcDz;
+    sy = (ey - Oy) * G.invSrcDz;
+    const float qx = fmaf(sx, G.colDz, Ox) - G.srcX, qy = fmaf(sy, G.colDz, Oy) - G.srcY;
+    eIdx = P.srcEIdx;
+    if (!(fmaf(qx, qx, qy * qy) < G.srcRadius2)) return SART_EXIT_COLLIMATOR;
+  }
+
+  // ================= bore and pipes rt:1813-1872
+  const float s2sum = fmaf(sx, sx, sy * sy);
+  const float p0x = fmaf(-sx, G.lengthB, ex), p0y = fmaf(-sy, G.lengthB, ey);
+  const bool hitEntrance = fmaf(p0x, p0x, p0y * p0y) < G.radiusCB2;
+  const float pex = fmaf(sx, G.dzExitCB, ex), pey = fmaf(sy, G.dzExitCB, ey);
+  const bool insideExit = fmaf(pex, pex, pey * pey) < G.radiusCB2;
+  if (!insideExit) return hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
+  float path2;
+  if (hitEntrance) {
+    path2 = G.lengthB2 * (1.0f + s2sum);
+  } else {
+    const float hb = fmaf(ex, sx, ey * sy), c = fmaf(ex, ex, ey * ey) - G.radiusCB2;
+    const float disc = fmaf(hb, hb, -s2sum * c);
+    const float sq = disc > 1e-30f ? disc * rsqrtf_nr(disc) : 0.0f;
+    const float t1 = (hb >= 0.0f) ? -(hb + sq) * rcpf_nr(s2sum) : c * rcpf_nr(sq - hb);
+    path2 = t1 * t1 * (1.0f + s2sum);
+  }
+  {
+    const float qx = fmaf(sx, G.dzPipe1, ex), qy = fmaf(sy, G.dzPipe1, ey);
+    if (!(fmaf(qx, qx, qy * qy) < G.rPipe12)) return SART_EXIT_CLIP_PIPE_VT3;
+  }
+  float x0 = fmaf(sx, G.dzPipe2, ex), y0 = fmaf(sy, G.dzPipe2, ey);
+  if (!(fmaf(x0, x0, y0 * y0) < G.rPipe12)) return SART_EXIT_CLIP_PIPE_XRT;  // quirk Q2
+  uint4 etA = make_uint4(0, 0, 0, 0);
+#if !SART_LAZY_THR
+  uint4 etB = etA;
+  if (eRow) etB = __ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4));
+#endif
+  if (eRow) etA = __ldg(reinterpret_cast<const uint4*>(eRow + e0));
+
+  // ================= telescope frame rt:1888-1905
+  float dx = sx, dy = sy, dz = 1.0f, z0 = 0.0f;
+  if (P.rotated) {
+    const float zt = 0.0f - G.halfLenTel;
+    const float xr = x0 * G.cosTX + zt * G.sinTX;
+    float zr = zt * G.cosTX - x0 * G.sinTX;
+    const float yr = y0 * G.cosTY - zr * G.sinTY;
+    zr = zr * G.cosTY + y0 * G.sinTY;
+    x0 = xr; y0 = yr; z0 = zr + G.halfLenTel;
+    const float ddx = dx * G.cosTX + dz * G.sinTX;
+    float ddz = dz * G.cosTX - dx * G.sinTX;
+    const float ddy = dy * G.cosTY - ddz * G.sinTY;
+    ddz = ddz * G.cosTY + dy * G.sinTY;
+    dx = ddx; dy = ddy; dz = ddz;
+  }
+  x0 -= G.oeX; y0 -= G.oeY;
+  const float invdz = (dz == 1.0f) ? 1.0f : rcpf_nr(dz);
+  const float tx = dx * invdz, ty = dy * invdz;
+  x0 = fmaf(-z0, tx, x0); y0 = fmaf(-z0, ty, y0);   // pointEntranceXRT
+  const float rho0sq = fmaf(x0, x0, y0 * y0);
+  const float invRho0 = rsqrtf_nr(rho0sq);
+  const float radialDist = rho0sq * invRho0;
+
+  // ================= opaque structures rt:1635-1704
+  if (kWolter) {
+    const bool xmm = P.telKind == SART_TK_XMM;
+    bool hit = false;
+    const float zs = xmm ? -85.0f : -35.0f;
+    const float phiF = acosf(x0 * invRho0) * 57.29577951308232f;
+    const float xs = fmaf(zs, tx, x0), ys = fmaf(zs, ty, y0);
+    const float phiS = acosf(xs * rsqrtf(xs * xs + ys * ys)) * 57.29577951308232f;
+    if (xmm) {
+      if (radialDist <= 64.7f) hit = true;
+      else if (radialDist < 151.6f && radialDist > (151.6f - 20.9f)) hit = true;
+      else {
+        const float a = fabsf(phiF - 22.5f * rintf(phiF * (1.0f / 22.5f)));
+        const float b = fabsf(phiS - 22.5f * rintf(phiS * (1.0f / 22.5f)));
+        hit = (a <= 1.145f) || (b <= 1.145f);
+      }
+    } else {
+      if (radialDist < 37.5f) hit = true;
+      else {
+        const float a = fabsf(phiF - 60.0f * rintf(phiF * (1.0f / 60.0f)));
+        const float b = fabsf(phiS - 60.0f * rintf(phiS * (1.0f / 60.0f)));
+        hit = (a <= 3.75f) || (b <= 3.75f);
+      }
+    }
+    if (hit) return SART_EXIT_OPAQUE;
+  }
+
+  // ================= shell rt:1932-1957: uniform radial guide + at most one forward step
+  const int nS = P.nShells;
+  if (radialDist > sShell[nS - 1].R1) return SART_EXIT_OUTSIDE_SHELLS;
+  int hitLayer;
+  {
+    int b = int((radialDist - G.shellRhoMin) * G.shellInvStep);
+    b = b < 0 ? 0 : (b > P.nShellGuide - 1 ? P.nShellGuide - 1 : b);
+    hitLayer = S.shellGuide[b];
+    while (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;
+    if (!(sShell[hitLayer].R1 > radialDist)) return SART_EXIT_NO_MIRROR_HIT;
+    if (hitLayer > 0 && radialDist < sShell[hitLayer - 1].R1pT) {
+      if (radialDist > sShell[hitLayer - 1].R1) return SART_EXIT_GLASS_FRONT;
+    }
+  }
+  if (eRow) {
+    const uint32_t we = w[5];
+    eIdx = e0 + count_le(etA, we);
+    if (eIdx == e0 + 4) {   // ~1 ray in 8: the next four thresholds (loaded only by the lanes that need them)
+#if SART_LAZY_THR
+      eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4)), we);
+#else
+      eIdx += count_le(etB, we);
+#endif
+      if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, P.nEnergies, we);
+    }
+    if (we == 0xffffffffu)
+      eIdx = lower_bound_window(T.energyCDF + size_t(eRow - T.energyThr) / thr_pitch(P.nEnergies) * P.nEnergies, 0, P.nEnergies, u01(we));
+    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
+  }
+  rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.rho0 = radialDist; rec.path2 = path2;
+  rec.hitLayer = hitLayer; rec.eIdx = eIdx; rec.clamped = clamped;
+  return -1;
+}
+
+// Stage B in FP32: the two reflections, nickel / degenerate exits, detector plane, weights, window (rt:1971-2221).
+template <bool kWolter, class Sink>
+__device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
+                                          const Rec32& rec, Sink& sink) {
+  const ShellF32* __restrict__ sShell = S.shell;
+  RayResult out;
+  out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
+  const float x0 = rec.x0, y0 = rec.y0, tx = rec.tx, ty = rec.ty, rho0 = rec.rho0;
+  const int hitLayer = rec.hitLayer, eIdx = rec.eIdx;
+  bool clamped = rec.clamped;
+  const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);
+  const EnergyLUT el = {elv.x, elv.y, elv.z, elv.w};
+  const float t2sum = fmaf(tx, tx, ty * ty);
+  const float invLen = rsqrtf_nr(1.0f + t2sum);
+  const ShellF32& sh = sShell[hitLayer];
+  const float lM = G.lMirror;
+  const float below = hitLayer > 0 ? sShell[hitLayer - 1].R1pT : 0.0f;
+  const float xt = fmaf(x0, tx, y0 * ty);
+
+  // ================= mirror 1 rt:1983-2020. Ray: (x0 + tx z, y0 + ty z, z); C in factored form
+  float z1;
+  bool hit1;
+  if (kWolter) {   // paraboloid rho^2 = c0 - e z, c0 = R0^2
+    hit1 = pick_root32(t2sum, xt + 0.5f * sh.p_e, (rho0 - sh.p_R0) * (rho0 + sh.p_R0), 1.0f, 0.0f, sh.zmax1, z1);
+  } else {         // cone rho = r1 - tan(beta) z
+    hit1 = pick_root32(t2sum - sh.tan1 * sh.tan1, fmaf(sh.tan1, sh.R1, xt), (rho0 - sh.R1) * (rho0 + sh.R1), 1.0f, 0.0f,
+                       sh.zmax1, z1);
+  }
+  if (!hit1) {
+    int code = SART_EXIT_NO_MIRROR_HIT;
+    if (hitLayer > 0) {
+      const float zc = G.zExitCBtel;
+      const float xc = fmaf(zc, tx, x0), yc = fmaf(zc, ty, y0);
+      const float rc2 = fmaf(xc, xc, yc * yc);
+      const float rc = rc2 * rsqrtf_nr(rc2);
+      float nz;
+      if (kWolter) nz = rc * sh.p_r3tan * rsqrtf_nr(fmaxf(fmaf(sh.p_e, lM - zc, sh.p_r3sq), 1e-30f));
+      else nz = sh.tan1 * rc;
+      const float sg = (fmaf(xc, tx, yc * ty) + nz) * invLen * rsqrtf_nr(fmaf(rc, rc, nz * nz));
+      const float a = fabsf(sg);
+      const float lhs = a * (lM - zc), rhs = sh.R1 - below;
+      if (lhs * lhs > rhs * rhs * (1.0f - a * a)) code = SART_EXIT_NICKEL;
+    }
+    sink.fail(code);
+    return;
+  }
+  F3 pm = {fmaf(tx, z1, x0), fmaf(ty, z1, y0), z1};
+  F3 v = {tx * invLen, ty * invLen, invLen};
+  float sinA1, rhoM;
+  {
+    const float rr = fmaf(pm.x, pm.x, pm.y * pm.y);
+    const float ir = rsqrtf_nr(rr);
+    rhoM = rr * ir;
+    F3 n;
+    if (kWolter) {
+      const float nz = sh.p_r3tan * rsqrtf_nr(fmaf(sh.p_e, lM - pm.z, sh.p_r3sq));
+      const float il = rsqrtf_nr(fmaf(nz, nz, 1.0f));
+      n = {pm.x * ir * il, pm.y * ir * il, nz * il};
+    } else {
+      n = {pm.x * ir * sh.cosb, pm.y * ir * sh.cosb, sh.sinb};
+    }
+    sinA1 = reflect32(n, v);
+  }
+  // ================= mirror 2 rt:1994-2029. Ray: pm + t v.
+  float t2;
+  bool hit2;
+  const float lo2 = sh.dm - pm.z, hi2 = sh.zmax2 - pm.z;
+  const float pv = fmaf(pm.x, v.x, pm.y * v.y), vv = fmaf(v.x, v.x, v.y * v.y);
+  if (kWolter) {  // hyperboloid rho^2 = r3^2 + e (l - z) + g (l - z)^2
+    const float u = lM - pm.z;
+    const float Rh2 = fmaf(fmaf(sh.h_g, u, sh.h_e), u, sh.h_r3sq);
+    const float Rh = Rh2 * rsqrtf_nr(Rh2);
+    hit2 = pick_root32(vv - sh.h_g * v.z * v.z, fmaf(fmaf(sh.h_g, u, 0.5f * sh.h_e), v.z, pv), (rhoM - Rh) * (rhoM + Rh), v.z,
+                       lo2, hi2, t2);
+  } else {        // cone rho = r4 - tan(3 beta) (z - distanceMirrors)
+    const float rc = fmaf(-sh.tan2, pm.z - sh.dm, sh.r4);
+    hit2 = pick_root32(vv - sh.tan2 * sh.tan2 * v.z * v.z, fmaf(sh.tan2 * rc, v.z, pv), (rhoM - rc) * (rhoM + rc), v.z, lo2,
+                       hi2, t2);
+  }
+  // ================= nickel of the shell below rt:1706-1734
+  if (hitLayer > 0) {
+    const float lhs = sinA1 * (lM - z1), rhs = sh.R1 - below;
+    if (lhs * lhs > rhs * rhs * (1.0f - sinA1 * sinA1)) { sink.fail(SART_EXIT_NICKEL); return; }
+  }
+  if (!hit2) { sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }
+  pm.x = fmaf(t2, v.x, pm.x); pm.y = fmaf(t2, v.y, pm.y); pm.z = fmaf(t2, v.z, pm.z);
+  float sinA2;
+  {
+    const float rr = fmaf(pm.x, pm.x, pm.y * pm.y);
+    const float ir = rsqrtf_nr(rr);
+    F3 n;
+    if (kWolter) {
+      const float u = lM - pm.z;
+      const float q1 = fmaf(2.0f * u, sh.h_inv_nden, 1.0f), q2 = fmaf(u, sh.h_inv_nden, 1.0f);
+      const float nz = sh.h_r3tan * q1 * rsqrtf_nr(fmaf(2.0f * sh.h_r3tan * u, q2, sh.h_r3sq));
+      const float il = rsqrtf_nr(fmaf(nz, nz, 1.0f));
+      n = {pm.x * ir * il, pm.y * ir * il, nz * il};
+    } else {
+      n = {pm.x * ir * sh.cos3b, pm.y * ir * sh.cos3b, sh.sin3b};
+    }
+    sinA2 = reflect32(n, v);
+  }
+  // ================= detector plane rt:797-814
+  float xw, yw, zw;
+  {
+    const float ax = fmaf(pm.x, G.cosPipe, pm.z * G.sinPipe) - G.dShift, az = fmaf(pm.z, G.cosPipe, -pm.x * G.sinPipe);
+    const float wx = fmaf(v.x, G.cosPipe, v.z * G.sinPipe), wz = fmaf(v.z, G.cosPipe, -v.x * G.sinPipe);
+    const float n = (sh.ddWin - az) * rcpf_nr(wz);
+    xw = fmaf(n, wx, ax); yw = fmaf(n, v.y, pm.y); zw = fmaf(n, wz, az);
+  }
+  xw -= G.lateralShift; yw -= G.transversalShift;
+  // ================= weights rt:2101-2128
+  out.energy = el.E;
+  {
+    const float ya = -atan_small(ty) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
+    float pre = __cosf(ya);
+    const float path2f = rec.path2;
+    if (P.stage == SART_SK_VACUUM) {
+      out.convVac = P.convK * path2f;
+    } else {
+      const float2 gv = __ldg(reinterpret_cast<const float2*>(T.glut) + eIdx);
+      const float pathm = sqrtf(path2f) * 1e-3f;
+      const double gamma = P.gasGamma0 * double(gv.x);
+      out.gasL = double(pathm) / 1.97e-7;
+      const float gl = float(gamma * out.gasL);
+      out.gasGamma = float(gamma);
+      out.gasE1 = __expf(-gl); out.gasE2 = __expf(-0.5f * gl);
+      out.gasInv2E = gv.y;
+      const float distPipe = (zw - G.zExitCBtel) * 1e-3f;
+      pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
+    }
+    float refl = 1.0f;
+    if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
+      const float* zt = T.reflE + (size_t(sh.coat) * (P.nEnergies + 1) + eIdx) * P.nAngles;
+      const float a1 = asin_small(sinA1) * 57.29577951308232f, a2 = asin_small(sinA2) * 57.29577951308232f;
+      refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
+    }
+    out.wPre = double(refl) * double(pre);
+    if (Sink::kFold) out.wPre *= conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
+  }
+  out.clamped = clamped;
+  out.shell = hitLayer;
+  out.code = -1;
+  // ================= window aperture rt:2139-2147
+  const float rw2 = fmaf(xw, xw, yw * yw);
+  if ((!(P.flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > G.radiusWindow2) || fabsf(xw) > G.chipCX || fabsf(yw) > G.chipCY) {
+    out.windowMiss = true; out.wPost = 0.0; out.x = out.y = out.r = 0.0; out.bin = -1;
+    sink.hit(out);
+    return;
+  }
+  out.windowMiss = false;
+  // ================= strongback strips rt:2149-2185
+  double post = 1.0;
+  {
+    const float yt = fabsf(fmaf(yw, G.cosTheta, -xw * G.sinTheta));
+    int sb = 2;
+    if (P.nStripHalf > 0) {
+      const float pitch = G.stripDist + G.stripWidth;
+      const float u = yt - 0.5f * G.stripDist;
+      const float fi = floorf(u * G.invStripPitch);
+      const float off = fmaf(-fi, pitch, u);
+      sb = (u > 0.0f && fi < float(P.nStripHalf) && off > 0.0f && off < G.stripWidth) ? 1 : 0;
+    }
+    const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
+    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) post *= double(tw);
+  }
+  if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
+  if (!(P.flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
+  out.wPost = post;
+  const float xc = G.chipCX - xw, yc = yw + G.chipCY;
+  out.r = double(rw2 > 1e-30f ? rw2 * rsqrtf_nr(rw2) : 0.0f);
+  out.x = double(xc);
+  out.y = double(yc);
+  const int cx = int(floorf(xc * G.invBinX)), cy = int(floorf(yc * G.invBinY));
+  out.bin = (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) ? cy * SART_IMAGE_BINS + cx : -1;
+  sink.hit(out);
+}
+
+#ifndef SART_F32_MINBLOCKS
+#define SART_F32_MINBLOCKS 4
+#endif
+
+__device__ __forceinline__ void flush_counters(sart_counters_t* c, const WarpCounters& wc, unsigned nIter, unsigned nPassed,
+                                               unsigned nTill, double sumW, double sumW2, double sumX, double sumY, double sumR) {
+  auto addu = [](uint64_t* p, unsigned long long v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), v); };
+  addu(&c->n_rays, nIter);
+  addu(&c->n_exit[SART_EXIT_PASSED], nPassed);
+  addu(&c->n_passed, nPassed);
+  addu(&c->n_passed_till_window, nTill);
+  for (int e = 1; e < SART_N_EXIT_CODES; ++e) addu(&c->n_exit[e], wc.n_exit[e]);
+  addu(&c->n_hit_nickel, wc.n_exit[SART_EXIT_NICKEL]);
+  addu(&c->n_interp_clamped, wc.n_clamped);
+  atomicAdd(&c->sum_w, sumW); atomicAdd(&c->sum_w2, sumW2);
+  atomicAdd(&c->sum_x, sumX); atomicAdd(&c->sum_y, sumY); atomicAdd(&c->sum_r, sumR);
+}
+
+// ---- fused kernel ---------------------------------------------------------------------------------------------
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, SART_F32_MINBLOCKS)
+k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G, const __grid_constant__ FastTables T,
+               double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
+               double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem32 S;
+  unsigned char* tail;
+  smem_layout32(P, smem, S, tail);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
+  smem_fill32(P, T, S);
+  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int nPassed = 0, nTill = 0, nIter = 0;
+  double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
+  ImageSink sink{T, mAxion2, image, imageW2, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
+    ++nIter;
+    Rec32 rec;
+    const int code = stage_a32<kWolter>(P, G, T, S, seed, first + i, rec);
+    if (code >= 0) { sink.fail(code); continue; }
+    stage_b32<kWolter>(P, G, T, S, rec, sink);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
+    nTill += __shfl_down_sync(0xffffffffu, nTill, o);
+    nIter += __shfl_down_sync(0xffffffffu, nIter, o);
+    sumW += __shfl_down_sync(0xffffffffu, sumW, o);
+    sumW2 += __shfl_down_sync(0xffffffffu, sumW2, o);
+    sumX += __shfl_down_sync(0xffffffffu, sumX, o);
+    sumY += __shfl_down_sync(0xffffffffu, sumY, o);
+    sumR += __shfl_down_sync(0xffffffffu, sumR, o);
+  }
+  __syncwarp();
+  if (lane == 0) flush_counters(counters, wc[warp], nIter, nPassed, nTill, sumW, sumW2, sumX, sumY, sumR);
+}
+
+// ---- fused kernel with warp-level compaction between stage A and stage B (see kernels_fast.cu) ----------------
+constexpr int kQueue32 = 64;
+struct WarpQueue32 {
+  float x0[kQueue32], y0[kQueue32], tx[kQueue32], ty[kQueue32], rho0[kQueue32], path2[kQueue32];
+  int meta[kQueue32];   // hitLayer | eIdx << 8 | clamped << 30
+};
+
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, SART_F32_MINBLOCKS)
+k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
+                       const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed,
+                       double* __restrict__ image, double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem32 S;
+  unsigned char* tail;
+  smem_layout32(P, smem, S, tail);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
+  WarpQueue32* queues = reinterpret_cast<WarpQueue32*>(tail + kWarps * sizeof(WarpCounters));
+  smem_fill32(P, T, S);
+  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  __syncthreads();
+
+  constexpr unsigned kFull = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpQueue32& Q = queues[warp];
+  unsigned int nPassed = 0, nTill = 0, nIter = 0;
+  double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
+  ImageSink sink{T, mAxion2, image, imageW2, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  uint64_t base = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31);
+  int qn = 0;
+  for (;;) {
+    while (qn <= kQueue32 - 32 && base < nRays) {
+      const uint64_t i = base + lane;
+      base += stride;
+      Rec32 rec;
+      int code = SART_N_EXIT_CODES;
+      if (i < nRays) {
+        code = stage_a32<kWolter>(P, G, T, S, seed, first + i, rec);
+        ++nIter;
+        if (code >= 0) sink.fail(code);
+      }
+      const unsigned m = __ballot_sync(kFull, code < 0);
+      if (code < 0) {
+        const int pos = qn + __popc(m & ((1u << lane) - 1u));
+        Q.x0[pos] = rec.x0; Q.y0[pos] = rec.y0; Q.tx[pos] = rec.tx; Q.ty[pos] = rec.ty; Q.rho0[pos] = rec.rho0;
+        Q.path2[pos] = rec.path2;
+        Q.meta[pos] = rec.hitLayer | (rec.eIdx << 8) | (rec.clamped ? (1 << 30) : 0);
+      }
+      qn += __popc(m);
+    }
+    if (qn == 0) break;
+    __syncwarp();
+    const int take = qn < 32 ? qn : 32;
+    if (lane < take) {
+      const int pos = qn - take + lane;
+      Rec32 rec;
+      rec.x0 = Q.x0[pos]; rec.y0 = Q.y0[pos]; rec.tx = Q.tx[pos]; rec.ty = Q.ty[pos]; rec.rho0 = Q.rho0[pos];
+      rec.path2 = Q.path2[pos];
+      const int meta = Q.meta[pos];
+      rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
+      stage_b32<kWolter>(P, G, T, S, rec, sink);
+    }
+    qn -= take;
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nPassed += __shfl_down_sync(kFull, nPassed, o);
+    nTill += __shfl_down_sync(kFull, nTill, o);
+    nIter += __shfl_down_sync(kFull, nIter, o);
+    sumW += __shfl_down_sync(kFull, sumW, o);
+    sumW2 += __shfl_down_sync(kFull, sumW2, o);
+    sumX += __shfl_down_sync(kFull, sumX, o);
+    sumY += __shfl_down_sync(kFull, sumY, o);
+    sumR += __shfl_down_sync(kFull, sumR, o);
+  }
+  __syncwarp();
+  if (lane == 0) flush_counters(counters, wc[warp], nIter, nPassed, nTill, sumW, sumW2, sumX, sumY, sumR);
+}
+
+// ---- per-ray records (traceAxionWrapper in FP32 mode) ----------------------------------------------------------
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, 2)
+k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
+                    const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed,
+                    double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
+                    int32_t* __restrict__ oshell, double* __restrict__ oenergy, double* __restrict__ orad) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem32 S;
+  unsigned char* tail;
+  smem_layout32(P, smem, S, tail);
+  smem_fill32(P, T, S);
+  __syncthreads();
+  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
+    RayResult r;
+    RecordSink<true> sink{r, mAxion2};
+    Rec32 rec;
+    const int c0 = stage_a32<kWolter>(P, G, T, S, seed, first + i, rec);
+    if (c0 >= 0) sink.fail(c0);
+    else stage_b32<kWolter>(P, G, T, S, rec, sink);
+    int code = r.code;
+    double wd = 0.0;
+    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
+    else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
+    const bool tail = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
+    ox[i] = tail ? r.x : 0.0; oy[i] = tail ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tail ? r.shell : -1;
+    if (oenergy) oenergy[i] = double(r.energy);
+    if (orad) orad[i] = tail ? r.r : 0.0;
+  }
+}
+
+static size_t smem_bytes32(const FastParams& P) {
+  return ((size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15)) + size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2 +
+         ((size_t(P.nShellGuide) + 15) & ~size_t(15)) + kWarps * sizeof(WarpCounters);
+}
+
+}  // namespace fast
+
+cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
+                                uint64_t first, uint64_t nRays, uint64_t seed, double* image, double* imageW2,
+                                sart_counters_t* counters, int smCount, bool compact, cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes32(P) + (compact ? fast::kWarps * sizeof(fast::WarpQueue32) : 0);
+  auto kern = compact ? (wolter ? fast::k_trace_mc_f32_compact<true> : fast::k_trace_mc_f32_compact<false>)
+                      : (wolter ? fast::k_trace_mc_f32<true> : fast::k_trace_mc_f32<false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int perSM = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * perSM;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
+                               uint64_t first, uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount,
+                               cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes32(P);
+  auto kern = wolter ? fast::k_trace_mc_rays_f32<true> : fast::k_trace_mc_rays_f32<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * 2;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, seed, o.x, o.y, o.w, o.code, o.shell,
+                                        o.energy, o.r);
+  return cudaGetLastError();
+}
+
+}  // namespace sart

@@ -19,101 +19,17 @@
 //   * run-wide tables (radius CDF, guide, shell constants) are staged once per block in shared memory;
 //   * counters live in registers / per-warp shared memory and are flushed once per block.
 // Exit codes follow the same decision sequence as the exact pipeline, so the counters of both are comparable.
-#include <cuda_runtime.h>
-
-#include <cfloat>
-
-#include "fast_params.h"
-#include "kernels.h"
-#include "philox.cuh"
+#include "fast_common.cuh"
 
 namespace sart {
 namespace fast {
-
-#ifndef SART_FAST_BLOCK
-#define SART_FAST_BLOCK 256
-#endif
-#ifndef SART_FAST_MINBLOCKS
-#define SART_FAST_MINBLOCKS 3
-#endif
-constexpr int kBlock = SART_FAST_BLOCK;
-constexpr int kWarps = kBlock / 32;
-
-// ---- FP64 divide / sqrt from FP32 seeds ---------------------------------------------------------------------
-// MUFU.RCP / MUFU.RSQ seeds (2^-23 relative); the *_rn intrinsics and rsqrtf() expand to range checks + slow paths.
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ double rcp_nr(double x) {
-  double r = double(rcp_approx(float(x)));
-  const double e = fma(-x, r, 1.0);
-  return fma(r, e, r);
-}
-__device__ __forceinline__ double rsqrt_nr(double x) {
-  double y = double(rsqrt_approx(float(x)));
-  const double h = 0.5 * x * y;
-  return fma(y, fma(-h, y, 0.5), y);  // y * (1.5 - 0.5 x y^2)
-}
-
-// sin/cos(2 pi u), u in [0, 1): MUFU.SIN/COS on the argument shifted into [-pi, pi) where their absolute error is
-// 2^-21.4; these only set the sampled emission direction / exit-disc point (a 5e-7 relative shift of a random point).
-__device__ __forceinline__ void sincos_2pi(float u, float& s, float& c) {
-  const float t = 6.283185307179586f * (u - 0.5f);
-  s = -__sinf(t);
-  c = -__cosf(t);
-}
-// asin / atan for small arguments (grazing angles <= 0.1 rad, slopes <= 0.1): odd series, relative error < 1e-7.
-__device__ __forceinline__ float asin_small(float x) {
-  if (fabsf(x) > 0.1f) return asinf(x);
-  const float x2 = x * x;
-  return x * fmaf(x2, fmaf(x2, 0.075f, 0.16666667f), 1.0f);
-}
-__device__ __forceinline__ float atan_small(float x) {
-  if (fabsf(x) > 0.1f) return atanf(x);
-  const float x2 = x * x;
-  return x * fmaf(x2, fmaf(x2, 0.2f, -0.33333334f), 1.0f);
-}
-
-struct D3 { double x, y, z; };
-
-__device__ __forceinline__ void rad_add(const RadialHist& h, double r, double w) {
-  int b = int(r * h.invStep);
-  b = b < 0 ? 0 : (b > h.nbins - 1 ? h.nbins - 1 : b);
-  atomicAdd(h.w + b, w);
-  atomicAdd(h.n + b, 1ull);
-}
-
-// ---- shared memory layout -----------------------------------------------------------------------------------
-struct WarpCounters { unsigned int n_exit[16]; unsigned int n_clamped; unsigned int pad[3]; };
-
-// lowerBound restricted to the guide window [lo, hi]
-__device__ __forceinline__ int lower_bound_window(const double* __restrict__ a, int lo, int hi, double key) {
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// Number of the 4 ascending thresholds that are <= w.
-__device__ __forceinline__ int count_le(const uint4& t, uint32_t w) {
-  return int(w >= t.x) + int(w >= t.y) + int(w >= t.z) + int(w >= t.w);
-}
-// lowerBound over u32 thresholds beyond the 8 prefetched ones (windows wider than 8 entries: flat CDF tails)
-__device__ __noinline__ int thr_search_tail(const uint32_t* __restrict__ thr, int from, int n, uint32_t w) {
-  int lo = from, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (w >= thr[mid]) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 // Root choice of findPos* (rt:646-658): roots of A t^2 + 2 hb t + C = 0 in the reference's order root1 = (-hb - sq)/A,
 // root2 = (-hb + sq)/A, each accepted only if zmin < pz + t dz < zmax. With q = -(hb + sign(hb) sq) the roots are q/A
 // (the larger in magnitude) and C/q. The large root is never inside a mirror in practice (it is metres away), so it is
 // excluded with a division-free bound and only then does the small root need a reciprocal; the rare other case
 // reproduces the reference's order exactly.
-__device__ __noinline__ bool pick_root_slow(double A, double q, double C, bool first_is_qA, double dz, double lo,
+static __device__ __noinline__ bool pick_root_slow(double A, double q, double C, bool first_is_qA, double dz, double lo,
                                             double hi, double& t) {
   auto in_range = [&](double num, double den) {
     const double nd = num * dz;  // lo < (num/den) dz < hi without dividing
@@ -152,34 +68,6 @@ __device__ __forceinline__ double reflect(D3 n, D3& v) {
   return as;
 }
 
-// Reflectivity at grazing angle alphaDeg from the row pre-interpolated at the ray's energy: linear in the angle.
-__device__ __forceinline__ float refl_lookup(const FastParams& P, const float* __restrict__ row, float alphaDeg, bool& clamped) {
-  float x = alphaDeg;
-  if (!(x >= P.angleMin)) { x = P.angleMin; clamped = true; }
-  if (!(x <= P.angleMax)) { x = P.angleMax; clamped = true; }
-  const float fx = (x - P.angleMin) * P.invReflDx;
-  int i = int(fx);
-  if (i > P.nAngles - 2) i = P.nAngles - 2;
-  const float z0 = __ldg(row + i), z1 = __ldg(row + i + 1);
-  return fmaf(fx - float(i), z1 - z0, z0);
-}
-
-// What trace_one knows about a ray. `code` is the exit code of a geometric early return, or -1 when the ray reached
-// the weight stage; then weight(m_a) = wPre * conv(m_a) * wPost (finish_ray), so a mass scan re-uses one traced ray.
-struct RayResult {
-  int code;
-  int bin;        // image bin or -1
-  int shell;
-  bool windowMiss, clamped;
-  float energy;
-  double wPre;    // reflectivity * cos(yaw) * He absorption        (everything before the window, without P(a->gamma))
-  double wPost;   // window or strongback * detector gas * exposure (0 when the window aperture is missed)
-  double x, y, r;
-  // conversion probability pieces: vacuum convVac = (g B L / 2)^2; gas: Gamma, L, exp(-Gamma L), exp(-Gamma L/2), 1/(2E)
-  float convVac, gasGamma, gasE1, gasE2, gasInv2E;
-  double gasL;
-};
-
 // Shared-memory tables of one block (shells first so their addresses are compile-time offsets).
 struct Smem {
   const ShellFast* shell;
@@ -208,19 +96,6 @@ __device__ __forceinline__ void smem_fill(const FastParams& P, const FastTables&
   for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
 }
 
-// Conversion probability for axion mass^2 m2 (computeMagnetTransmission rt:1582-1625 without the cos(ya) factor).
-__device__ __forceinline__ double conv_factor(const FastParams& P, float convVac, float gasGamma, float gasE1, float gasE2,
-                                              float gasInv2E, double gasL, double m2) {
-  if (P.flags & SART_CF_IGNORE_CONV_PROB) return 1.0;
-  if (P.stage == SART_SK_VACUUM) return double(convVac);
-  const double q = fabs(P.gasMgamma2 - m2) * double(gasInv2E);   // momentumTransfer am:63-68
-  double ph = q * gasL;   // phase reduced in FP64 before the FP32 cosine
-  ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);
-  const float cq = __cosf(float(ph));
-  const double g = double(gasGamma);
-  const double term2 = rcp_nr(fma(q, q, 0.25 * g * g));
-  return P.gasTerm1 * term2 * double(1.0f + gasE1 - 2.0f * gasE2 * cq);
-}
 // A ray that survived everything before the mirrors (stage A): what stage B needs to finish it. 48 bytes; this is
 // the record the compacting kernel queues in shared memory.
 struct Rec {
@@ -333,11 +208,12 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
   double x0 = fma(sx, P.dzPipe2, ex), y0 = fma(sy, P.dzPipe2, ey);
   if (!(fma(x0, x0, y0 * y0) < P.rPipe12)) return SART_EXIT_CLIP_PIPE_XRT;  // quirk Q2
   // energy thresholds: 8 entries from the 16-byte aligned entry at or below the guide's start (windows are 1-2 wide)
-  uint4 etA = make_uint4(0, 0, 0, 0), etB = etA;
-  if (eRow) {
-    etA = __ldg(reinterpret_cast<const uint4*>(eRow + e0));
-    etB = __ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4));
-  }
+  uint4 etA = make_uint4(0, 0, 0, 0);
+#if !SART_LAZY_THR
+  uint4 etB = etA;
+  if (eRow) etB = __ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4));
+#endif
+  if (eRow) etA = __ldg(reinterpret_cast<const uint4*>(eRow + e0));
 
   // ================= telescope frame rt:1888-1905 (rotation about (0, 0, halfLenTel); identity when not turned)
   double dx = sx, dy = sy, dz = 1.0, z0 = 0.0;
@@ -408,8 +284,12 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
   if (eRow) {
     const uint32_t we = w[5];
     eIdx = e0 + count_le(etA, we);
-    if (eIdx == e0 + 4) {
+    if (eIdx == e0 + 4) {   // ~1 ray in 8: the next four thresholds (loaded only by the lanes that need them)
+#if SART_LAZY_THR
+      eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4)), we);
+#else
       eIdx += count_le(etB, we);
+#endif
       if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, P.nEnergies, we);
     }
     if (we == 0xffffffffu)   // saturated thresholds: the f64 row decides
@@ -606,19 +486,6 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
   sink.hit(out);
 }
 
-// Sink that keeps the outcome as a RayResult (per-ray records, mass scan).
-template <bool kFoldT>
-struct RecordSink {
-  static constexpr bool kFold = kFoldT;
-  RayResult& out;
-  double m2;
-  __device__ __forceinline__ void fail(int code) {
-    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1; out.energy = 0.f;
-    out.x = out.y = out.r = 0.0; out.wPre = out.wPost = 0.0;
-  }
-  __device__ __forceinline__ void hit(const RayResult& h) { out = h; out.code = -1; }
-};
-
 template <bool kWolter, bool kFold>
 __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables& T, const Smem& S, uint64_t seed,
                                           uint64_t ray, double m2, RayResult& out) {
@@ -628,52 +495,6 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
   if (code >= 0) { sink.fail(code); return; }
   stage_b<kWolter>(P, T, S, rec, sink);
 }
-
-// Tail of traceAxion for one axion mass: exit code | flags and the final weight.
-template <bool kFolded>
-__device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& r, double m2, double& w) {
-  const double w0 = kFolded ? r.wPre
-                            : r.wPre * conv_factor(P, r.convVac, r.gasGamma, r.gasE1, r.gasE2, r.gasInv2E, r.gasL, m2);
-  int flags = (w0 != 0.0) ? SART_FLAG_PASSED_TILL_WINDOW : 0;
-  if (r.clamped) flags |= SART_FLAG_INTERP_CLAMPED;
-  w = 0.0;
-  if (r.windowMiss) return SART_EXIT_WINDOW_APERTURE | flags;
-  w = w0 * r.wPost;
-  return ((w != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
-}
-
-// Sink of the fused kernels: the tail of traceAxion (rt:2135-2221) + prepareHeatmap (rt:839-842) for one axion mass,
-// applied where the ray's outcome becomes known. Sums live in the caller's registers, exit counts in the warp's
-// shared-memory counters.
-struct ImageSink {
-  static constexpr bool kFold = true;
-  const FastTables& T;
-  double m2;
-  double* __restrict__ image;
-  double* __restrict__ imageW2;
-  WarpCounters& wc;
-  unsigned int &nPassed, &nTill;
-  double &sumW, &sumW2, &sumX, &sumY, &sumR;
-  __device__ __forceinline__ void fail(int code) { atomicAdd(&wc.n_exit[code], 1u); }
-  __device__ __forceinline__ void hit(const RayResult& h) {
-    const double w0 = h.wPre;   // conversion probability already folded in
-    if (w0 != 0.0) ++nTill;                                   // passedTillWindow rt:2135-2136
-    if (h.clamped) atomicAdd(&wc.n_clamped, 1u);
-    if (h.windowMiss) { atomicAdd(&wc.n_exit[SART_EXIT_WINDOW_APERTURE], 1u); return; }
-    const double wd = w0 * h.wPost;
-    if (wd != 0.0) {                                          // passed rt:2220
-      ++nPassed;
-      sumW += wd; sumW2 += wd * wd; sumX += h.x; sumY += h.y; sumR += h.r;
-      if (h.bin >= 0) {
-        atomicAdd(image + h.bin, wd);
-        atomicAdd(imageW2 + h.bin, wd * wd);
-      }
-      if (T.rad.w) rad_add(T.rad, h.r, wd);
-    } else {
-      atomicAdd(&wc.n_exit[SART_EXIT_ZERO_WEIGHT], 1u);
-    }
-  }
-};
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
 template <bool kWolter>

@@ -25,6 +25,7 @@ namespace fast {
 bool supported(const sart_setup_t& s, const char** why);
 void derive_shells(const sart_setup_t& s, const ShellF64* exactShells, ShellFast* out);
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f);
+void derive_f32(const FastParams& f, const ShellFast* shells, int nShells, Geo32* g, ShellF32* out);
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide);
 void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
                       const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out,
@@ -42,7 +43,7 @@ struct sart_handle {
   sart::Tables tables;          // device pointers
   void* table_blob = nullptr;   // one allocation backing every table
   size_t table_bytes = 0;
-  int precision = 0;            // 0 exact f64, 1 fast
+  int precision = 0;            // 0 exact f64, 1 fast (f64 algebra + f32 weights), 2 f32 geometry
   int compact = 0;              // fast mode: warp-level compaction between the clip stages and the mirrors
   double pilot_survival = 1.0;  // fraction of launched rays that reach the mirrors (pilot run at create)
   // "fast" pipeline: parameter block, LUTs and f32 reflectivity in a second allocation
@@ -50,8 +51,9 @@ struct sart_handle {
   const char* fast_why = "";
   sart::fast::FastParams fparams;
   sart::fast::FastTables ftables;
+  sart::fast::Geo32 geo32;      // single-precision geometry block of precision mode 2
   void* fast_blob = nullptr;
-  size_t fast_shell_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_sguide_off = 0, fast_refl_off = 0;
+  size_t fast_shell_off = 0, fast_shell32_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_sguide_off = 0, fast_refl_off = 0;
   std::vector<float> h_refl32;  // host copy of the reflectivity (f32) for rebuilding the X-ray-source row
   std::vector<double> h_energies, h_tab[3][2];  // host copies (energies; strongback/window/gas x,y) for LUT rebuilds
   int sm_count = 148;

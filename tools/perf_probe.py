@@ -5,14 +5,17 @@ being result-neutral against an earlier build:  python tools/perf_probe.py [libs
 import hashlib, json, os, sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-if len(sys.argv) > 1 and sys.argv[1].endswith(".so"):
-    os.environ["SART_LIB"] = sys.argv[1]
-prec = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+args = sys.argv[1:]
+lib = [a for a in args if a.endswith(".so")]
+if lib:
+    os.environ["SART_LIB"] = lib[0]
+precs = [int(a) for a in args if a.isdigit()] or [1]
 from solaraxionraytracing_b200 import raytracer as rt, tables
 
 def probe(name, args, em, ncoat, n):
     fs = rt.initFullSetup(*args, emission=em, reflectivity=tables.synthetic_reflectivity(ncoat, 1000, 1000))
     with rt.RayTracer(fs) as tr:
+      for prec in precs:
         tr.set_precision(prec)
         tr.trace_mc(n // 10, 1); tr.synchronize()
         best = 1e9
@@ -22,7 +25,9 @@ def probe(name, args, em, ncoat, n):
         r = tr.read_image()
         c = r.counters[0]
         h = hashlib.sha1(json.dumps(c["n_exit"], sort_keys=True).encode()).hexdigest()[:10]
-        print(f"{name}: {n/best:.4e} rays/s ({best*1e3:.2f} ms)  exit-hash {h} passed {c['n_passed']} till_window {c['n_passed_till_window']} "
+        if len(precs) > 1:
+            print("   ", {k: v for k, v in c["n_exit"].items() if v})
+        print(f"{name} prec {prec}: {n/best:.4e} rays/s ({best*1e3:.2f} ms)  exit-hash {h} passed {c['n_passed']} till_window {c['n_passed_till_window']} "
               f"sum_w {c['sum_w']:.12e} img {r.image.sum():.12e}", flush=True)
 
 em_abc = tables.synthetic_emission(1968, 1500, "abc"); em_prim = tables.synthetic_emission(1968, 1500, "primakoff")
