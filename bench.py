@@ -311,7 +311,7 @@ def run_ours(args):
     n_gpus = world
     R = int(args.rays_per_step)
     K, W = args.steps, args.warmup
-    precision = args.precision or ("fast" if rt.fast_available() else "exact")
+    precision = args.precision or ("f32" if rt.lib.sart_has_precision(2) else "fast")
 
     t0 = time.perf_counter()
     tb = workload_tables(rt, tables, local)
@@ -412,7 +412,7 @@ def run_ours(args):
         out = {
             "metric": "traced rays/s", "value": value, "unit": "rays/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if fp64 else "f32+f64", "data": "synthetic",
+            "dtype": {"exact": "f64", "fast": "f64 geometry + f32 weights", "f32": "f32"}[precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "precision": precision,
                        "l2": "256 MiB buffer written between steps (L2 flush)", "seed": SEED,
                        "table_upload_s": round(table_upload_s, 3),
@@ -425,7 +425,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64" if fp64 else "fp32", "achieved": achieved, "peak": peak.value,
                          "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
-                         "kernel": "k_trace_mc_image" if fp64 else "k_trace_mc_fast",
+                         "kernel": {"exact": "k_trace_mc_image", "fast": "k_trace_mc_fast", "f32": "k_trace_mc_f32"}[precision],
                          "kernel_ms": k_ms, "flop_per_ray": F_RAY_LLNL,
                          "peak_source": "sart_measure_fma_peak in this run (MEASURED_PEAKS.json has no CUDA-core "
                                         "figure); the kernel moves ~0 HBM bytes per ray"},

@@ -3,7 +3,7 @@
 
   python -m solaraxionraytracing_b200 [--ignoreDetWindow] [--ignoreGasAbs] [--ignoreConvProb] [--ignoreReflection]
       [--xrayTest] [--detectorInstall] [--magnet] [--angularScanMin A --angularScanMax B --numAngularScanPoints N]
-      [--noPlots] [--config FILE | --configPath DIR] [--nRays N] [--precision fast|exact] [--device D]
+      [--noPlots] [--config FILE | --configPath DIR] [--nRays N] [--precision f32|fast|exact] [--device D]
 
 Inputs the reference reads from `resources/` and that are not shipped with it (solar_model_dataframe.csv, the two
 reflectivity HDF5 files) are taken from [Resources] when present, else generated: Primakoff emission rates from AGSS09
@@ -30,7 +30,7 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--configPath", default="", help="directory holding config.toml")
     ap.add_argument("--nRays", type=float, default=1e6, help="NumberOfPointsSun (rt:251)")
     ap.add_argument("--seed", type=int, default=299792458)
-    ap.add_argument("--precision", choices=["fast", "exact"], default="fast")
+    ap.add_argument("--precision", choices=["f32", "fast", "exact"], default="f32")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--outputPath", default="", help="overrides [Resources].outputPath")
     return ap
@@ -72,7 +72,7 @@ def main(argv=None) -> int:
     fs = rt.FullRaytraceSetup(setup, tb, outpath)
     n = int(a.nRays)
     with rt.RayTracer(fs, a.device) as tr:
-        tr.set_precision(1 if a.precision == "fast" else 0)
+        tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[a.precision])
         if a.angularScanMin == a.angularScanMax:
             print("start")
             tr.enable_radial_hist()

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -289,6 +290,20 @@ static int ensure_image(sart_handle* h, int nMasses) {
 
 static int ensure_stage(sart_handle* h, size_t bytes);
 
+// Replica buffers for the single-mass throughput kernels. SART_IMG_REPLICAS overrides the count (1 = off).
+static int ensure_replicas(sart_handle* h) {
+  if (h->n_rep > 0) return SART_OK;
+  int n = 8;   // measured on B200, CAST+LLNL, 1e9 rays: 1 replica 43.8 ms, 4 / 16 / 64 replicas 36.1 ms
+  if (const char* e = std::getenv("SART_IMG_REPLICAS")) n = std::max(1, std::min(256, std::atoi(e)));
+  h->n_rep = n;
+  if (n > 1) {
+    const size_t bytes = size_t(2) * n * SART_IMAGE_BINS * SART_IMAGE_BINS * sizeof(double);
+    SART_CUDA(cudaMalloc(&h->d_rep, bytes));
+    SART_CUDA(cudaMemsetAsync(h->d_rep, 0, bytes, h->stream));
+  }
+  return SART_OK;
+}
+
 // Chooses the fast kernel variant for this setup from a pilot run: warp compaction pays off only when a large
 // fraction of the launched rays is removed before the mirrors (measured: BabyIAXO+XMM 0.33 survive, +35 %; CAST+LLNL
 // 0.93 survive, -13 %).
@@ -401,7 +416,7 @@ void sart_destroy(sart_handle_t* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
-  cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n);
+  cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n); cudaFree(h->d_rep);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -635,14 +650,24 @@ int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_
                                           h->d_image, h->d_image_w2, h->d_counters, h->sm_count, h->stream));
     return SART_OK;
   }
-  if (h->precision == 2) {
-    SART_CUDA(launch_mc_image_f32(h->fparams, h->geo32, h->ftables, h->masses[0], first_ray, n_rays, seed, h->d_image,
-                                  h->d_image_w2, h->d_counters, h->sm_count, h->compact != 0, h->stream));
-    return SART_OK;
-  }
-  if (h->precision == 1) {
-    SART_CUDA(launch_mc_image_fast(h->fparams, h->ftables, h->masses[0], first_ray, n_rays, seed, h->d_image,
-                                   h->d_image_w2, h->d_counters, h->sm_count, h->compact != 0, h->stream));
+  if (h->precision >= 1) {
+    int rc = ensure_replicas(h);
+    if (rc) return rc;
+    const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS;
+    fast::FastTables ft = h->ftables;
+    double *img = h->d_image, *img2 = h->d_image_w2;
+    if (h->n_rep > 1) {
+      ft.nImgRep = h->n_rep; ft.imgRepStride = plane;
+      img = h->d_rep; img2 = h->d_rep + size_t(h->n_rep) * plane;
+    }
+    if (h->precision == 2)
+      SART_CUDA(launch_mc_image_f32(h->fparams, h->geo32, ft, h->masses[0], first_ray, n_rays, seed, img, img2,
+                                    h->d_counters, h->sm_count, h->compact != 0, h->stream));
+    else
+      SART_CUDA(launch_mc_image_fast(h->fparams, ft, h->masses[0], first_ray, n_rays, seed, img, img2, h->d_counters,
+                                     h->sm_count, h->compact != 0, h->stream));
+    if (h->n_rep > 1)
+      SART_CUDA(launch_fold_replicas(img, img2, h->n_rep, plane, plane, h->d_image, h->d_image_w2, h->stream));
     return SART_OK;
   }
   SART_CUDA(launch_mc_image_exact(h->params, h->tables, h->n_masses, h->d_masses, first_ray, n_rays, seed, h->d_image,

@@ -186,10 +186,12 @@ struct ImageSink {
     if (wd != 0.0) {                                          // passed rt:2220
       ++nPassed;
       sumW += wd; sumW2 += wd * wd; sumX += h.x; sumY += h.y; sumR += h.r;
+#ifndef SART_NO_IMAGE_ATOMICS   // (experiment switch: measures what the histogram atomics cost)
       if (h.bin >= 0) {
         atomicAdd(image + h.bin, wd);
         atomicAdd(imageW2 + h.bin, wd * wd);
       }
+#endif
       if (T.rad.w) rad_add(T.rad, h.r, wd);
     } else {
       atomicAdd(&wc.n_exit[SART_EXIT_ZERO_WEIGHT], 1u);

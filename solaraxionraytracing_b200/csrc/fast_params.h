@@ -95,6 +95,11 @@ struct FastTables {
   const ShellF32* shells32;   // [nShells] the same records in single precision (kernels_f32.cu)
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
   RadialHist rad;             // optional (w == nullptr: off)
+  // Image replicas: block b adds into replica b % nImgRep of the image / w^2 image it is handed (replica r starts
+  // imgRepStride doubles after replica 0); 0 or 1 = the image itself. The focal spot concentrates ~1e9 atomic adds per
+  // launch on a few hundred bins; spreading them over replicas removes the same-address serialisation in L2.
+  int32_t nImgRep, pad_;
+  uint64_t imgRepStride;
 };
 
 }  // namespace fast

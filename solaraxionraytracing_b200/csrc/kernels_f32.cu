@@ -101,13 +101,39 @@ struct Rec32 {
   bool clamped;
 };
 
+// Head of stage A: the ray's random words, its emission shell (rt:437, integer search in shared memory) and the load of
+// the energy-guide entry of that shell. Split off so that a kernel can run it one ray ahead: the guide entry is the first
+// of two dependent L2 round trips of the energy search, and issued an iteration early it costs no stall at all.
+struct Head32 {
+  uint32_t w[6];
+  int rIdx;
+  uint16_t guide;
+};
+__device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S, uint64_t seed,
+                                               uint64_t ray, Head32& h) {
+  ray_words(seed, ray, h.w);
+  h.rIdx = 0; h.guide = 0;
+  if (!P.testXray) {
+    const uint32_t wr = h.w[2];
+    const int r0 = int(S.radGuide[wr >> (32 - kRadGuideBits)]) & ~3;
+    int rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
+    if (rIdx == r0 + 4) {
+      rIdx += count_le(*reinterpret_cast<const uint4*>(S.radThr + r0 + 4), wr);
+      if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, P.nRadii, wr);
+    }
+    if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
+    if (rIdx > P.nRadii - 1) rIdx = P.nRadii - 1;
+    h.rIdx = rIdx;
+    h.guide = __ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (h.w[5] >> (32 - kEnGuideBits)));
+  }
+}
+
 // Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
 template <bool kWolter>
 __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
-                                         uint64_t seed, uint64_t ray, Rec32& rec) {
+                                         const Head32& h, Rec32& rec) {
   const ShellF32* __restrict__ sShell = S.shell;
-  uint32_t w[6];
-  ray_words(seed, ray, w);
+  const uint32_t* w = h.w;
   constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
   bool clamped = false;
 
@@ -116,23 +142,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   int e0 = 0;
   const uint32_t* eRow = nullptr;
   if (!P.testXray) {
-    int rIdx;
-    {
-      const uint32_t wr = w[2];
-      const int r0 = int(S.radGuide[wr >> (32 - kRadGuideBits)]) & ~3;
-      rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
-      if (rIdx == r0 + 4) {
-        rIdx += count_le(*reinterpret_cast<const uint4*>(S.radThr + r0 + 4), wr);
-        if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, P.nRadii, wr);
-      }
-      if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
-      if (rIdx > P.nRadii - 1) rIdx = P.nRadii - 1;
-    }
-    {
-      const uint32_t we = w[5];
-      e0 = int(__ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (we >> (32 - kEnGuideBits)))) & ~3;
-      eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
-    }
+    const int rIdx = h.rIdx;
+    e0 = int(h.guide) & ~3;
+    eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
     const float rs = (0.0015f + float(rIdx) * 0.0005f);
     float s1, c1, s2, c2;
     sincos_2pi(float(w[0]) * k2m32, s1, c1);
@@ -497,14 +509,23 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
-  ImageSink sink{T, mAxion2, image, imageW2, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
+  ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
-  for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
+  uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x;
+  Head32 cur;
+  if (i < nRays) stage_a32_head(P, T, S, seed, first + i, cur);
+  while (i < nRays) {
     ++nIter;
+    const uint64_t inext = i + stride;
+    Head32 nxt;
+    if (inext < nRays) stage_a32_head(P, T, S, seed, first + inext, nxt);   // next ray's guide load goes out now
     Rec32 rec;
-    const int code = stage_a32<kWolter>(P, G, T, S, seed, first + i, rec);
-    if (code >= 0) { sink.fail(code); continue; }
-    stage_b32<kWolter>(P, G, T, S, rec, sink);
+    const int code = stage_a32<kWolter>(P, G, T, S, cur, rec);
+    if (code >= 0) sink.fail(code);
+    else stage_b32<kWolter>(P, G, T, S, rec, sink);
+    cur = nxt;
+    i = inext;
   }
   for (int o = 16; o > 0; o >>= 1) {
     nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
@@ -547,7 +568,8 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
   WarpQueue32& Q = queues[warp];
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
-  ImageSink sink{T, mAxion2, image, imageW2, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
+  ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   uint64_t base = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31);
   int qn = 0;
@@ -558,7 +580,9 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       Rec32 rec;
       int code = SART_N_EXIT_CODES;
       if (i < nRays) {
-        code = stage_a32<kWolter>(P, G, T, S, seed, first + i, rec);
+        Head32 hd;
+        stage_a32_head(P, T, S, seed, first + i, hd);
+        code = stage_a32<kWolter>(P, G, T, S, hd, rec);
         ++nIter;
         if (code >= 0) sink.fail(code);
       }
@@ -618,7 +642,9 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     RayResult r;
     RecordSink<true> sink{r, mAxion2};
     Rec32 rec;
-    const int c0 = stage_a32<kWolter>(P, G, T, S, seed, first + i, rec);
+    Head32 hd;
+    stage_a32_head(P, T, S, seed, first + i, hd);
+    const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
     else stage_b32<kWolter>(P, G, T, S, rec, sink);
     int code = r.code;

@@ -5,9 +5,29 @@
 // the same run as the throughput number, with these kernels.
 #include <cuda_runtime.h>
 
+#include "kernels.h"
 #include "sart_internal.h"
 
 namespace sart {
+
+// Folds the image replicas of a launch (fast_params.h: FastTables::nImgRep) into the handle's image and clears them.
+__global__ void __launch_bounds__(256) k_fold_replicas(double* __restrict__ rep, double* __restrict__ rep2, int nRep,
+                                                       size_t stride, size_t plane, double* __restrict__ image,
+                                                       double* __restrict__ imageW2) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  double a = 0.0, b = 0.0;
+  for (int r = 0; r < nRep; ++r) {
+    const double x = rep[size_t(r) * stride + i], y = rep2[size_t(r) * stride + i];
+    if (x != 0.0 || y != 0.0) { a += x; b += y; rep[size_t(r) * stride + i] = 0.0; rep2[size_t(r) * stride + i] = 0.0; }
+  }
+  if (a != 0.0 || b != 0.0) { image[i] += a; imageW2[i] += b; }
+}
+cudaError_t launch_fold_replicas(double* rep, double* rep2, int nRep, size_t stride, size_t plane, double* image,
+                                 double* imageW2, cudaStream_t s) {
+  k_fold_replicas<<<unsigned((plane + 255) / 256), 256, 0, s>>>(rep, rep2, nRep, stride, plane, image, imageW2);
+  return cudaGetLastError();
+}
 
 template <typename T, int kChains>
 __global__ void __launch_bounds__(256) k_fma_peak(T* out, T a, T b, int iters) {

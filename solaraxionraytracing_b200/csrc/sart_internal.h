@@ -66,6 +66,9 @@ struct sart_handle {
   double* d_image = nullptr;    // [n_masses][256][256]
   double* d_image_w2 = nullptr;
   sart_counters_t* d_counters = nullptr;  // [n_masses]
+  // image replicas of the throughput kernels (cleared by the fold that follows every launch)
+  double* d_rep = nullptr;      // [2][n_rep][256*256]
+  int n_rep = 0;
   // optional radial histogram of the passed rays (sart_enable_radial_hist)
   double* d_rad_w = nullptr;
   unsigned long long* d_rad_n = nullptr;
