@@ -187,7 +187,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   const bool hitEntrance = fmaf(p0x, p0x, p0y * p0y) < G.radiusCB2;
   const float pex = fmaf(sx, G.dzExitCB, ex), pey = fmaf(sy, G.dzExitCB, ey);
   const bool insideExit = fmaf(pex, pex, pey * pey) < G.radiusCB2;
-  if (!insideExit) return hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
+  // The clip tests of this stage do not branch: a warp goes on as long as one lane survives, so an early return saves
+  // nothing and costs a divergence region each. `code` collects the exit in reverse order (the first failing test of
+  // the reference's sequence is assigned last) and the stage returns once, at its end.
   float path2;
   if (hitEntrance) {
     path2 = G.lengthB2 * (1.0f + s2sum);
@@ -198,12 +200,13 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     const float t1 = (hb >= 0.0f) ? -(hb + sq) * rcpf_nr(s2sum) : c * rcpf_nr(sq - hb);
     path2 = t1 * t1 * (1.0f + s2sum);
   }
+  bool okPipe1;
   {
     const float qx = fmaf(sx, G.dzPipe1, ex), qy = fmaf(sy, G.dzPipe1, ey);
-    if (!(fmaf(qx, qx, qy * qy) < G.rPipe12)) return SART_EXIT_CLIP_PIPE_VT3;
+    okPipe1 = fmaf(qx, qx, qy * qy) < G.rPipe12;
   }
   float x0 = fmaf(sx, G.dzPipe2, ex), y0 = fmaf(sy, G.dzPipe2, ey);
-  if (!(fmaf(x0, x0, y0 * y0) < G.rPipe12)) return SART_EXIT_CLIP_PIPE_XRT;  // quirk Q2
+  const bool okPipe2 = fmaf(x0, x0, y0 * y0) < G.rPipe12;  // quirk Q2
   uint4 etA = make_uint4(0, 0, 0, 0);
 #if !SART_LAZY_THR
   uint4 etB = etA;
@@ -235,6 +238,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   const float radialDist = rho0sq * invRho0;
 
   // ================= opaque structures rt:1635-1704
+  bool opaque = false;
   if (kWolter) {
     const bool xmm = P.telKind == SART_TK_XMM;
     bool hit = false;
@@ -258,23 +262,28 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
         hit = (a <= 3.75f) || (b <= 3.75f);
       }
     }
-    if (hit) return SART_EXIT_OPAQUE;
+    opaque = hit;
   }
 
   // ================= shell rt:1932-1957: uniform radial guide + at most one forward step
   const int nS = P.nShells;
-  if (radialDist > sShell[nS - 1].R1) return SART_EXIT_OUTSIDE_SHELLS;
+  int code = -1;
   int hitLayer;
   {
     int b = int((radialDist - G.shellRhoMin) * G.shellInvStep);
     b = b < 0 ? 0 : (b > P.nShellGuide - 1 ? P.nShellGuide - 1 : b);
     hitLayer = S.shellGuide[b];
-    while (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;
-    if (!(sShell[hitLayer].R1 > radialDist)) return SART_EXIT_NO_MIRROR_HIT;
-    if (hitLayer > 0 && radialDist < sShell[hitLayer - 1].R1pT) {
-      if (radialDist > sShell[hitLayer - 1].R1) return SART_EXIT_GLASS_FRONT;
-    }
+    if (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;   // first j with R1[j] > radialDist
+    if (!(sShell[hitLayer].R1 > radialDist)) code = SART_EXIT_NO_MIRROR_HIT;     // == R1[last]
+    const int below = hitLayer > 0 ? hitLayer - 1 : 0;
+    if (hitLayer > 0 && radialDist < sShell[below].R1pT && radialDist > sShell[below].R1) code = SART_EXIT_GLASS_FRONT;
   }
+  if (radialDist > sShell[nS - 1].R1) code = SART_EXIT_OUTSIDE_SHELLS;
+  if (opaque) code = SART_EXIT_OPAQUE;
+  if (!okPipe2) code = SART_EXIT_CLIP_PIPE_XRT;
+  if (!okPipe1) code = SART_EXIT_CLIP_PIPE_VT3;
+  if (!insideExit) code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
+  if (code >= 0) return code;
   if (eRow) {
     const uint32_t we = w[5];
     eIdx = e0 + count_le(etA, we);
