@@ -278,7 +278,10 @@ int sart_emission_rates(int device, int nRadii, const double* temp_K, const doub
 
 /* ---- tier (a): trace pre-sampled rays. Replaces the body of traceAxion after the sampling block
  * (rt:1811-2221). origin_xyz = SoA [3][n] (rayOrigin), exit_xy = SoA [2][n] (pointExitCBMagneticField x,y;
- * z = lengthB), energy_keV [n]. Host buffers; copies are inside the call. */
+ * z = lengthB), energy_keV [n]. Host buffers; copies are inside the call. Precision 0 and 1 run the exact FP64 pipeline
+ * (every output array), precision 2 the FP32 pipeline (x, y, w, code, shell, energy, r; other optional arrays zeroed;
+ * the energy must be one of the tabulated energies as in the reference, rt:470 — otherwise the nearest one is traced
+ * and the ray is flagged SART_FLAG_INTERP_CLAMPED). */
 int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin_xyz, const double* exit_xy,
                           const double* energy_keV, const sart_ray_out_t* out);
 /* Same with DEVICE pointers (inputs resident in HBM, outputs left in HBM); asynchronous on sart_stream(). */

@@ -184,6 +184,10 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   sart_interp1d_t I[3];
   for (int k = 0; k < 3; ++k) I[k] = sart_interp1d_t{int32_t(h->h_tab[k][0].size()), 0, h->h_tab[k][0].data(), h->h_tab[k][1].data()};
   fast::derive_params(h->setup, P, &h->fparams);
+  if (h->h_energies.size() > 1) {
+    h->fparams.enE0 = h->h_energies.front();
+    h->fparams.enInvStep = double(h->h_energies.size() - 1) / (h->h_energies.back() - h->h_energies.front());
+  }
   std::vector<ShellF64> sh64(SART_MAX_SHELLS);
   derive_shells(h->setup, sh64.data());
   std::vector<fast::ShellFast> shf(SART_MAX_SHELLS);
@@ -242,6 +246,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
       SART_CUDA(cudaMemcpy(base + h->fast_refl_off, re.data(), re.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     fast::FastTables& F = h->ftables;
+    F.energies = h->tables.energies;
     F.radiusCDF = h->tables.fluxRadiusCDF;
     F.energyCDF = h->tables.diffFluxCDFs;
     F.radiusGuide = reinterpret_cast<const uint16_t*>(base + rgOff);
@@ -556,7 +561,11 @@ int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin
   if (rc) return rc;
   if (n && (!d_origin || !d_exit || !d_energy)) return fail(SART_ERR_ARG, "sart_trace_presampled: NULL input");
   DeviceGuard dg(h->device);
-  SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, d_origin, d_exit, d_energy, *d_out, h->stream));
+  if (h->precision == 2 && h->ftables.energies)
+    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, h->ftables, h->masses[0], n, d_origin, d_exit, d_energy, *d_out,
+                                    h->sm_count, h->stream));
+  else
+    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, d_origin, d_exit, d_energy, *d_out, h->stream));
   return SART_OK;
 }
 
@@ -614,7 +623,13 @@ int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin, cons
   SART_CUDA(cudaMemcpyAsync(dO, origin, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SART_CUDA(cudaMemcpyAsync(dX, exitxy, 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SART_CUDA(cudaMemcpyAsync(dE, energy, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, dO, dX, dE, dev, h->stream));
+  if (h->precision == 2 && h->ftables.energies) {
+    // the f32 pipeline fills x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
+    SART_CUDA(cudaMemsetAsync(base + inBytes, 0, outBytes, h->stream));
+    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, h->ftables, h->masses[0], n, dO, dX, dE, dev, h->sm_count, h->stream));
+  } else {
+    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, dO, dX, dE, dev, h->stream));
+  }
   return copy_out(h, n, *out, dev);
 }
 

@@ -40,6 +40,7 @@ struct FastParams {
   // X-ray source
   double srcX, srcY, srcZ, srcRadius, colDz, srcRadius2;
   float srcEnergy;
+  double enE0, enInvStep;   // uniform-grid guess of an energy's index in the tabulated energies (pre-sampled rays)
   int32_t telKind, nShells, reflKind, nCoatings, stage, nStripHalf, testXray, parallelSource;
   int32_t layers[SART_MAX_COATINGS];
   uint32_t flags;
@@ -86,6 +87,7 @@ struct FastTables {
   const double* energyCDF;       // [nRadii][nEnergies] f64, fallback only
   const uint32_t* energyThr;     // [nRadii][thr_pitch(nEnergies)]
   const uint16_t* energyGuide;   // [nRadii][kEnGuide]
+  const double* energies;        // [nEnergies] keV (pre-sampled rays: energy -> index)
   const EnergyLUT* elut;         // [nEnergies + 1]
   const GasLUT* glut;            // [nEnergies + 1]
   // reflectivity pre-interpolated along the energy axis at every tabulated energy: [coat][nEnergies + 1][nAngles];

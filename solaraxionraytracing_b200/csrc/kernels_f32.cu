@@ -108,6 +108,10 @@ struct Head32 {
   uint32_t w[6];
   int rIdx;
   uint16_t guide;
+  // pre-sampled rays (tier (a)): exit-disc point, slopes and energy index supplied by the caller instead of drawn
+  float ex, ey, sx, sy;
+  int eIdx;
+  bool offGrid;
 };
 __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S, uint64_t seed,
                                                uint64_t ray, Head32& h) {
@@ -129,7 +133,8 @@ __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTa
 }
 
 // Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
-template <bool kWolter>
+// kPre: the sampling block is skipped, the ray comes from the head record (sart_trace_presampled).
+template <bool kWolter, bool kPre = false>
 __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
                                          const Head32& h, Rec32& rec) {
   const ShellF32* __restrict__ sShell = S.shell;
@@ -141,7 +146,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   int eIdx;
   int e0 = 0;
   const uint32_t* eRow = nullptr;
-  if (!P.testXray) {
+  if (kPre) {
+    ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid;
+  } else if (!P.testXray) {
     const int rIdx = h.rIdx;
     e0 = int(h.guide) & ~3;
     eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
@@ -667,6 +674,63 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
   }
 }
 
+// ---- tier (a): pre-sampled rays, structure of arrays in HBM -> per-ray records in HBM -------------------------------
+// 48 B in (origin x, y, z; exit-disc x, y; energy — f64, coalesced) and 32 B out (x, y, w f64; code, shell i32) per ray.
+// The slopes are formed in FP64 from the caller's points (the origin is 1.5e14 mm away), everything after that is the
+// FP32 pipeline. The energy is mapped to its index in the tabulated energies (the reference only ever traces tabulated
+// energies, rt:470); an energy that is not a table value is traced at the nearest one and flagged INTERP_CLAMPED.
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, SART_F32_MINBLOCKS)
+k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
+                       const __grid_constant__ FastTables T, double mAxion2, size_t n, const double* __restrict__ origin,
+                       const double* __restrict__ exitxy, const double* __restrict__ energy, double* __restrict__ ox,
+                       double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
+                       int32_t* __restrict__ oshell, double* __restrict__ oenergy, double* __restrict__ orad) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem32 S;
+  unsigned char* tail;
+  smem_layout32(P, smem, S, tail);
+  smem_fill32(P, T, S);
+  __syncthreads();
+  const size_t stride = size_t(gridDim.x) * kBlock;
+  for (size_t i = size_t(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
+    const double Ox = origin[i], Oy = origin[n + i], Oz = origin[2 * n + i];
+    const double ex = exitxy[i], ey = exitxy[n + i], E = energy[i];
+    Head32 hd;
+    const double invD = rcp_nr(P.lengthB - Oz);
+    hd.ex = float(ex); hd.ey = float(ey);
+    hd.sx = float((ex - Ox) * invD); hd.sy = float((ey - Oy) * invD);
+    // energy -> index of the tabulated energy: uniform-grid guess, then the table decides
+    const double Ec = fmax(E, 0.03);
+    int k = int(rint((E - P.enE0) * P.enInvStep));
+    k = k < 0 ? 0 : (k > P.nEnergies - 1 ? P.nEnergies - 1 : k);
+    if (fmax(__ldg(T.energies + k), 0.03) != Ec) {
+      k = lower_bound_window(T.energies, 0, P.nEnergies, Ec);   // first tabulated energy >= Ec
+      if (k > P.nEnergies - 1) k = P.nEnergies - 1;
+      if (k > 0 && fmax(__ldg(T.energies + k), 0.03) != Ec) {
+        const double below = fmax(__ldg(T.energies + k - 1), 0.03);   // entries under 0.03 keV are traced at 0.03 (rt:471)
+        if (below == Ec || fabs(below - Ec) < fabs(__ldg(T.energies + k) - Ec)) --k;
+      }
+    }
+    hd.eIdx = k;
+    hd.offGrid = fmax(__ldg(T.energies + k), 0.03) != Ec;
+    RayResult r;
+    RecordSink<true> sink{r, mAxion2};
+    Rec32 rec;
+    const int c0 = stage_a32<kWolter, true>(P, G, T, S, hd, rec);
+    if (c0 >= 0) sink.fail(c0);
+    else stage_b32<kWolter>(P, G, T, S, rec, sink);
+    int code = r.code;
+    double wd = 0.0;
+    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
+    else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
+    const bool tl = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
+    ox[i] = tl ? r.x : 0.0; oy[i] = tl ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tl ? r.shell : -1;
+    if (oenergy) oenergy[i] = Ec;
+    if (orad) orad[i] = tl ? r.r : 0.0;
+  }
+}
+
 static size_t smem_bytes32(const FastParams& P) {
   return ((size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15)) + size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2 +
          ((size_t(P.nShellGuide) + 15) & ~size_t(15)) + kWarps * sizeof(WarpCounters);
@@ -692,6 +756,27 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
   kern<<<grid, fast::kBlock, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
+                                  size_t n, const double* origin, const double* exitxy, const double* energy,
+                                  const sart_ray_out_t& o, int smCount, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes32(P);
+  auto kern = wolter ? fast::k_trace_presampled_f32<true> : fast::k_trace_presampled_f32<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int perSM = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  const uint64_t want = (n + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * perSM;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, G, T, mAxion * mAxion, n, origin, exitxy, energy, o.x, o.y, o.w, o.code, o.shell,
+                                        o.energy, o.r);
   return cudaGetLastError();
 }
 
