@@ -340,6 +340,11 @@ int sart_measure_fma_peak(int device, int fp64, double* tflops);
  * draws them (rt:433-436, 418-419, 464): phi_sun, theta_sun, u_radius, u_disk_r, u_disk_phi, u_energy. */
 void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]);
 
+/* ---- the integer form of the inverse-CDF sampling (host helper, exported for tests): thr[i] = the smallest 32-bit
+ * word w whose uniform u = (w + 0.5) 2^-32 satisfies cdf[i] < u, saturated at 0xffffffff. lowerBound(cdf, u) (rt:437,
+ * 464) is then the number of thresholds <= w, for every w < 0xffffffff. */
+void sart_cdf_thresholds(const double* cdf, int n, uint32_t* thr);
+
 #ifdef __cplusplus
 }
 #endif

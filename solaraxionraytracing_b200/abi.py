@@ -197,4 +197,5 @@ SIGNATURES = {
                                        c_double_p, c_double_p, c_double_p, C.c_double, c_double_p,
                                        C.POINTER(C.c_uint64)]),
     "sart_ray_uniforms": (None, [C.c_uint64, C.c_uint64, c_double_p]),
+    "sart_cdf_thresholds": (None, [c_double_p, C.c_int, C.POINTER(C.c_uint32)]),
 }

@@ -375,6 +375,11 @@ int sart_device_count(void) {
   return n;
 }
 
+void sart_cdf_thresholds(const double* cdf, int n, uint32_t* thr) {
+  if (!cdf || !thr || n < 0) return;
+  for (int i = 0; i < n; ++i) thr[i] = cdf_threshold(cdf[i]);
+}
+
 void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {
   uint32_t w[6];
   ray_words(seed, ray, w);

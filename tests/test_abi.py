@@ -113,3 +113,36 @@ def test_product_does_not_import_oracle():
         txt = f.read_text()
         for needle in ("import oracle", "from oracle", "liboracle", "oracle/"):
             assert needle not in txt, (f, needle)
+
+
+def test_integer_cdf_thresholds_are_exact(rt):
+    """sart_cdf_thresholds: `cdf[i] < (w + 0.5) 2^-32` <=> `w >= thr[i]`, checked with exact rational arithmetic at the
+    words around every threshold, and lowerBound == number of thresholds <= w on a realistic CDF row."""
+    from fractions import Fraction
+    rng = np.random.default_rng(7)
+    cdf = np.sort(np.concatenate([rng.random(200), [0.0, 1.0, 2.0 ** -33, 1 - 2.0 ** -33, 0.5, 0.25 + 2.0 ** -34,
+                                                        3.0 / 2 ** 32, 3.5 / 2 ** 32, (2 ** 32 - 1.5) / 2 ** 32]]))
+    thr = np.zeros(cdf.size, dtype=np.uint32)
+    rt.lib.sart_cdf_thresholds(cdf.ctypes.data_as(abi.c_double_p), cdf.size, thr.ctypes.data_as(C.POINTER(C.c_uint32)))
+    for c, t in zip(cdf, thr):
+        t = int(t)
+        for w in {max(t - 1, 0), t, min(t + 1, 2 ** 32 - 2)}:
+            if w >= 2 ** 32 - 1:
+                continue                                      # the saturated word is resolved on the f64 table
+            below = Fraction(float(c)) < Fraction(2 * w + 1, 2 ** 33)
+            assert below == (w >= t) or t == 2 ** 32 - 1, (c, t, w)
+    nan = np.array([np.nan]); out = np.zeros(1, dtype=np.uint32)
+    rt.lib.sart_cdf_thresholds(nan.ctypes.data_as(abi.c_double_p), 1, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert out[0] == 0xFFFFFFFF                               # empty shells (0/0 rows, rt:2674) are never selected
+    from solaraxionraytracing_b200 import tables
+    from oracle import oracle as orc
+    em = tables.synthetic_emission(40, 300, "abc")
+    _, dc = orc.build_cdfs(em.radii, em.energies, em.emRates)
+    row = np.ascontiguousarray(dc[7])
+    th = np.zeros(row.size, dtype=np.uint32)
+    rt.lib.sart_cdf_thresholds(row.ctypes.data_as(abi.c_double_p), row.size, th.ctypes.data_as(C.POINTER(C.c_uint32)))
+    w = rng.integers(0, 2 ** 32 - 1, size=200_000, dtype=np.uint64)
+    u = (w.astype(np.float64) + 0.5) / 4294967296.0          # exact in f64
+    want = np.searchsorted(row, u, side="left")               # std/algorithm lowerBound
+    got = np.searchsorted(th.astype(np.uint64), w, side="right")   # number of thresholds <= w
+    assert np.array_equal(got, want)
