@@ -269,7 +269,8 @@ def presampled_leg(tr, torch, device, n_unique: int = 1 << 20, repeat: int = 16)
             "exact_fp64_kernel_rays_per_s": n / (ms_by_mode[0] * 1e-3),
             "bytes_per_ray": 80, "e2e_rays_per_s": e2e, "e2e_h2d_bytes": 48 * n_unique, "e2e_d2h_bytes": 32 * n_unique,
             "roofline": {"bound": "hbm", "achieved": rate * 80 / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": rate * 80 / 1e9 / hbm,
+                         "frac": rate * 80 / 1e9 / hbm, "traffic": ncu_traffic("k_trace_presampled_f32"),
+                         "algorithmic_bytes": 80 * n,
                          "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "note": "80 B of HBM traffic per ray (48 in, 32 out); the rest of the time is the per-ray "
                                  "arithmetic and table gathers of the fused kernel"}}
@@ -296,6 +297,14 @@ def records_leg(tr, torch, n: int = 1 << 24, reps: int = 3):
     return {"api": "sart_trace_mc_rays (traceAxionWrapper, per-ray records to host)", "rays_per_call": n,
             "value": n / dt, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32 * n,
             "d2h_GBps": 32 * n / dt / 1e9, "passed_fraction": float((hc.bitwise_and(0xff) == 0).double().mean())}
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())[kernel]["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def run_ours(args):
@@ -429,7 +438,11 @@ def run_ours(args):
             "gpu_launches": K,
             "clocks": clocks,
             "roofline": {"bound": "fp64" if fp64 else "fp32", "achieved": achieved, "peak": peak.value,
-                         "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
+                         "traffic": ncu_traffic({"exact": "k_trace_mc_image", "fast": "k_trace_mc_fast",
+                                                 "f32": "k_trace_mc_f32"}[precision]) if R == 10**9 else None,
+                         "traffic_note": "DRAM bytes per 1e9-ray launch from the committed ncu capture: the tables' "
+                                         "cold misses; the path has no per-ray HBM traffic",
                          "kernel": {"exact": "k_trace_mc_image", "fast": "k_trace_mc_fast", "f32": "k_trace_mc_f32"}[precision],
                          "kernel_ms": k_ms, "flop_per_ray": F_RAY_LLNL,
                          "peak_source": "sart_measure_fma_peak in this run (MEASURED_PEAKS.json has no CUDA-core "

@@ -1,15 +1,20 @@
+# Full validation on one B200: GPU test-suite, smoke, bench line, ncu launch list of the same bench command, and full ncu
+# captures of the dominant fused kernel and of the HBM-bound pre-sampled kernel. Usage: bash tools/gpu_validate.sh <tag>
 set -x
-mkdir -p gpurun_out/r01b
+out=gpurun_out/${1:-validate}
+mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 nproc
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r01b/pytest_gpu.log
-cat gpurun_out/r01b/pytest_gpu.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r01b/bench.json 2> gpurun_out/r01b/bench.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $out/pytest_gpu.log
+cat $out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; tail -2 $out/smoke.log
+timeout 600 python bench.py > $out/bench.json 2> $out/bench.err
 rc=$?
-tail -3 gpurun_out/r01b/bench.err; cat gpurun_out/r01b/bench.json
+tail -3 $out/bench.err; cat $out/bench.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_reference.json 2>> $out/bench.err; cat $out/bench_reference.json
 if [ $rc -eq 0 ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01b/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r01b/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_mc_fast -c 1 -o gpurun_out/r01b/prof_fast python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-presampled > gpurun_out/r01b/ncu_full.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_presampled -c 1 -o gpurun_out/r01b/prof_presampled python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r01b/ncu_full2.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_mc_f32 --launch-skip 1 -c 1 -o $out/prof_f32 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-presampled > $out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_presampled_f32 -c 1 -o $out/prof_presampled_f32 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_full2.log 2>&1
 fi
-ls -la gpurun_out/r01b
+ls -la $out
