@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--chunk", type=float, default=4e9, help="rays per launch per GPU")
     ap.add_argument("--check", type=float, default=0, help="also verify shard-invariance on this many rays")
     ap.add_argument("--out", default="")
+    ap.add_argument("--precision", type=int, default=2, help="0 exact, 1 fast, 2 f32")
     a = ap.parse_args()
     import torch
     from solaraxionraytracing_b200 import multi_gpu, output, raytracer as rt, tables
@@ -47,7 +48,7 @@ def main():
     setup = rt.newExperimentSetup("BabyIAXO", "InGridIAXO", "vacuum", "XMM", 0)
     fs = rt.FullRaytraceSetup(setup, tb)
     tr = rt.RayTracer(fs, local)
-    tr.set_precision(1)
+    tr.set_precision(a.precision)
     setup_s = time.perf_counter() - t0
     stream = torch.cuda.ExternalStream(tr.stream, device=local)
     views = multi_gpu.device_views(tr, local)
@@ -89,7 +90,7 @@ def main():
                   and bool(np.allclose(alone.image, sharded.image, rtol=1e-9, atol=0)))
     if rank == 0:
         line = {"config": "5: BabyIAXO+InGridIAXO+vacuum+XMM (config_default.toml), Primakoff from AGSS09, Henke gold",
-                "n_gpus": world, "rays": total, "device_ms": ms, "rays_per_s": total / (ms * 1e-3), "setup_s": round(setup_s, 2),
+                "n_gpus": world, "precision": a.precision, "rays": total, "device_ms": ms, "rays_per_s": total / (ms * 1e-3), "setup_s": round(setup_s, 2),
                 "n_rays": c["n_rays"], "n_passed": c["n_passed"], "passed_fraction": c["n_passed"] / max(1, c["n_rays"]),
                 "sum_w": c["sum_w"], "rel_mc_error_total_flux": float(np.sqrt(c["sum_w2"]) / c["sum_w"]) if c["sum_w"] else None,
                 "n_exit": c["n_exit"], "shard_invariant": ok}
