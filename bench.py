@@ -435,7 +435,7 @@ def run_ours(args):
                     "note": "sart_reset_image + sart_trace_mc + sart_read_image per step through the C-ABI; the path "
                             "has no per-step host inputs (rays are generated in-kernel from Philox), tables are "
                             "resident per run (config.table_upload_s)"},
-            "gpu_launches": K,
+            "gpu_launches": K * (2 if precision != "exact" else 1),   # fused trace kernel + image-replica fold per step
             "clocks": clocks,
             "roofline": {"bound": "fp64" if fp64 else "fp32", "achieved": achieved, "peak": peak.value,
                          "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,

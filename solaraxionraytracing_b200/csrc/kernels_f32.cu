@@ -113,11 +113,15 @@ struct Head32 {
   int eIdx;
   bool offGrid;
 };
+// kPlain (here and below): the kernel variant for the plain run — solar source, vacuum stage, telescope not turned, no
+// ignore* flag — in which those run-wide switches are compile-time constants instead of uniform branches (~5 % of the
+// instructions); every other setup takes the generic variant.
+template <bool kPlain = false>
 __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S, uint64_t seed,
                                                uint64_t ray, Head32& h) {
   ray_words(seed, ray, h.w);
   h.rIdx = 0; h.guide = 0;
-  if (!P.testXray) {
+  if (kPlain || !P.testXray) {
     const uint32_t wr = h.w[2];
     const int r0 = int(S.radGuide[wr >> (32 - kRadGuideBits)]) & ~3;
     int rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
@@ -134,7 +138,7 @@ __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTa
 
 // Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
 // kPre: the sampling block is skipped, the ray comes from the head record (sart_trace_presampled).
-template <bool kWolter, bool kPre = false>
+template <bool kWolter, bool kPre = false, bool kPlain = false>
 __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
                                          const Head32& h, Rec32& rec) {
   const ShellF32* __restrict__ sShell = S.shell;
@@ -148,7 +152,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   const uint32_t* eRow = nullptr;
   if (kPre) {
     ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid;
-  } else if (!P.testXray) {
+  } else if (kPlain || !P.testXray) {
     const int rIdx = h.rIdx;
     e0 = int(h.guide) & ~3;
     eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
@@ -223,7 +227,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
 
   // ================= telescope frame rt:1888-1905
   float dx = sx, dy = sy, dz = 1.0f, z0 = 0.0f;
-  if (P.rotated) {
+  if (!kPlain && P.rotated) {
     const float zt = 0.0f - G.halfLenTel;
     const float xr = x0 * G.cosTX + zt * G.sinTX;
     float zr = zt * G.cosTX - x0 * G.sinTX;
@@ -312,7 +316,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
 }
 
 // Stage B in FP32: the two reflections, nickel / degenerate exits, detector plane, weights, window (rt:1971-2221).
-template <bool kWolter, class Sink>
+template <bool kWolter, bool kPlain = false, class Sink>
 __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
                                           const Rec32& rec, Sink& sink) {
   const ShellF32* __restrict__ sShell = S.shell;
@@ -428,7 +432,7 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
     const float ya = -atan_small(ty) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
     float pre = __cosf(ya);
     const float path2f = rec.path2;
-    if (P.stage == SART_SK_VACUUM) {
+    if (kPlain || P.stage == SART_SK_VACUUM) {
       out.convVac = P.convK * path2f;
     } else {
       const float2 gv = __ldg(reinterpret_cast<const float2*>(T.glut) + eIdx);
@@ -443,20 +447,24 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
       pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
     }
     float refl = 1.0f;
-    if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
+    const uint32_t flags = kPlain ? 0u : P.flags;
+    if (!(flags & SART_CF_IGNORE_REFLECTION)) {
       const float* zt = T.reflE + (size_t(sh.coat) * (P.nEnergies + 1) + eIdx) * P.nAngles;
       const float a1 = asin_small(sinA1) * 57.29577951308232f, a2 = asin_small(sinA2) * 57.29577951308232f;
       refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
     }
     out.wPre = double(refl) * double(pre);
-    if (Sink::kFold) out.wPre *= conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
+    if (Sink::kFold)
+      out.wPre *= kPlain ? double(out.convVac)
+                         : conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
   }
+  const uint32_t flags = kPlain ? 0u : P.flags;
   out.clamped = clamped;
   out.shell = hitLayer;
   out.code = -1;
   // ================= window aperture rt:2139-2147
   const float rw2 = fmaf(xw, xw, yw * yw);
-  if ((!(P.flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > G.radiusWindow2) || fabsf(xw) > G.chipCX || fabsf(yw) > G.chipCY) {
+  if ((!(flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > G.radiusWindow2) || fabsf(xw) > G.chipCX || fabsf(yw) > G.chipCY) {
     out.windowMiss = true; out.wPost = 0.0; out.x = out.y = out.r = 0.0; out.bin = -1;
     sink.hit(out);
     return;
@@ -475,10 +483,10 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
       sb = (u > 0.0f && fi < float(P.nStripHalf) && off > 0.0f && off < G.stripWidth) ? 1 : 0;
     }
     const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
-    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) post *= double(tw);
+    if (!(flags & SART_CF_IGNORE_DET_WINDOW)) post *= double(tw);
   }
-  if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
-  if (!(P.flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
+  if (!(flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
+  if (!(flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
   out.wPost = post;
   const float xc = G.chipCX - xw, yc = yw + G.chipCY;
   out.r = double(rw2 > 1e-30f ? rw2 * rsqrtf_nr(rw2) : 0.0f);
@@ -508,7 +516,7 @@ __device__ __forceinline__ void flush_counters(sart_counters_t* c, const WarpCou
 }
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
-template <bool kWolter>
+template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock, SART_F32_MINBLOCKS)
 k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G, const __grid_constant__ FastTables T,
                double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
@@ -530,16 +538,16 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x;
   Head32 cur;
-  if (i < nRays) stage_a32_head(P, T, S, seed, first + i, cur);
+  if (i < nRays) stage_a32_head<kPlain>(P, T, S, seed, first + i, cur);
   while (i < nRays) {
     ++nIter;
     const uint64_t inext = i + stride;
     Head32 nxt;
-    if (inext < nRays) stage_a32_head(P, T, S, seed, first + inext, nxt);   // next ray's guide load goes out now
+    if (inext < nRays) stage_a32_head<kPlain>(P, T, S, seed, first + inext, nxt);   // next ray's guide load goes out now
     Rec32 rec;
-    const int code = stage_a32<kWolter>(P, G, T, S, cur, rec);
+    const int code = stage_a32<kWolter, false, kPlain>(P, G, T, S, cur, rec);
     if (code >= 0) sink.fail(code);
-    else stage_b32<kWolter>(P, G, T, S, rec, sink);
+    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     cur = nxt;
     i = inext;
   }
@@ -564,7 +572,7 @@ struct WarpQueue32 {
   int meta[kQueue32];   // hitLayer | eIdx << 8 | clamped << 30
 };
 
-template <bool kWolter>
+template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock, SART_F32_MINBLOCKS)
 k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                        const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed,
@@ -597,8 +605,8 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       int code = SART_N_EXIT_CODES;
       if (i < nRays) {
         Head32 hd;
-        stage_a32_head(P, T, S, seed, first + i, hd);
-        code = stage_a32<kWolter>(P, G, T, S, hd, rec);
+        stage_a32_head<kPlain>(P, T, S, seed, first + i, hd);
+        code = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
         ++nIter;
         if (code >= 0) sink.fail(code);
       }
@@ -621,7 +629,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       rec.path2 = Q.path2[pos];
       const int meta = Q.meta[pos];
       rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
-      stage_b32<kWolter>(P, G, T, S, rec, sink);
+      stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     }
     qn -= take;
     __syncwarp();
@@ -662,7 +670,7 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     stage_a32_head(P, T, S, seed, first + i, hd);
     const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
-    else stage_b32<kWolter>(P, G, T, S, rec, sink);
+    else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
     int code = r.code;
     double wd = 0.0;
     if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
@@ -719,7 +727,7 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
     Rec32 rec;
     const int c0 = stage_a32<kWolter, true>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
-    else stage_b32<kWolter>(P, G, T, S, rec, sink);
+    else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
     int code = r.code;
     double wd = 0.0;
     if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
@@ -744,8 +752,11 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P) + (compact ? fast::kWarps * sizeof(fast::WarpQueue32) : 0);
-  auto kern = compact ? (wolter ? fast::k_trace_mc_f32_compact<true> : fast::k_trace_mc_f32_compact<false>)
-                      : (wolter ? fast::k_trace_mc_f32<true> : fast::k_trace_mc_f32<false>);
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  auto kern = compact ? (wolter ? (plain ? fast::k_trace_mc_f32_compact<true, true> : fast::k_trace_mc_f32_compact<true, false>)
+                                : (plain ? fast::k_trace_mc_f32_compact<false, true> : fast::k_trace_mc_f32_compact<false, false>))
+                      : (wolter ? (plain ? fast::k_trace_mc_f32<true, true> : fast::k_trace_mc_f32<true, false>)
+                                : (plain ? fast::k_trace_mc_f32<false, true> : fast::k_trace_mc_f32<false, false>));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int perSM = 0;
