@@ -28,9 +28,9 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--numAngularScanPoints", type=int, default=50)
     ap.add_argument("--config", default="", help="path to a config.toml")
     ap.add_argument("--configPath", default="", help="directory holding config.toml")
-    ap.add_argument("--nRays", type=float, default=1e6, help="NumberOfPointsSun (rt:251)")
-    ap.add_argument("--seed", type=int, default=299792458)
-    ap.add_argument("--precision", choices=["f32", "fast", "exact"], default="f32")
+    ap.add_argument("--nRays", type=float, default=None, help="NumberOfPointsSun (rt:251); default [Run].nRays or 1e6")
+    ap.add_argument("--seed", type=int, default=None, help="default [Run].seed or 299792458 (rt:276)")
+    ap.add_argument("--precision", choices=["f32", "fast", "exact"], default=None)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--outputPath", default="", help="overrides [Resources].outputPath")
     return ap
@@ -67,22 +67,35 @@ def main(argv=None) -> int:
                               a.magnet, a.detectorInstall)
     print("Flags:", {n for n, on in vars(a).items() if on is True and n != "noPlots"})
     setup, res = cfgmod.setup_from_config(cfg_file, flags)
+    run = cfgmod.parseRun(cfgmod.load_config(cfg_file))
+    a.nRays = run.nRays if a.nRays is None else a.nRays
+    a.seed = run.seed if a.seed is None else a.seed
+    a.precision = a.precision or run.precision
     outpath = a.outputPath or res.outputPath
     tb = load_tables(rt, tables, res, setup, a.device)
     fs = rt.FullRaytraceSetup(setup, tb, outpath)
     n = int(a.nRays)
     with rt.RayTracer(fs, a.device) as tr:
         tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[a.precision])
+        if run.mAxion:
+            tr.set_axion_masses(run.mAxion)
         if a.angularScanMin == a.angularScanMax:
             print("start")
-            tr.enable_radial_hist()
+            if len(run.mAxion) <= 1:
+                tr.enable_radial_hist()
             tr.reset_image()
             tr.trace_mc(n, a.seed)
             result = tr.read_image()
-            radii = output.containment_radii_from_hist(*tr.read_radial_hist())
-            path = output.generateResultPlots(result, setup.detector.windowYear, outpath, radii=radii,
-                                              chipXMax=setup.consts.chipXMax, chipYMax=setup.consts.chipYMax)
-            print("wrote", path)
+            if len(run.mAxion) <= 1:
+                radii = output.containment_radii_from_hist(*tr.read_radial_hist())
+                path = output.generateResultPlots(result, setup.detector.windowYear, outpath, radii=radii,
+                                                  chipXMax=setup.consts.chipXMax, chipYMax=setup.consts.chipYMax)
+                print("wrote", path)
+            else:   # mass scan: one image per mass, total flux per mass on stdout
+                Path(outpath).mkdir(parents=True, exist_ok=True)
+                for m, c in zip(run.mAxion, result.counters):
+                    print(f"m_a = {m:.6g} eV: passed {c['n_passed']}, total flux {c['sum_w']:.6e}")
+                np.save(Path(outpath) / "axion_images_mass_scan.npy", result.image)
         else:
             angles, rel, _ = rt.performAngularScan(fs, a.angularScanMin, a.angularScanMax, a.numAngularScanPoints, n,
                                                    a.seed, tracer=tr)

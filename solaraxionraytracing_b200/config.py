@@ -53,6 +53,30 @@ def parseResources(cfg: dict) -> Resources:
     return Resources(**{k: r[k] for k in Resources.__dataclass_fields__ if k in r})
 
 
+@dataclass
+class Run:
+    """[Run] — NOT in the reference, whose values for these are hard-coded `let`s: NumberOfPointsSun (rt:251), the
+    `randomize` seed (rt:276) and mAxion (rt:255). Optional table; a strict superset of the reference's schema."""
+    nRays: int = 1_000_000
+    seed: int = 299792458
+    mAxion: tuple = ()          # eV; empty = the reference's 0.0853 eV; several values = a mass scan (gas stage)
+    precision: str = "f32"      # f32 | fast | exact
+
+
+def parseRun(cfg: dict) -> Run:
+    r = cfg.get("Run", {})
+    m = r.get("mAxion", ())
+    if isinstance(m, (int, float)):
+        m = (float(m),)
+    out = Run(nRays=int(r.get("nRays", 1_000_000)), seed=int(r.get("seed", 299792458)),
+              mAxion=tuple(float(x) for x in m), precision=str(r.get("precision", "f32")))
+    if out.precision not in ("f32", "fast", "exact"):
+        raise ValueError(f"[Run] precision = {out.precision!r}; expected f32, fast or exact")
+    if out.nRays < 0 or len(out.mAxion) > abi.MAX_MASSES:
+        raise ValueError("[Run] nRays must be >= 0 and at most %d axion masses can be scanned at once" % abi.MAX_MASSES)
+    return out
+
+
 def apply_config(setup: abi.Setup, cfg: dict, flags: int) -> abi.Setup:
     """Overrides the per-experiment defaults in `setup` with the [Magnet], [TestXraySource] and [DetectorInstallation]
     tables where the reference would (flag set or useConfig = true)."""

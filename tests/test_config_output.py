@@ -134,3 +134,14 @@ def test_cli_parser_has_the_reference_switches():
     from solaraxionraytracing_b200.__main__ import build_parser
     a = build_parser().parse_args(["--ignoreDetWindow", "--xrayTest", "--angularScanMax", "0.3", "--numAngularScanPoints", "14"])
     assert a.ignoreDetWindow and a.xrayTest and not a.magnet and a.angularScanMax == 0.3 and a.numAngularScanPoints == 14
+
+
+def test_run_table_is_an_optional_superset(tmp_path):
+    assert config.parseRun(config.load_config()) == config.Run()          # absent in the reference's default file
+    p = tmp_path / "config.toml"
+    p.write_text(config.DEFAULT_CONFIG.read_text() + '\n[Run]\nnRays = 5000000\nseed = 7\nmAxion = [0.01, 0.02]\nprecision = "exact"\n')
+    r = config.parseRun(config.load_config(p))
+    assert (r.nRays, r.seed, r.mAxion, r.precision) == (5_000_000, 7, (0.01, 0.02), "exact")
+    p.write_text(config.DEFAULT_CONFIG.read_text() + '\n[Run]\nprecision = "fp8"\n')
+    with pytest.raises(ValueError):
+        config.parseRun(config.load_config(p))
