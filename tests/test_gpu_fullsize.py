@@ -37,9 +37,9 @@ def _check_conservation(res, n):
     assert c["n_interp_clamped"] == 0
 
 
-@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("precision", [2, 1, 0])
 def test_config3_1e9_rays(rt, full_llnl, precision):
-    n = 1_000_000_000 if precision == 1 else 200_000_000
+    n = 1_000_000_000 if precision >= 1 else 200_000_000
     with rt.RayTracer(full_llnl) as tr:
         tr.set_precision(precision)
         tr.trace_mc(n, SEED)
@@ -66,7 +66,7 @@ def test_config5_babyiaxo_xmm_4e9_rays(rt):
     fs = rt.initFullSetup("BabyIAXO", "InGridIAXO", "vacuum", "XMM")
     n = 4_000_000_000
     with rt.RayTracer(fs) as tr:
-        tr.set_precision(1)
+        tr.set_precision(2)
         tr.trace_mc(n, 4, first_ray=3_000_000_000)     # crosses 2^32
         res = tr.read_image()
         _check_conservation(res, n)
@@ -89,7 +89,7 @@ def test_weight_linear_in_exposure_and_flags(rt, full_llnl):
 
     def run(setup):
         with rt.RayTracer(rt.FullRaytraceSetup(setup, full_llnl.tables)) as tr:
-            tr.set_precision(1)
+            tr.set_precision(2)     # the ignore* flags select the generic (non-"plain") kernel variant
             tr.trace_mc(n, 11)
             return tr.read_image()
 
