@@ -251,26 +251,34 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   // ================= opaque structures rt:1635-1704
   bool opaque = false;
   if (kWolter) {
+    // The spider is n equally spaced arms of half-width a: "|phi - k 360/n| <= a for some k", with phi = acos(x/rho) as
+    // the reference computes it (rt:1632, mirror-symmetric in y), is cos(n phi) >= cos(n a), and cos(n phi) is the
+    // Chebyshev polynomial T_n(x/rho): four doublings for XMM's 16 arms, T_6 for Abrixas' 6 — no inverse trigonometry.
     const bool xmm = P.telKind == SART_TK_XMM;
     bool hit = false;
     const float zs = xmm ? -85.0f : -35.0f;
-    const float phiF = acosf(x0 * invRho0) * 57.29577951308232f;
     const float xs = fmaf(zs, tx, x0), ys = fmaf(zs, ty, y0);
-    const float phiS = acosf(xs * rsqrtf(xs * xs + ys * ys)) * 57.29577951308232f;
+    const float cF = x0 * invRho0, cS = xs * rsqrtf_nr(fmaf(xs, xs, ys * ys));
     if (xmm) {
       if (radialDist <= 64.7f) hit = true;
       else if (radialDist < 151.6f && radialDist > (151.6f - 20.9f)) hit = true;
       else {
-        const float a = fabsf(phiF - 22.5f * rintf(phiF * (1.0f / 22.5f)));
-        const float b = fabsf(phiS - 22.5f * rintf(phiS * (1.0f / 22.5f)));
-        hit = (a <= 1.145f) || (b <= 1.145f);
+        auto t16 = [](float c) {
+          c = fmaf(2.0f * c, c, -1.0f); c = fmaf(2.0f * c, c, -1.0f); c = fmaf(2.0f * c, c, -1.0f);
+          return fmaf(2.0f * c, c, -1.0f);
+        };
+        constexpr float kCos = 0.94931733f;   // cos(16 * 1.145 deg)
+        hit = (t16(cF) >= kCos) || (t16(cS) >= kCos);
       }
     } else {
       if (radialDist < 37.5f) hit = true;
       else {
-        const float a = fabsf(phiF - 60.0f * rintf(phiF * (1.0f / 60.0f)));
-        const float b = fabsf(phiS - 60.0f * rintf(phiS * (1.0f / 60.0f)));
-        hit = (a <= 3.75f) || (b <= 3.75f);
+        auto t6 = [](float c) {
+          const float c2 = c * c;
+          return fmaf(c2, fmaf(c2, fmaf(c2, 32.0f, -48.0f), 18.0f), -1.0f);
+        };
+        constexpr float kCos = 0.92387953f;   // cos(6 * 3.75 deg)
+        hit = (t6(cF) >= kCos) || (t6(cS) >= kCos);
       }
     }
     opaque = hit;
