@@ -79,3 +79,43 @@ def test_two_ranks_gloo_equal_single_run(tmp_path, oracle):
     assert np.allclose(z["img"], img, rtol=1e-12, atol=0)
     assert np.allclose(z["img2"], img2, rtol=1e-12, atol=0)
     assert abs(float(z["sum_w"]) / cnt[0]["sum_w"] - 1) < 1e-12
+
+
+class _FakeTracer:
+    """Stands in for a RayTracer in performAngularScan: the flux of a scan point is a function of its angle and of
+    the global ray range it was asked to trace, so a wrong shard offset or a point traced twice shows up in the sum."""
+
+    def angular_scan(self, angles, n_rays, seed, want_images=False, first_ray=0):
+        a = np.asarray(angles, dtype=np.float64)
+        first = first_ray + n_rays * np.arange(a.size)
+        return np.cos(a) * 1e-3 + first.astype(np.float64) * 1e-12 + seed * 1e-15, [{}] * a.size, None
+
+
+def _scan_worker(rank: int, world: int, port: int, out_path: str):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    from solaraxionraytracing_b200 import raytracer as rt
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    angles, rel, flux = rt.performAngularScan(None, 0.0, 0.3, 7, nRays=1000, seed=5, tracer=_FakeTracer(), rank=rank, world=world)
+    if rank == 1:
+        np.savez(out_path, angles=angles, rel=rel, flux=flux)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_angular_scan_sharded_by_scan_points(tmp_path):
+    """performAngularScan over 2 ranks (gloo): contiguous blocks of scan points, scan point i traces the global rays
+    [i n, (i+1) n) whichever rank owns it, fluxes summed over ranks — equal to the unsharded scan on every rank."""
+    import torch.multiprocessing as mp
+    from solaraxionraytracing_b200 import raytracer as rt
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "scan.npz")
+    mp.spawn(_scan_worker, args=(2, port, out), nprocs=2, join=True)
+    z = np.load(out)
+    angles, rel, flux = rt.performAngularScan(None, 0.0, 0.3, 7, nRays=1000, seed=5, tracer=_FakeTracer())
+    assert np.array_equal(z["angles"], angles) and np.allclose(angles, np.linspace(0.0, 0.3, 7))
+    assert np.allclose(z["flux"], flux, rtol=1e-15) and np.allclose(z["rel"], rel, rtol=1e-15)
+    assert rel.max() == 1.0
