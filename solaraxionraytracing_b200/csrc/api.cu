@@ -426,7 +426,7 @@ void sart_destroy(sart_handle_t* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
-  cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n); cudaFree(h->d_rep);
+  cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n); cudaFree(h->d_rep); cudaFree(h->d_mass_acc);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -666,8 +666,15 @@ int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   DeviceGuard dg(h->device);
   if (h->precision >= 1 && h->n_masses > 1) {   // the mass scan has one implementation (FP64 algebra) for modes 1 and 2
+    const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS, accLen = plane * SART_MAX_MASSES;
+    if (!h->d_mass_acc) {
+      SART_CUDA(cudaMalloc(&h->d_mass_acc, 2 * accLen * sizeof(double)));
+      SART_CUDA(cudaMemsetAsync(h->d_mass_acc, 0, 2 * accLen * sizeof(double), h->stream));
+    }
     SART_CUDA(launch_mc_image_fast_masses(h->fparams, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays, seed,
-                                          h->d_image, h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+                                          h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
+    SART_CUDA(launch_fold_mass_acc(h->d_mass_acc, h->d_mass_acc + accLen, h->n_masses, plane, h->d_image, h->d_image_w2,
+                                   h->stream));
     return SART_OK;
   }
   if (h->precision >= 1) {

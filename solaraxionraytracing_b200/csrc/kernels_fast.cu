@@ -680,7 +680,6 @@ k_trace_mc_fast_masses(const __grid_constant__ FastParams P, const __grid_consta
     nPassed[k] = nZero[k] = nTill[k] = 0u;
   }
   unsigned int nIter = 0;
-  const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS;
   const uint64_t stride = uint64_t(gridDim.x) * kBlock;
   for (uint64_t b = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31); b < nRays; b += stride) {   // warp-uniform
     const uint64_t i = b + lane;
@@ -718,8 +717,10 @@ k_trace_mc_fast_masses(const __grid_constant__ FastParams P, const __grid_consta
           ++nPassed[k];
           sumW[k] += w; sumW2[k] += w * w; sumX[k] += x; sumY[k] += y; sumR[k] += rr;
           if (bin >= 0) {
-            atomicAdd(image + size_t(m) * plane + bin, w);
-            atomicAdd(imageW2 + size_t(m) * plane + bin, w * w);
+            // mass-major accumulators [bin][SART_MAX_MASSES]: the 32 lanes (= 32 masses) of this warp add to 256
+            // consecutive bytes instead of to 32 image planes 512 KiB apart; k_fold_mass_acc transposes afterwards
+            atomicAdd(image + size_t(bin) * SART_MAX_MASSES + m, w);
+            atomicAdd(imageW2 + size_t(bin) * SART_MAX_MASSES + m, w * w);
           }
         } else {
           ++nZero[k];

@@ -29,6 +29,26 @@ cudaError_t launch_fold_replicas(double* rep, double* rep2, int nRep, size_t str
   return cudaGetLastError();
 }
 
+// Mass scan: adds the mass-major accumulators acc[bin][SART_MAX_MASSES] of a launch to the images [mass][bin] and clears them.
+__global__ void __launch_bounds__(256) k_fold_mass_acc(double* __restrict__ acc, double* __restrict__ acc2, int nMasses,
+                                                       size_t plane, double* __restrict__ image, double* __restrict__ imageW2) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;   // = bin * SART_MAX_MASSES + mass
+  if (i >= plane * SART_MAX_MASSES) return;
+  const int m = int(i % SART_MAX_MASSES);
+  const size_t bin = i / SART_MAX_MASSES;
+  const double a = acc[i], b = acc2[i];
+  if (a != 0.0 || b != 0.0) {
+    acc[i] = 0.0; acc2[i] = 0.0;
+    if (m < nMasses) { image[size_t(m) * plane + bin] += a; imageW2[size_t(m) * plane + bin] += b; }
+  }
+}
+cudaError_t launch_fold_mass_acc(double* acc, double* acc2, int nMasses, size_t plane, double* image, double* imageW2,
+                                 cudaStream_t s) {
+  const size_t n = plane * SART_MAX_MASSES;
+  k_fold_mass_acc<<<unsigned((n + 255) / 256), 256, 0, s>>>(acc, acc2, nMasses, plane, image, imageW2);
+  return cudaGetLastError();
+}
+
 template <typename T, int kChains>
 __global__ void __launch_bounds__(256) k_fma_peak(T* out, T a, T b, int iters) {
   T acc[kChains];

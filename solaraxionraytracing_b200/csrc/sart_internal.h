@@ -68,6 +68,7 @@ struct sart_handle {
   sart_counters_t* d_counters = nullptr;  // [n_masses]
   // image replicas of the throughput kernels (cleared by the fold that follows every launch)
   double* d_rep = nullptr;      // [2][n_rep][256*256]
+  double* d_mass_acc = nullptr; // [2][256*256][SART_MAX_MASSES] mass-major accumulators of the mass-scan kernel
   int n_rep = 0;
   // optional radial histogram of the passed rays (sart_enable_radial_hist)
   double* d_rad_w = nullptr;
