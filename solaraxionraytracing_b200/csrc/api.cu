@@ -665,14 +665,18 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   DeviceGuard dg(h->device);
-  if (h->precision >= 1 && h->n_masses > 1) {   // the mass scan has one implementation (FP64 algebra) for modes 1 and 2
+  if (h->precision >= 1 && h->n_masses > 1) {
     const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS, accLen = plane * SART_MAX_MASSES;
     if (!h->d_mass_acc) {
       SART_CUDA(cudaMalloc(&h->d_mass_acc, 2 * accLen * sizeof(double)));
       SART_CUDA(cudaMemsetAsync(h->d_mass_acc, 0, 2 * accLen * sizeof(double), h->stream));
     }
-    SART_CUDA(launch_mc_image_fast_masses(h->fparams, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays, seed,
-                                          h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
+    if (h->precision == 2)
+      SART_CUDA(launch_mc_image_f32_masses(h->fparams, h->geo32, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays,
+                                           seed, h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
+    else
+      SART_CUDA(launch_mc_image_fast_masses(h->fparams, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays, seed,
+                                            h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
     SART_CUDA(launch_fold_mass_acc(h->d_mass_acc, h->d_mass_acc + accLen, h->n_masses, plane, h->d_image, h->d_image_w2,
                                    h->stream));
     return SART_OK;

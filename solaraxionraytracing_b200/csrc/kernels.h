@@ -38,6 +38,9 @@ cudaError_t launch_emission_rates(int nR, int nE, const double* dTemp, const dou
 cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
                                 uint64_t first, uint64_t nRays, uint64_t seed, double* image, double* imageW2,
                                 sart_counters_t* counters, int smCount, bool compact, cudaStream_t s);
+cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T,
+                                       int nMasses, const double* dMasses, uint64_t first, uint64_t nRays, uint64_t seed,
+                                       double* acc, double* accW2, sart_counters_t* counters, int smCount, cudaStream_t s);
 cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
                                   size_t n, const double* origin, const double* exitxy, const double* energy,
                                   const sart_ray_out_t& o, int smCount, cudaStream_t s);

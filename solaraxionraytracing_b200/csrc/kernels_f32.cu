@@ -656,6 +656,32 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
   if (lane == 0) flush_counters(counters, wc[warp], nIter, nPassed, nTill, sumW, sumW2, sumX, sumY, sumR);
 }
 
+// ---- axion-mass scan with FP32 tracing (the per-mass weighting is fast_common.cuh's mass_scan_loop) --------------
+template <bool kWolter>
+__global__ void __launch_bounds__(kBlock, 3)
+k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
+                      const __grid_constant__ FastTables T, const double* __restrict__ masses, int nMasses, uint64_t first,
+                      uint64_t nRays, uint64_t seed, double* __restrict__ image, double* __restrict__ imageW2,
+                      sart_counters_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Smem32 S;
+  unsigned char* tail;
+  smem_layout32(P, smem, S, tail);
+  WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
+  smem_fill32(P, T, S);
+  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  __syncthreads();
+  mass_scan_loop(P, masses, nMasses, first, nRays, image, imageW2, counters, wc, [&](uint64_t ray, RayResult& r) {
+    RecordSink<false> sink{r, 0.0};
+    Head32 hd;
+    stage_a32_head(P, T, S, seed, ray, hd);
+    Rec32 rec;
+    const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
+    if (c0 >= 0) sink.fail(c0);
+    else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
+  });
+}
+
 // ---- per-ray records (traceAxionWrapper in FP32 mode) ----------------------------------------------------------
 template <bool kWolter>
 __global__ void __launch_bounds__(kBlock, 2)
@@ -775,6 +801,26 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
   kern<<<grid, fast::kBlock, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T,
+                                       int nMasses, const double* dMasses, uint64_t first, uint64_t nRays, uint64_t seed,
+                                       double* acc, double* accW2, sart_counters_t* counters, int smCount, cudaStream_t s) {
+  if (nRays == 0) return cudaSuccess;
+  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
+  const size_t smem = fast::smem_bytes32(P);
+  auto kern = wolter ? fast::k_trace_mc_f32_masses<true> : fast::k_trace_mc_f32_masses<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int perSM = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t cap = uint64_t(smCount) * perSM;
+  const unsigned grid = unsigned(want < cap ? want : cap);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, G, T, dMasses, nMasses, first, nRays, seed, acc, accW2, counters);
   return cudaGetLastError();
 }
 

@@ -666,90 +666,8 @@ k_trace_mc_fast_masses(const __grid_constant__ FastParams P, const __grid_consta
   for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
-  constexpr int kPer = SART_MAX_MASSES / 32;
-  constexpr unsigned kFull = 0xffffffffu;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double m2[kPer], sumW[kPer], sumW2[kPer], sumX[kPer], sumY[kPer], sumR[kPer];
-  unsigned int nPassed[kPer], nZero[kPer], nTill[kPer];
-#pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    const int m = lane + 32 * k;
-    const double mm = m < nMasses ? masses[m] : 0.0;
-    m2[k] = mm * mm;
-    sumW[k] = sumW2[k] = sumX[k] = sumY[k] = sumR[k] = 0.0;
-    nPassed[k] = nZero[k] = nTill[k] = 0u;
-  }
-  unsigned int nIter = 0;
-  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
-  for (uint64_t b = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31); b < nRays; b += stride) {   // warp-uniform
-    const uint64_t i = b + lane;
-    const bool valid = i < nRays;
-    RayResult r;
-    r.code = SART_N_EXIT_CODES;
-    if (valid) {
-      trace_one<kWolter, false>(P, T, S, seed, first + i, 0.0, r);
-      ++nIter;
-      if (r.code >= 0) atomicAdd(&wc[warp].n_exit[r.code], 1u);
-      else if (r.windowMiss) atomicAdd(&wc[warp].n_exit[SART_EXIT_WINDOW_APERTURE], 1u);
-      if (r.clamped) atomicAdd(&wc[warp].n_clamped, 1u);
-    }
-    unsigned alive = __ballot_sync(kFull, valid && r.code < 0);
-    while (alive) {
-      const int src = __ffs(alive) - 1;
-      alive &= alive - 1;
-      const double wPre = __shfl_sync(kFull, r.wPre, src), wPost = __shfl_sync(kFull, r.wPost, src);
-      const double gasL = __shfl_sync(kFull, r.gasL, src);
-      const float convVac = __shfl_sync(kFull, r.convVac, src), gG = __shfl_sync(kFull, r.gasGamma, src);
-      const float gE1 = __shfl_sync(kFull, r.gasE1, src), gE2 = __shfl_sync(kFull, r.gasE2, src);
-      const float gI = __shfl_sync(kFull, r.gasInv2E, src);
-      const double x = __shfl_sync(kFull, r.x, src), y = __shfl_sync(kFull, r.y, src), rr = __shfl_sync(kFull, r.r, src);
-      const int bin = __shfl_sync(kFull, r.bin, src);
-      const bool miss = __shfl_sync(kFull, int(r.windowMiss), src) != 0;
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) {
-        const int m = lane + 32 * k;
-        if (m >= nMasses) continue;
-        const double w0 = wPre * conv_factor(P, convVac, gG, gE1, gE2, gI, gasL, m2[k]);
-        if (w0 != 0.0) ++nTill[k];
-        if (miss) continue;
-        const double w = w0 * wPost;
-        if (w != 0.0) {
-          ++nPassed[k];
-          sumW[k] += w; sumW2[k] += w * w; sumX[k] += x; sumY[k] += y; sumR[k] += rr;
-          if (bin >= 0) {
-            // mass-major accumulators [bin][SART_MAX_MASSES]: the 32 lanes (= 32 masses) of this warp add to 256
-            // consecutive bytes instead of to 32 image planes 512 KiB apart; k_fold_mass_acc transposes afterwards
-            atomicAdd(image + size_t(bin) * SART_MAX_MASSES + m, w);
-            atomicAdd(imageW2 + size_t(bin) * SART_MAX_MASSES + m, w * w);
-          }
-        } else {
-          ++nZero[k];
-        }
-      }
-    }
-  }
-  // ---- flush: the lane that owns a mass adds its sums; geometric exits are the same for every mass
-  for (int o = 16; o > 0; o >>= 1) nIter += __shfl_down_sync(kFull, nIter, o);
-  nIter = __shfl_sync(kFull, nIter, 0);
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    const int m = lane + 32 * k;
-    if (m >= nMasses) continue;
-    sart_counters_t* c = counters + m;
-    auto addu = [](uint64_t* p, unsigned long long v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), v); };
-    addu(&c->n_rays, nIter);
-    addu(&c->n_exit[SART_EXIT_PASSED], nPassed[k]);
-    addu(&c->n_exit[SART_EXIT_ZERO_WEIGHT], nZero[k]);
-    addu(&c->n_passed, nPassed[k]);
-    addu(&c->n_passed_till_window, nTill[k]);
-    for (int e = 1; e < SART_N_EXIT_CODES; ++e)
-      if (e != SART_EXIT_ZERO_WEIGHT) addu(&c->n_exit[e], wc[warp].n_exit[e]);
-    addu(&c->n_hit_nickel, wc[warp].n_exit[SART_EXIT_NICKEL]);
-    addu(&c->n_interp_clamped, wc[warp].n_clamped);
-    atomicAdd(&c->sum_w, sumW[k]); atomicAdd(&c->sum_w2, sumW2[k]);
-    atomicAdd(&c->sum_x, sumX[k]); atomicAdd(&c->sum_y, sumY[k]); atomicAdd(&c->sum_r, sumR[k]);
-  }
+  mass_scan_loop(P, masses, nMasses, first, nRays, image, imageW2, counters, wc,
+                 [&](uint64_t ray, RayResult& r) { trace_one<kWolter, false>(P, T, S, seed, ray, 0.0, r); });
 }
 
 // ---- per-ray records (traceAxionWrapper in fast mode) ----------------------------------------------------------

@@ -181,3 +181,29 @@ def test_f32_presampled_off_grid_energy_is_flagged(rt, oracle):
     assert tail.sum() > 100
     assert np.all((b.code[tail] & abi.FLAG_INTERP_CLAMPED) != 0) and not np.any(a.code[tail] & abi.FLAG_INTERP_CLAMPED)
     assert np.array_equal(a.x, b.x) and np.array_equal(a.w, b.w)      # traced at the nearest tabulated energy
+
+
+def test_f32_mass_scan_vs_exact(rt):
+    """BASELINE config 4 with FP32 tracing: 64 axion masses sharing one traced ray, against the exact pipeline."""
+    setup, tb = make_config("babyiaxo_gas")
+    n = 400_000
+    masses = np.concatenate([np.linspace(0.004, 0.012, 40), np.linspace(0.02, 0.4, 24)])
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_axion_masses(masses)
+        tr.trace_mc(n, 3)
+        e = tr.read_image()
+        tr.set_precision(2)
+        tr.reset_image()
+        tr.trace_mc(n // 3, 3); tr.trace_mc(n - n // 3, 3, first_ray=n // 3)     # two launches: the accumulators fold twice
+        f = tr.read_image()
+    assert f.image.shape == (64, 256, 256)
+    for m in range(64):
+        ce, cf = e.counters[m], f.counters[m]
+        assert cf["n_rays"] == n
+        assert abs(cf["n_passed"] - ce["n_passed"]) <= 20, m
+        for k, v in ce["n_exit"].items():
+            assert abs(cf["n_exit"][k] - v) <= 20, (m, k)
+        assert abs(cf["sum_w"] / ce["sum_w"] - 1.0) < 2e-3, (m, cf["sum_w"], ce["sum_w"])
+        assert abs(f.image[m].sum() / cf["sum_w"] - 1.0) < 1e-9
+        assert abs(f.image_w2[m].sum() / cf["sum_w2"] - 1.0) < 1e-9
+    assert np.abs(f.image - e.image).sum() / e.image.sum() < 2e-2

@@ -15,7 +15,7 @@ def timeit(tr, n, reps=3):
     return best
 
 def main():
-    prec = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    prec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     em_abc = tables.synthetic_emission(1968, 1500, "abc"); em_prim = tables.synthetic_emission(1968, 1500, "primakoff")
     cfgs = [("1/3 CAST+LLNL (window+Ar chain)", ("CAST", "InGrid2018", "vacuum", "LLNL"), em_abc, 4, None, 1e9),
             ("2 CAST+XMM (all rays opaque, see DESIGN)", ("CAST", "InGrid2018", "vacuum", "XMM"), em_prim, 1, None, 1e8),
