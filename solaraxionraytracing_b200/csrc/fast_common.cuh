@@ -19,8 +19,12 @@ namespace fast {
 #ifndef SART_FAST_MINBLOCKS
 #define SART_FAST_MINBLOCKS 3
 #endif
+#ifndef SART_REFL_ALIGNED
+#define SART_REFL_ALIGNED 0   // measured slower (35.2 -> 37.6 ms): 16 bytes per lane through L1TEX cost more than the request saved
+#endif
 #ifndef SART_LAZY_THR
-#define SART_LAZY_THR 0   // 1: second group of four energy thresholds loaded only by the lanes that need it (measured: neutral)
+#define SART_LAZY_THR 1   // second group of four energy thresholds loaded only by the ~12 % of lanes that need it: one
+                          // divergent 32-line gather less per ray (CAST+LLNL, gather-bound: 35.2 -> 32.8 ms)
 #endif
 constexpr int kBlock = SART_FAST_BLOCK;
 constexpr int kWarps = kBlock / 32;
@@ -105,7 +109,17 @@ __device__ __forceinline__ float refl_lookup(const FastParams& P, const float* _
   const float fx = (x - P.angleMin) * P.invReflDx;
   int i = int(fx);
   if (i > P.nAngles - 2) i = P.nAngles - 2;
+#if SART_REFL_ALIGNED
+  // one aligned 16-byte load holds both nodes of the cell unless the cell straddles two such words (1 lookup in 4):
+  // 1.25 gather requests per lookup instead of 2 (rows start 16-byte aligned: nAngles % 4 == 0, checked at create)
+  const int j = i & 3;
+  const float4 z = __ldg(reinterpret_cast<const float4*>(row + (i - j)));
+  const float z0 = j == 0 ? z.x : (j == 1 ? z.y : (j == 2 ? z.z : z.w));
+  float z1 = j == 0 ? z.y : (j == 1 ? z.z : z.w);
+  if (j == 3) z1 = __ldg(row + i + 1);
+#else
   const float z0 = __ldg(row + i), z1 = __ldg(row + i + 1);
+#endif
   return fmaf(fx - float(i), z1 - z0, z0);
 }
 
