@@ -207,3 +207,37 @@ def test_f32_mass_scan_vs_exact(rt):
         assert abs(f.image[m].sum() / cf["sum_w"] - 1.0) < 1e-9
         assert abs(f.image_w2[m].sum() / cf["sum_w2"] - 1.0) < 1e-9
     assert np.abs(f.image - e.image).sum() / e.image.sum() < 2e-2
+
+
+def _weighted_ks(a, wa, b, wb):
+    """Two-sample Kolmogorov-Smirnov distance of weighted samples and its effective sizes (Sum w)^2 / Sum w^2."""
+    ia, ib = np.argsort(a), np.argsort(b)
+    a, wa, b, wb = a[ia], wa[ia], b[ib], wb[ib]
+    grid = np.concatenate([a, b])
+    grid.sort()
+    Fa = np.searchsorted(a, grid, side="right")
+    Fb = np.searchsorted(b, grid, side="right")
+    ca, cb = np.concatenate([[0.0], np.cumsum(wa)]) / wa.sum(), np.concatenate([[0.0], np.cumsum(wb)]) / wb.sum()
+    d = float(np.max(np.abs(ca[Fa] - cb[Fb])))
+    return d, wa.sum() ** 2 / (wa ** 2).sum(), wb.sum() ** 2 / (wb ** 2).sum()
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_f32_ks_against_oracle(rt, oracle, cfg):
+    """Tier (b), Kolmogorov-Smirnov: the weighted distributions of x, y, r and energy of the passed rays, GPU (seed A)
+    against the CPU oracle (independent seed B), agree at the 0.1 % level (c(alpha) = 1.95)."""
+    setup, tb = make_config(cfg)
+    n_gpu, n_cpu = 3_000_000, 600_000
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        g = tr.traceAxionWrapper(n_gpu, 4242)
+    o = oracle.trace_mc_rays(setup, tb, 0, n_cpu, 987654321)
+    pg, po = g.passed, (o.code & abi.CODE_MASK) == abi.EXIT_PASSED
+    assert pg.sum() > 1000 and po.sum() > 1000
+    for name in ("x", "y", "r", "energy"):
+        va, vb = getattr(g, name)[pg], getattr(o, name)[po]
+        if name == "energy":     # a discrete distribution: the FP32 pipeline returns the table energy rounded to f32, so
+            va, vb = va.astype(np.float32), vb.astype(np.float32)   # compare the atoms at equal values
+        d, na, nb = _weighted_ks(va, g.w[pg], vb, o.w[po])
+        crit = 1.95 * np.sqrt((na + nb) / (na * nb))
+        assert d < crit, (name, d, crit, na, nb)
