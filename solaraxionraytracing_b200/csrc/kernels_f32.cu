@@ -99,7 +99,25 @@ struct Rec32 {
   float path2;            // pathCB^2
   int hitLayer, eIdx;
   bool clamped;
+  int rIdx;               // emission shell and energy word, for kernels that resolve the energy after the compaction
+  uint32_t we;
 };
+
+// Energy index rt:464 of a ray of emission shell rIdx whose energy word is `we`: idx = lowerBound(diffFluxCDFs[rIdx], u),
+// exact (integer thresholds). The three dependent gathers (guide entry, thresholds, then the caller's LUT / reflectivity
+// rows) are taken in a row here; the non-compacting kernel spreads them over stage A instead.
+__device__ __forceinline__ int energy_index(const FastParams& P, const FastTables& T, int rIdx, uint32_t we, bool& clamped) {
+  const int e0 = int(__ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (we >> (32 - kEnGuideBits)))) & ~3;
+  const uint32_t* eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
+  int eIdx = e0 + count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0)), we);
+  if (eIdx == e0 + 4) {
+    eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4)), we);
+    if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, P.nEnergies, we);
+  }
+  if (we == 0xffffffffu) eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
+  if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
+  return eIdx;
+}
 
 // Head of stage A: the ray's random words, its emission shell (rt:437, integer search in shared memory) and the load of
 // the energy-guide entry of that shell. Split off so that a kernel can run it one ray ahead: the guide entry is the first
@@ -116,7 +134,7 @@ struct Head32 {
 // kPlain (here and below): the kernel variant for the plain run — solar source, vacuum stage, telescope not turned, no
 // ignore* flag — in which those run-wide switches are compile-time constants instead of uniform branches (~5 % of the
 // instructions); every other setup takes the generic variant.
-template <bool kPlain = false>
+template <bool kPlain = false, bool kLateEnergy = false>
 __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S, uint64_t seed,
                                                uint64_t ray, Head32& h) {
   ray_words(seed, ray, h.w);
@@ -132,13 +150,15 @@ __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTa
     if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
     if (rIdx > P.nRadii - 1) rIdx = P.nRadii - 1;
     h.rIdx = rIdx;
-    h.guide = __ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (h.w[5] >> (32 - kEnGuideBits)));
+    if (!kLateEnergy) h.guide = __ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (h.w[5] >> (32 - kEnGuideBits)));
   }
 }
 
 // Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
 // kPre: the sampling block is skipped, the ray comes from the head record (sart_trace_presampled).
-template <bool kWolter, bool kPre = false, bool kPlain = false>
+// kLateEnergy: the energy search is left to the caller (energy_index after the compaction): 2/3 of the BabyIAXO+XMM
+// rays end in this stage and never need their energy.
+template <bool kWolter, bool kPre = false, bool kPlain = false, bool kLateEnergy = false>
 __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
                                          const Head32& h, Rec32& rec) {
   const ShellF32* __restrict__ sShell = S.shell;
@@ -154,8 +174,10 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid;
   } else if (kPlain || !P.testXray) {
     const int rIdx = h.rIdx;
-    e0 = int(h.guide) & ~3;
-    eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
+    if (!kLateEnergy) {
+      e0 = int(h.guide) & ~3;
+      eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
+    }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);
     float s1, c1, s2, c2;
     sincos_2pi(float(w[0]) * k2m32, s1, c1);
@@ -320,6 +342,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   }
   rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.rho0 = radialDist; rec.path2 = path2;
   rec.hitLayer = hitLayer; rec.eIdx = eIdx; rec.clamped = clamped;
+  rec.rIdx = h.rIdx; rec.we = w[5];
   return -1;
 }
 
@@ -577,7 +600,8 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
 constexpr int kQueue32 = 64;
 struct WarpQueue32 {
   float x0[kQueue32], y0[kQueue32], tx[kQueue32], ty[kQueue32], rho0[kQueue32], path2[kQueue32];
-  int meta[kQueue32];   // hitLayer | eIdx << 8 | clamped << 30
+  int meta[kQueue32];   // hitLayer | (eIdx or emission shell) << 8 | clamped << 30
+  uint32_t we[kQueue32];   // energy word of the ray (solar source: the energy is resolved after the compaction)
 };
 
 template <bool kWolter, bool kPlain>
@@ -613,8 +637,8 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       int code = SART_N_EXIT_CODES;
       if (i < nRays) {
         Head32 hd;
-        stage_a32_head<kPlain>(P, T, S, seed, first + i, hd);
-        code = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
+        stage_a32_head<kPlain, true>(P, T, S, seed, first + i, hd);
+        code = stage_a32<kWolter, false, kPlain, true>(P, G, T, S, hd, rec);
         ++nIter;
         if (code >= 0) sink.fail(code);
       }
@@ -623,7 +647,9 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
         const int pos = qn + __popc(m & ((1u << lane) - 1u));
         Q.x0[pos] = rec.x0; Q.y0[pos] = rec.y0; Q.tx[pos] = rec.tx; Q.ty[pos] = rec.ty; Q.rho0[pos] = rec.rho0;
         Q.path2[pos] = rec.path2;
-        Q.meta[pos] = rec.hitLayer | (rec.eIdx << 8) | (rec.clamped ? (1 << 30) : 0);
+        const bool solar = kPlain || !P.testXray;
+        Q.meta[pos] = rec.hitLayer | ((solar ? rec.rIdx : rec.eIdx) << 8) | (rec.clamped ? (1 << 30) : 0);
+        Q.we[pos] = rec.we;
       }
       qn += __popc(m);
     }
@@ -637,6 +663,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       rec.path2 = Q.path2[pos];
       const int meta = Q.meta[pos];
       rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
+      if (kPlain || !P.testXray) rec.eIdx = energy_index(P, T, rec.eIdx, Q.we[pos], rec.clamped);
       stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     }
     qn -= take;
