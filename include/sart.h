@@ -245,7 +245,7 @@ int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV);
  * 1 = "fast": FP64 algebra on (point, slopes) + FP32 weights (closer to exact arithmetic than the reference itself);
  * 2 = "f32": the same formulation with FP32 geometry (positions to ~1e-4 mm, the reference's own rounding level). */
 int sart_set_precision(sart_handle_t* h, int mode);
-/* Fast mode only: 1 = compact the rays that survive bore, pipes, vetoes and glass fronts into full warps before the
+/* Precision modes 1 and 2 only: 1 = compact the rays that survive bore, pipes, vetoes and glass fronts into full warps before the
  * mirror stage (pays off when most rays are clipped, e.g. BabyIAXO + XMM); 0 = one ray per lane throughout. Results are
  * identical ray by ray. Default: chosen at sart_create from the setup (on for XMM/Abrixas, off for LLNL). */
 int sart_set_compaction(sart_handle_t* h, int mode);
@@ -296,7 +296,9 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
 
 /* ---- fused run: sample + trace + prepareHeatmap (rt:818-842, 256x256 over the 14x14 mm chip, norm = 1).
  * Accumulates (+=) into the handle's device-resident image/counters; asynchronous. With M axion masses set
- * (sart_set_axion_masses) the image is [M][256][256]. */
+ * (sart_set_axion_masses) the image is [M][256][256]. In precision modes 1 and 2 the kernel adds into internal replicas
+ * (single mass) or mass-major accumulators (mass scan) that a small second kernel folds into the image on the same
+ * stream right after the trace kernel: when the call returns, everything it did is queued on sart_stream(). */
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed);
 int sart_reset_image(sart_handle_t* h);
 /* Optional weighted radial histogram of the passed rays, for the 68 % / 95.5 % containment radii of
