@@ -241,3 +241,23 @@ def test_f32_ks_against_oracle(rt, oracle, cfg):
         d, na, nb = _weighted_ks(va, g.w[pg], vb, o.w[po])
         crit = 1.95 * np.sqrt((na + nb) / (na * nb))
         assert d < crit, (name, d, crit, na, nb)
+
+
+def test_f32_presampled_edge_inputs(rt, oracle):
+    """Empty batch, a far-off-axis ray, NaN inputs and an energy outside the tabulated range in the FP32 pre-sampled
+    kernel: no crash, the geometric classification of the well-defined rays equals the oracle's, the NaN ray and the
+    out-of-range energy end in a defined exit code / the clamped flag."""
+    setup, tb = make_config("cast_llnl")
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        out = tr.trace_presampled(np.zeros((3, 0)), np.zeros((2, 0)), np.zeros(0))
+        assert out.n == 0
+        origin = np.array([[0.0, 1e13, np.nan, 3e11], [0.0, 0.0, 0.0, -2e11], [-1.5e14, -1.5e14, -1.5e14, -1.4999e14]])
+        exit_xy = np.array([[0.0, 0.0, 1.0, 21.49], [0.0, 0.0, 1.0, 0.0]])
+        energy = np.array([float(tb.energies[40]), float(tb.energies[40]), float(tb.energies[40]), 20.0])
+        ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy)
+        gpu = tr.trace_presampled(origin, exit_xy, energy)
+    for i in (0, 1, 3):
+        assert (gpu.code[i] & abi.CODE_MASK) == (ref.code[i] & abi.CODE_MASK), (i, gpu.code[i], ref.code[i])
+    assert 0 < (gpu.code[2] & abi.CODE_MASK) < abi.N_EXIT_CODES and gpu.w[2] == 0.0      # NaN origin: never "passed"
+    assert np.all(np.isfinite(gpu.x)) and np.all(np.isfinite(gpu.w))
