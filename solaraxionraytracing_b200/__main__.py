@@ -48,7 +48,12 @@ def load_tables(rt, tables, res, setup, device: int):
         em = rt.calculateEmissionRates(sm, ("primakoff",), device=device)
     rc, dc = rt.buildCdfs(em, device)
     from . import abi
-    if setup.telescope.kind == abi.TK_LLNL:
+    llnl = setup.telescope.kind == abi.TK_LLNL
+    h5 = base / (res.llnlReflFile if llnl else res.goldReflFile)
+    lims = {}
+    if h5.is_file():
+        refl, lims["angleLim"], lims["reflEnergyLim"] = tables.reflectivity_from_h5(h5, setup.telescope.nCoatings if llnl else None)
+    elif llnl:
         refl = tables.synthetic_reflectivity(max(1, setup.telescope.nCoatings))
     else:
         refl = tables.gold_reflectivity_packaged()
@@ -56,7 +61,7 @@ def load_tables(rt, tables, res, setup, device: int):
         det = tables.detector_tables_from_resources(base, setup.detector.windowThickness, setup.detector.alThickness)
     except OSError:
         det = tables.detector_tables_packaged()
-    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl, **det)
+    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl, **lims, **det)
 
 
 def main(argv=None) -> int:

@@ -231,3 +231,26 @@ def write_solar_model_dataframe(path: str | Path, table: EmissionTable) -> Path:
         f.write("Radius,Energy [keV],emRates\n")
         np.savetxt(f, np.column_stack([R, E, table.emRates.reshape(-1)]), delimiter=",", fmt="%.17g")
     return path
+
+
+def reflectivity_from_h5(path: str | Path, numCoatings: int | None = None):
+    """The reflectivity files initReflectivity reads (rt:1160-1232): `/Energy` [keV], `/Angles` [deg] and either
+    `/Reflectivity0 .. /Reflectivity{n-1}` (LLNL multilayer recipes, llnl_layer_reflectivities.h5) or `/Reflectivity`
+    (gold_0.25microns_reflectivities.h5), each [nAngles, nEnergies]. Returns (reflectivity [nCoat, nAng, nEn],
+    (angleMin, angleMax), (energyMin, energyMax)) ready for `TableSet(reflectivity=, angleLim=, reflEnergyLim=)`.
+    Needs h5py, which is not part of the build image (the two files are not part of the reference checkout either)."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError("reading the reference's HDF5 reflectivity files needs h5py; alternatively pass the arrays to "
+                          "TableSet directly or use gold_reflectivity_packaged() / synthetic_reflectivity()") from e
+    with h5py.File(path, "r") as f:
+        energies = np.asarray(f["Energy"], dtype=np.float64)
+        angles = np.asarray(f["Angles"], dtype=np.float64)
+        if "Reflectivity" in f:
+            data = [np.asarray(f["Reflectivity"], dtype=np.float64)]
+        else:
+            n = numCoatings if numCoatings is not None else sum(1 for k in f.keys() if k.startswith("Reflectivity"))
+            data = [np.asarray(f[f"Reflectivity{i}"], dtype=np.float64) for i in range(n)]
+    refl = np.stack([d.reshape(angles.size, energies.size) for d in data])
+    return np.ascontiguousarray(refl), (float(angles.min()), float(angles.max())), (float(energies.min()), float(energies.max()))

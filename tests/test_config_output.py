@@ -145,3 +145,19 @@ def test_run_table_is_an_optional_superset(tmp_path):
     p.write_text(config.DEFAULT_CONFIG.read_text() + '\n[Run]\nprecision = "fp8"\n')
     with pytest.raises(ValueError):
         config.parseRun(config.load_config(p))
+
+
+def test_h5_reflectivity_reader_fails_clearly_without_h5py(tmp_path):
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            tables.reflectivity_from_h5(tmp_path / "llnl_layer_reflectivities.h5")
+    else:
+        import h5py
+        p = tmp_path / "gold.h5"
+        with h5py.File(p, "w") as f:
+            f["Energy"] = np.linspace(0.03, 15, 7); f["Angles"] = np.linspace(0, 1.5, 5)
+            f["Reflectivity"] = np.arange(35.0).reshape(5, 7)
+        r, al, el = tables.reflectivity_from_h5(p)
+        assert r.shape == (1, 5, 7) and al == (0.0, 1.5) and el == (0.03, 15.0)
