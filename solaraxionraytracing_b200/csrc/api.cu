@@ -428,6 +428,9 @@ void sart_destroy(sart_handle_t* h) {
   cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
   cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n); cudaFree(h->d_rep); cudaFree(h->d_mass_acc);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream_in) cudaStreamDestroy(h->stream_in);
+  if (h->stream_out) cudaStreamDestroy(h->stream_out);
+  for (void* e : h->ev) if (e) cudaEventDestroy(static_cast<cudaEvent_t>(e));
   delete h;
 }
 
@@ -607,6 +610,28 @@ static int copy_out(sart_handle* h, size_t n, const sart_ray_out_t& host, const 
   return SART_OK;
 }
 
+// Offsets a host-side sart_ray_out_t by `a` rays.
+static sart_ray_out_t offset_out(const sart_ray_out_t& o, size_t a) {
+  sart_ray_out_t r = o;
+#define OFF(f) if (r.f) r.f += a
+  OFF(x); OFF(y); OFF(w); OFF(code); OFF(shell); OFF(energy); OFF(reflect); OFF(transMagnet); OFF(yaw); OFF(alpha1);
+  OFF(alpha2); OFF(pathCB); OFF(r); OFF(deviationDet); OFF(transProbArgon);
+#undef OFF
+  return r;
+}
+
+static int launch_presampled(sart_handle* h, size_t m, const double* dO, const double* dX, const double* dE,
+                             const sart_ray_out_t& dev, unsigned char* outBase, size_t outBytes) {
+  if (h->precision == 2 && h->ftables.energies) {
+    // the f32 pipeline fills x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
+    SART_CUDA(cudaMemsetAsync(outBase, 0, outBytes, h->stream));
+    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, h->ftables, h->masses[0], m, dO, dX, dE, dev, h->sm_count, h->stream));
+  } else {
+    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], m, dO, dX, dE, dev, h->stream));
+  }
+  return SART_OK;
+}
+
 int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin, const double* exitxy, const double* energy,
                           const sart_ray_out_t* out) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
@@ -615,27 +640,57 @@ int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin, cons
   if (n == 0) return SART_OK;
   if (!origin || !exitxy || !energy) return fail(SART_ERR_ARG, "sart_trace_presampled: NULL input");
   DeviceGuard dg(h->device);
-  const size_t inBytes = align256(3 * n * sizeof(double)) + align256(2 * n * sizeof(double)) + align256(n * sizeof(double));
+  // Chunks of up to 1 Mi rays through two device-side buffers: the host->device copies of chunk k+1, the kernel of
+  // chunk k and the device->host copies of chunk k-1 run on three streams at once (PCIe is full duplex; with pinned
+  // host arrays the call is bound by the larger of the two directions, 48 B/ray in, instead of by their sum).
+  const size_t chunk = size_t(1) << 20, m0 = n < chunk ? n : chunk;
+  const size_t inBytes = align256(3 * m0 * sizeof(double)) + align256(2 * m0 * sizeof(double)) + align256(m0 * sizeof(double));
   sart_ray_out_t probe;
-  const size_t outBytes = carve_out(nullptr, n, *out, &probe);
-  if ((rc = ensure_stage(h, inBytes + outBytes))) return rc;
-  unsigned char* base = static_cast<unsigned char*>(h->d_stage);
-  double* dO = reinterpret_cast<double*>(base);
-  double* dX = reinterpret_cast<double*>(base + align256(3 * n * sizeof(double)));
-  double* dE = reinterpret_cast<double*>(base + align256(3 * n * sizeof(double)) + align256(2 * n * sizeof(double)));
-  sart_ray_out_t dev;
-  carve_out(base + inBytes, n, *out, &dev);
-  SART_CUDA(cudaMemcpyAsync(dO, origin, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  SART_CUDA(cudaMemcpyAsync(dX, exitxy, 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  SART_CUDA(cudaMemcpyAsync(dE, energy, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (h->precision == 2 && h->ftables.energies) {
-    // the f32 pipeline fills x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
-    SART_CUDA(cudaMemsetAsync(base + inBytes, 0, outBytes, h->stream));
-    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, h->ftables, h->masses[0], n, dO, dX, dE, dev, h->sm_count, h->stream));
-  } else {
-    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, dO, dX, dE, dev, h->stream));
+  const size_t outBytes = carve_out(nullptr, m0, *out, &probe);
+  const size_t bufBytes = inBytes + outBytes;
+  const int nbuf = n > chunk ? 2 : 1;
+  if ((rc = ensure_stage(h, nbuf * bufBytes))) return rc;
+  if (nbuf == 2 && !h->stream_in) {
+    SART_CUDA(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+    SART_CUDA(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) SART_CUDA(cudaEventCreateWithFlags(reinterpret_cast<cudaEvent_t*>(&h->ev[i]), cudaEventDisableTiming));
   }
-  return copy_out(h, n, *out, dev);
+  cudaStream_t sIn = nbuf == 2 ? h->stream_in : h->stream, sOut = nbuf == 2 ? h->stream_out : h->stream;
+  auto ev = [&](int kind, int b) { return static_cast<cudaEvent_t>(h->ev[kind * 2 + b]); };   // 0 in, 1 kernel, 2 out
+  size_t k = 0;
+  for (size_t a = 0; a < n; a += chunk, ++k) {
+    const size_t m = n - a < chunk ? n - a : chunk;
+    const int b = int(k & 1);
+    unsigned char* base = static_cast<unsigned char*>(h->d_stage) + size_t(b) * bufBytes;
+    double* dO = reinterpret_cast<double*>(base);
+    double* dX = reinterpret_cast<double*>(base + align256(3 * m0 * sizeof(double)));
+    double* dE = reinterpret_cast<double*>(base + align256(3 * m0 * sizeof(double)) + align256(2 * m0 * sizeof(double)));
+    sart_ray_out_t dev;
+    carve_out(base + inBytes, m, *out, &dev);
+    if (nbuf == 2 && k >= 2) SART_CUDA(cudaStreamWaitEvent(sIn, ev(1, b), 0));      // kernel of chunk k-2 has read this buffer
+    for (int c = 0; c < 3; ++c) SART_CUDA(cudaMemcpyAsync(dO + c * m, origin + c * n + a, m * sizeof(double), cudaMemcpyHostToDevice, sIn));
+    for (int c = 0; c < 2; ++c) SART_CUDA(cudaMemcpyAsync(dX + c * m, exitxy + c * n + a, m * sizeof(double), cudaMemcpyHostToDevice, sIn));
+    SART_CUDA(cudaMemcpyAsync(dE, energy + a, m * sizeof(double), cudaMemcpyHostToDevice, sIn));
+    if (nbuf == 2) {
+      SART_CUDA(cudaEventRecord(ev(0, b), sIn));
+      SART_CUDA(cudaStreamWaitEvent(h->stream, ev(0, b), 0));
+      if (k >= 2) SART_CUDA(cudaStreamWaitEvent(h->stream, ev(2, b), 0));           // outputs of chunk k-2 have left this buffer
+    }
+    if ((rc = launch_presampled(h, m, dO, dX, dE, dev, base + inBytes, outBytes))) return rc;
+    if (nbuf == 2) {
+      SART_CUDA(cudaEventRecord(ev(1, b), h->stream));
+      SART_CUDA(cudaStreamWaitEvent(sOut, ev(1, b), 0));
+    }
+    const sart_ray_out_t host = offset_out(*out, a);
+#define CPD(f) if (host.f) SART_CUDA(cudaMemcpyAsync(host.f, dev.f, m * sizeof(*host.f), cudaMemcpyDeviceToHost, sOut))
+    CPD(x); CPD(y); CPD(w); CPD(code); CPD(shell); CPD(energy); CPD(reflect); CPD(transMagnet); CPD(yaw); CPD(alpha1);
+    CPD(alpha2); CPD(pathCB); CPD(r); CPD(deviationDet); CPD(transProbArgon);
+#undef CPD
+    if (nbuf == 2) SART_CUDA(cudaEventRecord(ev(2, b), sOut));
+  }
+  if (nbuf == 2) { SART_CUDA(cudaStreamSynchronize(sIn)); SART_CUDA(cudaStreamSynchronize(sOut)); }
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  return SART_OK;
 }
 
 int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t seed, const sart_ray_out_t* out) {

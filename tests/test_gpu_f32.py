@@ -261,3 +261,22 @@ def test_f32_presampled_edge_inputs(rt, oracle):
         assert (gpu.code[i] & abi.CODE_MASK) == (ref.code[i] & abi.CODE_MASK), (i, gpu.code[i], ref.code[i])
     assert 0 < (gpu.code[2] & abi.CODE_MASK) < abi.N_EXIT_CODES and gpu.w[2] == 0.0      # NaN origin: never "passed"
     assert np.all(np.isfinite(gpu.x)) and np.all(np.isfinite(gpu.w))
+
+
+@pytest.mark.parametrize("mode", [2, 0])
+def test_presampled_host_path_chunks(rt, oracle, mode):
+    """sart_trace_presampled with host buffers streams chunks of 1 Mi rays through two device buffers on three streams;
+    the records are bit-identical to tracing the same rays slice by slice (one chunk per call)."""
+    setup, tb = make_config("cast_llnl")
+    n = 2_300_007 if mode == 2 else 1_200_003
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, 77)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(mode)
+        whole = tr.trace_presampled(origin, exit_xy, energy, optional=True)
+        parts = []
+        for a in range(0, n, 700_000):
+            b = min(n, a + 700_000)
+            parts.append(tr.trace_presampled(origin[:, a:b], exit_xy[:, a:b], energy[a:b], optional=True))
+    for name in ("x", "y", "w", "code", "shell", "energy", "r"):
+        assert np.array_equal(getattr(whole, name), np.concatenate([getattr(p, name) for p in parts])), name
+    assert (whole.exit_code == abi.EXIT_PASSED).mean() > 0.8
