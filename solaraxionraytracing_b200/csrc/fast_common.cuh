@@ -238,8 +238,8 @@ __device__ __forceinline__ void mass_scan_loop(const FastParams& P, const double
     nPassed[k] = nZero[k] = nTill[k] = 0u;
   }
   unsigned int nIter = 0;
-  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
-  for (uint64_t b = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31); b < nRays; b += stride) {   // warp-uniform
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t b = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); b < nRays; b += stride) {   // warp-uniform
     const uint64_t i = b + lane;
     const bool valid = i < nRays;
     RayResult r;
