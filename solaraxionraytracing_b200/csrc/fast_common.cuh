@@ -53,7 +53,8 @@ __device__ __forceinline__ void sincos_2pi(float u, float& s, float& c) {
 }
 // asin / atan for small arguments (grazing angles <= 0.1 rad, slopes <= 0.1): odd series, relative error < 1e-7.
 __device__ __forceinline__ float asin_small(float x) {
-  if (fabsf(x) > 0.1f) return asinf(x);
+  // series of asin, relative error < 1e-7 for |x| <= 0.1 (grazing angles <= 5.7 deg); beyond that it is still monotone
+  // and the reflectivity lookup clamps at angleMax (1.5 deg), so the exact value does not matter
   const float x2 = x * x;
   return x * fmaf(x2, fmaf(x2, 0.075f, 0.16666667f), 1.0f);
 }
@@ -103,9 +104,8 @@ static __device__ __noinline__ int thr_search_tail(const uint32_t* __restrict__ 
 // a third and CAST+LLNL, whose tables already fill most of one L2 partition, loses 25 %; one aligned 16-byte load plus a
 // conditional second one — no gain over two 4-byte loads.)
 __device__ __forceinline__ float refl_lookup(const FastParams& P, const float* __restrict__ row, float alphaDeg, bool& clamped) {
-  float x = alphaDeg;
-  if (!(x >= P.angleMin)) { x = P.angleMin; clamped = true; }
-  if (!(x <= P.angleMax)) { x = P.angleMax; clamped = true; }
+  const float x = fminf(fmaxf(alphaDeg, P.angleMin), P.angleMax);   // NaN -> angleMin
+  clamped |= (x != alphaDeg);
   const float fx = (x - P.angleMin) * P.invReflDx;
   int i = int(fx);
   if (i > P.nAngles - 2) i = P.nAngles - 2;

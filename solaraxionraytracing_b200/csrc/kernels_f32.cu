@@ -27,6 +27,10 @@ namespace fast {
 #ifndef SART_F32_MINBLOCKS
 #define SART_F32_MINBLOCKS 1
 #endif
+#ifndef SART_F32_PREFETCH
+#define SART_F32_PREFETCH 0   // 1: run the sampling head (Philox, emission shell, energy-guide load) one ray ahead
+                              // (no gain once the kernel was issue-bound: 28.9 vs 28.6 ms)
+#endif
 constexpr int kBlock32 = SART_F32_BLOCK, kWarps32 = kBlock32 / 32;
 constexpr int kBlockM = 256, kWarpsM = kBlockM / 32;   // mass scan: its per-mass sums need more than 64 registers
 
@@ -148,9 +152,9 @@ struct Head32 {
 // ignore* flag — in which those run-wide switches are compile-time constants instead of uniform branches (~5 % of the
 // instructions); every other setup takes the generic variant.
 template <bool kPlain = false, bool kLateEnergy = false>
-__device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S, uint64_t seed,
-                                               uint64_t ray, Head32& h) {
-  ray_words(seed, ray, h.w);
+__device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S,
+                                               const PhiloxKeys& K, uint64_t ray, Head32& h) {
+  ray_words(K, ray, h.w);
   h.rIdx = 0; h.guide = 0;
   if (kPlain || !P.testXray) {
     const uint32_t wr = h.w[2];
@@ -559,7 +563,7 @@ __device__ __forceinline__ void flush_counters(sart_counters_t* c, const WarpCou
 template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G, const __grid_constant__ FastTables T,
-               double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
+               double mAxion2, uint64_t first, uint64_t nRays, const __grid_constant__ PhiloxKeys K, double* __restrict__ image,
                double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
@@ -576,14 +580,15 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
   ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
+#if SART_F32_PREFETCH
   uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x;
   Head32 cur;
-  if (i < nRays) stage_a32_head<kPlain>(P, T, S, seed, first + i, cur);
+  if (i < nRays) stage_a32_head<kPlain>(P, T, S, K, first + i, cur);
   while (i < nRays) {
     ++nIter;
     const uint64_t inext = i + stride;
     Head32 nxt;
-    if (inext < nRays) stage_a32_head<kPlain>(P, T, S, seed, first + inext, nxt);   // next ray's guide load goes out now
+    if (inext < nRays) stage_a32_head<kPlain>(P, T, S, K, first + inext, nxt);   // next ray's guide load goes out now
     Rec32 rec;
     const int code = stage_a32<kWolter, false, kPlain>(P, G, T, S, cur, rec);
     if (code >= 0) sink.fail(code);
@@ -591,6 +596,17 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
     cur = nxt;
     i = inext;
   }
+#else
+  for (uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x; i < nRays; i += stride) {
+    ++nIter;
+    Head32 hd;
+    stage_a32_head<kPlain>(P, T, S, K, first + i, hd);
+    Rec32 rec;
+    const int code = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
+    if (code >= 0) sink.fail(code);
+    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
+  }
+#endif
   for (int o = 16; o > 0; o >>= 1) {
     nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
     nTill += __shfl_down_sync(0xffffffffu, nTill, o);
@@ -616,8 +632,8 @@ struct WarpQueue32 {
 template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
-                       const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed,
-                       double* __restrict__ image, double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
+                       const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
+                       const __grid_constant__ PhiloxKeys K, double* __restrict__ image, double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
   unsigned char* tail;
@@ -646,7 +662,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       int code = SART_N_EXIT_CODES;
       if (i < nRays) {
         Head32 hd;
-        stage_a32_head<kPlain, true>(P, T, S, seed, first + i, hd);
+        stage_a32_head<kPlain, true>(P, T, S, K, first + i, hd);
         code = stage_a32<kWolter, false, kPlain, true>(P, G, T, S, hd, rec);
         ++nIter;
         if (code >= 0) sink.fail(code);
@@ -697,7 +713,7 @@ template <bool kWolter>
 __global__ void __launch_bounds__(kBlockM, 3)
 k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                       const __grid_constant__ FastTables T, const double* __restrict__ masses, int nMasses, uint64_t first,
-                      uint64_t nRays, uint64_t seed, double* __restrict__ image, double* __restrict__ imageW2,
+                      uint64_t nRays, const __grid_constant__ PhiloxKeys K, double* __restrict__ image, double* __restrict__ imageW2,
                       sart_counters_t* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
@@ -710,7 +726,7 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
   mass_scan_loop(P, masses, nMasses, first, nRays, image, imageW2, counters, wc, [&](uint64_t ray, RayResult& r) {
     RecordSink<false> sink{r, 0.0};
     Head32 hd;
-    stage_a32_head(P, T, S, seed, ray, hd);
+    stage_a32_head(P, T, S, K, ray, hd);
     Rec32 rec;
     const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
@@ -722,8 +738,8 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
 template <bool kWolter>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
-                    const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays, uint64_t seed,
-                    double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
+                    const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
+                    const __grid_constant__ PhiloxKeys K, double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
                     int32_t* __restrict__ oshell, double* __restrict__ oenergy, double* __restrict__ orad) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
@@ -737,7 +753,7 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     RecordSink<true> sink{r, mAxion2};
     Rec32 rec;
     Head32 hd;
-    stage_a32_head(P, T, S, seed, first + i, hd);
+    stage_a32_head(P, T, S, K, first + i, hd);
     const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
     else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
@@ -836,7 +852,7 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), image, imageW2, counters);
   return cudaGetLastError();
 }
 
@@ -856,7 +872,7 @@ cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Ge
   const uint64_t want = (nRays + fast::kBlockM - 1) / fast::kBlockM;
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlockM, smem, s>>>(P, G, T, dMasses, nMasses, first, nRays, seed, acc, accW2, counters);
+  kern<<<grid, fast::kBlockM, smem, s>>>(P, G, T, dMasses, nMasses, first, nRays, philox_round_keys(seed), acc, accW2, counters);
   return cudaGetLastError();
 }
 
@@ -893,7 +909,7 @@ cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, 
   const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * 2;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, seed, o.x, o.y, o.w, o.code, o.shell,
+  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), o.x, o.y, o.w, o.code, o.shell,
                                         o.energy, o.r);
   return cudaGetLastError();
 }

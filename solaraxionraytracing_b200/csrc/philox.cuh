@@ -40,6 +40,34 @@ SART_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
   return Philox4{c0, c1, c2, c3};
 }
 
+// The same generator with the ten round keys (k0 + r W0, k1 + r W1) precomputed: passed to a kernel by value they sit in
+// the constant bank and enter the XORs as operands, which removes the two key-schedule additions per round (40
+// instructions per ray).
+struct PhiloxKeys { uint32_t k[10][2]; };
+SART_HD PhiloxKeys philox_round_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+  for (int r = 0; r < 10; ++r) { K.k[r][0] = k0; K.k[r][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  return K;
+}
+SART_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ K.k[r][0];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ K.k[r][1];
+    c3 = lo0;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+SART_HD void ray_words(const PhiloxKeys& K, uint64_t ray, uint32_t w[6]) {
+  const Philox4 a = philox4x32_10(uint32_t(ray), uint32_t(ray >> 32), 0u, 0u, K);
+  const Philox4 b = philox4x32_10(uint32_t(ray), uint32_t(ray >> 32), 1u, 0u, K);
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y;
+}
+
 // word -> uniform in (0,1): (w + 0.5) * 2^-32, exact in f64.
 SART_HD double u01(uint32_t w) { return (double(w) + 0.5) * (1.0 / 4294967296.0); }
 
