@@ -24,6 +24,14 @@
 namespace sart {
 namespace fast {
 
+// The two fused kernels run one block of kBlockF threads per SM (24 warps, 76-78 registers: the register file allows no
+// more), so that the per-block tables exist once per SM and the shared memory saved goes to L1 (see kernels_f32.cu);
+// the per-ray and mass-scan kernels keep kBlock = 256.
+#ifndef SART_FAST_BLOCK_FUSED
+#define SART_FAST_BLOCK_FUSED 768
+#endif
+constexpr int kBlockF = SART_FAST_BLOCK_FUSED, kWarpsF = kBlockF / 32;
+
 // Root choice of findPos* (rt:646-658): roots of A t^2 + 2 hb t + C = 0 in the reference's order root1 = (-hb - sq)/A,
 // root2 = (-hb + sq)/A, each accepted only if zmin < pz + t dz < zmax. With q = -(hb + sign(hb) sq) the roots are q/A
 // (the larger in magnitude) and C/q. The large root is never inside a mirror in practice (it is metres away), so it is
@@ -86,14 +94,14 @@ __device__ __forceinline__ size_t smem_layout(const FastParams& P, unsigned char
   return off;
 }
 __device__ __forceinline__ void smem_fill(const FastParams& P, const FastTables& T, const Smem& s) {
-  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += kBlock)
+  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellFast) / 8); i += blockDim.x)
     reinterpret_cast<double*>(const_cast<ShellFast*>(s.shell))[i] = reinterpret_cast<const double*>(T.shells)[i];
   if (P.nRadii > 0) {
-    for (int i = threadIdx.x; i < thr_pitch(P.nRadii); i += kBlock) const_cast<uint32_t*>(s.radThr)[i] = T.radiusThr[i];
-    for (int i = threadIdx.x; i < kRadGuide / 8; i += kBlock)   // 16 bytes per thread and step
+    for (int i = threadIdx.x; i < thr_pitch(P.nRadii); i += blockDim.x) const_cast<uint32_t*>(s.radThr)[i] = T.radiusThr[i];
+    for (int i = threadIdx.x; i < kRadGuide / 8; i += blockDim.x)   // 16 bytes per thread and step
       reinterpret_cast<uint4*>(const_cast<uint16_t*>(s.radGuide))[i] = __ldg(reinterpret_cast<const uint4*>(T.radiusGuide) + i);
   }
-  for (int i = threadIdx.x; i < P.nShellGuide; i += kBlock) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
+  for (int i = threadIdx.x; i < P.nShellGuide; i += blockDim.x) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
 }
 
 // A ray that survived everything before the mirrors (stage A): what stage B needs to finish it. 48 bytes; this is
@@ -498,7 +506,7 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
 template <bool kWolter>
-__global__ void __launch_bounds__(kBlock, SART_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(kBlockF, 1)
 k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
                 uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
                 double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
@@ -508,7 +516,7 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
   smem_layout(P, smem, S, tail);
   WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
   smem_fill(P, T, S);
-  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  for (int i = threadIdx.x; i < kWarpsF * int(sizeof(WarpCounters) / 4); i += kBlockF) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -517,8 +525,8 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
 
   const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
   ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
-  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
-  for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
+  const uint64_t stride = uint64_t(gridDim.x) * kBlockF;
+  for (uint64_t i = uint64_t(blockIdx.x) * kBlockF + threadIdx.x; i < nRays; i += stride) {
     ++nIter;
     Rec rec;
     const int code = stage_a<kWolter>(P, T, S, seed, first + i, rec);
@@ -565,7 +573,7 @@ struct WarpQueue {
 };
 
 template <bool kWolter>
-__global__ void __launch_bounds__(kBlock, SART_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(kBlockF, 1)
 k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
                         uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ image,
                         double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
@@ -574,9 +582,9 @@ k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_const
   unsigned char* tail;
   smem_layout(P, smem, S, tail);
   WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
-  WarpQueue* queues = reinterpret_cast<WarpQueue*>(tail + kWarps * sizeof(WarpCounters));
+  WarpQueue* queues = reinterpret_cast<WarpQueue*>(tail + kWarpsF * sizeof(WarpCounters));
   smem_fill(P, T, S);
-  for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
+  for (int i = threadIdx.x; i < kWarpsF * int(sizeof(WarpCounters) / 4); i += kBlockF) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
   constexpr unsigned kFull = 0xffffffffu;
@@ -584,10 +592,10 @@ k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_const
   WarpQueue& Q = queues[warp];
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
-  const uint64_t stride = uint64_t(gridDim.x) * kBlock;
+  const uint64_t stride = uint64_t(gridDim.x) * kBlockF;
   const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
   ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
-  uint64_t base = uint64_t(blockIdx.x) * kBlock + (threadIdx.x & ~31);   // warp-uniform
+  uint64_t base = uint64_t(blockIdx.x) * kBlockF + (threadIdx.x & ~31);   // warp-uniform
   int qn = 0;                                                              // warp-uniform queue fill
   for (;;) {
     while (qn <= kQueue - 32 && base < nRays) {
@@ -698,9 +706,9 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
   }
 }
 
-size_t smem_bytes(const FastParams& P) {
+size_t smem_bytes(const FastParams& P, int nWarps = kWarps) {
   return align16(size_t(P.nShells) * sizeof(ShellFast)) + size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2 +
-         align16(size_t(P.nShellGuide)) + kWarps * sizeof(WarpCounters);
+         align16(size_t(P.nShellGuide)) + size_t(nWarps) * sizeof(WarpCounters);
 }
 
 }  // namespace fast
@@ -710,19 +718,19 @@ cudaError_t launch_mc_image_fast(const fast::FastParams& P, const fast::FastTabl
                                  sart_counters_t* counters, int smCount, bool compact, cudaStream_t s) {
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
-  const size_t smem = fast::smem_bytes(P) + (compact ? fast::kWarps * sizeof(fast::WarpQueue) : 0);
+  const size_t smem = fast::smem_bytes(P, fast::kWarpsF) + (compact ? fast::kWarpsF * sizeof(fast::WarpQueue) : 0);
   auto kern = compact ? (wolter ? fast::k_trace_mc_fast_compact<true> : fast::k_trace_mc_fast_compact<false>)
                       : (wolter ? fast::k_trace_mc_fast<true> : fast::k_trace_mc_fast<false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int perSM = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlockF, smem);
   if (e != cudaSuccess) return e;
   if (perSM < 1) perSM = 1;
-  const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
+  const uint64_t want = (nRays + fast::kBlockF - 1) / fast::kBlockF;
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
+  kern<<<grid, fast::kBlockF, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, image, imageW2, counters);
   return cudaGetLastError();
 }
 
