@@ -32,7 +32,13 @@ namespace fast {
                               // (no gain once the kernel was issue-bound: 28.9 vs 28.6 ms)
 #endif
 constexpr int kBlock32 = SART_F32_BLOCK, kWarps32 = kBlock32 / 32;
-constexpr int kBlockM = 256, kWarpsM = kBlockM / 32;   // mass scan: its per-mass sums need more than 64 registers
+#ifndef SART_F32_BLOCK_M
+#define SART_F32_BLOCK_M 768
+#endif
+#ifndef SART_F32_MINBLOCKS_M
+#define SART_F32_MINBLOCKS_M 1
+#endif
+constexpr int kBlockM = SART_F32_BLOCK_M, kWarpsM = kBlockM / 32;   // mass scan: its per-mass sums need more than 64 registers
 
 __device__ __forceinline__ float rcpf_nr(float x) {
   const float r = rcp_approx(x);
@@ -710,7 +716,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
 
 // ---- axion-mass scan with FP32 tracing (the per-mass weighting is fast_common.cuh's mass_scan_loop) --------------
 template <bool kWolter>
-__global__ void __launch_bounds__(kBlockM, 3)
+__global__ void __launch_bounds__(kBlockM, SART_F32_MINBLOCKS_M)
 k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                       const __grid_constant__ FastTables T, const double* __restrict__ masses, int nMasses, uint64_t first,
                       uint64_t nRays, const __grid_constant__ PhiloxKeys K, double* __restrict__ image, double* __restrict__ imageW2,

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the other BASELINE configurations (bench.py measures the headline one). Development aid."""
-import sys, time
+import os, sys, time
+if os.environ.get('SART_LIB_VARIANT'): os.environ['SART_LIB'] = os.environ['SART_LIB_VARIANT']
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np
@@ -17,11 +18,14 @@ def timeit(tr, n, reps=3):
 def main():
     prec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     em_abc = tables.synthetic_emission(1968, 1500, "abc"); em_prim = tables.synthetic_emission(1968, 1500, "primakoff")
+    only = [a for a in sys.argv[2:]]
     cfgs = [("1/3 CAST+LLNL (window+Ar chain)", ("CAST", "InGrid2018", "vacuum", "LLNL"), em_abc, 4, None, 1e9),
             ("2 CAST+XMM (all rays opaque, see DESIGN)", ("CAST", "InGrid2018", "vacuum", "XMM"), em_prim, 1, None, 1e8),
             ("4 BabyIAXO gas, 64 masses", ("BabyIAXO", "InGridIAXO", "gas", "XMM"), em_prim, 1, np.linspace(0.004, 0.012, 64), 1e8),
             ("5 BabyIAXO+XMM vacuum", ("BabyIAXO", "InGridIAXO", "vacuum", "XMM"), em_prim, 1, None, 1e9)]
     for name, setup, em, ncoat, masses, n in cfgs:
+        if only and name.split()[0] not in only:
+            continue
         fs = rt.initFullSetup(*setup, emission=em, reflectivity=tables.synthetic_reflectivity(ncoat, 1000, 1000))
         with rt.RayTracer(fs) as tr:
             tr.set_precision(prec)
