@@ -64,3 +64,22 @@ def test_command_line_writes_the_detector_image(rt, tmp_path, capsys):
                  "--angularScanMax", "0.04", "--numAngularScanPoints", "3"]) == 0
     scan = np.loadtxt(tmp_path / "out" / "angular_scan_telescope_y.csv", delimiter=",", skiprows=1)
     assert scan.shape == (3, 2) and scan[:, 1].max() == 1.0
+
+
+def test_command_line_mass_scan(rt, tmp_path, capsys):
+    """[Run] mAxion = [...] with the gas stage: one image per axion mass, total flux per mass on stdout."""
+    from solaraxionraytracing_b200.__main__ import main
+    from solaraxionraytracing_b200 import config
+    txt = config.DEFAULT_CONFIG.read_text().replace('outputPath = "../out"', f'outputPath = "{tmp_path}/out"')
+    txt = txt.replace('stageSetup = "vacuum"', 'stageSetup = "gas"')
+    txt += '\n[Run]\nnRays = 200000\nseed = 3\nmAxion = [0.006, 0.0082, 0.02]\n'
+    cfg = tmp_path / "config.toml"
+    cfg.write_text(txt)
+    assert main(["--config", str(cfg)]) == 0
+    out = capsys.readouterr().out
+    assert out.count("m_a = ") == 3
+    imgs = np.load(tmp_path / "out" / "axion_images_mass_scan.npy")
+    assert imgs.shape == (3, 256, 256) and np.all(imgs.sum(axis=(1, 2)) > 0)
+    flux = [float(line.split("total flux")[1]) for line in out.splitlines() if line.startswith("m_a = ")]
+    assert np.allclose(flux, imgs.sum(axis=(1, 2)), rtol=1e-5)
+    assert max(flux) / min(flux) > 1.5          # the scan crosses the m_a = m_gamma resonance
