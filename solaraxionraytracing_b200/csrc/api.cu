@@ -95,7 +95,10 @@ static uint32_t cdf_threshold(double c) {
 }
 static void build_thresholds(const double* cdf, int n, uint32_t* out /* [thr_pitch(n)] */) {
   const int pitch = thr_pitch(n);
-  for (int i = 0; i < n; ++i) out[i] = cdf_threshold(cdf[i]);
+  // non-decreasing by construction for a cumulative sum of non-negative rates; enforced, because the device counts
+  // "thresholds <= w" assuming it (count_le)
+  uint32_t prev = 0u;
+  for (int i = 0; i < n; ++i) { prev = std::max(prev, cdf_threshold(cdf[i])); out[i] = prev; }
   for (int i = n; i < pitch; ++i) out[i] = 0xffffffffu;
 }
 
@@ -201,6 +204,11 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   fast::build_energy_lut(nE, h->h_energies.data(), I[0], I[1], I[2], h->setup.testSource.energy, &lut, &glut);
   const int nCoat = P.nAngles > 0 && !h->h_refl32.empty() ? int(h->h_refl32.size() / (size_t(P.nAngles) * P.nReflEnergies)) : 0;
   const size_t reflRow = size_t(P.nAngles), reflPlane = reflRow * (size_t(nE) + 1);
+  // the throughput kernels address table rows with 32-bit element offsets
+  if (size_t(std::max(nCoat, 1)) * reflPlane >= (size_t(1) << 31) ||
+      size_t(std::max(P.nRadii, 1)) * thr_pitch(std::max(P.nEnergies, 1)) >= (size_t(1) << 31) ||
+      size_t(std::max(P.nRadii, 1)) * kEnGuide >= (size_t(1) << 31))
+    return fail(SART_ERR_CONFIG, "tables too large for the throughput pipelines (a table exceeds 2^31 elements)");
   unsigned char* base = static_cast<unsigned char*>(h->fast_blob);
   if (t) {
     // layout: shells | shell guide (4 KiB) | lut | gas lut | radius guide | energy guide | reflE

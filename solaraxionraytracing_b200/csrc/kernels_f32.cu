@@ -32,6 +32,7 @@ namespace fast {
                               // (no gain once the kernel was issue-bound: 28.9 vs 28.6 ms)
 #endif
 constexpr int kBlock32 = SART_F32_BLOCK, kWarps32 = kBlock32 / 32;
+constexpr uint64_t kMaxRaysPerLaunch = uint64_t(1) << 36;   // per-thread trip counts and their per-warp sums are 32-bit
 #ifndef SART_F32_BLOCK_M
 #define SART_F32_BLOCK_M 768
 #endif
@@ -49,6 +50,23 @@ __device__ __forceinline__ float rsqrtf_nr(float x) {
   const float h = 0.5f * x * y;
   return fmaf(y, fmaf(-h, y, 0.5f), y);
 }
+
+// sqrt of a positive normal number: the fast path of sqrtf() (MUFU.RSQ + one Newton step, same operations, same bits)
+// without the range check and slow-path branch the compiler wraps around it.
+__device__ __forceinline__ float sqrtf_pos(float x) {
+  const float y = rsqrt_approx(x);
+  const float s = x * y;
+  return fmaf(fmaf(-s, s, x), 0.5f * y, s);
+}
+// Table rows are addressed with 32-bit element offsets (sart_create checks that every table has < 2^31 elements): one
+// wide multiply-add per address instead of the 64-bit shift/add chains of size_t arithmetic.
+__device__ __forceinline__ const uint32_t* thr_row(const FastParams& P, const FastTables& T, int rIdx) {
+  return T.energyThr + uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies));
+}
+__device__ __forceinline__ const uint16_t* guide_row(const FastTables& T, int rIdx) {
+  return T.energyGuide + uint32_t(rIdx) * uint32_t(kEnGuide);
+}
+constexpr float kMiss = __builtin_nanf("");   // "no root in range" of pick_root32
 
 struct F3 { float x, y, z; };
 
@@ -79,8 +97,8 @@ __device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTable
 
 // Root choice of findPos* (rt:646-658) for A t^2 + 2 hb t + C = 0, as in kernels_fast.cu: q = -(hb + sign(hb) sq), the
 // roots are q/A (large, metres away) and C/q. Returns t with lo < t dz < hi.
-static __device__ __noinline__ bool pick_root_slow32(float A, float q, float C, bool first_is_qA, float dz, float lo,
-                                                     float hi, float& t) {
+static __device__ __noinline__ float pick_root_slow32(float A, float q, float C, bool first_is_qA, float dz, float lo,
+                                                      float hi) {
   auto in_range = [&](float num, float den) {
     const float nd = num * dz;
     return den > 0.0f ? (nd > lo * den && nd < hi * den) : (nd < lo * den && nd > hi * den);
@@ -89,20 +107,20 @@ static __device__ __noinline__ bool pick_root_slow32(float A, float q, float C, 
   float num, den;
   if (first_is_qA ? okA : okC) { num = first_is_qA ? q : C; den = first_is_qA ? A : q; }
   else if (first_is_qA ? okC : okA) { num = first_is_qA ? C : q; den = first_is_qA ? q : A; }
-  else return false;
-  t = num / den;
-  return true;
+  else return kMiss;
+  return num / den;
 }
-__device__ __forceinline__ bool pick_root32(float A, float hb, float C, float dz, float lo, float hi, float& t) {
+// Returns t, or NaN (kMiss) when no root lies in range: the value travels in a register — a bool + reference pair made the
+// out-of-line slow path spill t to local memory on every call (one STL + one LDL per mirror through L1TEX).
+__device__ __forceinline__ float pick_root32(float A, float hb, float C, float dz, float lo, float hi) {
   const float disc = fmaf(hb, hb, -A * C);
-  if (!(disc >= 0.0f)) return false;
+  if (!(disc >= 0.0f)) return kMiss;
   const float sq = disc > 1e-30f ? disc * rsqrtf_nr(disc) : 0.0f;
   const float q = -(hb + copysignf(sq, hb));
-  if (fabsf(q * dz) < fmaxf(fabsf(lo), fabsf(hi)) * fabsf(A)) return pick_root_slow32(A, q, C, hb >= 0.0f, dz, lo, hi, t);
+  if (fabsf(q * dz) < fmaxf(fabsf(lo), fabsf(hi)) * fabsf(A)) return pick_root_slow32(A, q, C, hb >= 0.0f, dz, lo, hi);
   const float ts = C * rcpf_nr(q);
   const float zs = ts * dz;
-  t = ts;
-  return zs > lo && zs < hi;
+  return (zs > lo && zs < hi) ? ts : kMiss;
 }
 
 // Reflection of unit vector v off unit normal n (rt:762-780 without trigonometry); returns |n.v| = sin(alpha).
@@ -130,14 +148,17 @@ struct Rec32 {
 // exact (integer thresholds). The three dependent gathers (guide entry, thresholds, then the caller's LUT / reflectivity
 // rows) are taken in a row here; the non-compacting kernel spreads them over stage A instead.
 __device__ __forceinline__ int energy_index(const FastParams& P, const FastTables& T, int rIdx, uint32_t we, bool& clamped) {
-  const int e0 = int(__ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (we >> (32 - kEnGuideBits)))) & ~3;
-  const uint32_t* eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
+  const uint32_t kb = we >> (32 - kEnGuideBits);
+  const uint16_t* gRow = guide_row(T, rIdx);
+  const int e0 = int(__ldg(gRow + kb)) & ~3;
+  const uint32_t* eRow = thr_row(P, T, rIdx);
   int eIdx = e0 + count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0)), we);
   if (eIdx == e0 + 4) {
     eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4)), we);
-    if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, P.nEnergies, we);
+    if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, guide_upper(gRow, kb, kEnGuide, P.nEnergies), we);
+    // saturated thresholds: the f64 row decides. The all-ones word passes every threshold, so it always gets here.
+    if (we == 0xffffffffu) eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
   }
-  if (we == 0xffffffffu) eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
   if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
   return eIdx;
 }
@@ -164,16 +185,18 @@ __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTa
   h.rIdx = 0; h.guide = 0;
   if (kPlain || !P.testXray) {
     const uint32_t wr = h.w[2];
-    const int r0 = int(S.radGuide[wr >> (32 - kRadGuideBits)]) & ~3;
+    const uint32_t kr = wr >> (32 - kRadGuideBits);
+    const int r0 = int(S.radGuide[kr]) & ~3;
     int rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
     if (rIdx == r0 + 4) {
       rIdx += count_le(*reinterpret_cast<const uint4*>(S.radThr + r0 + 4), wr);
-      if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, P.nRadii, wr);
+      if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, guide_upper(S.radGuide, kr, kRadGuide, P.nRadii), wr);
+      // saturated thresholds: the f64 table decides. The all-ones word passes every threshold, so it always gets here.
+      if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
     }
-    if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
-    if (rIdx > P.nRadii - 1) rIdx = P.nRadii - 1;
+    rIdx = min(rIdx, P.nRadii - 1);
     h.rIdx = rIdx;
-    if (!kLateEnergy) h.guide = __ldg(T.energyGuide + size_t(rIdx) * kEnGuide + (h.w[5] >> (32 - kEnGuideBits)));
+    if (!kLateEnergy) h.guide = __ldg(guide_row(T, rIdx) + (h.w[5] >> (32 - kEnGuideBits)));
   }
 }
 
@@ -199,7 +222,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     const int rIdx = h.rIdx;
     if (!kLateEnergy) {
       e0 = int(h.guide) & ~3;
-      eRow = T.energyThr + size_t(rIdx) * thr_pitch(P.nEnergies);
+      eRow = thr_row(P, T, rIdx);
     }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);
     float s1, c1, s2, c2;
@@ -209,7 +232,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     const float Ox = rsun * (c1 * s2), Oy = rsun * (s1 * s2), Ozr = rsun * c2;
     float sd, cd;
     sincos_2pi(float(w[4]) * k2m32, sd, cd);
-    const float rd = sqrtf((float(w[3]) + 0.5f) * k2m32);
+    const float rd = sqrtf_pos((float(w[3]) + 0.5f) * k2m32);
     ex = G.radiusCB * (rd * cd);
     ey = G.radiusCB * (rd * sd);
     const float invD = rcpf_nr(G.lengthBplusSun - Ozr);   // lengthB - O.z
@@ -335,7 +358,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   int hitLayer;
   {
     int b = int((radialDist - G.shellRhoMin) * G.shellInvStep);
-    b = b < 0 ? 0 : (b > P.nShellGuide - 1 ? P.nShellGuide - 1 : b);
+    b = max(0, min(b, P.nShellGuide - 1));
     hitLayer = S.shellGuide[b];
     if (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;   // first j with R1[j] > radialDist
     if (!(sShell[hitLayer].R1 > radialDist)) code = SART_EXIT_NO_MIRROR_HIT;     // == R1[last]
@@ -357,10 +380,12 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
 #else
       eIdx += count_le(etB, we);
 #endif
-      if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, P.nEnergies, we);
+      if (eIdx == e0 + 8)
+        eIdx = thr_search_tail(eRow, e0 + 8, guide_upper(guide_row(T, h.rIdx), we >> (32 - kEnGuideBits), kEnGuide, P.nEnergies), we);
+      // saturated thresholds: the f64 row decides. The all-ones word passes every threshold, so it always gets here.
+      if (we == 0xffffffffu)
+        eIdx = lower_bound_window(T.energyCDF + size_t(h.rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
     }
-    if (we == 0xffffffffu)
-      eIdx = lower_bound_window(T.energyCDF + size_t(eRow - T.energyThr) / thr_pitch(P.nEnergies) * P.nEnergies, 0, P.nEnergies, u01(we));
     if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
   }
   rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.rho0 = radialDist; rec.path2 = path2;
@@ -390,14 +415,13 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
 
   // ================= mirror 1 rt:1983-2020. Ray: (x0 + tx z, y0 + ty z, z); C in factored form
   float z1;
-  bool hit1;
   if (kWolter) {   // paraboloid rho^2 = c0 - e z, c0 = R0^2
-    hit1 = pick_root32(t2sum, xt + 0.5f * sh.p_e, (rho0 - sh.p_R0) * (rho0 + sh.p_R0), 1.0f, 0.0f, sh.zmax1, z1);
+    z1 = pick_root32(t2sum, xt + 0.5f * sh.p_e, (rho0 - sh.p_R0) * (rho0 + sh.p_R0), 1.0f, 0.0f, sh.zmax1);
   } else {         // cone rho = r1 - tan(beta) z
-    hit1 = pick_root32(t2sum - sh.tan1 * sh.tan1, fmaf(sh.tan1, sh.R1, xt), (rho0 - sh.R1) * (rho0 + sh.R1), 1.0f, 0.0f,
-                       sh.zmax1, z1);
+    z1 = pick_root32(t2sum - sh.tan1 * sh.tan1, fmaf(sh.tan1, sh.R1, xt), (rho0 - sh.R1) * (rho0 + sh.R1), 1.0f, 0.0f,
+                     sh.zmax1);
   }
-  if (!hit1) {
+  if (!(z1 == z1)) {   // kMiss
     int code = SART_EXIT_NO_MIRROR_HIT;
     if (hitLayer > 0) {
       const float zc = G.zExitCBtel;
@@ -434,26 +458,25 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
   }
   // ================= mirror 2 rt:1994-2029. Ray: pm + t v.
   float t2;
-  bool hit2;
   const float lo2 = sh.dm - pm.z, hi2 = sh.zmax2 - pm.z;
   const float pv = fmaf(pm.x, v.x, pm.y * v.y), vv = fmaf(v.x, v.x, v.y * v.y);
   if (kWolter) {  // hyperboloid rho^2 = r3^2 + e (l - z) + g (l - z)^2
     const float u = lM - pm.z;
     const float Rh2 = fmaf(fmaf(sh.h_g, u, sh.h_e), u, sh.h_r3sq);
     const float Rh = Rh2 * rsqrtf_nr(Rh2);
-    hit2 = pick_root32(vv - sh.h_g * v.z * v.z, fmaf(fmaf(sh.h_g, u, 0.5f * sh.h_e), v.z, pv), (rhoM - Rh) * (rhoM + Rh), v.z,
-                       lo2, hi2, t2);
+    t2 = pick_root32(vv - sh.h_g * v.z * v.z, fmaf(fmaf(sh.h_g, u, 0.5f * sh.h_e), v.z, pv), (rhoM - Rh) * (rhoM + Rh), v.z,
+                     lo2, hi2);
   } else {        // cone rho = r4 - tan(3 beta) (z - distanceMirrors)
     const float rc = fmaf(-sh.tan2, pm.z - sh.dm, sh.r4);
-    hit2 = pick_root32(vv - sh.tan2 * sh.tan2 * v.z * v.z, fmaf(sh.tan2 * rc, v.z, pv), (rhoM - rc) * (rhoM + rc), v.z, lo2,
-                       hi2, t2);
+    t2 = pick_root32(vv - sh.tan2 * sh.tan2 * v.z * v.z, fmaf(sh.tan2 * rc, v.z, pv), (rhoM - rc) * (rhoM + rc), v.z, lo2,
+                     hi2);
   }
   // ================= nickel of the shell below rt:1706-1734
   if (hitLayer > 0) {
     const float lhs = sinA1 * (lM - z1), rhs = sh.R1 - below;
     if (lhs * lhs > rhs * rhs * (1.0f - sinA1 * sinA1)) { sink.fail(SART_EXIT_NICKEL); return; }
   }
-  if (!hit2) { sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }
+  if (!(t2 == t2)) { sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }   // kMiss
   pm.x = fmaf(t2, v.x, pm.x); pm.y = fmaf(t2, v.y, pm.y); pm.z = fmaf(t2, v.z, pm.z);
   float sinA2;
   {
@@ -503,9 +526,9 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
     float refl = 1.0f;
     const uint32_t flags = kPlain ? 0u : P.flags;
     if (!(flags & SART_CF_IGNORE_REFLECTION)) {
-      const float* zt = T.reflE + (size_t(sh.coat) * (P.nEnergies + 1) + eIdx) * P.nAngles;
+      const uint32_t rowOff = (uint32_t(sh.coat) * uint32_t(P.nEnergies + 1) + uint32_t(eIdx)) * uint32_t(P.nAngles);
       const float a1 = asin_small(sinA1) * 57.29577951308232f, a2 = asin_small(sinA2) * 57.29577951308232f;
-      refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
+      refl = refl_lookup(P, T.reflE, a1, clamped, rowOff) * refl_lookup(P, T.reflE, a2, clamped, rowOff);
     }
     out.wPre = double(refl) * double(pre);
     if (Sink::kFold)
@@ -603,10 +626,14 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
     i = inext;
   }
 #else
-  for (uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x; i < nRays; i += stride) {
-    ++nIter;
+  // 32-bit trip count + running 64-bit ray index: 5 loop instructions per ray instead of 12 (the launcher keeps
+  // nRays <= kMaxRaysPerLaunch, so the count fits)
+  const uint64_t i0 = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x;
+  nIter = i0 < nRays ? unsigned((nRays - 1 - i0) / stride) + 1u : 0u;
+  uint64_t ray = first + i0;
+  for (unsigned k = nIter; k != 0u; --k, ray += stride) {
     Head32 hd;
-    stage_a32_head<kPlain>(P, T, S, K, first + i, hd);
+    stage_a32_head<kPlain>(P, T, S, K, ray, hd);
     Rec32 rec;
     const int code = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
     if (code >= 0) sink.fail(code);
@@ -855,11 +882,17 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock32, smem);
   if (e != cudaSuccess) return e;
   if (perSM < 1) perSM = 1;
-  const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * perSM;
-  const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), image, imageW2, counters);
-  return cudaGetLastError();
+  const PhiloxKeys keys = philox_round_keys(seed);
+  for (uint64_t done = 0; done < nRays; done += fast::kMaxRaysPerLaunch) {   // one launch for anything below 6.9e10 rays
+    const uint64_t n = nRays - done < fast::kMaxRaysPerLaunch ? nRays - done : fast::kMaxRaysPerLaunch;
+    const uint64_t want = (n + fast::kBlock32 - 1) / fast::kBlock32;
+    const unsigned grid = unsigned(want < cap ? want : cap);
+    kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first + done, n, keys, image, imageW2, counters);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T,
