@@ -347,6 +347,13 @@ void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]);
  * 464) is then the number of thresholds <= w, for every w < 0xffffffff. */
 void sart_cdf_thresholds(const double* cdf, int n, uint32_t* thr);
 
+/* ---- the radial lookup table of the shell search (host helper, exported for tests). The FP32 kernels replace the
+ * scan of rt:1932-1957 (hit shell = first j with R1[j] > rho; glass front of the shell below rt:1942-1944; outside the
+ * last shell rt:1934) by one record of a uniform radial table. For n radial distances rho [mm] this returns the outcome
+ * through the table (via_table) and through the scan (via_scan): the shell number (< 64), or 64 + the SART_EXIT_* code.
+ * SART_ERR_CONFIG when the shells are too closely spaced for the table (the throughput modes then refuse the setup). */
+int sart_shell_lookup(const sart_setup_t* setup, int n, const float* rho, int32_t* via_table, int32_t* via_scan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,4 +198,5 @@ SIGNATURES = {
                                        C.POINTER(C.c_uint64)]),
     "sart_ray_uniforms": (None, [C.c_uint64, C.c_uint64, c_double_p]),
     "sart_cdf_thresholds": (None, [c_double_p, C.c_int, C.POINTER(C.c_uint32)]),
+    "sart_shell_lookup": (C.c_int, [C.POINTER(Setup), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }

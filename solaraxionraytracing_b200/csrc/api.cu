@@ -198,6 +198,14 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   std::vector<uint8_t> sguide;
   fast::build_shell_guide(h->setup, &h->fparams, &sguide);
   if (sguide.size() > 4096) return fail(SART_ERR_CONFIG, "shell guide too large (%zu)", sguide.size());
+  std::vector<fast::ShellF32> sh32(SART_MAX_SHELLS);
+  fast::derive_f32(h->fparams, shf.data(), h->setup.telescope.nShells, &h->geo32, sh32.data());
+  std::vector<fast::ShellCell> stab;
+  if (!fast::build_shell_table(h->geo32, sh32.data(), h->setup.telescope.nShells, int(sguide.size()), &stab)) {
+    h->fast_ok = 0;
+    h->fast_why = "shell radii too closely spaced for the radial lookup table of the throughput pipelines";
+    return SART_OK;
+  }
   const int nE = int(h->h_energies.size());
   std::vector<fast::EnergyLUT> lut;
   std::vector<fast::GasLUT> glut;
@@ -216,6 +224,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     h->fast_shell_off = off; off += align256(shf.size() * sizeof(fast::ShellFast));
     h->fast_shell32_off = off; off += align256(size_t(SART_MAX_SHELLS) * sizeof(fast::ShellF32));
     h->fast_sguide_off = off; off += 4096;
+    h->fast_stab_off = off; off += 4096 * sizeof(fast::ShellCell);
     h->fast_lut_off = off; off += align256(lut.size() * sizeof(fast::EnergyLUT));
     h->fast_glut_off = off; off += align256(glut.size() * sizeof(fast::GasLUT));
     const size_t rgOff = off; off += align256(size_t(kRadGuide) * 2);
@@ -267,6 +276,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     F.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
     F.shells32 = reinterpret_cast<const fast::ShellF32*>(base + h->fast_shell32_off);
     F.shellGuide = reinterpret_cast<const uint8_t*>(base + h->fast_sguide_off);
+    F.shellTab = reinterpret_cast<const fast::ShellCell*>(base + h->fast_stab_off);
   } else if (nCoat > 0) {
     // setup update: only the X-ray-source row (index nE) of each coating can have changed
     std::vector<float> row(reflRow), line(size_t(P.nAngles));
@@ -277,13 +287,12 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
                            row.data(), reflRow * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
-  std::vector<fast::ShellF32> sh32(SART_MAX_SHELLS);
-  fast::derive_f32(h->fparams, shf.data(), h->setup.telescope.nShells, &h->geo32, sh32.data());
   SART_CUDA(cudaMemcpy(base + h->fast_shell_off, shf.data(), shf.size() * sizeof(fast::ShellFast), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_shell32_off, sh32.data(), sh32.size() * sizeof(fast::ShellF32), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_lut_off, lut.data(), lut.size() * sizeof(fast::EnergyLUT), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_glut_off, glut.data(), glut.size() * sizeof(fast::GasLUT), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_sguide_off, sguide.data(), sguide.size(), cudaMemcpyHostToDevice));
+  SART_CUDA(cudaMemcpy(base + h->fast_stab_off, stab.data(), stab.size() * sizeof(fast::ShellCell), cudaMemcpyHostToDevice));
   return SART_OK;
 }
 
@@ -386,6 +395,31 @@ int sart_device_count(void) {
 void sart_cdf_thresholds(const double* cdf, int n, uint32_t* thr) {
   if (!cdf || !thr || n < 0) return;
   for (int i = 0; i < n; ++i) thr[i] = cdf_threshold(cdf[i]);
+}
+
+int sart_shell_lookup(const sart_setup_t* setup, int n, const float* rho, int32_t* via_table, int32_t* via_scan) {
+  if (!setup || n < 0 || (n > 0 && (!rho || !via_table || !via_scan))) return fail(SART_ERR_ARG, "sart_shell_lookup: bad argument");
+  const int nS = setup->telescope.nShells;
+  if (nS < 1 || nS > SART_MAX_SHELLS) return fail(SART_ERR_ARG, "sart_shell_lookup: nShells = %d", nS);
+  std::vector<ShellF64> sh64(SART_MAX_SHELLS);
+  derive_shells(*setup, sh64.data());
+  std::vector<fast::ShellFast> shf(SART_MAX_SHELLS);
+  fast::derive_shells(*setup, sh64.data(), shf.data());
+  fast::FastParams F;
+  std::memset(&F, 0, sizeof F);
+  std::vector<uint8_t> sguide;
+  fast::build_shell_guide(*setup, &F, &sguide);
+  fast::Geo32 G;
+  std::vector<fast::ShellF32> sh32(SART_MAX_SHELLS);
+  fast::derive_f32(F, shf.data(), nS, &G, sh32.data());
+  std::vector<fast::ShellCell> tab;
+  if (sguide.size() > 4096 || !fast::build_shell_table(G, sh32.data(), nS, int(sguide.size()), &tab))
+    return fail(SART_ERR_CONFIG, "shell radii too closely spaced for the radial lookup table");
+  for (int i = 0; i < n; ++i) {
+    via_table[i] = fast::shell_table_lookup(G, tab, rho[i]);
+    via_scan[i] = fast::classify_radius(sh32.data(), nS, rho[i]);
+  }
+  return SART_OK;
 }
 
 void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {

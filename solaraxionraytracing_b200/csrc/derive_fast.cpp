@@ -108,13 +108,22 @@ void derive_f32(const FastParams& f, const ShellFast* a, int nShells, Geo32* g, 
 // step is at most half the smallest shell spacing, so the kernel's forward scan from guide[b] takes 0 or 1 steps.
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide) {
   const sart_telescope_t& t = s.telescope;
+  // smallest distance between two boundaries of the radial classification (front radius R1[j], outer glass edge
+  // R1[j] + thickness[j]): with a step of half of it no bucket holds two of them (build_shell_table verifies)
   double gap = t.allR1[0];
-  for (int j = 1; j < t.nShells; ++j) gap = std::min(gap, t.allR1[j] - t.allR1[j - 1]);
+  for (int j = 0; j < t.nShells; ++j) {
+    if (t.allThickness[j] > 0.0) gap = std::min(gap, t.allThickness[j]);
+    if (j > 0) {
+      gap = std::min(gap, t.allR1[j] - t.allR1[j - 1]);
+      const double open = t.allR1[j] - (t.allR1[j - 1] + t.allThickness[j - 1]);
+      if (open > 0.0) gap = std::min(gap, open);
+    }
+  }
   double step = 0.5 * gap;
   const double span = t.allR1[t.nShells - 1] - t.allR1[0];
-  if (span / step > 2000.0) step = span / 2000.0;
+  if (span / step > 4000.0) step = span / 4000.0;
   if (!(step > 0.0)) step = 1.0;
-  const double rmin = t.allR1[0] - step;
+  const double rmin = t.allR1[0] - 1.5 * step;   // R1[0] sits mid-bucket 1: bucket 0 holds no boundary whatever the rounding
   const int n = int(std::ceil((t.allR1[t.nShells - 1] - rmin) / step)) + 2;
   guide->assign(size_t(n), 0);
   for (int b = 0; b < n; ++b) {
@@ -126,6 +135,80 @@ void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t
   f->shellRhoMin = rmin;
   f->shellInvStep = 1.0 / step;
   f->nShellGuide = n;
+}
+
+// Shell search of stage A for one radial distance, as the FP32 kernels decide it (rt:1932-1957 on the f32 shell records):
+// the shell number, or kShellCellFail + exit code.
+int classify_radius(const ShellF32* sh, int nS, float rho) {
+  int hit = 0;
+  while (hit < nS - 1 && !(sh[hit].R1 > rho)) ++hit;   // first j with R1[j] > rho
+  int code = -1;
+  if (!(sh[hit].R1 > rho)) code = SART_EXIT_NO_MIRROR_HIT;   // == R1[last] (or NaN)
+  if (hit > 0 && rho < sh[hit - 1].R1pT && rho > sh[hit - 1].R1) code = SART_EXIT_GLASS_FRONT;
+  if (rho > sh[nS - 1].R1) code = SART_EXIT_OUTSIDE_SHELLS;
+  return code >= 0 ? kShellCellFail + code : hit;
+}
+
+// One record per radial bucket of the shell guide (fast_params.h: ShellCell). The bucket of a radius is computed with the
+// device's own FP32 expression, which is monotone in the radius, so the radii of one bucket form an interval and the
+// classification inside it changes only at the boundaries that map to this bucket. Returns false when two boundaries share
+// a bucket (shells closer than the grid can resolve): the throughput pipelines then report the setup as unsupported.
+bool build_shell_table(const Geo32& g, const ShellF32* sh, int nS, int nBuckets, std::vector<ShellCell>* out) {
+  if (nS < 1 || nS > kShellCellFail || nBuckets < 2) return false;
+  auto bucket = [&](float rho) {
+    const float d = rho - g.shellRhoMin;
+    const float x = d * g.shellInvStep;
+    int b = x >= float(nBuckets) ? nBuckets - 1 : int(x);   // F2I.TRUNC saturates; NaN -> 0
+    if (!(x == x)) b = 0;
+    return std::max(0, std::min(b, nBuckets - 1));
+  };
+  std::vector<float> bnd;
+  for (int j = 0; j < nS; ++j) {
+    bnd.push_back(sh[j].R1);
+    if (j < nS - 1 && sh[j].R1pT > sh[j].R1) bnd.push_back(sh[j].R1pT);
+  }
+  std::sort(bnd.begin(), bnd.end());
+  bnd.erase(std::unique(bnd.begin(), bnd.end()), bnd.end());
+  std::vector<int> owner(size_t(nBuckets), -1);
+  for (size_t k = 0; k < bnd.size(); ++k) {
+    const int b = bucket(bnd[k]);
+    if (b == 0) return false;            // bucket 0 (everything inside the first shell, and NaN) must be boundary-free
+    if (owner[size_t(b)] >= 0) return false;
+    owner[size_t(b)] = int(k);
+  }
+  out->assign(size_t(nBuckets), ShellCell{0.f, 0u});
+  // bucket 0: radii below R1[0] - step / 2 ... and NaN (neither < B nor > B): no mirror hit, like the scan it replaces
+  int cur = classify_radius(sh, nS, 0.0f);   // outcome of the open interval the next bucket starts in
+  (*out)[0].B = -INFINITY;   // every radius (a norm: >= 0) is "above"; NaN is "at"
+  (*out)[0].sel = uint32_t(cur) | (uint32_t(kShellCellFail + SART_EXIT_NO_MIRROR_HIT) << 8) | (uint32_t(cur) << 16);
+  for (int b = 1; b < nBuckets; ++b) {
+    ShellCell& c = (*out)[size_t(b)];
+    if (owner[size_t(b)] < 0) {
+      c.B = -INFINITY;   // every radius of the bucket is "above"
+      c.sel = uint32_t(cur) | (uint32_t(cur) << 8) | (uint32_t(cur) << 16);
+      continue;
+    }
+    const float B = bnd[size_t(owner[size_t(b)])];
+    const int below = classify_radius(sh, nS, std::nextafterf(B, -INFINITY));
+    const int at = classify_radius(sh, nS, B);
+    const int above = classify_radius(sh, nS, std::nextafterf(B, INFINITY));
+    if (below != cur) return false;   // cannot happen with one boundary per bucket; guards the construction
+    c.B = B;
+    c.sel = uint32_t(below) | (uint32_t(at) << 8) | (uint32_t(above) << 16);
+    cur = above;
+  }
+  return true;
+}
+
+// The device's table lookup (kernels_f32.cu, stage A), restated on the host for sart_shell_lookup.
+int shell_table_lookup(const Geo32& g, const std::vector<ShellCell>& tab, float rho) {
+  const int n = int(tab.size());
+  const float x = (rho - g.shellRhoMin) * g.shellInvStep;
+  int b = !(x == x) ? 0 : (x >= float(n) ? n - 1 : (x <= -1.0f ? 0 : int(x)));   // F2I.TRUNC saturates, NaN -> 0
+  b = std::max(0, std::min(b, n - 1));
+  const ShellCell& c = tab[size_t(b)];
+  const int k = rho < c.B ? 0 : (rho > c.B ? 2 : 1);
+  return int((c.sel >> (8 * k)) & 0xffu);
 }
 
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {

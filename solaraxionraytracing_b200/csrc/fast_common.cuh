@@ -194,12 +194,16 @@ struct RecordSink {
 // Sink of the fused kernels: the tail of traceAxion (rt:2135-2221) + prepareHeatmap (rt:839-842) for one axion mass,
 // applied where the ray's outcome becomes known. Sums live in the caller's registers, exit counts in the warp's
 // shared-memory counters.
-struct ImageSink {
+// kRadial = false compiles the optional radial histogram out (the plain-run kernel variants; the launcher takes the generic
+// variant when sart_enable_radial_hist is on).
+template <bool kRadial>
+struct ImageSinkT {
   static constexpr bool kFold = true;
   const FastTables& T;
   double m2;
   double* __restrict__ image;
   double* __restrict__ imageW2;
+  uint32_t rep;   // element offset of this block's image replica (32-bit: one wide multiply-add per address)
   WarpCounters& wc;
   unsigned int &nPassed, &nTill;
   double &sumW, &sumW2, &sumX, &sumY, &sumR;
@@ -215,17 +219,18 @@ struct ImageSink {
       sumW += wd; sumW2 += wd * wd; sumX += h.x; sumY += h.y; sumR += h.r;
 #ifndef SART_NO_IMAGE_ATOMICS   // (experiment switch: measures what the histogram atomics cost)
       if (h.bin >= 0) {
-        atomicAdd(image + h.bin, wd);
-        atomicAdd(imageW2 + h.bin, wd * wd);
+        const uint32_t at = rep + uint32_t(h.bin);
+        atomicAdd(image + at, wd);
+        atomicAdd(imageW2 + at, wd * wd);
       }
 #endif
-      if (T.rad.w) rad_add(T.rad, h.r, wd);
+      if (kRadial && T.rad.w) rad_add(T.rad, h.r, wd);
     } else {
       atomicAdd(&wc.n_exit[SART_EXIT_ZERO_WEIGHT], 1u);
     }
   }
 };
-
+using ImageSink = ImageSinkT<true>;
 
 // ---- axion-mass scan: the part shared by the FP64-algebra and the FP32 tracing --------------------------------
 // Rays are traced once (lanes = rays) by `trace(global ray index, RayResult&)`; each ray that reaches the weight stage

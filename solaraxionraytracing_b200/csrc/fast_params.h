@@ -70,6 +70,16 @@ struct Geo32 {
   float srcX, srcY, srcRadius, srcRadius2, invSrcDz, colDz;
 };
 
+// Radial lookup of the shell search (rt:1932-1957) for the FP32 kernels: the radial buckets of the shell guide are fine
+// enough to hold at most one boundary (a shell's front radius R1 or the outer edge R1 + thickness of its glass) each,
+// so one 8-byte record decides the outcome: sel holds the outcome below / at / above the boundary B, one byte each
+// (bits 0-7, 8-15, 16-23): a shell number < 64, or 64 + exit code.
+struct ShellCell {
+  float B;
+  uint32_t sel;
+};
+constexpr int kShellCellFail = 64;
+
 struct EnergyLUT {  // one record per tabulated energy index (16 B, one LDG.128)
   float E, Twindow, Tstrongback, Agas;
 };
@@ -96,6 +106,7 @@ struct FastTables {
   const ShellFast* shells;    // [nShells]
   const ShellF32* shells32;   // [nShells] the same records in single precision (kernels_f32.cu)
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
+  const ShellCell* shellTab;  // [nShellGuide] (kernels_f32.cu)
   RadialHist rad;             // optional (w == nullptr: off)
   // Image replicas: block b adds into replica b % nImgRep of the image / w^2 image it is handed (replica r starts
   // imgRepStride doubles after replica 0); 0 or 1 = the image itself. The focal spot concentrates ~1e9 atomic adds per

@@ -74,14 +74,14 @@ struct Smem32 {
   const ShellF32* shell;
   const uint32_t* radThr;
   const uint16_t* radGuide;
-  const uint8_t* shellGuide;
+  const ShellCell* shellTab;
 };
 __device__ __forceinline__ void smem_layout32(const FastParams& P, unsigned char* base, Smem32& s, unsigned char*& tail) {
   size_t off = 0;
   s.shell = reinterpret_cast<const ShellF32*>(base + off); off += (size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15);
   s.radThr = reinterpret_cast<const uint32_t*>(base + off); off += size_t(thr_pitch(P.nRadii)) * 4;
   s.radGuide = reinterpret_cast<const uint16_t*>(base + off); off += size_t(kRadGuide) * 2;
-  s.shellGuide = base + off; off += (size_t(P.nShellGuide) + 15) & ~size_t(15);
+  s.shellTab = reinterpret_cast<const ShellCell*>(base + off); off += (size_t(P.nShellGuide) * sizeof(ShellCell) + 15) & ~size_t(15);
   tail = base + off;
 }
 __device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTables& T, const Smem32& s) {
@@ -92,7 +92,8 @@ __device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTable
     for (int i = threadIdx.x; i < kRadGuide / 8; i += blockDim.x)
       reinterpret_cast<uint4*>(const_cast<uint16_t*>(s.radGuide))[i] = __ldg(reinterpret_cast<const uint4*>(T.radiusGuide) + i);
   }
-  for (int i = threadIdx.x; i < P.nShellGuide; i += blockDim.x) const_cast<uint8_t*>(s.shellGuide)[i] = T.shellGuide[i];
+  for (int i = threadIdx.x; i < P.nShellGuide; i += blockDim.x)
+    reinterpret_cast<uint2*>(const_cast<ShellCell*>(s.shellTab))[i] = __ldg(reinterpret_cast<const uint2*>(T.shellTab) + i);
 }
 
 // Root choice of findPos* (rt:646-658) for A t^2 + 2 hb t + C = 0, as in kernels_fast.cu: q = -(hb + sign(hb) sq), the
@@ -151,11 +152,11 @@ __device__ __forceinline__ int energy_index(const FastParams& P, const FastTable
   const uint32_t kb = we >> (32 - kEnGuideBits);
   const uint16_t* gRow = guide_row(T, rIdx);
   const int e0 = int(__ldg(gRow + kb)) & ~3;
-  const uint32_t* eRow = thr_row(P, T, rIdx);
-  int eIdx = e0 + count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0)), we);
+  const uint32_t eOff = uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies)) + uint32_t(e0);
+  int eIdx = e0 + count_le(__ldg(reinterpret_cast<const uint4*>(T.energyThr + eOff)), we);
   if (eIdx == e0 + 4) {
-    eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4)), we);
-    if (eIdx == e0 + 8) eIdx = thr_search_tail(eRow, e0 + 8, guide_upper(gRow, kb, kEnGuide, P.nEnergies), we);
+    eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u))), we);
+    if (eIdx == e0 + 8) eIdx = thr_search_tail(thr_row(P, T, rIdx), e0 + 8, guide_upper(gRow, kb, kEnGuide, P.nEnergies), we);
     // saturated thresholds: the f64 row decides. The all-ones word passes every threshold, so it always gets here.
     if (we == 0xffffffffu) eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
   }
@@ -215,14 +216,19 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   float ex, ey, sx, sy;
   int eIdx;
   int e0 = 0;
-  const uint32_t* eRow = nullptr;
+  // energy thresholds of this ray: first group at T.energyThr[eOff]. In the plain fused kernel every ray has a row, so
+  // the test is a compile-time constant there (a null-pointer test cost two 64-bit compares + a zero fill per ray).
+  constexpr bool kRowAlways = kPlain && !kPre && !kLateEnergy;
+  bool haveRow = false;
+  uint32_t eOff = 0u;
   if (kPre) {
     ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid;
   } else if (kPlain || !P.testXray) {
     const int rIdx = h.rIdx;
     if (!kLateEnergy) {
       e0 = int(h.guide) & ~3;
-      eRow = thr_row(P, T, rIdx);
+      eOff = uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies)) + uint32_t(e0);
+      haveRow = true;
     }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);
     float s1, c1, s2, c2;
@@ -289,9 +295,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   uint4 etA = make_uint4(0, 0, 0, 0);
 #if !SART_LAZY_THR
   uint4 etB = etA;
-  if (eRow) etB = __ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4));
+  if (kRowAlways || haveRow) etB = __ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u)));
 #endif
-  if (eRow) etA = __ldg(reinterpret_cast<const uint4*>(eRow + e0));
+  if (kRowAlways || haveRow) etA = __ldg(reinterpret_cast<const uint4*>(T.energyThr + eOff));
 
   // ================= telescope frame rt:1888-1905
   float dx = sx, dy = sy, dz = 1.0f, z0 = 0.0f;
@@ -309,9 +315,12 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     dx = ddx; dy = ddy; dz = ddz;
   }
   x0 -= G.oeX; y0 -= G.oeY;
-  const float invdz = (dz == 1.0f) ? 1.0f : rcpf_nr(dz);
-  const float tx = dx * invdz, ty = dy * invdz;
-  x0 = fmaf(-z0, tx, x0); y0 = fmaf(-z0, ty, y0);   // pointEntranceXRT
+  float tx = dx, ty = dy;
+  if (!kPlain && P.rotated) {
+    const float invdz = rcpf_nr(dz);
+    tx = dx * invdz; ty = dy * invdz;
+    x0 = fmaf(-z0, tx, x0); y0 = fmaf(-z0, ty, y0);   // pointEntranceXRT
+  }
   const float rho0sq = fmaf(x0, x0, y0 * y0);
   const float invRho0 = rsqrtf_nr(rho0sq);
   const float radialDist = rho0sq * invRho0;
@@ -352,36 +361,37 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     opaque = hit;
   }
 
-  // ================= shell rt:1932-1957: uniform radial guide + at most one forward step
-  const int nS = P.nShells;
+  // ================= shell rt:1932-1957 (hit shell = first j with R1[j] > radialDist; glass front of the shell below;
+  // outside the last shell): one record of the radial table holds the only boundary of its bucket and the outcomes below /
+  // at / above it (fast_params.h: ShellCell; derive_fast.cpp: build_shell_table)
   int code = -1;
   int hitLayer;
   {
     int b = int((radialDist - G.shellRhoMin) * G.shellInvStep);
     b = max(0, min(b, P.nShellGuide - 1));
-    hitLayer = S.shellGuide[b];
-    if (hitLayer < nS - 1 && !(sShell[hitLayer].R1 > radialDist)) ++hitLayer;   // first j with R1[j] > radialDist
-    if (!(sShell[hitLayer].R1 > radialDist)) code = SART_EXIT_NO_MIRROR_HIT;     // == R1[last]
-    const int below = hitLayer > 0 ? hitLayer - 1 : 0;
-    if (hitLayer > 0 && radialDist < sShell[below].R1pT && radialDist > sShell[below].R1) code = SART_EXIT_GLASS_FRONT;
+    const uint2 c = *reinterpret_cast<const uint2*>(S.shellTab + b);
+    const float B = __uint_as_float(c.x);
+    const uint32_t pick = radialDist < B ? 0x4440u : (radialDist > B ? 0x4442u : 0x4441u);   // NaN: "at" = no mirror hit
+    hitLayer = int(__byte_perm(c.y, 0u, pick));
+    if (hitLayer >= kShellCellFail) code = hitLayer - kShellCellFail;
   }
-  if (radialDist > sShell[nS - 1].R1) code = SART_EXIT_OUTSIDE_SHELLS;
   if (opaque) code = SART_EXIT_OPAQUE;
   if (!okPipe2) code = SART_EXIT_CLIP_PIPE_XRT;
   if (!okPipe1) code = SART_EXIT_CLIP_PIPE_VT3;
   if (!insideExit) code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
   if (code >= 0) return code;
-  if (eRow) {
+  if (kRowAlways || haveRow) {
     const uint32_t we = w[5];
     eIdx = e0 + count_le(etA, we);
     if (eIdx == e0 + 4) {   // ~1 ray in 8: the next four thresholds (loaded only by the lanes that need them)
 #if SART_LAZY_THR
-      eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(eRow + e0 + 4)), we);
+      eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u))), we);
 #else
       eIdx += count_le(etB, we);
 #endif
       if (eIdx == e0 + 8)
-        eIdx = thr_search_tail(eRow, e0 + 8, guide_upper(guide_row(T, h.rIdx), we >> (32 - kEnGuideBits), kEnGuide, P.nEnergies), we);
+        eIdx = thr_search_tail(thr_row(P, T, h.rIdx), e0 + 8,
+                               guide_upper(guide_row(T, h.rIdx), we >> (32 - kEnGuideBits), kEnGuide, P.nEnergies), we);
       // saturated thresholds: the f64 row decides. The all-ones word passes every threshold, so it always gets here.
       if (we == 0xffffffffu)
         eIdx = lower_bound_window(T.energyCDF + size_t(h.rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
@@ -606,8 +616,8 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
-  const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
-  ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const uint32_t rep = T.nImgRep > 1 ? (blockIdx.x % unsigned(T.nImgRep)) * uint32_t(T.imgRepStride) : 0u;
+  ImageSinkT<!kPlain> sink{T, mAxion2, image, imageW2, rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
 #if SART_F32_PREFETCH
   uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x;
@@ -682,8 +692,8 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
   WarpQueue32& Q = queues[warp];
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
-  const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
-  ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const uint32_t rep = T.nImgRep > 1 ? (blockIdx.x % unsigned(T.nImgRep)) * uint32_t(T.imgRepStride) : 0u;
+  ImageSinkT<!kPlain> sink{T, mAxion2, image, imageW2, rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
   uint64_t base = uint64_t(blockIdx.x) * kBlock32 + (threadIdx.x & ~31);
   int qn = 0;
@@ -860,7 +870,7 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
 
 static size_t smem_bytes32(const FastParams& P, int nWarps = kWarps32) {
   return ((size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15)) + size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2 +
-         ((size_t(P.nShellGuide) + 15) & ~size_t(15)) + size_t(nWarps) * sizeof(WarpCounters);
+         ((size_t(P.nShellGuide) * sizeof(ShellCell) + 15) & ~size_t(15)) + size_t(nWarps) * sizeof(WarpCounters);
 }
 
 }  // namespace fast
@@ -871,7 +881,7 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P) + (compact ? fast::kWarps32 * sizeof(fast::WarpQueue32) : 0);
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && !T.rad.w;
   auto kern = compact ? (wolter ? (plain ? fast::k_trace_mc_f32_compact<true, true> : fast::k_trace_mc_f32_compact<true, false>)
                                 : (plain ? fast::k_trace_mc_f32_compact<false, true> : fast::k_trace_mc_f32_compact<false, false>))
                       : (wolter ? (plain ? fast::k_trace_mc_f32<true, true> : fast::k_trace_mc_f32<true, false>)

@@ -523,8 +523,8 @@ k_trace_mc_fast(const __grid_constant__ FastParams P, const __grid_constant__ Fa
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
 
-  const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
-  ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const uint32_t rep = T.nImgRep > 1 ? (blockIdx.x % unsigned(T.nImgRep)) * uint32_t(T.imgRepStride) : 0u;
+  ImageSink sink{T, mAxion2, image, imageW2, rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlockF;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlockF + threadIdx.x; i < nRays; i += stride) {
     ++nIter;
@@ -593,8 +593,8 @@ k_trace_mc_fast_compact(const __grid_constant__ FastParams P, const __grid_const
   unsigned int nPassed = 0, nTill = 0, nIter = 0;
   double sumW = 0.0, sumW2 = 0.0, sumX = 0.0, sumY = 0.0, sumR = 0.0;
   const uint64_t stride = uint64_t(gridDim.x) * kBlockF;
-  const size_t rep = T.nImgRep > 1 ? size_t(blockIdx.x % unsigned(T.nImgRep)) * T.imgRepStride : 0;
-  ImageSink sink{T, mAxion2, image + rep, imageW2 + rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
+  const uint32_t rep = T.nImgRep > 1 ? (blockIdx.x % unsigned(T.nImgRep)) * uint32_t(T.imgRepStride) : 0u;
+  ImageSink sink{T, mAxion2, image, imageW2, rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   uint64_t base = uint64_t(blockIdx.x) * kBlockF + (threadIdx.x & ~31);   // warp-uniform
   int qn = 0;                                                              // warp-uniform queue fill
   for (;;) {

@@ -26,6 +26,9 @@ bool supported(const sart_setup_t& s, const char** why);
 void derive_shells(const sart_setup_t& s, const ShellF64* exactShells, ShellFast* out);
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f);
 void derive_f32(const FastParams& f, const ShellFast* shells, int nShells, Geo32* g, ShellF32* out);
+bool build_shell_table(const Geo32& g, const ShellF32* shells, int nShells, int nBuckets, std::vector<ShellCell>* out);
+int classify_radius(const ShellF32* shells, int nShells, float rho);
+int shell_table_lookup(const Geo32& g, const std::vector<ShellCell>& tab, float rho);
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide);
 void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
                       const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out,
@@ -53,7 +56,7 @@ struct sart_handle {
   sart::fast::FastTables ftables;
   sart::fast::Geo32 geo32;      // single-precision geometry block of precision mode 2
   void* fast_blob = nullptr;
-  size_t fast_shell_off = 0, fast_shell32_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_sguide_off = 0, fast_refl_off = 0;
+  size_t fast_shell_off = 0, fast_shell32_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_sguide_off = 0, fast_stab_off = 0, fast_refl_off = 0;
   std::vector<float> h_refl32;  // host copy of the reflectivity (f32) for rebuilding the X-ray-source row
   std::vector<double> h_energies, h_tab[3][2];  // host copies (energies; strongback/window/gas x,y) for LUT rebuilds
   int sm_count = 148;

@@ -146,3 +146,39 @@ def test_integer_cdf_thresholds_are_exact(rt):
     want = np.searchsorted(row, u, side="left")               # std/algorithm lowerBound
     got = np.searchsorted(th.astype(np.uint64), w, side="right")   # number of thresholds <= w
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("tel", [abi.TK_LLNL, abi.TK_XMM, abi.TK_ABRIXAS])
+def test_shell_lookup_table_equals_the_scan(rt, tel):
+    """sart_shell_lookup: the radial table the FP32 kernels use for the shell search (rt:1932-1957: hit shell, glass front
+    rt:1942-1944, outside the last shell rt:1934) gives the outcome of the scan it replaces for every radius: at each
+    boundary (R1[j], R1[j] + thickness[j]) and the FP32 numbers next to it, at the bucket edges of the table, on a dense
+    sweep, and for NaN / zero / huge arguments."""
+    setup = rt.newExperimentSetup(abi.ES_BABYIAXO, abi.DK_INGRIDIAXO, abi.SK_VACUUM, tel, 0)
+    t = setup.telescope
+    n_sh = t.nShells
+    r1 = np.array(t.allR1[:n_sh], dtype=np.float64)
+    th = np.array(t.allThickness[:n_sh], dtype=np.float64)
+    pts = []
+    for b in np.concatenate([r1, r1 + th]).astype(np.float32):
+        x = b
+        for _ in range(4):
+            x = np.nextafter(x, np.float32(-np.inf))
+        for _ in range(9):
+            pts.append(x)
+            x = np.nextafter(x, np.float32(np.inf))
+    rng = np.random.default_rng(5)
+    lo, hi = float(r1[0]) - 5.0, float(r1[-1]) + 5.0
+    pts = np.concatenate([np.array(pts, dtype=np.float32), np.linspace(lo, hi, 400_001).astype(np.float32),
+                          rng.uniform(lo, hi, 200_000).astype(np.float32),
+                          np.array([np.nan, 0.0, 1e-30, 1e9, np.inf], dtype=np.float32)])   # rho is a norm: >= 0 or NaN
+    a = np.zeros(pts.size, dtype=np.int32)
+    b = np.zeros(pts.size, dtype=np.int32)
+    rc = rt.lib.sart_shell_lookup(C.byref(setup), pts.size, pts.ctypes.data_as(C.POINTER(C.c_float)),
+                                  a.ctypes.data_as(C.POINTER(C.c_int32)), b.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0, rt.lib.sart_last_error()
+    assert np.array_equal(a, b), pts[a != b][:10]
+    # the outcomes are the expected mix: every shell is hit, glass fronts, outside, and NaN = no mirror hit
+    assert set(range(n_sh)) <= set(b.tolist())
+    assert (b == 64 + 7).sum() > 0 and (b == 64 + 6).sum() > 0
+    assert b[-5] == 64 + 9
