@@ -457,6 +457,8 @@ def run_ours(args):
             v, cores, sample, _ = cpu_leg(args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                                    "sample": sample + " (restated oracle, not the Nim executable)"}
+            v1, _, sample1, _ = cpu_leg(min(args.cpu_seconds, 3.0), threads=1)   # 1 thread next to all threads
+            out["cpu_baseline"]["one_thread"] = {"value": v1, "unit": "rays/s", "cores": 1, "sample": sample1}
         print(json.dumps(out), flush=True)
     tr.close()
     if dist is not None:

@@ -60,6 +60,24 @@ def test_config3_1e9_rays(rt, full_llnl, precision):
     assert c1["sum_r"] / c1["n_passed"] < 3.0
 
 
+def test_more_rays_than_one_launch_holds(rt, full_llnl):
+    """The fused FP32 kernel keeps a 32-bit trip count per thread, so the launcher cuts runs above 2^36 rays into several
+    launches (kernels_f32.cu: kMaxRaysPerLaunch): 2^36 + 98 765 rays are all traced, each exactly once."""
+    n = 2**36 + 98_765
+    with rt.RayTracer(full_llnl) as tr:
+        tr.set_precision(2)
+        tr.trace_mc(n, SEED)
+        res = tr.read_image()
+        _check_conservation(res, n)
+        # the rays across the cut, traced alone, are the same rays: counters of [2^36 - 5000, 2^36 + 5000) from a run that
+        # crosses the cut minus the two runs either side of it
+        tr.reset_image(); tr.trace_mc(2**36 + 5000, SEED); a = tr.read_image().counters[0]
+        tr.reset_image(); tr.trace_mc(2**36 - 5000, SEED); b = tr.read_image().counters[0]
+        tr.reset_image(); tr.trace_mc(10_000, SEED, first_ray=2**36 - 5000); c = tr.read_image().counters[0]
+    assert {k: a["n_exit"][k] - b["n_exit"][k] for k in a["n_exit"]} == c["n_exit"]
+    assert res.counters[0]["n_passed"] / n == pytest.approx(0.85763, abs=5e-5)   # 1e9-ray value +- its own error
+
+
 def test_config5_babyiaxo_xmm_4e9_rays(rt):
     """config_default.toml as shipped (BabyIAXO / InGridIAXO / vacuum / XMM) at the per-GPU share of 1e11/8 rays is
     1.25e10; 4e9 here keeps the test short. Ray indices beyond 2^32 exercise the 64-bit Philox counter."""
