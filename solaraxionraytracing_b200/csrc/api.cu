@@ -171,6 +171,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   const char* why = "";
   h->fast_ok = fast::supported(h->setup, &why) ? 1 : 0;
   h->fast_why = why;
+  h->f32_ok = 0;
   if (!h->fast_ok) return SART_OK;
   const Params& P = h->params;
   if (t) {
@@ -201,11 +202,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   std::vector<fast::ShellF32> sh32(SART_MAX_SHELLS);
   fast::derive_f32(h->fparams, shf.data(), h->setup.telescope.nShells, &h->geo32, sh32.data());
   std::vector<fast::ShellCell> stab;
-  if (!fast::build_shell_table(h->geo32, sh32.data(), h->setup.telescope.nShells, int(sguide.size()), &stab)) {
-    h->fast_ok = 0;
-    h->fast_why = "shell radii too closely spaced for the radial lookup table of the throughput pipelines";
-    return SART_OK;
-  }
+  h->f32_ok = fast::build_shell_table(h->geo32, sh32.data(), h->setup.telescope.nShells, int(sguide.size()), &stab) ? 1 : 0;
+  if (!h->f32_ok) stab.assign(sguide.size(), fast::ShellCell{0.f, 0u});   // mode 1 (its own shell scan) stays available
   const int nE = int(h->h_energies.size());
   std::vector<fast::EnergyLUT> lut;
   std::vector<fast::GasLUT> glut;
@@ -491,6 +489,7 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
   SART_CUDA(cudaStreamSynchronize(h->stream));
   if ((rc = upload_fast(h, nullptr))) return rc;
   if (h->precision >= 1 && !h->fast_ok) h->precision = 0;
+  if (h->precision == 2 && !h->f32_ok) h->precision = 1;
   if ((rc = autotune(h))) return rc;
   if (h->n_masses == 1 && h->masses_default) {
     h->masses[0] = setup->consts.mAxion;
@@ -519,6 +518,8 @@ int sart_set_precision(sart_handle_t* h, int mode) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   if (mode < 0 || mode > 2) return fail(SART_ERR_ARG, "unknown precision mode %d", mode);
   if (mode >= 1 && !h->fast_ok) return fail(SART_ERR_CONFIG, "fast pipeline unavailable for this setup: %s", h->fast_why);
+  if (mode == 2 && !h->f32_ok)
+    return fail(SART_ERR_CONFIG, "FP32 pipeline unavailable for this setup: shell radii too closely spaced for its radial lookup table");
   h->precision = mode;
   return SART_OK;
 }

@@ -52,6 +52,7 @@ struct sart_handle {
   // "fast" pipeline: parameter block, LUTs and f32 reflectivity in a second allocation
   int fast_ok = 0;
   const char* fast_why = "";
+  int f32_ok = 0;   // precision mode 2 also needs the radial shell table (derive_fast.cpp: build_shell_table)
   sart::fast::FastParams fparams;
   sart::fast::FastTables ftables;
   sart::fast::Geo32 geo32;      // single-precision geometry block of precision mode 2

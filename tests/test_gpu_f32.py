@@ -280,3 +280,26 @@ def test_presampled_host_path_chunks(rt, oracle, mode):
     for name in ("x", "y", "w", "code", "shell", "energy", "r"):
         assert np.array_equal(getattr(whole, name), np.concatenate([getattr(p, name) for p in parts])), name
     assert (whole.exit_code == abi.EXIT_PASSED).mean() > 0.8
+
+
+def test_f32_refuses_shells_its_radial_table_cannot_resolve(rt):
+    """A glass 1e-5 mm thick puts two boundaries of the shell search into one bucket of the radial table (at most 4000
+    buckets): the FP32 pipeline refuses the setup with a message, modes 1 and 0 (their own shell scans) trace it, and the
+    CPU-side helper reports the same condition."""
+    import ctypes as C
+    setup, tb = make_config("cast_llnl")
+    setup.telescope.allThickness[3] = 1e-5
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        with pytest.raises(rt.SartError, match="radial lookup table"):
+            tr.set_precision(2)
+        out = {}
+        for mode in (1, 0):
+            tr.set_precision(mode); tr.reset_image()
+            tr.trace_mc(200_000, 3)
+            out[mode] = tr.read_image().counters[0]
+    assert out[1]["n_rays"] == out[0]["n_rays"] == 200_000
+    assert sum(abs(out[1]["n_exit"][k] - out[0]["n_exit"][k]) for k in out[0]["n_exit"]) <= 4
+    rho = np.array([70.0], dtype=np.float32); a = np.zeros(1, dtype=np.int32); b = np.zeros(1, dtype=np.int32)
+    rc = rt.lib.sart_shell_lookup(C.byref(setup), 1, rho.ctypes.data_as(C.POINTER(C.c_float)),
+                                  a.ctypes.data_as(C.POINTER(C.c_int32)), b.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc != 0
