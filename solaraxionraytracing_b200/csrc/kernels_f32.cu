@@ -778,7 +778,7 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
 }
 
 // ---- per-ray records (traceAxionWrapper in FP32 mode) ----------------------------------------------------------
-template <bool kWolter>
+template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                     const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
@@ -796,10 +796,10 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     RecordSink<true> sink{r, mAxion2};
     Rec32 rec;
     Head32 hd;
-    stage_a32_head(P, T, S, K, first + i, hd);
-    const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
+    stage_a32_head<kPlain>(P, T, S, K, first + i, hd);
+    const int c0 = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
-    else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
+    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     int code = r.code;
     double wd = 0.0;
     if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
@@ -816,7 +816,7 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
 // The slopes are formed in FP64 from the caller's points (the origin is 1.5e14 mm away), everything after that is the
 // FP32 pipeline. The energy is mapped to its index in the tabulated energies (the reference only ever traces tabulated
 // energies, rt:470); an energy that is not a table value is traced at the nearest one and flagged INTERP_CLAMPED.
-template <bool kWolter>
+template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                        const __grid_constant__ FastTables T, double mAxion2, size_t n, const double* __restrict__ origin,
@@ -854,9 +854,9 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
     RayResult r;
     RecordSink<true> sink{r, mAxion2};
     Rec32 rec;
-    const int c0 = stage_a32<kWolter, true>(P, G, T, S, hd, rec);
+    const int c0 = stage_a32<kWolter, true, kPlain>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
-    else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
+    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     int code = r.code;
     double wd = 0.0;
     if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
@@ -931,7 +931,10 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
   if (n == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P);
-  auto kern = wolter ? fast::k_trace_presampled_f32<true> : fast::k_trace_presampled_f32<false>;
+  // the plain-run variant (run-wide switches as compile-time constants, see k_trace_mc_f32); pre-sampled rays have no source
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  auto kern = wolter ? (plain ? fast::k_trace_presampled_f32<true, true> : fast::k_trace_presampled_f32<true, false>)
+                     : (plain ? fast::k_trace_presampled_f32<false, true> : fast::k_trace_presampled_f32<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int perSM = 0;
@@ -952,7 +955,9 @@ cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, 
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P);
-  auto kern = wolter ? fast::k_trace_mc_rays_f32<true> : fast::k_trace_mc_rays_f32<false>;
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  auto kern = wolter ? (plain ? fast::k_trace_mc_rays_f32<true, true> : fast::k_trace_mc_rays_f32<true, false>)
+                     : (plain ? fast::k_trace_mc_rays_f32<false, true> : fast::k_trace_mc_rays_f32<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
