@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays-per-step", type=float, default=1e9)
     ap.add_argument("--precision", choices=["exact", "fast", "f32"], default=None)
+    ap.add_argument("--sampler", choices=["inverse_cdf", "alias"], default="inverse_cdf",
+                    help="inverse_cdf: the reference's lowerBound(cdf, u), the same rays as the CPU oracle (default, the "
+                         "headline); alias: the same distributions through alias tables (statistical parity only)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -191,6 +194,37 @@ class ClockSampler:
                 "samples": len(inside), "window": where, "reasons": sorted(reasons)}
 
 
+def alias_leg(tr, torch, stream, flush, R: int, peak_tflops: float, steps: int = 5, warmup: int = 3):
+    """The same fused kernel with sart_set_sampler(SART_SAMPLER_ALIAS): emission shell and energy drawn from alias
+    tables of the same discrete distributions (one lookup each) instead of the inverse-CDF search. Reported next to the
+    headline, not as the headline: its runs agree with the reference statistically (tier b: tests/test_gpu_f32.py), but
+    a (seed, index) pair no longer denotes the ray it denotes in the CPU oracle."""
+    from solaraxionraytracing_b200 import abi
+    tr.set_sampler(abi.SAMPLER_ALIAS)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        tr.reset_image()
+        for k in range(warmup + steps):
+            flush.zero_()
+            if k >= warmup:
+                ev[k - warmup][0].record(stream)
+            tr.trace_mc(R, SEED, first_ray=k * R)
+            if k >= warmup:
+                ev[k - warmup][1].record(stream)
+        torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    c = tr.read_image().counters[0]
+    tr.set_sampler(abi.SAMPLER_INVERSE_CDF)
+    tr.reset_image()
+    achieved = F_RAY_LLNL * R / (ms * 1e-3) / 1e12
+    return {"value": R / (ms * 1e-3), "unit": "rays/s", "kernel_ms": ms, "steps": steps, "warmup": warmup,
+            "passed_fraction": c["n_passed"] / max(1, c["n_rays"]),
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tflops if peak_tflops else None},
+            "note": "sart_set_sampler(SART_SAMPLER_ALIAS): same distributions, one table lookup per draw; statistical "
+                    "parity only (not the headline)"}
+
+
 def presampled_leg(tr, torch, device, n_unique: int = 1 << 20, repeat: int = 16, host_repeat: int = 8):
     """Tier-(a) kernel (k_trace_presampled, exact FP64 mode): SoA rays in HBM -> SoA records in HBM, 80 B/ray
     (48 in: origin xyz, exit xy, energy; 32 out: x, y, w f64 + code, shell i32), plus the same through host buffers.
@@ -335,6 +369,8 @@ def run_ours(args):
     fs = rt.FullRaytraceSetup(setup, tb)
     tr = rt.RayTracer(fs, local)
     tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[precision])
+    if args.sampler == "alias":
+        tr.set_sampler(abi.SAMPLER_ALIAS)
     table_upload_s = time.perf_counter() - t0
 
     stream = torch.cuda.ExternalStream(tr.stream, device=local)
@@ -429,7 +465,7 @@ def run_ours(args):
             "metric": "traced rays/s", "value": value, "unit": "rays/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"exact": "f64", "fast": "f64 geometry + f32 weights", "f32": "f32"}[precision], "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "precision": precision,
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "precision": precision, "sampler": args.sampler,
                        "l2": "256 MiB buffer written between steps (L2 flush)", "seed": SEED,
                        "table_upload_s": round(table_upload_s, 3),
                        "passed_fraction": c["n_passed"] / max(1, c["n_rays"])},
@@ -450,6 +486,8 @@ def run_ours(args):
                          "peak_source": "sart_measure_fma_peak in this run (MEASURED_PEAKS.json has no CUDA-core "
                                         "figure); the kernel moves ~0 HBM bytes per ray"},
         }
+        if n_gpus == 1 and not args.no_presampled and precision == "f32" and args.sampler == "inverse_cdf":
+            out["alias_sampler"] = alias_leg(tr, torch, stream, flush, R, peak.value)
         if n_gpus == 1 and not args.no_presampled:
             out["presampled"] = presampled_leg(tr, torch, local)
             out["e2e_records"] = records_leg(tr, torch)

@@ -347,6 +347,22 @@ void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]);
  * 464) is then the number of thresholds <= w, for every w < 0xffffffff. */
 void sart_cdf_thresholds(const double* cdf, int n, uint32_t* thr);
 
+/* ---- sampler of the emission shell and the energy (rt:437, 464). SART_SAMPLER_INVERSE_CDF (default) is the reference's
+ * lowerBound(cdf, u) as exact integer work: the ray a (seed, index) pair denotes is the same in every precision mode and in
+ * the CPU oracle. SART_SAMPLER_ALIAS draws from the very same discrete distributions — P(i) = the number of 32-bit words
+ * the inverse-CDF search maps to i, over 2^32 — through Walker/Vose alias tables: one table lookup instead of a search
+ * (+13 % rays/s on CAST+LLNL). The distributions agree to ~1e-9 per index, the (seed, index) -> ray mapping does not:
+ * runs agree with the other modes and the oracle statistically (tier b), not ray by ray. Honoured by sart_trace_mc (single
+ * mass), sart_angular_scan and sart_trace_mc_rays in precision mode 2; those calls fail with SART_ERR_CONFIG in any other
+ * configuration while it is selected. The X-ray test source draws no table values and is unaffected. */
+enum { SART_SAMPLER_INVERSE_CDF = 0, SART_SAMPLER_ALIAS = 1 };
+int sart_set_sampler(sart_handle_t* h, int sampler);
+/* Host helper, exported for tests: the alias entries of the distribution the n thresholds `thr` (sart_cdf_thresholds)
+ * define. entries[k]: bits 31..11 = the share of bucket k that stays with index k, in units of 2^-21 of the bucket;
+ * bits 10..0 = the index that receives the rest. A 32-bit word w selects k = (w n) >> 32 and takes index k when the low 32
+ * bits of w n are below (entries[k] & 0xfffff800), else the alias. n <= 2048 (entries are zeroed otherwise). */
+void sart_alias_table(const uint32_t* thr, int n, uint32_t* entries);
+
 /* ---- the radial lookup table of the shell search (host helper, exported for tests). The FP32 kernels replace the
  * scan of rt:1932-1957 (hit shell = first j with R1[j] > rho; glass front of the shell below rt:1942-1944; outside the
  * last shell rt:1934) by one record of a uniform radial table. For n radial distances rho [mm] this returns the outcome

@@ -31,6 +31,8 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--nRays", type=float, default=None, help="NumberOfPointsSun (rt:251); default [Run].nRays or 1e6")
     ap.add_argument("--seed", type=int, default=None, help="default [Run].seed or 299792458 (rt:276)")
     ap.add_argument("--precision", choices=["f32", "fast", "exact"], default=None)
+    ap.add_argument("--sampler", choices=["inverse_cdf", "alias"], default=None,
+                    help="alias: emission shell / energy from alias tables of the same distributions (f32, single mass)")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--outputPath", default="", help="overrides [Resources].outputPath")
     return ap
@@ -66,7 +68,7 @@ def load_tables(rt, tables, res, setup, device: int):
 
 def main(argv=None) -> int:
     a = build_parser().parse_args(argv)
-    from . import config as cfgmod, output, raytracer as rt, tables
+    from . import abi, config as cfgmod, output, raytracer as rt, tables
     cfg_file = a.config or (str(Path(a.configPath) / "config.toml") if a.configPath else None)
     flags = rt.flags_from_cli(a.ignoreDetWindow, a.ignoreGasAbs, a.ignoreConvProb, a.ignoreReflection, a.xrayTest,
                               a.magnet, a.detectorInstall)
@@ -82,6 +84,8 @@ def main(argv=None) -> int:
     n = int(a.nRays)
     with rt.RayTracer(fs, a.device) as tr:
         tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[a.precision])
+        if (a.sampler or run.sampler) == "alias":
+            tr.set_sampler(abi.SAMPLER_ALIAS)
         if run.mAxion:
             tr.set_axion_masses(run.mAxion)
         if a.angularScanMin == a.angularScanMax:

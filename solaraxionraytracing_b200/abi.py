@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as C
 
 ABI_VERSION = 1
+SAMPLER_INVERSE_CDF, SAMPLER_ALIAS = 0, 1
 MAX_SHELLS = 64
 MAX_COATINGS = 8
 IMAGE_BINS = 256
@@ -198,5 +199,7 @@ SIGNATURES = {
                                        C.POINTER(C.c_uint64)]),
     "sart_ray_uniforms": (None, [C.c_uint64, C.c_uint64, c_double_p]),
     "sart_cdf_thresholds": (None, [c_double_p, C.c_int, C.POINTER(C.c_uint32)]),
+    "sart_set_sampler": (C.c_int, [H, C.c_int]),
+    "sart_alias_table": (None, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
     "sart_shell_lookup": (C.c_int, [C.POINTER(Setup), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }

@@ -61,6 +61,7 @@ class Run:
     seed: int = 299792458
     mAxion: tuple = ()          # eV; empty = the reference's 0.0853 eV; several values = a mass scan (gas stage)
     precision: str = "f32"      # f32 | fast | exact
+    sampler: str = "inverse_cdf"   # inverse_cdf (the reference's lowerBound) | alias (same distributions, f32 single mass only)
 
 
 def parseRun(cfg: dict) -> Run:
@@ -69,7 +70,10 @@ def parseRun(cfg: dict) -> Run:
     if isinstance(m, (int, float)):
         m = (float(m),)
     out = Run(nRays=int(r.get("nRays", 1_000_000)), seed=int(r.get("seed", 299792458)),
-              mAxion=tuple(float(x) for x in m), precision=str(r.get("precision", "f32")))
+              mAxion=tuple(float(x) for x in m), precision=str(r.get("precision", "f32")),
+              sampler=str(r.get("sampler", "inverse_cdf")))
+    if out.sampler not in ("inverse_cdf", "alias"):
+        raise ValueError(f"[Run] sampler = {out.sampler!r}; expected inverse_cdf or alias")
     if out.precision not in ("f32", "fast", "exact"):
         raise ValueError(f"[Run] precision = {out.precision!r}; expected f32, fast or exact")
     if out.nRays < 0 or len(out.mAxion) > abi.MAX_MASSES:

@@ -137,6 +137,45 @@ void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t
   f->nShellGuide = n;
 }
 
+// Walker/Vose alias table of the discrete distribution the integer thresholds define: index i has the weight
+// c[i] = thr[i] - thr[i-1] (thr[-1] = 0, and the last index takes what is left of 2^32), i.e. exactly the number of
+// 32-bit words the inverse-CDF search maps to i. Exact integer arithmetic: masses c[i] n against a bucket capacity of
+// 2^32. Entry k: bits 31..11 = the share bucket k keeps for itself, floored to units of 2^11 (a bucket that keeps
+// everything is its own alias, so the flooring never loses it), bits 10..0 = alias. n <= 2048.
+bool build_alias_table(const uint32_t* thr, int n, uint32_t* out) {
+  if (n < 1 || n > 2048) return false;
+  const uint64_t cap = uint64_t(1) << 32;
+  std::vector<uint64_t> mass(size_t(n), 0);
+  uint64_t prev = 0;
+  for (int i = 0; i < n; ++i) {
+    const uint64_t t = i < n - 1 ? uint64_t(thr[i]) : cap;   // the last index ends the range
+    const uint64_t hi = t < prev ? prev : t;
+    mass[size_t(i)] = (hi - prev) * uint64_t(n);
+    prev = hi;
+  }
+  std::vector<int> small, large;
+  small.reserve(size_t(n)); large.reserve(size_t(n));
+  for (int i = 0; i < n; ++i) (mass[size_t(i)] < cap ? small : large).push_back(i);
+  std::vector<uint64_t> keep(size_t(n), cap);
+  std::vector<int> alias(static_cast<size_t>(n), 0);
+  for (int i = 0; i < n; ++i) alias[size_t(i)] = i;
+  while (!small.empty() && !large.empty()) {
+    const int s = small.back(); small.pop_back();
+    const int l = large.back();
+    keep[size_t(s)] = mass[size_t(s)];
+    alias[size_t(s)] = l;
+    mass[size_t(l)] -= cap - mass[size_t(s)];   // exact: the sum of all masses is n 2^32
+    if (mass[size_t(l)] < cap) { large.pop_back(); small.push_back(l); }
+  }
+  // what is left (either list) holds exactly one capacity each: such a bucket keeps everything
+  for (int i = 0; i < n; ++i) {
+    uint32_t share = keep[size_t(i)] >= cap ? 0xfffff800u : uint32_t(keep[size_t(i)]) & 0xfffff800u;
+    const int a = keep[size_t(i)] >= cap ? i : alias[size_t(i)];
+    out[i] = share | uint32_t(a);
+  }
+  return true;
+}
+
 // Shell search of stage A for one radial distance, as the FP32 kernels decide it (rt:1932-1957 on the f32 shell records):
 // the shell number, or kShellCellFail + exit code.
 int classify_radius(const ShellF32* sh, int nS, float rho) {

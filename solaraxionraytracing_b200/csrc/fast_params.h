@@ -107,6 +107,14 @@ struct FastTables {
   const ShellF32* shells32;   // [nShells] the same records in single precision (kernels_f32.cu)
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket
   const ShellCell* shellTab;  // [nShellGuide] (kernels_f32.cu)
+  // Alias tables (sart_set_sampler(SART_SAMPLER_ALIAS), kernels_f32.cu): the same discrete distributions as the
+  // thresholds above — P(i) = (thr[i] - thr[i-1]) 2^-32 — as Walker/Vose tables, one 32-bit entry per index:
+  // bits 31..11 = the bucket's own share in units of 2^-21, bits 10..0 = the alias index. A word w selects bucket
+  // k = (w n) >> 32 and keeps it when the low 32 bits of w n are below the share, else takes the alias: one lookup, no
+  // search. Needs n <= 2048; null when unavailable.
+  const uint32_t* radiusAlias;   // [nRadii]
+  const uint32_t* energyAlias;   // [nRadii][nEnergies]
+  int32_t sampler, pad2_;        // SART_SAMPLER_* for this launch
   RadialHist rad;             // optional (w == nullptr: off)
   // Image replicas: block b adds into replica b % nImgRep of the image / w^2 image it is handed (replica r starts
   // imgRepStride doubles after replica 0); 0 or 1 = the image itself. The focal spot concentrates ~1e9 atomic adds per

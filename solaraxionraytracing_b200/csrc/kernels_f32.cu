@@ -12,6 +12,9 @@
 //   * reciprocals / square roots are MUFU seeds plus one Newton step in FP32 (2-3 FFMA).
 // Sampling (integer inverse-CDF search, Philox) and weights (FP32 factors, FP64 product and accumulation) are the very
 // same code as mode 1 (fast_common.cuh), so a ray has the same emission shell, energy and exit-disc point in all modes.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fast_common.cuh"
 
 namespace sart {
@@ -72,22 +75,30 @@ struct F3 { float x, y, z; };
 
 struct Smem32 {
   const ShellF32* shell;
-  const uint32_t* radThr;
+  const uint32_t* radThr;     // alias sampler: the nRadii alias entries instead (and no guide)
   const uint16_t* radGuide;
   const ShellCell* shellTab;
 };
+__host__ __device__ __forceinline__ size_t rad_smem_bytes(const FastParams& P, bool alias) {
+  return alias ? ((size_t(P.nRadii) * 4 + 15) & ~size_t(15)) : size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2;
+}
+template <bool kAlias = false>
 __device__ __forceinline__ void smem_layout32(const FastParams& P, unsigned char* base, Smem32& s, unsigned char*& tail) {
   size_t off = 0;
   s.shell = reinterpret_cast<const ShellF32*>(base + off); off += (size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15);
-  s.radThr = reinterpret_cast<const uint32_t*>(base + off); off += size_t(thr_pitch(P.nRadii)) * 4;
-  s.radGuide = reinterpret_cast<const uint16_t*>(base + off); off += size_t(kRadGuide) * 2;
+  s.radThr = reinterpret_cast<const uint32_t*>(base + off);
+  s.radGuide = reinterpret_cast<const uint16_t*>(base + off + (kAlias ? 0 : size_t(thr_pitch(P.nRadii)) * 4));
+  off += rad_smem_bytes(P, kAlias);
   s.shellTab = reinterpret_cast<const ShellCell*>(base + off); off += (size_t(P.nShellGuide) * sizeof(ShellCell) + 15) & ~size_t(15);
   tail = base + off;
 }
+template <bool kAlias = false>
 __device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTables& T, const Smem32& s) {
   for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellF32) / 4); i += blockDim.x)
     reinterpret_cast<float*>(const_cast<ShellF32*>(s.shell))[i] = reinterpret_cast<const float*>(T.shells32)[i];
-  if (P.nRadii > 0) {
+  if (kAlias) {
+    for (int i = threadIdx.x; i < P.nRadii; i += blockDim.x) const_cast<uint32_t*>(s.radThr)[i] = __ldg(T.radiusAlias + i);
+  } else if (P.nRadii > 0) {
     for (int i = threadIdx.x; i < thr_pitch(P.nRadii); i += blockDim.x) const_cast<uint32_t*>(s.radThr)[i] = T.radiusThr[i];
     for (int i = threadIdx.x; i < kRadGuide / 8; i += blockDim.x)
       reinterpret_cast<uint4*>(const_cast<uint16_t*>(s.radGuide))[i] = __ldg(reinterpret_cast<const uint4*>(T.radiusGuide) + i);
@@ -145,10 +156,26 @@ struct Rec32 {
   uint32_t we;
 };
 
+// Alias-table lookup (fast_params.h: FastTables::radiusAlias): index of a distribution over n values for the random word w.
+__device__ __forceinline__ int alias_pick(uint32_t w, int n, uint32_t& bucket, uint32_t& coin) {
+  const uint64_t x = uint64_t(w) * uint32_t(n);
+  bucket = uint32_t(x >> 32); coin = uint32_t(x);
+  return int(bucket);
+}
+__device__ __forceinline__ int alias_resolve(uint32_t entry, uint32_t bucket, uint32_t coin) {
+  return coin < (entry & 0xfffff800u) ? int(bucket) : int(entry & 0x7ffu);
+}
+
 // Energy index rt:464 of a ray of emission shell rIdx whose energy word is `we`: idx = lowerBound(diffFluxCDFs[rIdx], u),
 // exact (integer thresholds). The three dependent gathers (guide entry, thresholds, then the caller's LUT / reflectivity
 // rows) are taken in a row here; the non-compacting kernel spreads them over stage A instead.
+template <bool kAlias = false>
 __device__ __forceinline__ int energy_index(const FastParams& P, const FastTables& T, int rIdx, uint32_t we, bool& clamped) {
+  if (kAlias) {
+    uint32_t k, coin;
+    alias_pick(we, P.nEnergies, k, coin);
+    return alias_resolve(__ldg(T.energyAlias + (uint32_t(rIdx) * uint32_t(P.nEnergies) + k)), k, coin);
+  }
   const uint32_t kb = we >> (32 - kEnGuideBits);
   const uint16_t* gRow = guide_row(T, rIdx);
   const int e0 = int(__ldg(gRow + kb)) & ~3;
@@ -179,13 +206,19 @@ struct Head32 {
 // kPlain (here and below): the kernel variant for the plain run — solar source, vacuum stage, telescope not turned, no
 // ignore* flag — in which those run-wide switches are compile-time constants instead of uniform branches (~5 % of the
 // instructions); every other setup takes the generic variant.
-template <bool kPlain = false, bool kLateEnergy = false>
+template <bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
 __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S,
                                                const PhiloxKeys& K, uint64_t ray, Head32& h) {
   ray_words(K, ray, h.w);
   h.rIdx = 0; h.guide = 0;
   if (kPlain || !P.testXray) {
     const uint32_t wr = h.w[2];
+    if (kAlias) {   // emission shell from the alias table in shared memory; the energy entry is loaded in stage A
+      uint32_t k, coin;
+      alias_pick(wr, P.nRadii, k, coin);
+      h.rIdx = alias_resolve(S.radThr[k], k, coin);
+      return;
+    }
     const uint32_t kr = wr >> (32 - kRadGuideBits);
     const int r0 = int(S.radGuide[kr]) & ~3;
     int rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
@@ -205,10 +238,9 @@ __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTa
 // kPre: the sampling block is skipped, the ray comes from the head record (sart_trace_presampled).
 // kLateEnergy: the energy search is left to the caller (energy_index after the compaction): 2/3 of the BabyIAXO+XMM
 // rays end in this stage and never need their energy.
-template <bool kWolter, bool kPre = false, bool kPlain = false, bool kLateEnergy = false>
+template <bool kWolter, bool kPre = false, bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
 __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
                                          const Head32& h, Rec32& rec) {
-  const ShellF32* __restrict__ sShell = S.shell;
   const uint32_t* w = h.w;
   constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
   bool clamped = false;
@@ -221,13 +253,19 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   constexpr bool kRowAlways = kPlain && !kPre && !kLateEnergy;
   bool haveRow = false;
   uint32_t eOff = 0u;
+  uint32_t aBucket = 0u, aCoin = 0u, aEntry = 0u;   // alias sampler
   if (kPre) {
     ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid;
   } else if (kPlain || !P.testXray) {
     const int rIdx = h.rIdx;
     if (!kLateEnergy) {
-      e0 = int(h.guide) & ~3;
-      eOff = uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies)) + uint32_t(e0);
+      if (kAlias) {
+        alias_pick(w[5], P.nEnergies, aBucket, aCoin);
+        eOff = uint32_t(rIdx) * uint32_t(P.nEnergies) + aBucket;
+      } else {
+        e0 = int(h.guide) & ~3;
+        eOff = uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies)) + uint32_t(e0);
+      }
       haveRow = true;
     }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);
@@ -297,7 +335,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   uint4 etB = etA;
   if (kRowAlways || haveRow) etB = __ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u)));
 #endif
-  if (kRowAlways || haveRow) etA = __ldg(reinterpret_cast<const uint4*>(T.energyThr + eOff));
+  if (kAlias) {
+    if (kRowAlways || haveRow) aEntry = __ldg(T.energyAlias + eOff);
+  } else if (kRowAlways || haveRow) etA = __ldg(reinterpret_cast<const uint4*>(T.energyThr + eOff));
 
   // ================= telescope frame rt:1888-1905
   float dx = sx, dy = sy, dz = 1.0f, z0 = 0.0f;
@@ -380,7 +420,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   if (!okPipe1) code = SART_EXIT_CLIP_PIPE_VT3;
   if (!insideExit) code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
   if (code >= 0) return code;
-  if (kRowAlways || haveRow) {
+  if (kAlias) {
+    if (kRowAlways || haveRow) eIdx = alias_resolve(aEntry, aBucket, aCoin);
+  } else if (kRowAlways || haveRow) {
     const uint32_t we = w[5];
     eIdx = e0 + count_le(etA, we);
     if (eIdx == e0 + 4) {   // ~1 ray in 8: the next four thresholds (loaded only by the lanes that need them)
@@ -599,7 +641,7 @@ __device__ __forceinline__ void flush_counters(sart_counters_t* c, const WarpCou
 }
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
-template <bool kWolter, bool kPlain>
+template <bool kWolter, bool kPlain, bool kAlias>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G, const __grid_constant__ FastTables T,
                double mAxion2, uint64_t first, uint64_t nRays, const __grid_constant__ PhiloxKeys K, double* __restrict__ image,
@@ -607,9 +649,9 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
   unsigned char* tail;
-  smem_layout32(P, smem, S, tail);
+  smem_layout32<kAlias>(P, smem, S, tail);
   WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
-  smem_fill32(P, T, S);
+  smem_fill32<kAlias>(P, T, S);
   for (int i = threadIdx.x; i < kWarps32 * int(sizeof(WarpCounters) / 4); i += kBlock32) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
@@ -622,14 +664,14 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
 #if SART_F32_PREFETCH
   uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x;
   Head32 cur;
-  if (i < nRays) stage_a32_head<kPlain>(P, T, S, K, first + i, cur);
+  if (i < nRays) stage_a32_head<kPlain, false, kAlias>(P, T, S, K, first + i, cur);
   while (i < nRays) {
     ++nIter;
     const uint64_t inext = i + stride;
     Head32 nxt;
-    if (inext < nRays) stage_a32_head<kPlain>(P, T, S, K, first + inext, nxt);   // next ray's guide load goes out now
+    if (inext < nRays) stage_a32_head<kPlain, false, kAlias>(P, T, S, K, first + inext, nxt);   // next ray's guide load goes out now
     Rec32 rec;
-    const int code = stage_a32<kWolter, false, kPlain>(P, G, T, S, cur, rec);
+    const int code = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, cur, rec);
     if (code >= 0) sink.fail(code);
     else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     cur = nxt;
@@ -643,9 +685,9 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   uint64_t ray = first + i0;
   for (unsigned k = nIter; k != 0u; --k, ray += stride) {
     Head32 hd;
-    stage_a32_head<kPlain>(P, T, S, K, ray, hd);
+    stage_a32_head<kPlain, false, kAlias>(P, T, S, K, ray, hd);
     Rec32 rec;
-    const int code = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
+    const int code = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, hd, rec);
     if (code >= 0) sink.fail(code);
     else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
   }
@@ -672,7 +714,7 @@ struct WarpQueue32 {
   uint32_t we[kQueue32];   // energy word of the ray (solar source: the energy is resolved after the compaction)
 };
 
-template <bool kWolter, bool kPlain>
+template <bool kWolter, bool kPlain, bool kAlias>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                        const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
@@ -680,10 +722,10 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
   unsigned char* tail;
-  smem_layout32(P, smem, S, tail);
+  smem_layout32<kAlias>(P, smem, S, tail);
   WarpCounters* wc = reinterpret_cast<WarpCounters*>(tail);
   WarpQueue32* queues = reinterpret_cast<WarpQueue32*>(tail + kWarps32 * sizeof(WarpCounters));
-  smem_fill32(P, T, S);
+  smem_fill32<kAlias>(P, T, S);
   for (int i = threadIdx.x; i < kWarps32 * int(sizeof(WarpCounters) / 4); i += kBlock32) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
@@ -705,8 +747,8 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       int code = SART_N_EXIT_CODES;
       if (i < nRays) {
         Head32 hd;
-        stage_a32_head<kPlain, true>(P, T, S, K, first + i, hd);
-        code = stage_a32<kWolter, false, kPlain, true>(P, G, T, S, hd, rec);
+        stage_a32_head<kPlain, true, kAlias>(P, T, S, K, first + i, hd);
+        code = stage_a32<kWolter, false, kPlain, true, kAlias>(P, G, T, S, hd, rec);
         ++nIter;
         if (code >= 0) sink.fail(code);
       }
@@ -731,7 +773,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       rec.path2 = Q.path2[pos];
       const int meta = Q.meta[pos];
       rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
-      if (kPlain || !P.testXray) rec.eIdx = energy_index(P, T, rec.eIdx, Q.we[pos], rec.clamped);
+      if (kPlain || !P.testXray) rec.eIdx = energy_index<kAlias>(P, T, rec.eIdx, Q.we[pos], rec.clamped);
       stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     }
     qn -= take;
@@ -778,7 +820,7 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
 }
 
 // ---- per-ray records (traceAxionWrapper in FP32 mode) ----------------------------------------------------------
-template <bool kWolter, bool kPlain>
+template <bool kWolter, bool kPlain, bool kAlias>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                     const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
@@ -787,8 +829,8 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
   unsigned char* tail;
-  smem_layout32(P, smem, S, tail);
-  smem_fill32(P, T, S);
+  smem_layout32<kAlias>(P, smem, S, tail);
+  smem_fill32<kAlias>(P, T, S);
   __syncthreads();
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x; i < nRays; i += stride) {
@@ -796,8 +838,8 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     RecordSink<true> sink{r, mAxion2};
     Rec32 rec;
     Head32 hd;
-    stage_a32_head<kPlain>(P, T, S, K, first + i, hd);
-    const int c0 = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
+    stage_a32_head<kPlain, false, kAlias>(P, T, S, K, first + i, hd);
+    const int c0 = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, hd, rec);
     if (c0 >= 0) sink.fail(c0);
     else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     int code = r.code;
@@ -868,9 +910,21 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
   }
 }
 
-static size_t smem_bytes32(const FastParams& P, int nWarps = kWarps32) {
-  return ((size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15)) + size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2 +
+static size_t smem_bytes32(const FastParams& P, int nWarps = kWarps32, bool alias = false) {
+  return ((size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15)) + rad_smem_bytes(P, alias) +
          ((size_t(P.nShellGuide) * sizeof(ShellCell) + 15) & ~size_t(15)) + size_t(nWarps) * sizeof(WarpCounters);
+}
+
+// Dynamic shared memory limit + an explicit L1 / shared-memory split for a kernel. Left to the driver, the split of a
+// launch depends on what ran on the SMs before it (measured: the same fused kernel ran at 20.0 or at 24.2 ms for a whole
+// process, depending on whether its first launch followed a 256 MB memset): these kernels live on L1 for their table
+// gathers, so they ask for the smallest shared-memory carve-out that holds their block.
+template <class K>
+static cudaError_t set_smem(K kern, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  const int pct = int(((smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));   // of 228 KB, rounded up (+1 KB the system reserves)
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 }
 
 }  // namespace fast
@@ -880,13 +934,26 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
                                 sart_counters_t* counters, int smCount, bool compact, cudaStream_t s) {
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
-  const size_t smem = fast::smem_bytes32(P) + (compact ? fast::kWarps32 * sizeof(fast::WarpQueue32) : 0);
+  // alias sampler: solar source only (the X-ray test source draws no table values)
+  const bool alias = T.sampler == SART_SAMPLER_ALIAS && !P.testXray && T.radiusAlias && T.energyAlias;
+  const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias) + (compact ? fast::kWarps32 * sizeof(fast::WarpQueue32) : 0);
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && !T.rad.w;
-  auto kern = compact ? (wolter ? (plain ? fast::k_trace_mc_f32_compact<true, true> : fast::k_trace_mc_f32_compact<true, false>)
-                                : (plain ? fast::k_trace_mc_f32_compact<false, true> : fast::k_trace_mc_f32_compact<false, false>))
-                      : (wolter ? (plain ? fast::k_trace_mc_f32<true, true> : fast::k_trace_mc_f32<true, false>)
-                                : (plain ? fast::k_trace_mc_f32<false, true> : fast::k_trace_mc_f32<false, false>));
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, double*, double*,
+                        sart_counters_t*);
+  static const Kern table[2][2][2][2] = {   // [compact][wolter][plain][alias]
+      {{{fast::k_trace_mc_f32<false, false, false>, fast::k_trace_mc_f32<false, false, true>},
+        {fast::k_trace_mc_f32<false, true, false>, fast::k_trace_mc_f32<false, true, true>}},
+       {{fast::k_trace_mc_f32<true, false, false>, fast::k_trace_mc_f32<true, false, true>},
+        {fast::k_trace_mc_f32<true, true, false>, fast::k_trace_mc_f32<true, true, true>}}},
+      {{{fast::k_trace_mc_f32_compact<false, false, false>, fast::k_trace_mc_f32_compact<false, false, true>},
+        {fast::k_trace_mc_f32_compact<false, true, false>, fast::k_trace_mc_f32_compact<false, true, true>}},
+       {{fast::k_trace_mc_f32_compact<true, false, false>, fast::k_trace_mc_f32_compact<true, false, true>},
+        {fast::k_trace_mc_f32_compact<true, true, false>, fast::k_trace_mc_f32_compact<true, true, true>}}}};
+  const Kern kern = table[compact ? 1 : 0][wolter ? 1 : 0][plain ? 1 : 0][alias ? 1 : 0];
+  if (getenv("SART_DEBUG"))
+    fprintf(stderr, "[sart] k_trace_mc_f32 compact=%d wolter=%d plain=%d alias=%d (sampler=%d ra=%p ea=%p) smem=%zu\n", int(compact),
+            int(wolter), int(plain), int(alias), T.sampler, (const void*)T.radiusAlias, (const void*)T.energyAlias, smem);
+  cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   int perSM = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock32, smem);
@@ -912,7 +979,7 @@ cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Ge
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P, fast::kWarpsM);
   auto kern = wolter ? fast::k_trace_mc_f32_masses<true> : fast::k_trace_mc_f32_masses<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   int perSM = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlockM, smem);
@@ -935,7 +1002,7 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
   auto kern = wolter ? (plain ? fast::k_trace_presampled_f32<true, true> : fast::k_trace_presampled_f32<true, false>)
                      : (plain ? fast::k_trace_presampled_f32<false, true> : fast::k_trace_presampled_f32<false, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   int perSM = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock32, smem);
@@ -954,11 +1021,18 @@ cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, 
                                cudaStream_t s) {
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
-  const size_t smem = fast::smem_bytes32(P);
+  const bool alias = T.sampler == SART_SAMPLER_ALIAS && !P.testXray && T.radiusAlias && T.energyAlias;
+  const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias);
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
-  auto kern = wolter ? (plain ? fast::k_trace_mc_rays_f32<true, true> : fast::k_trace_mc_rays_f32<true, false>)
-                     : (plain ? fast::k_trace_mc_rays_f32<false, true> : fast::k_trace_mc_rays_f32<false, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, double*, double*,
+                        double*, int32_t*, int32_t*, double*, double*);
+  static const Kern table[2][2][2] = {   // [wolter][plain][alias]
+      {{fast::k_trace_mc_rays_f32<false, false, false>, fast::k_trace_mc_rays_f32<false, false, true>},
+       {fast::k_trace_mc_rays_f32<false, true, false>, fast::k_trace_mc_rays_f32<false, true, true>}},
+      {{fast::k_trace_mc_rays_f32<true, false, false>, fast::k_trace_mc_rays_f32<true, false, true>},
+       {fast::k_trace_mc_rays_f32<true, true, false>, fast::k_trace_mc_rays_f32<true, true, true>}}};
+  const Kern kern = table[wolter ? 1 : 0][plain ? 1 : 0][alias ? 1 : 0];
+  cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * 2;

@@ -27,6 +27,7 @@ void derive_shells(const sart_setup_t& s, const ShellF64* exactShells, ShellFast
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f);
 void derive_f32(const FastParams& f, const ShellFast* shells, int nShells, Geo32* g, ShellF32* out);
 bool build_shell_table(const Geo32& g, const ShellF32* shells, int nShells, int nBuckets, std::vector<ShellCell>* out);
+bool build_alias_table(const uint32_t* thr, int n, uint32_t* out /* [n] */);
 int classify_radius(const ShellF32* shells, int nShells, float rho);
 int shell_table_lookup(const Geo32& g, const std::vector<ShellCell>& tab, float rho);
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide);
@@ -52,6 +53,8 @@ struct sart_handle {
   // "fast" pipeline: parameter block, LUTs and f32 reflectivity in a second allocation
   int fast_ok = 0;
   const char* fast_why = "";
+  int sampler = 0;      // SART_SAMPLER_*
+  int alias_ok = 0;     // alias tables built (nRadii, nEnergies <= 2048)
   int f32_ok = 0;   // precision mode 2 also needs the radial shell table (derive_fast.cpp: build_shell_table)
   sart::fast::FastParams fparams;
   sart::fast::FastTables ftables;

@@ -195,6 +195,11 @@ class RayTracer:
     def set_precision(self, mode: int):
         check(lib.sart_set_precision(self._h, mode))
 
+    def set_sampler(self, sampler: int):
+        """abi.SAMPLER_INVERSE_CDF (default: the reference's lowerBound, same rays as the oracle) or abi.SAMPLER_ALIAS
+        (same distributions through alias tables: statistical parity only, precision mode 2)."""
+        check(lib.sart_set_sampler(self._h, sampler))
+
     def set_compaction(self, mode: int):
         check(lib.sart_set_compaction(self._h, mode))
 

@@ -182,3 +182,59 @@ def test_shell_lookup_table_equals_the_scan(rt, tel):
     assert set(range(n_sh)) <= set(b.tolist())
     assert (b == 64 + 7).sum() > 0 and (b == 64 + 6).sum() > 0
     assert b[-5] == 64 + 9
+
+
+def _alias_realized_counts(entries, n):
+    """Number of 32-bit words that end at each index under the kernel's lookup (k = (w n) >> 32, coin = low 32 bits of
+    w n, index k if coin < share else alias), in exact integer arithmetic."""
+    two32 = 1 << 32
+    got = [0] * n
+    t_alias = [0] * n
+    for k in range(n):
+        e = int(entries[k])
+        share, al = e & 0xFFFFF800, e & 0x7FF
+        wlo, whi = (k * two32 + n - 1) // n, ((k + 1) * two32 + n - 1) // n      # words of bucket k
+        keep = min(max((k * two32 + share + n - 1) // n - wlo, 0), whi - wlo)    # coin = w n - k 2^32 < share
+        got[k] += keep
+        got[al] += (whi - wlo) - keep
+        if al != k:
+            t_alias[al] += 1
+    return got, t_alias
+
+
+def test_alias_table_realizes_the_threshold_distribution(rt):
+    """sart_alias_table: the alias sampler draws index i for (thr[i] - thr[i-1]) of the 2^32 words, like the inverse-CDF
+    search — up to the flooring of a bucket's share to 2^-21 and one word per bucket: |words(i) - c(i)| <= (1 + number of
+    buckets whose alias is i) (2048 / n + 2), total variation below 2e-6, on a solar-model row, a one-point distribution,
+    a uniform one, n = 1 and n = 2048."""
+    from solaraxionraytracing_b200 import tables
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    em = tables.synthetic_emission(40, 1500, "abc")
+    rc_, dc = orc.build_cdfs(em.radii, em.energies, em.emRates)
+    cases = [np.ascontiguousarray(dc[7]), np.ascontiguousarray(dc[35]), np.ascontiguousarray(rc_),
+             np.concatenate([np.zeros(100), np.ones(200)]), np.arange(1, 301) / 300.0, np.array([1.0]),
+             np.sort(np.concatenate([rng.random(2047), [1.0]]))]
+    two32 = 1 << 32
+    for cdf in cases:
+        n = cdf.size
+        thr = np.zeros(n, dtype=np.uint32)
+        rt.lib.sart_cdf_thresholds(cdf.ctypes.data_as(abi.c_double_p), n, thr.ctypes.data_as(C.POINTER(C.c_uint32)))
+        ent = np.zeros(n, dtype=np.uint32)
+        rt.lib.sart_alias_table(thr.ctypes.data_as(C.POINTER(C.c_uint32)), n, ent.ctypes.data_as(C.POINTER(C.c_uint32)))
+        t = np.maximum.accumulate(thr.astype(np.int64))
+        edges = np.concatenate([[0], t[:-1], [two32]])
+        want = np.diff(edges)                                   # c(i): words the inverse-CDF search maps to i
+        assert want.sum() == two32 and (want >= 0).all()
+        got, t_alias = _alias_realized_counts(ent, n)
+        assert sum(got) == two32
+        assert all((int(e) & 0x7FF) < n for e in ent)
+        for i in range(n):
+            assert abs(got[i] - int(want[i])) <= (1 + t_alias[i]) * (2048 / n + 2), (n, i, got[i], int(want[i]))
+            if want[i] == 0:
+                assert got[i] <= t_alias[i] * 3                 # an index without words stays (all but) unreachable
+        assert sum(abs(g - int(w)) for g, w in zip(got, want)) / (2 * two32) < 2e-6
+    big = np.zeros(4096, dtype=np.uint32)                        # n > 2048: refused (entries zeroed)
+    out = np.ones(4096, dtype=np.uint32)
+    rt.lib.sart_alias_table(big.ctypes.data_as(C.POINTER(C.c_uint32)), 4096, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert not out.any()

@@ -103,12 +103,16 @@ def test_f32_counters_and_compaction(rt, cfg):
     assert abs(out[0].image.sum() / a["sum_w"] - 1.0) < 1e-9
 
 
-def test_f32_image_statistically_equal_to_oracle(rt, oracle):
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_INVERSE_CDF, abi.SAMPLER_ALIAS])
+def test_f32_image_statistically_equal_to_oracle(rt, oracle, sampler):
+    """Tier (b) for both samplers of the FP32 pipeline: the inverse-CDF search (the reference's lowerBound) and the alias
+    tables of the same distributions."""
     setup, tb = make_config("cast_llnl")
     n_gpu, n_cpu = 20_000_000, 2_000_000
     img_o, img2_o, cnt_o = oracle.trace_mc(setup, tb, 0, n_cpu, 12345)
     with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
         tr.set_precision(2)
+        tr.set_sampler(sampler)
         tr.trace_mc(n_gpu, 777)
         res = tr.read_image()
     a, va = res.image[0] / n_gpu, res.image_w2[0] / n_gpu ** 2
@@ -222,14 +226,16 @@ def _weighted_ks(a, wa, b, wb):
     return d, wa.sum() ** 2 / (wa ** 2).sum(), wb.sum() ** 2 / (wb ** 2).sum()
 
 
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_INVERSE_CDF, abi.SAMPLER_ALIAS])
 @pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
-def test_f32_ks_against_oracle(rt, oracle, cfg):
+def test_f32_ks_against_oracle(rt, oracle, cfg, sampler):
     """Tier (b), Kolmogorov-Smirnov: the weighted distributions of x, y, r and energy of the passed rays, GPU (seed A)
     against the CPU oracle (independent seed B), agree at the 0.1 % level (c(alpha) = 1.95)."""
     setup, tb = make_config(cfg)
     n_gpu, n_cpu = 3_000_000, 600_000
     with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
         tr.set_precision(2)
+        tr.set_sampler(sampler)
         g = tr.traceAxionWrapper(n_gpu, 4242)
     o = oracle.trace_mc_rays(setup, tb, 0, n_cpu, 987654321)
     pg, po = g.passed, (o.code & abi.CODE_MASK) == abi.EXIT_PASSED
@@ -303,3 +309,54 @@ def test_f32_refuses_shells_its_radial_table_cannot_resolve(rt):
     rc = rt.lib.sart_shell_lookup(C.byref(setup), 1, rho.ctypes.data_as(C.POINTER(C.c_float)),
                                   a.ctypes.data_as(C.POINTER(C.c_int32)), b.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc != 0
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_alias_sampler_draws_the_same_distributions(rt, cfg):
+    """sart_set_sampler(ALIAS) against the inverse-CDF search on the same kernels: the energies of the rays that reach the
+    mirrors (a discrete distribution over the table energies, mixed over the emission shells) in a two-sample chi^2 over
+    the atoms; the exit-code histogram (which depends on the emission radius through the ray directions) within
+    binomial errors; the images (fused kernel, with warp compaction on BabyIAXO+XMM) in the per-bin chi^2 of tier (b).
+    The two samplers map the same random words to different rays, so the two runs are independent samples."""
+    setup, tb = make_config(cfg)
+    n = 6_000_000
+    recs, imgs = {}, {}
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        for smp in (abi.SAMPLER_INVERSE_CDF, abi.SAMPLER_ALIAS):
+            tr.set_sampler(smp)
+            recs[smp] = tr.traceAxionWrapper(n, 31337)
+            tr.reset_image()
+            tr.trace_mc(4 * n, 99)
+            imgs[smp] = tr.read_image()
+        tr.set_sampler(abi.SAMPLER_ALIAS)
+        tr.set_precision(1)
+        with pytest.raises(rt.SartError, match="alias sampler"):
+            tr.trace_mc(1000, 1)
+    a, b = recs[abi.SAMPLER_INVERSE_CDF], recs[abi.SAMPLER_ALIAS]
+    assert not np.array_equal(a.code, b.code)                       # different rays ...
+    # ... same statistics. Exit codes: every code within 5 sigma (two binomial samples)
+    for code in range(16):
+        ka, kb = int(((a.code & abi.CODE_MASK) == code).sum()), int(((b.code & abi.CODE_MASK) == code).sum())
+        p = (ka + kb) / (2 * n)
+        assert abs(ka - kb) <= 5.0 * np.sqrt(2 * n * p * (1 - p)) + 1, (code, ka, kb)
+    # energies of the rays with an energy (stage B reached): chi^2 over the atoms with enough entries
+    ea, eb = a.energy[a.energy > 0].astype(np.float32), b.energy[b.energy > 0].astype(np.float32)
+    atoms = np.union1d(ea, eb)
+    ha = np.bincount(np.searchsorted(atoms, ea), minlength=atoms.size).astype(np.float64)
+    hb = np.bincount(np.searchsorted(atoms, eb), minlength=atoms.size).astype(np.float64)
+    sel = (ha + hb) >= 50
+    assert sel.sum() > 100
+    sa, sb = ha[sel].sum(), hb[sel].sum()
+    chi2 = (((ha[sel] / sa - hb[sel] / sb) ** 2) / (ha[sel] / sa ** 2 + hb[sel] / sb ** 2)).sum()
+    ndf = int(sel.sum()) - 1
+    assert abs(chi2 - ndf) / np.sqrt(2.0 * ndf) < 5.0, (chi2, ndf)
+    # images of the fused kernels
+    ia, ib = imgs[abi.SAMPLER_INVERSE_CDF], imgs[abi.SAMPLER_ALIAS]
+    m = 4 * n
+    chi2, ndf = _chi2(ia.image[0] / m, ia.image_w2[0] / m ** 2, ib.image[0] / m, ib.image_w2[0] / m ** 2)
+    assert ndf > 50
+    assert abs(chi2 - ndf) / np.sqrt(2.0 * ndf) < 5.0, (chi2, ndf)
+    ca, cb = ia.counters[0], ib.counters[0]
+    assert abs(ca["sum_w"] - cb["sum_w"]) < 5.0 * np.sqrt(ca["sum_w2"] + cb["sum_w2"])
+    assert ca["n_rays"] == cb["n_rays"] == m and sum(cb["n_exit"].values()) == m

@@ -10,6 +10,7 @@ lib = [a for a in args if a.endswith(".so")]
 if lib:
     os.environ["SART_LIB"] = lib[0]
 precs = [int(a) for a in args if a.isdigit()] or [1]
+alias = "alias" in args      # sart_set_sampler(SART_SAMPLER_ALIAS): precision 2 only
 from solaraxionraytracing_b200 import raytracer as rt, tables
 
 def probe(name, args, em, ncoat, n):
@@ -17,6 +18,7 @@ def probe(name, args, em, ncoat, n):
     with rt.RayTracer(fs) as tr:
       for prec in precs:
         tr.set_precision(prec)
+        tr.set_sampler(1 if alias and prec == 2 else 0)
         tr.trace_mc(n // 10, 1); tr.synchronize()
         best = 1e9
         for _ in range(3):
@@ -27,7 +29,7 @@ def probe(name, args, em, ncoat, n):
         h = hashlib.sha1(json.dumps(c["n_exit"], sort_keys=True).encode()).hexdigest()[:10]
         if len(precs) > 1:
             print("   ", {k: v for k, v in c["n_exit"].items() if v})
-        print(f"{name} prec {prec}: {n/best:.4e} rays/s ({best*1e3:.2f} ms)  exit-hash {h} passed {c['n_passed']} till_window {c['n_passed_till_window']} "
+        print(f"{name} prec {prec}{' alias' if alias and prec == 2 else ''}: {n/best:.4e} rays/s ({best*1e3:.2f} ms)  exit-hash {h} passed {c['n_passed']} till_window {c['n_passed_till_window']} "
               f"sum_w {c['sum_w']:.12e} img {r.image.sum():.12e}", flush=True)
 
 em_abc = tables.synthetic_emission(1968, 1500, "abc"); em_prim = tables.synthetic_emission(1968, 1500, "primakoff")
