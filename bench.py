@@ -323,14 +323,14 @@ def records_leg(tr, torch, n: int = 1 << 24, reps: int = 3):
     ro = abi.RayOut()
     ro.x, ro.y, ro.w = (C.cast(t.data_ptr(), abi.c_double_p) for t in (hx, hy, hw))
     ro.code, ro.shell = (C.cast(t.data_ptr(), abi.c_int32_p) for t in (hc, hs))
-    tr.set_precision(1)
+    tr.set_precision(2)
     call = lambda k: check(lib.sart_trace_mc_rays(tr._h, k * n, n, SEED, C.byref(ro)))
     call(0)
     t0 = time.perf_counter()
     for k in range(reps):
         call(1 + k)
     dt = (time.perf_counter() - t0) / reps
-    return {"api": "sart_trace_mc_rays (traceAxionWrapper, per-ray records to host)", "rays_per_call": n,
+    return {"api": "sart_trace_mc_rays (traceAxionWrapper, per-ray records to host)", "precision": "f32", "rays_per_call": n,
             "value": n / dt, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32 * n,
             "d2h_GBps": 32 * n / dt / 1e9, "passed_fraction": float((hc.bitwise_and(0xff) == 0).double().mean())}
 
