@@ -450,6 +450,7 @@ void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {
 // of a process whose first trace launch followed a 256 MB memset, and at 20.0 ms when a small launch had come first.
 static int warm_f32(sart_handle* h) {
   if (!h->fast_ok || !h->f32_ok || h->setup.testSource.active) return SART_OK;
+  if (h->params.nRadii < 1 || h->params.nEnergies < 1 || !h->ftables.radiusThr || !h->ftables.energyThr) return SART_OK;   // no solar table: nothing to sample
   const int precision = h->precision, sampler = h->ftables.sampler;
   h->precision = 2;
   int rc = SART_OK;
