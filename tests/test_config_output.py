@@ -145,6 +145,15 @@ def test_run_table_is_an_optional_superset(tmp_path):
     p.write_text(config.DEFAULT_CONFIG.read_text() + '\n[Run]\nprecision = "fp8"\n')
     with pytest.raises(ValueError):
         config.parseRun(config.load_config(p))
+    # the sampler: the reference's inverse CDF unless asked otherwise
+    assert r.sampler == "inverse_cdf"
+    p.write_text(config.DEFAULT_CONFIG.read_text() + '\n[Run]\nsampler = "alias"\n')
+    assert config.parseRun(config.load_config(p)).sampler == "alias"
+    p.write_text(config.DEFAULT_CONFIG.read_text() + '\n[Run]\nsampler = "sobol"\n')
+    with pytest.raises(ValueError):
+        config.parseRun(config.load_config(p))
+    from solaraxionraytracing_b200.__main__ import build_parser
+    assert build_parser().parse_args([]).sampler is None and build_parser().parse_args(["--sampler", "alias"]).sampler == "alias"
 
 
 def test_h5_reflectivity_reader_fails_clearly_without_h5py(tmp_path):
