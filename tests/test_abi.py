@@ -238,3 +238,15 @@ def test_alias_table_realizes_the_threshold_distribution(rt):
     out = np.ones(4096, dtype=np.uint32)
     rt.lib.sart_alias_table(big.ctypes.data_as(C.POINTER(C.c_uint32)), 4096, out.ctypes.data_as(C.POINTER(C.c_uint32)))
     assert not out.any()
+
+
+def test_shell_lookup_refuses_unresolvable_shells(rt):
+    """A glass 1e-5 mm thick puts two boundaries into one bucket of the (at most 4000-bucket) radial table: the helper
+    reports it instead of building a wrong table (the FP32 pipeline then refuses the setup, modes 1 and 0 trace it)."""
+    setup = rt.newExperimentSetup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
+    setup.telescope.allThickness[3] = 1e-5
+    rho = np.array([70.0], dtype=np.float32)
+    a = np.zeros(1, dtype=np.int32); b = np.zeros(1, dtype=np.int32)
+    rc = rt.lib.sart_shell_lookup(C.byref(setup), 1, rho.ctypes.data_as(C.POINTER(C.c_float)),
+                                  a.ctypes.data_as(C.POINTER(C.c_int32)), b.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc != 0 and b"radial lookup table" in rt.lib.sart_last_error()
