@@ -75,6 +75,13 @@ def workload_tables_cpu(orc, tables):
 WORKLOAD = "CAST+LLNL vacuum, InGrid2018 window+Ar chain, solar table 1968x1500, reflectivity 4x1000x1000"
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def cpu_leg(seconds: float, threads: int | None = None):
     """Times the restated CPU oracle (the reference's algorithm; the Nim binary cannot be built in this image) on
     a bounded sample of the same workload. Returns (rays/s, cores, sample description)."""
@@ -82,7 +89,8 @@ def cpu_leg(seconds: float, threads: int | None = None):
     from oracle import ref_setup
     from solaraxionraytracing_b200 import abi, tables
     orc.lib()
-    cores = threads or orc.lib().oracle_num_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: ask for the host's cores explicitly
+    cores = threads or host_cores()
     orc.lib().oracle_set_num_threads(cores)
     setup = ref_setup.make_setup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
     tb = workload_tables_cpu(orc, tables)
@@ -94,7 +102,33 @@ def cpu_leg(seconds: float, threads: int | None = None):
     t0 = time.perf_counter()
     _, _, cnt = orc.trace_mc(setup, tb, n0, n, SEED)
     dt = time.perf_counter() - t0
-    return n / dt, cores, f"{n} rays of the same workload, OpenMP {cores} threads, {dt:.1f} s", cnt[0]
+    return n / dt, cores, f"{n} rays of the same workload, OpenMP {cores} threads, {dt:.1f} s", cnt[0], n0, n
+
+
+def parity_leg(tr, first: int, n: int, cnt_cpu: dict | None = None):
+    """bench.py checks what it times: the fused kernel on the global rays [first, first + n) of the workload against the
+    CPU oracle on the very same rays (Philox is keyed on the global ray index): exit-code histogram within n/5000 per
+    code, total flux within 1e-3. `cnt_cpu`: the oracle's counters if the cpu_baseline leg already traced that range."""
+    if cnt_cpu is None:
+        from oracle import oracle as orc
+        from oracle import ref_setup
+        from solaraxionraytracing_b200 import abi, tables
+        orc.lib().oracle_set_num_threads(host_cores())
+        setup = ref_setup.make_setup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
+        cnt_cpu = orc.trace_mc(setup, workload_tables_cpu(orc, tables), first, n, SEED)[2][0]
+    tr.reset_image()
+    tr.trace_mc(n, SEED, first_ray=first)
+    cg = tr.read_image().counters[0]
+    tr.reset_image()
+    diff = {k: cg["n_exit"][k] - v for k, v in cnt_cpu["n_exit"].items()}
+    tol = max(1, n // 5000)
+    flux = abs(cg["sum_w"] / cnt_cpu["sum_w"] - 1.0) if cnt_cpu["sum_w"] else None
+    ok = cg["n_rays"] == cnt_cpu["n_rays"] == n and all(abs(d) <= tol for d in diff.values()) and (flux is None or flux < 1e-3)
+    return {"ok": bool(ok), "rays": n, "first_ray": first, "tolerance_per_code": tol,
+            "exit_code_diff_gpu_minus_cpu": {k: d for k, d in diff.items() if d}, "max_abs_diff": max(abs(d) for d in diff.values()),
+            "sum_w_rel_diff": flux, "passed_gpu": cg["n_passed"], "passed_cpu": cnt_cpu["n_passed"],
+            "retraced_fp64": cg.get("n_retraced"), "unresolved": cg.get("n_unresolved"),
+            "against": "restated CPU oracle on the same Philox rays (not the Nim executable)"}
 
 
 def run_reference(args):
@@ -107,6 +141,10 @@ def run_reference(args):
     from oracle import ref_setup
     from solaraxionraytracing_b200 import abi, tables
     orc.lib()
+    # all the host threads the box has: under torchrun (N > 1) every rank inherits OMP_NUM_THREADS=1, which would time
+    # the CPU arm on one core
+    cores = host_cores()
+    orc.lib().oracle_set_num_threads(cores)
     cores = orc.lib().oracle_num_threads()
     setup = ref_setup.make_setup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
     tb = workload_tables_cpu(orc, tables)
@@ -491,13 +529,20 @@ def run_ours(args):
         if n_gpus == 1 and not args.no_presampled:
             out["presampled"] = presampled_leg(tr, torch, local)
             out["e2e_records"] = records_leg(tr, torch)
+        tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[precision])
         if n_gpus == 1 and not args.no_cpu_baseline:
-            v, cores, sample, _ = cpu_leg(args.cpu_seconds)
+            v, cores, sample, cnt_cpu, n0, n_cpu = cpu_leg(args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                                    "sample": sample + " (restated oracle, not the Nim executable)"}
-            v1, _, sample1, _ = cpu_leg(min(args.cpu_seconds, 3.0), threads=1)   # 1 thread next to all threads
+            v1, _, sample1, _, _, _ = cpu_leg(min(args.cpu_seconds, 3.0), threads=1)   # 1 thread next to all threads
             out["cpu_baseline"]["one_thread"] = {"value": v1, "unit": "rays/s", "cores": 1, "sample": sample1}
+            out["parity_check"] = parity_leg(tr, n0, n_cpu, cnt_cpu)
+        else:
+            out["parity_check"] = parity_leg(tr, 0, 1_000_000)
         print(json.dumps(out), flush=True)
+        if not out["parity_check"]["ok"]:
+            tr.close()
+            raise SystemExit("bench.py: the timed kernel disagrees with the CPU oracle on the same rays: %r" % (out["parity_check"],))
     tr.close()
     if dist is not None:
         dist.barrier()

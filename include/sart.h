@@ -294,6 +294,15 @@ int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin
  * streams or GPUs traces the same rays. */
 int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t seed, const sart_ray_out_t* out);
 
+/* ---- test hook: sart_trace_mc_rays with the six random words of every ray supplied by the caller (SoA [6][n]: phi_sun,
+ * theta_sun, radius, disc r, disc phi, energy; uniform = (word + 0.5) 2^-32) instead of drawn from Philox, so that tests
+ * can drive the integer inverse-CDF search (rt:437, 464) through its corners — word 0, word 0xffffffff, the words on
+ * either side of every CDF entry, flat CDF tails. Precision modes 0 and 2, solar source. late_energy != 0 (mode 2)
+ * resolves the energy after the clip stages, the way the compacting fused kernel does; 0 inside them, like the plain one.
+ * out->energy is filled for every ray, clipped or not (energiesPre, rt:1818-1819). */
+int sart_trace_words(sart_handle_t* h, size_t n, const uint32_t* words, int late_energy, const sart_ray_out_t* out,
+                     int32_t* emission_shell /* optional [n]: the radius index rt:437 of every ray */);
+
 /* ---- fused run: sample + trace + prepareHeatmap (rt:818-842, 256x256 over the 14x14 mm chip, norm = 1).
  * Accumulates (+=) into the handle's device-resident image/counters; asynchronous. With M axion masses set
  * (sart_set_axion_masses) the image is [M][256][256]. In precision modes 1 and 2 the kernel adds into internal replicas

@@ -868,12 +868,52 @@ int oracle_trace_mc_rays(const sart_setup_t* s, const sart_tables_t* tb, uint64_
 int oracle_sample_rays(const sart_setup_t* s, const sart_tables_t* tb, uint64_t first_ray, size_t n, uint64_t seed,
                        double* origin_xyz, double* exit_xy, double* energy) {
   centers_t cv = initCenterVectors(s);
-  for (size_t i = 0; i < n; ++i) {
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) {
     double u[6]; v3 o, e; double en; int clamped = 0;
-    oracle_ray_uniforms(seed, first_ray + i, u);
+    oracle_ray_uniforms(seed, first_ray + (uint64_t)i, u);
     sample_solar(s, tb, &cv, u, &o, &e, &en, &clamped);
     origin_xyz[i] = o.x; origin_xyz[n + i] = o.y; origin_xyz[2 * n + i] = o.z;
     exit_xy[i] = e.x; exit_xy[n + i] = e.y; energy[i] = en;
+  }
+  return 0;
+}
+
+/* The same two entry points driven by caller-supplied random words instead of Philox (words = SoA [6][n] in the draw
+ * order of oracle_ray_uniforms; u = (word + 0.5) 2^-32): lets tests reach the corners of the inverse-CDF sampling
+ * (rt:437, 464) — the words 0 and 0xffffffff, words on either side of every CDF entry, flat CDF tails — that random
+ * rays reach once in 2^32 draws. Solar source only. */
+static void words_to_uniforms(const uint32_t* words, size_t n, size_t i, double u[6]) {
+  const double sc = 1.0 / 4294967296.0;
+  for (int k = 0; k < 6; ++k) u[k] = ((double)words[(size_t)k * n + i] + 0.5) * sc;
+}
+int oracle_sample_words(const sart_setup_t* s, const sart_tables_t* tb, size_t n, const uint32_t* words,
+                        double* origin_xyz, double* exit_xy, double* energy) {
+  if (s->testSource.active) return -1;
+  centers_t cv = initCenterVectors(s);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) {
+    double u[6]; v3 o, e; double en; int clamped = 0;
+    words_to_uniforms(words, n, (size_t)i, u);
+    sample_solar(s, tb, &cv, u, &o, &e, &en, &clamped);
+    origin_xyz[i] = o.x; origin_xyz[n + i] = o.y; origin_xyz[2 * n + i] = o.z;
+    exit_xy[i] = e.x; exit_xy[n + i] = e.y; energy[i] = en;
+  }
+  return 0;
+}
+int oracle_trace_words(const sart_setup_t* s, const sart_tables_t* tb, size_t n, const uint32_t* words,
+                       const sart_ray_out_t* out) {
+  if (s->testSource.active) return -1;
+  centers_t cv = initCenterVectors(s);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (long long i = 0; i < (long long)n; ++i) {
+    double u[6]; v3 o, e; double en; int clamped = 0;
+    axion_t a;
+    words_to_uniforms(words, n, (size_t)i, u);
+    sample_solar(s, tb, &cv, u, &o, &e, &en, &clamped);
+    trace_after_sampling(&a, s, tb, &cv, s->consts.mAxion, o, e, en, 0);
+    a.clamped |= clamped;
+    store(out, (size_t)i, &a);
   }
   return 0;
 }

@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
             "oracle_trace_presampled": (C.c_int, [S, T, C.c_size_t, dp, dp, dp, R]),
             "oracle_trace_mc_rays": (C.c_int, [S, T, C.c_uint64, C.c_size_t, C.c_uint64, R]),
             "oracle_sample_rays": (C.c_int, [S, T, C.c_uint64, C.c_size_t, C.c_uint64, dp, dp, dp]),
+            "oracle_sample_words": (C.c_int, [S, T, C.c_size_t, C.POINTER(C.c_uint32), dp, dp, dp]),
+            "oracle_trace_words": (C.c_int, [S, T, C.c_size_t, C.POINTER(C.c_uint32), R]),
             "oracle_trace_mc": (C.c_int, [S, T, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, dp, dp, dp,
                                           C.POINTER(abi.Counters)]),
             "oracle_prepare_heatmap": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -80,8 +82,9 @@ class RayBatch:
         self.n = n
         self.x = np.zeros(n); self.y = np.zeros(n); self.w = np.zeros(n)
         self.code = np.zeros(n, dtype=np.int32); self.shell = np.zeros(n, dtype=np.int32)
-        for name in abi.RAY_OUT_OPTIONAL:
-            setattr(self, name, np.zeros(n) if optional else None)
+        for name in abi.RAY_OUT_OPTIONAL:   # optional: True / False, or the names of the optional arrays wanted
+            want = (name in optional) if isinstance(optional, (tuple, list, set)) else bool(optional)
+            setattr(self, name, np.zeros(n) if want else None)
 
     def c_struct(self) -> abi.RayOut:
         o = abi.RayOut()
@@ -132,6 +135,36 @@ def sample_rays(setup: abi.Setup, tables, first_ray: int, n: int, seed: int):
     t = tables.c_struct()
     lib().oracle_sample_rays(C.byref(setup), C.byref(t), first_ray, n, seed, _dp(origin), _dp(exit_xy), _dp(energy))
     return origin, exit_xy, energy
+
+
+def _words(words) -> np.ndarray:
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    if w.ndim != 2 or w.shape[0] != 6:
+        raise ValueError("words must be [6, n] (phi_sun, theta_sun, radius, disc r, disc phi, energy)")
+    return w
+
+
+def sample_words(setup: abi.Setup, tables, words):
+    """Emission point, exit-disc point and energy for caller-supplied random words [6, n] (u = (w + 0.5) 2^-32)."""
+    w = _words(words)
+    n = w.shape[1]
+    origin = np.empty((3, n)); exit_xy = np.empty((2, n)); energy = np.empty(n)
+    t = tables.c_struct()
+    rc = lib().oracle_sample_words(C.byref(setup), C.byref(t), n, w.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(origin),
+                                   _dp(exit_xy), _dp(energy))
+    assert rc == 0
+    return origin, exit_xy, energy
+
+
+def trace_words(setup: abi.Setup, tables, words, optional=True) -> RayBatch:
+    """oracle_trace_mc_rays with the six random words of every ray supplied by the caller instead of Philox."""
+    w = _words(words)
+    n = w.shape[1]
+    out = RayBatch(n, optional)
+    o = out.c_struct(); t = tables.c_struct()
+    rc = lib().oracle_trace_words(C.byref(setup), C.byref(t), n, w.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(o))
+    assert rc == 0
+    return out
 
 
 def trace_mc(setup: abi.Setup, tables, first_ray: int, n_rays: int, seed: int, masses=None):

@@ -181,6 +181,7 @@ SIGNATURES = {
     "sart_trace_presampled": (C.c_int, [H, C.c_size_t, c_double_p, c_double_p, c_double_p, C.POINTER(RayOut)]),
     "sart_trace_presampled_dev": (C.c_int, [H, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RayOut)]),
     "sart_trace_mc_rays": (C.c_int, [H, C.c_uint64, C.c_size_t, C.c_uint64, C.POINTER(RayOut)]),
+    "sart_trace_words": (C.c_int, [H, C.c_size_t, C.POINTER(C.c_uint32), C.c_int, C.POINTER(RayOut), c_int32_p]),
     "sart_trace_mc": (C.c_int, [H, C.c_uint64, C.c_uint64, C.c_uint64]),
     "sart_reset_image": (C.c_int, [H]),
     "sart_enable_radial_hist": (C.c_int, [H, C.c_int, C.c_double]),

@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False, defines: list[str] | None 
                                                                     Path(__file__)]
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
-    objs = []
+    objs, cmds = [], []
     for src, extra in UNITS:
         s = CSRC / src
         o = objdir / (src + ".o")
@@ -60,7 +60,14 @@ def build(force: bool = False, verbose: bool = False, defines: list[str] | None 
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
+            cmds.append(cmd)
+    if cmds:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            for r in ex.map(lambda c: subprocess.run(c, check=False, capture_output=not verbose, text=True), cmds):
+                if r.returncode != 0:
+                    sys.stderr.write((r.stdout or "") + (r.stderr or ""))
+                    raise subprocess.CalledProcessError(r.returncode, r.args)
     if force or _stale(LIB, objs):
         cmd = [NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(LIB), *map(str, objs)]
         if verbose:

@@ -163,6 +163,29 @@ static int upload_tables(sart_handle* h, const sart_tables_t* t) {
     }
   T.shells = reinterpret_cast<const ShellF64*>(base + oSh);
   h->shell_offset = oSh;
+  h->have_solar = solar ? 1 : 0;
+  h->n_refl_coatings = refl ? t->nCoatings : 0;
+  h->have_tel_transmission = (I[3]->n >= 2 && I[3]->x && I[3]->y) ? 1 : 0;
+  return SART_OK;
+}
+
+// sart_update_setup may only move to setups the tables uploaded at sart_create cover (validate() checked them against
+// the setup of that moment only).
+static int validate_update(const sart_handle* h, const sart_setup_t* s) {
+  int rc = validate(s, nullptr);
+  if (rc) return rc;
+  if (!s->testSource.active && !h->have_solar)
+    return fail(SART_ERR_ARG, "sart_update_setup: the solar source needs the solar model tables, and this handle was created without them");
+  if (!(s->flags & SART_CF_IGNORE_REFLECTION)) {
+    if (s->telescope.reflKind == SART_RK_EFFECTIVE_AREA) {
+      if (!h->have_tel_transmission)
+        return fail(SART_ERR_ARG, "sart_update_setup: rkEffectiveArea needs the telescopeTransmission table, and this handle was created without it");
+    } else {
+      const int need = s->telescope.reflKind == SART_RK_MULTI_COATING ? s->telescope.nCoatings : 1;
+      if (h->n_refl_coatings < need)
+        return fail(SART_ERR_ARG, "sart_update_setup: the setup needs %d reflectivity coatings, the handle holds %d", need, h->n_refl_coatings);
+    }
+  }
   return SART_OK;
 }
 
@@ -172,9 +195,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   h->fast_ok = fast::supported(h->setup, &why) ? 1 : 0;
   h->fast_why = why;
   h->f32_ok = 0;
-  if (!h->fast_ok) return SART_OK;
   const Params& P = h->params;
-  if (t) {
+  if (t) {   // host copies for later LUT rebuilds, kept whether or not this setup can use the throughput pipelines
     h->h_energies.assign(t->energies ? t->energies : nullptr, t->energies ? t->energies + t->nEnergies : nullptr);
     const sart_interp1d_t* I[3] = {&t->strongbackTransmission, &t->windowTransmission, &t->gasAbsorption};
     for (int k = 0; k < 3; ++k) {
@@ -184,6 +206,14 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     const size_t nRefl = t->reflectivity ? size_t(t->nCoatings) * t->nAngles * t->nReflEnergies : 0;
     h->h_refl32.resize(nRefl);
     for (size_t i = 0; i < nRefl; ++i) h->h_refl32[i] = float(t->reflectivity[i]);
+  }
+  if (!h->fast_ok) return SART_OK;
+  if (!t && !h->fast_blob) {
+    // the derived sampling tables (thresholds, guides, reflectivity rows) are built from the caller's tables at
+    // sart_create only; a handle created with a setup the throughput pipelines do not support never got them
+    h->fast_ok = 0;
+    h->fast_why = "the handle was created with a setup the throughput pipelines do not support; create a new handle for this setup";
+    return SART_OK;
   }
   sart_interp1d_t I[3];
   for (int k = 0; k < 3; ++k) I[k] = sart_interp1d_t{int32_t(h->h_tab[k][0].size()), 0, h->h_tab[k][0].data(), h->h_tab[k][1].data()};
@@ -316,7 +346,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
 static int ensure_image(sart_handle* h, int nMasses) {
   const size_t len = size_t(nMasses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
   if (h->d_image && h->image_masses == nMasses) return SART_OK;
-  if (h->d_image) { cudaFree(h->d_image); cudaFree(h->d_image_w2); cudaFree(h->d_counters); h->d_image = nullptr; }
+  cudaFree(h->d_image); cudaFree(h->d_image_w2); cudaFree(h->d_counters);
+  h->d_image = nullptr; h->d_image_w2 = nullptr; h->d_counters = nullptr; h->image_masses = 0;
   SART_CUDA(cudaMalloc(&h->d_image, len * sizeof(double)));
   SART_CUDA(cudaMalloc(&h->d_image_w2, len * sizeof(double)));
   SART_CUDA(cudaMalloc(&h->d_counters, size_t(nMasses) * sizeof(sart_counters_t)));
@@ -335,8 +366,10 @@ static int ensure_replicas(sart_handle* h) {
   int n = 8;   // measured on B200, CAST+LLNL, 1e9 rays: 1 replica 43.8 ms, 4 / 16 / 64 replicas 36.1 ms
   if (const char* e = std::getenv("SART_IMG_REPLICAS")) n = std::max(1, std::min(256, std::atoi(e)));
   h->n_rep = n;
+  h->rep_stride = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS;
+  if (const char* e = std::getenv("SART_IMG_REP_SKEW")) h->rep_stride += size_t(std::max(0, std::atoi(e)));   // experiment: replicas not 512 KiB apart
   if (n > 1) {
-    const size_t bytes = size_t(2) * n * SART_IMAGE_BINS * SART_IMAGE_BINS * sizeof(double);
+    const size_t bytes = size_t(2) * n * h->rep_stride * sizeof(double);
     SART_CUDA(cudaMalloc(&h->d_rep, bytes));
     SART_CUDA(cudaMemsetAsync(h->d_rep, 0, bytes, h->stream));
   }
@@ -514,12 +547,10 @@ void sart_destroy(sart_handle_t* h) {
   delete h;
 }
 
-int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
-  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
-  int rc = validate(setup, nullptr);
-  if (rc) return rc;
-  DeviceGuard dg(h->device);
-  h->setup = *setup;
+// The setup-dependent part of a handle: sart_update_setup applies a new setup to it and puts the old one back (host state
+// and the device-side records derived from it) if any step fails, so a failed update leaves the handle as it was.
+static int apply_setup(sart_handle* h, const sart_setup_t& s, bool retune) {
+  h->setup = s;
   rederive_params(h, h->setup, &h->params);
   std::vector<ShellF64> shells(SART_MAX_SHELLS);
   derive_shells(h->setup, shells.data());
@@ -527,10 +558,37 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
   SART_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(h->table_blob) + h->shell_offset, shells.data(),
                             shells.size() * sizeof(ShellF64), cudaMemcpyHostToDevice, h->stream));
   SART_CUDA(cudaStreamSynchronize(h->stream));
-  if ((rc = upload_fast(h, nullptr))) return rc;
+  int rc = upload_fast(h, nullptr);
+  if (rc) return rc;
   if (h->precision >= 1 && !h->fast_ok) h->precision = 0;
   if (h->precision == 2 && !h->f32_ok) h->precision = 1;
-  if ((rc = autotune(h))) return rc;
+  if (retune && !h->compact_user) rc = autotune(h);
+  return rc;
+}
+
+int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  int rc = validate_update(h, setup);
+  if (rc) return rc;
+  DeviceGuard dg(h->device);
+  const sart_setup_t old = h->setup;
+  const int oldPrecision = h->precision, oldCompact = h->compact;
+  const double oldSurvival = h->pilot_survival;
+  // the pilot run that chooses the kernel variant measures how many rays the bore, pipes and entrance structures remove:
+  // repeat it only when that geometry changes (not for every step of an angle or detector-position scan)
+  const bool retune = std::memcmp(&old.magnet, &setup->magnet, sizeof old.magnet) != 0 ||
+                      std::memcmp(&old.pipes, &setup->pipes, sizeof old.pipes) != 0 ||
+                      old.telescope.kind != setup->telescope.kind || old.telescope.nShells != setup->telescope.nShells ||
+                      old.testSource.active != setup->testSource.active || old.experiment != setup->experiment;
+  rc = apply_setup(h, *setup, retune);
+  if (rc) {
+    char msg[sizeof g_err];
+    std::snprintf(msg, sizeof msg, "%s", g_err);
+    h->precision = oldPrecision;
+    apply_setup(h, old, false);   // best effort: the old setup was valid for this handle
+    h->precision = oldPrecision; h->compact = oldCompact; h->pilot_survival = oldSurvival;
+    return fail(rc, "sart_update_setup failed, previous setup kept: %s", msg);
+  }
   if (h->n_masses == 1 && h->masses_default) {
     h->masses[0] = setup->consts.mAxion;
     SART_CUDA(cudaMemcpyAsync(h->d_masses, h->masses, sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -544,12 +602,16 @@ int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV) {
   if (n < 1 || n > SART_MAX_MASSES || !masses_eV) return fail(SART_ERR_ARG, "sart_set_axion_masses: need 1..%d masses", SART_MAX_MASSES);
   DeviceGuard dg(h->device);
   SART_CUDA(cudaStreamSynchronize(h->stream));
+  int rc = ensure_image(h, n);
+  if (rc) {   // the old buffers are gone: fall back to a state every entry point can work with
+    h->n_masses = 1;
+    if (ensure_image(h, 1) != SART_OK) h->n_masses = 0;
+    return rc;
+  }
   std::memcpy(h->masses, masses_eV, n * sizeof(double));
   h->n_masses = n;
   h->masses_default = 0;
   SART_CUDA(cudaMemcpyAsync(h->d_masses, h->masses, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  int rc = ensure_image(h, n);
-  if (rc) return rc;
   SART_CUDA(cudaStreamSynchronize(h->stream));
   return SART_OK;
 }
@@ -586,6 +648,7 @@ int sart_set_compaction(sart_handle_t* h, int mode) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   if (mode < 0 || mode > 1) return fail(SART_ERR_ARG, "compaction mode must be 0 or 1");
   h->compact = mode;
+  h->compact_user = 1;   // an explicit choice survives sart_update_setup
   return SART_OK;
 }
 
@@ -818,8 +881,41 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
   return copy_out(h, n, *out, dev);
 }
 
+int sart_trace_words(sart_handle_t* h, size_t n, const uint32_t* words, int late_energy, const sart_ray_out_t* out,
+                     int32_t* emission_shell) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  int rc = check_out(out);
+  if (rc) return rc;
+  if (n == 0) return SART_OK;
+  if (!words) return fail(SART_ERR_ARG, "sart_trace_words: words is NULL");
+  if (h->precision == 1) return fail(SART_ERR_CONFIG, "sart_trace_words: precision mode 0 or 2 (mode 1 runs the same integer search code as mode 2)");
+  if (h->setup.testSource.active) return fail(SART_ERR_CONFIG, "sart_trace_words: solar source only");
+  if (late_energy && h->precision != 2) return fail(SART_ERR_CONFIG, "sart_trace_words: late_energy is a variant of precision mode 2");
+  DeviceGuard dg(h->device);
+  sart_ray_out_t probe;
+  const size_t outBytes = carve_out(nullptr, n, *out, &probe);
+  const size_t wBytes = align256(6 * n * sizeof(uint32_t)), eBytes = align256(n * sizeof(int32_t));
+  if ((rc = ensure_stage(h, outBytes + wBytes + eBytes))) return rc;
+  unsigned char* base = static_cast<unsigned char*>(h->d_stage);
+  sart_ray_out_t dev;
+  carve_out(base, n, *out, &dev);
+  uint32_t* dW = reinterpret_cast<uint32_t*>(base + outBytes);
+  int32_t* dEmit = emission_shell ? reinterpret_cast<int32_t*>(base + outBytes + wBytes) : nullptr;
+  SART_CUDA(cudaMemcpyAsync(dW, words, 6 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  if (h->precision == 2) {
+    SART_CUDA(cudaMemsetAsync(base, 0, outBytes, h->stream));
+    SART_CUDA(launch_mc_rays_f32(h->fparams, h->geo32, h->ftables, h->masses[0], 0, n, 0, dev, h->sm_count, h->stream, dW,
+                                 late_energy != 0, dEmit));
+  } else {
+    SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], 0, n, 0, dev, h->stream, dW, dEmit));
+  }
+  if (dEmit) SART_CUDA(cudaMemcpyAsync(emission_shell, dEmit, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  return copy_out(h, n, *out, dev);
+}
+
 int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_t seed) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (!h->d_image) return fail(SART_ERR_NOMEM, "the image buffers of this handle could not be allocated");
   DeviceGuard dg(h->device);
   if (h->sampler == SART_SAMPLER_ALIAS && (h->precision != 2 || h->n_masses > 1))
     return fail(SART_ERR_CONFIG, "the alias sampler needs precision mode 2 and a single axion mass");
@@ -846,8 +942,8 @@ int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_
     fast::FastTables ft = h->ftables;
     double *img = h->d_image, *img2 = h->d_image_w2;
     if (h->n_rep > 1) {
-      ft.nImgRep = h->n_rep; ft.imgRepStride = plane;
-      img = h->d_rep; img2 = h->d_rep + size_t(h->n_rep) * plane;
+      ft.nImgRep = h->n_rep; ft.imgRepStride = h->rep_stride;
+      img = h->d_rep; img2 = h->d_rep + size_t(h->n_rep) * h->rep_stride;
     }
     if (h->precision == 2)
       SART_CUDA(launch_mc_image_f32(h->fparams, h->geo32, ft, h->masses[0], first_ray, n_rays, seed, img, img2,
@@ -856,7 +952,7 @@ int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_
       SART_CUDA(launch_mc_image_fast(h->fparams, ft, h->masses[0], first_ray, n_rays, seed, img, img2, h->d_counters,
                                      h->sm_count, h->compact != 0, h->stream));
     if (h->n_rep > 1)
-      SART_CUDA(launch_fold_replicas(img, img2, h->n_rep, plane, plane, h->d_image, h->d_image_w2, h->stream));
+      SART_CUDA(launch_fold_replicas(img, img2, h->n_rep, h->rep_stride, plane, h->d_image, h->d_image_w2, h->stream));
     return SART_OK;
   }
   SART_CUDA(launch_mc_image_exact(h->params, h->tables, h->n_masses, h->d_masses, first_ray, n_rays, seed, h->d_image,

@@ -13,7 +13,8 @@ cudaError_t launch_presampled_exact(const Params& P, const Tables& T, double mAx
                                     const double* exitxy, const double* energy, const sart_ray_out_t& out,
                                     cudaStream_t s);
 cudaError_t launch_mc_rays_exact(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n,
-                                 uint64_t seed, const sart_ray_out_t& out, cudaStream_t s);
+                                 uint64_t seed, const sart_ray_out_t& out, cudaStream_t s, const uint32_t* words = nullptr,
+                                 int32_t* emit = nullptr);
 cudaError_t launch_mc_image_exact(const Params& P, const Tables& T, int nMasses, const double* masses, uint64_t first,
                                   uint64_t nRays, uint64_t seed, double* image, double* imageW2,
                                   sart_counters_t* counters, int smCount, cudaStream_t s);
@@ -46,7 +47,8 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
                                   const sart_ray_out_t& o, int smCount, cudaStream_t s);
 cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
                                uint64_t first, uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount,
-                               cudaStream_t s);
+                               cudaStream_t s, const uint32_t* words = nullptr, bool lateEnergy = false,
+                               int32_t* emit = nullptr);
 cudaError_t launch_fold_replicas(double* rep, double* rep2, int nRep, size_t stride, size_t plane, double* image,
                                  double* imageW2, cudaStream_t s);
 cudaError_t launch_fold_mass_acc(double* acc, double* acc2, int nMasses, size_t plane, double* image, double* imageW2,

@@ -69,13 +69,21 @@ k_trace_presampled(const __grid_constant__ Params P, const __grid_constant__ Tab
 
 __global__ void __launch_bounds__(128)
 k_trace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, uint64_t first,
-                size_t n, uint64_t seed, const __grid_constant__ RayOutDev out) {
+                size_t n, uint64_t seed, const uint32_t* __restrict__ words, int32_t* __restrict__ emit,
+                const __grid_constant__ RayOutDev out) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   V3 O, E;
   double energy;
   int clamped = 0;
-  if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped)) {
+  uint32_t w[6];
+  if (words) {   // sart_trace_words: caller-supplied random words, SoA [6][n]
+    for (int k = 0; k < 6; ++k) w[k] = words[size_t(k) * n + i];
+  } else {
+    ray_words(seed, first + i, w);
+  }
+  if (emit) emit[i] = P.testXray ? 0 : min(lower_bound(T.fluxRadiusCDF, 0, P.nRadii, u01(w[2])), P.nRadii - 1);   // rIdx rt:437
+  if (!sample_ray_words(P, T, w, O, E, energy, clamped)) {
     out.x[i] = 0.0; out.y[i] = 0.0; out.w[i] = 0.0; out.code[i] = SART_EXIT_COLLIMATOR; out.shell[i] = -1;
     if (out.energy) out.energy[i] = energy;
     if (out.reflect) out.reflect[i] = 0.0;
@@ -262,11 +270,11 @@ cudaError_t launch_presampled_exact(const Params& P, const Tables& T, double mAx
 }
 
 cudaError_t launch_mc_rays_exact(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n,
-                                 uint64_t seed, const sart_ray_out_t& out, cudaStream_t s) {
+                                 uint64_t seed, const sart_ray_out_t& out, cudaStream_t s, const uint32_t* words, int32_t* emit) {
   if (n == 0) return cudaSuccess;
   const int block = 128;
   const unsigned grid = unsigned((n + block - 1) / block);
-  k_trace_mc_rays<<<grid, block, 0, s>>>(P, T, mAxion, first, n, seed, to_dev(out));
+  k_trace_mc_rays<<<grid, block, 0, s>>>(P, T, mAxion, first, n, seed, words, emit, to_dev(out));
   return cudaGetLastError();
 }
 

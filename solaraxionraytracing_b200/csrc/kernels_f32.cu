@@ -206,10 +206,9 @@ struct Head32 {
 // kPlain (here and below): the kernel variant for the plain run — solar source, vacuum stage, telescope not turned, no
 // ignore* flag — in which those run-wide switches are compile-time constants instead of uniform branches (~5 % of the
 // instructions); every other setup takes the generic variant.
+// (the random words h.w are set by the caller: Philox for Monte Carlo rays, caller-supplied for sart_trace_words)
 template <bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
-__device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S,
-                                               const PhiloxKeys& K, uint64_t ray, Head32& h) {
-  ray_words(K, ray, h.w);
+__device__ __forceinline__ void stage_a32_head_words(const FastParams& P, const FastTables& T, const Smem32& S, Head32& h) {
   h.rIdx = 0; h.guide = 0;
   if (kPlain || !P.testXray) {
     const uint32_t wr = h.w[2];
@@ -232,6 +231,12 @@ __device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTa
     h.rIdx = rIdx;
     if (!kLateEnergy) h.guide = __ldg(guide_row(T, rIdx) + (h.w[5] >> (32 - kEnGuideBits)));
   }
+}
+template <bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
+__device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S,
+                                               const PhiloxKeys& K, uint64_t ray, Head32& h) {
+  ray_words(K, ray, h.w);
+  stage_a32_head_words<kPlain, kLateEnergy, kAlias>(P, T, S, h);
 }
 
 // Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
@@ -820,11 +825,15 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
 }
 
 // ---- per-ray records (traceAxionWrapper in FP32 mode) ----------------------------------------------------------
-template <bool kWolter, bool kPlain, bool kAlias>
+// `words` (optional, sart_trace_words): SoA [6][nRays] random words used instead of the Philox words of ray first + i.
+// kLate: the energy is resolved by energy_index() after stage A, the way the compacting fused kernel does it (otherwise
+// inside stage A, the way the plain fused kernel does it) — so the test hook reaches both forms of the search.
+template <bool kWolter, bool kPlain, bool kAlias, bool kLate = false>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                     const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
-                    const __grid_constant__ PhiloxKeys K, double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
+                    const __grid_constant__ PhiloxKeys K, const uint32_t* __restrict__ words, int32_t* __restrict__ oemit,
+                    double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
                     int32_t* __restrict__ oshell, double* __restrict__ oenergy, double* __restrict__ orad) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
@@ -838,8 +847,15 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     RecordSink<true> sink{r, mAxion2};
     Rec32 rec;
     Head32 hd;
-    stage_a32_head<kPlain, false, kAlias>(P, T, S, K, first + i, hd);
-    const int c0 = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, hd, rec);
+    if (words) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) hd.w[k] = words[size_t(k) * nRays + i];
+    } else {
+      ray_words(K, first + i, hd.w);
+    }
+    stage_a32_head_words<kPlain, kLate, kAlias>(P, T, S, hd);
+    const int c0 = stage_a32<kWolter, false, kPlain, kLate, kAlias>(P, G, T, S, hd, rec);
+    if (kLate && c0 < 0 && (kPlain || !P.testXray)) rec.eIdx = energy_index<kAlias>(P, T, rec.rIdx, rec.we, rec.clamped);
     if (c0 >= 0) sink.fail(c0);
     else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     int code = r.code;
@@ -848,7 +864,18 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
     const bool tail = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
     ox[i] = tail ? r.x : 0.0; oy[i] = tail ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tail ? r.shell : -1;
-    if (oenergy) oenergy[i] = double(r.energy);
+    if (oenergy) {
+      // energiesPre is set for every ray (rt:1818-1819), clipped or not: rays that end in stage A resolve their energy here
+      int eIdx = rec.eIdx;
+      if (kPlain || !P.testXray) {
+        bool cl = false;
+        if (c0 >= 0) eIdx = energy_index<kAlias>(P, T, hd.rIdx, hd.w[5], cl);
+        oenergy[i] = fmax(__ldg(T.energies + eIdx), 0.03);   // the f64 table value itself (rt:470-471)
+      } else {
+        oenergy[i] = double(P.srcEnergy);
+      }
+    }
+    if (oemit) oemit[i] = hd.rIdx;
     if (orad) orad[i] = tail ? r.r : 0.0;
   }
 }
@@ -1018,27 +1045,30 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
 
 cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
                                uint64_t first, uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount,
-                               cudaStream_t s) {
+                               cudaStream_t s, const uint32_t* words, bool lateEnergy, int32_t* emit) {
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const bool alias = T.sampler == SART_SAMPLER_ALIAS && !P.testXray && T.radiusAlias && T.energyAlias;
   const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias);
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
-  using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, double*, double*,
-                        double*, int32_t*, int32_t*, double*, double*);
+  using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, const uint32_t*,
+                        int32_t*, double*, double*, double*, int32_t*, int32_t*, double*, double*);
   static const Kern table[2][2][2] = {   // [wolter][plain][alias]
       {{fast::k_trace_mc_rays_f32<false, false, false>, fast::k_trace_mc_rays_f32<false, false, true>},
        {fast::k_trace_mc_rays_f32<false, true, false>, fast::k_trace_mc_rays_f32<false, true, true>}},
       {{fast::k_trace_mc_rays_f32<true, false, false>, fast::k_trace_mc_rays_f32<true, false, true>},
        {fast::k_trace_mc_rays_f32<true, true, false>, fast::k_trace_mc_rays_f32<true, true, true>}}};
-  const Kern kern = table[wolter ? 1 : 0][plain ? 1 : 0][alias ? 1 : 0];
+  static const Kern late[2][2] = {   // [wolter][alias], generic (non-plain) variant: the hook of sart_trace_words
+      {fast::k_trace_mc_rays_f32<false, false, false, true>, fast::k_trace_mc_rays_f32<false, false, true, true>},
+      {fast::k_trace_mc_rays_f32<true, false, false, true>, fast::k_trace_mc_rays_f32<true, false, true, true>}};
+  const Kern kern = lateEnergy ? late[wolter ? 1 : 0][alias ? 1 : 0] : table[wolter ? 1 : 0][plain ? 1 : 0][alias ? 1 : 0];
   cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * 2;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), o.x, o.y, o.w, o.code, o.shell,
-                                        o.energy, o.r);
+  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), words, emit, o.x, o.y, o.w, o.code,
+                                        o.shell, o.energy, o.r);
   return cudaGetLastError();
 }
 

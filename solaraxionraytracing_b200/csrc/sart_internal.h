@@ -49,6 +49,8 @@ struct sart_handle {
   size_t table_bytes = 0;
   int precision = 0;            // 0 exact f64, 1 fast (f64 algebra + f32 weights), 2 f32 geometry
   int compact = 0;              // fast mode: warp-level compaction between the clip stages and the mirrors
+  int compact_user = 0;         // set by sart_set_compaction: sart_update_setup keeps it instead of re-running the pilot
+  int have_solar = 0, n_refl_coatings = 0, have_tel_transmission = 0;   // which caller tables sart_create uploaded
   double pilot_survival = 1.0;  // fraction of launched rays that reach the mirrors (pilot run at create)
   // "fast" pipeline: parameter block, LUTs and f32 reflectivity in a second allocation
   int fast_ok = 0;
@@ -77,6 +79,7 @@ struct sart_handle {
   double* d_rep = nullptr;      // [2][n_rep][256*256]
   double* d_mass_acc = nullptr; // [2][256*256][SART_MAX_MASSES] mass-major accumulators of the mass-scan kernel
   int n_rep = 0;
+  size_t rep_stride = 0;        // doubles between two replicas
   // optional radial histogram of the passed rays (sart_enable_radial_hist)
   double* d_rad_w = nullptr;
   unsigned long long* d_rad_n = nullptr;

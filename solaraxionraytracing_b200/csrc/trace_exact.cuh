@@ -540,10 +540,8 @@ __device__ __forceinline__ void ray_finish(const Params& P, const Geo& g, const 
 // ------------------------------------------------------------------------------------------------------------
 // Sampling block of traceAxion (rt:1754-1764) from the six Philox uniforms of the ray.
 // Returns false if an X-ray test-source ray is stopped by its collimator (rt:1800-1801).
-__device__ __forceinline__ bool sample_ray(const Params& P, const Tables& T, uint64_t seed, uint64_t ray, V3& O, V3& E,
-                                           double& energy, int& clamped) {
-  uint32_t w[6];
-  ray_words(seed, ray, w);
+__device__ __forceinline__ bool sample_ray_words(const Params& P, const Tables& T, const uint32_t w[6], V3& O, V3& E,
+                                                 double& energy, int& clamped) {
   if (!P.testXray) {
     // getRandomPointFromSolarModel rt:425-442
     const double angle1 = 360.0 * u01(w[0]);
@@ -594,6 +592,12 @@ __device__ __forceinline__ bool sample_ray(const Params& P, const Tables& T, uin
   const V3 q = plane_point(O, E - O, P.colZ);
   const double qx = q.x - P.srcX, qy = q.y - P.srcY;
   return sqrt(qx * qx + qy * qy) < P.srcRadius;
+}
+__device__ __forceinline__ bool sample_ray(const Params& P, const Tables& T, uint64_t seed, uint64_t ray, V3& O, V3& E,
+                                           double& energy, int& clamped) {
+  uint32_t w[6];
+  ray_words(seed, ray, w);
+  return sample_ray_words(P, T, w, O, E, energy, clamped);
 }
 
 }  // namespace sart

@@ -118,8 +118,9 @@ class AxionBatch:
             return np.zeros(n, dtype=dtype)
         self.x = alloc(); self.y = alloc(); self.w = alloc()
         self.code = alloc(np.int32); self.shell = alloc(np.int32)
-        for name in abi.RAY_OUT_OPTIONAL:
-            setattr(self, name, alloc() if optional else None)
+        for name in abi.RAY_OUT_OPTIONAL:   # optional: True / False, or the names of the optional arrays wanted
+            want = (name in optional) if isinstance(optional, (tuple, list, set)) else bool(optional)
+            setattr(self, name, alloc() if want else None)
 
     def c_struct(self) -> abi.RayOut:
         o = abi.RayOut()
@@ -234,6 +235,18 @@ class RayTracer:
         out = AxionBatch(bufLen, optional)
         o = out.c_struct()
         check(lib.sart_trace_mc_rays(self._h, first_ray, bufLen, seed, C.byref(o)))
+        return out
+
+    def trace_words(self, words, late_energy: bool = False, optional: bool = True) -> AxionBatch:
+        """Test hook (sart_trace_words): traceAxionWrapper with caller-supplied random words [6, n] instead of Philox."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        if w.ndim != 2 or w.shape[0] != 6:
+            raise ValueError("words must be [6, n]")
+        out = AxionBatch(w.shape[1], optional)
+        o = out.c_struct()
+        out.emission_shell = np.empty(w.shape[1], dtype=np.int32)
+        check(lib.sart_trace_words(self._h, w.shape[1], w.ctypes.data_as(C.POINTER(C.c_uint32)), int(late_energy),
+                                   C.byref(o), out.emission_shell.ctypes.data_as(abi.c_int32_p)))
         return out
 
     # -- fused run

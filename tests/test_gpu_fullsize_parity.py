@@ -1,0 +1,224 @@
+"""Ray-by-ray parity against the CPU oracle AT THE TABLE SIZES OF BASELINE.json — solar model 1968 radii x 1500
+energies (src/readOpacityFile.nim:608-609), reflectivity 1000 angles x 1000 energies per coating
+(tools/llnl_layer_reflectivity.nim:50-51) — i.e. on the very tables `bench.py` times. With 1500 energies per row the
+2048-bucket guide no longer resolves most searches in the first group of four thresholds: the second group, the bounded
+tail search of flat CDF regions and the saturated-word fallback (kernels_f32.cu: energy_index, stage_a32) all run here,
+and are driven through their corners with hand-built random words (sart_trace_words).
+
+What is compared, and how:
+  * tier (a), `sart_trace_presampled` against `oracle_trace_presampled` on 1e6 rays per setup, precision 0 (every code,
+    flag and shell identical; x, y to 1e-9 mm; every f64 field to 1e-10 relative) and precision 2 (every exit code
+    identical: the rays whose FP32 margins are inside the error bounds are re-traced in FP64; x, y 99 % within 1.5e-3 mm,
+    weights 99 % within 2e-4 — 5e-3 with the buffer gas);
+  * the sampling (rt:437, 464): emission shell and energy of 1e7 Monte Carlo rays per setup bit-identical to the
+    oracle's, and of ~1e6 hand-built words per setup: word 0, word 0xffffffff, the words on either side of every radius
+    threshold and of every energy threshold of 40 emission shells;
+  * tier (b): image chi^2, flux and pass fraction against the oracle with an independent seed, both samplers.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import make_config
+from solaraxionraytracing_b200 import abi
+from test_gpu_fast import _chi2
+
+pytestmark = pytest.mark.gpu
+SEED = 299792458
+FULL = dict(nR=1968, nE=1500, nAng=1000, nEn=1000)
+CFGS = ["cast_llnl", "babyiaxo_xmm", "babyiaxo_gas"]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from solaraxionraytracing_b200 import raytracer
+    if raytracer.lib.sart_device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests need a B200")
+    return raytracer
+
+
+@pytest.fixture(scope="module")
+def tracers(rt):
+    """One handle per setup for the whole module (the full-size tables take ~0.3 s each to derive and upload)."""
+    cache = {}
+
+    def get(cfg):
+        if cfg not in cache:
+            setup, tb = make_config(cfg, **FULL)
+            cache[cfg] = (setup, tb, rt.RayTracer(rt.FullRaytraceSetup(setup, tb)))
+        return cache[cfg]
+    yield get
+    for _, _, tr in cache.values():
+        tr.close()
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_fullsize_presampled_exact_vs_oracle(tracers, oracle, cfg):
+    setup, tb, tr = tracers(cfg)
+    n = 1_000_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, SEED)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy)
+    tr.set_precision(0)
+    gpu = tr.trace_presampled(origin, exit_xy, energy)
+    assert np.array_equal(gpu.code, ref.code), np.flatnonzero(gpu.code != ref.code)[:10]
+    assert np.array_equal(gpu.shell, ref.shell)
+    for name in ("x", "y", "r", "deviationDet", "yaw"):
+        assert np.max(np.abs(getattr(gpu, name) - getattr(ref, name))) <= 1e-9, name
+    for name in ("w", "energy", "reflect", "transMagnet", "alpha1", "alpha2", "pathCB", "transProbArgon"):
+        a, b = getattr(gpu, name), getattr(ref, name)
+        err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+        err[b == 0] = np.abs(a[b == 0])
+        assert err.max() <= 1e-10, (name, float(err.max()))
+    assert len(set(np.unique(ref.exit_code).tolist())) >= 5      # the sample exercises the path
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_fullsize_presampled_f32_vs_oracle(tracers, oracle, cfg):
+    setup, tb, tr = tracers(cfg)
+    n = 1_000_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, SEED + 1)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy, optional=False)
+    tr.set_precision(2)
+    gpu = tr.trace_presampled(origin, exit_xy, energy, optional=False)
+    mism = (gpu.code & abi.CODE_MASK) != (ref.code & abi.CODE_MASK)
+    print(cfg, "exit-code mismatches", int(mism.sum()), "of", n)
+    assert mism.sum() == 0, [(int(i), int(gpu.code[i]), int(ref.code[i])) for i in np.flatnonzero(mism)[:10]]
+    both = (ref.code & abi.CODE_MASK) == abi.EXIT_PASSED
+    assert both.sum() > n // 10
+    assert np.array_equal(gpu.shell[both], ref.shell[both])
+    d = np.hypot(gpu.x[both] - ref.x[both], gpu.y[both] - ref.y[both])
+    assert np.median(d) <= 2e-4 and np.quantile(d, 0.99) <= 1.5e-3, (np.median(d), np.quantile(d, 0.99))
+    dw = np.abs(gpu.w[both] / ref.w[both] - 1.0)
+    assert np.quantile(dw, 0.99) <= (5e-3 if cfg == "babyiaxo_gas" else 2e-4), np.quantile(dw, 0.99)
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_fullsize_mc_sampling_identical_to_oracle(tracers, oracle, cfg):
+    """1e7 Philox rays: the energy of every ray (energiesPre is set before any clipping, rt:1818-1819) is the oracle's
+    f64 table value, bit for bit, in the FP32 pipeline; in the exact pipeline on the first 1e6 of them."""
+    setup, tb, tr = tracers(cfg)
+    n = 10_000_000
+    _, _, e_ref = oracle.sample_rays(setup, tb, 0, n, SEED)
+    tr.set_precision(2)
+    g = tr.traceAxionWrapper(n, SEED, optional=("energy",))
+    assert np.array_equal(g.energy, e_ref), np.flatnonzero(g.energy != e_ref)[:10]
+    assert np.unique(e_ref).size > 1000      # the sample reaches most of the energy grid
+    tr.set_precision(0)
+    g0 = tr.traceAxionWrapper(1_000_000, SEED, optional=("energy",))
+    assert np.array_equal(g0.energy, e_ref[:1_000_000])
+
+
+def _thresholds(rt, cdf):
+    cdf = np.ascontiguousarray(cdf, dtype=np.float64)
+    thr = np.empty(cdf.size, dtype=np.uint32)
+    rt.lib.sart_cdf_thresholds(cdf.ctypes.data_as(abi.c_double_p), cdf.size, thr.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return thr
+
+
+def _around(thr):
+    """The words on either side of every threshold, plus the ends of the word range."""
+    t = thr.astype(np.int64)
+    w = np.concatenate([t - 1, t, t + 1, [0, 1, 2, 0xfffffffd, 0xfffffffe, 0xffffffff]])
+    return np.unique(np.clip(w, 0, 0xffffffff)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_fullsize_sampling_corner_words(rt, tracers, oracle, cfg):
+    """Hand-built random words through both forms of the integer search (inside stage A: plain fused kernel; after the
+    compaction: energy_index) and through the exact pipeline, against the oracle's lowerBound on the f64 CDFs."""
+    setup, tb, tr = tracers(cfg)
+    rng = np.random.default_rng(2024)
+    nR, nE = tb.fluxRadiusCDF.size, tb.energies.size
+    thr_r = _thresholds(rt, tb.fluxRadiusCDF)
+    blocks = []
+    # (1) radius words around every radius threshold; energy words random
+    wr = _around(thr_r)
+    blocks.append((wr, rng.integers(0, 2 ** 32, wr.size, dtype=np.uint64).astype(np.uint32)))
+    # (2) for 40 emission shells (both ends of the table, a spread in between, the shells with the flattest CDF tails):
+    # a radius word that selects the shell, energy words around every energy threshold of its row
+    flat = np.argsort([np.unique(_thresholds(rt, tb.diffFluxCDFs[r])).size for r in range(0, nR, 16)])[:8] * 16
+    rows = np.unique(np.concatenate([[0, 1, nR - 2, nR - 1], np.linspace(2, nR - 3, 28).astype(int), flat]))
+    for r in rows:
+        lo = 0 if r == 0 else int(thr_r[r - 1])       # the smallest word that maps to shell r
+        if r < nR - 1 and lo >= int(thr_r[r]):
+            continue                                   # a shell no word maps to
+        we = _around(_thresholds(rt, tb.diffFluxCDFs[r]))
+        we = np.concatenate([we, rng.integers(0, 2 ** 32, 500, dtype=np.uint64).astype(np.uint32)])
+        blocks.append((np.full(we.size, lo, dtype=np.uint32), we))
+    w_rad = np.concatenate([b[0] for b in blocks])
+    w_en = np.concatenate([b[1] for b in blocks])
+    n = w_rad.size
+    words = rng.integers(0, 2 ** 32, (6, n), dtype=np.uint64).astype(np.uint32)
+    words[2], words[5] = w_rad, w_en
+    assert n > 150_000
+    origin, _, e_ref = oracle.sample_words(setup, tb, words)
+    rsun = setup.consts.radiusSun
+    rr = np.sqrt(origin[0] ** 2 + origin[1] ** 2 + (origin[2] + setup.consts.distanceSunEarth) ** 2) / rsun
+    r_ref = np.rint((rr - 0.0015) / 0.0005).astype(np.int32)
+    expect_r = np.minimum(np.searchsorted(tb.fluxRadiusCDF, (w_rad.astype(np.float64) + 0.5) / 2.0 ** 32, side="left"),
+                          nR - 1)
+    assert np.array_equal(r_ref, expect_r)            # the oracle's emission shell is lowerBound on the f64 CDF
+    assert (w_en == 0xffffffff).sum() >= rows.size - 2 and (w_rad == 0xffffffff).sum() >= 1
+    for precision, late in ((2, False), (2, True), (0, False)):
+        tr.set_precision(precision)
+        g = tr.trace_words(words, late_energy=late, optional=("energy",))
+        bad_r = np.flatnonzero(g.emission_shell != r_ref)
+        assert bad_r.size == 0, (precision, late, [(int(i), hex(int(w_rad[i])), int(g.emission_shell[i]), int(r_ref[i])) for i in bad_r[:5]])
+        bad_e = np.flatnonzero(g.energy != e_ref)
+        assert bad_e.size == 0, (precision, late, [(int(i), int(r_ref[i]), hex(int(w_en[i])), float(g.energy[i]), float(e_ref[i])) for i in bad_e[:5]])
+    # the corner rays are traced like any others: codes of the exact pipeline equal the oracle's
+    ref = oracle.trace_words(setup, tb, words[:, :50_000], optional=False)
+    tr.set_precision(0)
+    g0 = tr.trace_words(words[:, :50_000], optional=False)
+    assert np.array_equal(g0.code, ref.code)
+
+
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_INVERSE_CDF, abi.SAMPLER_ALIAS])
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_fullsize_image_statistically_equal_to_oracle(tracers, oracle, cfg, sampler):
+    setup, tb, tr = tracers(cfg)
+    n_gpu, n_cpu = 40_000_000, 4_000_000
+    img_o, img2_o, cnt_o = oracle.trace_mc(setup, tb, 0, n_cpu, 12345)
+    tr.set_precision(2)
+    tr.set_sampler(sampler)
+    try:
+        tr.reset_image()
+        tr.trace_mc(n_gpu, 777)
+        res = tr.read_image()
+    finally:
+        tr.set_sampler(abi.SAMPLER_INVERSE_CDF)
+        tr.reset_image()
+    a, va = res.image[0] / n_gpu, res.image_w2[0] / n_gpu ** 2
+    b, vb = img_o[0] / n_cpu, img2_o[0] / n_cpu ** 2
+    chi2, ndf = _chi2(a, va, b, vb)
+    assert ndf > 50
+    z = (chi2 - ndf) / np.sqrt(2.0 * ndf)
+    assert abs(z) < 5.0, (chi2, ndf, z)
+    assert abs(a.sum() - b.sum()) < 4.0 * np.sqrt(va.sum() + vb.sum())
+    cg, co = res.counters[0], cnt_o[0]
+    for k, v in co["n_exit"].items():     # every exit code within 5 sigma (two binomial samples)
+        pg, po = cg["n_exit"][k] / n_gpu, v / n_cpu
+        p = (cg["n_exit"][k] + v) / (n_gpu + n_cpu)
+        assert abs(pg - po) <= 5.0 * np.sqrt(p * (1 - p) * (1 / n_gpu + 1 / n_cpu)) + 1e-12, (k, pg, po)
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_fullsize_fused_counters_equal_oracle(tracers, oracle, cfg):
+    """The fused kernels on the oracle's own rays: exit-code histogram of 4e6 Philox rays, exact mode identical, FP32
+    mode identical too (uncertain rays are re-traced in FP64), total flux to 1e-6 / 3e-4."""
+    setup, tb, tr = tracers(cfg)
+    n, first = 4_000_000, 123_456_789
+    _, _, cnt_o = oracle.trace_mc(setup, tb, first, n, SEED)
+    co = cnt_o[0]
+    for precision, tol in ((0, 1e-6), (2, 3e-4)):
+        tr.set_precision(precision)
+        tr.reset_image()
+        tr.trace_mc(n, SEED, first_ray=first)
+        res = tr.read_image()
+        cg = res.counters[0]
+        assert cg["n_rays"] == n
+        assert cg["n_exit"] == co["n_exit"], (precision, cg["n_exit"], co["n_exit"])
+        assert cg["n_passed_till_window"] == co["n_passed_till_window"]
+        assert abs(cg["sum_w"] / co["sum_w"] - 1.0) < tol, (precision, cg["sum_w"], co["sum_w"])
+    tr.reset_image()
