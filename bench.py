@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-presampled", action="store_true", help="skip the tier-(a) pre-sampled kernel measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (2, 4, 5)")
     return ap.parse_args()
 
 
@@ -373,6 +374,102 @@ def records_leg(tr, torch, n: int = 1 << 24, reps: int = 3):
             "d2h_GBps": 32 * n / dt / 1e9, "passed_fraction": float((hc.bitwise_and(0xff) == 0).double().mean())}
 
 
+# Algorithmic work per launched ray of the other BASELINE configurations (SURVEY.md section 8d tally x measured
+# stage-reach probabilities): BabyIAXO + XMM 565 FLOP (23 % of the rays pass, 2/3 never reach a mirror); the buffer-gas
+# mass scan adds 100 FLOP per mass for the rays that reach the weight stage (0.25 of them).
+F_RAY_XMM = 565.0
+F_MASS = 100.0
+
+
+def other_configs_leg(rt, tables, torch, device, peak_tflops, rank=0, world=1, rays5=None):
+    """BASELINE configs 2, 4 and 5 next to the headline (config 1/3), each a few launches, device-timed on its handle's
+    stream. With world > 1 only config 5 runs: its rays are sharded over the ranks by global ray index and merged with
+    sart_allreduce, as BASELINE.json describes it (1e11 rays over 8 GPUs)."""
+    import numpy as np
+    from solaraxionraytracing_b200 import multi_gpu
+    em = tables.synthetic_emission(1968, 1500, "primakoff")
+    rc, dc = rt.buildCdfs(em, device)
+    tb = tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc,
+                         reflectivity=tables.synthetic_reflectivity(1, 1000, 1000), **tables.detector_tables_packaged())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")
+
+    def timed(tr, n, first=0, reps=3, merge=False):
+        stream = torch.cuda.ExternalStream(tr.stream, device=device)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        with torch.cuda.stream(stream):
+            tr.reset_image()
+            tr.trace_mc(max(1, n // 10), SEED, first_ray=first)   # warm-up
+            tr.reset_image()
+            for a, b in ev:
+                flush.zero_()
+                a.record(stream)
+                tr.trace_mc(n, SEED, first_ray=first)
+                if merge:
+                    tr.allreduce()
+                b.record(stream)
+            torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in ev), reps
+
+    out = {}
+    if world == 1:
+        # config 2: CAST magnet + XMM optic. With the reference's own geometry the CAST bore (r = 21.5 mm) lies inside XMM's
+        # central blocker (<= 64.7 mm, rt:1674): every ray that leaves the bore ends as `opaque` (kept as a parity case)
+        with rt.RayTracer(rt.FullRaytraceSetup(rt.newExperimentSetup("CAST", "InGrid2018", "vacuum", "XMM", 0), tb), device) as tr:
+            tr.set_precision(2)
+            n = 10**8
+            ms, reps = timed(tr, n)
+            c = tr.read_image().counters[0]
+            out["2_cast_xmm"] = {"rays": n, "value": n / (ms * 1e-3), "unit": "rays/s", "kernel_ms": ms,
+                                 "passed_fraction": c["n_passed"] / c["n_rays"], "opaque_fraction": c["n_exit"]["opaque"] / c["n_rays"],
+                                 "note": "the CAST bore lies inside XMM's central blocker: no ray reaches the mirrors (rt:1674)"}
+        # config 4: BabyIAXO, buffer gas, 64 axion masses around m_gamma sharing every traced ray, 1e8 rays per mass
+        setup4 = rt.newExperimentSetup("BabyIAXO", "InGridIAXO", "gas", "XMM", 0)
+        with rt.RayTracer(rt.FullRaytraceSetup(setup4, tb), device) as tr:
+            tr.set_precision(2)
+            mag, k = setup4.magnet, setup4.consts
+            p_gas = mag.pGasRoom / k.roomTemp * mag.tGas                      # rt:1601 (bar, consumed as mbar: quirk Q4)
+            ne = 2.0 * 6.022e23 * ((p_gas * 1e2) / (8.314 * mag.tGas))       # am:51-61
+            m_gamma = float(np.sqrt(1.97e-7 ** 3 * 4.0 * np.pi * (1.0 / 137.0) * ne / 511e3))
+            masses = np.linspace(0.5 * m_gamma, 1.5 * m_gamma, 64)
+            tr.set_axion_masses(masses)
+            n = 10**8
+            ms, reps = timed(tr, n)
+            cs = tr.read_image().counters
+            reach = (cs[0]["n_passed"] + cs[0]["n_exit"]["zero_weight"] + cs[0]["n_exit"]["window_aperture"]) / cs[0]["n_rays"]
+            flop = F_RAY_XMM + 64 * F_MASS * reach
+            ach = flop * n / (ms * 1e-3) / 1e12
+            out["4_mass_scan"] = {"rays_per_mass": n, "masses": 64, "m_gamma_eV": m_gamma, "value": n / (ms * 1e-3), "unit": "rays/s",
+                                  "ray_masses_per_s": 64 * n / (ms * 1e-3), "kernel_ms": ms, "flop_per_ray": flop,
+                                  "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+                                               "frac": ach / peak_tflops if peak_tflops else None},
+                                  "passed_fraction_first_mass": cs[0]["n_passed"] / cs[0]["n_rays"],
+                                  "retraced_fp64_fraction": cs[0]["n_retraced"] / cs[0]["n_rays"]}
+    # config 5: BabyIAXO / InGridIAXO / vacuum / XMM = config_default.toml as shipped
+    with rt.RayTracer(rt.FullRaytraceSetup(rt.newExperimentSetup("BabyIAXO", "InGridIAXO", "vacuum", "XMM", 0), tb), device) as tr:
+        tr.set_precision(2)
+        total = int(rays5 or (10**9 if world == 1 else 10**11))
+        first, count = multi_gpu.shard(total, rank, world)
+        if world > 1:
+            multi_gpu.comm_init(tr, rank, world, device)
+        ms, reps = timed(tr, count, first=first, reps=2 if world > 1 else 3, merge=world > 1)
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{device}")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = (tr.read_merged() if world > 1 else tr.read_image()).counters[0]
+        assert c["n_rays"] == total * reps, (c["n_rays"], total, reps)
+        ach = F_RAY_XMM * (total / world) / (ms * 1e-3) / 1e12
+        out["5_babyiaxo_xmm"] = {"rays": total, "n_gpus": world, "value": total / (ms * 1e-3), "unit": "rays/s", "ms": ms,
+                                 "flop_per_ray": F_RAY_XMM,
+                                 "roofline": {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+                                              "frac": ach / peak_tflops if peak_tflops else None, "per": "GPU"},
+                                 "passed_fraction": c["n_passed"] / c["n_rays"],
+                                 "retraced_fp64_fraction": c["n_retraced"] / c["n_rays"], "unresolved": c["n_unresolved"],
+                                 "timed": "trace of this rank's shard + sart_allreduce, max over ranks" if world > 1 else "fused launch"}
+    return out
+
+
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
     try:
@@ -413,8 +510,11 @@ def run_ours(args):
 
     stream = torch.cuda.ExternalStream(tr.stream, device=local)
     _, _, img_len = tr.image_dev()
-    views = multi_gpu.device_views(tr, local)   # zero-copy torch views of the image, w^2 image and counters
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+    if dist is not None:
+        # the path's one collective lives behind the C-ABI (sart_allreduce: ONE ncclAllReduce over image | w^2 image |
+        # counters into a separate merged buffer); torch.distributed only ships the 128-byte NCCL id and the timings
+        multi_gpu.comm_init(tr, rank, world, local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -432,10 +532,7 @@ def run_ours(args):
         if ev is not None:
             ev[1].record(stream)
         if dist is not None:
-            multi_gpu.allreduce_device(tr, local, views=views)
-            # every rank now holds the merged image; non-zero ranks drop theirs so the next step's sum stays right
-            if rank != 0:
-                tr.reset_image()
+            tr.allreduce()   # the ranks' own images keep accumulating; the sum over ranks lands in the merged buffer
 
     smi_index = local
     try:
@@ -465,7 +562,15 @@ def run_ours(args):
         clocks = sampler.stop() if rank == 0 else None
         ms_total = e0.elapsed_time(e1)
         kernel_ms = [a.elapsed_time(b) for a, b in kev]
-    res = tr.read_image()
+    res = tr.read_merged() if dist is not None else tr.read_image()
+    # per-rank kernel times: a straggler rank must be visible
+    t_k = torch.tensor(kernel_ms, dtype=torch.float64, device=f"cuda:{local}")
+    all_k = [torch.empty_like(t_k) for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(all_k, t_k)
+    else:
+        all_k = [t_k]
+    rank_kernel_ms = [float(t.mean().item()) for t in all_k]
 
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
@@ -478,6 +583,9 @@ def run_ours(args):
         first = ((W + K + k) * n_gpus + rank) * R
         tr.reset_image()
         tr.trace_mc(R, SEED, first_ray=first)
+        if dist is not None:
+            tr.allreduce()
+            return tr.read_merged()   # D2H of the merged image, w2 image and counters, synchronises
         return tr.read_image()   # D2H of image, w2 image and counters, synchronises
     e2e_step(0)
     barrier()
@@ -492,12 +600,16 @@ def run_ours(args):
     e2e_value = n_gpus * R * K / float(t_e.item())
     d2h = 2 * img_len * 8 + C.sizeof(abi.Counters) * tr.n_masses
 
+    fp64 = precision == "exact"
+    peak = C.c_double(0.0)
+    rt.check(rt.lib.sart_measure_fma_peak(local, 1 if fp64 else 0, C.byref(peak)))
+    other = None
+    if not args.no_configs and precision == "f32":
+        other = other_configs_leg(rt, tables, torch, local, peak.value, rank, world)   # collective for N > 1
     if rank == 0:
         c = res.counters[0]
-        fp64 = precision == "exact"
-        peak = C.c_double(0.0)
-        rt.check(rt.lib.sart_measure_fma_peak(local, 1 if fp64 else 0, C.byref(peak)))
         k_ms = statistics.mean(kernel_ms)
+        assert c["n_rays"] == n_gpus * R * K, (c["n_rays"], n_gpus, R, K)   # every rank's shard is in the merged counters
         achieved = F_RAY_LLNL * R / (k_ms * 1e-3) / 1e12
         out = {
             "metric": "traced rays/s", "value": value, "unit": "rays/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
@@ -506,12 +618,17 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "precision": precision, "sampler": args.sampler,
                        "l2": "256 MiB buffer written between steps (L2 flush)", "seed": SEED,
                        "table_upload_s": round(table_upload_s, 3),
-                       "passed_fraction": c["n_passed"] / max(1, c["n_rays"])},
+                       "passed_fraction": c["n_passed"] / max(1, c["n_rays"]),
+                       "retraced_fp64_fraction": c["n_retraced"] / max(1, c["n_rays"]), "unresolved": c["n_unresolved"],
+                       "collective": None if dist is None else "sart_allreduce: one ncclAllReduce(f64 sum) of image | w^2 image | counters per step"},
+            "kernel_ms_over_ranks": {"min": min(rank_kernel_ms), "median": statistics.median(rank_kernel_ms),
+                                     "max": max(rank_kernel_ms)},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                    "note": "sart_reset_image + sart_trace_mc + sart_read_image per step through the C-ABI; the path "
+                    "note": "sart_reset_image + sart_trace_mc (+ sart_allreduce) + sart_read_image/_merged per step through the C-ABI; the path "
                             "has no per-step host inputs (rays are generated in-kernel from Philox), tables are "
                             "resident per run (config.table_upload_s)"},
-            "gpu_launches": K * (2 if precision != "exact" else 1),   # fused trace kernel + image-replica fold per step
+            # per step: fused trace kernel + FP64 re-trace of its uncertain rays + image-replica fold (+ counter pack before the all-reduce)
+            "gpu_launches": K * ((3 if precision == "f32" else 2 if precision == "fast" else 1) + (1 if dist is not None else 0)),
             "clocks": clocks,
             "roofline": {"bound": "fp64" if fp64 else "fp32", "achieved": achieved, "peak": peak.value,
                          "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
@@ -529,6 +646,8 @@ def run_ours(args):
         if n_gpus == 1 and not args.no_presampled:
             out["presampled"] = presampled_leg(tr, torch, local)
             out["e2e_records"] = records_leg(tr, torch)
+        if other is not None:
+            out["configs"] = other
         tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[precision])
         if n_gpus == 1 and not args.no_cpu_baseline:
             v, cores, sample, cnt_cpu, n0, n_cpu = cpu_leg(args.cpu_seconds)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SART_ABI_VERSION 1
+#define SART_ABI_VERSION 2
 #define SART_MAX_SHELLS 64   /* XMM has 58 shells (raytracer.nim:1289-1313) */
 #define SART_MAX_COATINGS 8  /* LLNL has 4 coating recipes (raytracer.nim:1167) */
 #define SART_IMAGE_BINS 256  /* prepareHeatmap(256, 256, ...) raytracer.nim:2629 */
@@ -208,6 +208,10 @@ typedef struct {
   uint64_t n_passed_till_window; /* Axion.passedTillWindow */
   uint64_t n_hit_nickel;         /* Axion.hitNickel */
   uint64_t n_interp_clamped;     /* rays where an interpolation argument was clamped */
+  uint64_t n_retraced;           /* precision mode 2: rays whose FP32 decision margins were inside the error budget and
+                                    that were therefore traced by the exact FP64 pipeline instead (sart_set_retrace) */
+  uint64_t n_unresolved;         /* such rays that did not fit the re-trace queue and kept their FP32 outcome (0 in
+                                    practice: the queue holds 3 % of a launch) */
   double sum_w;                  /* Σ weights | passed  (performAngularScan rt:2800; "total flux" rt:885) */
   double sum_w2;
   double sum_x, sum_y, sum_r;    /* unweighted sums over passed rays (means of rt:2276-2278) */
@@ -250,6 +254,15 @@ int sart_set_precision(sart_handle_t* h, int mode);
  * identical ray by ray. Default: chosen at sart_create from the setup (on for XMM/Abrixas, off for LLNL). */
 int sart_set_compaction(sart_handle_t* h, int mode);
 int sart_has_precision(int mode); /* 1 if this build has the pipeline for `mode` */
+/* Precision mode 2 only. Every hit/miss decision of the FP32 pipeline (rho < R at the bore exit and the pipes rt:481-492,
+ * the spider and the shell boundaries rt:1635-1704, 1932-1944, the mirror roots rt:646-658, the nickel test rt:1706-1734,
+ * the window aperture and the strongback strips rt:2139-2185) has a margin; a ray with a margin inside the error budget of
+ * that decision — FP32 rounding, the fast sampling arithmetic, and the reference's own f64 rounding noise — is "uncertain".
+ * mode 1 (default): uncertain rays are traced by the exact FP64 pipeline instead, right after the FP32 kernel on the same
+ * stream, so every ray has the exit code of precision mode 0 (counted in sart_counters_t::n_retraced; ~1e-4 .. 3e-3 of the
+ * rays). mode 0: pure FP32 (about 1e-5 of the rays then differ in their exit code). `scale` multiplies every budget
+ * (1 = the derived budgets; tests use it to show the safety factor they carry). Not applied with SART_SAMPLER_ALIAS. */
+int sart_set_retrace(sart_handle_t* h, int mode, double scale);
 void* sart_stream(sart_handle_t* h); /* cudaStream_t the handle launches on */
 
 /* ---- CDF build on the device (replaces rt:2679-2705). emRates is [nRadii][nEnergies] row-major,
@@ -321,6 +334,24 @@ double* sart_image_dev(sart_handle_t* h);       /* [M][256][256] Σw  */
 double* sart_image_w2_dev(sart_handle_t* h);    /* [M][256][256] Σw² */
 void* sart_counters_dev(sart_handle_t* h);      /* sart_counters_t[M] on the device */
 size_t sart_image_len(sart_handle_t* h);        /* M*256*256 */
+/* ---- multi-GPU: the one collective of the path. Rays shard over GPUs by global ray index with no exchange while tracing;
+ * afterwards the images and counters — all additive — are summed over the GPUs by ONE ncclAllReduce(sum, f64) over
+ * {image, sum-of-squares image, counters} (the reference has no counterpart: its only parallel construct is the Weave loop
+ * of rt:2234-2244 inside one process). The sum lands in a separate "merged" buffer of every handle: the handle's own
+ * accumulators are untouched, so steps can go on accumulating and the call can be repeated. NCCL is loaded with dlopen at
+ * first use (SART_ERR_CONFIG if libnccl.so.2 is absent).
+ *   one process per GPU (MPI / torchrun): rank 0 calls sart_comm_unique_id, ships the 128 bytes to the other ranks by
+ *     whatever transport the host has, every rank calls sart_comm_init_rank, then sart_allreduce(&h, 1);
+ *   one process, n GPUs: sart_comm_init_all(handles, n) (handles on distinct devices), then sart_allreduce(handles, n).
+ * Asynchronous on the handles' streams; sart_read_merged synchronises and copies the merged result out. */
+#define SART_COMM_ID_BYTES 128
+int sart_comm_unique_id(char id[SART_COMM_ID_BYTES]);
+int sart_comm_init_rank(sart_handle_t* h, int n_ranks, int rank, const char id[SART_COMM_ID_BYTES]);
+int sart_comm_init_all(sart_handle_t* const* handles, int n);
+void sart_comm_destroy(sart_handle_t* h);   /* also done by sart_destroy */
+int sart_allreduce(sart_handle_t* const* handles, int n);
+int sart_read_merged(sart_handle_t* h, double* image, double* image_w2, sart_counters_t* counters);
+
 /* Synchronise and copy out. image/image_w2 may be NULL. counters is [M]. */
 int sart_read_image(sart_handle_t* h, double* image, double* image_w2, sart_counters_t* counters);
 int sart_synchronize(sart_handle_t* h);

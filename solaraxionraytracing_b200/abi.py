@@ -4,12 +4,13 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 SAMPLER_INVERSE_CDF, SAMPLER_ALIAS = 0, 1
 MAX_SHELLS = 64
 MAX_COATINGS = 8
 IMAGE_BINS = 256
 MAX_MASSES = 64
+COMM_ID_BYTES = 128
 
 # enums (raytracer.nim:16-46, 59-64, 164-167)
 ES_CAST, ES_BABYIAXO = 0, 1
@@ -125,6 +126,7 @@ class RayOut(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("n_rays", C.c_uint64), ("n_exit", C.c_uint64 * 16), ("n_passed", C.c_uint64),
                 ("n_passed_till_window", C.c_uint64), ("n_hit_nickel", C.c_uint64), ("n_interp_clamped", C.c_uint64),
+                ("n_retraced", C.c_uint64), ("n_unresolved", C.c_uint64),
                 ("sum_w", C.c_double), ("sum_w2", C.c_double), ("sum_x", C.c_double), ("sum_y", C.c_double),
                 ("sum_r", C.c_double)]
 
@@ -132,7 +134,8 @@ class Counters(C.Structure):
         d = {"n_rays": int(self.n_rays), "n_passed": int(self.n_passed),
              "n_passed_till_window": int(self.n_passed_till_window), "n_hit_nickel": int(self.n_hit_nickel),
              "n_interp_clamped": int(self.n_interp_clamped), "sum_w": float(self.sum_w), "sum_w2": float(self.sum_w2),
-             "sum_x": float(self.sum_x), "sum_y": float(self.sum_y), "sum_r": float(self.sum_r)}
+             "sum_x": float(self.sum_x), "sum_y": float(self.sum_y), "sum_r": float(self.sum_r),
+             "n_retraced": int(self.n_retraced), "n_unresolved": int(self.n_unresolved)}
         d["n_exit"] = {EXIT_NAMES[i]: int(self.n_exit[i]) for i in range(N_EXIT_CODES)}
         return d
 
@@ -173,6 +176,7 @@ SIGNATURES = {
     "sart_set_precision": (C.c_int, [H, C.c_int]),
     "sart_has_precision": (C.c_int, [C.c_int]),
     "sart_set_compaction": (C.c_int, [H, C.c_int]),
+    "sart_set_retrace": (C.c_int, [H, C.c_int, C.c_double]),
     "sart_stream": (C.c_void_p, [H]),
     "sart_build_cdfs": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_double_p]),
@@ -192,6 +196,12 @@ SIGNATURES = {
     "sart_image_len": (C.c_size_t, [H]),
     "sart_read_image": (C.c_int, [H, c_double_p, c_double_p, C.POINTER(Counters)]),
     "sart_synchronize": (C.c_int, [H]),
+    "sart_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "sart_comm_init_rank": (C.c_int, [H, C.c_int, C.c_int, C.c_char_p]),
+    "sart_comm_init_all": (C.c_int, [C.POINTER(H), C.c_int]),
+    "sart_comm_destroy": (None, [H]),
+    "sart_allreduce": (C.c_int, [C.POINTER(H), C.c_int]),
+    "sart_read_merged": (C.c_int, [H, c_double_p, c_double_p, C.POINTER(Counters)]),
     "sart_angular_scan": (C.c_int, [H, C.c_int, c_double_p, C.c_uint64, C.c_uint64, C.c_uint64, c_double_p, C.POINTER(Counters),
                                     c_double_p]),
     "sart_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),

@@ -29,6 +29,7 @@ UNITS = [
     ("kernels_util.cu", []),
     ("kernels_emission.cu", []),
     ("api.cu", []),
+    ("comm.cu", []),
     ("derive.cpp", []),
     ("derive_fast.cpp", []),
     ("host_setup.cpp", []),
@@ -69,7 +70,7 @@ def build(force: bool = False, verbose: bool = False, defines: list[str] | None 
                     sys.stderr.write((r.stdout or "") + (r.stderr or ""))
                     raise subprocess.CalledProcessError(r.returncode, r.args)
     if force or _stale(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(LIB), *map(str, objs)]
+        cmd = [NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(LIB), *map(str, objs), "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
@@ -87,7 +88,7 @@ def _build_variant(defines: list[str], out: Path, verbose: bool) -> Path:
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
-    subprocess.run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(out), *map(str, objs)],
+    subprocess.run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-cudart", "static", "-o", str(out), *map(str, objs), "-ldl"],
                    check=True)
     return out
 

@@ -205,7 +205,12 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     }
     const size_t nRefl = t->reflectivity ? size_t(t->nCoatings) * t->nAngles * t->nReflEnergies : 0;
     h->h_refl32.resize(nRefl);
-    for (size_t i = 0; i < nRefl; ++i) h->h_refl32[i] = float(t->reflectivity[i]);
+    // a reflectivity that is non-zero in f64 stays non-zero in the f32 copy: `passed` means weight != 0 (rt:2220), and
+    // multilayer tables reach 1e-50 at large angles
+    for (size_t i = 0; i < nRefl; ++i) {
+      const double v = t->reflectivity[i];
+      h->h_refl32[i] = (v != 0.0 && std::fabs(v) < 1.2e-38) ? float(std::copysign(1.2e-38, v)) : float(v);
+    }
   }
   if (!h->fast_ok) return SART_OK;
   if (!t && !h->fast_blob) {
@@ -230,7 +235,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   fast::build_shell_guide(h->setup, &h->fparams, &sguide);
   if (sguide.size() > 4096) return fail(SART_ERR_CONFIG, "shell guide too large (%zu)", sguide.size());
   std::vector<fast::ShellF32> sh32(SART_MAX_SHELLS);
-  fast::derive_f32(h->fparams, shf.data(), h->setup.telescope.nShells, &h->geo32, sh32.data());
+  fast::derive_f32(h->fparams, shf.data(), h->setup.telescope.nShells, &h->geo32, sh32.data(), h->retrace_scale);
   std::vector<fast::ShellCell> stab;
   h->f32_ok = fast::build_shell_table(h->geo32, sh32.data(), h->setup.telescope.nShells, int(sguide.size()), &stab) ? 1 : 0;
   if (!h->f32_ok) stab.assign(sguide.size(), fast::ShellCell{0.f, 0u});   // mode 1 (its own shell scan) stays available
@@ -346,19 +351,37 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
 static int ensure_image(sart_handle* h, int nMasses) {
   const size_t len = size_t(nMasses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
   if (h->d_image && h->image_masses == nMasses) return SART_OK;
-  cudaFree(h->d_image); cudaFree(h->d_image_w2); cudaFree(h->d_counters);
-  h->d_image = nullptr; h->d_image_w2 = nullptr; h->d_counters = nullptr; h->image_masses = 0;
-  SART_CUDA(cudaMalloc(&h->d_image, len * sizeof(double)));
-  SART_CUDA(cudaMalloc(&h->d_image_w2, len * sizeof(double)));
+  cudaFree(h->d_image); cudaFree(h->d_counters);   // d_image_w2 points into d_image's block
+  h->d_image = nullptr; h->d_image_w2 = nullptr; h->d_counters = nullptr; h->image_masses = 0; h->merged_valid = 0;
+  SART_CUDA(cudaMalloc(&h->d_image, merged_words(nMasses) * sizeof(double)));
+  h->d_image_w2 = h->d_image + len;
   SART_CUDA(cudaMalloc(&h->d_counters, size_t(nMasses) * sizeof(sart_counters_t)));
   h->image_masses = nMasses;
-  SART_CUDA(cudaMemsetAsync(h->d_image, 0, len * sizeof(double), h->stream));
-  SART_CUDA(cudaMemsetAsync(h->d_image_w2, 0, len * sizeof(double), h->stream));
+  SART_CUDA(cudaMemsetAsync(h->d_image, 0, merged_words(nMasses) * sizeof(double), h->stream));
   SART_CUDA(cudaMemsetAsync(h->d_counters, 0, size_t(nMasses) * sizeof(sart_counters_t), h->stream));
   return SART_OK;
 }
 
 static int ensure_stage(sart_handle* h, size_t bytes);
+
+// Re-trace queue for a launch of n rays of the FP32 pipeline: room for 3 % of them (measured: 0.01 - 0.3 % are
+// uncertain), cleared on the stream. Returns a queue with cap = 0 when re-tracing is off.
+constexpr uint64_t kRetraceChunk = uint64_t(1) << 31;   // rays per launch: queue entries are 32-bit offsets
+static int begin_queue(sart_handle* h, uint64_t n, fast::RetraceQueue* q) {
+  *q = fast::RetraceQueue{nullptr, nullptr, 0u, 0u};
+  if (!h->retrace || n == 0) return SART_OK;
+  const size_t want = size_t(std::min<uint64_t>(n, std::max<uint64_t>(n / 32 + 65536, 1u << 20)));
+  if (h->queue_cap < want) {
+    SART_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_queue);
+    h->d_queue = nullptr; h->queue_cap = 0;
+    SART_CUDA(cudaMalloc(&h->d_queue, (want + 64) * sizeof(uint32_t)));
+    h->queue_cap = want;
+  }
+  SART_CUDA(cudaMemsetAsync(h->d_queue, 0, 64 * sizeof(uint32_t), h->stream));
+  q->list = h->d_queue + 64; q->count = h->d_queue; q->cap = uint32_t(std::min<size_t>(h->queue_cap, 0xffffffffu));
+  return SART_OK;
+}
 
 // Replica buffers for the single-mass throughput kernels. SART_IMG_REPLICAS overrides the count (1 = off).
 static int ensure_replicas(sart_handle* h) {
@@ -538,8 +561,10 @@ void sart_destroy(sart_handle_t* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_image_w2);
+  sart_comm_destroy(h);
+  cudaFree(h->table_blob); cudaFree(h->fast_blob); cudaFree(h->d_masses); cudaFree(h->d_image); cudaFree(h->d_merged);
   cudaFree(h->d_counters); cudaFree(h->d_stage); cudaFree(h->d_rad_w); cudaFree(h->d_rad_n); cudaFree(h->d_rep); cudaFree(h->d_mass_acc);
+  cudaFree(h->d_queue);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_in) cudaStreamDestroy(h->stream_in);
   if (h->stream_out) cudaStreamDestroy(h->stream_out);
@@ -644,6 +669,22 @@ void sart_alias_table(const uint32_t* thr, int n, uint32_t* entries) {
   if (!fast::build_alias_table(thr, n, entries)) std::memset(entries, 0, size_t(n) * 4);
 }
 
+int sart_set_retrace(sart_handle_t* h, int mode, double scale) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (mode < 0 || mode > 1 || !(scale >= 0.0) || scale > 1e6) return fail(SART_ERR_ARG, "sart_set_retrace: mode 0/1, scale in [0, 1e6]");
+  DeviceGuard dg(h->device);
+  h->retrace = mode;
+  if (float(scale) != h->retrace_scale) {
+    h->retrace_scale = float(scale);
+    if (h->fast_ok) {   // the budgets live in the FP32 geometry block
+      SART_CUDA(cudaStreamSynchronize(h->stream));
+      int rc = upload_fast(h, nullptr);
+      if (rc) return rc;
+    }
+  }
+  return SART_OK;
+}
+
 int sart_set_compaction(sart_handle_t* h, int mode) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   if (mode < 0 || mode > 1) return fail(SART_ERR_ARG, "compaction mode must be 0 or 1");
@@ -724,6 +765,24 @@ static int check_out(const sart_ray_out_t* out) {
   return SART_OK;
 }
 
+// One batch of pre-sampled rays, device pointers. Precision 2: the FP32 kernel writes every record and queues the rays
+// whose decision margins are inside their error budgets; the exact kernel then overwrites those records.
+static int launch_presampled(sart_handle* h, size_t m, const double* dO, const double* dX, const double* dE,
+                             const sart_ray_out_t& dev) {
+  if (h->precision == 2 && h->ftables.energies) {
+    if (m > kRetraceChunk) return fail(SART_ERR_ARG, "sart_trace_presampled: at most 2^31 rays per call in precision mode 2");
+    fast::FastTables ft = h->ftables;
+    int rc = begin_queue(h, m, &ft.rq);
+    if (rc) return rc;
+    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, ft, h->masses[0], m, dO, dX, dE, dev, h->sm_count, h->stream));
+    if (ft.rq.cap)
+      SART_CUDA(launch_retrace_presampled(h->params, h->tables, h->masses[0], m, dO, dX, dE, ft.rq, dev, h->sm_count, h->stream));
+  } else {
+    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], m, dO, dX, dE, dev, h->stream));
+  }
+  return SART_OK;
+}
+
 int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin, const double* d_exit,
                               const double* d_energy, const sart_ray_out_t* d_out) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
@@ -731,12 +790,7 @@ int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin
   if (rc) return rc;
   if (n && (!d_origin || !d_exit || !d_energy)) return fail(SART_ERR_ARG, "sart_trace_presampled: NULL input");
   DeviceGuard dg(h->device);
-  if (h->precision == 2 && h->ftables.energies)
-    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, h->ftables, h->masses[0], n, d_origin, d_exit, d_energy, *d_out,
-                                    h->sm_count, h->stream));
-  else
-    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], n, d_origin, d_exit, d_energy, *d_out, h->stream));
-  return SART_OK;
+  return launch_presampled(h, n, d_origin, d_exit, d_energy, *d_out);
 }
 
 // Lays a device-side sart_ray_out_t over the staging buffer; returns bytes used.
@@ -782,17 +836,6 @@ static sart_ray_out_t offset_out(const sart_ray_out_t& o, size_t a) {
   return r;
 }
 
-static int launch_presampled(sart_handle* h, size_t m, const double* dO, const double* dX, const double* dE,
-                             const sart_ray_out_t& dev, unsigned char* outBase, size_t outBytes) {
-  if (h->precision == 2 && h->ftables.energies) {
-    // the f32 pipeline fills x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
-    SART_CUDA(cudaMemsetAsync(outBase, 0, outBytes, h->stream));
-    SART_CUDA(launch_presampled_f32(h->fparams, h->geo32, h->ftables, h->masses[0], m, dO, dX, dE, dev, h->sm_count, h->stream));
-  } else {
-    SART_CUDA(launch_presampled_exact(h->params, h->tables, h->masses[0], m, dO, dX, dE, dev, h->stream));
-  }
-  return SART_OK;
-}
 
 int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin, const double* exitxy, const double* energy,
                           const sart_ray_out_t* out) {
@@ -838,7 +881,7 @@ int sart_trace_presampled(sart_handle_t* h, size_t n, const double* origin, cons
       SART_CUDA(cudaStreamWaitEvent(h->stream, ev(0, b), 0));
       if (k >= 2) SART_CUDA(cudaStreamWaitEvent(h->stream, ev(2, b), 0));           // outputs of chunk k-2 have left this buffer
     }
-    if ((rc = launch_presampled(h, m, dO, dX, dE, dev, base + inBytes, outBytes))) return rc;
+    if ((rc = launch_presampled(h, m, dO, dX, dE, dev))) return rc;
     if (nbuf == 2) {
       SART_CUDA(cudaEventRecord(ev(1, b), h->stream));
       SART_CUDA(cudaStreamWaitEvent(sOut, ev(1, b), 0));
@@ -868,13 +911,16 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
   if ((rc = ensure_stage(h, outBytes))) return rc;
   sart_ray_out_t dev;
   carve_out(static_cast<unsigned char*>(h->d_stage), n, *out, &dev);
-  if (h->precision >= 1) {
-    // the throughput modes fill x, y, w, code, shell, energy and r; the remaining optional arrays are zeroed
-    SART_CUDA(cudaMemsetAsync(h->d_stage, 0, outBytes, h->stream));
-    if (h->precision == 2)
-      SART_CUDA(launch_mc_rays_f32(h->fparams, h->geo32, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
-    else
-      SART_CUDA(launch_mc_rays_fast(h->fparams, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
+  if (h->precision == 2) {
+    if (n > kRetraceChunk) return fail(SART_ERR_ARG, "sart_trace_mc_rays: at most 2^31 rays per call");
+    fast::FastTables ft = h->ftables;
+    const bool alias = h->sampler == SART_SAMPLER_ALIAS;   // another ray <-> index mapping than the exact pipeline's: no re-trace
+    if (!alias && (rc = begin_queue(h, n, &ft.rq))) return rc;
+    SART_CUDA(launch_mc_rays_f32(h->fparams, h->geo32, ft, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
+    if (ft.rq.cap)
+      SART_CUDA(launch_retrace_mc_rays(h->params, h->tables, h->masses[0], first_ray, n, seed, nullptr, ft.rq, dev, h->sm_count, h->stream));
+  } else if (h->precision == 1) {
+    SART_CUDA(launch_mc_rays_fast(h->fparams, h->ftables, h->masses[0], first_ray, n, seed, dev, h->sm_count, h->stream));
   } else {
     SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], first_ray, n, seed, dev, h->stream));
   }
@@ -903,9 +949,13 @@ int sart_trace_words(sart_handle_t* h, size_t n, const uint32_t* words, int late
   int32_t* dEmit = emission_shell ? reinterpret_cast<int32_t*>(base + outBytes + wBytes) : nullptr;
   SART_CUDA(cudaMemcpyAsync(dW, words, 6 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   if (h->precision == 2) {
-    SART_CUDA(cudaMemsetAsync(base, 0, outBytes, h->stream));
-    SART_CUDA(launch_mc_rays_f32(h->fparams, h->geo32, h->ftables, h->masses[0], 0, n, 0, dev, h->sm_count, h->stream, dW,
+    if (n > kRetraceChunk) return fail(SART_ERR_ARG, "sart_trace_words: at most 2^31 rays per call");
+    fast::FastTables ft = h->ftables;
+    if (h->sampler != SART_SAMPLER_ALIAS && (rc = begin_queue(h, n, &ft.rq))) return rc;
+    SART_CUDA(launch_mc_rays_f32(h->fparams, h->geo32, ft, h->masses[0], 0, n, 0, dev, h->sm_count, h->stream, dW,
                                  late_energy != 0, dEmit));
+    if (ft.rq.cap)
+      SART_CUDA(launch_retrace_mc_rays(h->params, h->tables, h->masses[0], 0, n, 0, dW, ft.rq, dev, h->sm_count, h->stream));
   } else {
     SART_CUDA(launch_mc_rays_exact(h->params, h->tables, h->masses[0], 0, n, 0, dev, h->stream, dW, dEmit));
   }
@@ -919,18 +969,32 @@ int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_
   DeviceGuard dg(h->device);
   if (h->sampler == SART_SAMPLER_ALIAS && (h->precision != 2 || h->n_masses > 1))
     return fail(SART_ERR_CONFIG, "the alias sampler needs precision mode 2 and a single axion mass");
+  // Precision 2: launches of at most 2^31 rays, each followed on the same stream by the exact pipeline's pass over the
+  // rays the FP32 kernel queued as uncertain (it adds them to the same image and counters). Not with the alias sampler,
+  // whose ray <-> index mapping is not the exact pipeline's.
+  const bool retrace = h->precision == 2 && h->retrace && h->sampler != SART_SAMPLER_ALIAS;
   if (h->precision >= 1 && h->n_masses > 1) {
     const size_t plane = size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS, accLen = plane * SART_MAX_MASSES;
     if (!h->d_mass_acc) {
       SART_CUDA(cudaMalloc(&h->d_mass_acc, 2 * accLen * sizeof(double)));
       SART_CUDA(cudaMemsetAsync(h->d_mass_acc, 0, 2 * accLen * sizeof(double), h->stream));
     }
-    if (h->precision == 2)
-      SART_CUDA(launch_mc_image_f32_masses(h->fparams, h->geo32, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays,
-                                           seed, h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
-    else
+    if (h->precision == 2) {
+      for (uint64_t done = 0; done < n_rays; done += kRetraceChunk) {
+        const uint64_t n = std::min<uint64_t>(n_rays - done, kRetraceChunk);
+        fast::FastTables ft = h->ftables;
+        int rc = retrace ? begin_queue(h, n, &ft.rq) : SART_OK;
+        if (rc) return rc;
+        SART_CUDA(launch_mc_image_f32_masses(h->fparams, h->geo32, ft, h->n_masses, h->d_masses, first_ray + done, n, seed,
+                                             h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
+        if (ft.rq.cap)
+          SART_CUDA(launch_retrace_mc_image(h->params, h->tables, h->n_masses, h->d_masses, first_ray + done, seed, ft.rq,
+                                            h->d_image, h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+      }
+    } else {
       SART_CUDA(launch_mc_image_fast_masses(h->fparams, h->ftables, h->n_masses, h->d_masses, first_ray, n_rays, seed,
                                             h->d_mass_acc, h->d_mass_acc + accLen, h->d_counters, h->sm_count, h->stream));
+    }
     SART_CUDA(launch_fold_mass_acc(h->d_mass_acc, h->d_mass_acc + accLen, h->n_masses, plane, h->d_image, h->d_image_w2,
                                    h->stream));
     return SART_OK;
@@ -945,12 +1009,23 @@ int sart_trace_mc(sart_handle_t* h, uint64_t first_ray, uint64_t n_rays, uint64_
       ft.nImgRep = h->n_rep; ft.imgRepStride = h->rep_stride;
       img = h->d_rep; img2 = h->d_rep + size_t(h->n_rep) * h->rep_stride;
     }
-    if (h->precision == 2)
-      SART_CUDA(launch_mc_image_f32(h->fparams, h->geo32, ft, h->masses[0], first_ray, n_rays, seed, img, img2,
-                                    h->d_counters, h->sm_count, h->compact != 0, h->stream));
-    else
+    if (h->precision == 2) {
+      for (uint64_t done = 0; done < n_rays; done += kRetraceChunk) {
+        const uint64_t n = std::min<uint64_t>(n_rays - done, kRetraceChunk);
+        if (retrace && (rc = begin_queue(h, n, &ft.rq))) return rc;
+        SART_CUDA(launch_mc_image_f32(h->fparams, h->geo32, ft, h->masses[0], first_ray + done, n, seed, img, img2,
+                                      h->d_counters, h->sm_count, h->compact != 0, h->stream));
+        if (ft.rq.cap) {
+          Tables et = h->tables;
+          if (!ft.rad.w) et.rad = RadialHist{};
+          SART_CUDA(launch_retrace_mc_image(h->params, et, 1, h->d_masses, first_ray + done, seed, ft.rq, h->d_image,
+                                            h->d_image_w2, h->d_counters, h->sm_count, h->stream));
+        }
+      }
+    } else {
       SART_CUDA(launch_mc_image_fast(h->fparams, ft, h->masses[0], first_ray, n_rays, seed, img, img2, h->d_counters,
                                      h->sm_count, h->compact != 0, h->stream));
+    }
     if (h->n_rep > 1)
       SART_CUDA(launch_fold_replicas(img, img2, h->n_rep, h->rep_stride, plane, h->d_image, h->d_image_w2, h->stream));
     return SART_OK;
@@ -964,8 +1039,7 @@ int sart_reset_image(sart_handle_t* h) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");
   DeviceGuard dg(h->device);
   const size_t len = size_t(h->n_masses) * SART_IMAGE_BINS * SART_IMAGE_BINS;
-  SART_CUDA(cudaMemsetAsync(h->d_image, 0, len * sizeof(double), h->stream));
-  SART_CUDA(cudaMemsetAsync(h->d_image_w2, 0, len * sizeof(double), h->stream));
+  SART_CUDA(cudaMemsetAsync(h->d_image, 0, 2 * len * sizeof(double), h->stream));   // image | w^2 image: one block
   SART_CUDA(cudaMemsetAsync(h->d_counters, 0, size_t(h->n_masses) * sizeof(sart_counters_t), h->stream));
   if (h->rad_bins > 0) {
     SART_CUDA(cudaMemsetAsync(h->d_rad_w, 0, size_t(h->rad_bins) * sizeof(double), h->stream));
@@ -1091,8 +1165,20 @@ int sart_angular_scan(sart_handle_t* h, int n_angles, const double* angles_deg, 
         fast::Geo32 G;
         std::vector<fast::ShellF32> unused(SART_MAX_SHELLS);
         fast::derive_f32(F, nullptr, 0, &G, unused.data());
-        SART_CUDA(launch_mc_image_f32(F, G, ft, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,
-                                      dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->compact != 0, h->stream));
+        // error budgets: the handle's (they depend on the shells, which do not turn), doubled where the rotation of the
+        // telescope frame adds rounding steps
+        G.tol = h->geo32.tol;
+        if (F.rotated && !h->fparams.rotated) { G.tol.latA *= 2.0f; G.tol.detA *= 2.0f; }
+        for (uint64_t done = 0; done < n_rays_per_angle; done += kRetraceChunk) {
+          const uint64_t n = std::min<uint64_t>(n_rays_per_angle - done, kRetraceChunk);
+          fast::FastTables fq = ft;
+          if (h->retrace && h->sampler != SART_SAMPLER_ALIAS && (rc = begin_queue(h, n, &fq.rq))) return rc;
+          SART_CUDA(launch_mc_image_f32(F, G, fq, h->masses[0], first + done, n, seed, dImg + size_t(i) * plane,
+                                        dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->compact != 0, h->stream));
+          if (fq.rq.cap)
+            SART_CUDA(launch_retrace_mc_image(P, et, 1, h->d_masses, first + done, seed, fq.rq, dImg + size_t(i) * plane,
+                                              dImg2 + size_t(i) * plane, dCnt + i, h->sm_count, h->stream));
+        }
         continue;
       }
       SART_CUDA(launch_mc_image_fast(F, ft, h->masses[0], first, n_rays_per_angle, seed, dImg + size_t(i) * plane,

@@ -69,15 +69,88 @@ void derive_shells(const sart_setup_t& s, const ShellF64* a, ShellFast* out) {
     o.h_inv_nden = a[j].h_nden != 0.0 ? 1.0 / a[j].h_nden : 0.0;
     int coat = 0;
     if (t.reflKind == SART_RK_MULTI_COATING) {
-      while (coat < t.nCoatings - 1 && t.layers[coat] < j) ++coat;   // layers.lowerBound(hitLayer) rt:1573
+      while (coat < t.nCoatings && t.layers[coat] < j) ++coat;   // layers.lowerBound(hitLayer) rt:1573
+      if (coat > t.nCoatings - 1) coat = (t.nCoatings - 1) | kCoatClamped;   // past the last coating: clamped + flagged, as in the exact pipeline
     }
     o.coat = coat;
   }
 }
 
+// Error budgets of the FP32 decisions (fast_params.h: Tol32), in mm unless stated. eps = 2^-24 is the unit roundoff of
+// FP32. Three sources are budgeted (DESIGN.md section 3b has the derivation):
+//  (1) FP32 rounding of the pipeline itself: a coordinate of magnitude R carries ~eps R per operation;
+//  (2) Monte Carlo rays only: the fast sampling arithmetic (MUFU sin/cos, absolute error 2^-21.4) moves the exit-disc
+//      point by ~1e-6 radiusCB and the emission point by ~1e-6 rs R_sun, i.e. the direction by 1e-6 rs R_sun / D;
+//  (3) the reference's own rounding: it intersects planes with the line O + lambda (E - O) through a point D = 1.5e14 mm
+//      away (rt:481-492, 529-534), which leaves pointExitCB off the true line by up to ulp(|O.x|) + |slope| ulp(|O.z|)
+//      <= 2^-51 D (|sx| + |sy|); every later point is extrapolated from E (exact) through that point, so the error grows
+//      with z / (zExitCB - lengthB) and reaches the detector multiplied by focal length / (zExitCB - lengthB).
+// `scale` multiplies every budget (sart_set_retrace).
+void derive_tolerances(const FastParams& f, const ShellFast* a, int nShells, float scale, Tol32* t) {
+  std::memset(t, 0, sizeof *t);
+  const double eps = 5.9604644775390625e-08;
+  const double rPipe = std::sqrt(f.rPipe12);
+  double r1max = 0.0, tanMax = 0.0, focal = 0.0;
+  for (int j = 0; j < nShells; ++j) {
+    r1max = std::max(r1max, a[j].R1pT);
+    tanMax = std::max(tanMax, std::fabs(a[j].tan2));
+    focal = std::max(focal, std::fabs(a[j].ddWin));
+  }
+  const double rmax = std::max({f.radiusCB, rPipe + std::fabs(f.oeX), rPipe + std::fabs(f.oeY), r1max});
+  const double L = std::fabs(f.dzPipe2) + 100.0;                 // farthest plane of stage A behind the field exit (spider: 85 mm)
+  const double delta = std::max(f.dzExitCB, 1.0);                // zExitCB - lengthB: the base of the reference's extrapolation
+  const double lever = std::max(L / delta, 1.0);
+  const double D = f.testXray ? std::fabs(f.lengthB - f.srcZ) : f.sunDist;
+  const double kRef = 1.5 * 4.440892098500626e-16 * D;           // (3), per unit (|sx| + |sy|), safety 1.5
+  const double kSamp = f.testXray ? 0.0 : 2e-6 * f.radiusSun / f.sunDist;   // (2) direction, per unit rs, safety 2
+  const double tolE = f.testXray ? 16.0 * eps * (f.radiusCB + f.srcRadius) * (1.0 + L / std::max(D, 1.0))
+                                 : 16.0 * eps * f.radiusCB;      // (2) exit-disc point
+  const double rot = f.rotated ? 2.0 : 1.0;                      // the frame rotation doubles the rounding steps
+  t->latA = float(scale * rot * (tolE + 8.0 * eps * rmax));
+  t->latS = float(scale * kSamp * L);
+  t->latT = float(scale * (kRef * lever + 4.0 * eps * L));
+  t->latTpre = float(scale * 4.0 * eps * L);
+  t->latRef = float(scale * 1.5 * lever);
+  // entrance plane: the slope terms act over lengthB instead of L, the reference's noise enters without the lever
+  t->entK = float(std::max(1.0, std::fabs(f.lengthB) / L));
+  // At the detector the optic maps directions to positions (position = focal length x angle; a lateral shift of the
+  // incoming ray does not move its image), so the budget is the direction error times the distance fl to the detector:
+  // ~6 rounding steps of eps |v_lateral| through the two reflections (measured against 60-digit arithmetic: 4e-5 mm on
+  // CAST+LLNL, 1.1e-4 mm on BabyIAXO+XMM; budgeted 4x), the slope errors (2) and (3), and the aperture-plane budget once.
+  const double vlat = 1.4 * tanMax + 0.005;                      // lateral direction components after two reflections (~4 beta)
+  const double fl = focal + f.lMirror * 2.0;
+  t->detA = float(scale * rot * (24.0 * eps * vlat * fl + tolE + 8.0 * eps * rmax));
+  t->detS = float(scale * kSamp * fl);
+  t->detT = float(scale * (kRef * fl / delta + 4.0 * eps * fl));
+  t->detTpre = float(scale * 4.0 * eps * fl);
+  t->detRef = float(scale * 1.5 * fl / delta);
+  t->rho = float(scale * 4.0 * eps * r1max);
+  t->circ2 = float(scale * 8.0 * eps);
+  t->spider = float(scale * 512.0 * eps);
+  t->cond = float(scale * 2e-15);
+  t->zrel = float(scale * 16.0 * eps);
+  t->ang = float(scale * 2e-5);
+  t->sinA = float(scale * 8.0 * eps * (4.0 * tanMax + 0.01));
+  t->circCB = float(t->circ2 * f.radiusCB2);
+  t->circPipe = float(t->circ2 * f.rPipe12);
+  t->circWin = float(t->circ2 * f.radiusWindow2);
+  t->angLo = f.angleMax - t->ang;
+  {
+    double gap = 0.0;
+    for (int j = 1; j < nShells; ++j) gap = std::max(gap, a[j].R1 - a[j - 1].R1pT);
+    t->nick = float(t->sinA * f.lMirror + t->zrel * gap);
+  }
+  t->twoRcb = float(2.0 * f.radiusCB);
+  t->twoRpipe = float(2.0 * rPipe);
+  t->twoRwin = float(2.0 * std::sqrt(f.radiusWindow2));
+  t->chipInside = (std::min(f.chipCX, f.chipCY) < std::sqrt(f.radiusWindow2) * 1.001 + 4.0 * t->detA) ? 1 : 0;
+}
+
 // Single-precision blocks of precision mode 2, rounded from the FP64 ones.
-void derive_f32(const FastParams& f, const ShellFast* a, int nShells, Geo32* g, ShellF32* out) {
+void derive_f32(const FastParams& f, const ShellFast* a, int nShells, Geo32* g, ShellF32* out, float tolScale) {
   std::memset(g, 0, sizeof *g);
+  derive_tolerances(f, a, nShells, tolScale, &g->tol);
+  g->depthOverCos = float(f.depthOverCos);
   g->radiusCB = float(f.radiusCB); g->radiusCB2 = float(f.radiusCB2); g->lengthB = float(f.lengthB);
   g->lengthB2 = float(f.lengthB * f.lengthB); g->lengthBplusSun = float(f.lengthB + f.sunDist); g->radiusSun = float(f.radiusSun);
   g->dzExitCB = float(f.dzExitCB); g->dzPipe1 = float(f.dzPipe1); g->dzPipe2 = float(f.dzPipe2); g->rPipe12 = float(f.rPipe12);
@@ -101,6 +174,10 @@ void derive_f32(const FastParams& f, const ShellFast* a, int nShells, Geo32* g, 
     o.p_e = float(s.p_e); o.p_R0 = float(std::sqrt(std::max(s.p_c0, 0.0))); o.p_r3sq = float(s.p_r3sq); o.p_r3tan = float(s.p_r3tan);
     o.h_e = float(s.h_e); o.h_g = float(s.h_g); o.h_r3sq = float(s.h_r3sq); o.h_r3tan = float(s.h_r3tan);
     o.h_inv_nden = float(s.h_inv_nden); o.coat = s.coat;
+    o.zmid1 = float(0.5 * s.zmax1); o.zhalf1 = float(0.5 * s.zmax1);
+    o.zmid2 = float(0.5 * (s.dm + s.zmax2)); o.zhalf2 = float(0.5 * (s.zmax2 - s.dm));
+    o.twoR = 2.0f * (f.telKind == SART_TK_XMM || f.telKind == SART_TK_ABRIXAS ? o.p_R0 : o.R1);
+    o.tan2p = float(std::fabs(s.tan2) + 0.01);
   }
 }
 
@@ -236,6 +313,22 @@ bool build_shell_table(const Geo32& g, const ShellF32* sh, int nS, int nBuckets,
     c.sel = uint32_t(below) | (uint32_t(at) << 8) | (uint32_t(above) << 16);
     cur = above;
   }
+  // Boundary-free buckets carry the nearest boundary of a neighbouring bucket as B (all three outcomes are the same, so
+  // the lookup does not change): the kernel's margin test |rho - B| <= budget then also sees a boundary that sits just
+  // across the bucket's edge. Buckets are at most half the smallest boundary distance wide, so one B per bucket suffices
+  // for budgets below a quarter of a bucket.
+  for (int b = 1; b < nBuckets; ++b) {
+    if (owner[size_t(b)] >= 0) continue;
+    const float lo = g.shellRhoMin + float(b) / g.shellInvStep, hi = g.shellRhoMin + float(b + 1) / g.shellInvStep;
+    float best = -INFINITY, bestDist = INFINITY;
+    for (int nb = std::max(1, b - 2); nb <= std::min(nBuckets - 1, b + 2); ++nb) {
+      if (owner[size_t(nb)] < 0) continue;
+      const float B = bnd[size_t(owner[size_t(nb)])];
+      const float d = B < lo ? lo - B : (B > hi ? B - hi : 0.0f);
+      if (d < bestDist) { bestDist = d; best = B; }
+    }
+    (*out)[size_t(b)].B = best;
+  }
   return true;
 }
 
@@ -270,6 +363,7 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   f->cosTheta = P.cosTheta; f->sinTheta = P.sinTheta;
   f->stripDist = P.stripDist; f->stripWidth = P.stripWidth;
   f->invStripPitch = 1.0 / (P.stripDist + P.stripWidth);
+  f->depthOverCos = s.detector.depthDet / P.cosPipe;
   f->invBinX = double(SART_IMAGE_BINS) / (2.0 * P.chipCX);
   f->invBinY = double(SART_IMAGE_BINS) / (2.0 * P.chipCY);
   f->sunDist = s.consts.distanceSunEarth;
@@ -312,9 +406,18 @@ static void lut_entry(double E, const sart_interp1d_t& sb, const sart_interp1d_t
   // A transmission that is non-zero in f64 must stay non-zero in the f32 table: `passed` means weight != 0
   // (rt:2220), and e.g. 200 um of Si transmit 1e-60 at 0.3 keV.
   auto f32nz = [](double v) { return (v != 0.0 && std::fabs(v) < 1.2e-38) ? float(std::copysign(1.2e-38, v)) : float(v); };
-  e->E = float(E);
   e->Twindow = f32nz(lin1d(wd, E));
-  e->Tstrongback = f32nz(lin1d(sb, E));
+  {
+    const double t = lin1d(sb, E);
+    int ex = 0;
+    if (t != 0.0 && std::fabs(t) < 1e-30) {   // mantissa in [0.5, 1) as the FP32 value, the exponent beside it
+      const double m = std::frexp(t, &ex);
+      e->Tstrongback = float(m);
+    } else {
+      e->Tstrongback = float(t);
+    }
+    e->sbExp = ex;
+  }
   e->Agas = f32nz(lin1d(ga, E));
   const double lma = -1.5832 + 5.9195 * std::exp(-0.353808 * E) + 4.03598 * std::exp(-0.970557 * E);
   g->massAtt = float(std::exp(lma));

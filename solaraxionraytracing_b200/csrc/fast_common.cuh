@@ -74,7 +74,18 @@ __device__ __forceinline__ void rad_add(const RadialHist& h, double r, double w)
 }
 
 // ---- shared memory layout -----------------------------------------------------------------------------------
-struct WarpCounters { unsigned int n_exit[16]; unsigned int n_clamped; unsigned int pad[3]; };
+struct WarpCounters { unsigned int n_exit[16]; unsigned int n_clamped; unsigned int n_unresolved; unsigned int pad[2]; };
+
+// ---- re-trace queue (fast_params.h: RetraceQueue) ------------------------------------------------------------------
+// 1: queued (the exact pipeline will trace the ray and account for it), 2: the queue is full (the ray keeps its FP32
+// outcome and is counted as unresolved), 0: re-tracing is off.
+__device__ __forceinline__ int rq_push(const RetraceQueue& q, uint32_t id) {
+  if (q.cap == 0u) return 0;
+  const uint32_t slot = atomicAdd(q.count, 1u);
+  if (slot < q.cap) { q.list[slot] = id; return 1; }
+  return 2;
+}
+constexpr int kCodeDeferred = 0x40;   // RayResult::code of a ray that went to the re-trace queue (mass scan)
 
 // lowerBound restricted to the guide window [lo, hi]
 __device__ __forceinline__ int lower_bound_window(const double* __restrict__ a, int lo, int hi, double key) {
@@ -143,13 +154,20 @@ struct RayResult {
   int bin;        // image bin or -1
   int shell;
   bool windowMiss, clamped;
-  float energy;
   double wPre;    // reflectivity * cos(yaw) * He absorption        (everything before the window, without P(a->gamma))
   double wPost;   // window or strongback * detector gas * exposure (0 when the window aperture is missed)
   double x, y, r;
   // conversion probability pieces: vacuum convVac = (g B L / 2)^2; gas: Gamma, L, exp(-Gamma L), exp(-Gamma L/2), 1/(2E)
   float convVac, gasGamma, gasE1, gasE2, gasInv2E;
   double gasL;
+  // the rest of the Axion record (rt:192-221) for the per-ray entry points; dead code in the fused kernels
+  int eIdx;                 // index of the tabulated energy (the X-ray source energy sits at nEnergies)
+  double refl;              // reflect rt:2126
+  float pre;                // cos(yaw) * He absorption: transmissionMagnet = pre * conversion probability rt:2120
+  float yaw, a1, a2;        // yawAngles rt:2123, grazing angles [deg]
+  float path;               // pathCB rt:1843
+  float devDet;             // deviationDet rt:2085
+  float agas;               // transProbArgon rt:2193
 };
 
 // Conversion probability for axion mass^2 m2 (computeMagnetTransmission rt:1582-1625 without the cos(ya) factor).
@@ -178,15 +196,54 @@ __device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& 
   return ((w != 0.0) ? SART_EXIT_PASSED : SART_EXIT_ZERO_WEIGHT) | flags;
 }
 
+// The Axion record (rt:192-221) of one ray of the throughput pipelines, written to the structure of arrays `o` (device
+// pointers). Fields of the weight stage (reflect, transmissionMagnet, yawAngles, the grazing angles, pathCB, deviationDet)
+// are defined for the rays that reach it — exit codes PASSED, ZERO_WEIGHT, WINDOW_APERTURE, which is every ray
+// generateResultPlots (rt:2246-2289) reads them from — and 0 for rays clipped before; x, y, r, shellNumber and
+// transProbArgon for the rays past the window aperture, like the exact pipeline (kernels_exact.cu: store_ray).
+__device__ __forceinline__ void store_record(const FastParams& P, const sart_ray_out_t& o, size_t i, const RayResult& r,
+                                             double m2, double energyKeV) {
+  int code = r.code;
+  double wd = 0.0;
+  const bool weighted = r.code < 0;
+  if (weighted) code = finish_ray<true>(P, r, m2, wd);
+  else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
+  const int ec = code & SART_CODE_MASK;
+  const bool tail = ec == SART_EXIT_PASSED || ec == SART_EXIT_ZERO_WEIGHT;
+  o.x[i] = tail ? r.x : 0.0; o.y[i] = tail ? r.y : 0.0; o.w[i] = wd; o.code[i] = code; o.shell[i] = tail ? r.shell : -1;
+  if (o.energy) o.energy[i] = energyKeV;
+  if (o.reflect) o.reflect[i] = weighted ? r.refl : 0.0;
+  if (o.transMagnet)
+    o.transMagnet[i] = weighted ? double(r.pre) * conv_factor(P, r.convVac, r.gasGamma, r.gasE1, r.gasE2, r.gasInv2E, r.gasL, m2) : 0.0;
+  if (o.yaw) o.yaw[i] = weighted ? double(r.yaw) : 0.0;
+  if (o.alpha1) o.alpha1[i] = weighted ? double(r.a1) : 0.0;
+  if (o.alpha2) o.alpha2[i] = weighted ? double(r.a2) : 0.0;
+  if (o.pathCB) o.pathCB[i] = weighted ? double(r.path) : 0.0;
+  if (o.r) o.r[i] = tail ? r.r : 0.0;
+  if (o.deviationDet) o.deviationDet[i] = weighted ? double(r.devDet) : 0.0;
+  if (o.transProbArgon) o.transProbArgon[i] = tail ? double(r.agas) : 0.0;
+}
+
 // Sink that keeps the outcome as a RayResult (per-ray records, mass scan).
 template <bool kFoldT>
 struct RecordSink {
   static constexpr bool kFold = kFoldT;
   RayResult& out;
   double m2;
+  const RetraceQueue& rq;
+  bool dropDeferred;   // mass scan: a queued ray is dropped here (code = kCodeDeferred); the per-ray entry points write the
+                       // FP32 record anyway and the exact pipeline overwrites it
+  bool unresolved = false;
+  __device__ __forceinline__ bool defer(uint32_t id) {
+    const int r = rq_push(rq, id);
+    unresolved |= (r == 2);
+    if (r == 1 && dropDeferred) { fail(kCodeDeferred); return true; }
+    return false;
+  }
   __device__ __forceinline__ void fail(int code) {
-    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1; out.energy = 0.f;
+    out.code = code; out.clamped = false; out.windowMiss = false; out.bin = -1; out.shell = -1;
     out.x = out.y = out.r = 0.0; out.wPre = out.wPost = 0.0;
+    out.refl = 0.0; out.pre = out.yaw = out.a1 = out.a2 = out.devDet = out.agas = 0.f;
   }
   __device__ __forceinline__ void hit(const RayResult& h) { out = h; out.code = -1; }
 };
@@ -207,6 +264,11 @@ struct ImageSinkT {
   WarpCounters& wc;
   unsigned int &nPassed, &nTill;
   double &sumW, &sumW2, &sumX, &sumY, &sumR;
+  __device__ __forceinline__ bool defer(uint32_t id) {
+    const int r = rq_push(T.rq, id);
+    if (r == 2) atomicAdd(&wc.n_unresolved, 1u);
+    return r == 1;
+  }
   __device__ __forceinline__ void fail(int code) { atomicAdd(&wc.n_exit[code], 1u); }
   __device__ __forceinline__ void hit(const RayResult& h) {
     const double w0 = h.wPre;   // conversion probability already folded in
@@ -238,8 +300,8 @@ using ImageSink = ImageSinkT<true>;
 // the per-mass sums live in registers of the lane that owns the mass and need no reduction. `image` / `imageW2` are the
 // mass-major accumulators [bin][SART_MAX_MASSES] (see k_fold_mass_acc).
 template <class Trace>
-__device__ __forceinline__ void mass_scan_loop(const FastParams& P, const double* __restrict__ masses, int nMasses,
-                                               uint64_t first, uint64_t nRays, double* __restrict__ image,
+__device__ __forceinline__ void mass_scan_loop(const FastParams& P, const RadialHist& rad, const double* __restrict__ masses,
+                                               int nMasses, uint64_t first, uint64_t nRays, double* __restrict__ image,
                                                double* __restrict__ imageW2, sart_counters_t* __restrict__ counters,
                                                WarpCounters* wc, Trace trace) {
   constexpr int kPer = SART_MAX_MASSES / 32;
@@ -263,9 +325,10 @@ __device__ __forceinline__ void mass_scan_loop(const FastParams& P, const double
     RayResult r;
     r.code = SART_N_EXIT_CODES;
     if (valid) {
-      trace(first + i, r);
+      if (trace(first + i, uint32_t(i), r)) atomicAdd(&wc[warp].n_unresolved, 1u);
       ++nIter;
-      if (r.code >= 0) atomicAdd(&wc[warp].n_exit[r.code], 1u);
+      if (r.code == kCodeDeferred) { r.clamped = false; }   // queued for the exact pipeline, which accounts for it
+      else if (r.code >= 0) atomicAdd(&wc[warp].n_exit[r.code], 1u);
       else if (r.windowMiss) atomicAdd(&wc[warp].n_exit[SART_EXIT_WINDOW_APERTURE], 1u);
       if (r.clamped) atomicAdd(&wc[warp].n_clamped, 1u);
     }
@@ -298,6 +361,7 @@ __device__ __forceinline__ void mass_scan_loop(const FastParams& P, const double
             atomicAdd(image + size_t(bin) * SART_MAX_MASSES + m, w);
             atomicAdd(imageW2 + size_t(bin) * SART_MAX_MASSES + m, w * w);
           }
+          if (m == 0 && rad.w) rad_add(rad, rr, w);   // the radial histogram follows the first mass, as in the exact kernel
         } else {
           ++nZero[k];
         }
@@ -323,6 +387,7 @@ __device__ __forceinline__ void mass_scan_loop(const FastParams& P, const double
       if (e != SART_EXIT_ZERO_WEIGHT) addu(&c->n_exit[e], wc[warp].n_exit[e]);
     addu(&c->n_hit_nickel, wc[warp].n_exit[SART_EXIT_NICKEL]);
     addu(&c->n_interp_clamped, wc[warp].n_clamped);
+    addu(&c->n_unresolved, wc[warp].n_unresolved);
     atomicAdd(&c->sum_w, sumW[k]); atomicAdd(&c->sum_w2, sumW2[k]);
     atomicAdd(&c->sum_x, sumX[k]); atomicAdd(&c->sum_y, sumY[k]); atomicAdd(&c->sum_r, sumR[k]);
   }

@@ -18,9 +18,11 @@ struct ShellFast {
   // Wolter-I
   double p_e, p_c0, p_r3sq, p_r3tan;                       // paraboloid: rho^2 = r3^2 + e (l - z); c0 = r3^2 + e l
   double h_e, h_g, h_r3sq, h_r3tan, h_inv_nden;            // hyperboloid: rho^2 = r3^2 + e (l-z) + g (l-z)^2
-  int32_t coat;   // reflectivity table of this shell: layers.lowerBound(hitLayer) (rt:1573)
+  int32_t coat;   // reflectivity table of this shell: layers.lowerBound(hitLayer) (rt:1573) in bits 0..7; bit 8: the
+                  // lower bound ran past the last coating (the reference would raise; the exact pipeline clamps and flags)
   int32_t pad_;
 };
+constexpr int kCoatMask = 0xff, kCoatClamped = 0x100;
 static_assert(sizeof(ShellFast) % 16 == 8, "odd number of doubles keeps shared-memory rows off the same banks");
 
 struct FastParams {
@@ -31,6 +33,7 @@ struct FastParams {
   double radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invStripPitch, invBinX, invBinY;
   double sunDist, radiusSun, radiusCB;
   double shellRhoMin, shellInvStep;   // uniform radial grid -> first candidate shell (shellGuide)
+  double depthOverCos;                // depthDet / cos(pipesTurned): distance of the second detector plane (deviationDet rt:2081-2085)
   // weights (FP32)
   float convK;         // (g*1e-9 * B*T2eV2 * 1e-3*m2eV / 2)^2: conversionProb = convK * pathCB^2 (rt:363-365)
   float exposure;
@@ -57,8 +60,40 @@ struct ShellF32 {
   float p_e, p_R0, p_r3sq, p_r3tan;                        // p_R0 = sqrt(r3^2 + e l): paraboloid radius at z = 0
   float h_e, h_g, h_r3sq, h_r3tan, h_inv_nden;
   int32_t coat;
+  // the z intervals of the two mirrors as centre and half length ("hit" is |z - mid| < half, its margin ||z - mid| - half|),
+  // and two per-shell factors of the error budgets (kernels_f32.cu)
+  float zmid1, zhalf1, zmid2, zhalf2;
+  float twoR;     // 2 R of mirror 1 at z = 0 (R1, or p_R0 for a paraboloid): budget of C = twoR * budget of rho
+  float tan2p;    // tan(3 beta) + 0.01: how fast the gap between the ray and mirror 2 changes along z
 };
-static_assert(sizeof(ShellF32) == 92, "23 words: an odd stride keeps shared-memory rows off the same banks");
+static_assert(sizeof(ShellF32) == 116, "29 words: an odd stride keeps shared-memory rows off the same banks");
+
+// ---- error budgets of the FP32 decisions (derive_fast.cpp: derive_tolerances). Every hit/miss
+// decision of the FP32 pipeline has a margin (rho^2 - R^2, the discriminant, z - z_end, ...). A margin inside the budget
+// of what FP32 rounding, the fast sampling arithmetic and the reference's own f64 rounding noise can move makes the ray
+// "uncertain": it is handed to the exact FP64 pipeline (trace_exact.cuh) through the re-trace queue, so that the
+// classification of every ray is the exact pipeline's. All budgets carry the handle's retrace scale (sart_set_retrace;
+// 0 = pure FP32).
+struct Tol32 {
+  float latA, latS, latT;            // lateral position budget before the mirrors [mm], Monte Carlo rays:
+                                     //   latA + latS rs + latT (|sx| + |sy|)   (rs = emission radius / solar radius)
+  float latTpre, latRef;             // pre-sampled rays: latA + latTpre (|sx| + |sy|) + latRef epsO, epsO = the rounding
+                                     //   noise of the reference's line through the caller's origin (kernels_f32.cu)
+  float entK;                        // budget of the bore entrance test (z = 0, intersected separately by the reference) / budget of the other planes
+  float detA, detS, detT, detTpre, detRef;   // the same at the detector plane
+  float rho;                         // + rounding of a radial distance at the telescope entrance
+  float circ2;                       // |rho^2 - R^2| < 2 R lat + circ2 R^2
+  float circCB, circPipe, circWin;   // circ2 R^2 for the bore, the pipes and the detector window
+  float angLo;                       // angleMax - ang: grazing angles from here on touch the end of the reflectivity grid
+  float nick;                        // rounding part of the nickel test's budget: sinA lMirror + zrel (largest shell gap)
+  float spider;                      // rounding of the Chebyshev spider polynomial (in units of cos(n phi))
+  float cond;                        // the reference's quadratic formula loses hb^2 / |A C| digits (rt:646-658): dz |q| += cond hb^2 / |A|
+  float zrel;                        // relative rounding of a root
+  float ang;                         // grazing angle against the end of the reflectivity grid [deg]
+  float sinA;                        // absolute rounding of sin(alpha)
+  float twoRcb, twoRpipe, twoRwin;   // 2 R of the squared-radius compares
+  int32_t chipInside;                // the chip edge can cut inside the window aperture (else the aperture decides alone)
+};
 
 struct Geo32 {
   float radiusCB, radiusCB2, lengthB, lengthB2, lengthBplusSun, radiusSun;
@@ -68,6 +103,17 @@ struct Geo32 {
   float radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invStripPitch, invBinX, invBinY;
   float shellRhoMin, shellInvStep;
   float srcX, srcY, srcRadius, srcRadius2, invSrcDz, colDz;
+  float depthOverCos;   // ddEnd - ddWin = depthDet / cos(pipesTurned): the second detector plane of deviationDet (rt:2081-2085)
+  Tol32 tol;
+};
+
+// Re-trace queue of a launch: offsets (ray index - first ray of the launch) of the uncertain rays. count[0] counts the
+// pushes (it may run past cap: the pushes beyond cap are refused and the ray keeps its FP32 outcome, counted in
+// sart_counters_t::n_unresolved).
+struct RetraceQueue {
+  uint32_t* list;
+  uint32_t* count;
+  uint32_t cap, pad;
 };
 
 // Radial lookup of the shell search (rt:1932-1957) for the FP32 kernels: the radial buckets of the shell guide are fine
@@ -81,7 +127,10 @@ struct ShellCell {
 constexpr int kShellCellFail = 64;
 
 struct EnergyLUT {  // one record per tabulated energy index (16 B, one LDG.128)
-  float E, Twindow, Tstrongback, Agas;
+  // strongback transmission = Tstrongback * 2^sbExp: 200 um of silicon transmit 1e-60 at 0.9 keV, far below the FP32
+  // range, and a weight must keep its value there, not only its non-zeroness. sbExp = 0 wherever FP32 holds the value.
+  int32_t sbExp;
+  float Twindow, Tstrongback, Agas;
 };
 struct GasLUT {     // buffer-gas stage only
   float massAtt;   // exp(logMassAttenuation(E)) am:70-73
@@ -121,6 +170,7 @@ struct FastTables {
   // launch on a few hundred bins; spreading them over replicas removes the same-address serialisation in L2.
   int32_t nImgRep, pad_;
   uint64_t imgRepStride;
+  RetraceQueue rq;            // cap == 0: re-tracing off
 };
 
 }  // namespace fast

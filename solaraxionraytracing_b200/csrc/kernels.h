@@ -18,6 +18,16 @@ cudaError_t launch_mc_rays_exact(const Params& P, const Tables& T, double mAxion
 cudaError_t launch_mc_image_exact(const Params& P, const Tables& T, int nMasses, const double* masses, uint64_t first,
                                   uint64_t nRays, uint64_t seed, double* image, double* imageW2,
                                   sart_counters_t* counters, int smCount, cudaStream_t s);
+// re-trace of the uncertain rays of an FP32 launch (fast_params.h: RetraceQueue) by the exact pipeline
+cudaError_t launch_retrace_mc_image(const Params& P, const Tables& T, int nMasses, const double* masses, uint64_t first,
+                                    uint64_t seed, const fast::RetraceQueue& q, double* image, double* imageW2,
+                                    sart_counters_t* counters, int smCount, cudaStream_t s);
+cudaError_t launch_retrace_mc_rays(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n, uint64_t seed,
+                                   const uint32_t* words, const fast::RetraceQueue& q, const sart_ray_out_t& out, int smCount,
+                                   cudaStream_t s);
+cudaError_t launch_retrace_presampled(const Params& P, const Tables& T, double mAxion, size_t n, const double* origin,
+                                      const double* exitxy, const double* energy, const fast::RetraceQueue& q,
+                                      const sart_ray_out_t& out, int smCount, cudaStream_t s);
 cudaError_t launch_build_cdfs(int nR, int nE, const double* radii, const double* energies, const double* emRates,
                               double* rowTotals, double* cdfs, double* radiusCDF, cudaStream_t s);
 

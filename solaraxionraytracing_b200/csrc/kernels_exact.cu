@@ -67,12 +67,27 @@ k_trace_presampled(const __grid_constant__ Params P, const __grid_constant__ Tab
   trace_and_store(P, T, mAxion, O, E, energy[i], 0, out, i);
 }
 
+// ---- re-trace kernels: the rays of a launch of the FP32 pipeline (kernels_f32.cu) whose decision margins were inside
+// their error budgets, listed as offsets into the launch. Grid-stride over min(*count, cap) entries: the count is read on
+// the device, so the host queues these launches without a synchronisation.
 __global__ void __launch_bounds__(128)
-k_trace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, uint64_t first,
-                size_t n, uint64_t seed, const uint32_t* __restrict__ words, int32_t* __restrict__ emit,
-                const __grid_constant__ RayOutDev out) {
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+k_retrace_presampled(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, size_t n,
+                     const double* __restrict__ origin, const double* __restrict__ exitxy,
+                     const double* __restrict__ energy, const uint32_t* __restrict__ list,
+                     const uint32_t* __restrict__ count, uint32_t cap, const __grid_constant__ RayOutDev out) {
+  const uint32_t m = min(*count, cap);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    const size_t i = list[j];
+    if (i >= n) continue;
+    const V3 O = {origin[i], origin[n + i], origin[2 * n + i]};
+    const V3 E = {exitxy[i], exitxy[n + i], P.lengthB};
+    trace_and_store(P, T, mAxion, O, E, energy[i], 0, out, i);
+  }
+}
+
+__device__ __forceinline__ void mc_ray_record(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n,
+                                              uint64_t seed, const uint32_t* __restrict__ words, int32_t* __restrict__ emit,
+                                              const RayOutDev& out, size_t i) {
   V3 O, E;
   double energy;
   int clamped = 0;
@@ -100,6 +115,26 @@ k_trace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tables
   trace_and_store(P, T, mAxion, O, E, energy, clamped, out, i);
 }
 
+__global__ void __launch_bounds__(128)
+k_trace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, uint64_t first,
+                size_t n, uint64_t seed, const uint32_t* __restrict__ words, int32_t* __restrict__ emit,
+                const __grid_constant__ RayOutDev out) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  mc_ray_record(P, T, mAxion, first, n, seed, words, emit, out, i);
+}
+
+__global__ void __launch_bounds__(128)
+k_retrace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, uint64_t first,
+                  size_t n, uint64_t seed, const uint32_t* __restrict__ words, const uint32_t* __restrict__ list,
+                  const uint32_t* __restrict__ count, uint32_t cap, const __grid_constant__ RayOutDev out) {
+  const uint32_t m = min(*count, cap);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    const size_t i = list[j];
+    if (i < n) mc_ray_record(P, T, mAxion, first, n, seed, words, nullptr, out, i);
+  }
+}
+
 // ---- fused Monte Carlo run -------------------------------------------------------------------------------
 // Block-level counters live in shared memory and are flushed once per block.
 struct BlockCounters {
@@ -112,9 +147,65 @@ struct MassCounters {
   double sum_w, sum_w2, sum_x, sum_y, sum_r;
 };
 
+// One ray of the fused run: sample, trace, weight for every axion mass, histogram (rt:1736-2221 + 818-842).
+__device__ __forceinline__ void mc_image_ray(const Params& P, const Tables& T, int nMasses, const double* __restrict__ masses,
+                                             uint64_t seed, uint64_t ray, double* __restrict__ image,
+                                             double* __restrict__ imageW2, BlockCounters* bc, MassCounters* mc) {
+  const double step = (P.chipCX * 2.0 - 0.0) / double(SART_IMAGE_BINS);  // (stop - start)/rows rt:828-830
+  const double stepY = (P.chipCY * 2.0 - 0.0) / double(SART_IMAGE_BINS);
+  V3 O, E;
+  double energy;
+  int clamped = 0;
+  if (!sample_ray(P, T, seed, ray, O, E, energy, clamped)) {
+    atomicAdd(&bc->n_exit[SART_EXIT_COLLIMATOR], 1ull);
+    return;
+  }
+  Geo g;
+  trace_geometry<false>(P, T, O, E, energy, g);
+  g.clamped |= clamped;
+  if (g.code >= 0) {
+    atomicAdd(&bc->n_exit[g.code], 1ull);
+    if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
+    return;
+  }
+  Weights w;
+  ray_weights(P, T, g, w);
+  if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
+  if (g.windowMiss) atomicAdd(&bc->n_exit[SART_EXIT_WINDOW_APERTURE], 1ull);
+  for (int m = 0; m < nMasses; ++m) {
+    Final f;
+    ray_finish(P, g, w, masses[m], f);
+    if (f.code & SART_FLAG_PASSED_TILL_WINDOW) atomicAdd(&mc[m].n_till_window, 1ull);
+    const int code = f.code & SART_CODE_MASK;
+    if (code == SART_EXIT_ZERO_WEIGHT) atomicAdd(&mc[m].n_zero, 1ull);
+    if (code != SART_EXIT_PASSED) continue;
+    atomicAdd(&mc[m].n_passed, 1ull);
+    atomicAdd(&mc[m].sum_w, f.w);
+    atomicAdd(&mc[m].sum_w2, f.w * f.w);
+    atomicAdd(&mc[m].sum_x, f.x);
+    atomicAdd(&mc[m].sum_y, f.y);
+    atomicAdd(&mc[m].sum_r, f.r);
+    // prepareHeatmap rt:839-842
+    const double cx = floor((f.x - 0.0) / step), cy = floor((f.y - 0.0) / stepY);
+    if (cx >= 0.0 && cx < double(SART_IMAGE_BINS) && cy >= 0.0 && cy < double(SART_IMAGE_BINS)) {
+      const size_t bin = size_t(m) * SART_IMAGE_BINS * SART_IMAGE_BINS + size_t(int(cy)) * SART_IMAGE_BINS + size_t(int(cx));
+      atomicAdd(image + bin, f.w);
+      atomicAdd(imageW2 + bin, f.w * f.w);
+    }
+    if (T.rad.w && m == 0) {
+      int b = int(f.r * T.rad.invStep);
+      b = b < 0 ? 0 : (b > T.rad.nbins - 1 ? T.rad.nbins - 1 : b);
+      atomicAdd(T.rad.w + b, f.w);
+      atomicAdd(T.rad.n + b, 1ull);
+    }
+  }
+}
+
+// `list` != nullptr: trace the rays first + list[j], j < min(*listCount, listCap), instead of first + [0, nRays).
 __global__ void __launch_bounds__(128)
 k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Tables T, int nMasses,
                  const double* __restrict__ masses, uint64_t first, uint64_t nRays, uint64_t seed,
+                 const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount, uint32_t listCap,
                  double* __restrict__ image, double* __restrict__ imageW2, sart_counters_t* __restrict__ counters) {
   extern __shared__ unsigned char smem_raw[];
   BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem_raw);
@@ -125,56 +216,17 @@ k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Table
     reinterpret_cast<unsigned long long*>(mc)[k] = 0ull;
   __syncthreads();
 
-  const double step = (P.chipCX * 2.0 - 0.0) / double(SART_IMAGE_BINS);  // (stop - start)/rows rt:828-830
-  const double stepY = (P.chipCY * 2.0 - 0.0) / double(SART_IMAGE_BINS);
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nRays; i += stride) {
-    V3 O, E;
-    double energy;
-    int clamped = 0;
-    atomicAdd(&bc->n_rays, 1ull);
-    if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped)) {
-      atomicAdd(&bc->n_exit[SART_EXIT_COLLIMATOR], 1ull);
-      continue;
-    }
-    Geo g;
-    trace_geometry<false>(P, T, O, E, energy, g);
-    g.clamped |= clamped;
-    if (g.code >= 0) {
-      atomicAdd(&bc->n_exit[g.code], 1ull);
-      if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
-      continue;
-    }
-    Weights w;
-    ray_weights(P, T, g, w);
-    if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
-    if (g.windowMiss) atomicAdd(&bc->n_exit[SART_EXIT_WINDOW_APERTURE], 1ull);
-    for (int m = 0; m < nMasses; ++m) {
-      Final f;
-      ray_finish(P, g, w, masses[m], f);
-      if (f.code & SART_FLAG_PASSED_TILL_WINDOW) atomicAdd(&mc[m].n_till_window, 1ull);
-      const int code = f.code & SART_CODE_MASK;
-      if (code == SART_EXIT_ZERO_WEIGHT) atomicAdd(&mc[m].n_zero, 1ull);
-      if (code != SART_EXIT_PASSED) continue;
-      atomicAdd(&mc[m].n_passed, 1ull);
-      atomicAdd(&mc[m].sum_w, f.w);
-      atomicAdd(&mc[m].sum_w2, f.w * f.w);
-      atomicAdd(&mc[m].sum_x, f.x);
-      atomicAdd(&mc[m].sum_y, f.y);
-      atomicAdd(&mc[m].sum_r, f.r);
-      // prepareHeatmap rt:839-842
-      const double cx = floor((f.x - 0.0) / step), cy = floor((f.y - 0.0) / stepY);
-      if (cx >= 0.0 && cx < double(SART_IMAGE_BINS) && cy >= 0.0 && cy < double(SART_IMAGE_BINS)) {
-        const size_t bin = size_t(m) * SART_IMAGE_BINS * SART_IMAGE_BINS + size_t(int(cy)) * SART_IMAGE_BINS + size_t(int(cx));
-        atomicAdd(image + bin, f.w);
-        atomicAdd(imageW2 + bin, f.w * f.w);
-      }
-      if (T.rad.w && m == 0) {
-        int b = int(f.r * T.rad.invStep);
-        b = b < 0 ? 0 : (b > T.rad.nbins - 1 ? T.rad.nbins - 1 : b);
-        atomicAdd(T.rad.w + b, f.w);
-        atomicAdd(T.rad.n + b, 1ull);
-      }
+  if (list) {   // re-trace of the uncertain rays of an FP32 launch, which has counted them in n_rays already
+    const uint32_t nList = min(*listCount, listCap);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nList; j += uint32_t(stride))
+      mc_image_ray(P, T, nMasses, masses, seed, first + list[j], image, imageW2, bc, mc);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (int m = 0; m < nMasses; ++m) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[m].n_retraced), (unsigned long long)nList);
+  } else {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nRays; i += stride) {
+      atomicAdd(&bc->n_rays, 1ull);
+      mc_image_ray(P, T, nMasses, masses, seed, first + i, image, imageW2, bc, mc);
     }
   }
   __syncthreads();
@@ -291,7 +343,32 @@ cudaError_t launch_mc_image_exact(const Params& P, const Tables& T, int nMasses,
   uint64_t want = (nRays + block - 1) / block;
   uint64_t cap = uint64_t(smCount) * perSM;  // one resident wave; the grid-stride loop covers the rest
   const unsigned grid = unsigned(want < cap ? want : cap);
-  k_trace_mc_image<<<grid, block, smem, s>>>(P, T, nMasses, masses, first, nRays, seed, image, imageW2, counters);
+  k_trace_mc_image<<<grid, block, smem, s>>>(P, T, nMasses, masses, first, nRays, seed, nullptr, nullptr, 0u, image, imageW2,
+                                             counters);
+  return cudaGetLastError();
+}
+
+// ---- re-trace launchers (fixed grids: the list length lives on the device) -------------------------------------
+cudaError_t launch_retrace_mc_image(const Params& P, const Tables& T, int nMasses, const double* masses, uint64_t first,
+                                    uint64_t seed, const fast::RetraceQueue& q, double* image, double* imageW2,
+                                    sart_counters_t* counters, int smCount, cudaStream_t s) {
+  const int block = 128;
+  const size_t smem = sizeof(BlockCounters) + size_t(nMasses) * sizeof(MassCounters);
+  k_trace_mc_image<<<unsigned(smCount) * 4u, block, smem, s>>>(P, T, nMasses, masses, first, 0, seed, q.list, q.count, q.cap, image,
+                                                             imageW2, counters);
+  return cudaGetLastError();
+}
+cudaError_t launch_retrace_mc_rays(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n, uint64_t seed,
+                                   const uint32_t* words, const fast::RetraceQueue& q, const sart_ray_out_t& out, int smCount,
+                                   cudaStream_t s) {
+  k_retrace_mc_rays<<<unsigned(smCount) * 4u, 128, 0, s>>>(P, T, mAxion, first, n, seed, words, q.list, q.count, q.cap, to_dev(out));
+  return cudaGetLastError();
+}
+cudaError_t launch_retrace_presampled(const Params& P, const Tables& T, double mAxion, size_t n, const double* origin,
+                                      const double* exitxy, const double* energy, const fast::RetraceQueue& q,
+                                      const sart_ray_out_t& out, int smCount, cudaStream_t s) {
+  k_retrace_presampled<<<unsigned(smCount) * 4u, 128, 0, s>>>(P, T, mAxion, n, origin, exitxy, energy, q.list, q.count, q.cap,
+                                                            to_dev(out));
   return cudaGetLastError();
 }
 

@@ -30,12 +30,8 @@ namespace fast {
 #ifndef SART_F32_MINBLOCKS
 #define SART_F32_MINBLOCKS 1
 #endif
-#ifndef SART_F32_PREFETCH
-#define SART_F32_PREFETCH 0   // 1: run the sampling head (Philox, emission shell, energy-guide load) one ray ahead
-                              // (no gain once the kernel was issue-bound: 28.9 vs 28.6 ms)
-#endif
 constexpr int kBlock32 = SART_F32_BLOCK, kWarps32 = kBlock32 / 32;
-constexpr uint64_t kMaxRaysPerLaunch = uint64_t(1) << 36;   // per-thread trip counts and their per-warp sums are 32-bit
+constexpr uint64_t kMaxRaysPerLaunch = uint64_t(1) << 31;   // re-trace queue entries (ray index - first ray) are 32-bit
 #ifndef SART_F32_BLOCK_M
 #define SART_F32_BLOCK_M 768
 #endif
@@ -107,6 +103,36 @@ __device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTable
     reinterpret_cast<uint2*>(const_cast<ShellCell*>(s.shellTab))[i] = __ldg(reinterpret_cast<const uint2*>(T.shellTab) + i);
 }
 
+// ---- margins ---------------------------------------------------------------------------------------------------------
+// SART_UNC(group, slack): slack = |margin of the decision just taken| - its error budget (fast_params.h: Tol32); the ray is
+// uncertain when the smallest slack on its way is <= 0 (one FADD + one FMNMX per decision, no predicate logic). SART_NO_MARGINS is an
+// experiment switch that compiles every margin test out (measures what they cost; not a shipped configuration).
+// The first argument names the decision group; SART_UNC_GROUPS (a bit mask, all groups by default) lets a development build
+// keep only some of them, to measure how many rays each decision sends to the re-trace queue.
+enum { kUncBore = 0, kUncOpaque = 1, kUncShell = 2, kUncMirror1 = 3, kUncMirror2 = 4, kUncNickel = 5, kUncAngle = 6,
+       kUncWindow = 7, kUncStrips = 8, kUncSlowRoot = 9 };
+#ifndef SART_UNC_GROUPS
+#define SART_UNC_GROUPS 0xffffffffu
+#endif
+#ifdef SART_NO_MARGINS
+#define SART_UNC(group, value) ((void)0)
+#else
+#define SART_UNC(group, value) do { if ((SART_UNC_GROUPS >> (group)) & 1u) slack = fminf(slack, (value)); } while (0)
+#endif
+constexpr float kSlackInf = 3.0e38f;
+// lateral position budgets of one ray before the mirrors (lat) and at the detector plane (det); `bud` is rs (emission
+// radius / solar radius; 1 for the X-ray source) for Monte Carlo rays and epsO for pre-sampled ones (Tol32)
+template <bool kPre>
+__device__ __forceinline__ void ray_budget(const Tol32& Q, float s1, float bud, float& lat, float& det) {
+  if (kPre) {
+    lat = fmaf(Q.latRef, bud, fmaf(Q.latTpre, s1, Q.latA));
+    det = fmaf(Q.detRef, bud, fmaf(Q.detTpre, s1, Q.detA));
+  } else {
+    lat = fmaf(Q.latS, bud, fmaf(Q.latT, s1, Q.latA));
+    det = fmaf(Q.detS, bud, fmaf(Q.detT, s1, Q.detA));
+  }
+}
+
 // Root choice of findPos* (rt:646-658) for A t^2 + 2 hb t + C = 0, as in kernels_fast.cu: q = -(hb + sign(hb) sq), the
 // roots are q/A (large, metres away) and C/q. Returns t with lo < t dz < hi.
 static __device__ __noinline__ float pick_root_slow32(float A, float q, float C, bool first_is_qA, float dz, float lo,
@@ -124,15 +150,37 @@ static __device__ __noinline__ float pick_root_slow32(float A, float q, float C,
 }
 // Returns t, or NaN (kMiss) when no root lies in range: the value travels in a register — a bool + reference pair made the
 // out-of-line slow path spill t to local memory on every call (one STL + one LDL per mirror through L1TEX).
-__device__ __forceinline__ float pick_root32(float A, float hb, float C, float dz, float lo, float hi) {
+// The interval of the mirror is given as centre and half length: the root z is a hit when |z - mid| < half.
+// Margins: tolC is the budget of C (the squared-radius difference at the start point), tolEnd that of the interval ends.
+// d z / d C = -1 / (2 (A z + hb)) = -+ 1 / (2 sqrt(disc)) exactly, so the budget of the root is tolC / (2 sqrt(disc))
+// (the safety factors sit in the budgets themselves; a near-tangent ray, disc -> 0, is uncertain by itself); tolZ returns it. Wolter optics add the
+// reference's own loss of digits in (-hb +- sqrt(hb^2 - A C)) / A for near-axial rays, where A -> 0 (Tol32::cond).
+template <int grp, bool kCond>
+__device__ __forceinline__ float pick_root32(const Tol32& Q, float A, float hb, float C, float dz, float mid, float half,
+                                             float tolC, float tolEnd, float& slack, float& tolZ) {
   const float disc = fmaf(hb, hb, -A * C);
-  if (!(disc >= 0.0f)) return kMiss;
-  const float sq = disc > 1e-30f ? disc * rsqrtf_nr(disc) : 0.0f;
+  tolZ = 0.0f;
+  if (!(disc >= 0.0f)) {
+    SART_UNC(grp, -disc - fmaf(2.0f * fabsf(A), tolC, Q.zrel * hb * hb));
+    return kMiss;
+  }
+  const float rsq = rsqrtf_nr(fmaxf(disc, 1e-30f));
+  const float sq = disc * rsq;
   const float q = -(hb + copysignf(sq, hb));
-  if (fabsf(q * dz) < fmaxf(fabsf(lo), fabsf(hi)) * fabsf(A)) return pick_root_slow32(A, q, C, hb >= 0.0f, dz, lo, hi);
+  const float reach = fabsf(mid) + half;
+  if (fabsf(q * dz) < reach * fabsf(A)) {   // the far root q/A may lie in range as well
+    SART_UNC(kUncSlowRoot, -1.0f);
+    return pick_root_slow32(A, q, C, hb >= 0.0f, dz, mid - half, mid + half);
+  }
   const float ts = C * rcpf_nr(q);
   const float zs = ts * dz;
-  return (zs > lo && zs < hi) ? ts : kMiss;
+  const float d = fabsf(zs - mid) - half;
+#ifndef SART_NO_MARGINS
+  tolZ = fmaf(Q.zrel, fabsf(zs), 0.5f * tolC * rsq);
+  if (kCond) tolZ = fmaf(0.5f * Q.cond * hb * hb, fabsf(rcp_approx(A)) * rsq, tolZ);
+  SART_UNC(grp, fabsf(d) - (tolZ + tolEnd));
+#endif
+  return d < 0.0f ? ts : kMiss;
 }
 
 // Reflection of unit vector v off unit normal n (rt:762-780 without trigonometry); returns |n.v| = sin(alpha).
@@ -152,8 +200,11 @@ struct Rec32 {
   float path2;            // pathCB^2
   int hitLayer, eIdx;
   bool clamped;
+  bool unc;               // a decision of stage A was inside its error budget (Tol32)
   int rIdx;               // emission shell and energy word, for kernels that resolve the energy after the compaction
   uint32_t we;
+  float bud;              // ray_budget's per-ray term: rs (Monte Carlo) or epsO (pre-sampled)
+  uint32_t id;            // ray index - first ray of the launch (re-trace queue entry), set by the kernel
 };
 
 // Alias-table lookup (fast_params.h: FastTables::radiusAlias): index of a distribution over n values for the random word w.
@@ -200,6 +251,7 @@ struct Head32 {
   uint16_t guide;
   // pre-sampled rays (tier (a)): exit-disc point, slopes and energy index supplied by the caller instead of drawn
   float ex, ey, sx, sy;
+  float epsO;    // rounding noise of the reference's line through the caller's origin [mm] (Tol32::latRef)
   int eIdx;
   bool offGrid;
 };
@@ -259,8 +311,12 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   bool haveRow = false;
   uint32_t eOff = 0u;
   uint32_t aBucket = 0u, aCoin = 0u, aEntry = 0u;   // alias sampler
+  const Tol32& Q = G.tol;
+  float slack = kSlackInf;
+  float bud = 1.0f;   // ray_budget's per-ray term
+  rec.unc = false;
   if (kPre) {
-    ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid;
+    ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid; bud = h.epsO;
   } else if (kPlain || !P.testXray) {
     const int rIdx = h.rIdx;
     if (!kLateEnergy) {
@@ -274,6 +330,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
       haveRow = true;
     }
     const float rs = (0.0015f + float(rIdx) * 0.0005f);
+    bud = rs;
     float s1, c1, s2, c2;
     sincos_2pi(float(w[0]) * k2m32, s1, c1);
     __sincosf(3.14159265358979f * (float(w[1]) * k2m32), &s2, &c2);
@@ -306,15 +363,31 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     sy = (ey - Oy) * G.invSrcDz;
     const float qx = fmaf(sx, G.colDz, Ox) - G.srcX, qy = fmaf(sy, G.colDz, Oy) - G.srcY;
     eIdx = P.srcEIdx;
-    if (!(fmaf(qx, qx, qy * qy) < G.srcRadius2)) return SART_EXIT_COLLIMATOR;
+    const float mc = fmaf(qx, qx, qy * qy) - G.srcRadius2;
+    SART_UNC(kUncBore, fabsf(mc) - (2.0f * G.srcRadius * Q.latA + Q.circ2 * G.srcRadius2));
+    if (!(mc < 0.0f)) { rec.unc = slack <= 0.0f; return SART_EXIT_COLLIMATOR; }
+  }
+  // error budgets of this ray (Tol32): lateral position before the mirrors, and at the bore entrance
+  const float s1abs = fabsf(sx) + fabsf(sy);
+  float lat;
+  {
+    float detUnused;
+    ray_budget<kPre>(Q, s1abs, bud, lat, detUnused);
   }
 
   // ================= bore and pipes rt:1813-1872
   const float s2sum = fmaf(sx, sx, sy * sy);
+  const float thrCB = fmaf(Q.twoRcb, lat, Q.circCB);
   const float p0x = fmaf(-sx, G.lengthB, ex), p0y = fmaf(-sy, G.lengthB, ey);
-  const bool hitEntrance = fmaf(p0x, p0x, p0y * p0y) < G.radiusCB2;
+  const float mEnt = fmaf(p0x, p0x, p0y * p0y) - G.radiusCB2;
+  const bool hitEntrance = mEnt < 0.0f;
   const float pex = fmaf(sx, G.dzExitCB, ex), pey = fmaf(sy, G.dzExitCB, ey);
-  const bool insideExit = fmaf(pex, pex, pey * pey) < G.radiusCB2;
+  const float mExit = fmaf(pex, pex, pey * pey) - G.radiusCB2;
+  const bool insideExit = mExit < 0.0f;
+  SART_UNC(kUncBore, fabsf(mExit) - thrCB);
+  // the entrance disc only tells "missed the bore" from "clipped at its exit" (rt:1813-1825 vs 1846); the reference
+  // intersects it separately, lengthB behind the field exit: Tol32::entK times the budget of the other planes covers it
+  SART_UNC(kUncBore, insideExit ? kSlackInf : fmaf(-Q.entK, thrCB, fabsf(mEnt)));
   // The clip tests of this stage do not branch: a warp goes on as long as one lane survives, so an early return saves
   // nothing and costs a divergence region each. `code` collects the exit in reverse order (the first failing test of
   // the reference's sequence is assigned last) and the stage returns once, at its end.
@@ -323,18 +396,26 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     path2 = G.lengthB2 * (1.0f + s2sum);
   } else {
     const float hb = fmaf(ex, sx, ey * sy), c = fmaf(ex, ex, ey * ey) - G.radiusCB2;
+    // wall entry with the exit-disc point itself on the rim: the path inside the field, and with it the weight, may be
+    // exactly zero on one side of the rounding and 1e-27 on the other (passed means weight != 0, rt:2220)
+    SART_UNC(kUncBore, fabsf(c) - thrCB);
     const float disc = fmaf(hb, hb, -s2sum * c);
     const float sq = disc > 1e-30f ? disc * rsqrtf_nr(disc) : 0.0f;
     const float t1 = (hb >= 0.0f) ? -(hb + sq) * rcpf_nr(s2sum) : c * rcpf_nr(sq - hb);
     path2 = t1 * t1 * (1.0f + s2sum);
   }
+  const float thrPipe = fmaf(Q.twoRpipe, lat, Q.circPipe);
   bool okPipe1;
   {
     const float qx = fmaf(sx, G.dzPipe1, ex), qy = fmaf(sy, G.dzPipe1, ey);
-    okPipe1 = fmaf(qx, qx, qy * qy) < G.rPipe12;
+    const float m = fmaf(qx, qx, qy * qy) - G.rPipe12;
+    okPipe1 = m < 0.0f;
+    SART_UNC(kUncBore, fabsf(m) - thrPipe);
   }
   float x0 = fmaf(sx, G.dzPipe2, ex), y0 = fmaf(sy, G.dzPipe2, ey);
-  const bool okPipe2 = fmaf(x0, x0, y0 * y0) < G.rPipe12;  // quirk Q2
+  const float mPipe2 = fmaf(x0, x0, y0 * y0) - G.rPipe12;
+  const bool okPipe2 = mPipe2 < 0.0f;  // quirk Q2
+  SART_UNC(kUncBore, fabsf(mPipe2) - thrPipe);
   uint4 etA = make_uint4(0, 0, 0, 0);
 #if !SART_LAZY_THR
   uint4 etB = etA;
@@ -369,6 +450,7 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   const float rho0sq = fmaf(x0, x0, y0 * y0);
   const float invRho0 = rsqrtf_nr(rho0sq);
   const float radialDist = rho0sq * invRho0;
+  const float latRho = lat + Q.rho;
 
   // ================= opaque structures rt:1635-1704
   bool opaque = false;
@@ -380,8 +462,11 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     bool hit = false;
     const float zs = xmm ? -85.0f : -35.0f;
     const float xs = fmaf(zs, tx, x0), ys = fmaf(zs, ty, y0);
-    const float cF = x0 * invRho0, cS = xs * rsqrtf_nr(fmaf(xs, xs, ys * ys));
+    const float invRhoS = rsqrtf_nr(fmaf(xs, xs, ys * ys));
+    const float cF = x0 * invRho0, cS = xs * invRhoS;
+    // margins: radial edges against latRho; an arm edge at angle a moves cos(n phi) by n sin(n a) dphi <= n lat / rho
     if (xmm) {
+      SART_UNC(kUncOpaque, fminf(fminf(fabsf(radialDist - 64.7f), fabsf(radialDist - 151.6f)), fabsf(radialDist - (151.6f - 20.9f))) - latRho);
       if (radialDist <= 64.7f) hit = true;
       else if (radialDist < 151.6f && radialDist > (151.6f - 20.9f)) hit = true;
       else {
@@ -390,9 +475,12 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
           return fmaf(2.0f * c, c, -1.0f);
         };
         constexpr float kCos = 0.94931733f;   // cos(16 * 1.145 deg)
-        hit = (t16(cF) >= kCos) || (t16(cS) >= kCos);
+        const float tF = t16(cF), tS = t16(cS);
+        hit = (tF >= kCos) || (tS >= kCos);
+        SART_UNC(kUncOpaque, fminf(fabsf(tF - kCos) - fmaf(16.0f * lat, invRho0, Q.spider), fabsf(tS - kCos) - fmaf(16.0f * lat, invRhoS, Q.spider)));
       }
     } else {
+      SART_UNC(kUncOpaque, fabsf(radialDist - 37.5f) - latRho);
       if (radialDist < 37.5f) hit = true;
       else {
         auto t6 = [](float c) {
@@ -400,7 +488,9 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
           return fmaf(c2, fmaf(c2, fmaf(c2, 32.0f, -48.0f), 18.0f), -1.0f);
         };
         constexpr float kCos = 0.92387953f;   // cos(6 * 3.75 deg)
-        hit = (t6(cF) >= kCos) || (t6(cS) >= kCos);
+        const float tF = t6(cF), tS = t6(cS);
+        hit = (tF >= kCos) || (tS >= kCos);
+        SART_UNC(kUncOpaque, fminf(fabsf(tF - kCos) - fmaf(6.0f * lat, invRho0, Q.spider), fabsf(tS - kCos) - fmaf(6.0f * lat, invRhoS, Q.spider)));
       }
     }
     opaque = hit;
@@ -419,11 +509,13 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
     const uint32_t pick = radialDist < B ? 0x4440u : (radialDist > B ? 0x4442u : 0x4441u);   // NaN: "at" = no mirror hit
     hitLayer = int(__byte_perm(c.y, 0u, pick));
     if (hitLayer >= kShellCellFail) code = hitLayer - kShellCellFail;
+    SART_UNC(kUncShell, fabsf(radialDist - B) - latRho);   // B: the boundary of this bucket, else the nearest one (build_shell_table)
   }
   if (opaque) code = SART_EXIT_OPAQUE;
   if (!okPipe2) code = SART_EXIT_CLIP_PIPE_XRT;
   if (!okPipe1) code = SART_EXIT_CLIP_PIPE_VT3;
   if (!insideExit) code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
+  rec.unc = slack <= 0.0f;
   if (code >= 0) return code;
   if (kAlias) {
     if (kRowAlways || haveRow) eIdx = alias_resolve(aEntry, aBucket, aCoin);
@@ -447,22 +539,29 @@ __device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, co
   }
   rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.rho0 = radialDist; rec.path2 = path2;
   rec.hitLayer = hitLayer; rec.eIdx = eIdx; rec.clamped = clamped;
-  rec.rIdx = h.rIdx; rec.we = w[5];
+  rec.rIdx = h.rIdx; rec.we = w[5]; rec.bud = bud;
   return -1;
 }
 
 // Stage B in FP32: the two reflections, nickel / degenerate exits, detector plane, weights, window (rt:1971-2221).
-template <bool kWolter, bool kPlain = false, class Sink>
+// Every exit hands the ray to the re-trace queue instead (sink.defer) when a decision on its way there was inside its
+// error budget.
+#define SART_DEFER() do { if (slack <= 0.0f && sink.defer(rec.id)) return; } while (0)
+template <bool kWolter, bool kPlain = false, bool kPre = false, class Sink>
 __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
                                           const Rec32& rec, Sink& sink) {
   const ShellF32* __restrict__ sShell = S.shell;
+  const Tol32& Q = G.tol;
   RayResult out;
   out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
   const float x0 = rec.x0, y0 = rec.y0, tx = rec.tx, ty = rec.ty, rho0 = rec.rho0;
   const int hitLayer = rec.hitLayer, eIdx = rec.eIdx;
   bool clamped = rec.clamped;
+  float slack = rec.unc ? -1.0f : kSlackInf;
+  float lat, det;
+  ray_budget<kPre>(Q, fabsf(tx) + fabsf(ty), rec.bud, lat, det);
   const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);
-  const EnergyLUT el = {elv.x, elv.y, elv.z, elv.w};
+  const EnergyLUT el = {__float_as_int(elv.x), elv.y, elv.z, elv.w};
   const float t2sum = fmaf(tx, tx, ty * ty);
   const float invLen = rsqrtf_nr(1.0f + t2sum);
   const ShellF32& sh = sShell[hitLayer];
@@ -471,12 +570,14 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
   const float xt = fmaf(x0, tx, y0 * ty);
 
   // ================= mirror 1 rt:1983-2020. Ray: (x0 + tx z, y0 + ty z, z); C in factored form
-  float z1;
+  float z1, tolZ1;
+  const float tolC1 = sh.twoR * (lat + Q.rho);   // budget of C = rho0^2 - R^2: 2 R x the budget of rho0
   if (kWolter) {   // paraboloid rho^2 = c0 - e z, c0 = R0^2
-    z1 = pick_root32(t2sum, xt + 0.5f * sh.p_e, (rho0 - sh.p_R0) * (rho0 + sh.p_R0), 1.0f, 0.0f, sh.zmax1);
+    z1 = pick_root32<kUncMirror1, true>(Q, t2sum, xt + 0.5f * sh.p_e, (rho0 - sh.p_R0) * (rho0 + sh.p_R0), 1.0f, sh.zmid1,
+                                        sh.zhalf1, tolC1, 0.0f, slack, tolZ1);
   } else {         // cone rho = r1 - tan(beta) z
-    z1 = pick_root32(t2sum - sh.tan1 * sh.tan1, fmaf(sh.tan1, sh.R1, xt), (rho0 - sh.R1) * (rho0 + sh.R1), 1.0f, 0.0f,
-                     sh.zmax1);
+    z1 = pick_root32<kUncMirror1, false>(Q, t2sum - sh.tan1 * sh.tan1, fmaf(sh.tan1, sh.R1, xt), (rho0 - sh.R1) * (rho0 + sh.R1),
+                                         1.0f, sh.zmid1, sh.zhalf1, tolC1, 0.0f, slack, tolZ1);
   }
   if (!(z1 == z1)) {   // kMiss
     int code = SART_EXIT_NO_MIRROR_HIT;
@@ -491,8 +592,11 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
       const float sg = (fmaf(xc, tx, yc * ty) + nz) * invLen * rsqrtf_nr(fmaf(rc, rc, nz * nz));
       const float a = fabsf(sg);
       const float lhs = a * (lM - zc), rhs = sh.R1 - below;
-      if (lhs * lhs > rhs * rhs * (1.0f - a * a)) code = SART_EXIT_NICKEL;
+      const float m = fmaf(lhs, lhs, -rhs * rhs * (1.0f - a * a));
+      SART_UNC(kUncNickel, fmaf(-4.0f * Q.nick, lhs + rhs, fabsf(m)));
+      if (m > 0.0f) code = SART_EXIT_NICKEL;
     }
+    SART_DEFER();
     sink.fail(code);
     return;
   }
@@ -513,27 +617,31 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
     }
     sinA1 = reflect32(n, v);
   }
-  // ================= mirror 2 rt:1994-2029. Ray: pm + t v.
-  float t2;
-  const float lo2 = sh.dm - pm.z, hi2 = sh.zmax2 - pm.z;
+  // ================= mirror 2 rt:1994-2029. Ray: pm + t v. The budget of C: the start point sits on mirror 1 at z1 +-
+  // tolZ1, where the radii of the ray and of mirror 2 move by (|slope| + tan(3 beta)) tolZ1, plus the ray's own lat
+  float t2, tolZ2;
+  const float mid2 = sh.zmid2 - pm.z;
   const float pv = fmaf(pm.x, v.x, pm.y * v.y), vv = fmaf(v.x, v.x, v.y * v.y);
+  const float tolC2 = (rhoM + rhoM) * fmaf(sh.tan2p, tolZ1, lat);
   if (kWolter) {  // hyperboloid rho^2 = r3^2 + e (l - z) + g (l - z)^2
     const float u = lM - pm.z;
     const float Rh2 = fmaf(fmaf(sh.h_g, u, sh.h_e), u, sh.h_r3sq);
     const float Rh = Rh2 * rsqrtf_nr(Rh2);
-    t2 = pick_root32(vv - sh.h_g * v.z * v.z, fmaf(fmaf(sh.h_g, u, 0.5f * sh.h_e), v.z, pv), (rhoM - Rh) * (rhoM + Rh), v.z,
-                     lo2, hi2);
+    t2 = pick_root32<kUncMirror2, true>(Q, vv - sh.h_g * v.z * v.z, fmaf(fmaf(sh.h_g, u, 0.5f * sh.h_e), v.z, pv),
+                                        (rhoM - Rh) * (rhoM + Rh), v.z, mid2, sh.zhalf2, tolC2, tolZ1, slack, tolZ2);
   } else {        // cone rho = r4 - tan(3 beta) (z - distanceMirrors)
     const float rc = fmaf(-sh.tan2, pm.z - sh.dm, sh.r4);
-    t2 = pick_root32(vv - sh.tan2 * sh.tan2 * v.z * v.z, fmaf(sh.tan2 * rc, v.z, pv), (rhoM - rc) * (rhoM + rc), v.z, lo2,
-                     hi2);
+    t2 = pick_root32<kUncMirror2, false>(Q, vv - sh.tan2 * sh.tan2 * v.z * v.z, fmaf(sh.tan2 * rc, v.z, pv),
+                                         (rhoM - rc) * (rhoM + rc), v.z, mid2, sh.zhalf2, tolC2, tolZ1, slack, tolZ2);
   }
   // ================= nickel of the shell below rt:1706-1734
   if (hitLayer > 0) {
     const float lhs = sinA1 * (lM - z1), rhs = sh.R1 - below;
-    if (lhs * lhs > rhs * rhs * (1.0f - sinA1 * sinA1)) { sink.fail(SART_EXIT_NICKEL); return; }
+    const float m = fmaf(lhs, lhs, -rhs * rhs * (1.0f - sinA1 * sinA1));
+    SART_UNC(kUncNickel, fmaf(-(lhs + rhs), fmaf(sinA1, tolZ1, Q.nick), fabsf(m)));
+    if (m > 0.0f) { SART_DEFER(); sink.fail(SART_EXIT_NICKEL); return; }
   }
-  if (!(t2 == t2)) { sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }   // kMiss
+  if (!(t2 == t2)) { SART_DEFER(); sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }   // kMiss
   pm.x = fmaf(t2, v.x, pm.x); pm.y = fmaf(t2, v.y, pm.y); pm.z = fmaf(t2, v.z, pm.z);
   float sinA2;
   {
@@ -556,16 +664,22 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
   {
     const float ax = fmaf(pm.x, G.cosPipe, pm.z * G.sinPipe) - G.dShift, az = fmaf(pm.z, G.cosPipe, -pm.x * G.sinPipe);
     const float wx = fmaf(v.x, G.cosPipe, v.z * G.sinPipe), wz = fmaf(v.z, G.cosPipe, -v.x * G.sinPipe);
-    const float n = (sh.ddWin - az) * rcpf_nr(wz);
+    const float iwz = rcpf_nr(wz);
+    const float n = (sh.ddWin - az) * iwz;
     xw = fmaf(n, wx, ax); yw = fmaf(n, v.y, pm.y); zw = fmaf(n, wz, az);
+    // deviationDet rt:2081-2085: distance in the detector plane between the hits at the window and depthDet behind it
+    out.devDet = fabsf(G.depthOverCos * iwz) * sqrtf(fmaf(wx, wx, v.y * v.y));
   }
   xw -= G.lateralShift; yw -= G.transversalShift;
   // ================= weights rt:2101-2128
-  out.energy = el.E;
+  out.eIdx = eIdx;
+  const uint32_t flags = kPlain ? 0u : P.flags;
   {
     const float ya = -atan_small(ty) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
+    out.yaw = ya;
     float pre = __cosf(ya);
     const float path2f = rec.path2;
+    out.path = sqrtf(path2f);
     if (kPlain || P.stage == SART_SK_VACUUM) {
       out.convVac = P.convK * path2f;
     } else {
@@ -580,26 +694,35 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
       const float distPipe = (zw - G.zExitCBtel) * 1e-3f;
       pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
     }
-    float refl = 1.0f;
-    const uint32_t flags = kPlain ? 0u : P.flags;
+    out.pre = pre;
+    double refl = 1.0;   // the product of two FP32 reflectivities can leave the FP32 range (1e-20 each at large angles)
+    const float a1 = asin_small(sinA1) * 57.29577951308232f, a2 = asin_small(sinA2) * 57.29577951308232f;
+    out.a1 = a1; out.a2 = a2;
     if (!(flags & SART_CF_IGNORE_REFLECTION)) {
-      const uint32_t rowOff = (uint32_t(sh.coat) * uint32_t(P.nEnergies + 1) + uint32_t(eIdx)) * uint32_t(P.nAngles);
-      const float a1 = asin_small(sinA1) * 57.29577951308232f, a2 = asin_small(sinA2) * 57.29577951308232f;
-      refl = refl_lookup(P, T.reflE, a1, clamped, rowOff) * refl_lookup(P, T.reflE, a2, clamped, rowOff);
+      const uint32_t rowOff = (uint32_t(sh.coat & kCoatMask) * uint32_t(P.nEnergies + 1) + uint32_t(eIdx)) * uint32_t(P.nAngles);
+      clamped |= (sh.coat & kCoatClamped) != 0;
+      SART_UNC(kUncAngle, Q.angLo - fmaxf(a1, a2));   // at or beyond the end of the grid: the clamped flag
+      refl = double(refl_lookup(P, T.reflE, a1, clamped, rowOff)) * double(refl_lookup(P, T.reflE, a2, clamped, rowOff));
     }
-    out.wPre = double(refl) * double(pre);
+    out.refl = refl;
+    out.wPre = refl * double(pre);
     if (Sink::kFold)
       out.wPre *= kPlain ? double(out.convVac)
                          : conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
   }
-  const uint32_t flags = kPlain ? 0u : P.flags;
+  out.agas = el.Agas;
   out.clamped = clamped;
   out.shell = hitLayer;
   out.code = -1;
   // ================= window aperture rt:2139-2147
   const float rw2 = fmaf(xw, xw, yw * yw);
-  if ((!(flags & SART_CF_IGNORE_DET_WINDOW) && rw2 > G.radiusWindow2) || fabsf(xw) > G.chipCX || fabsf(yw) > G.chipCY) {
+  const bool ignoreWin = (flags & SART_CF_IGNORE_DET_WINDOW) != 0;
+  SART_UNC(kUncWindow, ignoreWin ? kSlackInf : fabsf(rw2 - G.radiusWindow2) - fmaf(Q.twoRwin, det, Q.circWin));
+  if (ignoreWin || Q.chipInside)   // otherwise the window aperture lies inside the chip and decides alone
+    SART_UNC(kUncWindow, fminf(fabsf(fabsf(xw) - G.chipCX), fabsf(fabsf(yw) - G.chipCY)) - det);
+  if ((!ignoreWin && rw2 > G.radiusWindow2) || fabsf(xw) > G.chipCX || fabsf(yw) > G.chipCY) {
     out.windowMiss = true; out.wPost = 0.0; out.x = out.y = out.r = 0.0; out.bin = -1;
+    SART_DEFER();
     sink.hit(out);
     return;
   }
@@ -615,9 +738,15 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
       const float fi = floorf(u * G.invStripPitch);
       const float off = fmaf(-fi, pitch, u);
       sb = (u > 0.0f && fi < float(P.nStripHalf) && off > 0.0f && off < G.stripWidth) ? 1 : 0;
+      // a strip edge within det of the hit (off = 0, the strip width, or the next strip's start) changes the transmission
+      SART_UNC(kUncStrips, ignoreWin ? kSlackInf : fminf(fminf(off, fabsf(off - G.stripWidth)), pitch - off) - det);
     }
     const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
-    if (!(flags & SART_CF_IGNORE_DET_WINDOW)) post *= double(tw);
+    if (!ignoreWin) {
+      post *= double(tw);
+      if (sb == 1 && el.sbExp != 0)   // rare (soft X-rays on a strip): add the exponent; the product stays far inside the f64 range
+        post = __hiloint2double(__double2hiint(post) + (el.sbExp << 20), __double2loint(post));
+    }
   }
   if (!(flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
   if (!(flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
@@ -628,6 +757,7 @@ __device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, c
   out.y = double(yc);
   const int cx = int(floorf(xc * G.invBinX)), cy = int(floorf(yc * G.invBinY));
   out.bin = (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) ? cy * SART_IMAGE_BINS + cx : -1;
+  SART_DEFER();
   sink.hit(out);
 }
 
@@ -641,11 +771,14 @@ __device__ __forceinline__ void flush_counters(sart_counters_t* c, const WarpCou
   for (int e = 1; e < SART_N_EXIT_CODES; ++e) addu(&c->n_exit[e], wc.n_exit[e]);
   addu(&c->n_hit_nickel, wc.n_exit[SART_EXIT_NICKEL]);
   addu(&c->n_interp_clamped, wc.n_clamped);
+  addu(&c->n_unresolved, wc.n_unresolved);
   atomicAdd(&c->sum_w, sumW); atomicAdd(&c->sum_w2, sumW2);
   atomicAdd(&c->sum_x, sumX); atomicAdd(&c->sum_y, sumY); atomicAdd(&c->sum_r, sumR);
 }
 
 // ---- fused kernel ---------------------------------------------------------------------------------------------
+// A ray of stage A that is uncertain (rec.unc) goes to the re-trace queue whatever its code; stage B does the same at its
+// own exits. The launcher keeps nRays below 2^32, so the queue entry (ray index - first) fits 32 bits.
 template <bool kWolter, bool kPlain, bool kAlias>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G, const __grid_constant__ FastTables T,
@@ -666,37 +799,22 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
   const uint32_t rep = T.nImgRep > 1 ? (blockIdx.x % unsigned(T.nImgRep)) * uint32_t(T.imgRepStride) : 0u;
   ImageSinkT<!kPlain> sink{T, mAxion2, image, imageW2, rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
-#if SART_F32_PREFETCH
-  uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x;
-  Head32 cur;
-  if (i < nRays) stage_a32_head<kPlain, false, kAlias>(P, T, S, K, first + i, cur);
-  while (i < nRays) {
-    ++nIter;
-    const uint64_t inext = i + stride;
-    Head32 nxt;
-    if (inext < nRays) stage_a32_head<kPlain, false, kAlias>(P, T, S, K, first + inext, nxt);   // next ray's guide load goes out now
-    Rec32 rec;
-    const int code = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, cur, rec);
-    if (code >= 0) sink.fail(code);
-    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
-    cur = nxt;
-    i = inext;
-  }
-#else
   // 32-bit trip count + running 64-bit ray index: 5 loop instructions per ray instead of 12 (the launcher keeps
   // nRays <= kMaxRaysPerLaunch, so the count fits)
   const uint64_t i0 = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x;
   nIter = i0 < nRays ? unsigned((nRays - 1 - i0) / stride) + 1u : 0u;
   uint64_t ray = first + i0;
-  for (unsigned k = nIter; k != 0u; --k, ray += stride) {
+  uint32_t id = uint32_t(i0);
+  const uint32_t stride32 = uint32_t(stride);
+  for (unsigned k = nIter; k != 0u; --k, ray += stride, id += stride32) {
     Head32 hd;
     stage_a32_head<kPlain, false, kAlias>(P, T, S, K, ray, hd);
     Rec32 rec;
+    rec.id = id;
     const int code = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, hd, rec);
-    if (code >= 0) sink.fail(code);
+    if (code >= 0) { if (!(rec.unc && sink.defer(rec.id))) sink.fail(code); }
     else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
   }
-#endif
   for (int o = 16; o > 0; o >>= 1) {
     nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
     nTill += __shfl_down_sync(0xffffffffu, nTill, o);
@@ -715,8 +833,9 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
 constexpr int kQueue32 = 64;
 struct WarpQueue32 {
   float x0[kQueue32], y0[kQueue32], tx[kQueue32], ty[kQueue32], rho0[kQueue32], path2[kQueue32];
-  int meta[kQueue32];   // hitLayer | (eIdx or emission shell) << 8 | clamped << 30
+  int meta[kQueue32];   // hitLayer | (eIdx or emission shell) << 8 | clamped << 30 | uncertain << 31
   uint32_t we[kQueue32];   // energy word of the ray (solar source: the energy is resolved after the compaction)
+  uint32_t id[kQueue32];   // ray index - first ray of the launch
 };
 
 template <bool kWolter, bool kPlain, bool kAlias>
@@ -743,6 +862,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
   ImageSinkT<!kPlain> sink{T, mAxion2, image, imageW2, rep, wc[warp], nPassed, nTill, sumW, sumW2, sumX, sumY, sumR};
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
   uint64_t base = uint64_t(blockIdx.x) * kBlock32 + (threadIdx.x & ~31);
+  const bool solar = kPlain || !P.testXray;
   int qn = 0;
   for (;;) {
     while (qn <= kQueue32 - 32 && base < nRays) {
@@ -753,18 +873,19 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       if (i < nRays) {
         Head32 hd;
         stage_a32_head<kPlain, true, kAlias>(P, T, S, K, first + i, hd);
+        rec.id = uint32_t(i);
         code = stage_a32<kWolter, false, kPlain, true, kAlias>(P, G, T, S, hd, rec);
         ++nIter;
-        if (code >= 0) sink.fail(code);
+        if (code >= 0 && !(rec.unc && sink.defer(rec.id))) sink.fail(code);
       }
       const unsigned m = __ballot_sync(kFull, code < 0);
       if (code < 0) {
         const int pos = qn + __popc(m & ((1u << lane) - 1u));
         Q.x0[pos] = rec.x0; Q.y0[pos] = rec.y0; Q.tx[pos] = rec.tx; Q.ty[pos] = rec.ty; Q.rho0[pos] = rec.rho0;
         Q.path2[pos] = rec.path2;
-        const bool solar = kPlain || !P.testXray;
-        Q.meta[pos] = rec.hitLayer | ((solar ? rec.rIdx : rec.eIdx) << 8) | (rec.clamped ? (1 << 30) : 0);
+        Q.meta[pos] = rec.hitLayer | ((solar ? rec.rIdx : rec.eIdx) << 8) | (rec.clamped ? (1 << 30) : 0) | (rec.unc ? (1 << 31) : 0);
         Q.we[pos] = rec.we;
+        Q.id[pos] = rec.id;
       }
       qn += __popc(m);
     }
@@ -777,8 +898,10 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       rec.x0 = Q.x0[pos]; rec.y0 = Q.y0[pos]; rec.tx = Q.tx[pos]; rec.ty = Q.ty[pos]; rec.rho0 = Q.rho0[pos];
       rec.path2 = Q.path2[pos];
       const int meta = Q.meta[pos];
-      rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1;
-      if (kPlain || !P.testXray) rec.eIdx = energy_index<kAlias>(P, T, rec.eIdx, Q.we[pos], rec.clamped);
+      rec.hitLayer = meta & 0xff; rec.eIdx = (meta >> 8) & 0x3fffff; rec.clamped = (meta >> 30) & 1; rec.unc = meta < 0;
+      rec.id = Q.id[pos];
+      rec.bud = solar ? (0.0015f + float(rec.eIdx) * 0.0005f) : 1.0f;   // rs of the emission shell (rec.eIdx still holds it)
+      if (solar) rec.eIdx = energy_index<kAlias>(P, T, rec.eIdx, Q.we[pos], rec.clamped);
       stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
     }
     qn -= take;
@@ -813,14 +936,17 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
   smem_fill32(P, T, S);
   for (int i = threadIdx.x; i < kWarpsM * int(sizeof(WarpCounters) / 4); i += kBlockM) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
-  mass_scan_loop(P, masses, nMasses, first, nRays, image, imageW2, counters, wc, [&](uint64_t ray, RayResult& r) {
-    RecordSink<false> sink{r, 0.0};
+  mass_scan_loop(P, T.rad, masses, nMasses, first, nRays, image, imageW2, counters, wc,
+                 [&](uint64_t ray, uint32_t id, RayResult& r) {
+    RecordSink<false> sink{r, 0.0, T.rq, true};
     Head32 hd;
     stage_a32_head(P, T, S, K, ray, hd);
     Rec32 rec;
+    rec.id = id;
     const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
-    if (c0 >= 0) sink.fail(c0);
+    if (c0 >= 0) { if (!(rec.unc && sink.defer(rec.id))) sink.fail(c0); }
     else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
+    return sink.unresolved;
   });
 }
 
@@ -828,13 +954,13 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
 // `words` (optional, sart_trace_words): SoA [6][nRays] random words used instead of the Philox words of ray first + i.
 // kLate: the energy is resolved by energy_index() after stage A, the way the compacting fused kernel does it (otherwise
 // inside stage A, the way the plain fused kernel does it) — so the test hook reaches both forms of the search.
+// An uncertain ray gets its FP32 record like any other and is queued; the exact pipeline overwrites the record afterwards.
 template <bool kWolter, bool kPlain, bool kAlias, bool kLate = false>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                     const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
                     const __grid_constant__ PhiloxKeys K, const uint32_t* __restrict__ words, int32_t* __restrict__ oemit,
-                    double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
-                    int32_t* __restrict__ oshell, double* __restrict__ oenergy, double* __restrict__ orad) {
+                    const __grid_constant__ sart_ray_out_t o) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
   unsigned char* tail;
@@ -844,8 +970,9 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
   const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x; i < nRays; i += stride) {
     RayResult r;
-    RecordSink<true> sink{r, mAxion2};
+    RecordSink<true> sink{r, mAxion2, T.rq, false};
     Rec32 rec;
+    rec.id = uint32_t(i);
     Head32 hd;
     if (words) {
 #pragma unroll
@@ -855,33 +982,26 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     }
     stage_a32_head_words<kPlain, kLate, kAlias>(P, T, S, hd);
     const int c0 = stage_a32<kWolter, false, kPlain, kLate, kAlias>(P, G, T, S, hd, rec);
-    if (kLate && c0 < 0 && (kPlain || !P.testXray)) rec.eIdx = energy_index<kAlias>(P, T, rec.rIdx, rec.we, rec.clamped);
-    if (c0 >= 0) sink.fail(c0);
+    const bool solar = kPlain || !P.testXray;
+    if (kLate && c0 < 0 && solar) rec.eIdx = energy_index<kAlias>(P, T, rec.rIdx, rec.we, rec.clamped);
+    if (c0 >= 0) { if (rec.unc) sink.defer(rec.id); sink.fail(c0); }
     else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
-    int code = r.code;
-    double wd = 0.0;
-    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
-    else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
-    const bool tail = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
-    ox[i] = tail ? r.x : 0.0; oy[i] = tail ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tail ? r.shell : -1;
-    if (oenergy) {
-      // energiesPre is set for every ray (rt:1818-1819), clipped or not: rays that end in stage A resolve their energy here
+    // energiesPre is set for every ray (rt:1818-1819), clipped or not: rays that end in stage A resolve their energy here
+    double energy = double(P.srcEnergy);
+    if (solar) {
       int eIdx = rec.eIdx;
-      if (kPlain || !P.testXray) {
-        bool cl = false;
-        if (c0 >= 0) eIdx = energy_index<kAlias>(P, T, hd.rIdx, hd.w[5], cl);
-        oenergy[i] = fmax(__ldg(T.energies + eIdx), 0.03);   // the f64 table value itself (rt:470-471)
-      } else {
-        oenergy[i] = double(P.srcEnergy);
-      }
+      bool cl = false;
+      if (c0 >= 0) eIdx = energy_index<kAlias>(P, T, hd.rIdx, hd.w[5], cl);
+      energy = fmax(__ldg(T.energies + eIdx), 0.03);   // the f64 table value itself (rt:470-471)
     }
+    store_record(P, o, i, r, mAxion2, energy);
     if (oemit) oemit[i] = hd.rIdx;
-    if (orad) orad[i] = tail ? r.r : 0.0;
   }
 }
 
 // ---- tier (a): pre-sampled rays, structure of arrays in HBM -> per-ray records in HBM -------------------------------
-// 48 B in (origin x, y, z; exit-disc x, y; energy — f64, coalesced) and 32 B out (x, y, w f64; code, shell i32) per ray.
+// 48 B in (origin x, y, z; exit-disc x, y; energy — f64, coalesced) and 32 B out (x, y, w f64; code, shell i32) per ray,
+// plus whatever optional record arrays the caller asks for.
 // The slopes are formed in FP64 from the caller's points (the origin is 1.5e14 mm away), everything after that is the
 // FP32 pipeline. The energy is mapped to its index in the tabulated energies (the reference only ever traces tabulated
 // energies, rt:470); an energy that is not a table value is traced at the nearest one and flagged INTERP_CLAMPED.
@@ -889,9 +1009,8 @@ template <bool kWolter, bool kPlain>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                        const __grid_constant__ FastTables T, double mAxion2, size_t n, const double* __restrict__ origin,
-                       const double* __restrict__ exitxy, const double* __restrict__ energy, double* __restrict__ ox,
-                       double* __restrict__ oy, double* __restrict__ ow, int32_t* __restrict__ ocode,
-                       int32_t* __restrict__ oshell, double* __restrict__ oenergy, double* __restrict__ orad) {
+                       const double* __restrict__ exitxy, const double* __restrict__ energy,
+                       const __grid_constant__ sart_ray_out_t o) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem32 S;
   unsigned char* tail;
@@ -906,6 +1025,9 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
     const double invD = rcp_nr(P.lengthB - Oz);
     hd.ex = float(ex); hd.ey = float(ey);
     hd.sx = float((ex - Ox) * invD); hd.sy = float((ey - Oy) * invD);
+    // rounding noise of the reference's line O + lambda (E - O) (rt:481-492, 529-534) at pointExitCB: one ulp of the
+    // origin's x / y, plus one ulp of its z seen through the slope
+    hd.epsO = 4.4408921e-16f * (fabsf(float(Ox)) + fabsf(float(Oy)) + (fabsf(hd.sx) + fabsf(hd.sy)) * fabsf(float(Oz)));
     // energy -> index of the tabulated energy: uniform-grid guess, then the table decides
     const double Ec = fmax(E, 0.03);
     int k = int(rint((E - P.enE0) * P.enInvStep));
@@ -921,19 +1043,13 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
     hd.eIdx = k;
     hd.offGrid = fmax(__ldg(T.energies + k), 0.03) != Ec;
     RayResult r;
-    RecordSink<true> sink{r, mAxion2};
+    RecordSink<true> sink{r, mAxion2, T.rq, false};
     Rec32 rec;
+    rec.id = uint32_t(i);
     const int c0 = stage_a32<kWolter, true, kPlain>(P, G, T, S, hd, rec);
-    if (c0 >= 0) sink.fail(c0);
-    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
-    int code = r.code;
-    double wd = 0.0;
-    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
-    else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
-    const bool tl = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
-    ox[i] = tl ? r.x : 0.0; oy[i] = tl ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tl ? r.shell : -1;
-    if (oenergy) oenergy[i] = Ec;
-    if (orad) orad[i] = tl ? r.r : 0.0;
+    if (c0 >= 0) { if (rec.unc) sink.defer(rec.id); sink.fail(c0); }
+    else stage_b32<kWolter, kPlain, true>(P, G, T, S, rec, sink);
+    store_record(P, o, i, r, mAxion2, Ec);
   }
 }
 
@@ -1038,8 +1154,7 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
   const uint64_t want = (n + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, n, origin, exitxy, energy, o.x, o.y, o.w, o.code, o.shell,
-                                        o.energy, o.r);
+  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, n, origin, exitxy, energy, o);
   return cudaGetLastError();
 }
 
@@ -1052,7 +1167,7 @@ cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, 
   const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias);
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
   using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, const uint32_t*,
-                        int32_t*, double*, double*, double*, int32_t*, int32_t*, double*, double*);
+                        int32_t*, sart_ray_out_t);
   static const Kern table[2][2][2] = {   // [wolter][plain][alias]
       {{fast::k_trace_mc_rays_f32<false, false, false>, fast::k_trace_mc_rays_f32<false, false, true>},
        {fast::k_trace_mc_rays_f32<false, true, false>, fast::k_trace_mc_rays_f32<false, true, true>}},
@@ -1067,8 +1182,7 @@ cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, 
   const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
   const uint64_t cap = uint64_t(smCount) * 2;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), words, emit, o.x, o.y, o.w, o.code,
-                                        o.shell, o.energy, o.r);
+  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), words, emit, o);
   return cudaGetLastError();
 }
 

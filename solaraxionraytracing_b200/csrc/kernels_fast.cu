@@ -324,7 +324,7 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
   const int hitLayer = rec.hitLayer, eIdx = rec.eIdx;
   bool clamped = rec.clamped;
   const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);   // needed at the weight stage
-  const EnergyLUT el = {elv.x, elv.y, elv.z, elv.w};
+  const EnergyLUT el = {__float_as_int(elv.x), elv.y, elv.z, elv.w};
   const double rho0sq = fma(x0, x0, y0 * y0);
   const double t2sum = fma(tx, tx, ty * ty);
   const double invLen = rsqrt_nr(1.0 + t2sum);
@@ -422,16 +422,20 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
   {
     const double ax = pm.x * P.cosPipe + pm.z * P.sinPipe - P.dShift, az = pm.z * P.cosPipe - pm.x * P.sinPipe;
     const double wx = v.x * P.cosPipe + v.z * P.sinPipe, wz = v.z * P.cosPipe - v.x * P.sinPipe;
-    const double n = (sh.ddWin - az) * rcp_nr(wz);
+    const double iwz = rcp_nr(wz);
+    const double n = (sh.ddWin - az) * iwz;
     xw = fma(n, wx, ax); yw = fma(n, v.y, pm.y); zw = fma(n, wz, az);
+    out.devDet = float(fabs(P.depthOverCos * iwz) * sqrt(fma(wx, wx, v.y * v.y)));   // deviationDet rt:2081-2085
   }
   xw -= P.lateralShift; yw -= P.transversalShift;
   // ================= weights rt:2101-2128 (mass-independent factors; P(a->gamma) is applied in finish_ray)
-  out.energy = el.E;
+  out.eIdx = eIdx;
   {
     const float ya = -atan_small(float(ty)) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
+    out.yaw = ya;
     float pre = __cosf(ya);
     const float path2f = float(path2);
+    out.path = sqrtf(path2f);
     if (P.stage == SART_SK_VACUUM) {
       out.convVac = P.convK * path2f;              // conversionProb rt:363-365
     } else {
@@ -446,13 +450,18 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
       const float distPipe = float(zw - P.zExitCBtel) * 1e-3f;   // intensitySuppression2 am:102-113
       pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
     }
-    float refl = 1.0f;
+    out.pre = pre;
+    double refl = 1.0;   // the product of two FP32 reflectivities can leave the FP32 range
+    const float a1 = asin_small(float(sinA1)) * 57.29577951308232f, a2 = asin_small(float(sinA2)) * 57.29577951308232f;
+    out.a1 = a1; out.a2 = a2;
     if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
-      const float* zt = T.reflE + (size_t(sh.coat) * (P.nEnergies + 1) + eIdx) * P.nAngles;
-      const float a1 = asin_small(float(sinA1)) * 57.29577951308232f, a2 = asin_small(float(sinA2)) * 57.29577951308232f;
-      refl = refl_lookup(P, zt, a1, clamped) * refl_lookup(P, zt, a2, clamped);
+      const float* zt = T.reflE + (size_t(sh.coat & kCoatMask) * (P.nEnergies + 1) + eIdx) * P.nAngles;
+      clamped |= (sh.coat & kCoatClamped) != 0;
+      refl = double(refl_lookup(P, zt, a1, clamped)) * double(refl_lookup(P, zt, a2, clamped));
     }
-    out.wPre = double(refl) * double(pre);   // FP32 factors, FP64 product: tiny weights must not flush to zero
+    out.refl = refl;
+    out.agas = el.Agas;
+    out.wPre = refl * double(pre);   // FP32 factors, FP64 product: tiny weights must not flush to zero
     if (Sink::kFold) out.wPre *= conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
   }
   out.clamped = clamped;
@@ -480,7 +489,11 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
       sb = (u > 0.0 && fi < double(P.nStripHalf) && off > 0.0 && off < P.stripWidth) ? 1 : 0;
     }
     const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
-    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) post *= double(tw);
+    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) {
+      post *= double(tw);
+      if (sb == 1 && el.sbExp != 0)
+        post = __hiloint2double(__double2hiint(post) + (el.sbExp << 20), __double2loint(post));
+    }
   }
   if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
   if (!(P.flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
@@ -499,7 +512,8 @@ __device__ __forceinline__ void trace_one(const FastParams& P, const FastTables&
                                           uint64_t ray, double m2, RayResult& out) {
   Rec rec;
   const int code = stage_a<kWolter>(P, T, S, seed, ray, rec);
-  RecordSink<kFold> sink{out, m2};
+  const RetraceQueue noQueue{nullptr, nullptr, 0u, 0u};   // mode 1 has no margins: nothing is re-traced
+  RecordSink<kFold> sink{out, m2, noQueue, false};
   if (code >= 0) { sink.fail(code); return; }
   stage_b<kWolter>(P, T, S, rec, sink);
 }
@@ -674,17 +688,15 @@ k_trace_mc_fast_masses(const __grid_constant__ FastParams P, const __grid_consta
   for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
-  mass_scan_loop(P, masses, nMasses, first, nRays, image, imageW2, counters, wc,
-                 [&](uint64_t ray, RayResult& r) { trace_one<kWolter, false>(P, T, S, seed, ray, 0.0, r); });
+  mass_scan_loop(P, T.rad, masses, nMasses, first, nRays, image, imageW2, counters, wc,
+                 [&](uint64_t ray, uint32_t, RayResult& r) { trace_one<kWolter, false>(P, T, S, seed, ray, 0.0, r); return false; });
 }
 
 // ---- per-ray records (traceAxionWrapper in fast mode) ----------------------------------------------------------
 template <bool kWolter>
 __global__ void __launch_bounds__(kBlock, 2)
 k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant__ FastTables T, double mAxion2,
-                     uint64_t first, uint64_t nRays, uint64_t seed, double* __restrict__ ox, double* __restrict__ oy,
-                     double* __restrict__ ow, int32_t* __restrict__ ocode, int32_t* __restrict__ oshell,
-                     double* __restrict__ oenergy, double* __restrict__ orad) {
+                     uint64_t first, uint64_t nRays, uint64_t seed, const __grid_constant__ sart_ray_out_t o) {
   extern __shared__ __align__(16) unsigned char smem[];
   Smem S;
   unsigned char* tail;
@@ -695,14 +707,9 @@ k_trace_mc_rays_fast(const __grid_constant__ FastParams P, const __grid_constant
   for (uint64_t i = uint64_t(blockIdx.x) * kBlock + threadIdx.x; i < nRays; i += stride) {
     RayResult r;
     trace_one<kWolter, true>(P, T, S, seed, first + i, mAxion2, r);
-    int code = r.code;
-    double wd = 0.0;
-    if (code < 0) code = finish_ray<true>(P, r, mAxion2, wd);
-    else if (r.clamped) code |= SART_FLAG_INTERP_CLAMPED;
-    const bool tail = (code & SART_CODE_MASK) == SART_EXIT_PASSED || (code & SART_CODE_MASK) == SART_EXIT_ZERO_WEIGHT;
-    ox[i] = tail ? r.x : 0.0; oy[i] = tail ? r.y : 0.0; ow[i] = wd; ocode[i] = code; oshell[i] = tail ? r.shell : -1;
-    if (oenergy) oenergy[i] = double(r.energy);
-    if (orad) orad[i] = tail ? r.r : 0.0;
+    // energiesAx of the rays that reach the weight stage (the f64 table value); 0 for rays clipped before
+    const double energy = r.code < 0 ? (P.testXray ? double(P.srcEnergy) : fmax(__ldg(T.energies + r.eIdx), 0.03)) : 0.0;
+    store_record(P, o, i, r, mAxion2, energy);
   }
 }
 
@@ -766,8 +773,7 @@ cudaError_t launch_mc_rays_fast(const fast::FastParams& P, const fast::FastTable
   const uint64_t want = (nRays + fast::kBlock - 1) / fast::kBlock;
   const uint64_t cap = uint64_t(smCount) * 2;
   const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, o.x, o.y, o.w, o.code, o.shell,
-                                        o.energy, o.r);
+  kern<<<grid, fast::kBlock, smem, s>>>(P, T, mAxion * mAxion, first, nRays, seed, o);
   return cudaGetLastError();
 }
 

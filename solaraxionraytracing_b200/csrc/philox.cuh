@@ -53,8 +53,10 @@ SART_HD PhiloxKeys philox_round_keys(uint64_t seed) {
 SART_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    // one 32 x 32 -> 64 bit multiply (IMAD.WIDE.U32) gives both halves of a product: 2 multiplies per round instead of 4
+    const uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
+    const uint32_t hi0 = uint32_t(p0 >> 32), lo0 = uint32_t(p0);
+    const uint32_t hi1 = uint32_t(p1 >> 32), lo1 = uint32_t(p1);
     c0 = hi1 ^ c1 ^ K.k[r][0];
     c1 = lo1;
     c2 = hi0 ^ c3 ^ K.k[r][1];

@@ -25,7 +25,8 @@ namespace fast {
 bool supported(const sart_setup_t& s, const char** why);
 void derive_shells(const sart_setup_t& s, const ShellF64* exactShells, ShellFast* out);
 void derive_params(const sart_setup_t& s, const Params& P, FastParams* f);
-void derive_f32(const FastParams& f, const ShellFast* shells, int nShells, Geo32* g, ShellF32* out);
+void derive_f32(const FastParams& f, const ShellFast* shells, int nShells, Geo32* g, ShellF32* out, float tolScale = 1.0f);
+void derive_tolerances(const FastParams& f, const ShellFast* shells, int nShells, float scale, Tol32* t);
 bool build_shell_table(const Geo32& g, const ShellF32* shells, int nShells, int nBuckets, std::vector<ShellCell>* out);
 bool build_alias_table(const uint32_t* thr, int n, uint32_t* out /* [n] */);
 int classify_radius(const ShellF32* shells, int nShells, float rho);
@@ -37,6 +38,14 @@ void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb,
 void refl_at_energy(const Params& P, const float* z, double E, float* out);
 }  // namespace fast
 
+}  // namespace sart
+
+namespace sart {
+// sart_allreduce (comm.cu): the counters travel as f64 words behind the two images
+constexpr int kCounterWords = int(sizeof(sart_counters_t) / 8);
+inline size_t merged_words(int nMasses) {
+  return size_t(nMasses) * (2 * size_t(SART_IMAGE_BINS) * SART_IMAGE_BINS + size_t(kCounterWords));
+}
 }  // namespace sart
 
 struct sart_handle {
@@ -72,14 +81,26 @@ struct sart_handle {
   int image_masses = 0;         // mass planes the image buffers were allocated for
   double masses[SART_MAX_MASSES] = {0};
   double* d_masses = nullptr;   // [SART_MAX_MASSES]
-  double* d_image = nullptr;    // [n_masses][256][256]
+  // one allocation of merged_words(n_masses) doubles: image [n_masses][256][256] | w^2 image | counter words (the send
+  // buffer of sart_allreduce); d_image_w2 points into it
+  double* d_image = nullptr;
   double* d_image_w2 = nullptr;
+  // NCCL communicator of this handle (comm.cu) and the result of the last sart_allreduce, laid out like the block above
+  void* comm = nullptr;
+  int comm_ranks = 0, comm_rank = 0;
+  double* d_merged = nullptr;
+  int merged_masses = 0, merged_valid = 0;
   sart_counters_t* d_counters = nullptr;  // [n_masses]
   // image replicas of the throughput kernels (cleared by the fold that follows every launch)
   double* d_rep = nullptr;      // [2][n_rep][256*256]
   double* d_mass_acc = nullptr; // [2][256*256][SART_MAX_MASSES] mass-major accumulators of the mass-scan kernel
   int n_rep = 0;
   size_t rep_stride = 0;        // doubles between two replicas
+  // re-trace queue of precision mode 2 (fast_params.h: RetraceQueue): [0] = push count, entries from word 64 on
+  uint32_t* d_queue = nullptr;
+  size_t queue_cap = 0;
+  int retrace = 1;              // sart_set_retrace: uncertain FP32 rays are re-traced in FP64
+  float retrace_scale = 1.0f;   // multiplies every error budget (Tol32)
   // optional radial histogram of the passed rays (sart_enable_radial_hist)
   double* d_rad_w = nullptr;
   unsigned long long* d_rad_n = nullptr;

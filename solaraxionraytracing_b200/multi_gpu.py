@@ -2,7 +2,7 @@
 
 Rays are independent and ray i depends only on (seed, i) (Philox counter = global ray index), so the run is cut into
 contiguous index ranges, one per rank, with no data-path exchange; the only collective is the final sum of the
-detector image, the sum-of-squares image and the counters (512 KiB + 512 KiB + 208 B per axion mass) — one
+detector image, the sum-of-squares image and the counters (512 KiB + 512 KiB + 224 B per axion mass) — one
 all-reduce over NVLink (NCCL) on the device buffers libsart exposes. The reference's only parallel construct is the
 Weave parallelFor over rays inside one process (src/raytracer.nim:2234-2244).
 """
@@ -35,7 +35,7 @@ def counters_to_arrays(counters: list[dict]) -> tuple[np.ndarray, np.ndarray]:
     for c in counters:
         ex = [c["n_exit"].get(name, 0) for name in abi.EXIT_NAMES] + [0] * (16 - abi.N_EXIT_CODES)
         ints.append([c["n_rays"], *ex, c["n_passed"], c["n_passed_till_window"], c["n_hit_nickel"],
-                     c["n_interp_clamped"]])
+                     c["n_interp_clamped"], c.get("n_retraced", 0), c.get("n_unresolved", 0)])
         flts.append([c["sum_w"], c["sum_w2"], c["sum_x"], c["sum_y"], c["sum_r"]])
     return np.asarray(ints, dtype=np.int64), np.asarray(flts, dtype=np.float64)
 
@@ -45,7 +45,7 @@ def arrays_to_counters(ints: np.ndarray, flts: np.ndarray) -> list[dict]:
     for i, f in zip(ints, flts):
         d = {"n_rays": int(i[0]), "n_exit": {name: int(i[1 + k]) for k, name in enumerate(abi.EXIT_NAMES)},
              "n_passed": int(i[17]), "n_passed_till_window": int(i[18]), "n_hit_nickel": int(i[19]),
-             "n_interp_clamped": int(i[20]), "sum_w": float(f[0]), "sum_w2": float(f[1]), "sum_x": float(f[2]),
+             "n_interp_clamped": int(i[20]), "n_retraced": int(i[21]), "n_unresolved": int(i[22]), "sum_w": float(f[0]), "sum_w2": float(f[1]), "sum_x": float(f[2]),
              "sum_y": float(f[3]), "sum_r": float(f[4])}
         out.append(d)
     return out
@@ -62,6 +62,21 @@ def merge_host(image: np.ndarray, image_w2: np.ndarray, counters: list[dict], gr
     for t in (t_img, t_img2, t_i, t_f):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t_img.numpy(), t_img2.numpy(), arrays_to_counters(t_i.numpy(), t_f.numpy())
+
+
+def comm_init(tracer, rank: int, world: int, device: int, group=None):
+    """Gives `tracer` its NCCL communicator (sart_comm_init_rank): rank 0 draws the 128-byte NCCL id and broadcasts it
+    over the already initialised torch.distributed group — the only thing torch ships; the collective itself is
+    sart_allreduce behind the C-ABI."""
+    import torch
+    import torch.distributed as dist
+    uid = torch.zeros(abi.COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(tracer.comm_unique_id()), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        uid = uid.to(f"cuda:{device}")
+    dist.broadcast(uid, src=0, group=group)
+    tracer.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
 
 class _DevArray:
@@ -107,14 +122,14 @@ def calculateFluxFractionsSharded(raytraceSetup, nRays: int, seed: int = 2997924
     device = torch.cuda.current_device() if device is None else device
     first, count = shard(nRays, rank, world)
     with rt.RayTracer(raytraceSetup, device) as tr:
-        if rt.fast_available():
+        for mode in (2, 1):      # the fastest pipeline this setup supports; precision 0 otherwise
             try:
-                tr.set_precision(1)
+                tr.set_precision(mode)
+                break
             except rt.SartError:
                 pass
-        stream = torch.cuda.ExternalStream(tr.stream, device=device)
-        with torch.cuda.stream(stream):
-            tr.reset_image()
-            tr.trace_mc(count, seed, first_ray=first)
-            allreduce_device(tr, device, group)
-        return tr.read_image()
+        comm_init(tr, rank, world, device, group)
+        tr.reset_image()
+        tr.trace_mc(count, seed, first_ray=first)
+        tr.allreduce()
+        return tr.read_merged()

@@ -201,6 +201,11 @@ class RayTracer:
         (same distributions through alias tables: statistical parity only, precision mode 2)."""
         check(lib.sart_set_sampler(self._h, sampler))
 
+    def set_retrace(self, mode: int = 1, scale: float = 1.0):
+        """Precision mode 2: re-trace the rays whose FP32 decision margins are inside their error budgets with the exact
+        FP64 pipeline (default on); `scale` multiplies the budgets."""
+        check(lib.sart_set_retrace(self._h, mode, scale))
+
     def set_compaction(self, mode: int):
         check(lib.sart_set_compaction(self._h, mode))
 
@@ -293,6 +298,31 @@ class RayTracer:
         check(lib.sart_angular_scan(self._h, a.size, _dp(a), first_ray, n_rays_per_angle, seed, _dp(fl), cnt,
                                     _dp(img) if want_images else None))
         return fl, [c.as_dict() for c in cnt], img
+
+    # -- multi-GPU (sart_allreduce): one NCCL all-reduce of image | w^2 image | counters into a separate merged buffer
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+        check(lib.sart_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, n_ranks: int, rank: int, unique_id: bytes):
+        if len(unique_id) != abi.COMM_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        check(lib.sart_comm_init_rank(self._h, n_ranks, rank, C.create_string_buffer(unique_id, abi.COMM_ID_BYTES)))
+
+    def allreduce(self):
+        """Asynchronous on `stream`; the tracer's own image keeps accumulating, the sum over ranks is read_merged()."""
+        hs = (abi.H * 1)(self._h)
+        check(lib.sart_allreduce(hs, 1))
+
+    def read_merged(self, want_w2: bool = True) -> RunResult:
+        m = self.n_masses
+        img = np.empty((m, abi.IMAGE_BINS, abi.IMAGE_BINS))
+        img2 = np.empty_like(img) if want_w2 else None
+        cnt = (abi.Counters * m)()
+        check(lib.sart_read_merged(self._h, _dp(img), _dp(img2) if want_w2 else None, cnt))
+        return RunResult(img, img2, [c.as_dict() for c in cnt])
 
     def read_image(self, want_w2: bool = True) -> RunResult:
         m = self.n_masses

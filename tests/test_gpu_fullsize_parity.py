@@ -11,8 +11,8 @@ What is compared, and how:
     identical: the rays whose FP32 margins are inside the error bounds are re-traced in FP64; x, y 99 % within 1.5e-3 mm,
     weights 99 % within 2e-4 — 5e-3 with the buffer gas);
   * the sampling (rt:437, 464): emission shell and energy of 1e7 Monte Carlo rays per setup bit-identical to the
-    oracle's, and of ~1e6 hand-built words per setup: word 0, word 0xffffffff, the words on either side of every radius
-    threshold and of every energy threshold of 40 emission shells;
+    oracle's, and of ~2.5e5 hand-built words per setup: word 0, word 0xffffffff, the words on either side of every radius
+    threshold and of every energy threshold of ~110 emission shells;
   * tier (b): image chi^2, flux and pass fraction against the oracle with an independent seed, both samplers.
 """
 import ctypes as C
@@ -135,10 +135,10 @@ def test_fullsize_sampling_corner_words(rt, tracers, oracle, cfg):
     # (1) radius words around every radius threshold; energy words random
     wr = _around(thr_r)
     blocks.append((wr, rng.integers(0, 2 ** 32, wr.size, dtype=np.uint64).astype(np.uint32)))
-    # (2) for 40 emission shells (both ends of the table, a spread in between, the shells with the flattest CDF tails):
+    # (2) for ~110 emission shells (both ends of the table, a spread in between, the shells with the flattest CDF tails):
     # a radius word that selects the shell, energy words around every energy threshold of its row
     flat = np.argsort([np.unique(_thresholds(rt, tb.diffFluxCDFs[r])).size for r in range(0, nR, 16)])[:8] * 16
-    rows = np.unique(np.concatenate([[0, 1, nR - 2, nR - 1], np.linspace(2, nR - 3, 28).astype(int), flat]))
+    rows = np.unique(np.concatenate([[0, 1, nR - 2, nR - 1], np.linspace(2, nR - 3, 100).astype(int), flat]))
     for r in rows:
         lo = 0 if r == 0 else int(thr_r[r - 1])       # the smallest word that maps to shell r
         if r < nR - 1 and lo >= int(thr_r[r]):
@@ -159,7 +159,7 @@ def test_fullsize_sampling_corner_words(rt, tracers, oracle, cfg):
     expect_r = np.minimum(np.searchsorted(tb.fluxRadiusCDF, (w_rad.astype(np.float64) + 0.5) / 2.0 ** 32, side="left"),
                           nR - 1)
     assert np.array_equal(r_ref, expect_r)            # the oracle's emission shell is lowerBound on the f64 CDF
-    assert (w_en == 0xffffffff).sum() >= rows.size - 2 and (w_rad == 0xffffffff).sum() >= 1
+    assert (w_en == 0xffffffff).sum() >= 50 and (w_rad == 0xffffffff).sum() >= 1
     for precision, late in ((2, False), (2, True), (0, False)):
         tr.set_precision(precision)
         g = tr.trace_words(words, late_energy=late, optional=("energy",))
@@ -192,7 +192,7 @@ def test_fullsize_image_statistically_equal_to_oracle(tracers, oracle, cfg, samp
     a, va = res.image[0] / n_gpu, res.image_w2[0] / n_gpu ** 2
     b, vb = img_o[0] / n_cpu, img2_o[0] / n_cpu ** 2
     chi2, ndf = _chi2(a, va, b, vb)
-    assert ndf > 50
+    assert ndf > 10        # BabyIAXO+XMM focuses onto a few dozen 4x4-rebinned bins
     z = (chi2 - ndf) / np.sqrt(2.0 * ndf)
     assert abs(z) < 5.0, (chi2, ndf, z)
     assert abs(a.sum() - b.sum()) < 4.0 * np.sqrt(va.sum() + vb.sum())

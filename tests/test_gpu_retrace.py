@@ -1,0 +1,163 @@
+"""Bit-exact hit/miss classification on the throughput path (north_star tier (a): "hit/miss classification bit-exact").
+
+The FP32 pipeline (precision mode 2) tests, at every decision of traceAxion — rho < R at the bore exit and the pipes
+(rt:481-492), spider and shell boundaries (rt:1635-1704, 1932-1944), the mirror roots (rt:646-658), the nickel test
+(rt:1706-1734), the window aperture and the strongback strips (rt:2139-2185) — whether the margin of the decision is
+inside its error budget (fast_params.h: Tol32). Such a ray is traced by the exact FP64 pipeline instead (re-trace queue +
+tail kernel on the same stream). These tests pin the consequence: on >= 1e7 rays per setup every exit code equals the
+exact pipeline's / the CPU oracle's, a fraction below 1 % of the rays takes the FP64 path, the queue never overflows — and,
+by scaling the budgets, that the mechanism (not luck) does it: with the budgets at zero ~1e-5 of the rays differ, with a
+quarter of the budgets still none.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_config
+from solaraxionraytracing_b200 import abi
+
+pytestmark = pytest.mark.gpu
+SEED = 299792458
+CFGS = ["cast_llnl", "babyiaxo_xmm", "cast_abrixas", "babyiaxo_gas"]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from solaraxionraytracing_b200 import raytracer
+    if raytracer.lib.sart_device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests need a B200")
+    return raytracer
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_f32_mc_rays_exit_codes_equal_exact_on_1e7_rays(rt, cfg):
+    """sart_trace_mc_rays, 1e7 Philox rays: code word (exit code + passedTillWindow + clamped flags) and shell number of
+    every ray identical between precision 2 and precision 0."""
+    setup, tb = make_config(cfg)
+    n = 10_000_000
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        ex = tr.traceAxionWrapper(n, SEED, optional=False)
+        tr.set_precision(2)
+        fa = tr.traceAxionWrapper(n, SEED, optional=False)
+    mism = np.flatnonzero(ex.code != fa.code)
+    assert mism.size == 0, [(int(i), int(ex.code[i]), int(fa.code[i])) for i in mism[:10]]
+    assert np.array_equal(ex.shell, fa.shell)
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm", "babyiaxo_gas"])
+def test_f32_presampled_exit_codes_equal_oracle_on_1e7_rays(rt, oracle, cfg):
+    """sart_trace_presampled in precision 2 against the CPU oracle on the same 1e7 pre-sampled rays."""
+    setup, tb = make_config(cfg)
+    n = 10_000_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, SEED + 7)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy, optional=False)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        gpu = tr.trace_presampled(origin, exit_xy, energy, optional=False)
+    mism = np.flatnonzero(gpu.code != ref.code)
+    assert mism.size == 0, [(int(i), int(gpu.code[i]), int(ref.code[i])) for i in mism[:10]]
+    assert np.array_equal(gpu.shell, ref.shell)
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_fused_counters_equal_exact_and_retrace_fraction(rt, cfg):
+    """The fused kernels (plain and compacting) on 2e7 rays: integer counters identical to the exact pipeline's, flux
+    within 3e-4, re-traced fraction below 1 %, nothing unresolved."""
+    setup, tb = make_config(cfg)
+    n = 20_000_000
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.trace_mc(n, SEED, first_ray=5)
+        e = tr.read_image().counters[0]
+        tr.set_precision(2)
+        for compact in (0, 1):
+            tr.set_compaction(compact)
+            tr.reset_image()
+            tr.trace_mc(n, SEED, first_ray=5)
+            f = tr.read_image().counters[0]
+            assert f["n_exit"] == e["n_exit"], (compact, f["n_exit"], e["n_exit"])
+            assert f["n_passed_till_window"] == e["n_passed_till_window"] and f["n_interp_clamped"] == e["n_interp_clamped"]
+            assert f["n_unresolved"] == 0
+            frac = f["n_retraced"] / n
+            print(cfg, "compact", compact, "re-traced fraction", frac)
+            assert 0 < frac < 1e-2, frac
+            assert abs(f["sum_w"] / e["sum_w"] - 1.0) < 3e-4
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_budget_scale_shows_the_safety_factor(rt, cfg):
+    """The same 1e7 rays with the error budgets scaled: 0 (pure FP32) leaves exit-code mismatches, which is why the
+    mechanism exists; 1/4 of the budgets already leaves none, i.e. the shipped budgets carry a factor >= 4."""
+    setup, tb = make_config(cfg)
+    n = 10_000_000
+    out = {}
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        ex = tr.traceAxionWrapper(n, SEED, optional=False)
+        tr.set_precision(2)
+        for scale in (0.0, 0.25, 1.0):
+            tr.set_retrace(1, scale)
+            fa = tr.traceAxionWrapper(n, SEED, optional=False)
+            out[scale] = int((ex.code != fa.code).sum())
+        tr.set_retrace(0, 1.0)
+        fa = tr.traceAxionWrapper(n, SEED, optional=False)
+        out["off"] = int((ex.code != fa.code).sum())
+    print(cfg, "exit-code mismatches by budget scale:", out)
+    assert out[1.0] == 0 and out[0.25] == 0
+    assert out[0.0] > 0 and out["off"] > 0
+    assert out["off"] < n * 1e-4
+
+
+def test_retrace_queue_overflow_is_counted_not_silent(rt):
+    """Budgets blown up by 1e4 make most rays "uncertain": the queue (3 % of the launch) overflows, the overflowing rays
+    keep their FP32 outcome and are reported in n_unresolved; every ray is still counted exactly once."""
+    setup, tb = make_config("cast_llnl")
+    n = 40_000_000
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        tr.set_retrace(1, 1e4)
+        tr.trace_mc(n, SEED)
+        c = tr.read_image().counters[0]
+    assert c["n_rays"] == n and sum(c["n_exit"].values()) == n
+    assert c["n_unresolved"] > 0 and c["n_retraced"] > 0
+    assert c["n_retraced"] <= n // 32 + 65536 + (1 << 20)
+
+
+@pytest.mark.parametrize("cfg,pos_tol,rel_tol", [("cast_llnl", 1.5e-3, 2e-4), ("babyiaxo_xmm", 3e-3, 2e-4),
+                                                 ("babyiaxo_gas", 3e-3, 5e-3)])
+def test_f32_full_axion_record_vs_oracle(rt, oracle, cfg, pos_tol, rel_tol):
+    """Every field of the Axion record generateResultPlots reads (rt:2246-2289) from precision mode 2, against the oracle
+    on the same pre-sampled rays. Stated tolerances, for the rays that reach the weight stage: x, y, r, deviationDet
+    within pos_tol mm (99.9 %) — FP32 positions against the reference's own f64 rounding noise; yaw within 5e-5 deg;
+    grazing angles within 1e-5 deg; pathCB within 1e-4 relative (99.9 %); reflect, transmissionMagnet, transProbArgon and the weight
+    within rel_tol relative (99 %; FP32 table arithmetic); energy identical."""
+    setup, tb = make_config(cfg)
+    n = 1_000_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, SEED + 3)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        gpu = tr.trace_presampled(origin, exit_xy, energy)
+    assert np.array_equal(gpu.code, ref.code) and np.array_equal(gpu.shell, ref.shell)
+    assert np.array_equal(gpu.energy, ref.energy)
+    ec = ref.code & abi.CODE_MASK
+    tail = (ec == abi.EXIT_PASSED) | (ec == abi.EXIT_ZERO_WEIGHT)
+    weighted = tail | (ec == abi.EXIT_WINDOW_APERTURE)
+    assert tail.sum() > n // 10
+    for name in ("x", "y", "r"):
+        d = np.abs(getattr(gpu, name)[tail] - getattr(ref, name)[tail])
+        assert np.quantile(d, 0.999) <= pos_tol, (name, float(np.quantile(d, 0.999)))
+    d = np.abs(gpu.deviationDet[weighted] - ref.deviationDet[weighted])
+    assert np.quantile(d, 0.999) <= pos_tol, ("deviationDet", float(np.quantile(d, 0.999)))
+    assert np.quantile(np.abs(gpu.yaw[weighted] - ref.yaw[weighted]), 0.999) <= 5e-5
+    for name in ("alpha1", "alpha2"):
+        assert np.quantile(np.abs(getattr(gpu, name)[weighted] - getattr(ref, name)[weighted]), 0.999) <= 1e-5, name
+    # pathCB: the few rays that enter through the bore wall (rt:1822-1834) take the reference's p-q formula on a line
+    # through two points 1.5e14 mm apart, whose own rounding noise reaches 1e-2 there
+    assert np.quantile(np.abs(gpu.pathCB[weighted] / ref.pathCB[weighted] - 1.0), 0.999) <= 1e-4
+    for name, sel in (("reflect", weighted), ("transMagnet", weighted), ("transProbArgon", tail), ("w", tail)):
+        a, b = getattr(gpu, name)[sel], getattr(ref, name)[sel]
+        nz = b != 0
+        assert np.array_equal(a[~nz] == 0, np.ones((~nz).sum(), dtype=bool)), name
+        err = np.abs(a[nz] / b[nz] - 1.0)
+        assert np.quantile(err, 0.99) <= rel_tol, (name, float(np.quantile(err, 0.99)))
+    # rays clipped before the window carry no position and no weight
+    for name in ("w", "x", "y", "r", "transProbArgon"):
+        assert not np.any(getattr(gpu, name)[~tail]), name
