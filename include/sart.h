@@ -307,6 +307,34 @@ int sart_trace_presampled_dev(sart_handle_t* h, size_t n, const double* d_origin
  * streams or GPUs traces the same rays. */
 int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t seed, const sart_ray_out_t* out);
 
+/* ---- the same drop-in for consumers that only read the rays that PASS (generateResultPlots rt:2246-2289 filters
+ * `axions.filterIt(it.passed)` before it touches any field): the records of the passed rays only, compacted on the device
+ * and in single precision where the pipeline computes in single precision, so that the clipped rays (14 % CAST+LLNL, 77 %
+ * BabyIAXO+XMM) are not shipped over PCIe at all. Order is arbitrary; `ray` tells which ray a record belongs to (ray index
+ * - first_ray). Every array is optional (NULL to skip) and must hold `capacity` records; *n_passed returns how many rays
+ * passed (SART_ERR_ARG if more than capacity: the first `capacity` records are valid). counters (optional, host): the
+ * whole-run counters of these rays, as sart_read_image would return them. Precision mode 2, inverse-CDF sampler, single
+ * axion mass; uncertain rays are re-traced in FP64 like everywhere else (sart_set_retrace). */
+typedef struct {
+  uint32_t* ray;         /* ray index - first_ray */
+  float* x;              /* pointdataX (chip frame, mm) rt:2214 */
+  float* y;              /* pointdataY rt:2215 */
+  float* w;              /* weights rt:2216 */
+  uint8_t* shell;        /* shellNumber rt:2198 */
+  float* energy;         /* energiesAx [keV] rt:2197 */
+  float* r;              /* pointdataR rt:2202 */
+  float* reflect;        /* rt:2126 */
+  float* transMagnet;    /* transmissionMagnet rt:2120 */
+  float* yaw;            /* yawAngles rt:2123 */
+  float* alpha1;         /* grazing angles [deg] */
+  float* alpha2;
+  float* pathCB;         /* rt:1843 */
+  float* deviationDet;   /* rt:2085 */
+  float* transProbArgon; /* rt:2193 */
+} sart_passed_out_t;
+int sart_trace_mc_passed(sart_handle_t* h, uint64_t first_ray, uint64_t n, uint64_t seed, size_t capacity,
+                         const sart_passed_out_t* out, uint64_t* n_passed, sart_counters_t* counters);
+
 /* ---- test hook: sart_trace_mc_rays with the six random words of every ray supplied by the caller (SoA [6][n]: phi_sun,
  * theta_sun, radius, disc r, disc phi, energy; uniform = (word + 0.5) 2^-32) instead of drawn from Philox, so that tests
  * can drive the integer inverse-CDF search (rt:437, 464) through its corners — word 0, word 0xffffffff, the words on

@@ -35,35 +35,68 @@ def build_parser() -> argparse.ArgumentParser:
                     help="alias: emission shell / energy from alias tables of the same distributions (f32, single mass)")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--outputPath", default="", help="overrides [Resources].outputPath")
+    ap.add_argument("--allowSynthetic", action="store_true",
+                    help="continue with stand-in tables (and a warning) when a [Resources] input file is missing; the "
+                         "reference stops in that case")
     return ap
 
 
-def load_tables(rt, tables, res, setup, device: int):
+def _substitute(what: str, missing, used: str, allow: bool):
+    """The reference fails hard when a [Resources] file is missing (rt:2647, 1174, 1498). A stand-in changes the physics
+    of the result, so it is used only with --allowSynthetic, and never silently."""
+    msg = f"{what}: {missing} not found"
+    if not allow:
+        raise SystemExit(f"raytracer: {msg}. The reference stops here; pass --allowSynthetic to continue with {used}.")
+    print(f"WARNING: {msg}; using {used}. The image and flux below do NOT come from the reference's input data.",
+          file=sys.stderr)
+
+
+def load_tables(rt, tables, res, setup, device: int, allow_synthetic: bool = False):
     """initFullSetup's inputs (rt:2645-2705, 1160-1249, 1498-1527): files under [Resources] when they exist."""
+    from . import abi
     base = Path(res.resourcePath)
     csv = base / res.solarModelFile
     if res.solarModelFile and csv.is_file():
         em = tables.read_solar_model_dataframe(csv)
     else:
         raw = base / res.rawSolarModel
-        sm = tables.read_solar_model(raw) if res.rawSolarModel and raw.is_file() else None
+        have_raw = bool(res.rawSolarModel) and raw.is_file()
+        _substitute("solar model", csv, "Primakoff-only emission rates computed on the GPU from "
+                    + (str(raw) if have_raw else "the packaged AGSS09 model"), allow_synthetic)
+        sm = tables.read_solar_model(raw) if have_raw else None
         em = rt.calculateEmissionRates(sm, ("primakoff",), device=device)
     rc, dc = rt.buildCdfs(em, device)
-    from . import abi
     llnl = setup.telescope.kind == abi.TK_LLNL
-    h5 = base / (res.llnlReflFile if llnl else res.goldReflFile)
-    lims = {}
-    if h5.is_file():
-        refl, lims["angleLim"], lims["reflEnergyLim"] = tables.reflectivity_from_h5(h5, setup.telescope.nCoatings if llnl else None)
-    elif llnl:
-        refl = tables.synthetic_reflectivity(max(1, setup.telescope.nCoatings))
+    extra = {}
+    refl = None
+    if setup.telescope.reflKind == abi.RK_EFFECTIVE_AREA:
+        # rkEffectiveArea (rt:1245-1249): the telescope transmission comes from llnlEfficiency, no reflectivity table
+        eff = base / (res.llnlEfficiency or "llnl_xray_telescope_cast_effective_area.csv")
+        if not eff.is_file():
+            raise SystemExit(f"raytracer: rkEffectiveArea needs the effective-area table {eff}")
+        header = eff.read_text().splitlines()[0].split(",")
+        if "Energy[keV]" not in header or "Transmission" not in header:
+            # the shipped csv has Energy[keV], EffectiveArea[cm^2] only; the reference reads df["Transmission"] (rt:1247-1248)
+            # and fails on it as well (the conversion from the effective area is `when false`, rt:1238-1244)
+            raise SystemExit(f"raytracer: {eff} has no 'Transmission' column (columns: {header}); the reference needs it too")
+        data = np.loadtxt(eff, delimiter=",", skiprows=1)
+        extra["telescopeTransmission"] = (data[:, header.index("Energy[keV]")], data[:, header.index("Transmission")])
     else:
-        refl = tables.gold_reflectivity_packaged()
+        h5 = base / (res.llnlReflFile if llnl else res.goldReflFile)
+        if h5.is_file():
+            refl, extra["angleLim"], extra["reflEnergyLim"] = tables.reflectivity_from_h5(h5, setup.telescope.nCoatings if llnl else None)
+        elif llnl:
+            _substitute("LLNL multilayer reflectivity", h5, "SYNTHETIC multilayer tables (made-up coatings)", allow_synthetic)
+            refl = tables.synthetic_reflectivity(max(1, setup.telescope.nCoatings))
+        else:
+            _substitute("gold reflectivity", h5, "the packaged Henke gold data (resources/reflectivity.zip, coarser grid)", allow_synthetic)
+            refl = tables.gold_reflectivity_packaged()
     try:
         det = tables.detector_tables_from_resources(base, setup.detector.windowThickness, setup.detector.alThickness)
-    except OSError:
+    except OSError as e:
+        _substitute("detector transmission tables", e.filename or base, "the packaged copies of the reference's own .tsv files", True)
         det = tables.detector_tables_packaged()
-    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl, **lims, **det)
+    return tables.TableSet(energies=em.energies, fluxRadiusCDF=rc, diffFluxCDFs=dc, reflectivity=refl, **extra, **det)
 
 
 def main(argv=None) -> int:
@@ -79,11 +112,18 @@ def main(argv=None) -> int:
     a.seed = run.seed if a.seed is None else a.seed
     a.precision = a.precision or run.precision
     outpath = a.outputPath or res.outputPath
-    tb = load_tables(rt, tables, res, setup, a.device)
+    tb = load_tables(rt, tables, res, setup, a.device, a.allowSynthetic)
     fs = rt.FullRaytraceSetup(setup, tb, outpath)
     n = int(a.nRays)
     with rt.RayTracer(fs, a.device) as tr:
-        tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[a.precision])
+        want = {"exact": 0, "fast": 1, "f32": 2}[a.precision]
+        for mode in range(want, -1, -1):     # f32 -> fast -> exact: the fastest pipeline that supports this setup
+            try:
+                tr.set_precision(mode)
+                break
+            except rt.SartError as e:
+                print(f"precision {['exact', 'fast', 'f32'][mode]} is not available for this setup ({e}); falling back",
+                      file=sys.stderr)
         if (a.sampler or run.sampler) == "alias":
             tr.set_sampler(abi.SAMPLER_ALIAS)
         if run.mAxion:

@@ -123,6 +123,16 @@ class RayOut(C.Structure):
         (n, c_double_p) for n in RAY_OUT_OPTIONAL]
 
 
+PASSED_OUT_FIELDS = (("ray", C.c_uint32), ("x", C.c_float), ("y", C.c_float), ("w", C.c_float), ("shell", C.c_uint8),
+                     ("energy", C.c_float), ("r", C.c_float), ("reflect", C.c_float), ("transMagnet", C.c_float),
+                     ("yaw", C.c_float), ("alpha1", C.c_float), ("alpha2", C.c_float), ("pathCB", C.c_float),
+                     ("deviationDet", C.c_float), ("transProbArgon", C.c_float))
+
+
+class PassedOut(C.Structure):
+    _fields_ = [(n, C.POINTER(t)) for n, t in PASSED_OUT_FIELDS]
+
+
 class Counters(C.Structure):
     _fields_ = [("n_rays", C.c_uint64), ("n_exit", C.c_uint64 * 16), ("n_passed", C.c_uint64),
                 ("n_passed_till_window", C.c_uint64), ("n_hit_nickel", C.c_uint64), ("n_interp_clamped", C.c_uint64),
@@ -185,6 +195,8 @@ SIGNATURES = {
     "sart_trace_presampled": (C.c_int, [H, C.c_size_t, c_double_p, c_double_p, c_double_p, C.POINTER(RayOut)]),
     "sart_trace_presampled_dev": (C.c_int, [H, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RayOut)]),
     "sart_trace_mc_rays": (C.c_int, [H, C.c_uint64, C.c_size_t, C.c_uint64, C.POINTER(RayOut)]),
+    "sart_trace_mc_passed": (C.c_int, [H, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.POINTER(PassedOut),
+                                       C.POINTER(C.c_uint64), C.POINTER(Counters)]),
     "sart_trace_words": (C.c_int, [H, C.c_size_t, C.POINTER(C.c_uint32), C.c_int, C.POINTER(RayOut), c_int32_p]),
     "sart_trace_mc": (C.c_int, [H, C.c_uint64, C.c_uint64, C.c_uint64]),
     "sart_reset_image": (C.c_int, [H]),

@@ -26,6 +26,7 @@ UNITS = [
     ("kernels_exact.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
     ("kernels_fast.cu", []),
     ("kernels_f32.cu", []),
+    ("kernels_f32_rays.cu", []),
     ("kernels_util.cu", []),
     ("kernels_emission.cu", []),
     ("api.cu", []),

@@ -927,6 +927,95 @@ int sart_trace_mc_rays(sart_handle_t* h, uint64_t first_ray, size_t n, uint64_t 
   return copy_out(h, n, *out, dev);
 }
 
+int sart_trace_mc_passed(sart_handle_t* h, uint64_t first_ray, uint64_t n, uint64_t seed, size_t capacity,
+                         const sart_passed_out_t* out, uint64_t* n_passed, sart_counters_t* counters) {
+  if (!h) return fail(SART_ERR_ARG, "handle is NULL");
+  if (!out || !n_passed) return fail(SART_ERR_ARG, "sart_trace_mc_passed: out and n_passed are required");
+  *n_passed = 0;
+  if (h->precision != 2) return fail(SART_ERR_CONFIG, "sart_trace_mc_passed: precision mode 2");
+  if (h->sampler != SART_SAMPLER_INVERSE_CDF || h->n_masses != 1)
+    return fail(SART_ERR_CONFIG, "sart_trace_mc_passed: inverse-CDF sampler and a single axion mass");
+  if (n > (uint64_t(1) << 32)) return fail(SART_ERR_ARG, "sart_trace_mc_passed: at most 2^32 rays per call (32-bit ray offsets)");
+  DeviceGuard dg(h->device);
+  // the fields of sart_passed_out_t in declaration order: host pointer and element size
+  void* const hostp[15] = {out->ray, out->x, out->y, out->w, out->shell, out->energy, out->r, out->reflect, out->transMagnet,
+                           out->yaw, out->alpha1, out->alpha2, out->pathCB, out->deviationDet, out->transProbArgon};
+  const size_t esize[15] = {4, 4, 4, 4, 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+  // chunks of 2^24 rays through two device buffers: the kernels of chunk k + 1 run while the records of chunk k (whose
+  // number the host learns from a 4-byte read) cross PCIe on a second stream
+  const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), uint64_t(1) << 24);
+  size_t off[15], bufBytes = 256;   // [0, 256): the record count of the chunk
+  for (int f = 0; f < 15; ++f) { off[f] = bufBytes; if (hostp[f]) bufBytes += align256(size_t(chunk) * esize[f]); }
+  const size_t cntOff = 2 * bufBytes;
+  int rc = ensure_stage(h, cntOff + align256(sizeof(sart_counters_t)));
+  if (rc) return rc;
+  if (!h->stream_in) {
+    SART_CUDA(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+    SART_CUDA(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) SART_CUDA(cudaEventCreateWithFlags(reinterpret_cast<cudaEvent_t*>(&h->ev[i]), cudaEventDisableTiming));
+  }
+  if (!h->h_stage) { SART_CUDA(cudaHostAlloc(&h->h_stage, 256, cudaHostAllocDefault)); h->h_stage_bytes = 256; }
+  unsigned int* hcount = static_cast<unsigned int*>(h->h_stage);
+  unsigned char* base = static_cast<unsigned char*>(h->d_stage);
+  sart_counters_t* dCnt = reinterpret_cast<sart_counters_t*>(base + cntOff);
+  SART_CUDA(cudaMemsetAsync(dCnt, 0, sizeof(sart_counters_t), h->stream));
+  auto evDone = [&](int b) { return static_cast<cudaEvent_t>(h->ev[b]); };
+  auto evCopied = [&](int b) { return static_cast<cudaEvent_t>(h->ev[2 + b]); };
+  auto devOut = [&](int b) {
+    sart_passed_out_t d;
+    unsigned char* p = base + size_t(b) * bufBytes;
+    void** dp[15] = {(void**)&d.ray, (void**)&d.x, (void**)&d.y, (void**)&d.w, (void**)&d.shell, (void**)&d.energy, (void**)&d.r,
+                     (void**)&d.reflect, (void**)&d.transMagnet, (void**)&d.yaw, (void**)&d.alpha1, (void**)&d.alpha2,
+                     (void**)&d.pathCB, (void**)&d.deviationDet, (void**)&d.transProbArgon};
+    for (int f = 0; f < 15; ++f) *dp[f] = hostp[f] ? static_cast<void*>(p + off[f]) : nullptr;
+    return d;
+  };
+  uint64_t total = 0;
+  bool overflow = false;
+  auto finish = [&](uint64_t k) -> int {   // chunk k: wait for its kernels, learn its record count, send the records home
+    const int b = int(k & 1);
+    SART_CUDA(cudaEventSynchronize(evDone(b)));
+    const uint64_t c = std::min<uint64_t>(hcount[b], chunk);
+    const uint64_t room = total < capacity ? capacity - total : 0;
+    const uint64_t take = std::min(c, room);
+    if (take < c) overflow = true;
+    unsigned char* p = base + size_t(b) * bufBytes;
+    for (int f = 0; f < 15 && take; ++f)
+      if (hostp[f])
+        SART_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(hostp[f]) + total * esize[f], p + off[f], take * esize[f],
+                                  cudaMemcpyDeviceToHost, h->stream_out));
+    SART_CUDA(cudaEventRecord(evCopied(b), h->stream_out));
+    total += c;
+    return SART_OK;
+  };
+  uint64_t k = 0;
+  for (uint64_t done = 0; done < n; done += chunk, ++k) {
+    const uint64_t m = std::min<uint64_t>(n - done, chunk);
+    const int b = int(k & 1);
+    unsigned int* dCount = reinterpret_cast<unsigned int*>(base + size_t(b) * bufBytes);
+    if (k >= 2) SART_CUDA(cudaStreamWaitEvent(h->stream, evCopied(b), 0));   // the records of chunk k - 2 have left this buffer
+    SART_CUDA(cudaMemsetAsync(dCount, 0, 256, h->stream));
+    fast::FastTables ft = h->ftables;
+    if ((rc = begin_queue(h, m, &ft.rq))) return rc;
+    const sart_passed_out_t d = devOut(b);
+    SART_CUDA(launch_mc_passed_f32(h->fparams, h->geo32, ft, h->masses[0], first_ray + done, m, seed, d, dCount, unsigned(chunk),
+                                   uint32_t(done), dCnt, h->sm_count, h->stream));
+    if (ft.rq.cap)
+      SART_CUDA(launch_retrace_mc_passed(h->params, h->tables, h->masses[0], first_ray + done, seed, ft.rq, d, dCount, unsigned(chunk),
+                                         uint32_t(done), dCnt, h->sm_count, h->stream));
+    SART_CUDA(cudaMemcpyAsync(hcount + b, dCount, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    SART_CUDA(cudaEventRecord(evDone(b), h->stream));
+    if (k >= 1 && (rc = finish(k - 1))) return rc;
+  }
+  if (k >= 1 && (rc = finish(k - 1))) return rc;
+  if (counters) SART_CUDA(cudaMemcpyAsync(counters, dCnt, sizeof(sart_counters_t), cudaMemcpyDeviceToHost, h->stream));
+  SART_CUDA(cudaStreamSynchronize(h->stream_out));
+  SART_CUDA(cudaStreamSynchronize(h->stream));
+  *n_passed = total;
+  if (overflow) return fail(SART_ERR_ARG, "sart_trace_mc_passed: %llu rays passed, the output arrays hold %zu", (unsigned long long)total, capacity);
+  return SART_OK;
+}
+
 int sart_trace_words(sart_handle_t* h, size_t n, const uint32_t* words, int late_energy, const sart_ray_out_t* out,
                      int32_t* emission_shell) {
   if (!h) return fail(SART_ERR_ARG, "handle is NULL");

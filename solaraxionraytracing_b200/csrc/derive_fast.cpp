@@ -129,6 +129,7 @@ void derive_tolerances(const FastParams& f, const ShellFast* a, int nShells, flo
   t->spider = float(scale * 512.0 * eps);
   t->cond = float(scale * 2e-15);
   t->zrel = float(scale * 16.0 * eps);
+  t->discRel = float(scale * 2e-3);   // |A| budget(C) / hb^2 stays below 1e-3 for every shell of the three optics
   t->ang = float(scale * 2e-5);
   t->sinA = float(scale * 8.0 * eps * (4.0 * tanMax + 0.01));
   t->circCB = float(t->circ2 * f.radiusCB2);
@@ -399,6 +400,14 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   f->shellsMonotonic = 1;
   f->rotated = (P.sinTX != 0.0 || P.sinTY != 0.0) ? 1 : 0;
   f->srcEIdx = P.nEnergies;  // the record after the tabulated energies holds the X-ray source energy
+  {
+    // largest slope of a ray from the outermost tabulated solar shell through the field-exit disc, and the largest radius
+    // it can have at the second pipe plane if it passed the bore exit; 1 mm is far above every error budget
+    const double rsMax = 0.0015 + 0.0005 * double(std::max(P.nRadii, 1) - 1);
+    const double sMax = (rsMax * s.consts.radiusSun + P.radiusCB) / (s.consts.distanceSunEarth - s.consts.radiusSun);
+    const double reach = P.radiusCB + sMax * std::fabs(P.zPipe2 - P.lengthB) * 1.5 + 1.0;
+    f->pipesFree = (!P.testXray && P.nRadii > 0 && reach < P.rPipe1 && P.zPipe2 >= P.zPipe1 && P.zPipe1 >= P.zExitCB) ? 1 : 0;
+  }
 }
 
 static void lut_entry(double E, const sart_interp1d_t& sb, const sart_interp1d_t& wd, const sart_interp1d_t& ga,

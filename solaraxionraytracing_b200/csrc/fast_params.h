@@ -49,6 +49,7 @@ struct FastParams {
   uint32_t flags;
   int32_t nRadii, nEnergies, nAngles, nReflEnergies, shellsMonotonic, srcEIdx;
   int32_t nShellGuide, rotated;
+  int32_t pipesFree, padP_;   // solar Monte Carlo rays cannot reach the pipe walls (kernels_f32.cu, stage A)
 };
 
 // ---- single-precision pipeline (kernels_f32.cu): the same blocks rounded to FP32, plus a few derived values that
@@ -89,6 +90,7 @@ struct Tol32 {
   float spider;                      // rounding of the Chebyshev spider polynomial (in units of cos(n phi))
   float cond;                        // the reference's quadratic formula loses hb^2 / |A C| digits (rt:646-658): dz |q| += cond hb^2 / |A|
   float zrel;                        // relative rounding of a root
+  float discRel;                     // a negative discriminant above -discRel hb^2 may be a rounding artefact
   float ang;                         // grazing angle against the end of the reflectivity grid [deg]
   float sinA;                        // absolute rounding of sin(alpha)
   float twoRcb, twoRpipe, twoRwin;   // 2 R of the squared-radius compares

@@ -25,6 +25,12 @@ cudaError_t launch_retrace_mc_image(const Params& P, const Tables& T, int nMasse
 cudaError_t launch_retrace_mc_rays(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n, uint64_t seed,
                                    const uint32_t* words, const fast::RetraceQueue& q, const sart_ray_out_t& out, int smCount,
                                    cudaStream_t s);
+cudaError_t launch_retrace_mc_passed(const Params& P, const Tables& T, double mAxion, uint64_t first, uint64_t seed,
+                                     const fast::RetraceQueue& q, const sart_passed_out_t& o, unsigned int* count, unsigned int cap,
+                                     uint32_t idBase, sart_counters_t* counters, int smCount, cudaStream_t s);
+cudaError_t launch_mc_passed_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
+                                 uint64_t first, uint64_t nRays, uint64_t seed, const sart_passed_out_t& o, unsigned int* count,
+                                 unsigned int cap, uint32_t idBase, sart_counters_t* counters, int smCount, cudaStream_t s);
 cudaError_t launch_retrace_presampled(const Params& P, const Tables& T, double mAxion, size_t n, const double* origin,
                                       const double* exitxy, const double* energy, const fast::RetraceQueue& q,
                                       const sart_ray_out_t& out, int smCount, cudaStream_t s);

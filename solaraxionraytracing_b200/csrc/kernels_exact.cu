@@ -135,6 +135,62 @@ k_retrace_mc_rays(const __grid_constant__ Params P, const __grid_constant__ Tabl
   }
 }
 
+// Re-trace pass of sart_trace_mc_passed: the queued rays traced exactly; those that pass are appended to the compacted
+// records (single precision, like the FP32 kernel writes them), all of them are counted.
+__global__ void __launch_bounds__(128)
+k_retrace_mc_passed(const __grid_constant__ Params P, const __grid_constant__ Tables T, double mAxion, uint64_t first,
+                    uint64_t seed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount, uint32_t listCap,
+                    const __grid_constant__ sart_passed_out_t o, unsigned int* __restrict__ count, unsigned int cap,
+                    uint32_t idBase, sart_counters_t* __restrict__ c) {
+  auto addu = [](uint64_t* p, unsigned long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), v); };
+  const uint32_t m = min(*listCount, listCap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) addu(&c->n_retraced, m);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    const uint32_t i = list[j];
+    V3 O, E;
+    double energy;
+    int clamped = 0;
+    if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped)) { addu(&c->n_exit[SART_EXIT_COLLIMATOR], 1); continue; }
+    Geo g;
+    trace_geometry<true>(P, T, O, E, energy, g);
+    g.clamped |= clamped;
+    if (g.clamped) addu(&c->n_interp_clamped, 1);
+    if (g.code >= 0) {
+      addu(&c->n_exit[g.code], 1);
+      if (g.code == SART_EXIT_NICKEL) addu(&c->n_hit_nickel, 1);
+      continue;
+    }
+    Weights w;
+    ray_weights(P, T, g, w);
+    Final f;
+    ray_finish(P, g, w, mAxion, f);
+    if (f.code & SART_FLAG_PASSED_TILL_WINDOW) addu(&c->n_passed_till_window, 1);
+    const int ec = f.code & SART_CODE_MASK;
+    addu(&c->n_exit[ec], 1);
+    if (ec != SART_EXIT_PASSED) continue;
+    addu(&c->n_passed, 1);
+    atomicAdd(&c->sum_w, f.w); atomicAdd(&c->sum_w2, f.w * f.w);
+    atomicAdd(&c->sum_x, f.x); atomicAdd(&c->sum_y, f.y); atomicAdd(&c->sum_r, f.r);
+    const unsigned int slot = atomicAdd(count, 1u);
+    if (slot >= cap) continue;
+    if (o.ray) o.ray[slot] = idBase + i;
+    if (o.x) o.x[slot] = float(f.x);
+    if (o.y) o.y[slot] = float(f.y);
+    if (o.w) o.w[slot] = float(f.w);
+    if (o.shell) o.shell[slot] = uint8_t(g.shell);
+    if (o.energy) o.energy[slot] = float(g.energy);
+    if (o.r) o.r[slot] = float(f.r);
+    if (o.reflect) o.reflect[slot] = float(w.reflect);
+    if (o.transMagnet) o.transMagnet[slot] = float(f.transMagnet);
+    if (o.yaw) o.yaw[slot] = float(g.ya);
+    if (o.alpha1) o.alpha1[slot] = float(g.alpha1);
+    if (o.alpha2) o.alpha2[slot] = float(g.alpha2);
+    if (o.pathCB) o.pathCB[slot] = float(g.pathCB);
+    if (o.deviationDet) o.deviationDet[slot] = float(g.deviationDet);
+    if (o.transProbArgon) o.transProbArgon[slot] = float(w.absGas);
+  }
+}
+
 // ---- fused Monte Carlo run -------------------------------------------------------------------------------
 // Block-level counters live in shared memory and are flushed once per block.
 struct BlockCounters {
@@ -362,6 +418,13 @@ cudaError_t launch_retrace_mc_rays(const Params& P, const Tables& T, double mAxi
                                    const uint32_t* words, const fast::RetraceQueue& q, const sart_ray_out_t& out, int smCount,
                                    cudaStream_t s) {
   k_retrace_mc_rays<<<unsigned(smCount) * 4u, 128, 0, s>>>(P, T, mAxion, first, n, seed, words, q.list, q.count, q.cap, to_dev(out));
+  return cudaGetLastError();
+}
+cudaError_t launch_retrace_mc_passed(const Params& P, const Tables& T, double mAxion, uint64_t first, uint64_t seed,
+                                     const fast::RetraceQueue& q, const sart_passed_out_t& o, unsigned int* count, unsigned int cap,
+                                     uint32_t idBase, sart_counters_t* counters, int smCount, cudaStream_t s) {
+  k_retrace_mc_passed<<<unsigned(smCount) * 4u, 128, 0, s>>>(P, T, mAxion, first, seed, q.list, q.count, q.cap, o, count, cap, idBase,
+                                                           counters);
   return cudaGetLastError();
 }
 cudaError_t launch_retrace_presampled(const Params& P, const Tables& T, double mAxion, size_t n, const double* origin,

@@ -12,774 +12,17 @@
 //   * reciprocals / square roots are MUFU seeds plus one Newton step in FP32 (2-3 FFMA).
 // Sampling (integer inverse-CDF search, Philox) and weights (FP32 factors, FP64 product and accumulation) are the very
 // same code as mode 1 (fast_common.cuh), so a ray has the same emission shell, energy and exit-disc point in all modes.
-#include <cstdio>
-#include <cstdlib>
 
-#include "fast_common.cuh"
+
+#include "trace_f32.cuh"
 
 namespace sart {
 namespace fast {
 
-// One block of 1024 threads per SM (64 registers per thread = the whole register file) instead of four of 256: the
-// per-block tables (radius thresholds + guide + shells, 27 KB) then exist once per SM instead of four times, and the
-// 81 KB of shared memory saved go to L1 — which the table gathers of this kernel live on (measured: CAST+LLNL
-// 32.7 -> 28.9 ms, BabyIAXO+XMM 23.5 -> 20.5 ms; 512 x 2 is half way).
-#ifndef SART_F32_BLOCK
-#define SART_F32_BLOCK 1024
-#endif
-#ifndef SART_F32_MINBLOCKS
-#define SART_F32_MINBLOCKS 1
-#endif
-constexpr int kBlock32 = SART_F32_BLOCK, kWarps32 = kBlock32 / 32;
-constexpr uint64_t kMaxRaysPerLaunch = uint64_t(1) << 31;   // re-trace queue entries (ray index - first ray) are 32-bit
-#ifndef SART_F32_BLOCK_M
-#define SART_F32_BLOCK_M 768
-#endif
-#ifndef SART_F32_MINBLOCKS_M
-#define SART_F32_MINBLOCKS_M 1
-#endif
-constexpr int kBlockM = SART_F32_BLOCK_M, kWarpsM = kBlockM / 32;   // mass scan: its per-mass sums need more than 64 registers
-
-__device__ __forceinline__ float rcpf_nr(float x) {
-  const float r = rcp_approx(x);
-  return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
-__device__ __forceinline__ float rsqrtf_nr(float x) {
-  const float y = rsqrt_approx(x);
-  const float h = 0.5f * x * y;
-  return fmaf(y, fmaf(-h, y, 0.5f), y);
-}
-
-// sqrt of a positive normal number: the fast path of sqrtf() (MUFU.RSQ + one Newton step, same operations, same bits)
-// without the range check and slow-path branch the compiler wraps around it.
-__device__ __forceinline__ float sqrtf_pos(float x) {
-  const float y = rsqrt_approx(x);
-  const float s = x * y;
-  return fmaf(fmaf(-s, s, x), 0.5f * y, s);
-}
-// Table rows are addressed with 32-bit element offsets (sart_create checks that every table has < 2^31 elements): one
-// wide multiply-add per address instead of the 64-bit shift/add chains of size_t arithmetic.
-__device__ __forceinline__ const uint32_t* thr_row(const FastParams& P, const FastTables& T, int rIdx) {
-  return T.energyThr + uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies));
-}
-__device__ __forceinline__ const uint16_t* guide_row(const FastTables& T, int rIdx) {
-  return T.energyGuide + uint32_t(rIdx) * uint32_t(kEnGuide);
-}
-constexpr float kMiss = __builtin_nanf("");   // "no root in range" of pick_root32
-
-struct F3 { float x, y, z; };
-
-struct Smem32 {
-  const ShellF32* shell;
-  const uint32_t* radThr;     // alias sampler: the nRadii alias entries instead (and no guide)
-  const uint16_t* radGuide;
-  const ShellCell* shellTab;
-};
-__host__ __device__ __forceinline__ size_t rad_smem_bytes(const FastParams& P, bool alias) {
-  return alias ? ((size_t(P.nRadii) * 4 + 15) & ~size_t(15)) : size_t(thr_pitch(P.nRadii)) * 4 + size_t(kRadGuide) * 2;
-}
-template <bool kAlias = false>
-__device__ __forceinline__ void smem_layout32(const FastParams& P, unsigned char* base, Smem32& s, unsigned char*& tail) {
-  size_t off = 0;
-  s.shell = reinterpret_cast<const ShellF32*>(base + off); off += (size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15);
-  s.radThr = reinterpret_cast<const uint32_t*>(base + off);
-  s.radGuide = reinterpret_cast<const uint16_t*>(base + off + (kAlias ? 0 : size_t(thr_pitch(P.nRadii)) * 4));
-  off += rad_smem_bytes(P, kAlias);
-  s.shellTab = reinterpret_cast<const ShellCell*>(base + off); off += (size_t(P.nShellGuide) * sizeof(ShellCell) + 15) & ~size_t(15);
-  tail = base + off;
-}
-template <bool kAlias = false>
-__device__ __forceinline__ void smem_fill32(const FastParams& P, const FastTables& T, const Smem32& s) {
-  for (int i = threadIdx.x; i < P.nShells * int(sizeof(ShellF32) / 4); i += blockDim.x)
-    reinterpret_cast<float*>(const_cast<ShellF32*>(s.shell))[i] = reinterpret_cast<const float*>(T.shells32)[i];
-  if (kAlias) {
-    for (int i = threadIdx.x; i < P.nRadii; i += blockDim.x) const_cast<uint32_t*>(s.radThr)[i] = __ldg(T.radiusAlias + i);
-  } else if (P.nRadii > 0) {
-    for (int i = threadIdx.x; i < thr_pitch(P.nRadii); i += blockDim.x) const_cast<uint32_t*>(s.radThr)[i] = T.radiusThr[i];
-    for (int i = threadIdx.x; i < kRadGuide / 8; i += blockDim.x)
-      reinterpret_cast<uint4*>(const_cast<uint16_t*>(s.radGuide))[i] = __ldg(reinterpret_cast<const uint4*>(T.radiusGuide) + i);
-  }
-  for (int i = threadIdx.x; i < P.nShellGuide; i += blockDim.x)
-    reinterpret_cast<uint2*>(const_cast<ShellCell*>(s.shellTab))[i] = __ldg(reinterpret_cast<const uint2*>(T.shellTab) + i);
-}
-
-// ---- margins ---------------------------------------------------------------------------------------------------------
-// SART_UNC(group, slack): slack = |margin of the decision just taken| - its error budget (fast_params.h: Tol32); the ray is
-// uncertain when the smallest slack on its way is <= 0 (one FADD + one FMNMX per decision, no predicate logic). SART_NO_MARGINS is an
-// experiment switch that compiles every margin test out (measures what they cost; not a shipped configuration).
-// The first argument names the decision group; SART_UNC_GROUPS (a bit mask, all groups by default) lets a development build
-// keep only some of them, to measure how many rays each decision sends to the re-trace queue.
-enum { kUncBore = 0, kUncOpaque = 1, kUncShell = 2, kUncMirror1 = 3, kUncMirror2 = 4, kUncNickel = 5, kUncAngle = 6,
-       kUncWindow = 7, kUncStrips = 8, kUncSlowRoot = 9 };
-#ifndef SART_UNC_GROUPS
-#define SART_UNC_GROUPS 0xffffffffu
-#endif
-#ifdef SART_NO_MARGINS
-#define SART_UNC(group, value) ((void)0)
-#else
-#define SART_UNC(group, value) do { if ((SART_UNC_GROUPS >> (group)) & 1u) slack = fminf(slack, (value)); } while (0)
-#endif
-constexpr float kSlackInf = 3.0e38f;
-// lateral position budgets of one ray before the mirrors (lat) and at the detector plane (det); `bud` is rs (emission
-// radius / solar radius; 1 for the X-ray source) for Monte Carlo rays and epsO for pre-sampled ones (Tol32)
-template <bool kPre>
-__device__ __forceinline__ void ray_budget(const Tol32& Q, float s1, float bud, float& lat, float& det) {
-  if (kPre) {
-    lat = fmaf(Q.latRef, bud, fmaf(Q.latTpre, s1, Q.latA));
-    det = fmaf(Q.detRef, bud, fmaf(Q.detTpre, s1, Q.detA));
-  } else {
-    lat = fmaf(Q.latS, bud, fmaf(Q.latT, s1, Q.latA));
-    det = fmaf(Q.detS, bud, fmaf(Q.detT, s1, Q.detA));
-  }
-}
-
-// Root choice of findPos* (rt:646-658) for A t^2 + 2 hb t + C = 0, as in kernels_fast.cu: q = -(hb + sign(hb) sq), the
-// roots are q/A (large, metres away) and C/q. Returns t with lo < t dz < hi.
-static __device__ __noinline__ float pick_root_slow32(float A, float q, float C, bool first_is_qA, float dz, float lo,
-                                                      float hi) {
-  auto in_range = [&](float num, float den) {
-    const float nd = num * dz;
-    return den > 0.0f ? (nd > lo * den && nd < hi * den) : (nd < lo * den && nd > hi * den);
-  };
-  const bool okA = in_range(q, A), okC = in_range(C, q);
-  float num, den;
-  if (first_is_qA ? okA : okC) { num = first_is_qA ? q : C; den = first_is_qA ? A : q; }
-  else if (first_is_qA ? okC : okA) { num = first_is_qA ? C : q; den = first_is_qA ? q : A; }
-  else return kMiss;
-  return num / den;
-}
-// Returns t, or NaN (kMiss) when no root lies in range: the value travels in a register — a bool + reference pair made the
-// out-of-line slow path spill t to local memory on every call (one STL + one LDL per mirror through L1TEX).
-// The interval of the mirror is given as centre and half length: the root z is a hit when |z - mid| < half.
-// Margins: tolC is the budget of C (the squared-radius difference at the start point), tolEnd that of the interval ends.
-// d z / d C = -1 / (2 (A z + hb)) = -+ 1 / (2 sqrt(disc)) exactly, so the budget of the root is tolC / (2 sqrt(disc))
-// (the safety factors sit in the budgets themselves; a near-tangent ray, disc -> 0, is uncertain by itself); tolZ returns it. Wolter optics add the
-// reference's own loss of digits in (-hb +- sqrt(hb^2 - A C)) / A for near-axial rays, where A -> 0 (Tol32::cond).
-template <int grp, bool kCond>
-__device__ __forceinline__ float pick_root32(const Tol32& Q, float A, float hb, float C, float dz, float mid, float half,
-                                             float tolC, float tolEnd, float& slack, float& tolZ) {
-  const float disc = fmaf(hb, hb, -A * C);
-  tolZ = 0.0f;
-  if (!(disc >= 0.0f)) {
-    SART_UNC(grp, -disc - fmaf(2.0f * fabsf(A), tolC, Q.zrel * hb * hb));
-    return kMiss;
-  }
-  const float rsq = rsqrtf_nr(fmaxf(disc, 1e-30f));
-  const float sq = disc * rsq;
-  const float q = -(hb + copysignf(sq, hb));
-  const float reach = fabsf(mid) + half;
-  if (fabsf(q * dz) < reach * fabsf(A)) {   // the far root q/A may lie in range as well
-    SART_UNC(kUncSlowRoot, -1.0f);
-    return pick_root_slow32(A, q, C, hb >= 0.0f, dz, mid - half, mid + half);
-  }
-  const float ts = C * rcpf_nr(q);
-  const float zs = ts * dz;
-  const float d = fabsf(zs - mid) - half;
-#ifndef SART_NO_MARGINS
-  tolZ = fmaf(Q.zrel, fabsf(zs), 0.5f * tolC * rsq);
-  if (kCond) tolZ = fmaf(0.5f * Q.cond * hb * hb, fabsf(rcp_approx(A)) * rsq, tolZ);
-  SART_UNC(grp, fabsf(d) - (tolZ + tolEnd));
-#endif
-  return d < 0.0f ? ts : kMiss;
-}
-
-// Reflection of unit vector v off unit normal n (rt:762-780 without trigonometry); returns |n.v| = sin(alpha).
-__device__ __forceinline__ float reflect32(F3 n, F3& v) {
-  const float s = fmaf(n.x, v.x, fmaf(n.y, v.y, n.z * v.z));
-  const float as = fabsf(s);
-  const float f = fmaf(2.0f * as, s, fmaf(-2.0f * s, s, 1.0f));
-  v.x = fmaf(v.x, f, -2.0f * as * n.x);
-  v.y = fmaf(v.y, f, -2.0f * as * n.y);
-  v.z = fmaf(v.z, f, -2.0f * as * n.z);
-  return as;
-}
-
-struct Rec32 {
-  float x0, y0, tx, ty;   // pointEntranceXRT (telescope frame, z = 0) and slopes dx/dz, dy/dz
-  float rho0;             // radialDist
-  float path2;            // pathCB^2
-  int hitLayer, eIdx;
-  bool clamped;
-  bool unc;               // a decision of stage A was inside its error budget (Tol32)
-  int rIdx;               // emission shell and energy word, for kernels that resolve the energy after the compaction
-  uint32_t we;
-  float bud;              // ray_budget's per-ray term: rs (Monte Carlo) or epsO (pre-sampled)
-  uint32_t id;            // ray index - first ray of the launch (re-trace queue entry), set by the kernel
-};
-
-// Alias-table lookup (fast_params.h: FastTables::radiusAlias): index of a distribution over n values for the random word w.
-__device__ __forceinline__ int alias_pick(uint32_t w, int n, uint32_t& bucket, uint32_t& coin) {
-  const uint64_t x = uint64_t(w) * uint32_t(n);
-  bucket = uint32_t(x >> 32); coin = uint32_t(x);
-  return int(bucket);
-}
-__device__ __forceinline__ int alias_resolve(uint32_t entry, uint32_t bucket, uint32_t coin) {
-  return coin < (entry & 0xfffff800u) ? int(bucket) : int(entry & 0x7ffu);
-}
-
-// Energy index rt:464 of a ray of emission shell rIdx whose energy word is `we`: idx = lowerBound(diffFluxCDFs[rIdx], u),
-// exact (integer thresholds). The three dependent gathers (guide entry, thresholds, then the caller's LUT / reflectivity
-// rows) are taken in a row here; the non-compacting kernel spreads them over stage A instead.
-template <bool kAlias = false>
-__device__ __forceinline__ int energy_index(const FastParams& P, const FastTables& T, int rIdx, uint32_t we, bool& clamped) {
-  if (kAlias) {
-    uint32_t k, coin;
-    alias_pick(we, P.nEnergies, k, coin);
-    return alias_resolve(__ldg(T.energyAlias + (uint32_t(rIdx) * uint32_t(P.nEnergies) + k)), k, coin);
-  }
-  const uint32_t kb = we >> (32 - kEnGuideBits);
-  const uint16_t* gRow = guide_row(T, rIdx);
-  const int e0 = int(__ldg(gRow + kb)) & ~3;
-  const uint32_t eOff = uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies)) + uint32_t(e0);
-  int eIdx = e0 + count_le(__ldg(reinterpret_cast<const uint4*>(T.energyThr + eOff)), we);
-  if (eIdx == e0 + 4) {
-    eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u))), we);
-    if (eIdx == e0 + 8) eIdx = thr_search_tail(thr_row(P, T, rIdx), e0 + 8, guide_upper(gRow, kb, kEnGuide, P.nEnergies), we);
-    // saturated thresholds: the f64 row decides. The all-ones word passes every threshold, so it always gets here.
-    if (we == 0xffffffffu) eIdx = lower_bound_window(T.energyCDF + size_t(rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
-  }
-  if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
-  return eIdx;
-}
-
-// Head of stage A: the ray's random words, its emission shell (rt:437, integer search in shared memory) and the load of
-// the energy-guide entry of that shell. Split off so that a kernel can run it one ray ahead: the guide entry is the first
-// of two dependent L2 round trips of the energy search, and issued an iteration early it costs no stall at all.
-struct Head32 {
-  uint32_t w[6];
-  int rIdx;
-  uint16_t guide;
-  // pre-sampled rays (tier (a)): exit-disc point, slopes and energy index supplied by the caller instead of drawn
-  float ex, ey, sx, sy;
-  float epsO;    // rounding noise of the reference's line through the caller's origin [mm] (Tol32::latRef)
-  int eIdx;
-  bool offGrid;
-};
-// kPlain (here and below): the kernel variant for the plain run — solar source, vacuum stage, telescope not turned, no
-// ignore* flag — in which those run-wide switches are compile-time constants instead of uniform branches (~5 % of the
-// instructions); every other setup takes the generic variant.
-// (the random words h.w are set by the caller: Philox for Monte Carlo rays, caller-supplied for sart_trace_words)
-template <bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
-__device__ __forceinline__ void stage_a32_head_words(const FastParams& P, const FastTables& T, const Smem32& S, Head32& h) {
-  h.rIdx = 0; h.guide = 0;
-  if (kPlain || !P.testXray) {
-    const uint32_t wr = h.w[2];
-    if (kAlias) {   // emission shell from the alias table in shared memory; the energy entry is loaded in stage A
-      uint32_t k, coin;
-      alias_pick(wr, P.nRadii, k, coin);
-      h.rIdx = alias_resolve(S.radThr[k], k, coin);
-      return;
-    }
-    const uint32_t kr = wr >> (32 - kRadGuideBits);
-    const int r0 = int(S.radGuide[kr]) & ~3;
-    int rIdx = r0 + count_le(*reinterpret_cast<const uint4*>(S.radThr + r0), wr);
-    if (rIdx == r0 + 4) {
-      rIdx += count_le(*reinterpret_cast<const uint4*>(S.radThr + r0 + 4), wr);
-      if (rIdx == r0 + 8) rIdx = thr_search_tail(S.radThr, r0 + 8, guide_upper(S.radGuide, kr, kRadGuide, P.nRadii), wr);
-      // saturated thresholds: the f64 table decides. The all-ones word passes every threshold, so it always gets here.
-      if (wr == 0xffffffffu) rIdx = lower_bound_window(T.radiusCDF, 0, P.nRadii, u01(wr));
-    }
-    rIdx = min(rIdx, P.nRadii - 1);
-    h.rIdx = rIdx;
-    if (!kLateEnergy) h.guide = __ldg(guide_row(T, rIdx) + (h.w[5] >> (32 - kEnGuideBits)));
-  }
-}
-template <bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
-__device__ __forceinline__ void stage_a32_head(const FastParams& P, const FastTables& T, const Smem32& S,
-                                               const PhiloxKeys& K, uint64_t ray, Head32& h) {
-  ray_words(K, ray, h.w);
-  stage_a32_head_words<kPlain, kLateEnergy, kAlias>(P, T, S, h);
-}
-
-// Stage A of traceAxion in FP32: sampling, bore/pipe clipping, telescope frame, opaque structures, shell (rt:1754-1957).
-// kPre: the sampling block is skipped, the ray comes from the head record (sart_trace_presampled).
-// kLateEnergy: the energy search is left to the caller (energy_index after the compaction): 2/3 of the BabyIAXO+XMM
-// rays end in this stage and never need their energy.
-template <bool kWolter, bool kPre = false, bool kPlain = false, bool kLateEnergy = false, bool kAlias = false>
-__device__ __forceinline__ int stage_a32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
-                                         const Head32& h, Rec32& rec) {
-  const uint32_t* w = h.w;
-  constexpr float k2m32 = 2.3283064365386963e-10f;  // 2^-32
-  bool clamped = false;
-
-  float ex, ey, sx, sy;
-  int eIdx;
-  int e0 = 0;
-  // energy thresholds of this ray: first group at T.energyThr[eOff]. In the plain fused kernel every ray has a row, so
-  // the test is a compile-time constant there (a null-pointer test cost two 64-bit compares + a zero fill per ray).
-  constexpr bool kRowAlways = kPlain && !kPre && !kLateEnergy;
-  bool haveRow = false;
-  uint32_t eOff = 0u;
-  uint32_t aBucket = 0u, aCoin = 0u, aEntry = 0u;   // alias sampler
-  const Tol32& Q = G.tol;
-  float slack = kSlackInf;
-  float bud = 1.0f;   // ray_budget's per-ray term
-  rec.unc = false;
-  if (kPre) {
-    ex = h.ex; ey = h.ey; sx = h.sx; sy = h.sy; eIdx = h.eIdx; clamped = h.offGrid; bud = h.epsO;
-  } else if (kPlain || !P.testXray) {
-    const int rIdx = h.rIdx;
-    if (!kLateEnergy) {
-      if (kAlias) {
-        alias_pick(w[5], P.nEnergies, aBucket, aCoin);
-        eOff = uint32_t(rIdx) * uint32_t(P.nEnergies) + aBucket;
-      } else {
-        e0 = int(h.guide) & ~3;
-        eOff = uint32_t(rIdx) * uint32_t(thr_pitch(P.nEnergies)) + uint32_t(e0);
-      }
-      haveRow = true;
-    }
-    const float rs = (0.0015f + float(rIdx) * 0.0005f);
-    bud = rs;
-    float s1, c1, s2, c2;
-    sincos_2pi(float(w[0]) * k2m32, s1, c1);
-    __sincosf(3.14159265358979f * (float(w[1]) * k2m32), &s2, &c2);
-    const float rsun = rs * G.radiusSun;
-    const float Ox = rsun * (c1 * s2), Oy = rsun * (s1 * s2), Ozr = rsun * c2;
-    float sd, cd;
-    sincos_2pi(float(w[4]) * k2m32, sd, cd);
-    const float rd = sqrtf_pos((float(w[3]) + 0.5f) * k2m32);
-    ex = G.radiusCB * (rd * cd);
-    ey = G.radiusCB * (rd * sd);
-    const float invD = rcpf_nr(G.lengthBplusSun - Ozr);   // lengthB - O.z
-    sx = fmaf(ex, invD, -Ox * invD);
-    sy = fmaf(ey, invD, -Oy * invD);
-    eIdx = 0;
-  } else {
-    float sd, cd;
-    sincos_2pi(float(w[1]) * k2m32, sd, cd);
-    const float rd = sqrtf((float(w[0]) + 0.5f) * k2m32);
-    const float Ox = fmaf(G.srcRadius, rd * cd, G.srcX), Oy = fmaf(G.srcRadius, rd * sd, G.srcY);
-    if (P.parallelSource) {
-      ex = Ox + (0.5f * ((float(w[2]) + 0.5f) * k2m32) - 0.25f);
-      ey = Oy + (0.5f * ((float(w[3]) + 0.5f) * k2m32) - 0.25f);
-    } else {
-      sincos_2pi(float(w[3]) * k2m32, sd, cd);
-      const float r2 = sqrtf((float(w[2]) + 0.5f) * k2m32);
-      ex = G.radiusCB * (r2 * cd);
-      ey = G.radiusCB * (r2 * sd);
-    }
-    sx = (ex - Ox) * G.invSrcDz;
-    sy = (ey - Oy) * G.invSrcDz;
-    const float qx = fmaf(sx, G.colDz, Ox) - G.srcX, qy = fmaf(sy, G.colDz, Oy) - G.srcY;
-    eIdx = P.srcEIdx;
-    const float mc = fmaf(qx, qx, qy * qy) - G.srcRadius2;
-    SART_UNC(kUncBore, fabsf(mc) - (2.0f * G.srcRadius * Q.latA + Q.circ2 * G.srcRadius2));
-    if (!(mc < 0.0f)) { rec.unc = slack <= 0.0f; return SART_EXIT_COLLIMATOR; }
-  }
-  // error budgets of this ray (Tol32): lateral position before the mirrors, and at the bore entrance
-  const float s1abs = fabsf(sx) + fabsf(sy);
-  float lat;
-  {
-    float detUnused;
-    ray_budget<kPre>(Q, s1abs, bud, lat, detUnused);
-  }
-
-  // ================= bore and pipes rt:1813-1872
-  const float s2sum = fmaf(sx, sx, sy * sy);
-  const float thrCB = fmaf(Q.twoRcb, lat, Q.circCB);
-  const float p0x = fmaf(-sx, G.lengthB, ex), p0y = fmaf(-sy, G.lengthB, ey);
-  const float mEnt = fmaf(p0x, p0x, p0y * p0y) - G.radiusCB2;
-  const bool hitEntrance = mEnt < 0.0f;
-  const float pex = fmaf(sx, G.dzExitCB, ex), pey = fmaf(sy, G.dzExitCB, ey);
-  const float mExit = fmaf(pex, pex, pey * pey) - G.radiusCB2;
-  const bool insideExit = mExit < 0.0f;
-  SART_UNC(kUncBore, fabsf(mExit) - thrCB);
-  // the entrance disc only tells "missed the bore" from "clipped at its exit" (rt:1813-1825 vs 1846); the reference
-  // intersects it separately, lengthB behind the field exit: Tol32::entK times the budget of the other planes covers it
-  SART_UNC(kUncBore, insideExit ? kSlackInf : fmaf(-Q.entK, thrCB, fabsf(mEnt)));
-  // The clip tests of this stage do not branch: a warp goes on as long as one lane survives, so an early return saves
-  // nothing and costs a divergence region each. `code` collects the exit in reverse order (the first failing test of
-  // the reference's sequence is assigned last) and the stage returns once, at its end.
-  float path2;
-  if (hitEntrance) {
-    path2 = G.lengthB2 * (1.0f + s2sum);
-  } else {
-    const float hb = fmaf(ex, sx, ey * sy), c = fmaf(ex, ex, ey * ey) - G.radiusCB2;
-    // wall entry with the exit-disc point itself on the rim: the path inside the field, and with it the weight, may be
-    // exactly zero on one side of the rounding and 1e-27 on the other (passed means weight != 0, rt:2220)
-    SART_UNC(kUncBore, fabsf(c) - thrCB);
-    const float disc = fmaf(hb, hb, -s2sum * c);
-    const float sq = disc > 1e-30f ? disc * rsqrtf_nr(disc) : 0.0f;
-    const float t1 = (hb >= 0.0f) ? -(hb + sq) * rcpf_nr(s2sum) : c * rcpf_nr(sq - hb);
-    path2 = t1 * t1 * (1.0f + s2sum);
-  }
-  const float thrPipe = fmaf(Q.twoRpipe, lat, Q.circPipe);
-  bool okPipe1;
-  {
-    const float qx = fmaf(sx, G.dzPipe1, ex), qy = fmaf(sy, G.dzPipe1, ey);
-    const float m = fmaf(qx, qx, qy * qy) - G.rPipe12;
-    okPipe1 = m < 0.0f;
-    SART_UNC(kUncBore, fabsf(m) - thrPipe);
-  }
-  float x0 = fmaf(sx, G.dzPipe2, ex), y0 = fmaf(sy, G.dzPipe2, ey);
-  const float mPipe2 = fmaf(x0, x0, y0 * y0) - G.rPipe12;
-  const bool okPipe2 = mPipe2 < 0.0f;  // quirk Q2
-  SART_UNC(kUncBore, fabsf(mPipe2) - thrPipe);
-  uint4 etA = make_uint4(0, 0, 0, 0);
-#if !SART_LAZY_THR
-  uint4 etB = etA;
-  if (kRowAlways || haveRow) etB = __ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u)));
-#endif
-  if (kAlias) {
-    if (kRowAlways || haveRow) aEntry = __ldg(T.energyAlias + eOff);
-  } else if (kRowAlways || haveRow) etA = __ldg(reinterpret_cast<const uint4*>(T.energyThr + eOff));
-
-  // ================= telescope frame rt:1888-1905
-  float dx = sx, dy = sy, dz = 1.0f, z0 = 0.0f;
-  if (!kPlain && P.rotated) {
-    const float zt = 0.0f - G.halfLenTel;
-    const float xr = x0 * G.cosTX + zt * G.sinTX;
-    float zr = zt * G.cosTX - x0 * G.sinTX;
-    const float yr = y0 * G.cosTY - zr * G.sinTY;
-    zr = zr * G.cosTY + y0 * G.sinTY;
-    x0 = xr; y0 = yr; z0 = zr + G.halfLenTel;
-    const float ddx = dx * G.cosTX + dz * G.sinTX;
-    float ddz = dz * G.cosTX - dx * G.sinTX;
-    const float ddy = dy * G.cosTY - ddz * G.sinTY;
-    ddz = ddz * G.cosTY + dy * G.sinTY;
-    dx = ddx; dy = ddy; dz = ddz;
-  }
-  x0 -= G.oeX; y0 -= G.oeY;
-  float tx = dx, ty = dy;
-  if (!kPlain && P.rotated) {
-    const float invdz = rcpf_nr(dz);
-    tx = dx * invdz; ty = dy * invdz;
-    x0 = fmaf(-z0, tx, x0); y0 = fmaf(-z0, ty, y0);   // pointEntranceXRT
-  }
-  const float rho0sq = fmaf(x0, x0, y0 * y0);
-  const float invRho0 = rsqrtf_nr(rho0sq);
-  const float radialDist = rho0sq * invRho0;
-  const float latRho = lat + Q.rho;
-
-  // ================= opaque structures rt:1635-1704
-  bool opaque = false;
-  if (kWolter) {
-    // The spider is n equally spaced arms of half-width a: "|phi - k 360/n| <= a for some k", with phi = acos(x/rho) as
-    // the reference computes it (rt:1632, mirror-symmetric in y), is cos(n phi) >= cos(n a), and cos(n phi) is the
-    // Chebyshev polynomial T_n(x/rho): four doublings for XMM's 16 arms, T_6 for Abrixas' 6 — no inverse trigonometry.
-    const bool xmm = P.telKind == SART_TK_XMM;
-    bool hit = false;
-    const float zs = xmm ? -85.0f : -35.0f;
-    const float xs = fmaf(zs, tx, x0), ys = fmaf(zs, ty, y0);
-    const float invRhoS = rsqrtf_nr(fmaf(xs, xs, ys * ys));
-    const float cF = x0 * invRho0, cS = xs * invRhoS;
-    // margins: radial edges against latRho; an arm edge at angle a moves cos(n phi) by n sin(n a) dphi <= n lat / rho
-    if (xmm) {
-      SART_UNC(kUncOpaque, fminf(fminf(fabsf(radialDist - 64.7f), fabsf(radialDist - 151.6f)), fabsf(radialDist - (151.6f - 20.9f))) - latRho);
-      if (radialDist <= 64.7f) hit = true;
-      else if (radialDist < 151.6f && radialDist > (151.6f - 20.9f)) hit = true;
-      else {
-        auto t16 = [](float c) {
-          c = fmaf(2.0f * c, c, -1.0f); c = fmaf(2.0f * c, c, -1.0f); c = fmaf(2.0f * c, c, -1.0f);
-          return fmaf(2.0f * c, c, -1.0f);
-        };
-        constexpr float kCos = 0.94931733f;   // cos(16 * 1.145 deg)
-        const float tF = t16(cF), tS = t16(cS);
-        hit = (tF >= kCos) || (tS >= kCos);
-        SART_UNC(kUncOpaque, fminf(fabsf(tF - kCos) - fmaf(16.0f * lat, invRho0, Q.spider), fabsf(tS - kCos) - fmaf(16.0f * lat, invRhoS, Q.spider)));
-      }
-    } else {
-      SART_UNC(kUncOpaque, fabsf(radialDist - 37.5f) - latRho);
-      if (radialDist < 37.5f) hit = true;
-      else {
-        auto t6 = [](float c) {
-          const float c2 = c * c;
-          return fmaf(c2, fmaf(c2, fmaf(c2, 32.0f, -48.0f), 18.0f), -1.0f);
-        };
-        constexpr float kCos = 0.92387953f;   // cos(6 * 3.75 deg)
-        const float tF = t6(cF), tS = t6(cS);
-        hit = (tF >= kCos) || (tS >= kCos);
-        SART_UNC(kUncOpaque, fminf(fabsf(tF - kCos) - fmaf(6.0f * lat, invRho0, Q.spider), fabsf(tS - kCos) - fmaf(6.0f * lat, invRhoS, Q.spider)));
-      }
-    }
-    opaque = hit;
-  }
-
-  // ================= shell rt:1932-1957 (hit shell = first j with R1[j] > radialDist; glass front of the shell below;
-  // outside the last shell): one record of the radial table holds the only boundary of its bucket and the outcomes below /
-  // at / above it (fast_params.h: ShellCell; derive_fast.cpp: build_shell_table)
-  int code = -1;
-  int hitLayer;
-  {
-    int b = int((radialDist - G.shellRhoMin) * G.shellInvStep);
-    b = max(0, min(b, P.nShellGuide - 1));
-    const uint2 c = *reinterpret_cast<const uint2*>(S.shellTab + b);
-    const float B = __uint_as_float(c.x);
-    const uint32_t pick = radialDist < B ? 0x4440u : (radialDist > B ? 0x4442u : 0x4441u);   // NaN: "at" = no mirror hit
-    hitLayer = int(__byte_perm(c.y, 0u, pick));
-    if (hitLayer >= kShellCellFail) code = hitLayer - kShellCellFail;
-    SART_UNC(kUncShell, fabsf(radialDist - B) - latRho);   // B: the boundary of this bucket, else the nearest one (build_shell_table)
-  }
-  if (opaque) code = SART_EXIT_OPAQUE;
-  if (!okPipe2) code = SART_EXIT_CLIP_PIPE_XRT;
-  if (!okPipe1) code = SART_EXIT_CLIP_PIPE_VT3;
-  if (!insideExit) code = hitEntrance ? SART_EXIT_CLIP_EXIT_CB : SART_EXIT_MISSED_BORE;
-  rec.unc = slack <= 0.0f;
-  if (code >= 0) return code;
-  if (kAlias) {
-    if (kRowAlways || haveRow) eIdx = alias_resolve(aEntry, aBucket, aCoin);
-  } else if (kRowAlways || haveRow) {
-    const uint32_t we = w[5];
-    eIdx = e0 + count_le(etA, we);
-    if (eIdx == e0 + 4) {   // ~1 ray in 8: the next four thresholds (loaded only by the lanes that need them)
-#if SART_LAZY_THR
-      eIdx += count_le(__ldg(reinterpret_cast<const uint4*>(T.energyThr + (eOff + 4u))), we);
-#else
-      eIdx += count_le(etB, we);
-#endif
-      if (eIdx == e0 + 8)
-        eIdx = thr_search_tail(thr_row(P, T, h.rIdx), e0 + 8,
-                               guide_upper(guide_row(T, h.rIdx), we >> (32 - kEnGuideBits), kEnGuide, P.nEnergies), we);
-      // saturated thresholds: the f64 row decides. The all-ones word passes every threshold, so it always gets here.
-      if (we == 0xffffffffu)
-        eIdx = lower_bound_window(T.energyCDF + size_t(h.rIdx) * P.nEnergies, 0, P.nEnergies, u01(we));
-    }
-    if (eIdx > P.nEnergies - 1) { eIdx = P.nEnergies - 1; clamped = true; }
-  }
-  rec.x0 = x0; rec.y0 = y0; rec.tx = tx; rec.ty = ty; rec.rho0 = radialDist; rec.path2 = path2;
-  rec.hitLayer = hitLayer; rec.eIdx = eIdx; rec.clamped = clamped;
-  rec.rIdx = h.rIdx; rec.we = w[5]; rec.bud = bud;
-  return -1;
-}
-
-// Stage B in FP32: the two reflections, nickel / degenerate exits, detector plane, weights, window (rt:1971-2221).
-// Every exit hands the ray to the re-trace queue instead (sink.defer) when a decision on its way there was inside its
-// error budget.
-#define SART_DEFER() do { if (slack <= 0.0f && sink.defer(rec.id)) return; } while (0)
-template <bool kWolter, bool kPlain = false, bool kPre = false, class Sink>
-__device__ __forceinline__ void stage_b32(const FastParams& P, const Geo32& G, const FastTables& T, const Smem32& S,
-                                          const Rec32& rec, Sink& sink) {
-  const ShellF32* __restrict__ sShell = S.shell;
-  const Tol32& Q = G.tol;
-  RayResult out;
-  out.convVac = 1.f; out.gasGamma = 0.f; out.gasE1 = 0.f; out.gasE2 = 0.f; out.gasInv2E = 0.f; out.gasL = 0.0;
-  const float x0 = rec.x0, y0 = rec.y0, tx = rec.tx, ty = rec.ty, rho0 = rec.rho0;
-  const int hitLayer = rec.hitLayer, eIdx = rec.eIdx;
-  bool clamped = rec.clamped;
-  float slack = rec.unc ? -1.0f : kSlackInf;
-  float lat, det;
-  ray_budget<kPre>(Q, fabsf(tx) + fabsf(ty), rec.bud, lat, det);
-  const float4 elv = __ldg(reinterpret_cast<const float4*>(T.elut) + eIdx);
-  const EnergyLUT el = {__float_as_int(elv.x), elv.y, elv.z, elv.w};
-  const float t2sum = fmaf(tx, tx, ty * ty);
-  const float invLen = rsqrtf_nr(1.0f + t2sum);
-  const ShellF32& sh = sShell[hitLayer];
-  const float lM = G.lMirror;
-  const float below = hitLayer > 0 ? sShell[hitLayer - 1].R1pT : 0.0f;
-  const float xt = fmaf(x0, tx, y0 * ty);
-
-  // ================= mirror 1 rt:1983-2020. Ray: (x0 + tx z, y0 + ty z, z); C in factored form
-  float z1, tolZ1;
-  const float tolC1 = sh.twoR * (lat + Q.rho);   // budget of C = rho0^2 - R^2: 2 R x the budget of rho0
-  if (kWolter) {   // paraboloid rho^2 = c0 - e z, c0 = R0^2
-    z1 = pick_root32<kUncMirror1, true>(Q, t2sum, xt + 0.5f * sh.p_e, (rho0 - sh.p_R0) * (rho0 + sh.p_R0), 1.0f, sh.zmid1,
-                                        sh.zhalf1, tolC1, 0.0f, slack, tolZ1);
-  } else {         // cone rho = r1 - tan(beta) z
-    z1 = pick_root32<kUncMirror1, false>(Q, t2sum - sh.tan1 * sh.tan1, fmaf(sh.tan1, sh.R1, xt), (rho0 - sh.R1) * (rho0 + sh.R1),
-                                         1.0f, sh.zmid1, sh.zhalf1, tolC1, 0.0f, slack, tolZ1);
-  }
-  if (!(z1 == z1)) {   // kMiss
-    int code = SART_EXIT_NO_MIRROR_HIT;
-    if (hitLayer > 0) {
-      const float zc = G.zExitCBtel;
-      const float xc = fmaf(zc, tx, x0), yc = fmaf(zc, ty, y0);
-      const float rc2 = fmaf(xc, xc, yc * yc);
-      const float rc = rc2 * rsqrtf_nr(rc2);
-      float nz;
-      if (kWolter) nz = rc * sh.p_r3tan * rsqrtf_nr(fmaxf(fmaf(sh.p_e, lM - zc, sh.p_r3sq), 1e-30f));
-      else nz = sh.tan1 * rc;
-      const float sg = (fmaf(xc, tx, yc * ty) + nz) * invLen * rsqrtf_nr(fmaf(rc, rc, nz * nz));
-      const float a = fabsf(sg);
-      const float lhs = a * (lM - zc), rhs = sh.R1 - below;
-      const float m = fmaf(lhs, lhs, -rhs * rhs * (1.0f - a * a));
-      SART_UNC(kUncNickel, fmaf(-4.0f * Q.nick, lhs + rhs, fabsf(m)));
-      if (m > 0.0f) code = SART_EXIT_NICKEL;
-    }
-    SART_DEFER();
-    sink.fail(code);
-    return;
-  }
-  F3 pm = {fmaf(tx, z1, x0), fmaf(ty, z1, y0), z1};
-  F3 v = {tx * invLen, ty * invLen, invLen};
-  float sinA1, rhoM;
-  {
-    const float rr = fmaf(pm.x, pm.x, pm.y * pm.y);
-    const float ir = rsqrtf_nr(rr);
-    rhoM = rr * ir;
-    F3 n;
-    if (kWolter) {
-      const float nz = sh.p_r3tan * rsqrtf_nr(fmaf(sh.p_e, lM - pm.z, sh.p_r3sq));
-      const float il = rsqrtf_nr(fmaf(nz, nz, 1.0f));
-      n = {pm.x * ir * il, pm.y * ir * il, nz * il};
-    } else {
-      n = {pm.x * ir * sh.cosb, pm.y * ir * sh.cosb, sh.sinb};
-    }
-    sinA1 = reflect32(n, v);
-  }
-  // ================= mirror 2 rt:1994-2029. Ray: pm + t v. The budget of C: the start point sits on mirror 1 at z1 +-
-  // tolZ1, where the radii of the ray and of mirror 2 move by (|slope| + tan(3 beta)) tolZ1, plus the ray's own lat
-  float t2, tolZ2;
-  const float mid2 = sh.zmid2 - pm.z;
-  const float pv = fmaf(pm.x, v.x, pm.y * v.y), vv = fmaf(v.x, v.x, v.y * v.y);
-  const float tolC2 = (rhoM + rhoM) * fmaf(sh.tan2p, tolZ1, lat);
-  if (kWolter) {  // hyperboloid rho^2 = r3^2 + e (l - z) + g (l - z)^2
-    const float u = lM - pm.z;
-    const float Rh2 = fmaf(fmaf(sh.h_g, u, sh.h_e), u, sh.h_r3sq);
-    const float Rh = Rh2 * rsqrtf_nr(Rh2);
-    t2 = pick_root32<kUncMirror2, true>(Q, vv - sh.h_g * v.z * v.z, fmaf(fmaf(sh.h_g, u, 0.5f * sh.h_e), v.z, pv),
-                                        (rhoM - Rh) * (rhoM + Rh), v.z, mid2, sh.zhalf2, tolC2, tolZ1, slack, tolZ2);
-  } else {        // cone rho = r4 - tan(3 beta) (z - distanceMirrors)
-    const float rc = fmaf(-sh.tan2, pm.z - sh.dm, sh.r4);
-    t2 = pick_root32<kUncMirror2, false>(Q, vv - sh.tan2 * sh.tan2 * v.z * v.z, fmaf(sh.tan2 * rc, v.z, pv),
-                                         (rhoM - rc) * (rhoM + rc), v.z, mid2, sh.zhalf2, tolC2, tolZ1, slack, tolZ2);
-  }
-  // ================= nickel of the shell below rt:1706-1734
-  if (hitLayer > 0) {
-    const float lhs = sinA1 * (lM - z1), rhs = sh.R1 - below;
-    const float m = fmaf(lhs, lhs, -rhs * rhs * (1.0f - sinA1 * sinA1));
-    SART_UNC(kUncNickel, fmaf(-(lhs + rhs), fmaf(sinA1, tolZ1, Q.nick), fabsf(m)));
-    if (m > 0.0f) { SART_DEFER(); sink.fail(SART_EXIT_NICKEL); return; }
-  }
-  if (!(t2 == t2)) { SART_DEFER(); sink.fail(SART_EXIT_NO_MIRROR_HIT); return; }   // kMiss
-  pm.x = fmaf(t2, v.x, pm.x); pm.y = fmaf(t2, v.y, pm.y); pm.z = fmaf(t2, v.z, pm.z);
-  float sinA2;
-  {
-    const float rr = fmaf(pm.x, pm.x, pm.y * pm.y);
-    const float ir = rsqrtf_nr(rr);
-    F3 n;
-    if (kWolter) {
-      const float u = lM - pm.z;
-      const float q1 = fmaf(2.0f * u, sh.h_inv_nden, 1.0f), q2 = fmaf(u, sh.h_inv_nden, 1.0f);
-      const float nz = sh.h_r3tan * q1 * rsqrtf_nr(fmaf(2.0f * sh.h_r3tan * u, q2, sh.h_r3sq));
-      const float il = rsqrtf_nr(fmaf(nz, nz, 1.0f));
-      n = {pm.x * ir * il, pm.y * ir * il, nz * il};
-    } else {
-      n = {pm.x * ir * sh.cos3b, pm.y * ir * sh.cos3b, sh.sin3b};
-    }
-    sinA2 = reflect32(n, v);
-  }
-  // ================= detector plane rt:797-814
-  float xw, yw, zw;
-  {
-    const float ax = fmaf(pm.x, G.cosPipe, pm.z * G.sinPipe) - G.dShift, az = fmaf(pm.z, G.cosPipe, -pm.x * G.sinPipe);
-    const float wx = fmaf(v.x, G.cosPipe, v.z * G.sinPipe), wz = fmaf(v.z, G.cosPipe, -v.x * G.sinPipe);
-    const float iwz = rcpf_nr(wz);
-    const float n = (sh.ddWin - az) * iwz;
-    xw = fmaf(n, wx, ax); yw = fmaf(n, v.y, pm.y); zw = fmaf(n, wz, az);
-    // deviationDet rt:2081-2085: distance in the detector plane between the hits at the window and depthDet behind it
-    out.devDet = fabsf(G.depthOverCos * iwz) * sqrtf(fmaf(wx, wx, v.y * v.y));
-  }
-  xw -= G.lateralShift; yw -= G.transversalShift;
-  // ================= weights rt:2101-2128
-  out.eIdx = eIdx;
-  const uint32_t flags = kPlain ? 0u : P.flags;
-  {
-    const float ya = -atan_small(ty) * 57.29577951308232f;  // degrees; fed to cos as radians (quirk Q3)
-    out.yaw = ya;
-    float pre = __cosf(ya);
-    const float path2f = rec.path2;
-    out.path = sqrtf(path2f);
-    if (kPlain || P.stage == SART_SK_VACUUM) {
-      out.convVac = P.convK * path2f;
-    } else {
-      const float2 gv = __ldg(reinterpret_cast<const float2*>(T.glut) + eIdx);
-      const float pathm = sqrtf(path2f) * 1e-3f;
-      const double gamma = P.gasGamma0 * double(gv.x);
-      out.gasL = double(pathm) / 1.97e-7;
-      const float gl = float(gamma * out.gasL);
-      out.gasGamma = float(gamma);
-      out.gasE1 = __expf(-gl); out.gasE2 = __expf(-0.5f * gl);
-      out.gasInv2E = gv.y;
-      const float distPipe = (zw - G.zExitCBtel) * 1e-3f;
-      pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
-    }
-    out.pre = pre;
-    double refl = 1.0;   // the product of two FP32 reflectivities can leave the FP32 range (1e-20 each at large angles)
-    const float a1 = asin_small(sinA1) * 57.29577951308232f, a2 = asin_small(sinA2) * 57.29577951308232f;
-    out.a1 = a1; out.a2 = a2;
-    if (!(flags & SART_CF_IGNORE_REFLECTION)) {
-      const uint32_t rowOff = (uint32_t(sh.coat & kCoatMask) * uint32_t(P.nEnergies + 1) + uint32_t(eIdx)) * uint32_t(P.nAngles);
-      clamped |= (sh.coat & kCoatClamped) != 0;
-      SART_UNC(kUncAngle, Q.angLo - fmaxf(a1, a2));   // at or beyond the end of the grid: the clamped flag
-      refl = double(refl_lookup(P, T.reflE, a1, clamped, rowOff)) * double(refl_lookup(P, T.reflE, a2, clamped, rowOff));
-    }
-    out.refl = refl;
-    out.wPre = refl * double(pre);
-    if (Sink::kFold)
-      out.wPre *= kPlain ? double(out.convVac)
-                         : conv_factor(P, out.convVac, out.gasGamma, out.gasE1, out.gasE2, out.gasInv2E, out.gasL, sink.m2);
-  }
-  out.agas = el.Agas;
-  out.clamped = clamped;
-  out.shell = hitLayer;
-  out.code = -1;
-  // ================= window aperture rt:2139-2147
-  const float rw2 = fmaf(xw, xw, yw * yw);
-  const bool ignoreWin = (flags & SART_CF_IGNORE_DET_WINDOW) != 0;
-  SART_UNC(kUncWindow, ignoreWin ? kSlackInf : fabsf(rw2 - G.radiusWindow2) - fmaf(Q.twoRwin, det, Q.circWin));
-  if (ignoreWin || Q.chipInside)   // otherwise the window aperture lies inside the chip and decides alone
-    SART_UNC(kUncWindow, fminf(fabsf(fabsf(xw) - G.chipCX), fabsf(fabsf(yw) - G.chipCY)) - det);
-  if ((!ignoreWin && rw2 > G.radiusWindow2) || fabsf(xw) > G.chipCX || fabsf(yw) > G.chipCY) {
-    out.windowMiss = true; out.wPost = 0.0; out.x = out.y = out.r = 0.0; out.bin = -1;
-    SART_DEFER();
-    sink.hit(out);
-    return;
-  }
-  out.windowMiss = false;
-  // ================= strongback strips rt:2149-2185
-  double post = 1.0;
-  {
-    const float yt = fabsf(fmaf(yw, G.cosTheta, -xw * G.sinTheta));
-    int sb = 2;
-    if (P.nStripHalf > 0) {
-      const float pitch = G.stripDist + G.stripWidth;
-      const float u = yt - 0.5f * G.stripDist;
-      const float fi = floorf(u * G.invStripPitch);
-      const float off = fmaf(-fi, pitch, u);
-      sb = (u > 0.0f && fi < float(P.nStripHalf) && off > 0.0f && off < G.stripWidth) ? 1 : 0;
-      // a strip edge within det of the hit (off = 0, the strip width, or the next strip's start) changes the transmission
-      SART_UNC(kUncStrips, ignoreWin ? kSlackInf : fminf(fminf(off, fabsf(off - G.stripWidth)), pitch - off) - det);
-    }
-    const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
-    if (!ignoreWin) {
-      post *= double(tw);
-      if (sb == 1 && el.sbExp != 0)   // rare (soft X-rays on a strip): add the exponent; the product stays far inside the f64 range
-        post = __hiloint2double(__double2hiint(post) + (el.sbExp << 20), __double2loint(post));
-    }
-  }
-  if (!(flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);
-  if (!(flags & SART_CF_XRAY_TEST)) post *= double(P.exposure);
-  out.wPost = post;
-  const float xc = G.chipCX - xw, yc = yw + G.chipCY;
-  out.r = double(rw2 > 1e-30f ? rw2 * rsqrtf_nr(rw2) : 0.0f);
-  out.x = double(xc);
-  out.y = double(yc);
-  const int cx = int(floorf(xc * G.invBinX)), cy = int(floorf(yc * G.invBinY));
-  out.bin = (cx >= 0 && cx < SART_IMAGE_BINS && cy >= 0 && cy < SART_IMAGE_BINS) ? cy * SART_IMAGE_BINS + cx : -1;
-  SART_DEFER();
-  sink.hit(out);
-}
-
-__device__ __forceinline__ void flush_counters(sart_counters_t* c, const WarpCounters& wc, unsigned nIter, unsigned nPassed,
-                                               unsigned nTill, double sumW, double sumW2, double sumX, double sumY, double sumR) {
-  auto addu = [](uint64_t* p, unsigned long long v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p), v); };
-  addu(&c->n_rays, nIter);
-  addu(&c->n_exit[SART_EXIT_PASSED], nPassed);
-  addu(&c->n_passed, nPassed);
-  addu(&c->n_passed_till_window, nTill);
-  for (int e = 1; e < SART_N_EXIT_CODES; ++e) addu(&c->n_exit[e], wc.n_exit[e]);
-  addu(&c->n_hit_nickel, wc.n_exit[SART_EXIT_NICKEL]);
-  addu(&c->n_interp_clamped, wc.n_clamped);
-  addu(&c->n_unresolved, wc.n_unresolved);
-  atomicAdd(&c->sum_w, sumW); atomicAdd(&c->sum_w2, sumW2);
-  atomicAdd(&c->sum_x, sumX); atomicAdd(&c->sum_y, sumY); atomicAdd(&c->sum_r, sumR);
-}
-
 // ---- fused kernel ---------------------------------------------------------------------------------------------
 // A ray of stage A that is uncertain (rec.unc) goes to the re-trace queue whatever its code; stage B does the same at its
 // own exits. The launcher keeps nRays below 2^32, so the queue entry (ray index - first) fits 32 bits.
-template <bool kWolter, bool kPlain, bool kAlias>
+template <bool kWolter, bool kPlain, bool kAlias, bool kMargins>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G, const __grid_constant__ FastTables T,
                double mAxion2, uint64_t first, uint64_t nRays, const __grid_constant__ PhiloxKeys K, double* __restrict__ image,
@@ -811,9 +54,9 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
     stage_a32_head<kPlain, false, kAlias>(P, T, S, K, ray, hd);
     Rec32 rec;
     rec.id = id;
-    const int code = stage_a32<kWolter, false, kPlain, false, kAlias>(P, G, T, S, hd, rec);
-    if (code >= 0) { if (!(rec.unc && sink.defer(rec.id))) sink.fail(code); }
-    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
+    const int code = stage_a32<kWolter, false, kPlain, false, kAlias, kMargins>(P, G, T, S, hd, rec);
+    if (code >= 0) { if (!(kMargins && rec.unc && sink.defer(rec.id))) sink.fail(code); }
+    else stage_b32<kWolter, kPlain, false, kMargins>(P, G, T, S, rec, sink);
   }
   for (int o = 16; o > 0; o >>= 1) {
     nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
@@ -838,7 +81,7 @@ struct WarpQueue32 {
   uint32_t id[kQueue32];   // ray index - first ray of the launch
 };
 
-template <bool kWolter, bool kPlain, bool kAlias>
+template <bool kWolter, bool kPlain, bool kAlias, bool kMargins>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                        const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
@@ -874,9 +117,9 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
         Head32 hd;
         stage_a32_head<kPlain, true, kAlias>(P, T, S, K, first + i, hd);
         rec.id = uint32_t(i);
-        code = stage_a32<kWolter, false, kPlain, true, kAlias>(P, G, T, S, hd, rec);
+        code = stage_a32<kWolter, false, kPlain, true, kAlias, kMargins>(P, G, T, S, hd, rec);
         ++nIter;
-        if (code >= 0 && !(rec.unc && sink.defer(rec.id))) sink.fail(code);
+        if (code >= 0 && !(kMargins && rec.unc && sink.defer(rec.id))) sink.fail(code);
       }
       const unsigned m = __ballot_sync(kFull, code < 0);
       if (code < 0) {
@@ -902,7 +145,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       rec.id = Q.id[pos];
       rec.bud = solar ? (0.0015f + float(rec.eIdx) * 0.0005f) : 1.0f;   // rs of the emission shell (rec.eIdx still holds it)
       if (solar) rec.eIdx = energy_index<kAlias>(P, T, rec.eIdx, Q.we[pos], rec.clamped);
-      stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
+      stage_b32<kWolter, kPlain, false, kMargins>(P, G, T, S, rec, sink);
     }
     qn -= take;
     __syncwarp();
@@ -922,7 +165,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
 }
 
 // ---- axion-mass scan with FP32 tracing (the per-mass weighting is fast_common.cuh's mass_scan_loop) --------------
-template <bool kWolter>
+template <bool kWolter, bool kMargins>
 __global__ void __launch_bounds__(kBlockM, SART_F32_MINBLOCKS_M)
 k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                       const __grid_constant__ FastTables T, const double* __restrict__ masses, int nMasses, uint64_t first,
@@ -943,131 +186,11 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
     stage_a32_head(P, T, S, K, ray, hd);
     Rec32 rec;
     rec.id = id;
-    const int c0 = stage_a32<kWolter>(P, G, T, S, hd, rec);
-    if (c0 >= 0) { if (!(rec.unc && sink.defer(rec.id))) sink.fail(c0); }
-    else stage_b32<kWolter, false>(P, G, T, S, rec, sink);
+    const int c0 = stage_a32<kWolter, false, false, false, false, kMargins>(P, G, T, S, hd, rec);
+    if (c0 >= 0) { if (!(kMargins && rec.unc && sink.defer(rec.id))) sink.fail(c0); }
+    else stage_b32<kWolter, false, false, kMargins>(P, G, T, S, rec, sink);
     return sink.unresolved;
   });
-}
-
-// ---- per-ray records (traceAxionWrapper in FP32 mode) ----------------------------------------------------------
-// `words` (optional, sart_trace_words): SoA [6][nRays] random words used instead of the Philox words of ray first + i.
-// kLate: the energy is resolved by energy_index() after stage A, the way the compacting fused kernel does it (otherwise
-// inside stage A, the way the plain fused kernel does it) — so the test hook reaches both forms of the search.
-// An uncertain ray gets its FP32 record like any other and is queued; the exact pipeline overwrites the record afterwards.
-template <bool kWolter, bool kPlain, bool kAlias, bool kLate = false>
-__global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
-k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
-                    const __grid_constant__ FastTables T, double mAxion2, uint64_t first, uint64_t nRays,
-                    const __grid_constant__ PhiloxKeys K, const uint32_t* __restrict__ words, int32_t* __restrict__ oemit,
-                    const __grid_constant__ sart_ray_out_t o) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  Smem32 S;
-  unsigned char* tail;
-  smem_layout32<kAlias>(P, smem, S, tail);
-  smem_fill32<kAlias>(P, T, S);
-  __syncthreads();
-  const uint64_t stride = uint64_t(gridDim.x) * kBlock32;
-  for (uint64_t i = uint64_t(blockIdx.x) * kBlock32 + threadIdx.x; i < nRays; i += stride) {
-    RayResult r;
-    RecordSink<true> sink{r, mAxion2, T.rq, false};
-    Rec32 rec;
-    rec.id = uint32_t(i);
-    Head32 hd;
-    if (words) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) hd.w[k] = words[size_t(k) * nRays + i];
-    } else {
-      ray_words(K, first + i, hd.w);
-    }
-    stage_a32_head_words<kPlain, kLate, kAlias>(P, T, S, hd);
-    const int c0 = stage_a32<kWolter, false, kPlain, kLate, kAlias>(P, G, T, S, hd, rec);
-    const bool solar = kPlain || !P.testXray;
-    if (kLate && c0 < 0 && solar) rec.eIdx = energy_index<kAlias>(P, T, rec.rIdx, rec.we, rec.clamped);
-    if (c0 >= 0) { if (rec.unc) sink.defer(rec.id); sink.fail(c0); }
-    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
-    // energiesPre is set for every ray (rt:1818-1819), clipped or not: rays that end in stage A resolve their energy here
-    double energy = double(P.srcEnergy);
-    if (solar) {
-      int eIdx = rec.eIdx;
-      bool cl = false;
-      if (c0 >= 0) eIdx = energy_index<kAlias>(P, T, hd.rIdx, hd.w[5], cl);
-      energy = fmax(__ldg(T.energies + eIdx), 0.03);   // the f64 table value itself (rt:470-471)
-    }
-    store_record(P, o, i, r, mAxion2, energy);
-    if (oemit) oemit[i] = hd.rIdx;
-  }
-}
-
-// ---- tier (a): pre-sampled rays, structure of arrays in HBM -> per-ray records in HBM -------------------------------
-// 48 B in (origin x, y, z; exit-disc x, y; energy — f64, coalesced) and 32 B out (x, y, w f64; code, shell i32) per ray,
-// plus whatever optional record arrays the caller asks for.
-// The slopes are formed in FP64 from the caller's points (the origin is 1.5e14 mm away), everything after that is the
-// FP32 pipeline. The energy is mapped to its index in the tabulated energies (the reference only ever traces tabulated
-// energies, rt:470); an energy that is not a table value is traced at the nearest one and flagged INTERP_CLAMPED.
-template <bool kWolter, bool kPlain>
-__global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
-k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
-                       const __grid_constant__ FastTables T, double mAxion2, size_t n, const double* __restrict__ origin,
-                       const double* __restrict__ exitxy, const double* __restrict__ energy,
-                       const __grid_constant__ sart_ray_out_t o) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  Smem32 S;
-  unsigned char* tail;
-  smem_layout32(P, smem, S, tail);
-  smem_fill32(P, T, S);
-  __syncthreads();
-  const size_t stride = size_t(gridDim.x) * kBlock32;
-  for (size_t i = size_t(blockIdx.x) * kBlock32 + threadIdx.x; i < n; i += stride) {
-    const double Ox = origin[i], Oy = origin[n + i], Oz = origin[2 * n + i];
-    const double ex = exitxy[i], ey = exitxy[n + i], E = energy[i];
-    Head32 hd;
-    const double invD = rcp_nr(P.lengthB - Oz);
-    hd.ex = float(ex); hd.ey = float(ey);
-    hd.sx = float((ex - Ox) * invD); hd.sy = float((ey - Oy) * invD);
-    // rounding noise of the reference's line O + lambda (E - O) (rt:481-492, 529-534) at pointExitCB: one ulp of the
-    // origin's x / y, plus one ulp of its z seen through the slope
-    hd.epsO = 4.4408921e-16f * (fabsf(float(Ox)) + fabsf(float(Oy)) + (fabsf(hd.sx) + fabsf(hd.sy)) * fabsf(float(Oz)));
-    // energy -> index of the tabulated energy: uniform-grid guess, then the table decides
-    const double Ec = fmax(E, 0.03);
-    int k = int(rint((E - P.enE0) * P.enInvStep));
-    k = k < 0 ? 0 : (k > P.nEnergies - 1 ? P.nEnergies - 1 : k);
-    if (fmax(__ldg(T.energies + k), 0.03) != Ec) {
-      k = lower_bound_window(T.energies, 0, P.nEnergies, Ec);   // first tabulated energy >= Ec
-      if (k > P.nEnergies - 1) k = P.nEnergies - 1;
-      if (k > 0 && fmax(__ldg(T.energies + k), 0.03) != Ec) {
-        const double below = fmax(__ldg(T.energies + k - 1), 0.03);   // entries under 0.03 keV are traced at 0.03 (rt:471)
-        if (below == Ec || fabs(below - Ec) < fabs(__ldg(T.energies + k) - Ec)) --k;
-      }
-    }
-    hd.eIdx = k;
-    hd.offGrid = fmax(__ldg(T.energies + k), 0.03) != Ec;
-    RayResult r;
-    RecordSink<true> sink{r, mAxion2, T.rq, false};
-    Rec32 rec;
-    rec.id = uint32_t(i);
-    const int c0 = stage_a32<kWolter, true, kPlain>(P, G, T, S, hd, rec);
-    if (c0 >= 0) { if (rec.unc) sink.defer(rec.id); sink.fail(c0); }
-    else stage_b32<kWolter, kPlain, true>(P, G, T, S, rec, sink);
-    store_record(P, o, i, r, mAxion2, Ec);
-  }
-}
-
-static size_t smem_bytes32(const FastParams& P, int nWarps = kWarps32, bool alias = false) {
-  return ((size_t(P.nShells) * sizeof(ShellF32) + 15) & ~size_t(15)) + rad_smem_bytes(P, alias) +
-         ((size_t(P.nShellGuide) * sizeof(ShellCell) + 15) & ~size_t(15)) + size_t(nWarps) * sizeof(WarpCounters);
-}
-
-// Dynamic shared memory limit + an explicit L1 / shared-memory split for a kernel. Left to the driver, the split of a
-// launch depends on what ran on the SMs before it (measured: the same fused kernel ran at 20.0 or at 24.2 ms for a whole
-// process, depending on whether its first launch followed a 256 MB memset): these kernels live on L1 for their table
-// gathers, so they ask for the smallest shared-memory carve-out that holds their block.
-template <class K>
-static cudaError_t set_smem(K kern, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return e;
-  const int pct = int(((smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));   // of 228 KB, rounded up (+1 KB the system reserves)
-  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 }
 
 }  // namespace fast
@@ -1083,16 +206,17 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && !T.rad.w;
   using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, double*, double*,
                         sart_counters_t*);
-  static const Kern table[2][2][2][2] = {   // [compact][wolter][plain][alias]
-      {{{fast::k_trace_mc_f32<false, false, false>, fast::k_trace_mc_f32<false, false, true>},
-        {fast::k_trace_mc_f32<false, true, false>, fast::k_trace_mc_f32<false, true, true>}},
-       {{fast::k_trace_mc_f32<true, false, false>, fast::k_trace_mc_f32<true, false, true>},
-        {fast::k_trace_mc_f32<true, true, false>, fast::k_trace_mc_f32<true, true, true>}}},
-      {{{fast::k_trace_mc_f32_compact<false, false, false>, fast::k_trace_mc_f32_compact<false, false, true>},
-        {fast::k_trace_mc_f32_compact<false, true, false>, fast::k_trace_mc_f32_compact<false, true, true>}},
-       {{fast::k_trace_mc_f32_compact<true, false, false>, fast::k_trace_mc_f32_compact<true, false, true>},
-        {fast::k_trace_mc_f32_compact<true, true, false>, fast::k_trace_mc_f32_compact<true, true, true>}}}};
-  const Kern kern = table[compact ? 1 : 0][wolter ? 1 : 0][plain ? 1 : 0][alias ? 1 : 0];
+  // [compact][wolter][plain][variant]; variant 0: inverse-CDF sampler, pure FP32; 1: inverse-CDF sampler with the margin tests
+  // (re-trace queue attached); 2: alias sampler (no re-trace: its ray <-> index mapping is not the exact pipeline's)
+#define SART_ROW(K, W, PL) {fast::K<W, PL, false, false>, fast::K<W, PL, false, true>, fast::K<W, PL, true, false>}
+  static const Kern table[2][2][2][3] = {
+      {{SART_ROW(k_trace_mc_f32, false, false), SART_ROW(k_trace_mc_f32, false, true)},
+       {SART_ROW(k_trace_mc_f32, true, false), SART_ROW(k_trace_mc_f32, true, true)}},
+      {{SART_ROW(k_trace_mc_f32_compact, false, false), SART_ROW(k_trace_mc_f32_compact, false, true)},
+       {SART_ROW(k_trace_mc_f32_compact, true, false), SART_ROW(k_trace_mc_f32_compact, true, true)}}};
+#undef SART_ROW
+  const bool margins = !alias && T.rq.cap != 0u;
+  const Kern kern = table[compact ? 1 : 0][wolter ? 1 : 0][plain ? 1 : 0][alias ? 2 : (margins ? 1 : 0)];
   if (getenv("SART_DEBUG"))
     fprintf(stderr, "[sart] k_trace_mc_f32 compact=%d wolter=%d plain=%d alias=%d (sampler=%d ra=%p ea=%p) smem=%zu\n", int(compact),
             int(wolter), int(plain), int(alias), T.sampler, (const void*)T.radiusAlias, (const void*)T.energyAlias, smem);
@@ -1121,7 +245,9 @@ cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Ge
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P, fast::kWarpsM);
-  auto kern = wolter ? fast::k_trace_mc_f32_masses<true> : fast::k_trace_mc_f32_masses<false>;
+  const bool margins = T.rq.cap != 0u;
+  auto kern = wolter ? (margins ? fast::k_trace_mc_f32_masses<true, true> : fast::k_trace_mc_f32_masses<true, false>)
+                     : (margins ? fast::k_trace_mc_f32_masses<false, true> : fast::k_trace_mc_f32_masses<false, false>);
   cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   int perSM = 0;
@@ -1132,57 +258,6 @@ cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Ge
   const uint64_t cap = uint64_t(smCount) * perSM;
   const unsigned grid = unsigned(want < cap ? want : cap);
   kern<<<grid, fast::kBlockM, smem, s>>>(P, G, T, dMasses, nMasses, first, nRays, philox_round_keys(seed), acc, accW2, counters);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
-                                  size_t n, const double* origin, const double* exitxy, const double* energy,
-                                  const sart_ray_out_t& o, int smCount, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
-  const size_t smem = fast::smem_bytes32(P);
-  // the plain-run variant (run-wide switches as compile-time constants, see k_trace_mc_f32); pre-sampled rays have no source
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
-  auto kern = wolter ? (plain ? fast::k_trace_presampled_f32<true, true> : fast::k_trace_presampled_f32<true, false>)
-                     : (plain ? fast::k_trace_presampled_f32<false, true> : fast::k_trace_presampled_f32<false, false>);
-  cudaError_t e = fast::set_smem(kern, smem);
-  if (e != cudaSuccess) return e;
-  int perSM = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, fast::kBlock32, smem);
-  if (e != cudaSuccess) return e;
-  if (perSM < 1) perSM = 1;
-  const uint64_t want = (n + fast::kBlock32 - 1) / fast::kBlock32;
-  const uint64_t cap = uint64_t(smCount) * perSM;
-  const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, n, origin, exitxy, energy, o);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
-                               uint64_t first, uint64_t nRays, uint64_t seed, const sart_ray_out_t& o, int smCount,
-                               cudaStream_t s, const uint32_t* words, bool lateEnergy, int32_t* emit) {
-  if (nRays == 0) return cudaSuccess;
-  const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
-  const bool alias = T.sampler == SART_SAMPLER_ALIAS && !P.testXray && T.radiusAlias && T.energyAlias;
-  const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias);
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
-  using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, const uint32_t*,
-                        int32_t*, sart_ray_out_t);
-  static const Kern table[2][2][2] = {   // [wolter][plain][alias]
-      {{fast::k_trace_mc_rays_f32<false, false, false>, fast::k_trace_mc_rays_f32<false, false, true>},
-       {fast::k_trace_mc_rays_f32<false, true, false>, fast::k_trace_mc_rays_f32<false, true, true>}},
-      {{fast::k_trace_mc_rays_f32<true, false, false>, fast::k_trace_mc_rays_f32<true, false, true>},
-       {fast::k_trace_mc_rays_f32<true, true, false>, fast::k_trace_mc_rays_f32<true, true, true>}}};
-  static const Kern late[2][2] = {   // [wolter][alias], generic (non-plain) variant: the hook of sart_trace_words
-      {fast::k_trace_mc_rays_f32<false, false, false, true>, fast::k_trace_mc_rays_f32<false, false, true, true>},
-      {fast::k_trace_mc_rays_f32<true, false, false, true>, fast::k_trace_mc_rays_f32<true, false, true, true>}};
-  const Kern kern = lateEnergy ? late[wolter ? 1 : 0][alias ? 1 : 0] : table[wolter ? 1 : 0][plain ? 1 : 0][alias ? 1 : 0];
-  cudaError_t e = fast::set_smem(kern, smem);
-  if (e != cudaSuccess) return e;
-  const uint64_t want = (nRays + fast::kBlock32 - 1) / fast::kBlock32;
-  const uint64_t cap = uint64_t(smCount) * 2;
-  const unsigned grid = unsigned(want < cap ? want : cap);
-  kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first, nRays, philox_round_keys(seed), words, emit, o);
   return cudaGetLastError();
 }
 

@@ -242,6 +242,25 @@ class RayTracer:
         check(lib.sart_trace_mc_rays(self._h, first_ray, bufLen, seed, C.byref(o)))
         return out
 
+    def trace_passed(self, n: int, seed: int = 299792458, first_ray: int = 0, fields=("ray", "x", "y", "w", "shell"),
+                     capacity: int | None = None, buffers: dict | None = None):
+        """sart_trace_mc_passed: the records of the rays that pass only, compacted on the GPU, single precision. Returns
+        (dict of numpy arrays cut to the number of passed rays, counters dict). `buffers` supplies pre-allocated
+        (e.g. pinned) arrays by field name."""
+        cap = int(capacity if capacity is not None else n)
+        dtypes = {name: np.dtype(t) for name, t in abi.PASSED_OUT_FIELDS}
+        arrays = {}
+        po = abi.PassedOut()
+        for name in fields:
+            a = buffers[name] if buffers and name in buffers else np.empty(cap, dtype=dtypes[name])
+            assert a.dtype == dtypes[name] and a.size >= cap and a.flags.c_contiguous
+            arrays[name] = a
+            setattr(po, name, a.ctypes.data_as(C.POINTER(dict(abi.PASSED_OUT_FIELDS)[name])))
+        npass = C.c_uint64(0)
+        cnt = abi.Counters()
+        check(lib.sart_trace_mc_passed(self._h, first_ray, n, seed, cap, C.byref(po), C.byref(npass), C.byref(cnt)))
+        return {k: v[:npass.value] for k, v in arrays.items()}, cnt.as_dict()
+
     def trace_words(self, words, late_energy: bool = False, optional: bool = True) -> AxionBatch:
         """Test hook (sart_trace_words): traceAxionWrapper with caller-supplied random words [6, n] instead of Philox."""
         w = np.ascontiguousarray(words, dtype=np.uint32)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Generates tests/golden/oracle_rays_v1.npz: per-ray outputs of the CPU oracle for 2000 Philox rays of each test
-configuration. The reference ships no per-ray golden data and cannot be executed here (Nim), so this fixture pins
-the ORACLE (regression guard), not the reference. Run:  python tests/golden/make_golden.py"""
+"""Generates tests/regression/oracle_rays_v1.npz: per-ray outputs of the CPU oracle for 2000 Philox rays of each test
+configuration. NOT golden data: the reference ships no per-ray vectors and cannot be executed here (Nim), so this
+fixture is the oracle's own output and only guards the oracle against accidental changes (what pins the oracle to the
+reference is tests/test_oracle_known_answers.py). Run:  python tests/regression/make_regression.py"""
 import json
 import sys
 from pathlib import Path

@@ -53,14 +53,14 @@ def test_command_line_writes_the_detector_image(rt, tmp_path, capsys):
     cfg = tmp_path / "config.toml"
     from solaraxionraytracing_b200 import config
     cfg.write_text(config.DEFAULT_CONFIG.read_text().replace('outputPath = "../out"', f'outputPath = "{tmp_path}/out"'))
-    assert main(["--config", str(cfg), "--nRays", "300000", "--ignoreGasAbs"]) == 0
+    assert main(["--config", str(cfg), "--nRays", "300000", "--ignoreGasAbs", "--allowSynthetic"]) == 0
     out = capsys.readouterr().out
     assert "Passed axions " in out and "The total flux arriving in the detector is: " in out
     img, cols = output.read_axion_image_csv(tmp_path / "out" / "axion_image_BabyIAXO.csv")   # config_default.toml setup
     flux = float(out.split("The total flux arriving in the detector is: ")[1].split()[0])
     assert img.sum() == pytest.approx(flux, rel=1e-12) and flux > 0
     assert cols["yr0"][-1] > 0          # rSigma1W of the run
-    assert main(["--config", str(cfg), "--nRays", "100000", "--xrayTest", "--ignoreDetWindow", "--angularScanMin", "0",
+    assert main(["--config", str(cfg), "--allowSynthetic", "--nRays", "100000", "--xrayTest", "--ignoreDetWindow", "--angularScanMin", "0",
                  "--angularScanMax", "0.04", "--numAngularScanPoints", "3"]) == 0
     scan = np.loadtxt(tmp_path / "out" / "angular_scan_telescope_y.csv", delimiter=",", skiprows=1)
     assert scan.shape == (3, 2) and scan[:, 1].max() == 1.0
@@ -75,7 +75,7 @@ def test_command_line_mass_scan(rt, tmp_path, capsys):
     txt += '\n[Run]\nnRays = 200000\nseed = 3\nmAxion = [0.006, 0.0082, 0.02]\n'
     cfg = tmp_path / "config.toml"
     cfg.write_text(txt)
-    assert main(["--config", str(cfg)]) == 0
+    assert main(["--config", str(cfg), "--allowSynthetic"]) == 0
     out = capsys.readouterr().out
     assert out.count("m_a = ") == 3
     imgs = np.load(tmp_path / "out" / "axion_images_mass_scan.npy")

@@ -161,3 +161,36 @@ def test_f32_full_axion_record_vs_oracle(rt, oracle, cfg, pos_tol, rel_tol):
     # rays clipped before the window carry no position and no weight
     for name in ("w", "x", "y", "r", "transProbArgon"):
         assert not np.any(getattr(gpu, name)[~tail]), name
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_passed_only_records_equal_the_full_records(rt, cfg):
+    """sart_trace_mc_passed (passed rays only, compacted on the device, single precision, two chunks of the internal
+    pipeline) against sart_trace_mc_rays on the same 2e7 rays: the same set of rays, each with the same record (the f64
+    record rounded to f32), and the counters of the fused run."""
+    setup, tb = make_config(cfg)
+    n, first = 20_000_000, 1_000
+    names = ("ray", "x", "y", "w", "shell", "energy", "r", "reflect", "transMagnet", "yaw", "alpha1", "alpha2", "pathCB",
+             "deviationDet", "transProbArgon")
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.set_precision(2)
+        full = tr.traceAxionWrapper(n, SEED, first_ray=first)
+        rec, cnt = tr.trace_passed(n, SEED, first_ray=first, fields=names)
+        tr.reset_image()
+        tr.trace_mc(n, SEED, first_ray=first)
+        fused = tr.read_image().counters[0]
+        with pytest.raises(rt.SartError, match="passed"):
+            tr.trace_passed(1_000_000, SEED, capacity=1000)
+    idx = np.flatnonzero(full.passed)
+    assert rec["ray"].size == idx.size == cnt["n_passed"]
+    order = np.argsort(rec["ray"])
+    assert np.array_equal(rec["ray"][order], idx.astype(np.uint32))
+    assert np.array_equal(rec["shell"][order], full.shell[idx].astype(np.uint8))
+    for name in names[1:]:
+        if name == "shell":
+            continue
+        a, b = rec[name][order], getattr(full, name)[idx].astype(np.float32)
+        assert np.array_equal(a, b), (name, np.flatnonzero(a != b)[:5], a[a != b][:3], b[a != b][:3])
+    for key in ("n_rays", "n_exit", "n_passed", "n_passed_till_window", "n_hit_nickel", "n_interp_clamped", "n_retraced", "n_unresolved"):
+        assert cnt[key] == fused[key], key
+    assert abs(cnt["sum_w"] / fused["sum_w"] - 1.0) < 1e-12

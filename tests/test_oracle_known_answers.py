@@ -137,10 +137,11 @@ def test_heatmap_matches_numpy(oracle):
     assert np.allclose(out, ref, rtol=1e-12)
 
 
-def test_golden_rays(oracle):
-    """Committed per-ray fixture (tests/golden/make_golden.py): guards the oracle itself against regressions."""
+def test_oracle_regression_rays(oracle):
+    """Committed per-ray fixture (tests/regression/make_regression.py): the oracle's own output of an earlier date, a
+    guard against accidental changes of the oracle — not a golden vector of the reference (it holds none for this path)."""
     from helpers import make_config
-    z = np.load(GOLDEN / "oracle_rays_v1.npz")
+    z = np.load(GOLDEN.parent / "regression" / "oracle_rays_v1.npz")
     meta = json.loads(str(z["meta"]))
     for cfg in meta["configs"]:
         setup, tb = make_config(cfg)
