@@ -329,6 +329,10 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     F.radiusAlias = h->alias_ok ? reinterpret_cast<const uint32_t*>(base + raOff) : nullptr;
     F.energyAlias = h->alias_ok ? reinterpret_cast<const uint32_t*>(base + eaOff) : nullptr;
     F.sampler = h->alias_ok ? h->sampler : SART_SAMPLER_INVERSE_CDF;
+    // the exact pipeline narrows its two CDF searches with the same guide tables (device_params.h: Tables)
+    const bool solarGuides = P.nRadii > 0 && t->fluxRadiusCDF;
+    h->tables.radiusGuide = solarGuides ? F.radiusGuide : nullptr;
+    h->tables.energyGuide = solarGuides ? F.energyGuide : nullptr;
   } else if (nCoat > 0) {
     // setup update: only the X-ray-source row (index nE) of each coating can have changed
     std::vector<float> row(reflRow), line(size_t(P.nAngles));

@@ -148,6 +148,9 @@ void derive_params(const sart_setup_t& s, const sart_tables_t* tb, Params* p) {
   p->srcRadius = s.testSource.radius;
   p->srcEnergy = s.testSource.energy;
   p->colZ = -s.testSource.distance + s.testSource.lengthCol;
+  p->shellsMonotonic = 1;
+  for (int j = 1; j < t.nShells; ++j)
+    if (!(t.allR1[j] > t.allR1[j - 1]) || !(t.allR1[j - 1] + t.allThickness[j - 1] < t.allR1[j])) p->shellsMonotonic = 0;
   if (tb) {
     p->nAngles = tb->nAngles;
     p->nReflEnergies = tb->nReflEnergies;

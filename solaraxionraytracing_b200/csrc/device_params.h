@@ -38,7 +38,8 @@ struct Params {
   int32_t telKind, nShells, reflKind, nCoatings, stage, experiment, nStripHalf, testXray;
   uint32_t flags;
   int32_t layers[SART_MAX_COATINGS];
-  int32_t holeType, numberOfHoles, parallelSource, reserved;
+  int32_t holeType, numberOfHoles, parallelSource;
+  int32_t shellsMonotonic;   // R1 strictly increasing and no glass reaching the next shell: the shell scan may stop early
   // sun + sampling
   double sunX, sunY, sunZ, radiusSun;
   // magnet / pipes (z of the clip planes, radii)
@@ -81,6 +82,11 @@ struct Tables {
   int32_t sbN, wdN, gaN, ttN;
   const ShellF64* shells;
   RadialHist rad;
+  // Optional guide tables of the two CDFs (null: search the whole table): guide[k] = lowerBound(cdf, k / nBuckets), so the
+  // lower bound of a uniform of bucket k lies in [guide[k], guide[k + 1]] and the binary search of rt:437 / rt:464 runs over
+  // that window instead of over the whole CDF — the same index, a fraction of the dependent loads.
+  const uint16_t* radiusGuide;   // [kRadGuide]
+  const uint16_t* energyGuide;   // [nRadii][kEnGuide]
 };
 
 // Guide-table buckets per CDF row; the bucket of the uniform (w + 0.5) 2^-32 is w >> (32 - bits). Sized so that the

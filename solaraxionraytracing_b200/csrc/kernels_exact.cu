@@ -193,10 +193,17 @@ k_retrace_mc_passed(const __grid_constant__ Params P, const __grid_constant__ Ta
 
 // ---- fused Monte Carlo run -------------------------------------------------------------------------------
 // Block-level counters live in shared memory and are flushed once per block.
+// 32-bit shared-memory counters (native ATOMS.ADD; the 64-bit and f64 shared-memory atomics this kernel used before are
+// compare-and-swap loops that all 128 threads of a block fought over: a third of its instructions). A block sees fewer
+// than 2^32 rays per launch (the launcher cuts a run into launches of at most 2^31 rays).
 struct BlockCounters {
-  unsigned long long n_rays;
-  unsigned long long n_exit[16];   // geometric exits (mass independent); PASSED / ZERO_WEIGHT are per mass
-  unsigned long long n_clamped;
+  unsigned int n_exit[16];   // geometric exits (mass independent); PASSED / ZERO_WEIGHT are per mass
+  unsigned int n_clamped, pad[3];
+};
+// Sums of the first axion mass live in the registers of each thread and are reduced once at the end of the kernel.
+struct ThreadSums {
+  unsigned int n_rays = 0, n_passed = 0, n_zero = 0, n_till = 0;
+  double sum_w = 0.0, sum_w2 = 0.0, sum_x = 0.0, sum_y = 0.0, sum_r = 0.0;
 };
 struct MassCounters {
   unsigned long long n_passed, n_zero, n_till_window, pad;
@@ -206,41 +213,49 @@ struct MassCounters {
 // One ray of the fused run: sample, trace, weight for every axion mass, histogram (rt:1736-2221 + 818-842).
 __device__ __forceinline__ void mc_image_ray(const Params& P, const Tables& T, int nMasses, const double* __restrict__ masses,
                                              uint64_t seed, uint64_t ray, double* __restrict__ image,
-                                             double* __restrict__ imageW2, BlockCounters* bc, MassCounters* mc) {
+                                             double* __restrict__ imageW2, BlockCounters* bc, MassCounters* mc, ThreadSums& ts) {
   const double step = (P.chipCX * 2.0 - 0.0) / double(SART_IMAGE_BINS);  // (stop - start)/rows rt:828-830
   const double stepY = (P.chipCY * 2.0 - 0.0) / double(SART_IMAGE_BINS);
   V3 O, E;
   double energy;
   int clamped = 0;
   if (!sample_ray(P, T, seed, ray, O, E, energy, clamped)) {
-    atomicAdd(&bc->n_exit[SART_EXIT_COLLIMATOR], 1ull);
+    atomicAdd(&bc->n_exit[SART_EXIT_COLLIMATOR], 1u);
     return;
   }
   Geo g;
   trace_geometry<false>(P, T, O, E, energy, g);
   g.clamped |= clamped;
   if (g.code >= 0) {
-    atomicAdd(&bc->n_exit[g.code], 1ull);
-    if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
+    atomicAdd(&bc->n_exit[g.code], 1u);
+    if (g.clamped) atomicAdd(&bc->n_clamped, 1u);
     return;
   }
   Weights w;
   ray_weights(P, T, g, w);
-  if (g.clamped) atomicAdd(&bc->n_clamped, 1ull);
-  if (g.windowMiss) atomicAdd(&bc->n_exit[SART_EXIT_WINDOW_APERTURE], 1ull);
+  if (g.clamped) atomicAdd(&bc->n_clamped, 1u);
+  if (g.windowMiss) atomicAdd(&bc->n_exit[SART_EXIT_WINDOW_APERTURE], 1u);
   for (int m = 0; m < nMasses; ++m) {
     Final f;
     ray_finish(P, g, w, masses[m], f);
-    if (f.code & SART_FLAG_PASSED_TILL_WINDOW) atomicAdd(&mc[m].n_till_window, 1ull);
     const int code = f.code & SART_CODE_MASK;
-    if (code == SART_EXIT_ZERO_WEIGHT) atomicAdd(&mc[m].n_zero, 1ull);
-    if (code != SART_EXIT_PASSED) continue;
-    atomicAdd(&mc[m].n_passed, 1ull);
-    atomicAdd(&mc[m].sum_w, f.w);
-    atomicAdd(&mc[m].sum_w2, f.w * f.w);
-    atomicAdd(&mc[m].sum_x, f.x);
-    atomicAdd(&mc[m].sum_y, f.y);
-    atomicAdd(&mc[m].sum_r, f.r);
+    if (m == 0) {   // the first (usually only) mass: per-thread registers
+      if (f.code & SART_FLAG_PASSED_TILL_WINDOW) ++ts.n_till;
+      if (code == SART_EXIT_ZERO_WEIGHT) ++ts.n_zero;
+      if (code != SART_EXIT_PASSED) continue;
+      ++ts.n_passed;
+      ts.sum_w += f.w; ts.sum_w2 += f.w * f.w; ts.sum_x += f.x; ts.sum_y += f.y; ts.sum_r += f.r;
+    } else {
+      if (f.code & SART_FLAG_PASSED_TILL_WINDOW) atomicAdd(&mc[m].n_till_window, 1ull);
+      if (code == SART_EXIT_ZERO_WEIGHT) atomicAdd(&mc[m].n_zero, 1ull);
+      if (code != SART_EXIT_PASSED) continue;
+      atomicAdd(&mc[m].n_passed, 1ull);
+      atomicAdd(&mc[m].sum_w, f.w);
+      atomicAdd(&mc[m].sum_w2, f.w * f.w);
+      atomicAdd(&mc[m].sum_x, f.x);
+      atomicAdd(&mc[m].sum_y, f.y);
+      atomicAdd(&mc[m].sum_r, f.r);
+    }
     // prepareHeatmap rt:839-842
     const double cx = floor((f.x - 0.0) / step), cy = floor((f.y - 0.0) / stepY);
     if (cx >= 0.0 && cx < double(SART_IMAGE_BINS) && cy >= 0.0 && cy < double(SART_IMAGE_BINS)) {
@@ -266,39 +281,61 @@ k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Table
   extern __shared__ unsigned char smem_raw[];
   BlockCounters* bc = reinterpret_cast<BlockCounters*>(smem_raw);
   MassCounters* mc = reinterpret_cast<MassCounters*>(smem_raw + sizeof(BlockCounters));
-  for (int k = threadIdx.x; k < int(sizeof(BlockCounters) / 8); k += blockDim.x)
-    reinterpret_cast<unsigned long long*>(bc)[k] = 0ull;
+  unsigned long long* nRaysBlock = &mc[0].pad;   // rays of this block (zeroed with the mass counters)
+  for (int k = threadIdx.x; k < int(sizeof(BlockCounters) / 4); k += blockDim.x)
+    reinterpret_cast<unsigned int*>(bc)[k] = 0u;
   for (int k = threadIdx.x; k < int(nMasses * sizeof(MassCounters) / 8); k += blockDim.x)
     reinterpret_cast<unsigned long long*>(mc)[k] = 0ull;
   __syncthreads();
 
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  ThreadSums ts;
   if (list) {   // re-trace of the uncertain rays of an FP32 launch, which has counted them in n_rays already
     const uint32_t nList = min(*listCount, listCap);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nList; j += uint32_t(stride))
-      mc_image_ray(P, T, nMasses, masses, seed, first + list[j], image, imageW2, bc, mc);
+      mc_image_ray(P, T, nMasses, masses, seed, first + list[j], image, imageW2, bc, mc, ts);
     if (blockIdx.x == 0 && threadIdx.x == 0)
       for (int m = 0; m < nMasses; ++m) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[m].n_retraced), (unsigned long long)nList);
   } else {
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nRays; i += stride) {
-      atomicAdd(&bc->n_rays, 1ull);
-      mc_image_ray(P, T, nMasses, masses, seed, first + i, image, imageW2, bc, mc);
+      ++ts.n_rays;
+      mc_image_ray(P, T, nMasses, masses, seed, first + i, image, imageW2, bc, mc, ts);
     }
+  }
+  // the thread sums of the first mass: warp shuffle, then one shared-memory atomic per warp and quantity
+  for (int o = 16; o > 0; o >>= 1) {
+    ts.n_rays += __shfl_down_sync(0xffffffffu, ts.n_rays, o);
+    ts.n_passed += __shfl_down_sync(0xffffffffu, ts.n_passed, o);
+    ts.n_zero += __shfl_down_sync(0xffffffffu, ts.n_zero, o);
+    ts.n_till += __shfl_down_sync(0xffffffffu, ts.n_till, o);
+    ts.sum_w += __shfl_down_sync(0xffffffffu, ts.sum_w, o);
+    ts.sum_w2 += __shfl_down_sync(0xffffffffu, ts.sum_w2, o);
+    ts.sum_x += __shfl_down_sync(0xffffffffu, ts.sum_x, o);
+    ts.sum_y += __shfl_down_sync(0xffffffffu, ts.sum_y, o);
+    ts.sum_r += __shfl_down_sync(0xffffffffu, ts.sum_r, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(nRaysBlock, (unsigned long long)ts.n_rays);
+    atomicAdd(&mc[0].n_passed, (unsigned long long)ts.n_passed);
+    atomicAdd(&mc[0].n_zero, (unsigned long long)ts.n_zero);
+    atomicAdd(&mc[0].n_till_window, (unsigned long long)ts.n_till);
+    atomicAdd(&mc[0].sum_w, ts.sum_w); atomicAdd(&mc[0].sum_w2, ts.sum_w2);
+    atomicAdd(&mc[0].sum_x, ts.sum_x); atomicAdd(&mc[0].sum_y, ts.sum_y); atomicAdd(&mc[0].sum_r, ts.sum_r);
   }
   __syncthreads();
   // flush
   for (int m = threadIdx.x; m < nMasses; m += blockDim.x) {
     sart_counters_t* c = counters + m;
-    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_rays), bc->n_rays);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_rays), *nRaysBlock);
     for (int e = 1; e < SART_N_EXIT_CODES; ++e)
       if (e != SART_EXIT_ZERO_WEIGHT && bc->n_exit[e])
-        atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[e]), bc->n_exit[e]);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[e]), (unsigned long long)bc->n_exit[e]);
     atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[SART_EXIT_PASSED]), mc[m].n_passed);
     atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_exit[SART_EXIT_ZERO_WEIGHT]), mc[m].n_zero);
     atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_passed), mc[m].n_passed);
     atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_passed_till_window), mc[m].n_till_window);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_hit_nickel), bc->n_exit[SART_EXIT_NICKEL]);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_interp_clamped), bc->n_clamped);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_hit_nickel), (unsigned long long)bc->n_exit[SART_EXIT_NICKEL]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c->n_interp_clamped), (unsigned long long)bc->n_clamped);
     atomicAdd(&c->sum_w, mc[m].sum_w);
     atomicAdd(&c->sum_w2, mc[m].sum_w2);
     atomicAdd(&c->sum_x, mc[m].sum_x);
@@ -410,8 +447,13 @@ cudaError_t launch_retrace_mc_image(const Params& P, const Tables& T, int nMasse
                                     sart_counters_t* counters, int smCount, cudaStream_t s) {
   const int block = 128;
   const size_t smem = sizeof(BlockCounters) + size_t(nMasses) * sizeof(MassCounters);
-  k_trace_mc_image<<<unsigned(smCount) * 4u, block, smem, s>>>(P, T, nMasses, masses, first, 0, seed, q.list, q.count, q.cap, image,
-                                                             imageW2, counters);
+  int perSM = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace_mc_image, block, smem);
+  if (e != cudaSuccess) return e;
+  if (perSM < 1) perSM = 1;
+  // one resident wave (the list length lives on the device): latency-bound FP64 code wants every warp slot it can get
+  k_trace_mc_image<<<unsigned(smCount * perSM), block, smem, s>>>(P, T, nMasses, masses, first, 0, seed, q.list, q.count, q.cap, image,
+                                                                 imageW2, counters);
   return cudaGetLastError();
 }
 cudaError_t launch_retrace_mc_rays(const Params& P, const Tables& T, double mAxion, uint64_t first, size_t n, uint64_t seed,

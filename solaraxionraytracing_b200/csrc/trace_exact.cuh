@@ -278,7 +278,18 @@ __device__ __forceinline__ void trace_geometry(const Params& P, const Tables& T,
   if (radialDist > __ldg(&S[nS - 1].R1)) { g.code = SART_EXIT_OUTSIDE_SHELLS; return; }
   int hitLayer = -1;
   double minDist = INFINITY;
-  {
+  if (P.shellsMonotonic) {
+    // the reference's scan over every shell (no break, rt:1937-1950), for radii that increase shell by shell with no glass
+    // reaching the next one: the hit shell is the first with R1 > radialDist, and only the shell below it can show its
+    // glass front — the same outcome from a binary search and one test
+    int lo = 0, hi = nS;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(&S[mid].R1) > radialDist) hi = mid; else lo = mid + 1;
+    }
+    if (lo > 0 && radialDist > __ldg(&S[lo - 1].R1) && radialDist < __ldg(&S[lo - 1].R1pT)) { g.code = SART_EXIT_GLASS_FRONT; return; }
+    if (lo < nS) { hitLayer = lo; minDist = __ldg(&S[lo].R1) - radialDist; }
+  } else {
     for (int j = 0; j < nS; ++j) {
       const double R1 = __ldg(&S[j].R1);
       if (radialDist > R1 && radialDist < __ldg(&S[j].R1pT)) { g.code = SART_EXIT_GLASS_FRONT; return; }
@@ -546,7 +557,13 @@ __device__ __forceinline__ bool sample_ray_words(const Params& P, const Tables& 
     // getRandomPointFromSolarModel rt:425-442
     const double angle1 = 360.0 * u01(w[0]);
     const double angle2 = 180.0 * u01(w[1]);
-    const int rIdx = lower_bound(T.fluxRadiusCDF, 0, P.nRadii, u01(w[2]));
+    int rLo = 0, rHi = P.nRadii;
+    if (T.radiusGuide) {   // window of the word's guide bucket (device_params.h: Tables::radiusGuide)
+      const uint32_t k = w[2] >> (32 - kRadGuideBits);
+      rLo = int(__ldg(T.radiusGuide + k));
+      if (k + 1 < uint32_t(kRadGuide)) rHi = min(int(__ldg(T.radiusGuide + k + 1)), P.nRadii);
+    }
+    const int rIdx = lower_bound(T.fluxRadiusCDF, rLo, rHi, u01(w[2]));
     const double r = (0.0015 + double(rIdx) * 0.0005) * P.radiusSun;
     double s1, c1, s2, c2;
     sincos(angle1 * kRadPerDeg, &s1, &c1);
@@ -567,7 +584,14 @@ __device__ __forceinline__ bool sample_ray_words(const Params& P, const Tables& 
     if (iRad < 0) { iRad = 0; clamped = 1; }
     if (iRad > P.nRadii - 1) { iRad = P.nRadii - 1; clamped = 1; }
     const double* cdf = T.diffFluxCDFs + size_t(iRad) * P.nEnergies;
-    int idx = lower_bound(cdf, 0, P.nEnergies, u01(w[5]));
+    int eLo = 0, eHi = P.nEnergies;
+    if (T.energyGuide) {
+      const uint32_t k = w[5] >> (32 - kEnGuideBits);
+      const uint16_t* gRow = T.energyGuide + size_t(iRad) * kEnGuide;
+      eLo = int(__ldg(gRow + k));
+      if (k + 1 < uint32_t(kEnGuide)) eHi = min(int(__ldg(gRow + k + 1)), P.nEnergies);
+    }
+    int idx = lower_bound(cdf, eLo, eHi, u01(w[5]));
     if (idx > P.nEnergies - 1) { idx = P.nEnergies - 1; clamped = 1; }
     const double e = __ldg(T.energies + idx);
     energy = e > 0.03 ? e : 0.03;
