@@ -126,17 +126,22 @@ def test_mc_image_matches_oracle(rt, oracle, cfg):
         res = tr.read_image()
     c, cr = res.counters[0], cnt_ref[0]
     assert c["n_rays"] == n == cr["n_rays"]
-    budget = n // 5000
+    # The exact pipeline on the oracle's own rays. The only arithmetic that differs is libm (CUDA vs glibc sin/cos of the
+    # emission angles, <= 1 ulp, i.e. 1e-4 mm at the solar radius, which the reference's geometry carries to the detector):
+    # at most 2 rays of 3e5 may change their exit code, the flux agrees to 1e-6, and the image differs only through rays
+    # that such a shift moves across a bin edge (L1 difference below 5e-4 of the total).
+    budget = 2
     for k, v in cr["n_exit"].items():
         assert abs(c["n_exit"][k] - v) <= budget, (k, c["n_exit"][k], v)
     assert abs(c["n_passed"] - cr["n_passed"]) <= budget
     assert abs(c["n_passed_till_window"] - cr["n_passed_till_window"]) <= budget
     assert c["n_hit_nickel"] == c["n_exit"]["nickel"]
-    assert abs(c["sum_w"] / cr["sum_w"] - 1.0) < 1e-3
-    # image: same rays land in the same bins except those within ~1e-3 mm of a bin edge
+    assert abs(c["sum_w"] / cr["sum_w"] - 1.0) < 1e-6
     tot = img_ref.sum()
-    assert abs(res.image.sum() / tot - 1.0) < 1e-3
-    assert np.abs(res.image[0] - img_ref[0]).sum() / tot < 0.05
+    assert abs(res.image.sum() / tot - 1.0) < 1e-6
+    l1 = np.abs(res.image[0] - img_ref[0]).sum() / tot
+    print(cfg, "image L1 difference / total", l1)
+    assert l1 < 5e-4
     # Σw in the image equals the counter
     assert abs(res.image.sum() / c["sum_w"] - 1.0) < 1e-9
     assert abs(res.image_w2.sum() / c["sum_w2"] - 1.0) < 1e-9

@@ -1,0 +1,39 @@
+"""The oracle's exit codes against 60-digit arithmetic (tests/hp_trace.py: classify), clipped rays included.
+
+The oracle and the exact CUDA pipeline are two statements of the same reading of traceAxion; this is the independent
+check of that reading's geometry: every decision of rt:1813-2147 re-derived from the reference's formulas in mpmath. For a
+ray that stays further than 1e-2 mm from every decision boundary — far above the reference's own f64 rounding noise — the
+exit code does not depend on the arithmetic, so the oracle must return the 60-digit one. (A ray that misses mirror 1 is
+carried on by the reference with pointMirror1 = pointExitCB, rt:655-658, and ends as nickel or no_mirror_hit depending on
+that garbage: either is accepted there.)"""
+import numpy as np
+import pytest
+
+from helpers import make_config
+from solaraxionraytracing_b200 import abi
+
+import hp_trace
+
+
+@pytest.mark.parametrize("cfg,n,kinds", [("cast_llnl", 2500, 4), ("babyiaxo_xmm", 900, 5), ("cast_abrixas", 1500, 4)])
+def test_oracle_exit_codes_agree_with_60_digit_geometry(oracle, cfg, n, kinds):
+    setup, tb = make_config(cfg)
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, 424242)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy, optional=False)
+    code = ref.code & abi.CODE_MASK
+    seen, checked = set(), 0
+    for i in range(n):
+        hp, margin, ambiguous = hp_trace.classify(setup, origin[:, i], exit_xy[:, i])
+        if margin < 1e-2:
+            continue
+        got = int(code[i])
+        if got == abi.EXIT_ZERO_WEIGHT:      # reached the detector window with weight 0: geometry says "passed"
+            got = abi.EXIT_PASSED
+        if ambiguous:
+            assert got in (abi.EXIT_NO_MIRROR_HIT, abi.EXIT_NICKEL), (i, got, hp)
+        else:
+            assert got == hp, (i, got, hp, margin)
+        seen.add(hp)
+        checked += 1
+    assert checked > 0.9 * n
+    assert len(seen) >= kinds, seen      # clipped rays of several kinds, not only passed ones
