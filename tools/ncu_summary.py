@@ -11,7 +11,7 @@ def main(path, out=None, title=""):
         name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
         for h,u,v in zip(hdr,units,vals):
             if h in KEEP or (h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio')):
-                lines.append(f"{name.split('(')[0]},{h},{u},{v}")
+                lines.append(f"{name.split('(')[0].replace(',', ';')},{h},{u},{v}")
     txt = "\n".join(lines)+"\n"
     if out: open(out,"w").write(txt)
     print(txt)
