@@ -425,7 +425,11 @@ def other_configs_leg(rt, tables, torch, device, peak_tflops, rank=0, world=1, r
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         with torch.cuda.stream(stream):
             tr.reset_image()
-            tr.trace_mc(max(1, n // 10), SEED, first_ray=first)   # warm-up
+            tr.trace_mc(max(1, n // 10), SEED, first_ray=first)   # warm-up (a full-size launch: the re-trace queue gets its final size)
+            tr.reset_image()
+            tr.trace_mc(n, SEED, first_ray=first)
+            if merge:
+                tr.allreduce()   # the first collective of a new communicator sets up its connections
             tr.reset_image()
             for a, b in ev:
                 flush.zero_()
@@ -698,10 +702,17 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner to stdout when a
+    # communicator is created): send file descriptor 1 to stderr for the whole run and keep the real stdout for the line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
