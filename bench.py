@@ -501,6 +501,31 @@ def other_configs_leg(rt, tables, torch, device, peak_tflops, rank=0, world=1, r
     return out
 
 
+def passed_leg(tr, torch, n: int = 1 << 26, reps: int = 3):
+    """sart_trace_mc_passed: the drop-in for consumers that filter `passed` first (generateResultPlots does, rt:2252-2289) —
+    only the passed rays cross PCIe, as f32 records compacted on the GPU (ray offset, x, y, w, shell = 17 B per passed
+    ray), in 2^24-ray chunks whose copies overlap the next chunk's kernels. Pinned host arrays."""
+    import numpy as np
+    from solaraxionraytracing_b200 import abi
+    tr.set_precision(2)
+    dt = {name: np.dtype(t) for name, t in abi.PASSED_OUT_FIELDS}
+    fields = ("ray", "x", "y", "w", "shell")
+    torch_dt = {"ray": torch.int32, "x": torch.float32, "y": torch.float32, "w": torch.float32, "shell": torch.uint8}
+    pinned = {f: torch.empty(n, dtype=torch_dt[f]).pin_memory() for f in fields}
+    bufs = {f: pinned[f].numpy().view(dt[f]) for f in fields}
+    rec, cnt = tr.trace_passed(n, SEED, first_ray=0, fields=fields, buffers=bufs)
+    t0 = time.perf_counter()
+    for k in range(reps):
+        rec, cnt = tr.trace_passed(n, SEED, first_ray=(1 + k) * n, fields=fields, buffers=bufs)
+    dtm = (time.perf_counter() - t0) / reps
+    n_pass = int(rec["ray"].size)
+    bytes_per = sum(dt[f].itemsize for f in fields)
+    return {"api": "sart_trace_mc_passed (records of the passed rays only, compacted, f32)", "rays_per_call": n, "value": n / dtm,
+            "unit": "rays/s", "passed_fraction": n_pass / n, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": bytes_per * n_pass,
+            "d2h_GBps": bytes_per * n_pass / dtm / 1e9, "bytes_per_passed_ray": bytes_per,
+            "retraced_fp64_fraction": cnt["n_retraced"] / n}
+
+
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
     try:
@@ -678,6 +703,7 @@ def run_ours(args):
         if n_gpus == 1 and not args.no_presampled:
             out["presampled"] = presampled_leg(tr, torch, local)
             out["e2e_records"] = records_leg(tr, torch)
+            out["e2e_passed"] = passed_leg(tr, torch)
         if other is not None:
             out["configs"] = other
         tr.set_precision({"exact": 0, "fast": 1, "f32": 2}[precision])
