@@ -438,6 +438,14 @@ void sart_alias_table(const uint32_t* thr, int n, uint32_t* entries);
  * SART_ERR_CONFIG when the shells are too closely spaced for the table (the throughput modes then refuse the setup). */
 int sart_shell_lookup(const sart_setup_t* setup, int n, const float* rho, int32_t* via_table, int32_t* via_scan);
 
+/* ---- the error budgets of the FP32 decisions (host helper, exported for tests and for the curious): for a Monte Carlo ray
+ * of this setup with slopes |sx| + |sy| = slope_sum and emission radius rs (in solar radii), the lateral position budget
+ * before the mirrors and at the detector plane [mm], as the kernels of precision mode 2 form them (sart_set_retrace;
+ * DESIGN.md section 3b), and whether the pipe tests are skipped for this setup (no solar ray can reach the pipe wall).
+ * nRadii: rows of the solar table (the outermost emission shell bounds the slopes). */
+int sart_error_budgets(const sart_setup_t* setup, int nRadii, double scale, double slope_sum, double rs, double* lat_mm,
+                       double* det_mm, int* pipes_free);
+
 #ifdef __cplusplus
 }
 #endif

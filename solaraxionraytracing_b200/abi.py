@@ -224,5 +224,7 @@ SIGNATURES = {
     "sart_cdf_thresholds": (None, [c_double_p, C.c_int, C.POINTER(C.c_uint32)]),
     "sart_set_sampler": (C.c_int, [H, C.c_int]),
     "sart_alias_table": (None, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
+    "sart_error_budgets": (C.c_int, [C.POINTER(Setup), C.c_int, C.c_double, C.c_double, C.c_double, c_double_p, c_double_p,
+                                     C.POINTER(C.c_int)]),
     "sart_shell_lookup": (C.c_int, [C.POINTER(Setup), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }

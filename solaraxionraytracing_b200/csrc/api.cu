@@ -499,6 +499,28 @@ int sart_shell_lookup(const sart_setup_t* setup, int n, const float* rho, int32_
   return SART_OK;
 }
 
+int sart_error_budgets(const sart_setup_t* setup, int nRadii, double scale, double slope_sum, double rs, double* lat_mm,
+                       double* det_mm, int* pipes_free) {
+  int rc = validate(setup, nullptr);
+  if (rc) return rc;
+  if (!(scale >= 0.0) || nRadii < 1) return fail(SART_ERR_ARG, "sart_error_budgets: bad argument");
+  Params P;
+  derive_params(*setup, nullptr, &P);
+  P.nRadii = nRadii;
+  fast::FastParams F;
+  fast::derive_params(*setup, P, &F);
+  std::vector<ShellF64> sh64(SART_MAX_SHELLS);
+  derive_shells(*setup, sh64.data());
+  std::vector<fast::ShellFast> shf(SART_MAX_SHELLS);
+  fast::derive_shells(*setup, sh64.data(), shf.data());
+  fast::Tol32 t;
+  fast::derive_tolerances(F, shf.data(), setup->telescope.nShells, float(scale), &t);
+  if (lat_mm) *lat_mm = double(t.latA) + double(t.latS) * rs + double(t.latT) * slope_sum;
+  if (det_mm) *det_mm = double(t.detA) + double(t.detS) * rs + double(t.detT) * slope_sum;
+  if (pipes_free) *pipes_free = F.pipesFree;
+  return SART_OK;
+}
+
 void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {
   uint32_t w[6];
   ray_words(seed, ray, w);
