@@ -117,6 +117,25 @@ struct Blob {  // bump allocator over one device allocation
   }
 };
 
+// numericalnim newLinear1D.eval as the device evaluates it (trace_exact.cuh: eval_linear1d), operation for operation: this
+// translation unit's host code is compiled without contraction, the device code with -fmad=false, so both produce the same
+// bits.
+static double eval_linear1d_host(const sart_interp1d_t& t, double x, int* clamped) {
+  const int n = t.n;
+  if (n < 2 || !t.x || !t.y) { *clamped = 1; return (n == 1 && t.y) ? t.y[0] : 0.0; }
+  const double x0 = t.x[0], xn = t.x[n - 1];
+  if (!(x >= x0)) { *clamped = 1; x = x0; }
+  if (!(x <= xn)) { *clamped = 1; x = xn; }
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (t.x[mid] <= x) lo = mid; else hi = mid;
+  }
+  const double xl = t.x[lo], yl = t.y[lo];
+  const double slope = (t.y[lo + 1] - yl) / (t.x[lo + 1] - xl);
+  return yl + (x - xl) * slope;
+}
+
 static int upload_tables(sart_handle* h, const sart_tables_t* t) {
   Blob b;
   size_t oEn = 0, oRC = 0, oDC = 0, oRefl = 0;
@@ -135,6 +154,22 @@ static int upload_tables(sart_handle* h, const sart_tables_t* t) {
   std::vector<sart::ShellF64> shells(SART_MAX_SHELLS);
   derive_shells(h->setup, shells.data());
   const size_t oSh = b.add(shells.data(), shells.size());
+  // window / strongback / detector-gas factors at each tabulated energy (device_params.h: EnergyFactors)
+  std::vector<EnergyFactors> ef;
+  size_t oEf = 0;
+  if (solar) {
+    ef.resize(size_t(t->nEnergies));
+    for (int i = 0; i < t->nEnergies; ++i) {
+      const double E = t->energies[i] > 0.03 ? t->energies[i] : 0.03;   // rt:470-471
+      int cw = 0, cs = 0, cg = 0;
+      ef[size_t(i)].window = eval_linear1d_host(t->windowTransmission, E, &cw);
+      ef[size_t(i)].strongback = eval_linear1d_host(t->strongbackTransmission, E, &cs);
+      ef[size_t(i)].gas = eval_linear1d_host(t->gasAbsorption, E, &cg);
+      ef[size_t(i)].clamped = cw | (cs << 1) | (cg << 2);
+      ef[size_t(i)].pad = 0;
+    }
+    oEf = b.add(ef.data(), ef.size());
+  }
 
   if (h->table_blob) { cudaFree(h->table_blob); h->table_blob = nullptr; }
   SART_CUDA(cudaMalloc(&h->table_blob, b.off ? b.off : 256));
@@ -162,6 +197,7 @@ static int upload_tables(sart_handle* h, const sart_tables_t* t) {
       *PN[k] = I[k]->n;
     }
   T.shells = reinterpret_cast<const ShellF64*>(base + oSh);
+  if (solar) T.energyFactors = reinterpret_cast<const EnergyFactors*>(base + oEf);
   h->shell_offset = oSh;
   h->have_solar = solar ? 1 : 0;
   h->n_refl_coatings = refl ? t->nCoatings : 0;

@@ -87,6 +87,16 @@ struct Tables {
   // that window instead of over the whole CDF — the same index, a fraction of the dependent loads.
   const uint16_t* radiusGuide;   // [kRadGuide]
   const uint16_t* energyGuide;   // [nRadii][kEnGuide]
+  // Optional (null: interpolate per ray): window / strongback / detector-gas factors of rt:2165-2190 at each tabulated
+  // energy, evaluated on the host by the very expression the device uses (eval_linear1d: same IEEE operations, no
+  // contraction on either side => the same bits). A Monte Carlo ray's energy is a table value (rt:470), so its three
+  // 10-step binary searches with dependent loads become one 32-byte record.
+  const struct EnergyFactors* energyFactors;   // [nEnergies]
+};
+struct EnergyFactors {
+  double window, strongback, gas;
+  int32_t clamped;   // bit 0 / 1 / 2: the energy lies outside the window / strongback / gas grid
+  int32_t pad;
 };
 
 // Guide-table buckets per CDF row; the bucket of the uniform (w + 0.5) 2^-32 is w >> (32 - bits). Sized so that the

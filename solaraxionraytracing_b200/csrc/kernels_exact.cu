@@ -40,10 +40,11 @@ __device__ __forceinline__ void store_ray(const RayOutDev& o, size_t i, const Ge
 }
 
 __device__ __forceinline__ void trace_and_store(const Params& P, const Tables& T, double mAxion, V3 O, V3 E,
-                                                double energy, int preClamped, const RayOutDev& out, size_t i) {
+                                                double energy, int preClamped, const RayOutDev& out, size_t i, int eIdx = -1) {
   Geo g;
   trace_geometry<true>(P, T, O, E, energy, g);
   g.clamped |= preClamped;
+  g.eIdx = eIdx;
   Weights w = {};
   Final f = {};
   if (g.code < 0) {
@@ -98,7 +99,8 @@ __device__ __forceinline__ void mc_ray_record(const Params& P, const Tables& T, 
     ray_words(seed, first + i, w);
   }
   if (emit) emit[i] = P.testXray ? 0 : min(lower_bound(T.fluxRadiusCDF, 0, P.nRadii, u01(w[2])), P.nRadii - 1);   // rIdx rt:437
-  if (!sample_ray_words(P, T, w, O, E, energy, clamped)) {
+  int eIdx = -1;
+  if (!sample_ray_words(P, T, w, O, E, energy, clamped, &eIdx)) {
     out.x[i] = 0.0; out.y[i] = 0.0; out.w[i] = 0.0; out.code[i] = SART_EXIT_COLLIMATOR; out.shell[i] = -1;
     if (out.energy) out.energy[i] = energy;
     if (out.reflect) out.reflect[i] = 0.0;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void mc_ray_record(const Params& P, const Tables& T, 
     if (out.transProbArgon) out.transProbArgon[i] = 0.0;
     return;
   }
-  trace_and_store(P, T, mAxion, O, E, energy, clamped, out, i);
+  trace_and_store(P, T, mAxion, O, E, energy, clamped, out, i, eIdx);
 }
 
 __global__ void __launch_bounds__(128)
@@ -150,10 +152,12 @@ k_retrace_mc_passed(const __grid_constant__ Params P, const __grid_constant__ Ta
     V3 O, E;
     double energy;
     int clamped = 0;
-    if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped)) { addu(&c->n_exit[SART_EXIT_COLLIMATOR], 1); continue; }
+    int eIdx = -1;
+    if (!sample_ray(P, T, seed, first + i, O, E, energy, clamped, &eIdx)) { addu(&c->n_exit[SART_EXIT_COLLIMATOR], 1); continue; }
     Geo g;
     trace_geometry<true>(P, T, O, E, energy, g);
     g.clamped |= clamped;
+    g.eIdx = eIdx;
     if (g.clamped) addu(&c->n_interp_clamped, 1);
     if (g.code >= 0) {
       addu(&c->n_exit[g.code], 1);
@@ -219,13 +223,15 @@ __device__ __forceinline__ void mc_image_ray(const Params& P, const Tables& T, i
   V3 O, E;
   double energy;
   int clamped = 0;
-  if (!sample_ray(P, T, seed, ray, O, E, energy, clamped)) {
+  int eIdx = -1;
+  if (!sample_ray(P, T, seed, ray, O, E, energy, clamped, &eIdx)) {
     atomicAdd(&bc->n_exit[SART_EXIT_COLLIMATOR], 1u);
     return;
   }
   Geo g;
   trace_geometry<false>(P, T, O, E, energy, g);
   g.clamped |= clamped;
+  g.eIdx = eIdx;
   if (g.code >= 0) {
     atomicAdd(&bc->n_exit[g.code], 1u);
     if (g.clamped) atomicAdd(&bc->n_clamped, 1u);
@@ -272,8 +278,11 @@ __device__ __forceinline__ void mc_image_ray(const Params& P, const Tables& T, i
   }
 }
 
+#ifndef SART_EXACT_MINBLOCKS
+#define SART_EXACT_MINBLOCKS 6   // 85 registers instead of 108: 24 instead of 16 warps per SM for this latency-bound kernel (+5 %; 8 is slower)
+#endif
 // `list` != nullptr: trace the rays first + list[j], j < min(*listCount, listCap), instead of first + [0, nRays).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SART_EXACT_MINBLOCKS)
 k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Tables T, int nMasses,
                  const double* __restrict__ masses, uint64_t first, uint64_t nRays, uint64_t seed,
                  const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount, uint32_t listCap,

@@ -145,6 +145,7 @@ struct Geo {
   int clamped;
   int windowMiss;  // rt:2139-2147 (decided here, reported after the weight like the reference)
   int strongback;  // window strip hit (rt:2167-2177); 2 = no strip loop ran (numberOfStrips == 0)
+  int eIdx;        // index of the ray's energy in the tabulated energies (Monte Carlo rays), -1 if it is not a table value
   double energy, pathCB, ya, cosya, alpha1, alpha2, pitch, distancePipe;
   double xw, yw;   // pointDetectorWindow after the shifts (window frame)
   double deviationDet;
@@ -152,7 +153,7 @@ struct Geo {
 
 template <bool kFull>
 __device__ __forceinline__ void trace_geometry(const Params& P, const Tables& T, V3 O, V3 E, double energy, Geo& g) {
-  g.code = -1; g.shell = -1; g.clamped = 0; g.windowMiss = 0; g.strongback = 0;
+  g.code = -1; g.shell = -1; g.clamped = 0; g.windowMiss = 0; g.strongback = 0; g.eIdx = -1;
   g.energy = energy; g.pathCB = 0.0; g.ya = 0.0; g.cosya = 0.0; g.alpha1 = 0.0; g.alpha2 = 0.0; g.pitch = 0.0;
   g.distancePipe = 0.0; g.xw = 0.0; g.yw = 0.0; g.deviationDet = 0.0;
 
@@ -478,11 +479,19 @@ __device__ __forceinline__ void ray_weights(const Params& P, const Tables& T, Ge
   }
   // window + detector gas: the reference evaluates these only past the aperture cut (rt:2139-2147)
   if (g.windowMiss) { w.transWindow = 0.0; w.absGas = 0.0; }
-  else {
-  if (g.strongback == 1) w.transWindow = eval_linear1d(T.sbX, T.sbY, T.sbN, E, g.clamped);
-  else if (g.strongback == 0) w.transWindow = eval_linear1d(T.wdX, T.wdY, T.wdN, E, g.clamped);
-  else w.transWindow = 0.0;
-  w.absGas = eval_linear1d(T.gaX, T.gaY, T.gaN, E, g.clamped);
+  else if (g.eIdx >= 0 && T.energyFactors) {   // the same values from the per-energy table (device_params.h: EnergyFactors)
+    const EnergyFactors* f = T.energyFactors + g.eIdx;
+    const int cl = __ldg(&f->clamped);
+    if (g.strongback == 1) { w.transWindow = __ldg(&f->strongback); g.clamped |= (cl >> 1) & 1; }
+    else if (g.strongback == 0) { w.transWindow = __ldg(&f->window); g.clamped |= cl & 1; }
+    else w.transWindow = 0.0;
+    w.absGas = __ldg(&f->gas);
+    g.clamped |= (cl >> 2) & 1;
+  } else {
+    if (g.strongback == 1) w.transWindow = eval_linear1d(T.sbX, T.sbY, T.sbN, E, g.clamped);
+    else if (g.strongback == 0) w.transWindow = eval_linear1d(T.wdX, T.wdY, T.wdN, E, g.clamped);
+    else w.transWindow = 0.0;
+    w.absGas = eval_linear1d(T.gaX, T.gaY, T.gaN, E, g.clamped);
   }
   // buffer gas
   if (P.stage == SART_SK_GAS) {
@@ -552,7 +561,8 @@ __device__ __forceinline__ void ray_finish(const Params& P, const Geo& g, const 
 // Sampling block of traceAxion (rt:1754-1764) from the six Philox uniforms of the ray.
 // Returns false if an X-ray test-source ray is stopped by its collimator (rt:1800-1801).
 __device__ __forceinline__ bool sample_ray_words(const Params& P, const Tables& T, const uint32_t w[6], V3& O, V3& E,
-                                                 double& energy, int& clamped) {
+                                                 double& energy, int& clamped, int* eIdx = nullptr) {
+  if (eIdx) *eIdx = -1;
   if (!P.testXray) {
     // getRandomPointFromSolarModel rt:425-442
     const double angle1 = 360.0 * u01(w[0]);
@@ -595,6 +605,7 @@ __device__ __forceinline__ bool sample_ray_words(const Params& P, const Tables& 
     if (idx > P.nEnergies - 1) { idx = P.nEnergies - 1; clamped = 1; }
     const double e = __ldg(T.energies + idx);
     energy = e > 0.03 ? e : 0.03;
+    if (eIdx) *eIdx = idx;
     return true;
   }
   // X-ray test source rt:1765-1801
@@ -618,10 +629,10 @@ __device__ __forceinline__ bool sample_ray_words(const Params& P, const Tables& 
   return sqrt(qx * qx + qy * qy) < P.srcRadius;
 }
 __device__ __forceinline__ bool sample_ray(const Params& P, const Tables& T, uint64_t seed, uint64_t ray, V3& O, V3& E,
-                                           double& energy, int& clamped) {
+                                           double& energy, int& clamped, int* eIdx = nullptr) {
   uint32_t w[6];
   ray_words(seed, ray, w);
-  return sample_ray_words(P, T, w, O, E, energy, clamped);
+  return sample_ray_words(P, T, w, O, E, energy, clamped, eIdx);
 }
 
 }  // namespace sart
