@@ -278,7 +278,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   const int nE = int(h->h_energies.size());
   std::vector<fast::EnergyLUT> lut;
   std::vector<fast::GasLUT> glut;
-  fast::build_energy_lut(nE, h->h_energies.data(), I[0], I[1], I[2], h->setup.testSource.energy, &lut, &glut);
+  fast::build_energy_lut(nE, h->h_energies.data(), I[0], I[1], I[2], h->setup.testSource.energy, P.reflEMin, P.reflEMax, &lut, &glut);
   const int nCoat = P.nAngles > 0 && !h->h_refl32.empty() ? int(h->h_refl32.size() / (size_t(P.nAngles) * P.nReflEnergies)) : 0;
   const size_t reflRow = size_t(P.nAngles), reflPlane = reflRow * (size_t(nE) + 1);
   // the throughput kernels address table rows with 32-bit element offsets

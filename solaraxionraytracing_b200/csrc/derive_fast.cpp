@@ -410,8 +410,14 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   }
 }
 
+// eval_linear1d (trace_exact.cuh) flags an abscissa outside the grid, or a grid it cannot interpolate on
+static bool lin1d_clamps(const sart_interp1d_t& t, double x) {
+  if (t.n < 2 || !t.x || !t.y) return true;
+  return !(x >= t.x[0]) || !(x <= t.x[t.n - 1]);
+}
+
 static void lut_entry(double E, const sart_interp1d_t& sb, const sart_interp1d_t& wd, const sart_interp1d_t& ga,
-                      EnergyLUT* e, GasLUT* g) {
+                      double reflEMin, double reflEMax, EnergyLUT* e, GasLUT* g) {
   // A transmission that is non-zero in f64 must stay non-zero in the f32 table: `passed` means weight != 0
   // (rt:2220), and e.g. 200 um of Si transmit 1e-60 at 0.3 keV.
   auto f32nz = [](double v) { return (v != 0.0 && std::fabs(v) < 1.2e-38) ? float(std::copysign(1.2e-38, v)) : float(v); };
@@ -425,7 +431,12 @@ static void lut_entry(double E, const sart_interp1d_t& sb, const sart_interp1d_t
     } else {
       e->Tstrongback = float(t);
     }
-    e->sbExp = ex;
+    int cl = 0;
+    if (lin1d_clamps(wd, E)) cl |= kLutClampWindow;
+    if (lin1d_clamps(sb, E)) cl |= kLutClampStrongback;
+    if (lin1d_clamps(ga, E)) cl |= kLutClampGas;
+    if (!(E >= reflEMin) || !(E <= reflEMax)) cl |= kLutClampRefl;
+    e->sbExp = (ex & 0xffff) | (cl << 16);
   }
   e->Agas = f32nz(lin1d(ga, E));
   const double lma = -1.5832 + 5.9195 * std::exp(-0.353808 * E) + 4.03598 * std::exp(-0.970557 * E);
@@ -435,11 +446,12 @@ static void lut_entry(double E, const sart_interp1d_t& sb, const sart_interp1d_t
 
 // nEnergies records (E = max(0.03 keV, energies[i]), rt:470-471) + one for the X-ray test-source energy.
 void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
-                      const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out, std::vector<GasLUT>* gout) {
+                      const sart_interp1d_t& ga, double srcEnergy, double reflEMin, double reflEMax,
+                      std::vector<EnergyLUT>* out, std::vector<GasLUT>* gout) {
   out->resize(size_t(nE) + 1);
   gout->resize(size_t(nE) + 1);
   for (int i = 0; i <= nE; ++i)
-    lut_entry(i < nE ? std::max(0.03, energies[i]) : srcEnergy, sb, wd, ga, &(*out)[i], &(*gout)[i]);
+    lut_entry(i < nE ? std::max(0.03, energies[i]) : srcEnergy, sb, wd, ga, reflEMin, reflEMax, &(*out)[i], &(*gout)[i]);
 }
 
 // Reflectivity of one coating interpolated along the energy axis at energy E, for every angle node:

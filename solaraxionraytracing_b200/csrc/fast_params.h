@@ -130,10 +130,13 @@ constexpr int kShellCellFail = 64;
 
 struct EnergyLUT {  // one record per tabulated energy index (16 B, one LDG.128)
   // strongback transmission = Tstrongback * 2^sbExp: 200 um of silicon transmit 1e-60 at 0.9 keV, far below the FP32
-  // range, and a weight must keep its value there, not only its non-zeroness. sbExp = 0 wherever FP32 holds the value.
+  // range, and a weight must keep its value there, not only its non-zeroness. The exponent is the low 16 bits of sbExp
+  // (signed; 0 wherever FP32 holds the value); bits 16.. say which interpolations of the exact pipeline clamp at this
+  // energy (kLutClamp*: SART_FLAG_INTERP_CLAMPED of the rays that evaluate them). sbExp == 0 for an ordinary energy.
   int32_t sbExp;
   float Twindow, Tstrongback, Agas;
 };
+constexpr int kLutClampWindow = 1, kLutClampStrongback = 2, kLutClampGas = 4, kLutClampRefl = 8;
 struct GasLUT {     // buffer-gas stage only
   float massAtt;   // exp(logMassAttenuation(E)) am:70-73
   float inv2E;     // 1 / (2 E[eV])

@@ -457,6 +457,7 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
     if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
       const float* zt = T.reflE + (size_t(sh.coat & kCoatMask) * (P.nEnergies + 1) + eIdx) * P.nAngles;
       clamped |= (sh.coat & kCoatClamped) != 0;
+      clamped |= (el.sbExp & (kLutClampRefl << 16)) != 0;   // the ray's energy lies outside the reflectivity grid
       refl = double(refl_lookup(P, zt, a1, clamped)) * double(refl_lookup(P, zt, a2, clamped));
     }
     out.refl = refl;
@@ -489,10 +490,14 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
       sb = (u > 0.0 && fi < double(P.nStripHalf) && off > 0.0 && off < P.stripWidth) ? 1 : 0;
     }
     const float tw = sb == 1 ? el.Tstrongback : (sb == 0 ? el.Twindow : 0.f);
-    if (!(P.flags & SART_CF_IGNORE_DET_WINDOW)) {
-      post *= double(tw);
-      if (sb == 1 && el.sbExp != 0)
-        post = __hiloint2double(__double2hiint(post) + (el.sbExp << 20), __double2loint(post));
+    const bool ignoreWin = (P.flags & SART_CF_IGNORE_DET_WINDOW) != 0;
+    if (!ignoreWin) post *= double(tw);
+    if (el.sbExp != 0) {   // rare: an energy at which a Henke grid clamps, or soft X-rays on a strip (fast_params.h: EnergyLUT)
+      const int cl = el.sbExp >> 16;
+      out.clamped |= (cl & (sb == 1 ? kLutClampStrongback : (sb == 0 ? kLutClampWindow : 0)) | (cl & kLutClampGas)) != 0;
+      const int ex = (el.sbExp << 16) >> 16;
+      if (!ignoreWin && sb == 1 && ex != 0)
+        post = __hiloint2double(__double2hiint(post) + ex * (1 << 20), __double2loint(post));
     }
   }
   if (!(P.flags & SART_CF_IGNORE_GAS_ABS)) post *= double(el.Agas);

@@ -33,7 +33,8 @@ int classify_radius(const ShellF32* shells, int nShells, float rho);
 int shell_table_lookup(const Geo32& g, const std::vector<ShellCell>& tab, float rho);
 void build_shell_guide(const sart_setup_t& s, FastParams* f, std::vector<uint8_t>* guide);
 void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb, const sart_interp1d_t& wd,
-                      const sart_interp1d_t& ga, double srcEnergy, std::vector<EnergyLUT>* out,
+                      const sart_interp1d_t& ga, double srcEnergy, double reflEMin, double reflEMax,
+                      std::vector<EnergyLUT>* out,
                       std::vector<GasLUT>* gout);
 void refl_at_energy(const Params& P, const float* z, double E, float* out);
 }  // namespace fast
