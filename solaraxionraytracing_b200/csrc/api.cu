@@ -284,7 +284,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   // the throughput kernels address table rows with 32-bit element offsets
   if (size_t(std::max(nCoat, 1)) * reflPlane >= (size_t(1) << 31) ||
       size_t(std::max(P.nRadii, 1)) * thr_pitch(std::max(P.nEnergies, 1)) >= (size_t(1) << 31) ||
-      size_t(std::max(P.nRadii, 1)) * kEnGuide >= (size_t(1) << 31))
+      size_t(std::max(P.nRadii, 1)) * kEnGuide >= (size_t(1) << 31) ||
+      size_t(std::max(P.nRadii, 1)) * kEnCells >= (size_t(1) << 31))
     return fail(SART_ERR_CONFIG, "tables too large for the throughput pipelines (a table exceeds 2^31 elements)");
   unsigned char* base = static_cast<unsigned char*>(h->fast_blob);
   if (t) {
@@ -300,6 +301,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     const size_t egOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * kEnGuide * 2);
     const size_t rtOff = off; off += align256(size_t(thr_pitch(std::max(P.nRadii, 1))) * 4);
     const size_t etOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * thr_pitch(std::max(P.nEnergies, 1)) * 4);
+    const size_t rcOff = off; off += align256(size_t(kRadCells) * sizeof(fast::SampleCell));
+    const size_t ecOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * kEnCells * sizeof(fast::SampleCell));
     h->fast_refl_off = off; off += align256(size_t(std::max(nCoat, 1)) * reflPlane * sizeof(float));
     // alias tables of the same distributions (sart_set_sampler), when the packed 11-bit alias index can hold them
     const bool aliasFits = P.nRadii > 0 && t->fluxRadiusCDF && P.nRadii <= 2048 && P.nEnergies <= 2048;
@@ -323,6 +326,14 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
       SART_CUDA(cudaMemcpy(base + egOff, eg.data(), eg.size() * 2, cudaMemcpyHostToDevice));
       SART_CUDA(cudaMemcpy(base + rtOff, rth.data(), rth.size() * 4, cudaMemcpyHostToDevice));
       SART_CUDA(cudaMemcpy(base + etOff, eth.data(), eth.size() * 4, cudaMemcpyHostToDevice));
+      {
+        std::vector<fast::SampleCell> rc(kRadCells), ec(size_t(P.nRadii) * kEnCells);
+        fast::build_sample_cells(rth.data(), P.nRadii, kRadCellBits, rc.data());
+        for (int r = 0; r < P.nRadii; ++r)
+          fast::build_sample_cells(eth.data() + size_t(r) * ep, P.nEnergies, kEnCellBits, ec.data() + size_t(r) * kEnCells);
+        SART_CUDA(cudaMemcpy(base + rcOff, rc.data(), rc.size() * sizeof(fast::SampleCell), cudaMemcpyHostToDevice));
+        SART_CUDA(cudaMemcpy(base + ecOff, ec.data(), ec.size() * sizeof(fast::SampleCell), cudaMemcpyHostToDevice));
+      }
       if (aliasFits) {
         std::vector<uint32_t> ra(size_t(P.nRadii)), ea(size_t(P.nRadii) * P.nEnergies);
         bool ok = fast::build_alias_table(rth.data(), P.nRadii, ra.data());
@@ -355,6 +366,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     F.energyGuide = reinterpret_cast<const uint16_t*>(base + egOff);
     F.radiusThr = reinterpret_cast<const uint32_t*>(base + rtOff);
     F.energyThr = reinterpret_cast<const uint32_t*>(base + etOff);
+    F.radiusCells = reinterpret_cast<const fast::SampleCell*>(base + rcOff);
+    F.energyCells = reinterpret_cast<const fast::SampleCell*>(base + ecOff);
     F.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
     F.glut = reinterpret_cast<const fast::GasLUT*>(base + h->fast_glut_off);
     F.reflE = reinterpret_cast<const float*>(base + h->fast_refl_off);

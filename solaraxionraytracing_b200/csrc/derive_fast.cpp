@@ -454,6 +454,23 @@ void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb,
     lut_entry(i < nE ? std::max(0.03, energies[i]) : srcEnergy, sb, wd, ga, reflEMin, reflEMax, &(*out)[i], &(*gout)[i]);
 }
 
+// Sampling cells of one threshold row (fast_params.h: SampleCell); thr[0..n) non-decreasing.
+void build_sample_cells(const uint32_t* thr, int n, int bits, SampleCell* out) {
+  const int K = 1 << bits, shift = 32 - bits;
+  int pos = 0;   // thresholds below the current cell
+  for (int k = 0; k < K; ++k) {
+    const uint64_t end = (uint64_t(k) + 1) << shift;   // first word of the next cell
+    int q = pos;
+    while (q < n && uint64_t(thr[q]) < end) ++q;
+    int nIn = q - pos;
+    const uint32_t thr0 = nIn > 0 ? thr[pos] : 0xffffffffu;
+    // the all-ones word compares >= every threshold and >= the "none" marker: it must take the slow path (f64 fallback)
+    if (k == K - 1 && (nIn == 0 || thr[q - 1] == 0xffffffffu)) nIn = std::max(nIn, 2);
+    out[k] = SampleCell{thr0, uint32_t(pos) | uint32_t(std::min(nIn, 0xffff)) << 16};
+    pos = q;
+  }
+}
+
 // Reflectivity of one coating interpolated along the energy axis at energy E, for every angle node:
 // out[i] = z[i][j] + yc (z[i][j+1] - z[i][j]) with (j, yc) the energy cell of the bilinear spline (rt:1567-1578).
 void refl_at_energy(const Params& P, const float* z, double E, float* out) {

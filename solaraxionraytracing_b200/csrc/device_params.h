@@ -110,6 +110,22 @@ struct EnergyFactors {
 #endif
 constexpr int kRadGuideBits = SART_RAD_GUIDE_BITS, kRadGuide = 1 << kRadGuideBits;
 constexpr int kEnGuideBits = SART_EN_GUIDE_BITS, kEnGuide = 1 << kEnGuideBits;
+// Sampling cells of the single-precision pipeline (fast_params.h: SampleCell): the word's top bits pick a cell that holds
+// the answer for every word of the cell up to its first threshold; only a ray at or past the first threshold of a cell
+// with two or more thresholds searches (thr_search_tail). A cell covers 2^-bits of the probability, so the share of such
+// rays is below the share of such cells: 0.7 % (radius) and 0.9 % (energy) at 13 bits on the bench tables — per warp that
+// is one slow path in five launches of the search, which is what the size buys (measured on CAST+LLNL, 1e9 rays:
+// 12/11 bits 27.4 ms, 13/12 bits 26.4 ms, 13/13 bits 26.0 ms; the guide + 8 prefetched thresholds before: 28.2 ms).
+// Radius cells live in shared memory (64 KiB), energy cells in global memory (64 KiB per emission shell, 129 MB for
+// 1968 shells; a ray reads one 8-byte cell of it).
+#ifndef SART_RAD_CELL_BITS
+#define SART_RAD_CELL_BITS 13
+#endif
+#ifndef SART_EN_CELL_BITS
+#define SART_EN_CELL_BITS 13
+#endif
+constexpr int kRadCellBits = SART_RAD_CELL_BITS, kRadCells = 1 << kRadCellBits;
+constexpr int kEnCellBits = SART_EN_CELL_BITS, kEnCells = 1 << kEnCellBits;
 // Entries per row of a u32 threshold table: the row rounded up to 4 entries plus 8 saturated pad entries, so that two
 // 16-byte loads from any 4-aligned start inside the row stay inside the row's storage.
 #if defined(__CUDACC__)

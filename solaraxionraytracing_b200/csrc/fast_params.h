@@ -75,37 +75,45 @@ static_assert(sizeof(ShellF32) == 116, "29 words: an odd stride keeps shared-mem
 // "uncertain": it is handed to the exact FP64 pipeline (trace_exact.cuh) through the re-trace queue, so that the
 // classification of every ray is the exact pipeline's. All budgets carry the handle's retrace scale (sart_set_retrace;
 // 0 = pure FP32).
-struct Tol32 {
-  float latA, latS, latT;            // lateral position budget before the mirrors [mm], Monte Carlo rays:
+// Field order of Tol32 and Geo32: the order in which the plain fused kernel uses them, in 16-byte groups — constants come
+// from the kernel's parameter bank one LDC / LDCU per use, and neighbours that are used together load as one.
+struct alignas(16) Tol32 {
+  float latS, latT, latA;            // lateral position budget before the mirrors [mm], Monte Carlo rays:
                                      //   latA + latS rs + latT (|sx| + |sy|)   (rs = emission radius / solar radius)
+  float twoRcb;                      // 2 R of the squared-radius compares (bore; pipes and window below)
+  float circCB;                      // circ2 R^2 for the bore: |rho^2 - R^2| < 2 R lat + circ2 R^2
+  float entK;                        // budget of the bore entrance test (z = 0, intersected separately by the reference) / budget of the other planes
+  float rho;                         // + rounding of a radial distance at the telescope entrance
+  float discRel;                     // a negative discriminant above -discRel hb^2 may be a rounding artefact
+  float detS, detT, detA;            // the same as lat* at the detector plane
+  float zrel;                        // relative rounding of a root
+  float nick;                        // rounding part of the nickel test's budget: sinA lMirror + zrel (largest shell gap)
+  float angLo;                       // angleMax - ang: grazing angles from here on touch the end of the reflectivity grid
+  float twoRwin, circWin;            // detector window aperture
+  int32_t chipInside;                // the chip edge can cut inside the window aperture (else the aperture decides alone)
+  float twoRpipe, circPipe;          // pipes
+  float circ2;
   float latTpre, latRef;             // pre-sampled rays: latA + latTpre (|sx| + |sy|) + latRef epsO, epsO = the rounding
                                      //   noise of the reference's line through the caller's origin (kernels_f32.cu)
-  float entK;                        // budget of the bore entrance test (z = 0, intersected separately by the reference) / budget of the other planes
-  float detA, detS, detT, detTpre, detRef;   // the same at the detector plane
-  float rho;                         // + rounding of a radial distance at the telescope entrance
-  float circ2;                       // |rho^2 - R^2| < 2 R lat + circ2 R^2
-  float circCB, circPipe, circWin;   // circ2 R^2 for the bore, the pipes and the detector window
-  float angLo;                       // angleMax - ang: grazing angles from here on touch the end of the reflectivity grid
-  float nick;                        // rounding part of the nickel test's budget: sinA lMirror + zrel (largest shell gap)
+  float detTpre, detRef;
   float spider;                      // rounding of the Chebyshev spider polynomial (in units of cos(n phi))
   float cond;                        // the reference's quadratic formula loses hb^2 / |A C| digits (rt:646-658): dz |q| += cond hb^2 / |A|
-  float zrel;                        // relative rounding of a root
-  float discRel;                     // a negative discriminant above -discRel hb^2 may be a rounding artefact
   float ang;                         // grazing angle against the end of the reflectivity grid [deg]
   float sinA;                        // absolute rounding of sin(alpha)
-  float twoRcb, twoRpipe, twoRwin;   // 2 R of the squared-radius compares
-  int32_t chipInside;                // the chip edge can cut inside the window aperture (else the aperture decides alone)
 };
 
-struct Geo32 {
-  float radiusCB, radiusCB2, lengthB, lengthB2, lengthBplusSun, radiusSun;
-  float dzExitCB, dzPipe1, dzPipe2, rPipe12;
-  float cosTX, sinTX, cosTY, sinTY, halfLenTel, oeX, oeY, zExitCBtel;
-  float lMirror, cosPipe, sinPipe, dShift, lateralShift, transversalShift;
-  float radiusWindow2, chipCX, chipCY, cosTheta, sinTheta, stripDist, stripWidth, invStripPitch, invBinX, invBinY;
-  float shellRhoMin, shellInvStep;
+struct alignas(16) Geo32 {
+  float radiusSun, lengthBplusSun, radiusCB, radiusCB2;
+  float lengthB, dzExitCB, lengthB2, dzPipe2;
+  float oeX, oeY, shellRhoMin, shellInvStep;
+  float lMirror, zExitCBtel, cosPipe, sinPipe;
+  float dShift, depthOverCos, lateralShift, transversalShift;   // depthOverCos = ddEnd - ddWin = depthDet / cos(pipesTurned): the second detector plane of deviationDet (rt:2081-2085)
+  float radiusWindow2, chipCX, chipCY, cosTheta;
+  float sinTheta, stripDist, stripWidth, invStripPitch;
+  float invBinX, invBinY, dzPipe1, rPipe12;
+  float cosTX, sinTX, cosTY, sinTY, halfLenTel;
   float srcX, srcY, srcRadius, srcRadius2, invSrcDz, colDz;
-  float depthOverCos;   // ddEnd - ddWin = depthDet / cos(pipesTurned): the second detector plane of deviationDet (rt:2081-2085)
+  float pad_;
   Tol32 tol;
 };
 
@@ -142,6 +150,13 @@ struct GasLUT {     // buffer-gas stage only
   float inv2E;     // 1 / (2 E[eV])
 };
 
+// One cell of a sampling table (mode 2): the words w with w >> (32 - bits) == k. base = number of thresholds below the
+// cell (the answer for words below the cell's first threshold thr0; 0xffffffff when the cell holds none), n = number of
+// thresholds inside it. Answer = base + (w >= thr0) when n < 2; otherwise the thresholds base + 1 .. base + n - 1 are
+// searched (thr_search_tail). The last cell is given n >= 2 when it holds a saturated threshold, so that the all-ones word
+// always reaches the slow path and its f64 fallback. Indices are 16-bit (sart_create checks nRadii, nEnergies < 65536).
+struct alignas(8) SampleCell { uint32_t thr0; uint32_t baseN; };   // baseN = base | min(n, 0xffff) << 16
+
 struct FastTables {
   // Inverse-CDF sampling (rt:437, 464) in integers: with u = (w + 0.5) 2^-32, cdf[i] < u  <=>  w >= thr[i], where
   // thr[i] is the smallest such 32-bit word (saturated at 0xffffffff; that word falls back to the f64 tables).
@@ -151,6 +166,8 @@ struct FastTables {
   const double* energyCDF;       // [nRadii][nEnergies] f64, fallback only
   const uint32_t* energyThr;     // [nRadii][thr_pitch(nEnergies)]
   const uint16_t* energyGuide;   // [nRadii][kEnGuide]
+  const SampleCell* radiusCells; // [kRadCells]          (mode 2; modes 0 / 1 use the guides above)
+  const SampleCell* energyCells; // [nRadii][kEnCells]
   const double* energies;        // [nEnergies] keV (pre-sampled rays: energy -> index)
   const EnergyLUT* elut;         // [nEnergies + 1]
   const GasLUT* glut;            // [nEnergies + 1]

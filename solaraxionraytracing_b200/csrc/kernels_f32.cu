@@ -55,8 +55,7 @@ k_trace_mc_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo
     Rec32 rec;
     rec.id = id;
     const int code = stage_a32<kWolter, false, kPlain, false, kAlias, kMargins>(P, G, T, S, hd, rec);
-    if (code >= 0) { if (!(kMargins && rec.unc && sink.defer(rec.id))) sink.fail(code); }
-    else stage_b32<kWolter, kPlain, false, kMargins>(P, G, T, S, rec, sink);
+    finish32<kWolter, kPlain, false, kMargins>(P, G, T, S, code, rec, sink);
   }
   for (int o = 16; o > 0; o >>= 1) {
     nPassed += __shfl_down_sync(0xffffffffu, nPassed, o);
@@ -145,7 +144,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
       rec.id = Q.id[pos];
       rec.bud = solar ? (0.0015f + float(rec.eIdx) * 0.0005f) : 1.0f;   // rs of the emission shell (rec.eIdx still holds it)
       if (solar) rec.eIdx = energy_index<kAlias>(P, T, rec.eIdx, Q.we[pos], rec.clamped);
-      stage_b32<kWolter, kPlain, false, kMargins>(P, G, T, S, rec, sink);
+      finish32<kWolter, kPlain, false, kMargins>(P, G, T, S, -1, rec, sink);
     }
     qn -= take;
     __syncwarp();
@@ -187,14 +186,14 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
     Rec32 rec;
     rec.id = id;
     const int c0 = stage_a32<kWolter, false, false, false, false, kMargins>(P, G, T, S, hd, rec);
-    if (c0 >= 0) { if (!(kMargins && rec.unc && sink.defer(rec.id))) sink.fail(c0); }
-    else stage_b32<kWolter, false, false, kMargins>(P, G, T, S, rec, sink);
+    finish32<kWolter, false, false, kMargins>(P, G, T, S, c0, rec, sink);
     return sink.unresolved;
   });
 }
 
 }  // namespace fast
 
+#ifndef SART_NO_LAUNCHERS   // tools/micro/one_kernel.cu instantiates single kernels of this file for SASS inspection
 cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
                                 uint64_t first, uint64_t nRays, uint64_t seed, double* image, double* imageW2,
                                 sart_counters_t* counters, int smCount, bool compact, cudaStream_t s) {
@@ -260,5 +259,7 @@ cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Ge
   kern<<<grid, fast::kBlockM, smem, s>>>(P, G, T, dMasses, nMasses, first, nRays, philox_round_keys(seed), acc, accW2, counters);
   return cudaGetLastError();
 }
+
+#endif  // SART_NO_LAUNCHERS
 
 }  // namespace sart

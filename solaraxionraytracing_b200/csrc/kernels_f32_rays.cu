@@ -41,8 +41,7 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
     const int c0 = stage_a32<kWolter, false, kPlain, kLate, kAlias>(P, G, T, S, hd, rec);
     const bool solar = kPlain || !P.testXray;
     if (kLate && c0 < 0 && solar) rec.eIdx = energy_index<kAlias>(P, T, rec.rIdx, rec.we, rec.clamped);
-    if (c0 >= 0) { if (rec.unc) sink.defer(rec.id); sink.fail(c0); }
-    else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
+    finish32<kWolter, kPlain>(P, G, T, S, c0, rec, sink);
     // energiesPre is set for every ray (rt:1818-1819), clipped or not: rays that end in stage A resolve their energy here
     double energy = double(P.srcEnergy);
     if (solar) {
@@ -110,8 +109,7 @@ k_trace_mc_passed_f32(const __grid_constant__ FastParams P, const __grid_constan
       Rec32 rec;
       rec.id = uint32_t(i);
       const int c0 = stage_a32<kWolter, false, kPlain>(P, G, T, S, hd, rec);
-      if (c0 >= 0) { if (!(rec.unc && sink.defer(rec.id))) sink.fail(c0); }
-      else stage_b32<kWolter, kPlain>(P, G, T, S, rec, sink);
+      finish32<kWolter, kPlain>(P, G, T, S, c0, rec, sink);
       if (have) {   // reached the weight stage: the tail of traceAxion (rt:2135-2221)
         const int code = finish_ray<true>(P, r, mAxion2, wd);
         if (code & SART_FLAG_PASSED_TILL_WINDOW) ++nTill;
@@ -210,8 +208,7 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
     Rec32 rec;
     rec.id = uint32_t(i);
     const int c0 = stage_a32<kWolter, true, kPlain, false, false, kMargins>(P, G, T, S, hd, rec);
-    if (c0 >= 0) { if (kMargins && rec.unc) sink.defer(rec.id); sink.fail(c0); }
-    else stage_b32<kWolter, kPlain, true, kMargins>(P, G, T, S, rec, sink);
+    finish32<kWolter, kPlain, true, kMargins>(P, G, T, S, c0, rec, sink);
     store_record(P, o, i, r, mAxion2, Ec);
   }
 }

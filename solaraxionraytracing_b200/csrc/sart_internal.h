@@ -37,6 +37,7 @@ void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb,
                       std::vector<EnergyLUT>* out,
                       std::vector<GasLUT>* gout);
 void refl_at_energy(const Params& P, const float* z, double E, float* out);
+void build_sample_cells(const uint32_t* thr, int n, int bits, SampleCell* out /* [1 << bits] */);
 }  // namespace fast
 
 }  // namespace sart
