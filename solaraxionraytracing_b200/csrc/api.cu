@@ -234,8 +234,9 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   const Params& P = h->params;
   if (t) {   // host copies for later LUT rebuilds, kept whether or not this setup can use the throughput pipelines
     h->h_energies.assign(t->energies ? t->energies : nullptr, t->energies ? t->energies + t->nEnergies : nullptr);
-    const sart_interp1d_t* I[3] = {&t->strongbackTransmission, &t->windowTransmission, &t->gasAbsorption};
-    for (int k = 0; k < 3; ++k) {
+    const sart_interp1d_t* I[4] = {&t->strongbackTransmission, &t->windowTransmission, &t->gasAbsorption, &t->telescopeTransmission};
+    for (int k = 0; k < 4; ++k) {
+      if (I[k]->n < 1 || !I[k]->x || !I[k]->y) { h->h_tab[k][0].clear(); h->h_tab[k][1].clear(); continue; }
       h->h_tab[k][0].assign(I[k]->x, I[k]->x + I[k]->n);
       h->h_tab[k][1].assign(I[k]->y, I[k]->y + I[k]->n);
     }
@@ -256,8 +257,8 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     h->fast_why = "the handle was created with a setup the throughput pipelines do not support; create a new handle for this setup";
     return SART_OK;
   }
-  sart_interp1d_t I[3];
-  for (int k = 0; k < 3; ++k) I[k] = sart_interp1d_t{int32_t(h->h_tab[k][0].size()), 0, h->h_tab[k][0].data(), h->h_tab[k][1].data()};
+  sart_interp1d_t I[4];
+  for (int k = 0; k < 4; ++k) I[k] = sart_interp1d_t{int32_t(h->h_tab[k][0].size()), 0, h->h_tab[k][0].data(), h->h_tab[k][1].data()};
   fast::derive_params(h->setup, P, &h->fparams);
   if (h->h_energies.size() > 1) {
     h->fparams.enE0 = h->h_energies.front();
@@ -278,7 +279,14 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   const int nE = int(h->h_energies.size());
   std::vector<fast::EnergyLUT> lut;
   std::vector<fast::GasLUT> glut;
-  fast::build_energy_lut(nE, h->h_energies.data(), I[0], I[1], I[2], h->setup.testSource.energy, P.reflEMin, P.reflEMax, &lut, &glut);
+  // the "reflectivity grid" whose ends set the clamped flag of an energy: the reflectivity table's energy axis, or the
+  // abscissae of the telescope transmission for rkEffectiveArea (trace_exact.cuh: ray_weights)
+  const bool effArea = P.reflKind == SART_RK_EFFECTIVE_AREA;
+  const double rEMin = effArea ? (I[3].n >= 2 ? I[3].x[0] : INFINITY) : P.reflEMin;
+  const double rEMax = effArea ? (I[3].n >= 2 ? I[3].x[I[3].n - 1] : -INFINITY) : P.reflEMax;
+  fast::build_energy_lut(nE, h->h_energies.data(), I[0], I[1], I[2], h->setup.testSource.energy, rEMin, rEMax, &lut, &glut);
+  std::vector<float> telTrans;
+  fast::build_tel_trans(nE, h->h_energies.data(), I[3], h->setup.testSource.energy, &telTrans);
   const int nCoat = P.nAngles > 0 && !h->h_refl32.empty() ? int(h->h_refl32.size() / (size_t(P.nAngles) * P.nReflEnergies)) : 0;
   const size_t reflRow = size_t(P.nAngles), reflPlane = reflRow * (size_t(nE) + 1);
   // the throughput kernels address table rows with 32-bit element offsets
@@ -297,6 +305,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     h->fast_stab_off = off; off += 4096 * sizeof(fast::ShellCell);
     h->fast_lut_off = off; off += align256(lut.size() * sizeof(fast::EnergyLUT));
     h->fast_glut_off = off; off += align256(glut.size() * sizeof(fast::GasLUT));
+    h->fast_tt_off = off; off += align256(telTrans.size() * sizeof(float));
     const size_t rgOff = off; off += align256(size_t(kRadGuide) * 2);
     const size_t egOff = off; off += align256(size_t(std::max(P.nRadii, 1)) * kEnGuide * 2);
     const size_t rtOff = off; off += align256(size_t(thr_pitch(std::max(P.nRadii, 1))) * 4);
@@ -371,6 +380,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
     F.elut = reinterpret_cast<const fast::EnergyLUT*>(base + h->fast_lut_off);
     F.glut = reinterpret_cast<const fast::GasLUT*>(base + h->fast_glut_off);
     F.reflE = reinterpret_cast<const float*>(base + h->fast_refl_off);
+    F.telTrans = reinterpret_cast<const float*>(base + h->fast_tt_off);
     F.shells = reinterpret_cast<const fast::ShellFast*>(base + h->fast_shell_off);
     F.shells32 = reinterpret_cast<const fast::ShellF32*>(base + h->fast_shell32_off);
     F.shellGuide = reinterpret_cast<const uint8_t*>(base + h->fast_sguide_off);
@@ -396,6 +406,7 @@ static int upload_fast(sart_handle* h, const sart_tables_t* t) {
   SART_CUDA(cudaMemcpy(base + h->fast_shell32_off, sh32.data(), sh32.size() * sizeof(fast::ShellF32), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_lut_off, lut.data(), lut.size() * sizeof(fast::EnergyLUT), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_glut_off, glut.data(), glut.size() * sizeof(fast::GasLUT), cudaMemcpyHostToDevice));
+  SART_CUDA(cudaMemcpy(base + h->fast_tt_off, telTrans.data(), telTrans.size() * sizeof(float), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_sguide_off, sguide.data(), sguide.size(), cudaMemcpyHostToDevice));
   SART_CUDA(cudaMemcpy(base + h->fast_stab_off, stab.data(), stab.size() * sizeof(fast::ShellCell), cudaMemcpyHostToDevice));
   return SART_OK;

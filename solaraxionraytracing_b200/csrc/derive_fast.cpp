@@ -36,12 +36,8 @@ static double he_density(double p, double temp) {  // axionMassforMagnet.nim:4-1
 
 bool supported(const sart_setup_t& s, const char** why) {
   const sart_telescope_t& t = s.telescope;
-  if (t.reflKind == SART_RK_EFFECTIVE_AREA && !(s.flags & SART_CF_IGNORE_REFLECTION)) {
-    *why = "effective-area reflectivity (rkEffectiveArea) is only implemented in the exact pipeline";
-    return false;
-  }
-  if (t.kind == SART_TK_XMM && t.holeType != SART_HT_NONE) {
-    *why = "XMM with a hole in the optics is only implemented in the exact pipeline";
+  if (t.kind == SART_TK_XMM && t.holeType != SART_HT_NONE && (t.numberOfHoles < 1 || t.numberOfHoles > 64)) {
+    *why = "XMM hole pattern: the throughput pipelines take 1 to 64 holes";
     return false;
   }
   for (int j = 1; j < t.nShells; ++j)
@@ -165,6 +161,7 @@ void derive_f32(const FastParams& f, const ShellFast* a, int nShells, Geo32* g, 
   g->invBinY = float(f.invBinY); g->shellRhoMin = float(f.shellRhoMin); g->shellInvStep = float(f.shellInvStep);
   g->srcX = float(f.srcX); g->srcY = float(f.srcY); g->srcRadius = float(f.srcRadius); g->srcRadius2 = float(f.srcRadius2);
   g->invSrcDz = float(1.0 / (f.lengthB - f.srcZ)); g->colDz = float(f.colDz);
+  g->holeR = float(f.holeInOptics);
   for (int j = 0; j < nShells; ++j) {
     const ShellFast& s = a[j];
     ShellF32& o = out[j];
@@ -400,6 +397,9 @@ void derive_params(const sart_setup_t& s, const Params& P, FastParams* f) {
   f->shellsMonotonic = 1;
   f->rotated = (P.sinTX != 0.0 || P.sinTY != 0.0) ? 1 : 0;
   f->srcEIdx = P.nEnergies;  // the record after the tabulated energies holds the X-ray source energy
+  f->holeType = P.telKind == SART_TK_XMM ? P.holeType : SART_HT_NONE;
+  f->numberOfHoles = P.numberOfHoles;
+  f->holeInOptics = P.holeInOptics;
   {
     // largest slope of a ray from the outermost tabulated solar shell through the field-exit disc, and the largest radius
     // it can have at the second pipe plane if it passed the bore exit; 1 mm is far above every error budget
@@ -452,6 +452,12 @@ void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb,
   gout->resize(size_t(nE) + 1);
   for (int i = 0; i <= nE; ++i)
     lut_entry(i < nE ? std::max(0.03, energies[i]) : srcEnergy, sb, wd, ga, reflEMin, reflEMax, &(*out)[i], &(*gout)[i]);
+}
+
+// rkEffectiveArea: the telescope transmission (eval_linear1d of trace_exact.cuh, rt:1560) at the energies of the LUT.
+void build_tel_trans(int nE, const double* energies, const sart_interp1d_t& tt, double srcEnergy, std::vector<float>* out) {
+  out->resize(size_t(nE) + 1);
+  for (int i = 0; i <= nE; ++i) (*out)[i] = float(lin1d(tt, i < nE ? std::max(0.03, energies[i]) : srcEnergy));
 }
 
 // Sampling cells of one threshold row (fast_params.h: SampleCell); thr[0..n) non-decreasing.

@@ -66,6 +66,68 @@ __device__ __forceinline__ float atan_small(float x) {
 
 struct D3 { double x, y, z; };
 
+// rkEffectiveArea (rt:1553-1562): the two angle polynomials of the LLNL effective-area parametrisation, pitch and yaw in
+// degrees; the ray's "reflectivity" is their product times the telescope transmission at its energy (FastTables::telTrans).
+__device__ __forceinline__ float eff_area_angles(float p, float y) {
+  const float tp = fmaf(p, fmaf(p, fmaf(p, fmaf(p, 0.0008f, 1e-04f), -0.4489f), -0.3116f), 96.787f) * 0.01f;
+  const float ty = fmaf(y, fmaf(y, fmaf(y, fmaf(y, fmaf(y, fmaf(y, 6.0e-7f, -1.0e-5f), -0.0001f), 0.0034f), -0.0292f), -0.1534f), 99.959f) * 0.01f;
+  return tp * ty;
+}
+
+// XMM's central blocker with a hole pattern (rt:1674-1688; lineIntersectsObject rt:494-527): does the point (x, y) of the
+// telescope entrance plane lie inside one of the nHoles holes of half size R? Hole l = -half .. half sits at
+// (2 (l + sign l) R, 0) for odd l and at (0, 2 l R) for even l. `edge` returns the distance [mm] of the point to the
+// nearest edge line (or circle) of any hole — conservative for the margin test: also edges that do not bound the shape
+// there count. Distances along the diagonal axes of the star / diamond are scaled by 1 / sqrt 2, the factor by which a
+// displacement of the point can grow in those coordinates.
+template <class F>
+__device__ __forceinline__ bool in_hole(int holeType, int nHoles, F R, F x, F y, F& edge) {
+  const int half = nHoles / 2;   // nHoles - ceil(nHoles / 2)
+  const F k = F(0.7071067811865476);
+  bool any = false;
+  edge = F(1e30);
+  auto near = [&](F a, F bound, F scale) { const F d = fabs(fabs(a) - bound) * scale; edge = d < edge ? d : edge; };
+  for (int l = -half; l <= half; ++l) {
+    F cx = F(0), cy = F(0);
+    if (l != 0) {
+      if ((abs(l) & 1) == 0) cy = F(2 * l) * R;
+      else cx = F(2 * (l + (l > 0 ? 1 : -1))) * R;
+    }
+    const F ix = x - cx, iy = y - cy;
+    const F tx = (ix - iy) * k, ty = (ix + iy) * k;
+    const F ax = fabs(ix), ay = fabs(iy), atx = fabs(tx), aty = fabs(ty);
+    const F R16 = R * F(16);
+    bool in = false;
+    switch (holeType) {
+      case SART_HT_CIRCLE: {
+        const F r = sqrt(ix * ix + iy * iy);
+        in = r < R;
+        near(r, R, F(1));
+        break;
+      }
+      case SART_HT_STAR:
+        in = (atx < R && aty < R16) || (aty < R && atx < R16);
+        near(tx, R, k); near(ty, R, k); near(tx, R16, k); near(ty, R16, k);
+        // fall through: the star is the cross plus the same cross turned by 45 degrees
+      case SART_HT_CROSS:
+        in = in || (ax < R && ay < R16) || (ay < R && ax < R16);
+        near(ix, R, F(1)); near(iy, R, F(1)); near(ix, R16, F(1)); near(iy, R16, F(1));
+        break;
+      case SART_HT_SQUARE:
+        in = ax < R && ay < R;
+        near(ix, R, F(1)); near(iy, R, F(1));
+        break;
+      case SART_HT_DIAMOND:
+        in = atx < R && aty < R;
+        near(tx, R, k); near(ty, R, k);
+        break;
+      default: break;
+    }
+    any = any || in;
+  }
+  return any;
+}
+
 __device__ __forceinline__ void rad_add(const RadialHist& h, double r, double w) {
   int b = int(r * h.invStep);
   b = b < 0 ? 0 : (b > h.nbins - 1 ? h.nbins - 1 : b);

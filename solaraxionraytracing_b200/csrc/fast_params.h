@@ -50,6 +50,9 @@ struct FastParams {
   int32_t nRadii, nEnergies, nAngles, nReflEnergies, shellsMonotonic, srcEIdx;
   int32_t nShellGuide, rotated;
   int32_t pipesFree, padP_;   // solar Monte Carlo rays cannot reach the pipe walls (kernels_f32.cu, stage A)
+  // XMM's central blocker with holes (rt:1674-1688): hole shape, number of holes and half size [mm]
+  int32_t holeType, numberOfHoles;
+  double holeInOptics;
 };
 
 // ---- single-precision pipeline (kernels_f32.cu): the same blocks rounded to FP32, plus a few derived values that
@@ -113,7 +116,7 @@ struct alignas(16) Geo32 {
   float invBinX, invBinY, dzPipe1, rPipe12;
   float cosTX, sinTX, cosTY, sinTY, halfLenTel;
   float srcX, srcY, srcRadius, srcRadius2, invSrcDz, colDz;
-  float pad_;
+  float holeR;   // holeInOptics
   Tol32 tol;
 };
 
@@ -174,6 +177,9 @@ struct FastTables {
   // reflectivity pre-interpolated along the energy axis at every tabulated energy: [coat][nEnergies + 1][nAngles];
   // the per-ray lookup is then linear in the grazing angle only (same value as the bilinear form of rt:1567-1578)
   const float* reflE;
+  // rkEffectiveArea (rt:1553-1562): the telescope transmission at every tabulated energy, [nEnergies + 1]; the ray's
+  // "reflectivity" is this value times two polynomials in its pitch and yaw angles
+  const float* telTrans;
   const ShellFast* shells;    // [nShells]
   const ShellF32* shells32;   // [nShells] the same records in single precision (kernels_f32.cu)
   const uint8_t* shellGuide;  // [nShellGuide]: smallest j with R1[j] > lower edge of the radial bucket

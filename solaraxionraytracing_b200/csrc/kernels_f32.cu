@@ -16,6 +16,10 @@
 
 #include "trace_f32.cuh"
 
+#ifndef SART_F32_PAIR_DEFAULT
+#define SART_F32_PAIR_DEFAULT 0
+#endif
+
 namespace sart {
 namespace fast {
 
@@ -194,6 +198,17 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
 }  // namespace fast
 
 #ifndef SART_NO_LAUNCHERS   // tools/micro/one_kernel.cu instantiates single kernels of this file for SASS inspection
+cudaError_t launch_mc_image_f32x2(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion2,
+                                  uint64_t first, uint64_t n, const PhiloxKeys& keys, double* image, double* imageW2,
+                                  sart_counters_t* counters, int smCount, bool margins, cudaStream_t s);   // kernels_f32x2.cu
+
+// Two rays per thread (kernels_f32x2.cu) for the plain run of a cone telescope without compaction. SART_F32_PAIR=0 / 1 in the
+// environment overrides the default for A/B measurements and for the test that compares the two kernels ray set by ray set.
+static bool pair_kernel_wanted() {
+  const char* e = getenv("SART_F32_PAIR");
+  return e ? (e[0] != '0') : (SART_F32_PAIR_DEFAULT != 0);
+}
+
 cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G, const fast::FastTables& T, double mAxion,
                                 uint64_t first, uint64_t nRays, uint64_t seed, double* image, double* imageW2,
                                 sart_counters_t* counters, int smCount, bool compact, cudaStream_t s) {
@@ -202,7 +217,7 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   // alias sampler: solar source only (the X-ray test source draws no table values)
   const bool alias = T.sampler == SART_SAMPLER_ALIAS && !P.testXray && T.radiusAlias && T.energyAlias;
   const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias) + (compact ? fast::kWarps32 * sizeof(fast::WarpQueue32) : 0);
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && !T.rad.w;
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && P.reflKind != SART_RK_EFFECTIVE_AREA && !T.rad.w;
   using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, double*, double*,
                         sart_counters_t*);
   // [compact][wolter][plain][variant]; variant 0: inverse-CDF sampler, pure FP32; 1: inverse-CDF sampler with the margin tests
@@ -227,8 +242,14 @@ cudaError_t launch_mc_image_f32(const fast::FastParams& P, const fast::Geo32& G,
   if (perSM < 1) perSM = 1;
   const uint64_t cap = uint64_t(smCount) * perSM;
   const PhiloxKeys keys = philox_round_keys(seed);
+  const bool pairs = plain && !wolter && !compact && !alias && pair_kernel_wanted();
   for (uint64_t done = 0; done < nRays; done += fast::kMaxRaysPerLaunch) {   // one launch for anything below 6.9e10 rays
     const uint64_t n = nRays - done < fast::kMaxRaysPerLaunch ? nRays - done : fast::kMaxRaysPerLaunch;
+    if (pairs) {
+      e = launch_mc_image_f32x2(P, G, T, mAxion * mAxion, first + done, n, keys, image, imageW2, counters, smCount, margins, s);
+      if (e != cudaSuccess) return e;
+      continue;
+    }
     const uint64_t want = (n + fast::kBlock32 - 1) / fast::kBlock32;
     const unsigned grid = unsigned(want < cap ? want : cap);
     kern<<<grid, fast::kBlock32, smem, s>>>(P, G, T, mAxion * mAxion, first + done, n, keys, image, imageW2, counters);

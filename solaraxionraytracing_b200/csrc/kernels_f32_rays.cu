@@ -222,7 +222,7 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P);
   // the plain-run variant (run-wide switches as compile-time constants, see k_trace_mc_f32); pre-sampled rays have no source
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && P.reflKind != SART_RK_EFFECTIVE_AREA;
   using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, size_t, const double*, const double*, const double*,
                         sart_ray_out_t);
   static const Kern table[2][2][2] = {   // [wolter][plain][margins]
@@ -250,7 +250,7 @@ cudaError_t launch_mc_passed_f32(const fast::FastParams& P, const fast::Geo32& G
   if (nRays == 0) return cudaSuccess;
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P);
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && P.reflKind != SART_RK_EFFECTIVE_AREA;
   auto kern = wolter ? (plain ? fast::k_trace_mc_passed_f32<true, true> : fast::k_trace_mc_passed_f32<true, false>)
                      : (plain ? fast::k_trace_mc_passed_f32<false, true> : fast::k_trace_mc_passed_f32<false, false>);
   cudaError_t e = fast::set_smem(kern, smem);
@@ -268,7 +268,7 @@ cudaError_t launch_mc_rays_f32(const fast::FastParams& P, const fast::Geo32& G, 
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const bool alias = T.sampler == SART_SAMPLER_ALIAS && !P.testXray && T.radiusAlias && T.energyAlias;
   const size_t smem = fast::smem_bytes32(P, fast::kWarps32, alias);
-  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0;
+  const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && P.reflKind != SART_RK_EFFECTIVE_AREA;
   using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, uint64_t, uint64_t, PhiloxKeys, const uint32_t*,
                         int32_t*, sart_ray_out_t);
   static const Kern table[2][2][2] = {   // [wolter][plain][alias]

@@ -255,7 +255,13 @@ __device__ __forceinline__ int stage_a(const FastParams& P, const FastTables& T,
     const float xs = float(fma(double(zs), tx, x0)), ys = float(fma(double(zs), ty, y0));
     const float phiS = acosf(xs * rsqrtf(xs * xs + ys * ys)) * 57.29577951308232f;
     if (xmm) {
-      if (radialDist <= 64.7) hit = true;  // htNone hole: always opaque (rt:1674-1688)
+      if (radialDist <= 64.7) {
+        hit = true;   // htNone: the centre is opaque; other hole types open a pattern of holes in it (rt:1674-1688)
+        if (P.holeType != SART_HT_NONE) {
+          double edge;
+          hit = !in_hole(P.holeType, P.numberOfHoles, P.holeInOptics, x0, y0, edge);
+        }
+      }
       else if (radialDist < 151.6 && radialDist > (151.6 - 20.9)) hit = true;
       else {
         // |phi - 22.5 k| <= 1.145 for some k in 0..16 (phi in [0, 180])
@@ -454,7 +460,14 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
     double refl = 1.0;   // the product of two FP32 reflectivities can leave the FP32 range
     const float a1 = asin_small(float(sinA1)) * 57.29577951308232f, a2 = asin_small(float(sinA2)) * 57.29577951308232f;
     out.a1 = a1; out.a2 = a2;
-    if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
+    if (P.reflKind == SART_RK_EFFECTIVE_AREA) {
+      if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {   // rt:1553-1562; pitch = acos(-v.x) - 90 deg = asin(v.x) of the incoming ray
+        const float sp = float(tx * invLen);
+        const float pitch = (fabsf(sp) > 0.1f ? asinf(sp) : asin_small(sp)) * 57.29577951308232f;
+        clamped |= (el.sbExp & (kLutClampRefl << 16)) != 0;   // the ray's energy lies outside the transmission table
+        refl = double(__ldg(T.telTrans + eIdx)) * double(eff_area_angles(pitch, ya));
+      }
+    } else if (!(P.flags & SART_CF_IGNORE_REFLECTION)) {
       const float* zt = T.reflE + (size_t(sh.coat & kCoatMask) * (P.nEnergies + 1) + eIdx) * P.nAngles;
       clamped |= (sh.coat & kCoatClamped) != 0;
       clamped |= (el.sbExp & (kLutClampRefl << 16)) != 0;   // the ray's energy lies outside the reflectivity grid

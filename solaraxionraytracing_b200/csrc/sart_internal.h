@@ -37,6 +37,7 @@ void build_energy_lut(int nE, const double* energies, const sart_interp1d_t& sb,
                       std::vector<EnergyLUT>* out,
                       std::vector<GasLUT>* gout);
 void refl_at_energy(const Params& P, const float* z, double E, float* out);
+void build_tel_trans(int nE, const double* energies, const sart_interp1d_t& tt, double srcEnergy, std::vector<float>* out);
 void build_sample_cells(const uint32_t* thr, int n, int bits, SampleCell* out /* [1 << bits] */);
 }  // namespace fast
 
@@ -73,9 +74,9 @@ struct sart_handle {
   sart::fast::FastTables ftables;
   sart::fast::Geo32 geo32;      // single-precision geometry block of precision mode 2
   void* fast_blob = nullptr;
-  size_t fast_shell_off = 0, fast_shell32_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_sguide_off = 0, fast_stab_off = 0, fast_refl_off = 0;
+  size_t fast_shell_off = 0, fast_shell32_off = 0, fast_lut_off = 0, fast_glut_off = 0, fast_tt_off = 0, fast_sguide_off = 0, fast_stab_off = 0, fast_refl_off = 0;
   std::vector<float> h_refl32;  // host copy of the reflectivity (f32) for rebuilding the X-ray-source row
-  std::vector<double> h_energies, h_tab[3][2];  // host copies (energies; strongback/window/gas x,y) for LUT rebuilds
+  std::vector<double> h_energies, h_tab[4][2];  // host copies (energies; strongback/window/gas/telescope transmission x,y) for LUT rebuilds
   int sm_count = 148;
   size_t shell_offset = 0;      // byte offset of the ShellF64 array inside table_blob
   int n_masses = 1;

@@ -135,9 +135,11 @@ def test_image_statistically_equal_to_oracle(rt, oracle, precision):
 
 
 def test_fast_rejects_unsupported(rt):
-    setup, tb = make_config("cast_llnl")
-    setup.telescope.reflKind = abi.RK_EFFECTIVE_AREA
-    tb.telescopeTransmission = (np.array([0.0, 15.0]), np.array([0.5, 0.5]))
+    """What the throughput pipelines still refuse (derive_fast.cpp: supported): a hole pattern of more than 64 holes. The
+    exact pipeline takes it. (Effective-area reflectivity and XMM hole patterns are covered by all pipelines since round 2:
+    test_gpu_hole_effarea.py.)"""
+    setup, tb = make_config("babyiaxo_xmm")
+    setup.telescope.holeType, setup.telescope.numberOfHoles, setup.telescope.holeInOptics = abi.HT_CIRCLE, 65, 0.5
     with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
         with pytest.raises(rt.SartError):
             tr.set_precision(1)
