@@ -81,14 +81,16 @@ static_assert(sizeof(ShellF32) == 116, "29 words: an odd stride keeps shared-mem
 // Field order of Tol32 and Geo32: the order in which the plain fused kernel uses them, in 16-byte groups — constants come
 // from the kernel's parameter bank one LDC / LDCU per use, and neighbours that are used together load as one.
 struct alignas(16) Tol32 {
-  float latS, latT, latA;            // lateral position budget before the mirrors [mm], Monte Carlo rays:
-                                     //   latA + latS rs + latT (|sx| + |sy|)   (rs = emission radius / solar radius)
+  // lateral position budget before the mirrors [mm], Monte Carlo rays: latA + latS rs + latT (|sx| + |sy|)   (rs = emission
+  // radius / solar radius), and the same at the detector plane (det*); lat / det neighbours load as one 64-bit constant
+  // and go through one packed multiply-add (trace_f32.cuh: ray_budget2)
+  float latS, detS, latT, detT;
+  float latA, detA;
   float twoRcb;                      // 2 R of the squared-radius compares (bore; pipes and window below)
   float circCB;                      // circ2 R^2 for the bore: |rho^2 - R^2| < 2 R lat + circ2 R^2
   float entK;                        // budget of the bore entrance test (z = 0, intersected separately by the reference) / budget of the other planes
   float rho;                         // + rounding of a radial distance at the telescope entrance
   float discRel;                     // a negative discriminant above -discRel hb^2 may be a rounding artefact
-  float detS, detT, detA;            // the same as lat* at the detector plane
   float zrel;                        // relative rounding of a root
   float nick;                        // rounding part of the nickel test's budget: sinA lMirror + zrel (largest shell gap)
   float angLo;                       // angleMax - ang: grazing angles from here on touch the end of the reflectivity grid
@@ -96,9 +98,9 @@ struct alignas(16) Tol32 {
   int32_t chipInside;                // the chip edge can cut inside the window aperture (else the aperture decides alone)
   float twoRpipe, circPipe;          // pipes
   float circ2;
-  float latTpre, latRef;             // pre-sampled rays: latA + latTpre (|sx| + |sy|) + latRef epsO, epsO = the rounding
+  float latTpre, detTpre;            // pre-sampled rays: latA + latTpre (|sx| + |sy|) + latRef epsO, epsO = the rounding
                                      //   noise of the reference's line through the caller's origin (kernels_f32.cu)
-  float detTpre, detRef;
+  float latRef, detRef;
   float spider;                      // rounding of the Chebyshev spider polynomial (in units of cos(n phi))
   float cond;                        // the reference's quadratic formula loses hb^2 / |A C| digits (rt:646-658): dz |q| += cond hb^2 / |A|
   float ang;                         // grazing angle against the end of the reflectivity grid [deg]
@@ -111,8 +113,8 @@ struct alignas(16) Geo32 {
   float oeX, oeY, shellRhoMin, shellInvStep;
   float lMirror, zExitCBtel, cosPipe, sinPipe;
   float dShift, depthOverCos, lateralShift, transversalShift;   // depthOverCos = ddEnd - ddWin = depthDet / cos(pipesTurned): the second detector plane of deviationDet (rt:2081-2085)
-  float radiusWindow2, chipCX, chipCY, cosTheta;
-  float sinTheta, stripDist, stripWidth, invStripPitch;
+  float chipCX, chipCY, radiusWindow2, cosTheta;   // (chipCX, chipCY), (invBinX, invBinY), (oeX, oeY), (lateralShift,
+  float sinTheta, stripDist, stripWidth, invStripPitch;   //  transversalShift): 8-byte aligned pairs for the packed x / y arithmetic
   float invBinX, invBinY, dzPipe1, rPipe12;
   float cosTX, sinTX, cosTY, sinTY, halfLenTel;
   float srcX, srcY, srcRadius, srcRadius2, invSrcDz, colDz;

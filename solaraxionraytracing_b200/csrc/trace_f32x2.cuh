@@ -25,34 +25,6 @@ namespace fast {
 #endif
 constexpr int kBlockX2 = SART_F32X2_BLOCK, kWarpsX2 = kBlockX2 / 32;
 
-// Two floats, one per ray of the pair, in an aligned register pair.
-struct f2 {
-  float2 v;
-  __device__ __forceinline__ f2() {}
-  __device__ __forceinline__ f2(float2 a) : v(a) {}
-  __device__ __forceinline__ explicit f2(float s) : v(make_float2(s, s)) {}
-  __device__ __forceinline__ f2(float a, float b) : v(make_float2(a, b)) {}
-};
-__device__ __forceinline__ f2 operator+(f2 a, f2 b) { return f2(__fadd2_rn(a.v, b.v)); }
-__device__ __forceinline__ f2 operator*(f2 a, f2 b) { return f2(__fmul2_rn(a.v, b.v)); }
-__device__ __forceinline__ f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }   // folds into the consumer's operand modifier
-__device__ __forceinline__ f2 operator-(f2 a, f2 b) { return f2(__fadd2_rn(a.v, (-b).v)); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return f2(__ffma2_rn(a.v, b.v, c.v)); }
-__device__ __forceinline__ f2 abs2(f2 a) { return f2(fabsf(a.v.x), fabsf(a.v.y)); }   // operand modifier as well
-__device__ __forceinline__ f2 rcp_nr2(f2 x) {
-  const f2 r(rcp_approx(x.v.x), rcp_approx(x.v.y));
-  return fma2(r, fma2(-x, r, f2(1.0f)), r);
-}
-__device__ __forceinline__ f2 rsqrt_nr2(f2 x) {
-  const f2 y(rsqrt_approx(x.v.x), rsqrt_approx(x.v.y));
-  const f2 h = f2(0.5f) * x * y;
-  return fma2(y, fma2(-h, y, f2(0.5f)), y);
-}
-__device__ __forceinline__ f2 sqrt_pos2(f2 x) {
-  const f2 y(rsqrt_approx(x.v.x), rsqrt_approx(x.v.y));
-  const f2 s = x * y;
-  return fma2(fma2(-s, s, x), f2(0.5f) * y, s);
-}
 // sincos_2pi (fast_common.cuh) of u = w 2^-32 for the two words' float values
 __device__ __forceinline__ void sincos_2pi_w2(f2 wf, f2& s, f2& c) {
   const f2 t = f2(6.283185307179586f) * fma2(wf, f2(2.3283064365386963e-10f), f2(-0.5f));
