@@ -361,12 +361,14 @@ using ImageSink = ImageSinkT<true>;
 // is then broadcast through the warp and weighted for all M masses at once with lanes = masses (mass lane + 32 k), so
 // the per-mass sums live in registers of the lane that owns the mass and need no reduction. `image` / `imageW2` are the
 // mass-major accumulators [bin][SART_MAX_MASSES] (see k_fold_mass_acc).
-template <class Trace>
+// kPer = masses per lane (1, 2 or SART_MAX_MASSES / 32): the launcher picks the smallest that holds nMasses, because the
+// per-mass sums are 15 registers per mass and lane (with 4 masses per lane the FP32 kernel spilled: 80 registers, 112 bytes).
+template <int kPer, class Trace>
 __device__ __forceinline__ void mass_scan_loop(const FastParams& P, const RadialHist& rad, const double* __restrict__ masses,
                                                int nMasses, uint64_t first, uint64_t nRays, double* __restrict__ image,
                                                double* __restrict__ imageW2, sart_counters_t* __restrict__ counters,
                                                WarpCounters* wc, Trace trace) {
-  constexpr int kPer = SART_MAX_MASSES / 32;
+  static_assert(kPer >= 1 && kPer <= SART_MAX_MASSES / 32, "masses per lane");
   constexpr unsigned kFull = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double m2[kPer], sumW[kPer], sumW2[kPer], sumX[kPer], sumY[kPer], sumR[kPer];

@@ -168,7 +168,7 @@ k_trace_mc_f32_compact(const __grid_constant__ FastParams P, const __grid_consta
 }
 
 // ---- axion-mass scan with FP32 tracing (the per-mass weighting is fast_common.cuh's mass_scan_loop) --------------
-template <bool kWolter, bool kMargins>
+template <bool kWolter, bool kMargins, int kPer>
 __global__ void __launch_bounds__(kBlockM, SART_F32_MINBLOCKS_M)
 k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                       const __grid_constant__ FastTables T, const double* __restrict__ masses, int nMasses, uint64_t first,
@@ -182,7 +182,7 @@ k_trace_mc_f32_masses(const __grid_constant__ FastParams P, const __grid_constan
   smem_fill32(P, T, S);
   for (int i = threadIdx.x; i < kWarpsM * int(sizeof(WarpCounters) / 4); i += kBlockM) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
-  mass_scan_loop(P, T.rad, masses, nMasses, first, nRays, image, imageW2, counters, wc,
+  mass_scan_loop<kPer>(P, T.rad, masses, nMasses, first, nRays, image, imageW2, counters, wc,
                  [&](uint64_t ray, uint32_t id, RayResult& r) {
     RecordSink<false> sink{r, 0.0, T.rq, true};
     Head32 hd;
@@ -266,8 +266,13 @@ cudaError_t launch_mc_image_f32_masses(const fast::FastParams& P, const fast::Ge
   const bool wolter = P.telKind == SART_TK_XMM || P.telKind == SART_TK_ABRIXAS;
   const size_t smem = fast::smem_bytes32(P, fast::kWarpsM);
   const bool margins = T.rq.cap != 0u;
-  auto kern = wolter ? (margins ? fast::k_trace_mc_f32_masses<true, true> : fast::k_trace_mc_f32_masses<true, false>)
-                     : (margins ? fast::k_trace_mc_f32_masses<false, true> : fast::k_trace_mc_f32_masses<false, false>);
+  using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, const double*, int, uint64_t, uint64_t, PhiloxKeys, double*,
+                        double*, sart_counters_t*);
+  constexpr int kAll = SART_MAX_MASSES / 32;
+#define SART_ROW(W, M) {fast::k_trace_mc_f32_masses<W, M, 1>, fast::k_trace_mc_f32_masses<W, M, 2>, fast::k_trace_mc_f32_masses<W, M, kAll>}
+  static const Kern table[2][2][3] = {{SART_ROW(false, false), SART_ROW(false, true)}, {SART_ROW(true, false), SART_ROW(true, true)}};
+#undef SART_ROW
+  const Kern kern = table[wolter ? 1 : 0][margins ? 1 : 0][nMasses <= 32 ? 0 : (nMasses <= 64 ? 1 : 2)];   // masses per lane
   cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   int perSM = 0;

@@ -706,7 +706,7 @@ k_trace_mc_fast_masses(const __grid_constant__ FastParams P, const __grid_consta
   for (int i = threadIdx.x; i < kWarps * int(sizeof(WarpCounters) / 4); i += kBlock) reinterpret_cast<unsigned int*>(wc)[i] = 0u;
   __syncthreads();
 
-  mass_scan_loop(P, T.rad, masses, nMasses, first, nRays, image, imageW2, counters, wc,
+  mass_scan_loop<SART_MAX_MASSES / 32>(P, T.rad, masses, nMasses, first, nRays, image, imageW2, counters, wc,
                  [&](uint64_t ray, uint32_t, RayResult& r) { trace_one<kWolter, false>(P, T, S, seed, ray, 0.0, r); return false; });
 }
 
