@@ -263,6 +263,9 @@ __device__ __forceinline__ int finish_ray(const FastParams& P, const RayResult& 
 // are defined for the rays that reach it — exit codes PASSED, ZERO_WEIGHT, WINDOW_APERTURE, which is every ray
 // generateResultPlots (rt:2246-2289) reads them from — and 0 for rays clipped before; x, y, r, shellNumber and
 // transProbArgon for the rays past the window aperture, like the exact pipeline (kernels_exact.cu: store_ray).
+// kOptional = false: the caller asked for none of the optional arrays (the launcher checks the pointers), so neither their
+// null tests nor the values behind them are compiled in.
+template <bool kOptional = true>
 __device__ __forceinline__ void store_record(const FastParams& P, const sart_ray_out_t& o, size_t i, const RayResult& r,
                                              double m2, double energyKeV) {
   int code = r.code;
@@ -273,6 +276,7 @@ __device__ __forceinline__ void store_record(const FastParams& P, const sart_ray
   const int ec = code & SART_CODE_MASK;
   const bool tail = ec == SART_EXIT_PASSED || ec == SART_EXIT_ZERO_WEIGHT;
   o.x[i] = tail ? r.x : 0.0; o.y[i] = tail ? r.y : 0.0; o.w[i] = wd; o.code[i] = code; o.shell[i] = tail ? r.shell : -1;
+  if (!kOptional) return;
   if (o.energy) o.energy[i] = energyKeV;
   if (o.reflect) o.reflect[i] = weighted ? r.refl : 0.0;
   if (o.transMagnet)
@@ -287,9 +291,10 @@ __device__ __forceinline__ void store_record(const FastParams& P, const sart_ray
 }
 
 // Sink that keeps the outcome as a RayResult (per-ray records, mass scan).
-template <bool kFoldT>
+template <bool kFoldT, bool kRecordT = true>
 struct RecordSink {
   static constexpr bool kFold = kFoldT;
+  static constexpr bool kRecord = kRecordT;   // false: the record fields nobody reads (pathCB, deviationDet) are not computed
   RayResult& out;
   double m2;
   const RetraceQueue& rq;
@@ -318,6 +323,7 @@ struct RecordSink {
 template <bool kRadial>
 struct ImageSinkT {
   static constexpr bool kFold = true;
+  static constexpr bool kRecord = false;
   const FastTables& T;
   double m2;
   double* __restrict__ image;

@@ -61,6 +61,7 @@ k_trace_mc_rays_f32(const __grid_constant__ FastParams P, const __grid_constant_
 // pipeline's pass over the re-trace queue, which appends its own passed rays. Counters as in the fused kernel.
 struct PassedSink {
   static constexpr bool kFold = true;
+  static constexpr bool kRecord = true;    // the optional arrays of sart_passed_out_t include pathCB and deviationDet
   const FastTables& T;
   double m2;
   WarpCounters& wc;
@@ -166,7 +167,8 @@ k_trace_mc_passed_f32(const __grid_constant__ FastParams P, const __grid_constan
 // The slopes are formed in FP64 from the caller's points (the origin is 1.5e14 mm away), everything after that is the
 // FP32 pipeline. The energy is mapped to its index in the tabulated energies (the reference only ever traces tabulated
 // energies, rt:470); an energy that is not a table value is traced at the nearest one and flagged INTERP_CLAMPED.
-template <bool kWolter, bool kPlain, bool kMargins>
+// kOptional: the caller wants optional record arrays (else only x, y, w, code, shell are formed and stored).
+template <bool kWolter, bool kPlain, bool kMargins, bool kOptional>
 __global__ void __launch_bounds__(kBlock32, SART_F32_MINBLOCKS)
 k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_constant__ Geo32 G,
                        const __grid_constant__ FastTables T, double mAxion2, size_t n, const double* __restrict__ origin,
@@ -204,12 +206,12 @@ k_trace_presampled_f32(const __grid_constant__ FastParams P, const __grid_consta
     hd.eIdx = k;
     hd.offGrid = fmax(__ldg(T.energies + k), 0.03) != Ec;
     RayResult r;
-    RecordSink<true> sink{r, mAxion2, T.rq, false};
+    RecordSink<true, kOptional> sink{r, mAxion2, T.rq, false};
     Rec32 rec;
     rec.id = uint32_t(i);
     const int c0 = stage_a32<kWolter, true, kPlain, false, false, kMargins>(P, G, T, S, hd, rec);
     finish32<kWolter, kPlain, true, kMargins>(P, G, T, S, c0, rec, sink);
-    store_record(P, o, i, r, mAxion2, Ec);
+    store_record<kOptional>(P, o, i, r, mAxion2, Ec);
   }
 }
 
@@ -225,12 +227,14 @@ cudaError_t launch_presampled_f32(const fast::FastParams& P, const fast::Geo32& 
   const bool plain = !P.testXray && P.stage == SART_SK_VACUUM && !P.rotated && P.flags == 0 && P.reflKind != SART_RK_EFFECTIVE_AREA;
   using Kern = void (*)(fast::FastParams, fast::Geo32, fast::FastTables, double, size_t, const double*, const double*, const double*,
                         sart_ray_out_t);
-  static const Kern table[2][2][2] = {   // [wolter][plain][margins]
-      {{fast::k_trace_presampled_f32<false, false, false>, fast::k_trace_presampled_f32<false, false, true>},
-       {fast::k_trace_presampled_f32<false, true, false>, fast::k_trace_presampled_f32<false, true, true>}},
-      {{fast::k_trace_presampled_f32<true, false, false>, fast::k_trace_presampled_f32<true, false, true>},
-       {fast::k_trace_presampled_f32<true, true, false>, fast::k_trace_presampled_f32<true, true, true>}}};
-  const Kern kern = table[wolter ? 1 : 0][plain ? 1 : 0][T.rq.cap != 0u ? 1 : 0];
+#define SART_ROW(W, PL) {{fast::k_trace_presampled_f32<W, PL, false, false>, fast::k_trace_presampled_f32<W, PL, false, true>}, \
+                         {fast::k_trace_presampled_f32<W, PL, true, false>, fast::k_trace_presampled_f32<W, PL, true, true>}}
+  static const Kern table[2][2][2][2] = {   // [wolter][plain][margins][optional arrays wanted]
+      {SART_ROW(false, false), SART_ROW(false, true)}, {SART_ROW(true, false), SART_ROW(true, true)}};
+#undef SART_ROW
+  const bool optional = o.energy || o.reflect || o.transMagnet || o.yaw || o.alpha1 || o.alpha2 || o.pathCB || o.r ||
+                        o.deviationDet || o.transProbArgon;
+  const Kern kern = table[wolter ? 1 : 0][plain ? 1 : 0][T.rq.cap != 0u ? 1 : 0][optional ? 1 : 0];
   cudaError_t e = fast::set_smem(kern, smem);
   if (e != cudaSuccess) return e;
   int perSM = 0;
