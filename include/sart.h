@@ -247,7 +247,9 @@ int sart_update_setup(sart_handle_t* h, const sart_setup_t* setup);
 int sart_set_axion_masses(sart_handle_t* h, int n, const double* masses_eV);
 /* 0 = "exact": FP64, the reference's operation order (bit-faithful hit/miss classification);
  * 1 = "fast": FP64 algebra on (point, slopes) + FP32 weights (closer to exact arithmetic than the reference itself);
- * 2 = "f32": the same formulation with FP32 geometry (positions to ~1e-4 mm, the reference's own rounding level). */
+ * 2 = "f32": the same formulation with FP32 geometry (positions to ~1e-4 mm, the reference's own rounding level).
+ * Every reflectivity kind (rt:1533-1580, rkEffectiveArea included) and XMM hole type (rt:1674-1688) runs in all three modes;
+ * modes 1 and 2 return SART_ERR_CONFIG for shells that overlap / are not in ascending order and for more than 64 holes. */
 int sart_set_precision(sart_handle_t* h, int mode);
 /* Precision modes 1 and 2 only: 1 = compact the rays that survive bore, pipes, vetoes and glass fronts into full warps before the
  * mirror stage (pays off when most rays are clipped, e.g. BabyIAXO + XMM); 0 = one ray per lane throughout. Results are

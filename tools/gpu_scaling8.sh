@@ -4,7 +4,7 @@ set -x
 out=gpurun_out/${1:-scale8}
 mkdir -p $out
 nvidia-smi -L | wc -l
-for n in 8 4; do
+for n in 8 4 2; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n bench.py --gpus $n --steps 20 --warmup 3 > $out/bench_$n.json 2> $out/bench_$n.err
 tail -2 $out/bench_$n.err; cut -c1-1500 $out/bench_$n.json
 done
