@@ -448,6 +448,14 @@ int sart_shell_lookup(const sart_setup_t* setup, int n, const float* rho, int32_
 int sart_error_budgets(const sart_setup_t* setup, int nRadii, double scale, double slope_sum, double rs, double* lat_mm,
                        double* det_mm, int* pipes_free);
 
+/* ---- which pipelines take this setup (host helper; no device needed). Returns 1 when precision modes 1 and 2 can run it,
+ * 0 when only the exact pipeline can — `why` (optional, at most why_len bytes incl. the terminator) then says what is in
+ * the way — and a negative SART_ERR_* for an invalid setup. Since round 2 the throughput modes cover every reflectivity
+ * kind (rt:1533-1580) and XMM hole type (rt:1674-1688) of the reference; they refuse shells that overlap or are not in
+ * ascending order of radius and hole patterns of more than 64 holes. (Mode 2 in addition needs its radial shell table:
+ * sart_shell_lookup tells.) */
+int sart_throughput_supported(const sart_setup_t* setup, char* why, int why_len);
+
 #ifdef __cplusplus
 }
 #endif

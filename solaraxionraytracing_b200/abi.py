@@ -227,4 +227,5 @@ SIGNATURES = {
     "sart_error_budgets": (C.c_int, [C.POINTER(Setup), C.c_int, C.c_double, C.c_double, C.c_double, c_double_p, c_double_p,
                                      C.POINTER(C.c_int)]),
     "sart_shell_lookup": (C.c_int, [C.POINTER(Setup), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "sart_throughput_supported": (C.c_int, [C.POINTER(Setup), C.c_char_p, C.c_int]),
 }

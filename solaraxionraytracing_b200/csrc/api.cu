@@ -581,6 +581,15 @@ int sart_error_budgets(const sart_setup_t* setup, int nRadii, double scale, doub
   return SART_OK;
 }
 
+int sart_throughput_supported(const sart_setup_t* setup, char* why, int why_len) {
+  int rc = validate(setup, nullptr);
+  if (rc) return rc;
+  const char* w = "";
+  const bool ok = fast::supported(*setup, &w);
+  if (why && why_len > 0) { std::strncpy(why, ok ? "" : w, size_t(why_len)); why[why_len - 1] = 0; }
+  return ok ? 1 : 0;
+}
+
 void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {
   uint32_t w[6];
   ray_words(seed, ray, w);

@@ -62,3 +62,33 @@ def test_command_line_refuses_silent_stand_ins(rt, tmp_path):
     with pytest.raises(SystemExit) as e:
         main(["--config", str(cfg), "--nRays", "1000"])
     assert "allowSynthetic" in str(e.value) and "solar model" in str(e.value)
+
+
+def _supported(rt, setup):
+    why = C.create_string_buffer(256)
+    rc = rt.lib.sart_throughput_supported(C.byref(setup), why, len(why))
+    return rc, why.value.decode()
+
+
+def test_throughput_modes_cover_every_reflectivity_kind_and_hole_type(rt):
+    """sart_throughput_supported (host-only): since round 2 precision modes 1 and 2 take rkEffectiveArea (rt:1553-1562) and
+    every XMM hole type (rt:1674-1688); they still refuse shells that overlap or are out of order and more than 64 holes."""
+    for tel in (abi.TK_LLNL, abi.TK_XMM, abi.TK_ABRIXAS):
+        exp = abi.ES_CAST if tel == abi.TK_LLNL else abi.ES_BABYIAXO
+        setup = ref_setup.make_setup(exp, abi.DK_INGRID2018, abi.SK_VACUUM, tel, 0)
+        assert _supported(rt, setup) == (1, "")
+        setup.telescope.reflKind = abi.RK_EFFECTIVE_AREA
+        assert _supported(rt, setup) == (1, "")
+    xmm = ref_setup.make_setup(abi.ES_BABYIAXO, abi.DK_INGRIDIAXO, abi.SK_VACUUM, abi.TK_XMM, 0)
+    for hole in (abi.HT_CROSS, abi.HT_STAR, abi.HT_CIRCLE, abi.HT_SQUARE, abi.HT_DIAMOND):
+        xmm.telescope.holeType, xmm.telescope.numberOfHoles, xmm.telescope.holeInOptics = hole, 5, 2.0
+        assert _supported(rt, xmm) == (1, "")
+    xmm.telescope.numberOfHoles = 65
+    rc, why = _supported(rt, xmm)
+    assert rc == 0 and "64 holes" in why
+    llnl = ref_setup.make_setup(abi.ES_CAST, abi.DK_INGRID2018, abi.SK_VACUUM, abi.TK_LLNL, 0)
+    llnl.telescope.allR1[3] = llnl.telescope.allR1[2]      # two shells at the same radius
+    rc, why = _supported(rt, llnl)
+    assert rc == 0 and "shell" in why
+    llnl.abi_version = 0
+    assert rt.lib.sart_throughput_supported(C.byref(llnl), None, 0) < 0
