@@ -299,18 +299,18 @@ k_trace_mc_image(const __grid_constant__ Params P, const __grid_constant__ Table
 
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   ThreadSums ts;
-  if (list) {   // re-trace of the uncertain rays of an FP32 launch, which has counted them in n_rays already
-    const uint32_t nList = min(*listCount, listCap);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nList; j += uint32_t(stride))
-      mc_image_ray(P, T, nMasses, masses, seed, first + list[j], image, imageW2, bc, mc, ts);
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-      for (int m = 0; m < nMasses; ++m) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[m].n_retraced), (unsigned long long)nList);
-  } else {
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nRays; i += stride) {
-      ++ts.n_rays;
-      mc_image_ray(P, T, nMasses, masses, seed, first + i, image, imageW2, bc, mc, ts);
-    }
+  // One loop for both modes, so that the per-ray code (8500 SASS instructions, most of them inlined f64 libm) exists once:
+  // this kernel waits for instruction fetches more than for anything else (profiles/README.md).
+  // List mode: the re-trace of the uncertain rays of an FP32 launch, which has counted them in n_rays already.
+  const bool listMode = list != nullptr;
+  const uint64_t total = listMode ? uint64_t(min(*listCount, listCap)) : nRays;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const uint64_t ray = first + (listMode ? uint64_t(list[i]) : i);
+    if (!listMode) ++ts.n_rays;
+    mc_image_ray(P, T, nMasses, masses, seed, ray, image, imageW2, bc, mc, ts);
   }
+  if (listMode && blockIdx.x == 0 && threadIdx.x == 0)
+    for (int m = 0; m < nMasses; ++m) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[m].n_retraced), (unsigned long long)total);
   // the thread sums of the first mass: warp shuffle, then one shared-memory atomic per warp and quantity
   for (int o = 16; o > 0; o >>= 1) {
     ts.n_rays += __shfl_down_sync(0xffffffffu, ts.n_rays, o);

@@ -28,14 +28,15 @@ SART_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 SART_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ k0;
+    // one 32 x 32 -> 64 bit multiply (IMAD.WIDE.U32) gives both halves of a product; the round keys k + r W are written
+    // as such, so that with a kernel-uniform seed they are uniform-datapath values rather than a running per-thread sum
+    const uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
+    const uint32_t hi0 = uint32_t(p0 >> 32), lo0 = uint32_t(p0);
+    const uint32_t hi1 = uint32_t(p1 >> 32), lo1 = uint32_t(p1);
+    c0 = hi1 ^ c1 ^ (k0 + uint32_t(r) * 0x9E3779B9u);
     c1 = lo1;
-    c2 = hi0 ^ c3 ^ k1;
+    c2 = hi0 ^ c3 ^ (k1 + uint32_t(r) * 0xBB67AE85u);
     c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
   }
   return Philox4{c0, c1, c2, c3};
 }

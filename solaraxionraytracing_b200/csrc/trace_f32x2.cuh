@@ -190,7 +190,7 @@ __device__ __forceinline__ void trace_pair32(const FastParams& P, const Geo32& G
     const f2 mA = abs2(mExit) - thrCB;
     const f2 mB = fma2(-f2(Q.entK), thrCB, abs2(mEnt));
     min_into(slack0, mA.v.x); min_into(slack1, mA.v.y);
-    min_into(slack0, inExit0 ? kSlackInf : mB.v.x); min_into(slack1, inExit1 ? kSlackInf : mB.v.y);
+    min_into(slack0, mB.v.x); min_into(slack1, mB.v.y);   // every ray: trace_f32.cuh, stage_a32
   }
   f2 path2 = f2(G.lengthB2) * (f2(1.0f) + s2sum);
   if (!(hitEnt0 && hitEnt1)) {   // a ray that enters through the bore wall rt:1820-1843
