@@ -220,7 +220,7 @@ struct RayResult {
   double wPost;   // window or strongback * detector gas * exposure (0 when the window aperture is missed)
   double x, y, r;
   // conversion probability pieces: vacuum convVac = (g B L / 2)^2; gas: Gamma, L, exp(-Gamma L), exp(-Gamma L/2), 1/(2E)
-  float convVac, gasGamma, gasE1, gasE2, gasInv2E;
+  float convVac, gasGamma, gasE1, gasE2, gasInv2E;   // gasE1 holds 1 - exp(-Gamma L / 2), gasE2 exp(-Gamma L / 2) (conv_factor)
   double gasL;
   // the rest of the Axion record (rt:192-221) for the per-ray entry points; dead code in the fused kernels
   int eIdx;                 // index of the tabulated energy (the X-ray source energy sits at nEnergies)
@@ -233,17 +233,23 @@ struct RayResult {
 };
 
 // Conversion probability for axion mass^2 m2 (computeMagnetTransmission rt:1582-1625 without the cos(ya) factor).
-__device__ __forceinline__ double conv_factor(const FastParams& P, float convVac, float gasGamma, float gasE1, float gasE2,
+// gasA = 1 - exp(-Gamma L / 2) (from expm1f), gasE2 = exp(-Gamma L / 2). The reference's bracket
+//   1 + exp(-Gamma L) - 2 exp(-Gamma L / 2) cos(q L)  =  (1 - exp(-Gamma L / 2))^2 + 4 exp(-Gamma L / 2) sin^2(q L / 2)
+// is evaluated in the second form: at the resonance m_a = m_gamma (q -> 0) with a thin gas (Gamma L ~ 1e-4) the first one
+// is (Gamma L)^2 / 4 ~ 1e-9 left over from terms of order 1 — nothing in FP32: half the rays of a scan point at the
+// resonance came out with weight zero (tests/test_gpu_retrace.py: test_mass_scan_counters_equal_exact_on_1e8_rays).
+__device__ __forceinline__ double conv_factor(const FastParams& P, float convVac, float gasGamma, float gasA, float gasE2,
                                               float gasInv2E, double gasL, double m2) {
   if (P.flags & SART_CF_IGNORE_CONV_PROB) return 1.0;
   if (P.stage == SART_SK_VACUUM) return double(convVac);
   const double q = fabs(P.gasMgamma2 - m2) * double(gasInv2E);   // momentumTransfer am:63-68
-  double ph = q * gasL;   // phase reduced in FP64 before the FP32 cosine
-  ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);
-  const float cq = __cosf(float(ph));
+  double ph = q * gasL;   // phase reduced in FP64 before the FP32 sine
+  ph = fma(-6.283185307179586, rint(ph * 0.15915494309189535), ph);   // [-pi, pi]
+  const float sh = sinf(float(0.5 * ph));   // relative accuracy also for a tiny phase (the MUFU sine has an absolute one)
   const double g = double(gasGamma);
   const double term2 = rcp_nr(fma(q, q, 0.25 * g * g));
-  return P.gasTerm1 * term2 * double(1.0f + gasE1 - 2.0f * gasE2 * cq);
+  const double a = double(gasA), s2 = double(sh) * double(sh);   // FP64 products: (Gamma L)^2 may leave the FP32 range
+  return P.gasTerm1 * term2 * fma(a, a, 4.0 * double(gasE2) * s2);
 }
 // Tail of traceAxion for one axion mass: exit code | flags and the final weight.
 template <bool kFolded>

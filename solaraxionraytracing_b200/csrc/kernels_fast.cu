@@ -451,7 +451,7 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
       out.gasL = double(pathm) / 1.97e-7;
       const float gl = float(gamma * out.gasL);
       out.gasGamma = float(gamma);
-      out.gasE1 = __expf(-gl); out.gasE2 = __expf(-0.5f * gl);
+      out.gasE1 = -expm1f(-0.5f * gl); out.gasE2 = __expf(-0.5f * gl);   // 1 - e^(-Gamma L / 2) without cancellation, e^(-Gamma L / 2)
       out.gasInv2E = gv.y;
       const float distPipe = float(zw - P.zExitCBtel) * 1e-3f;   // intensitySuppression2 am:102-113
       pre *= __expf(-gv.x * float(P.gasRhoPipe100) * distPipe) * __expf(-gv.x * float(P.gasRhoMagnet100) * pathm);
