@@ -265,3 +265,33 @@ def test_counters_equal_the_oracle_on_2e8_rays(cfg):
             # and a bin is 0.055 mm wide, so ~4e-3 of the rays land in a neighbouring bin (measured 3.6e-3; LLNL 3e-4)
             assert l1 < (1e-5 if mode == 0 else (5e-4 if cfg == "cast_llnl" else 1e-2))
     assert got[2]["n_exit"] == got[0]["n_exit"] and got[2]["n_passed_till_window"] == got[0]["n_passed_till_window"]
+
+
+_COMBOS = [(ex, dk, sk, tk) for ex in (abi.ES_CAST, abi.ES_BABYIAXO) for dk in (abi.DK_INGRID2017, abi.DK_INGRID2018, abi.DK_INGRIDIAXO)
+           for sk in (abi.SK_VACUUM, abi.SK_GAS) for tk in (abi.TK_LLNL, abi.TK_XMM, abi.TK_ABRIXAS)]
+
+
+@pytest.mark.parametrize("ex,dk,sk,tk", _COMBOS, ids=["%d%d%d%d" % c for c in _COMBOS])
+def test_every_setup_combination_equals_the_oracle_on_2e7_rays(ex, dk, sk, tk):
+    """initFullSetup's whole matrix against the CPU oracle: 2e7 Monte Carlo rays per combination (~1 s of oracle each), exact
+    pipeline. Cone optics: every counter identical; Wolter optics: at most 3 rays of 2e7 differ (the libm ulps of the sampling,
+    see test_counters_equal_the_oracle_on_2e8_rays). Flux within 1e-9. (The FP32 pipeline equals the exact one on 1e9 rays of
+    each combination: tests/test_gpu_retrace.py.)"""
+    import os
+    from oracle import oracle as orc, ref_setup
+    from helpers import make_tables
+    from solaraxionraytracing_b200 import raytracer as rt
+    setup = ref_setup.make_setup(ex, dk, sk, tk, 0)
+    tb = make_tables(setup.telescope.nCoatings, kind="primakoff" if tk != abi.TK_LLNL else "abc")
+    n, seed = 20_000_000, SEED + 11
+    orc.lib().oracle_set_num_threads(os.cpu_count() or 1)
+    _, _, cnt = orc.trace_mc(setup, tb, 0, n, seed)
+    ref = cnt[0]
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.trace_mc(n, seed)
+        c = tr.read_image().counters[0]
+    diff = {k: (c["n_exit"][k], v) for k, v in ref["n_exit"].items() if c["n_exit"][k] != v}
+    assert sum(abs(a - b) for a, b in diff.values()) <= (0 if tk == abi.TK_LLNL else 6), diff
+    assert c["n_interp_clamped"] == ref["n_interp_clamped"]
+    if ref["sum_w"] > 0:
+        assert abs(c["sum_w"] / ref["sum_w"] - 1.0) < (1e-9 if not diff else 1e-6)
