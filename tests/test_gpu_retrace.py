@@ -372,3 +372,20 @@ def test_every_setup_combination_counters_equal_exact_on_1e9_rays(rt, ex, dk, sk
     assert f["n_unresolved"] == 0
     if e["sum_w"] > 0:
         assert abs(f["sum_w"] / e["sum_w"] - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", ["cast_llnl", "babyiaxo_xmm"])
+def test_f32_mc_rays_exit_codes_equal_exact_on_2e8_rays(rt, cfg):
+    """The per-ray entry point at a sample size that holds the rare classes (the entrance-rim rays occur 4.5e-8 of the time):
+    sart_trace_mc_rays in precision 2 against precision 0, 2e8 rays in ten chunks, code word and shell of every ray."""
+    setup, tb = make_config(cfg)
+    chunk, n_chunks = 20_000_000, 10
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        for k in range(n_chunks):
+            tr.set_precision(0)
+            ex = tr.traceAxionWrapper(chunk, SEED + 5, first_ray=k * chunk, optional=False)
+            tr.set_precision(2)
+            fa = tr.traceAxionWrapper(chunk, SEED + 5, first_ray=k * chunk, optional=False)
+            mism = np.flatnonzero(ex.code != fa.code)
+            assert mism.size == 0, (k, [(int(i) + k * chunk, int(ex.code[i]), int(fa.code[i])) for i in mism[:10]])
+            assert np.array_equal(ex.shell, fa.shell)
