@@ -596,26 +596,6 @@ void sart_ray_uniforms(uint64_t seed, uint64_t ray, double u[6]) {
   for (int i = 0; i < 6; ++i) u[i] = u01(w[i]);
 }
 
-// First launches of the FP32 fused kernels (both samplers), made here, right after the table upload, instead of inside the
-// caller's first sart_trace_mc: measured on B200, the alias-sampler kernel ran at 24.2 ms per 1e9 rays for the whole life
-// of a process whose first trace launch followed a 256 MB memset, and at 20.0 ms when a small launch had come first.
-static int warm_f32(sart_handle* h) {
-  if (!h->fast_ok || !h->f32_ok || h->setup.testSource.active) return SART_OK;
-  if (h->params.nRadii < 1 || h->params.nEnergies < 1 || !h->ftables.radiusThr || !h->ftables.energyThr) return SART_OK;   // no solar table: nothing to sample
-  const int precision = h->precision, sampler = h->ftables.sampler;
-  h->precision = 2;
-  int rc = SART_OK;
-  for (int smp = 0; smp <= (h->alias_ok ? 1 : 0) && rc == SART_OK; ++smp) {
-    h->ftables.sampler = smp;
-    rc = sart_trace_mc(h, 0, uint64_t(1) << 20, 0x5eedull);
-  }
-  h->ftables.sampler = sampler;
-  h->precision = precision;
-  if (rc == SART_OK) rc = sart_reset_image(h);
-  if (rc == SART_OK) SART_CUDA(cudaStreamSynchronize(h->stream));
-  return rc;
-}
-
 int sart_create(const sart_setup_t* setup, const sart_tables_t* tables, int device, sart_handle_t** out) {
   if (!out) return fail(SART_ERR_ARG, "sart_create: out is NULL");
   *out = nullptr;
@@ -646,7 +626,6 @@ int sart_create(const sart_setup_t* setup, const sart_tables_t* tables, int devi
   if ((e = cudaMemcpyAsync(h->d_masses, h->masses, sizeof(double), cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) { sart_destroy(h); return cuda_fail(e, "cudaMemcpyAsync"); }
   if ((rc = ensure_image(h, 1))) { sart_destroy(h); return rc; }
   if ((rc = autotune(h))) { sart_destroy(h); return rc; }
-  if ((rc = warm_f32(h))) { sart_destroy(h); return rc; }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { sart_destroy(h); return cuda_fail(e, "cudaStreamSynchronize"); }
   *out = h;
   return SART_OK;

@@ -15,8 +15,8 @@ tail -3 $out/bench.err; cat $out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_reference.json 2>> $out/bench.err; cat $out/bench_reference.json
 if [ $rc -eq 0 ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > $out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_mc_f32 --launch-skip 3 -c 1 -o $out/prof_f32 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-presampled --no-configs > $out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_mc_f32 --launch-skip 2 -c 1 -o $out/prof_f32 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-presampled --no-configs > $out/ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_presampled_f32 -c 1 -o $out/prof_presampled_f32 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > $out/ncu_full2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_mc_image --launch-skip 2 -c 1 -o $out/prof_exact python tools/ncu_driver_exact.py cast_llnl > $out/ncu_full3.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace_mc_image --launch-skip 1 -c 1 -o $out/prof_exact python tools/ncu_driver_exact.py cast_llnl > $out/ncu_full3.log 2>&1
 fi
 ls -la $out
