@@ -352,7 +352,11 @@ __device__ __forceinline__ void stage_b(const FastParams& P, const FastTables& T
     // nickel test before the degenerate-hit test (rt:2040-2057): reproduce which of the two exits it takes.
     int code = SART_EXIT_NO_MIRROR_HIT;
     if (hitLayer > 0) {
-      const double zc = P.zExitCBtel;  // pointExitCB.z in the telescope frame (not turned: exact; turned: approx.)
+      double zc = P.zExitCBtel;  // pointExitCB.z in the telescope frame
+      if (P.rotated) {   // turned: the z of the ray's point whose laboratory z is zExitCB (trace_f32.cuh: exit_plane_z32)
+        const double r13 = P.sinTX, r23 = -P.cosTX * P.sinTY, r33 = P.cosTX * P.cosTY, h = P.halfLenTel;
+        zc = (fma(r33, h, P.zExitCBtel - h) - fma(r13, x0 + P.oeX, r23 * (y0 + P.oeY))) * rcp_nr(fma(r13, tx, fma(r23, ty, r33)));
+      }
       const double xc = fma(zc, tx, x0), yc = fma(zc, ty, y0);
       const double rc2 = fma(xc, xc, yc * yc);
       const double rc = rc2 * rsqrt_nr(rc2);

@@ -115,7 +115,7 @@ __device__ __forceinline__ int miss1_code32(const Geo32& G, const ShellF32& sh, 
     const float a = fabsf(sg);
     const float lhs = a * (lM - zc), rhs = sh.R1 - below;
     const float m = fmaf(lhs, lhs, -rhs * rhs * (1.0f - a * a));
-    SART_UNC(kUncNickel, fmaf(-4.0f * Q.nick, lhs + rhs, fabsf(m)));
+    SART_UNC(kUncNickel, fmaf(-fmaf(8.0f * Q.sinA, lM - zc, 4.0f * Q.nick), lhs + rhs, fabsf(m)));   // stage_b32: the budget over this lever arm
     if (m > 0.0f) code = SART_EXIT_NICKEL;
   }
   return code;

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Randomised differential test of the FP32 pipeline against the exact one (development aid; the permanent versions of what
+it found live in tests/test_gpu_retrace.py): random telescope turns, detector shifts, ignore* flags, X-ray sources and
+hole patterns on top of the five base setups, N rays each in precision 0 and 2 (both compaction settings), every integer
+counter compared.   python tools/fuzz_setups.py [n_setups] [rays] [seed]"""
+import sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from helpers import make_config
+from solaraxionraytracing_b200 import abi, raytracer as rt
+
+n_setups = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000_000
+rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+bad = 0
+for it in range(n_setups):
+    base = str(rng.choice(["cast_llnl", "babyiaxo_xmm", "cast_abrixas", "babyiaxo_gas", "cast_xmm"]))
+    flags = 0
+    desc = [base]
+    xray = rng.random() < 0.3
+    for name, bit in (("ignoreDetWindow", abi.CF_IGNORE_DET_WINDOW), ("ignoreGasAbs", abi.CF_IGNORE_GAS_ABS),
+                      ("ignoreConvProb", abi.CF_IGNORE_CONV_PROB), ("ignoreReflection", abi.CF_IGNORE_REFLECTION)):
+        if rng.random() < 0.25:
+            flags |= bit; desc.append(name)
+    if xray:
+        flags |= abi.CF_XRAY_TEST
+    setup, tb = make_config(base, flags=flags)
+    if rng.random() < 0.5:
+        setup.telescope.telescope_turned_x = float(rng.uniform(-0.3, 0.3))
+        setup.telescope.telescope_turned_y = float(rng.uniform(-0.3, 0.3))
+        desc.append("turned %.3f %.3f" % (setup.telescope.telescope_turned_x, setup.telescope.telescope_turned_y))
+    if rng.random() < 0.3:
+        setup.detectorInstall.lateralShift = float(rng.uniform(-3, 3))
+        setup.detectorInstall.transversalShift = float(rng.uniform(-3, 3))
+        desc.append("shift %.2f %.2f" % (setup.detectorInstall.lateralShift, setup.detectorInstall.transversalShift))
+    if xray:
+        s = setup.testSource
+        s.parallel = int(rng.random() < 0.5)
+        s.energy = float(rng.uniform(0.5, 8.0))
+        s.radius = float(rng.uniform(2.0, 25.0))
+        s.offAxisUp = float(rng.uniform(-30, 30)) if rng.random() < 0.5 else 0.0
+        s.offAxisLeft = float(rng.uniform(-30, 30)) if rng.random() < 0.5 else 0.0
+        s.distance = float(rng.uniform(2000.0, 12000.0)); s.lengthCol = float(rng.uniform(0.2, 0.8)) * s.distance
+        desc.append("xray par=%d E=%.2f r=%.1f off=(%.1f, %.1f) d=%.0f col=%.0f" % (s.parallel, s.energy, s.radius, s.offAxisUp,
+                                                                                   s.offAxisLeft, s.distance, s.lengthCol))
+    if setup.telescope.kind == abi.TK_XMM and rng.random() < 0.4:
+        setup.telescope.holeType = int(rng.integers(1, 6)); setup.telescope.numberOfHoles = int(rng.integers(1, 8))
+        setup.telescope.holeInOptics = float(rng.uniform(0.5, 12.0))
+        desc.append("hole %d x%d R=%.1f" % (setup.telescope.holeType, setup.telescope.numberOfHoles, setup.telescope.holeInOptics))
+    try:
+        with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+            seed = int(rng.integers(1, 2**62))
+            tr.trace_mc(n, seed); e = tr.read_image().counters[0]
+            tr.set_precision(2)
+            res = []
+            for compact in (0, 1):
+                tr.set_compaction(compact); tr.reset_image(); tr.trace_mc(n, seed); f = tr.read_image().counters[0]
+                diff = {k: (f["n_exit"][k], v) for k, v in e["n_exit"].items() if f["n_exit"][k] != v}
+                for key in ("n_passed_till_window", "n_interp_clamped"):
+                    if f[key] != e[key]: diff[key] = (f[key], e[key])
+                if f["n_unresolved"]: diff["unresolved"] = f["n_unresolved"]
+                res.append((diff, f["n_retraced"] / n))
+        ok = not res[0][0] and not res[1][0]
+        bad += not ok
+        print("%3d %s  passed=%.4f retraced=%.2e  %s" % (it, "ok  " if ok else "DIFF", e["n_passed"] / n, res[0][1], "; ".join(desc)), flush=True)
+        if not ok: print("     ", res[0][0], res[1][0], flush=True)
+    except rt.SartError as ex:
+        print("%3d skip (%s): %s" % (it, str(ex)[:80], "; ".join(desc)), flush=True)
+print("setups with differing counters:", bad)
