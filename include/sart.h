@@ -211,7 +211,7 @@ typedef struct {
   uint64_t n_retraced;           /* precision mode 2: rays whose FP32 decision margins were inside the error budget and
                                     that were therefore traced by the exact FP64 pipeline instead (sart_set_retrace) */
   uint64_t n_unresolved;         /* such rays that did not fit the re-trace queue and kept their FP32 outcome (0 in
-                                    practice: the queue holds 3 % of a launch) */
+                                    practice: the queue holds 6 % of a launch) */
   double sum_w;                  /* Σ weights | passed  (performAngularScan rt:2800; "total flux" rt:885) */
   double sum_w2;
   double sum_x, sum_y, sum_r;    /* unweighted sums over passed rays (means of rt:2276-2278) */

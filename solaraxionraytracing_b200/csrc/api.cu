@@ -428,13 +428,13 @@ static int ensure_image(sart_handle* h, int nMasses) {
 
 static int ensure_stage(sart_handle* h, size_t bytes);
 
-// Re-trace queue for a launch of n rays of the FP32 pipeline: room for 3 % of them (measured: 0.01 - 0.3 % are
+// Re-trace queue for a launch of n rays of the FP32 pipeline: room for 6 % of them (measured: 0.01 - 0.3 % are
 // uncertain), cleared on the stream. Returns a queue with cap = 0 when re-tracing is off.
 constexpr uint64_t kRetraceChunk = uint64_t(1) << 31;   // rays per launch: queue entries are 32-bit offsets
 static int begin_queue(sart_handle* h, uint64_t n, fast::RetraceQueue* q) {
   *q = fast::RetraceQueue{nullptr, nullptr, 0u, 0u};
   if (!h->retrace || n == 0) return SART_OK;
-  const size_t want = size_t(std::min<uint64_t>(n, std::max<uint64_t>(n / 32 + 65536, 1u << 20)));
+  const size_t want = size_t(std::min<uint64_t>(n, std::max<uint64_t>(n / 16 + 65536, 1u << 20)));
   if (h->queue_cap < want) {
     SART_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_queue);

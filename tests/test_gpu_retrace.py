@@ -106,7 +106,7 @@ def test_budget_scale_shows_the_safety_factor(rt, cfg):
 
 
 def test_retrace_queue_overflow_is_counted_not_silent(rt):
-    """Budgets blown up by 1e4 make most rays "uncertain": the queue (3 % of the launch) overflows, the overflowing rays
+    """Budgets blown up by 1e4 make most rays "uncertain": the queue (6 % of the launch) overflows, the overflowing rays
     keep their FP32 outcome and are reported in n_unresolved; every ray is still counted exactly once."""
     setup, tb = make_config("cast_llnl")
     n = 40_000_000
@@ -117,7 +117,7 @@ def test_retrace_queue_overflow_is_counted_not_silent(rt):
         c = tr.read_image().counters[0]
     assert c["n_rays"] == n and sum(c["n_exit"].values()) == n
     assert c["n_unresolved"] > 0 and c["n_retraced"] > 0
-    assert c["n_retraced"] <= n // 32 + 65536 + (1 << 20)
+    assert c["n_retraced"] <= n // 16 + 65536 + (1 << 20)
 
 
 @pytest.mark.parametrize("cfg,pos_tol,rel_tol", [("cast_llnl", 1.5e-3, 2e-4), ("babyiaxo_xmm", 3e-3, 2e-4),
