@@ -99,12 +99,7 @@ void derive_tolerances(const FastParams& f, const ShellFast* a, int nShells, flo
   const double delta = std::max(f.dzExitCB, 1.0);                // zExitCB - lengthB: the base of the reference's extrapolation
   const double lever = std::max(L / delta, 1.0);
   const double D = f.testXray ? std::fabs(f.lengthB - f.srcZ) : f.sunDist;
-  // (3), per unit (|sx| + |sy|), safety 1.5 — and 4 for a turned telescope, which is an empirical factor: randomised
-  // differential runs (tools/fuzz_setups.py, 1e11 rays over 400 setups) found no misclassified ray in any unturned setup,
-  // and in telescopes turned by 0.2-0.3 degrees one ray in 1.5e10 whose lateral error was 1.5-2x the budget at 1.5. The
-  // reference's noise itself does not depend on the turn; what does has not been identified, so the slope term — which in
-  // the turned frame is evaluated with the frame's slopes, up to 10x the laboratory ones — carries it.
-  const double kRef = (f.rotated ? 4.0 : 1.5) * 4.440892098500626e-16 * D;
+  const double kRef = 1.5 * 4.440892098500626e-16 * D;           // (3), per unit (|sx| + |sy|), safety 1.5
   const double kSamp = f.testXray ? 0.0 : 2e-6 * f.radiusSun / f.sunDist;   // (2) direction, per unit rs, safety 2
   const double tolE = f.testXray ? 16.0 * eps * (f.radiusCB + f.srcRadius) * (1.0 + L / std::max(D, 1.0))
                                  : 16.0 * eps * f.radiusCB;      // (2) exit-disc point
@@ -114,7 +109,7 @@ void derive_tolerances(const FastParams& f, const ShellFast* a, int nShells, flo
   t->latS = float(scale * kSamp * L);
   t->latT = float(scale * (kRef * lever + 4.0 * eps * L));
   t->latTpre = float(scale * 4.0 * eps * L);
-  t->latRef = float(scale * (f.rotated ? 4.0 : 1.5) * lever);   // x epsO: the same factor for pre-sampled rays
+  t->latRef = float(scale * 1.5 * lever);
   // entrance plane: the slope terms act over lengthB instead of L, the reference's noise enters without the lever
   t->entK = float(std::max(1.0, std::fabs(f.lengthB) / L));
   // At the detector the optic maps directions to positions (position = focal length x angle; a lateral shift of the
@@ -127,7 +122,7 @@ void derive_tolerances(const FastParams& f, const ShellFast* a, int nShells, flo
   t->detS = float(scale * kSamp * fl);
   t->detT = float(scale * (kRef * fl / delta + 4.0 * eps * fl));
   t->detTpre = float(scale * 4.0 * eps * fl);
-  t->detRef = float(scale * (f.rotated ? 4.0 : 1.5) * fl / delta);
+  t->detRef = float(scale * 1.5 * fl / delta);
   t->rho = float(scale * 4.0 * eps * r1max);
   t->circ2 = float(scale * 8.0 * eps);
   t->spider = float(scale * 512.0 * eps);

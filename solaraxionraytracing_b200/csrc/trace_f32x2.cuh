@@ -52,7 +52,7 @@ __device__ __forceinline__ f2 pick_root2(const Tol32& Q, f2 A, f2 hb, f2 C, f2 d
   const f2 rsq = rsqrt_nr2(f2(fmaxf(disc.v.x, 1e-30f), fmaxf(disc.v.y, 1e-30f)));
   const f2 sq = disc * rsq;
   const f2 q = -(hb + f2(copysignf(sq.v.x, hb.v.x), copysignf(sq.v.y, hb.v.y)));
-  const f2 reach = abs2(mid) + half;
+  const f2 reach = fma2(abs2(mid) + half, f2(1.02f), f2(1.0f));   // pick_root32: the far root anywhere near the mirror
   const f2 far = abs2(q * dz) - reach * abs2(A);   // < 0: the far root q/A may lie in range as well
   const bool slow0 = !neg0 && far.v.x < 0.0f, slow1 = !neg1 && far.v.y < 0.0f;
   const f2 ts = C * rcp_nr2(q);

@@ -419,3 +419,35 @@ def test_strongly_turned_telescope_counters_equal_exact_on_1e8_rays(rt, cfg, tur
         g = tr.read_image().counters[0]
         for k, v in e["n_exit"].items():
             assert abs(g["n_exit"][k] - v) <= 3e-5 * n, (k, g["n_exit"][k], v)
+
+
+@pytest.mark.parametrize("fuzz_seed,turned,index,n", [(2024, False, 73, 100_000_000), (31337, True, 24, 1_000_000_000),
+                                                      (31337, True, 41, 1_000_000_000), (31337, True, 69, 1_000_000_000)])
+def test_fuzz_regressions_far_root_near_the_mirror(rt, monkeypatch, fuzz_seed, turned, index, n):
+    """Setups of the randomised differential run (tools/fuzz_setups.py) that had 1-2 rays of 1e8 / 1e9 "no mirror hit" in
+    precision 2 and a hit in precision 0: steep rays in turned Wolter telescopes, for which the FAR root of a mirror's
+    quadratic comes within rounding of the mirror's z interval — the reference tries that root first (rt:646-658). The FP32
+    pipeline decided "far root out of reach" without a margin; it now leaves every far root near the mirror to the re-trace."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    import fuzz_setups
+    if turned:
+        monkeypatch.setenv("FUZZ_TURN", "1")
+    else:
+        monkeypatch.delenv("FUZZ_TURN", raising=False)
+    rng = np.random.default_rng(fuzz_seed)
+    for _ in range(index + 1):
+        setup, tb, desc = fuzz_setups.random_setup(rng)
+        seed = int(rng.integers(1, 2**62)); first = int(rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]))
+    print(desc)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        tr.trace_mc(n, seed, first_ray=first)
+        e = tr.read_image().counters[0]
+        tr.set_precision(2)
+        for compact in (0, 1):
+            tr.set_compaction(compact); tr.reset_image(); tr.trace_mc(n, seed, first_ray=first)
+            f = tr.read_image().counters[0]
+            diff = {k: (f["n_exit"][k], v) for k, v in e["n_exit"].items() if f["n_exit"][k] != v}
+            assert not diff, (desc, compact, diff)
+            assert f["n_passed_till_window"] == e["n_passed_till_window"] and f["n_unresolved"] == 0

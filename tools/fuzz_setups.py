@@ -11,11 +11,10 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from helpers import make_config
 from solaraxionraytracing_b200 import abi, raytracer as rt
 
-n_setups = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000_000
-rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
-bad = 0
-for it in range(n_setups):
+
+
+def random_setup(rng):
+    """One random setup; consumes the generator exactly as the runs recorded in DESIGN.md did."""
     base = str(rng.choice(["cast_llnl", "babyiaxo_xmm", "cast_abrixas", "babyiaxo_gas", "cast_xmm"]))
     flags = 0
     desc = [base]
@@ -69,47 +68,61 @@ for it in range(n_setups):
         setup.telescope.holeType = int(rng.integers(1, 6)); setup.telescope.numberOfHoles = int(rng.integers(1, 8))
         setup.telescope.holeInOptics = float(rng.uniform(0.5, 12.0))
         desc.append("hole %d x%d R=%.1f" % (setup.telescope.holeType, setup.telescope.numberOfHoles, setup.telescope.holeInOptics))
-    try:
-        with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
-            seed = int(rng.integers(1, 2**62))
-            if os.environ.get("FUZZ_DIAG") and int(os.environ["FUZZ_DIAG"]) == it:   # locate the differing rays of one setup
+    return setup, tb, desc
+
+
+def main():
+    n_setups = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000_000
+    rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    bad = 0
+    for it in range(n_setups):
+        setup, tb, desc = random_setup(rng)
+        try:
+            with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+                seed = int(rng.integers(1, 2**62))
+                if os.environ.get("FUZZ_DIAG") and int(os.environ["FUZZ_DIAG"]) == it:   # locate the differing rays of one setup
+                    first = int(rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]))
+                    chunk = 10_000_000
+                    for k in range(n // chunk):
+                        tr.set_precision(0); ex = tr.traceAxionWrapper(chunk, seed, first_ray=first + k * chunk, optional=False)
+                        tr.set_precision(2); fa = tr.traceAxionWrapper(chunk, seed, first_ray=first + k * chunk, optional=False)
+                        for i in np.flatnonzero(ex.code != fa.code):
+                            print("DIAG ray", first + k * chunk + int(i), "seed", seed, "exact code", hex(int(ex.code[i])), "f32 code", hex(int(fa.code[i])),
+                                  "exact x,y", ex.x[i], ex.y[i], flush=True)
+                            for scale in (1.0, 1.5, 2.0, 4.0, 16.0):
+                                tr.set_retrace(1, scale)
+                                one = tr.traceAxionWrapper(1, seed, first_ray=first + k * chunk + int(i), optional=False)
+                                print("   budgets x", scale, "-> f32 code", hex(int(one.code[0])), flush=True)
+                            for name in ("latS", "latT", "latA", "detS", "detT", "detA", "rho", "discRel", "zrel", "nick", "sinA", "cond", "spider", "entK"):
+                                os.environ["SART_TOL_BOOST"] = name + "=4"
+                                tr.set_retrace(1, 0.5); tr.set_retrace(1, 1.0)   # a changed scale makes the library derive the budgets anew
+                                one = tr.traceAxionWrapper(1, seed, first_ray=first + k * chunk + int(i), optional=False)
+                                print("   4 x", name, "-> f32 code", hex(int(one.code[0])), flush=True)
+                            os.environ.pop("SART_TOL_BOOST")
+                            tr.set_retrace(1, 0.5); tr.set_retrace(1, 1.0)
+                    print("DIAG done:", "; ".join(desc)); sys.exit(0)
+                if os.environ.get("FUZZ_DIAG"):
+                    rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]); continue
                 first = int(rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]))
-                chunk = 10_000_000
-                for k in range(n // chunk):
-                    tr.set_precision(0); ex = tr.traceAxionWrapper(chunk, seed, first_ray=first + k * chunk, optional=False)
-                    tr.set_precision(2); fa = tr.traceAxionWrapper(chunk, seed, first_ray=first + k * chunk, optional=False)
-                    for i in np.flatnonzero(ex.code != fa.code):
-                        print("DIAG ray", first + k * chunk + int(i), "seed", seed, "exact code", hex(int(ex.code[i])), "f32 code", hex(int(fa.code[i])),
-                              "exact x,y", ex.x[i], ex.y[i], flush=True)
-                        for scale in (1.0, 1.5, 2.0, 4.0, 16.0):
-                            tr.set_retrace(1, scale)
-                            one = tr.traceAxionWrapper(1, seed, first_ray=first + k * chunk + int(i), optional=False)
-                            print("   budgets x", scale, "-> f32 code", hex(int(one.code[0])), flush=True)
-                        for name in ("latS", "latT", "latA", "detS", "detT", "detA", "rho", "discRel", "zrel", "nick", "sinA", "cond", "spider", "entK"):
-                            os.environ["SART_TOL_BOOST"] = name + "=4"
-                            tr.set_retrace(1, 0.5); tr.set_retrace(1, 1.0)   # a changed scale makes the library derive the budgets anew
-                            one = tr.traceAxionWrapper(1, seed, first_ray=first + k * chunk + int(i), optional=False)
-                            print("   4 x", name, "-> f32 code", hex(int(one.code[0])), flush=True)
-                        os.environ.pop("SART_TOL_BOOST")
-                        tr.set_retrace(1, 0.5); tr.set_retrace(1, 1.0)
-                print("DIAG done:", "; ".join(desc)); sys.exit(0)
-            if os.environ.get("FUZZ_DIAG"):
-                rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]); continue
-            first = int(rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]))
-            tr.trace_mc(n, seed, first_ray=first); e = tr.read_image().counters[0]
-            tr.set_precision(2)
-            res = []
-            for compact in (0, 1):
-                tr.set_compaction(compact); tr.reset_image(); tr.trace_mc(n, seed, first_ray=first); f = tr.read_image().counters[0]
-                diff = {k: (f["n_exit"][k], v) for k, v in e["n_exit"].items() if f["n_exit"][k] != v}
-                for key in ("n_passed_till_window", "n_interp_clamped"):
-                    if f[key] != e[key]: diff[key] = (f[key], e[key])
-                if f["n_unresolved"]: diff["unresolved"] = f["n_unresolved"]
-                res.append((diff, f["n_retraced"] / n))
-        ok = not res[0][0] and not res[1][0]
-        bad += not ok
-        print("%3d %s  passed=%.4f retraced=%.2e  %s" % (it, "ok  " if ok else "DIFF", e["n_passed"] / n, res[0][1], "; ".join(desc)), flush=True)
-        if not ok: print("     ", res[0][0], res[1][0], flush=True)
-    except rt.SartError as ex:
-        print("%3d skip (%s): %s" % (it, str(ex)[:80], "; ".join(desc)), flush=True)
-print("setups with differing counters:", bad)
+                tr.trace_mc(n, seed, first_ray=first); e = tr.read_image().counters[0]
+                tr.set_precision(2)
+                res = []
+                for compact in (0, 1):
+                    tr.set_compaction(compact); tr.reset_image(); tr.trace_mc(n, seed, first_ray=first); f = tr.read_image().counters[0]
+                    diff = {k: (f["n_exit"][k], v) for k, v in e["n_exit"].items() if f["n_exit"][k] != v}
+                    for key in ("n_passed_till_window", "n_interp_clamped"):
+                        if f[key] != e[key]: diff[key] = (f[key], e[key])
+                    if f["n_unresolved"]: diff["unresolved"] = f["n_unresolved"]
+                    res.append((diff, f["n_retraced"] / n))
+            ok = not res[0][0] and not res[1][0]
+            bad += not ok
+            print("%3d %s  passed=%.4f retraced=%.2e  %s" % (it, "ok  " if ok else "DIFF", e["n_passed"] / n, res[0][1], "; ".join(desc)), flush=True)
+            if not ok: print("     ", res[0][0], res[1][0], flush=True)
+        except rt.SartError as ex:
+            print("%3d skip (%s): %s" % (it, str(ex)[:80], "; ".join(desc)), flush=True)
+    print("setups with differing counters:", bad)
+
+
+if __name__ == "__main__":
+    main()
