@@ -105,6 +105,22 @@ def main():
                 if os.environ.get("FUZZ_DIAG"):
                     rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]); continue
                 first = int(rng.choice([0, 17, 2**32 - 12345, 2**40 + 3]))
+                if os.environ.get("FUZZ_MASSES") and setup.stage == abi.SK_GAS:   # a mass scan around the resonance instead
+                    masses = np.sort(np.concatenate([[0.008235101411623404], rng.uniform(0.002, 0.03, 4)]))
+                    tr.set_axion_masses(masses); desc.append("masses " + " ".join("%.5f" % m for m in masses))
+                    m1 = n // 4
+                    tr.trace_mc(m1, seed, first_ray=first); e = tr.read_image().counters
+                    tr.set_precision(2); tr.reset_image(); tr.trace_mc(m1, seed, first_ray=first); f = tr.read_image().counters
+                    diff = {}
+                    for k in range(len(masses)):
+                        for key, v in e[k]["n_exit"].items():
+                            if f[k]["n_exit"][key] != v: diff[(k, key)] = (f[k]["n_exit"][key], v)
+                        if f[k]["n_passed_till_window"] != e[k]["n_passed_till_window"]: diff[(k, "till")] = 1
+                        if e[k]["sum_w"] > 0 and abs(f[k]["sum_w"] / e[k]["sum_w"] - 1) > 1e-5: diff[(k, "flux")] = f[k]["sum_w"] / e[k]["sum_w"]
+                    bad += bool(diff)
+                    print("%3d %s  mass scan  %s" % (it, "DIFF" if diff else "ok  ", "; ".join(desc)), flush=True)
+                    if diff: print("     ", diff, flush=True)
+                    continue
                 tr.trace_mc(n, seed, first_ray=first); e = tr.read_image().counters[0]
                 tr.set_precision(2)
                 res = []
