@@ -451,3 +451,21 @@ def test_fuzz_regressions_far_root_near_the_mirror(rt, monkeypatch, fuzz_seed, t
             diff = {k: (f["n_exit"][k], v) for k, v in e["n_exit"].items() if f["n_exit"][k] != v}
             assert not diff, (desc, compact, diff)
             assert f["n_passed_till_window"] == e["n_passed_till_window"] and f["n_unresolved"] == 0
+
+
+@pytest.mark.parametrize("cfg,turn", [("cast_llnl", (0.21, -0.17)), ("babyiaxo_xmm", (-0.18, 0.25)), ("cast_abrixas", (0.3, 0.1))])
+def test_presampled_exit_codes_equal_oracle_turned_telescope(rt, oracle, cfg, turn):
+    """Tier (a) in a turned telescope (the setting of performAngularScan): sart_trace_presampled in precisions 0 and 2 against the
+    CPU oracle on 1e7 pre-sampled rays, every code word and shell."""
+    setup, tb = make_config(cfg)
+    setup.telescope.telescope_turned_x, setup.telescope.telescope_turned_y = turn
+    n = 10_000_000
+    origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, SEED + 21)
+    ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy, optional=False)
+    with rt.RayTracer(rt.FullRaytraceSetup(setup, tb)) as tr:
+        for mode in (0, 2):
+            tr.set_precision(mode)
+            gpu = tr.trace_presampled(origin, exit_xy, energy, optional=False)
+            mism = np.flatnonzero(gpu.code != ref.code)
+            assert mism.size == 0, (mode, [(int(i), int(gpu.code[i]), int(ref.code[i])) for i in mism[:10]])
+            assert np.array_equal(gpu.shell, ref.shell)
