@@ -15,9 +15,12 @@ from solaraxionraytracing_b200 import abi
 import hp_trace
 
 
-@pytest.mark.parametrize("cfg,n,kinds", [("cast_llnl", 2500, 4), ("babyiaxo_xmm", 900, 5), ("cast_abrixas", 1500, 4)])
-def test_oracle_exit_codes_agree_with_60_digit_geometry(oracle, cfg, n, kinds):
+@pytest.mark.parametrize("cfg,n,kinds,turn", [("cast_llnl", 2500, 4, None), ("babyiaxo_xmm", 900, 5, None), ("cast_abrixas", 1500, 4, None),
+                                              ("cast_llnl", 800, 3, (0.05, -0.04)), ("babyiaxo_xmm", 600, 4, (-0.18, 0.25))])
+def test_oracle_exit_codes_agree_with_60_digit_geometry(oracle, cfg, n, kinds, turn):
     setup, tb = make_config(cfg)
+    if turn:   # the frame change of a turned telescope (rt:1888-1905), as performAngularScan uses it
+        setup.telescope.telescope_turned_x, setup.telescope.telescope_turned_y = turn
     origin, exit_xy, energy = oracle.sample_rays(setup, tb, 0, n, 424242)
     ref = oracle.trace_presampled(setup, tb, origin, exit_xy, energy, optional=False)
     code = ref.code & abi.CODE_MASK
