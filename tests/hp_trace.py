@@ -217,10 +217,42 @@ def classify(setup, O, E_xy):
             for edge in (mpf("64.7"), mpf("151.6"), mpf("151.6") - mpf("20.9")):
                 near(rd - edge)
             hit = rd <= mpf("64.7") or (mpf("151.6") - mpf("20.9") < rd < mpf("151.6"))
+            if rd <= mpf("64.7") and tel.holeType != 0:
+                # holes in the central blocker (rt:1674-1688; lineIntersectsObject rt:494-527 with centre z = 0: the point
+                # of the line pointExitCB -> pointEntranceXRT in the plane z = 0, i.e. pointEntranceXRT itself)
+                R = mpf(tel.holeInOptics)
+                nH = tel.numberOfHoles
+                half_n = nH - -(-nH // 2)
+                s2 = mp.sqrt(2)
+                for l in range(-half_n, half_n + 1):
+                    cx = cy = mpf(0)
+                    if l != 0:
+                        if abs(l) % 2 == 0:
+                            cy = 2 * mpf(l) * R
+                        else:
+                            cx = 2 * (mpf(l) + mpf(l) / abs(l)) * R
+                    ix, iy = pEnt[0] - cx, pEnt[1] - cy
+                    tx, ty = ix / s2 - iy / s2, ix / s2 + iy / s2
+                    kind = tel.holeType      # 1 cross, 2 star, 3 circle, 4 square, 5 diamond (include/sart.h)
+                    for a in (ix, iy):
+                        if kind in (1, 2, 4): near(abs(a) - R)
+                        if kind in (1, 2): near(abs(a) - 16 * R)
+                    for a in (tx, ty):
+                        if kind in (2, 5): near(abs(a) - R)
+                        if kind == 2: near(abs(a) - 16 * R)
+                    if kind == 3: near(mp.sqrt(ix * ix + iy * iy) - R)
+                    cross = (abs(ix) < R and abs(iy) < 16 * R) or (abs(iy) < R and abs(ix) < 16 * R)
+                    crossT = (abs(tx) < R and abs(ty) < 16 * R) or (abs(ty) < R and abs(tx) < 16 * R)
+                    inside = {1: cross, 2: cross or crossT, 3: mp.sqrt(ix * ix + iy * iy) < R,
+                              4: abs(ix) < R and abs(iy) < R, 5: abs(tx) < R and abs(ty) < R}[kind]
+                    if inside:
+                        hit = False
+                        break
         else:
             near(rd - mpf("37.5"))
             hit = rd < mpf("37.5")
-        if not hit:
+        central = rd <= mpf("64.7") if xmm else rd < mpf("37.5")   # the arm test is the branch for rays outside the centre (rt:1689-1701)
+        if not hit and not central:
             for pt in (pEnt, pS):
                 r = rho(pt)
                 phi = mp.acos(pt[0] / r) / rad
